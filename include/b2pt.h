@@ -1,0 +1,224 @@
+/*
+ * b2pt.h — C-ABI of libb2pt: the B200-native wavefront path tracer that drops in under
+ * Mitsuba 2's scalar_rgb PathIntegrator / Scene hot path.
+ *
+ * Plain C: pointers + sizes only, no C++/torch types, no exceptions. Every entry point
+ * returns an int status (0 = ok); b2_last_error() gives the message for the calling thread.
+ * All file:line citations are relative to the reference tree (mitsuba2 @ 62863cb3).
+ *
+ * What each group of entry points replaces on the reference side:
+ *
+ *   b2_scene_create / b2_scene_destroy
+ *        Scene::accel_init_gpu / accel_release_gpu     include/mitsuba/render/scene.h:184-190
+ *        (+ the flattening of Mesh / BSDF / Emitter / Sensor / Film plugin state the
+ *         reference reads through virtual calls: mesh.h:344-361, scene.cpp:23-59)
+ *   b2_render / b2_render_device / b2_cancel
+ *        Integrator::render(Scene*, Sensor*) / cancel() include/mitsuba/render/integrator.h:42-51
+ *        = SamplingIntegrator::render + render_block + render_sample (src/librender/
+ *          integrator.cpp:51-288) + PathIntegrator::sample (src/integrators/path.cpp:100-211)
+ *   b2_stage_*           (device SoA queues; per-stage parity tests and ncu)
+ *        raygen    : render_sample + PerspectiveCamera::sample_ray_differential
+ *                    (integrator.cpp:233-262, src/sensors/perspective.cpp:182-216)
+ *        intersect : Scene::ray_intersect_preliminary_gpu   scene.h:196, scene_optix.inl:426
+ *        occluded  : Scene::ray_test_gpu                    scene.h:202, scene_optix.inl:554
+ *        si_fill   : Mesh::compute_surface_interaction      src/librender/mesh.cpp:449-545
+ *   b2_develop
+ *        HDRFilm::bitmap(): XYZAW -> linear sRGB, divide by W  src/films/hdrfilm.cpp:251-322
+ *   b2_host_*            (host-side C++ helpers that mirror reference host code)
+ *        perspective_projection / update_camera_transforms  include/mitsuba/render/sensor.h:196-232,
+ *                                                            src/sensors/perspective.cpp:119-139
+ *        Transform::look_at                                 include/mitsuba/core/transform.h:241-270
+ *        ReconstructionFilter::init_discretization          src/libcore/rfilter.cpp:9-20
+ *        Spiral::next_block order                           src/librender/spiral.cpp:27-72
+ */
+#ifndef B2PT_H
+#define B2PT_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_API __attribute__((visibility("default")))
+
+/* ---- status codes --------------------------------------------------------------------- */
+enum {
+    B2_OK = 0,
+    B2_ERR_INVALID = 1,     /* bad argument / unsupported scene feature (reference: Throw())  */
+    B2_ERR_CUDA = 2,        /* CUDA runtime failure                                           */
+    B2_ERR_CANCELLED = 3,   /* b2_cancel() observed (reference: render() returns false)       */
+    B2_ERR_NO_DEVICE = 4    /* no CUDA device: the product path has NO CPU fallback           */
+};
+
+/* ---- BSDF records (src/bsdfs/{diffuse,dielectric,roughconductor}.cpp) ------------------- */
+enum {
+    B2_BSDF_DIFFUSE = 0,        /* SmoothDiffuse      diffuse.cpp:78-135                      */
+    B2_BSDF_DIELECTRIC = 1,     /* SmoothDielectric   dielectric.cpp:201-320                  */
+    B2_BSDF_ROUGHCONDUCTOR = 2, /* RoughConductor     roughconductor.cpp:196-382              */
+    B2_BSDF_NULL = 3            /* reflectance-0 diffuse given to emitters without a BSDF     */
+};
+enum { B2_MF_BECKMANN = 0, B2_MF_GGX = 1 };   /* MicrofacetType, microfacet.h:27-33          */
+
+typedef struct B2Bsdf {
+    int32_t type;               /* B2_BSDF_*                                                   */
+    int32_t distribution;       /* B2_MF_* (roughconductor)                                    */
+    int32_t sample_visible;     /* roughconductor 'sample_visible' (default 1)                 */
+    int32_t _pad;
+    float reflectance[3];       /* diffuse 'reflectance' (constant rgb texture)                */
+    float eta;                  /* dielectric int_ior / ext_ior                                */
+    float specular_reflectance[3];    /* dielectric / roughconductor, default 1               */
+    float alpha_u;
+    float specular_transmittance[3];  /* dielectric, default 1                                */
+    float alpha_v;
+    float cond_eta[3];          /* roughconductor complex IOR, real part (default 0)           */
+    float _pad1;
+    float cond_k[3];            /* imaginary part (default 1)                                  */
+    float _pad2;
+} B2Bsdf;
+
+/* ---- emitters (src/emitters/{area,envmap,constant}.cpp) --------------------------------- */
+enum { B2_EMITTER_AREA = 0, B2_EMITTER_ENVMAP = 1, B2_EMITTER_CONSTANT = 2 };
+
+typedef struct B2Emitter {
+    int32_t type;               /* B2_EMITTER_*                                                */
+    int32_t mesh;               /* area: index of the mesh it is attached to                   */
+    float radiance[3];          /* area / constant: rgb radiance (srgb_d65 in rgb mode)        */
+    float scale;                /* envmap 'scale'                                              */
+    const float *envmap;        /* envmap: RGBA fp32 texels, (height x width x 4), row-major   */
+    int32_t env_width, env_height;
+    float env_to_world[16];     /* envmap to_world, row-major 4x4                              */
+} B2Emitter;
+
+/* ---- meshes (include/mitsuba/render/mesh.h:344-361) ------------------------------------- */
+typedef struct B2Mesh {
+    uint32_t n_vertices, n_faces;
+    const float *positions;     /* 3 fp32 / vertex, world space (obj.cpp:172)                  */
+    const float *normals;       /* 3 fp32 / vertex or NULL (face normals)                      */
+    const float *texcoords;     /* 2 fp32 / vertex or NULL                                     */
+    const uint32_t *faces;      /* 3 u32 / face                                                */
+    int32_t bsdf;               /* index into B2SceneDesc.bsdfs                                */
+    int32_t emitter;            /* index into B2SceneDesc.emitters or -1                       */
+} B2Mesh;
+
+/* one-level instancing (src/shapes/instance.cpp:107-164, src/librender/shapegroup.cpp) */
+typedef struct B2Instance {
+    int32_t group;              /* index of the shapegroup                                     */
+    float to_world[16];         /* row-major 4x4                                               */
+    float to_object[16];        /* its inverse, as the reference stores it                     */
+} B2Instance;
+
+/* ---- sensor + film (perspective.cpp, hdrfilm.cpp, rfilter.h) ---------------------------- */
+typedef struct B2Sensor {
+    float sample_to_camera[16]; /* row-major; m_sample_to_camera  perspective.cpp:124          */
+    float to_world[16];         /* row-major; m_world_transform                                */
+    float near_clip, far_clip;
+    float principal_point_offset[2];
+} B2Sensor;
+
+#define B2_FILTER_RESOLUTION 31  /* MTS_FILTER_RESOLUTION, include/mitsuba/core/rfilter.h:10   */
+
+typedef struct B2Film {
+    int32_t width, height;              /* film->size()                                        */
+    int32_t crop_offset[2], crop_size[2];
+    float filter_radius;                /* ReconstructionFilter::radius()                      */
+    float filter_scale;                 /* m_scale_factor = 31 / radius                        */
+    float filter_lut[B2_FILTER_RESOLUTION + 1];
+    int32_t border;                     /* border_size()                                       */
+} B2Film;
+
+typedef struct B2SceneDesc {
+    uint32_t n_meshes;   const B2Mesh *meshes;
+    uint32_t n_bsdfs;    const B2Bsdf *bsdfs;
+    uint32_t n_emitters; const B2Emitter *emitters;   /* scene.m_emitters order (scene.cpp:23-59) */
+    /* shapegroups: meshes [group_first[g], group_first[g+1]) belong to group g and are NOT
+       part of the top-level scene; n_groups == 0 for flat scenes. */
+    uint32_t n_groups;    const uint32_t *group_first;
+    uint32_t n_instances; const B2Instance *instances;
+    uint32_t n_top_meshes;              /* meshes [0, n_top_meshes) are top-level shapes       */
+    B2Sensor sensor;
+    B2Film film;
+} B2SceneDesc;
+
+/* ---- render parameters (integrator.cpp:23-40, sampler.cpp:20-30) ------------------------ */
+typedef struct B2RenderParams {
+    int32_t max_depth;          /* MonteCarloIntegrator 'max_depth' (-1 = infinite)            */
+    int32_t rr_depth;           /* 'rr_depth' (default 5)                                      */
+    uint32_t spp;               /* sampler 'sample_count'                                      */
+    uint32_t samples_per_pass;  /* integrator 'samples_per_pass' (0 = spp)                     */
+    uint32_t block_size;        /* integrator 'block_size' (power of two; MUST be pinned, it
+                                   feeds the per-pixel seed, integrator.cpp:198)               */
+    uint32_t lane_slots;        /* wavefront width (0 = auto)                                  */
+    uint64_t seed;              /* sampler 'seed' (m_base_seed)                                */
+    int32_t rank, world_size;   /* this process renders spiral blocks b with b % world == rank */
+} B2RenderParams;
+
+typedef struct B2Stats {
+    uint64_t n_samples;         /* camera samples put on the film                              */
+    uint64_t n_segments;        /* closest-hit rays traced (camera + bounce rays)              */
+    uint64_t n_shadow_rays;     /* any-hit rays traced                                         */
+    uint64_t n_invalid;         /* samples dropped by the ImageBlock::put validity rule        */
+    uint64_t n_iterations;      /* wavefront iterations                                        */
+    uint64_t n_launches;        /* kernels launched                                            */
+    float ms_total;             /* device time of the whole render (CUDA events)               */
+    float ms_regen, ms_intersect, ms_shade, ms_shadow;   /* per-stage device time              */
+    uint64_t bvh_nodes, bvh_tris;
+} B2Stats;
+
+typedef struct B2Scene B2Scene;     /* opaque */
+
+/* ---- lifecycle --------------------------------------------------------------------------- */
+B2_API int b2_scene_create(const B2SceneDesc *desc, B2Scene **out);
+B2_API int b2_scene_destroy(B2Scene *scene);
+B2_API const char *b2_last_error(void);
+B2_API int b2_device_count(void);
+
+/* ---- whole-path entry points ------------------------------------------------------------- */
+/* Renders into a HOST buffer xyzaw[crop_h * crop_w * 5] (channel order X,Y,Z,A,W,
+   integrator.cpp:71-72). Host<->device copies are inside the call. */
+B2_API int b2_render(B2Scene *scene, const B2RenderParams *params, float *xyzaw, B2Stats *stats);
+/* Same, but leaves the film in device memory (pointer returned, owned by the scene, valid
+   until the next render / destroy). For multi-GPU the caller reduces it (ncclReduce). */
+B2_API int b2_render_device(B2Scene *scene, const B2RenderParams *params, float **d_xyzaw,
+                            B2Stats *stats);
+B2_API int b2_cancel(B2Scene *scene);                     /* async-safe: sets a flag */
+/* HDRFilm::bitmap(): rgb[h*w*3] = M_xyz2rgb * xyz / W  (host in, host out, done on device) */
+B2_API int b2_develop(B2Scene *scene, const float *xyzaw, float *rgb);
+/* run stream for b2_render_device (cudaStream_t as void*); default = legacy stream */
+B2_API int b2_set_stream(B2Scene *scene, void *cuda_stream);
+
+/* ---- stage-level entry points (host arrays in/out; the kernels run on device queues) ----- */
+/* n lanes; (px,py) = integer pixel of each lane, seed_offset = value passed to Sampler::seed.
+   Outputs: ray_o[n*4] = (o.xyz, mint), ray_d[n*4] = (d.xyz, maxt), rng_state[n] after the
+   3 draws of render_sample (integrator.cpp:242,252), pos[n*2] = position_sample. */
+B2_API int b2_stage_raygen(B2Scene *scene, uint32_t n, const uint32_t *px, const uint32_t *py,
+                           const uint64_t *seed_offset, uint64_t base_seed,
+                           float *ray_o, float *ray_d, uint64_t *rng_state, float *pos);
+/* hit[n*4] = (t, u, v, prim-as-bits); t = +inf on miss; prim = global triangle index
+   (mesh order, then face order); inst[n] = instance index or -1 (may be NULL). */
+B2_API int b2_stage_intersect(B2Scene *scene, uint32_t n, const float *ray_o, const float *ray_d,
+                              float *hit, int32_t *inst);
+B2_API int b2_stage_occluded(B2Scene *scene, uint32_t n, const float *ray_o, const float *ray_d,
+                             uint8_t *occluded);
+/* si[n*16] = p3, n3, sh_n3, sh_s3, wi3, (bsdf index as bits) */
+B2_API int b2_stage_si_fill(B2Scene *scene, uint32_t n, const float *ray_o, const float *ray_d,
+                            const float *hit, const int32_t *inst, float *si);
+
+/* ---- host-side helpers (C++ mirrors of reference host code; no GPU needed) --------------- */
+B2_API int b2_host_look_at(const float origin[3], const float target[3], const float up[3],
+                           float to_world[16]);
+B2_API int b2_host_perspective_sensor(const float to_world[16], float fov_x_deg, float near_clip,
+                                      float far_clip, const B2Film *film, B2Sensor *out);
+/* fov given on another axis: 'fov_axis' = "x","y","smaller","larger","diagonal" (sensor.cpp parse_fov) */
+B2_API float b2_host_parse_fov(float fov_deg, const char *fov_axis, int width, int height);
+B2_API int b2_host_film_box(int width, int height, B2Film *out);                 /* box.cpp      */
+B2_API int b2_host_film_gaussian(int width, int height, float stddev, B2Film *out); /* gaussian.cpp */
+/* order[i] = (bx, by) of the i-th block handed out by Spiral::next_block */
+B2_API int b2_host_spiral(int width, int height, int block_size, uint32_t *n_blocks,
+                          int32_t *order_xy /* 2 * n_blocks or NULL to query n_blocks */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PT_H */

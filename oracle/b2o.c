@@ -1,0 +1,1253 @@
+/*
+ * b2o.c — TEST INFRASTRUCTURE: CPU oracle for the b2pt hot path.
+ *
+ * A plain-C restatement of the reference's scalar_rgb path tracer (mitsuba2 @ 62863cb3),
+ * written in the reference's own (depth-first, one path at a time) shape — NOT in the
+ * wavefront shape of the CUDA product — so that a bit-for-bit match of the two is evidence
+ * that the wavefront stages compute what the reference computes. Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library; the product (mitsuba2_b200/) never does.
+ *
+ * Pinned against the reference by tests/golden/ (images rendered with the unmodified
+ * reference CLI built by oracle/build_ref.sh, identical sampler seeds) and by the
+ * known-answer values transcribed from the reference's own tests (see tests/test_oracle_*.py).
+ *
+ * Every function cites the reference file:line it follows (paths relative to the reference).
+ * Float operation order is fixed (see b2o_math.h); compile with -ffp-contract=off.
+ */
+#include "../include/b2pt.h"
+#include "b2o_math.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <pthread.h>
+
+#define B2O_API __attribute__((visibility("default")))
+
+/* ============================================================================================
+ * PCG32  —  ext/enoki/include/enoki/random.h:62-119, src/librender/sampler.cpp:83-96
+ * ============================================================================================ */
+#define PCG32_DEFAULT_STREAM 0xda3e39cb94b95bdbULL
+#define PCG32_MULT           0x5851f42d4c957f2dULL
+
+typedef struct { uint64_t state, inc; } pcg32;
+
+static inline uint32_t pcg32_next_uint32(pcg32 *r) {            /* random.h:71-77 */
+    uint64_t oldstate = r->state;
+    r->state = oldstate * PCG32_MULT + r->inc;
+    uint32_t xorshifted = (uint32_t) (((oldstate >> 18u) ^ oldstate) >> 27u);
+    uint32_t rot = (uint32_t) (oldstate >> 59u);
+    return (xorshifted >> rot) | (xorshifted << ((-rot) & 31));
+}
+static inline void pcg32_seed(pcg32 *r, uint64_t initstate, uint64_t initseq) { /* random.h:62-68 */
+    r->state = 0u;
+    r->inc = (initseq << 1u) | 1u;
+    pcg32_next_uint32(r);
+    r->state += initstate;
+    pcg32_next_uint32(r);
+}
+static inline float pcg32_next_float(pcg32 *r) {                 /* random.h:117-119 */
+    return b2o_u2f((pcg32_next_uint32(r) >> 9) | 0x3f800000u) - 1.0f;
+}
+/* PCG32Sampler::seed(seed_offset): m_rng.seed(m_base_seed + seed_offset, PCG32_DEFAULT_STREAM)
+   (sampler.cpp:83-96, scalar branch) */
+static inline void sampler_seed(pcg32 *r, uint64_t base_seed, uint64_t seed_offset) {
+    pcg32_seed(r, base_seed + seed_offset, PCG32_DEFAULT_STREAM);
+}
+
+B2O_API void b2o_pcg32_seed(uint64_t base_seed, uint64_t seed_offset, uint64_t *state_inc) {
+    pcg32 r; sampler_seed(&r, base_seed, seed_offset);
+    state_inc[0] = r.state; state_inc[1] = r.inc;
+}
+B2O_API float b2o_pcg32_next_float(uint64_t *state_inc) {
+    pcg32 r = { state_inc[0], state_inc[1] };
+    float f = pcg32_next_float(&r);
+    state_inc[0] = r.state;
+    return f;
+}
+B2O_API uint32_t b2o_pcg32_next_uint32(uint64_t *state_inc) {
+    pcg32 r = { state_inc[0], state_inc[1] };
+    uint32_t u = pcg32_next_uint32(&r);
+    state_inc[0] = r.state;
+    return u;
+}
+
+/* ============================================================================================
+ * Host-side scene setup mirrors
+ * ============================================================================================ */
+/* 4x4 matrices are row-major float[16] at the ABI; Enoki's are column-major. m(r,c) = a[4*r+c] */
+typedef struct { float a[16]; } m44;
+static m44 m44_identity(void) { m44 m; memset(&m, 0, sizeof m); m.a[0] = m.a[5] = m.a[10] = m.a[15] = 1.f; return m; }
+/* ext/enoki/include/enoki/matrix.h:154-167: column j of the result = m0.col(0)*m1(0,j), then
+   fmadd over i = 1..3 */
+static m44 m44_mul(const m44 *A, const m44 *B) {
+    m44 R;
+    for (int j = 0; j < 4; ++j)
+        for (int r = 0; r < 4; ++r) {
+            float sum = A->a[4 * r + 0] * B->a[4 * 0 + j];
+            for (int i = 1; i < 4; ++i)
+                sum = b2o_fma(A->a[4 * r + i], B->a[4 * i + j], sum);
+            R.a[4 * r + j] = sum;
+        }
+    return R;
+}
+static m44 m44_transpose(const m44 *A) {
+    m44 R;
+    for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) R.a[4 * r + c] = A->a[4 * c + r];
+    return R;
+}
+typedef struct { m44 m, inv_t; } xform;   /* Transform: matrix + inverse_transpose (transform.h:29-33) */
+static xform xf_mul(const xform *a, const xform *b) {   /* transform.h:46-49 */
+    xform r; r.m = m44_mul(&a->m, &b->m); r.inv_t = m44_mul(&a->inv_t, &b->inv_t); return r;
+}
+static xform xf_scale(float x, float y, float z) {      /* transform.h:167-171 */
+    xform r; r.m = m44_identity(); r.inv_t = m44_identity();
+    r.m.a[0] = x; r.m.a[5] = y; r.m.a[10] = z;
+    r.inv_t.a[0] = b2o_rcp(x); r.inv_t.a[5] = b2o_rcp(y); r.inv_t.a[10] = b2o_rcp(z);
+    return r;
+}
+static xform xf_translate(float x, float y, float z) {  /* transform.h:161-164 */
+    xform r; r.m = m44_identity();
+    r.m.a[3] = x; r.m.a[7] = y; r.m.a[11] = z;
+    m44 inv = m44_identity(); inv.a[3] = -x; inv.a[7] = -y; inv.a[11] = -z;
+    r.inv_t = m44_transpose(&inv);
+    return r;
+}
+static xform xf_perspective(float fov, float near_, float far_) {  /* transform.h:203-220 */
+    float recip = 1.f / (far_ - near_);
+    /* deg_to_rad(fov * .5f) = value * (Pi / 180) (include/mitsuba/core/math.h) ; enoki::tan -> tanf */
+    float tn = tanf((fov * .5f) * (B2O_PI / 180.f));
+    float cot = 1.f / tn;
+    xform r; memset(&r, 0, sizeof r);
+    r.m.a[0] = cot; r.m.a[5] = cot; r.m.a[10] = far_ * recip; r.m.a[15] = 0.f;
+    r.m.a[4 * 2 + 3] = -near_ * far_ * recip;
+    r.m.a[4 * 3 + 2] = 1.f;
+    m44 inv; memset(&inv, 0, sizeof inv);
+    inv.a[0] = tn; inv.a[5] = tn; inv.a[10] = 0.f; inv.a[15] = b2o_rcp(near_);
+    inv.a[4 * 2 + 3] = 1.f;
+    inv.a[4 * 3 + 2] = (near_ - far_) / (far_ * near_);
+    r.inv_t = m44_transpose(&inv);
+    return r;
+}
+
+/* Transform::look_at — include/mitsuba/core/transform.h:241-270 */
+B2O_API int b2o_look_at(const float o[3], const float tg[3], const float up_[3], float out[16]) {
+    v3 origin = v3_make(o[0], o[1], o[2]), target = v3_make(tg[0], tg[1], tg[2]), up = v3_make(up_[0], up_[1], up_[2]);
+    v3 dir = v3_normalize(v3_sub(target, origin));
+    dir = v3_normalize(dir);
+    v3 left = v3_normalize(v3_cross(up, dir));
+    v3 new_up = v3_cross(dir, left);
+    float m[16] = { left.x, new_up.x, dir.x, origin.x,
+                    left.y, new_up.y, dir.y, origin.y,
+                    left.z, new_up.z, dir.z, origin.z,
+                    0.f, 0.f, 0.f, 1.f };
+    memcpy(out, m, sizeof m);
+    return 0;
+}
+
+/* parse_fov — src/librender/sensor.cpp (fov_axis handling); float arithmetic as there */
+B2O_API float b2o_parse_fov(float fov, const char *axis, int width, int height) {
+    float aspect = (float) width / (float) height;
+    int mode; /* 0 = x, 1 = y, 2 = diagonal */
+    if (!strcmp(axis, "x")) mode = 0;
+    else if (!strcmp(axis, "y")) mode = 1;
+    else if (!strcmp(axis, "diagonal")) mode = 2;
+    else if (!strcmp(axis, "smaller")) mode = aspect > 1.f ? 1 : 0;
+    else if (!strcmp(axis, "larger")) mode = aspect > 1.f ? 0 : 1;
+    else return -1.f;
+    if (mode == 0) return fov;
+    if (mode == 1)
+        return (180.f / B2O_PI) * (2.f * atanf(tanf(.5f * (fov * (B2O_PI / 180.f))) * aspect));
+    float diagonal = 2.f * tanf(.5f * (fov * (B2O_PI / 180.f)));
+    float w = diagonal / sqrtf(1.f + 1.f / (aspect * aspect));
+    return (180.f / B2O_PI) * (2.f * atanf(w * .5f));
+}
+
+/* perspective_projection + update_camera_transforms —
+   include/mitsuba/render/sensor.h:196-232, src/sensors/perspective.cpp:119-139 */
+B2O_API int b2o_perspective_sensor(const float to_world[16], float fov_x, float near_clip, float far_clip,
+                                   const B2Film *film, B2Sensor *out) {
+    float fw = (float) film->width, fh = (float) film->height;
+    float rel_size_x = (float) film->crop_size[0] / fw, rel_size_y = (float) film->crop_size[1] / fh;
+    float rel_off_x = (float) film->crop_offset[0] / fw, rel_off_y = (float) film->crop_offset[1] / fh;
+    float aspect = fw / fh;
+    xform s1 = xf_scale(1.f / rel_size_x, 1.f / rel_size_y, 1.f);
+    xform t1 = xf_translate(-rel_off_x, -rel_off_y, 0.f);
+    xform s2 = xf_scale(-0.5f, -0.5f * aspect, 1.f);
+    xform t2 = xf_translate(-1.f, -1.f / aspect, 0.f);
+    xform p = xf_perspective(fov_x, near_clip, far_clip);
+    xform c2s = xf_mul(&s1, &t1);
+    c2s = xf_mul(&c2s, &s2);
+    c2s = xf_mul(&c2s, &t2);
+    c2s = xf_mul(&c2s, &p);
+    /* inverse(): matrix = transpose(inverse_transpose) (transform.h:59-61) */
+    m44 s2c = m44_transpose(&c2s.inv_t);
+    memcpy(out->sample_to_camera, s2c.a, sizeof s2c.a);
+    memcpy(out->to_world, to_world, 16 * sizeof(float));
+    out->near_clip = near_clip; out->far_clip = far_clip;
+    out->principal_point_offset[0] = 0.f; out->principal_point_offset[1] = 0.f;
+    return 0;
+}
+
+/* ReconstructionFilter::init_discretization — src/libcore/rfilter.cpp:9-20 */
+static void film_init_filter(B2Film *f, float radius, float (*eval)(float, const float *), const float *p) {
+    f->filter_radius = radius;
+    for (int i = 0; i < B2_FILTER_RESOLUTION; ++i)
+        f->filter_lut[i] = eval((radius * (float) i) / (float) B2_FILTER_RESOLUTION, p);
+    f->filter_lut[B2_FILTER_RESOLUTION] = 0.f;
+    f->filter_scale = (float) B2_FILTER_RESOLUTION / radius;
+    f->border = (int) ceilf(radius - .5f - 2.f * B2O_RAY_EPS);
+}
+static float box_eval(float x, const float *p) { return fabsf(x) <= p[0] ? 1.f : 0.f; }        /* box.cpp:31-33 */
+static float gauss_eval(float x, const float *p) {                                               /* gaussian.cpp:45-47 */
+    return b2o_max(0.f, expf(p[0] * (x * x)) - p[1]);
+}
+static void film_dims(B2Film *f, int w, int h) {
+    memset(f, 0, sizeof *f);
+    f->width = w; f->height = h; f->crop_offset[0] = f->crop_offset[1] = 0; f->crop_size[0] = w; f->crop_size[1] = h;
+}
+B2O_API int b2o_film_box(int w, int h, B2Film *f) {            /* src/rfilters/box.cpp:24-29 */
+    film_dims(f, w, h);
+    float radius = .5f + B2O_RAY_EPS;
+    film_init_filter(f, radius, box_eval, &radius);
+    return 0;
+}
+B2O_API int b2o_film_gaussian(int w, int h, float stddev, B2Film *f) {   /* src/rfilters/gaussian.cpp:32-43 */
+    film_dims(f, w, h);
+    float radius = 4 * stddev;
+    float p[2];
+    p[0] = -1.f / (2.f * stddev * stddev);
+    p[1] = expf(p[0] * (radius * radius));
+    film_init_filter(f, radius, gauss_eval, p);
+    return 0;
+}
+
+/* Spiral — src/librender/spiral.cpp:8-72. order_xy[2*i] = block position of the i-th block. */
+B2O_API int b2o_spiral(int width, int height, int bs, uint32_t *n_blocks, int32_t *order_xy) {
+    int bx = (int) ceilf((float) width / (float) bs), by = (int) ceilf((float) height / (float) bs);
+    uint32_t count = (uint32_t) (bx * by);
+    *n_blocks = count;
+    if (!order_xy) return 0;
+    int px = bx / 2, py = by / 2, dir = 0 /* Right, Down, Left, Up */, steps_left = 1, steps = 1;
+    for (uint32_t counter = 0; counter < count;) {
+        order_xy[2 * counter] = px; order_xy[2 * counter + 1] = py;
+        ++counter;
+        if (counter != count) {
+            do {
+                switch (dir) {
+                    case 0: ++px; break;
+                    case 1: ++py; break;
+                    case 2: --px; break;
+                    case 3: --py; break;
+                }
+                if (--steps_left == 0) {
+                    dir = (dir + 1) % 4;
+                    if (dir == 2 || dir == 0) ++steps;
+                    steps_left = steps;
+                }
+            } while (px < 0 || py < 0 || px >= bx || py >= by);
+        }
+    }
+    return 0;
+}
+
+/* ============================================================================================
+ * Scene: flattened triangles + a plain BVH2 (median split) used ONLY for speed. Results are
+ * independent of the acceleration structure: closest hit = lexicographic min of (t, prim)
+ * over all triangles whose Moeller-Trumbore test passes (see DESIGN.md "tie rule").
+ * ============================================================================================ */
+typedef struct {
+    v3 p0, p1, p2;
+    v3 n0, n1, n2;
+    int has_normals;
+    int mesh;
+} otri;
+
+typedef struct { float lo[3], hi[3]; int left, right, first, count; } onode;
+
+typedef struct {
+    const B2SceneDesc *desc;
+    uint32_t n_tris;
+    otri *tris;
+    uint32_t *order;      /* BVH leaf order -> prim */
+    onode *nodes; int n_nodes;
+    /* per-mesh area distribution (mesh.cpp:285-312, distr_1d.h:49-90) */
+    float **cdf; float *cdf_sum, *cdf_norm; uint32_t *mesh_first;
+} oscene;
+
+static void tri_bounds(const otri *t, float lo[3], float hi[3]) {
+    const v3 *p[3] = { &t->p0, &t->p1, &t->p2 };
+    lo[0] = lo[1] = lo[2] = INFINITY; hi[0] = hi[1] = hi[2] = -INFINITY;
+    for (int i = 0; i < 3; ++i) {
+        float c[3] = { p[i]->x, p[i]->y, p[i]->z };
+        for (int k = 0; k < 3; ++k) { if (c[k] < lo[k]) lo[k] = c[k]; if (c[k] > hi[k]) hi[k] = c[k]; }
+    }
+}
+static int g_axis; static const otri *g_tris;
+static int cmp_centroid(const void *a, const void *b) {
+    const otri *ta = &g_tris[*(const uint32_t *) a], *tb = &g_tris[*(const uint32_t *) b];
+    float la[3], ha[3], lb[3], hb[3];
+    tri_bounds(ta, la, ha); tri_bounds(tb, lb, hb);
+    float ca = la[g_axis] + ha[g_axis], cb = lb[g_axis] + hb[g_axis];
+    return (ca > cb) - (ca < cb);
+}
+static int build_node(oscene *s, int first, int count) {
+    int id = s->n_nodes++;
+    onode *n = &s->nodes[id];
+    for (int k = 0; k < 3; ++k) { n->lo[k] = INFINITY; n->hi[k] = -INFINITY; }
+    for (int i = first; i < first + count; ++i) {
+        float lo[3], hi[3]; tri_bounds(&s->tris[s->order[i]], lo, hi);
+        for (int k = 0; k < 3; ++k) { if (lo[k] < n->lo[k]) n->lo[k] = lo[k]; if (hi[k] > n->hi[k]) n->hi[k] = hi[k]; }
+    }
+    n->first = first; n->count = count; n->left = n->right = -1;
+    if (count > 4) {
+        int ax = 0; float ext = n->hi[0] - n->lo[0];
+        for (int k = 1; k < 3; ++k) if (n->hi[k] - n->lo[k] > ext) { ext = n->hi[k] - n->lo[k]; ax = k; }
+        g_axis = ax; g_tris = s->tris;
+        qsort(s->order + first, (size_t) count, sizeof(uint32_t), cmp_centroid);
+        int half = count / 2;
+        int l = build_node(s, first, half);
+        int r = build_node(s, first + half, count - half);
+        n = &s->nodes[id];
+        n->left = l; n->right = r; n->count = 0;
+    }
+    return id;
+}
+
+static void mesh_vertex(const B2Mesh *m, const float *buf, uint32_t i, v3 *out) {
+    out->x = buf[3 * i]; out->y = buf[3 * i + 1]; out->z = buf[3 * i + 2]; (void) m;
+}
+
+static oscene *oscene_create(const B2SceneDesc *d) {
+    oscene *s = (oscene *) calloc(1, sizeof *s);
+    s->desc = d;
+    uint32_t nt = 0;
+    s->mesh_first = (uint32_t *) calloc(d->n_meshes + 1, sizeof(uint32_t));
+    for (uint32_t m = 0; m < d->n_meshes; ++m) { s->mesh_first[m] = nt; nt += d->meshes[m].n_faces; }
+    s->mesh_first[d->n_meshes] = nt;
+    s->n_tris = nt;
+    s->tris = (otri *) calloc(nt ? nt : 1, sizeof(otri));
+    s->order = (uint32_t *) calloc(nt ? nt : 1, sizeof(uint32_t));
+    s->cdf = (float **) calloc(d->n_meshes, sizeof(float *));
+    s->cdf_sum = (float *) calloc(d->n_meshes, sizeof(float));
+    s->cdf_norm = (float *) calloc(d->n_meshes, sizeof(float));
+    for (uint32_t m = 0; m < d->n_meshes; ++m) {
+        const B2Mesh *me = &d->meshes[m];
+        for (uint32_t f = 0; f < me->n_faces; ++f) {
+            otri *t = &s->tris[s->mesh_first[m] + f];
+            uint32_t i0 = me->faces[3 * f], i1 = me->faces[3 * f + 1], i2 = me->faces[3 * f + 2];
+            mesh_vertex(me, me->positions, i0, &t->p0);
+            mesh_vertex(me, me->positions, i1, &t->p1);
+            mesh_vertex(me, me->positions, i2, &t->p2);
+            t->has_normals = me->normals != NULL;
+            if (me->normals) {
+                mesh_vertex(me, me->normals, i0, &t->n0);
+                mesh_vertex(me, me->normals, i1, &t->n1);
+                mesh_vertex(me, me->normals, i2, &t->n2);
+            }
+            t->mesh = (int) m;
+        }
+        /* area pmf + cdf only needed for emitter meshes: Mesh::build_pmf mesh.cpp:285-312,
+           face_area mesh.h:108-116, DiscreteDistribution::update distr_1d.h:49-90 */
+        if (me->emitter >= 0) {
+            s->cdf[m] = (float *) calloc(me->n_faces, sizeof(float));
+            double sum = 0.0;
+            for (uint32_t f = 0; f < me->n_faces; ++f) {
+                const otri *t = &s->tris[s->mesh_first[m] + f];
+                v3 c = v3_cross(v3_sub(t->p1, t->p0), v3_sub(t->p2, t->p0));
+                float area = 0.5f * sqrtf(v3_dot(c, c));
+                sum += (double) area;
+                s->cdf[m][f] = (float) sum;
+            }
+            s->cdf_sum[m] = (float) sum;
+            s->cdf_norm[m] = (float) (1.0 / sum);
+        }
+    }
+    for (uint32_t i = 0; i < nt; ++i) s->order[i] = i;
+    s->nodes = (onode *) calloc(2 * (nt ? nt : 1) + 1, sizeof(onode));
+    s->n_nodes = 0;
+    if (nt) build_node(s, 0, (int) nt);
+    return s;
+}
+static void oscene_destroy(oscene *s) {
+    if (!s) return;
+    for (uint32_t m = 0; m < s->desc->n_meshes; ++m) free(s->cdf[m]);
+    free(s->cdf); free(s->cdf_sum); free(s->cdf_norm); free(s->mesh_first);
+    free(s->tris); free(s->order); free(s->nodes); free(s);
+}
+
+typedef struct { v3 o, d; float mint, maxt; } oray;
+typedef struct { float t, u, v; uint32_t prim; } ohit;   /* t = +inf: miss */
+
+/* Mesh::ray_intersect_triangle — include/mitsuba/render/mesh.h:194-226 */
+static inline int tri_intersect(const otri *tr, const oray *ray, float *t_out, float *u_out, float *v_out) {
+    v3 e1 = v3_sub(tr->p1, tr->p0), e2 = v3_sub(tr->p2, tr->p0);
+    v3 pvec = v3_cross(ray->d, e2);
+    float inv_det = b2o_rcp(v3_dot(e1, pvec));
+    v3 tvec = v3_sub(ray->o, tr->p0);
+    float u = v3_dot(tvec, pvec) * inv_det;
+    int active = u >= 0.f && u <= 1.f;
+    v3 qvec = v3_cross(tvec, e1);
+    float v = v3_dot(ray->d, qvec) * inv_det;
+    active &= v >= 0.f && u + v <= 1.f;
+    float t = v3_dot(e2, qvec) * inv_det;
+    active &= t >= ray->mint && t <= ray->maxt;
+    *t_out = t; *u_out = u; *v_out = v;
+    return active;
+}
+
+static inline int box_hit(const onode *n, const oray *r, float tmax) {
+    /* conservative slab test in double (never culls a box the fp32 triangle test could hit) */
+    double t0 = (double) r->mint, t1 = (double) tmax;
+    const float o[3] = { r->o.x, r->o.y, r->o.z }, d[3] = { r->d.x, r->d.y, r->d.z };
+    for (int k = 0; k < 3; ++k) {
+        if (d[k] == 0.f) { if (o[k] < n->lo[k] - 1e-3f || o[k] > n->hi[k] + 1e-3f) return 0; continue; }
+        double inv = 1.0 / (double) d[k];
+        double a = ((double) n->lo[k] - o[k]) * inv, b = ((double) n->hi[k] - o[k]) * inv;
+        if (a > b) { double tmp = a; a = b; b = tmp; }
+        a -= 1e-4 * (fabs(a) + 1.0); b += 1e-4 * (fabs(b) + 1.0);
+        if (a > t0) t0 = a;
+        if (b < t1) t1 = b;
+        if (t0 > t1) return 0;
+    }
+    return 1;
+}
+
+/* Scene::ray_intersect_preliminary (scene.cpp:131-137) with the order-independent tie rule */
+static ohit scene_intersect(const oscene *s, const oray *ray, int brute) {
+    ohit best; best.t = INFINITY; best.u = best.v = 0.f; best.prim = 0xffffffffu;
+    if (!s->n_tris) return best;
+    if (brute) {
+        for (uint32_t i = 0; i < s->n_tris; ++i) {
+            float t, u, v;
+            if (tri_intersect(&s->tris[i], ray, &t, &u, &v) && (t < best.t || (t == best.t && (best.prim == 0xffffffffu || i > best.prim)))) {
+                best.t = t; best.u = u; best.v = v; best.prim = i;
+            }
+        }
+        return best;
+    }
+    int stack[128], sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const onode *n = &s->nodes[stack[--sp]];
+        if (!box_hit(n, ray, best.t < ray->maxt ? best.t : ray->maxt)) continue;
+        if (n->left < 0) {
+            for (int i = n->first; i < n->first + n->count; ++i) {
+                uint32_t prim = s->order[i];
+                float t, u, v;
+                if (tri_intersect(&s->tris[prim], ray, &t, &u, &v) && (t < best.t || (t == best.t && (best.prim == 0xffffffffu || prim > best.prim)))) {
+                    best.t = t; best.u = u; best.v = v; best.prim = prim;
+                }
+            }
+        } else { stack[sp++] = n->left; stack[sp++] = n->right; }
+    }
+    return best;
+}
+/* Scene::ray_test (scene.cpp:154-162) */
+static int scene_occluded(const oscene *s, const oray *ray, int brute) {
+    if (!s->n_tris) return 0;
+    float t, u, v;
+    if (brute) {
+        for (uint32_t i = 0; i < s->n_tris; ++i) if (tri_intersect(&s->tris[i], ray, &t, &u, &v)) return 1;
+        return 0;
+    }
+    int stack[128], sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const onode *n = &s->nodes[stack[--sp]];
+        if (!box_hit(n, ray, ray->maxt)) continue;
+        if (n->left < 0) {
+            for (int i = n->first; i < n->first + n->count; ++i)
+                if (tri_intersect(&s->tris[s->order[i]], ray, &t, &u, &v)) return 1;
+        } else { stack[sp++] = n->left; stack[sp++] = n->right; }
+    }
+    return 0;
+}
+
+/* ============================================================================================
+ * SurfaceInteraction — mesh.cpp:449-545, interaction.h:153-156,571-596, vector.h:116-136
+ * ============================================================================================ */
+typedef struct {
+    float t; v3 p, n, sh_n, sh_s, sh_t, wi;
+    uint32_t prim; int mesh;
+} osi;
+
+static inline void coordinate_system_s(v3 n, v3 *s) {   /* vector.h:116-136 (first vector only) */
+    float sign = b2o_sign(n.z);
+    float a = -b2o_rcp(sign + n.z);
+    float b = (n.x * n.y) * a;
+    s->x = b2o_mulsign(b2o_sqr(n.x) * a, n.z) + 1.f;
+    s->y = b2o_mulsign(b, n.z);
+    s->z = b2o_mulsign_neg(n.x, n.z);
+}
+static inline void coordinate_system(v3 n, v3 *s, v3 *t) {
+    float sign = b2o_sign(n.z);
+    float a = -b2o_rcp(sign + n.z);
+    float b = (n.x * n.y) * a;
+    coordinate_system_s(n, s);
+    t->x = b; t->y = sign + b2o_sqr(n.y) * a; t->z = -n.y;
+}
+static inline v3 to_local(const osi *si, v3 v) { return v3_make(v3_dot(v, si->sh_s), v3_dot(v, si->sh_t), v3_dot(v, si->sh_n)); }
+static inline v3 to_world(const osi *si, v3 v) {   /* frame.h:35-37: s*v.x + t*v.y + n*v.z */
+    return v3_add(v3_add(v3_scale(si->sh_s, v.x), v3_scale(si->sh_t, v.y)), v3_scale(si->sh_n, v.z));
+}
+
+static void si_fill(const oscene *s, const oray *ray, const ohit *h, osi *si) {
+    memset(si, 0, sizeof *si);
+    si->t = h->t; si->prim = h->prim; si->mesh = -1;
+    if (!(h->t < INFINITY)) { si->wi = v3_neg(ray->d); return; }   /* interaction.h:591 */
+    const otri *tr = &s->tris[h->prim];
+    si->mesh = tr->mesh;
+    float b1 = h->u, b2 = h->v, b0 = 1.f - b1 - b2;
+    v3 dp0 = v3_sub(tr->p1, tr->p0), dp1 = v3_sub(tr->p2, tr->p0);
+    si->p = v3_add(v3_add(v3_scale(tr->p0, b0), v3_scale(tr->p1, b1)), v3_scale(tr->p2, b2));  /* mesh.cpp:484 */
+    si->n = v3_normalize(v3_cross(dp0, dp1));                                                   /* mesh.cpp:487 */
+    v3 dp_du; coordinate_system_s(si->n, &dp_du);                                               /* mesh.cpp:491 */
+    if (tr->has_normals)                                                                         /* mesh.cpp:514-519 */
+        si->sh_n = v3_normalize(v3_add(v3_add(v3_scale(tr->n0, b0), v3_scale(tr->n1, b1)), v3_scale(tr->n2, b2)));
+    else
+        si->sh_n = si->n;
+    /* initialize_sh_frame interaction.h:153-156 */
+    si->sh_s = v3_normalize(v3_fnmadd(si->sh_n, v3_dot(si->sh_n, dp_du), dp_du));
+    si->sh_t = v3_cross(si->sh_n, si->sh_s);
+    si->wi = to_local(si, v3_neg(ray->d));                                                       /* interaction.h:591 */
+}
+
+/* ============================================================================================
+ * Warps — include/mitsuba/core/warp.h
+ * ============================================================================================ */
+static inline void square_to_uniform_disk_concentric(float sx, float sy, float *ox, float *oy) { /* warp.h:53-90 */
+    float x = b2o_fma(2.f, sx, -1.f), y = b2o_fma(2.f, sy, -1.f);
+    int is_zero = x == 0.f && y == 0.f, q13 = fabsf(x) < fabsf(y);
+    float r = q13 ? y : x, rp = q13 ? x : y;
+    float phi = ((.25f * B2O_PI) * rp) / r;
+    if (q13) phi = .5f * B2O_PI - phi;
+    if (is_zero) phi = 0.f;
+    float s, c; b2o_sincos(phi, &s, &c);
+    *ox = r * c; *oy = r * s;
+}
+static inline v3 square_to_cosine_hemisphere(float sx, float sy) {   /* warp.h:325-333 */
+    float px, py; square_to_uniform_disk_concentric(sx, sy, &px, &py);
+    float z = b2o_safe_sqrt(1.f - (px * px + py * py));
+    return v3_make(px, py, z);
+}
+
+/* ============================================================================================
+ * Fresnel + microfacet — include/mitsuba/render/fresnel.h, microfacet.h
+ * ============================================================================================ */
+static inline void fresnel(float cos_theta_i, float eta, float *r_out, float *cos_theta_t_out,
+                           float *eta_it_out, float *eta_ti_out) {       /* fresnel.h:34-70 */
+    int outside = cos_theta_i >= 0.f;
+    float rcp_eta = b2o_rcp(eta), eta_it = outside ? eta : rcp_eta, eta_ti = outside ? rcp_eta : eta;
+    float cos_theta_t_sqr = b2o_fma(-b2o_fma(-cos_theta_i, cos_theta_i, 1.f), eta_ti * eta_ti, 1.f);
+    float cos_theta_i_abs = fabsf(cos_theta_i);
+    float cos_theta_t_abs = b2o_safe_sqrt(cos_theta_t_sqr);
+    int index_matched = eta == 1.f, special_case = index_matched || cos_theta_i_abs == 0.f;
+    float r_sc = index_matched ? 0.f : 1.f;
+    float a_s = b2o_fma(-eta_it, cos_theta_t_abs, cos_theta_i_abs) / b2o_fma(eta_it, cos_theta_t_abs, cos_theta_i_abs);
+    float a_p = b2o_fma(-eta_it, cos_theta_i_abs, cos_theta_t_abs) / b2o_fma(eta_it, cos_theta_i_abs, cos_theta_t_abs);
+    float r = .5f * (b2o_sqr(a_s) + b2o_sqr(a_p));
+    if (special_case) r = r_sc;
+    *r_out = r; *cos_theta_t_out = b2o_mulsign_neg(cos_theta_t_abs, cos_theta_i);
+    *eta_it_out = eta_it; *eta_ti_out = eta_ti;
+}
+static inline float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {   /* fresnel.h:92-116 */
+    float cos_theta_i_2 = cos_theta_i * cos_theta_i, sin_theta_i_2 = 1.f - cos_theta_i_2,
+          sin_theta_i_4 = sin_theta_i_2 * sin_theta_i_2;
+    float temp_1 = eta_r * eta_r - eta_i * eta_i - sin_theta_i_2,
+          a_2_pb_2 = b2o_safe_sqrt(temp_1 * temp_1 + 4.f * eta_i * eta_i * eta_r * eta_r),
+          a = b2o_safe_sqrt(.5f * (a_2_pb_2 + temp_1));
+    float term_1 = a_2_pb_2 + cos_theta_i_2, term_2 = 2.f * cos_theta_i * a;
+    float r_s = (term_1 - term_2) / (term_1 + term_2);
+    float term_3 = a_2_pb_2 * cos_theta_i_2 + sin_theta_i_4, term_4 = term_2 * sin_theta_i_2;
+    float r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return .5f * (r_s + r_p);
+}
+
+typedef struct { int type; float au, av; int sample_visible; } omf;
+static inline omf mf_make(const B2Bsdf *b) {     /* microfacet.h configure(): alpha = max(alpha, 1e-4) */
+    omf m; m.type = b->distribution; m.au = b2o_max(b->alpha_u, 1e-4f); m.av = b2o_max(b->alpha_v, 1e-4f);
+    m.sample_visible = b->sample_visible; return m;
+}
+static inline float mf_eval(const omf *d, v3 m) {   /* microfacet.h:184-203 */
+    float alpha_uv = d->au * d->av, cos_theta = m.z, cos_theta_2 = b2o_sqr(cos_theta), result;
+    if (d->type == B2_MF_BECKMANN)
+        result = b2o_exp(-(b2o_sqr(m.x / d->au) + b2o_sqr(m.y / d->av)) / cos_theta_2) /
+                 (B2O_PI * alpha_uv * b2o_sqr(cos_theta_2));
+    else
+        result = b2o_rcp(B2O_PI * alpha_uv * b2o_sqr(b2o_sqr(m.x / d->au) + b2o_sqr(m.y / d->av) + b2o_sqr(m.z)));
+    return result * cos_theta > 1e-20f ? result : 0.f;
+}
+static inline float mf_smith_g1(const omf *d, v3 v, v3 m) {    /* microfacet.h:331-355 */
+    float xy_alpha_2 = b2o_sqr(d->au * v.x) + b2o_sqr(d->av * v.y),
+          tan_theta_alpha_2 = xy_alpha_2 / b2o_sqr(v.z), result;
+    if (d->type == B2_MF_BECKMANN) {
+        float a = b2o_rsqrt(tan_theta_alpha_2), a_sqr = b2o_sqr(a);
+        result = a >= 1.6f ? 1.f : (3.535f * a + 2.181f * a_sqr) / (1.f + 2.276f * a + 2.577f * a_sqr);
+    } else
+        result = 2.f / (1.f + sqrtf(1.f + tan_theta_alpha_2));
+    if (xy_alpha_2 == 0.f) result = 1.f;
+    if (v3_dot(v, m) * v.z <= 0.f) result = 0.f;
+    return result;
+}
+static inline void mf_sample_visible_11(const omf *d, float cos_theta_i, float sx, float sy, float *ox, float *oy) {
+    if (d->type == B2_MF_BECKMANN) {                                    /* microfacet.h:359-394 */
+        float tan_theta_i = b2o_safe_sqrt(b2o_fma(-cos_theta_i, cos_theta_i, 1.f)) / cos_theta_i;
+        float cot_theta_i = b2o_rcp(tan_theta_i);
+        float maxval = b2o_erf(cot_theta_i);
+        sx = b2o_max(b2o_min(sx, 1.f - 1e-6f), 1e-6f);
+        sy = b2o_max(b2o_min(sy, 1.f - 1e-6f), 1e-6f);
+        float x = maxval - (maxval + 1.f) * b2o_erf(sqrtf(-b2o_log(sx)));
+        sx *= 1.f + maxval + B2O_INV_SQRT_PI * tan_theta_i * b2o_exp(-b2o_sqr(cot_theta_i));
+        for (int i = 0; i < 3; ++i) {
+            float slope = b2o_erfinv(x),
+                  value = 1.f + x + B2O_INV_SQRT_PI * tan_theta_i * b2o_exp(-b2o_sqr(slope)) - sx,
+                  derivative = 1.f - slope * tan_theta_i;
+            x -= value / derivative;
+        }
+        *ox = b2o_erfinv(x); *oy = b2o_erfinv(b2o_fma(2.f, sy, -1.f));
+    } else {                                                             /* microfacet.h:395-410 */
+        float px, py; square_to_uniform_disk_concentric(sx, sy, &px, &py);
+        float s = .5f * (1.f + cos_theta_i);
+        /* enoki::lerp(a, b, t) = fmadd(b, t, fnmadd(a, t, a)) (array_router.h) */
+        float a0 = b2o_safe_sqrt(1.f - b2o_sqr(px));
+        py = b2o_fma(py, s, b2o_fma(-a0, s, a0));
+        float x = px, y = py, z = b2o_safe_sqrt(1.f - (px * px + py * py));
+        float sin_theta_i = b2o_safe_sqrt(1.f - b2o_sqr(cos_theta_i));
+        float norm = b2o_rcp(b2o_fma(sin_theta_i, y, cos_theta_i * z));
+        *ox = b2o_fma(cos_theta_i, y, -(sin_theta_i * z)) * norm; *oy = x * norm;
+    }
+}
+/* MicrofacetDistribution::sample, visible-normal branch — microfacet.h:283-316 */
+static inline v3 mf_sample(const omf *d, v3 wi, float sx, float sy, float *pdf) {
+    v3 wi_p = v3_normalize(v3_make(d->au * wi.x, d->av * wi.y, wi.z));
+    /* Frame3f::sincos_phi (frame.h:105-117): sin_theta_2 = fnmadd(z,z,1); inv = rsqrt; result = (y,x)*inv,
+       or (0,1) if |sin_theta_2| <= 4 eps */
+    float sin_theta_2 = b2o_fma(-wi_p.z, wi_p.z, 1.f), inv_sin_theta = b2o_rsqrt(sin_theta_2);
+    float sin_phi = wi_p.y * inv_sin_theta, cos_phi = wi_p.x * inv_sin_theta;
+    if (fabsf(sin_theta_2) <= 4.f * 5.9604644775390625e-08f) { sin_phi = 0.f; cos_phi = 1.f; }
+    float cos_theta = wi_p.z;
+    float slx, sly; mf_sample_visible_11(d, cos_theta, sx, sy, &slx, &sly);
+    float s0 = b2o_fma(cos_phi, slx, -(sin_phi * sly)) * d->au;
+    float s1 = b2o_fma(sin_phi, slx, cos_phi * sly) * d->av;
+    v3 m = v3_normalize(v3_make(-s0, -s1, 1.f));
+    *pdf = mf_eval(d, m) * mf_smith_g1(d, wi, m) * fabsf(v3_dot(wi, m)) / wi.z;
+    return m;
+}
+
+/* ============================================================================================
+ * BSDFs — src/bsdfs/{diffuse,dielectric,roughconductor}.cpp
+ * ============================================================================================ */
+typedef struct { v3 wo; float pdf, eta; int delta; } obs;
+
+static inline int bsdf_is_smooth(const B2Bsdf *b) {   /* has_flag(flags, BSDFFlags::Smooth), path.cpp:155 */
+    return b->type != B2_BSDF_DIELECTRIC;
+}
+
+static v3 bsdf_eval(const B2Bsdf *b, const osi *si, v3 wo) {
+    float cti = si->wi.z, cto = wo.z;
+    v3 zero = v3_make(0.f, 0.f, 0.f);
+    switch (b->type) {
+        case B2_BSDF_DIFFUSE: case B2_BSDF_NULL: {                        /* diffuse.cpp:104-119 */
+            if (!(cti > 0.f && cto > 0.f)) return zero;
+            const float *r = b->reflectance;
+            return v3_make((r[0] * B2O_INV_PI) * cto, (r[1] * B2O_INV_PI) * cto, (r[2] * B2O_INV_PI) * cto);
+        }
+        case B2_BSDF_ROUGHCONDUCTOR: {                                     /* roughconductor.cpp:277-343 */
+            if (!(cti > 0.f && cto > 0.f)) return zero;
+            v3 H = v3_normalize(v3_add(wo, si->wi));
+            omf d = mf_make(b);
+            float D = mf_eval(&d, H);
+            if (D == 0.f) return zero;
+            float G = mf_smith_g1(&d, si->wi, H) * mf_smith_g1(&d, wo, H);
+            float result = D * G / (4.f * cti);
+            float c = v3_dot(si->wi, H);
+            v3 F = v3_make(fresnel_conductor(c, b->cond_eta[0], b->cond_k[0]),
+                           fresnel_conductor(c, b->cond_eta[1], b->cond_k[1]),
+                           fresnel_conductor(c, b->cond_eta[2], b->cond_k[2]));
+            v3 res = v3_make(result * b->specular_reflectance[0], result * b->specular_reflectance[1],
+                             result * b->specular_reflectance[2]);
+            return v3_mul(F, res);
+        }
+        default: return zero;                                              /* dielectric.cpp:312-315 */
+    }
+}
+static float bsdf_pdf(const B2Bsdf *b, const osi *si, v3 wo) {
+    float cti = si->wi.z, cto = wo.z;
+    switch (b->type) {
+        case B2_BSDF_DIFFUSE: case B2_BSDF_NULL:                           /* diffuse.cpp:121-135 */
+            return (cti > 0.f && cto > 0.f) ? B2O_INV_PI * cto : 0.f;
+        case B2_BSDF_ROUGHCONDUCTOR: {                                     /* roughconductor.cpp:345-382 */
+            v3 m = v3_normalize(v3_add(wo, si->wi));
+            if (!(cti > 0.f && cto > 0.f && v3_dot(si->wi, m) > 0.f && v3_dot(wo, m) > 0.f)) return 0.f;
+            omf d = mf_make(b);
+            return mf_eval(&d, m) * mf_smith_g1(&d, si->wi, m) / (4.f * cti);
+        }
+        default: return 0.f;
+    }
+}
+/* returns the weight f/pdf; sample1 / (s2x,s2y) as in BSDF::sample(ctx, si, sample1, sample2) */
+static v3 bsdf_sample(const B2Bsdf *b, const osi *si, float sample1, float s2x, float s2y, obs *bs) {
+    v3 zero = v3_make(0.f, 0.f, 0.f);
+    memset(bs, 0, sizeof *bs);
+    float cti = si->wi.z;
+    switch (b->type) {
+        case B2_BSDF_DIFFUSE: case B2_BSDF_NULL: {                         /* diffuse.cpp:78-102 */
+            if (!(cti > 0.f)) return zero;
+            bs->wo = square_to_cosine_hemisphere(s2x, s2y);
+            bs->pdf = B2O_INV_PI * bs->wo.z;
+            bs->eta = 1.f; bs->delta = 0;
+            if (!(bs->pdf > 0.f)) return zero;
+            return v3_make(b->reflectance[0], b->reflectance[1], b->reflectance[2]);
+        }
+        case B2_BSDF_DIELECTRIC: {                                         /* dielectric.cpp:201-310 */
+            float r_i, cos_theta_t, eta_it, eta_ti;
+            fresnel(cti, b->eta, &r_i, &cos_theta_t, &eta_it, &eta_ti);
+            float t_i = 1.f - r_i;
+            int selected_r = sample1 <= r_i;
+            bs->pdf = selected_r ? r_i : t_i;
+            bs->delta = 1;
+            if (selected_r) { bs->wo = v3_make(-si->wi.x, -si->wi.y, si->wi.z); bs->eta = 1.f; }
+            else { bs->wo = v3_make(-eta_ti * si->wi.x, -eta_ti * si->wi.y, cos_theta_t); bs->eta = eta_it; }
+            v3 w = v3_make(1.f, 1.f, 1.f);
+            if (selected_r) w = v3_mul(w, v3_make(b->specular_reflectance[0], b->specular_reflectance[1], b->specular_reflectance[2]));
+            else {
+                w = v3_mul(w, v3_make(b->specular_transmittance[0], b->specular_transmittance[1], b->specular_transmittance[2]));
+                w = v3_scale(w, b2o_sqr(eta_ti));                            /* dielectric.cpp:303-307 (Radiance mode) */
+            }
+            return w;
+        }
+        case B2_BSDF_ROUGHCONDUCTOR: {                                     /* roughconductor.cpp:196-275 */
+            if (!(cti > 0.f)) return zero;
+            omf d = mf_make(b);
+            float pdf; v3 m = mf_sample(&d, si->wi, s2x, s2y, &pdf);
+            /* reflect(wi, m) = fmsub(m, 2*dot(wi,m), wi)  fresnel.h:281-283 */
+            float dwm = 2.f * v3_dot(si->wi, m);
+            bs->wo = v3_make(b2o_fma(m.x, dwm, -si->wi.x), b2o_fma(m.y, dwm, -si->wi.y), b2o_fma(m.z, dwm, -si->wi.z));
+            bs->eta = 1.f; bs->delta = 0;
+            int active = pdf != 0.f && bs->wo.z > 0.f;
+            float weight = mf_smith_g1(&d, bs->wo, m);
+            bs->pdf = pdf / (4.f * v3_dot(bs->wo, m));
+            float c = v3_dot(si->wi, m);
+            v3 F = v3_make(fresnel_conductor(c, b->cond_eta[0], b->cond_k[0]),
+                           fresnel_conductor(c, b->cond_eta[1], b->cond_k[1]),
+                           fresnel_conductor(c, b->cond_eta[2], b->cond_k[2]));
+            v3 wv = v3_make(weight * b->specular_reflectance[0], weight * b->specular_reflectance[1],
+                            weight * b->specular_reflectance[2]);
+            return active ? v3_mul(F, wv) : zero;
+        }
+        default: return zero;
+    }
+}
+
+/* ============================================================================================
+ * Emitters — src/emitters/area.cpp, src/librender/shape.cpp:292-323, mesh.cpp:352-397,
+ *            scene.cpp:164-231, distr_1d.h:144-204
+ * ============================================================================================ */
+typedef struct { v3 p, n, d; float pdf, dist; int emitter; } ods;
+
+static uint32_t distr_sample(const float *cdf, uint32_t n, float sum, float value) {   /* distr_1d.h:144-155 */
+    value *= sum;
+    /* m_valid: first/last index with nonzero pmf; binary_search array_utils.h:153-170 */
+    uint32_t first = 0, last = n - 1;
+    while (first < n - 1 && !(cdf[first] > 0.f)) ++first;
+    while (last > 0 && cdf[last] == cdf[last - 1]) --last;
+    uint32_t start = first, end = last;
+    uint32_t iterations = 0;
+    if (start < end) { uint32_t x = end - start; while (x) { ++iterations; x >>= 1; } } /* log2i(x)+1 */
+    for (uint32_t i = 0; i < iterations; ++i) {
+        uint32_t middle = (start + end) >> 1;
+        int cond = cdf[middle] < value;
+        if (cond) start = (middle + 1 < end) ? middle + 1 : end; else end = middle;
+    }
+    return start;
+}
+
+/* Mesh::sample_position mesh.cpp:352-397 + Shape::sample_direction shape.cpp:292-310 +
+   AreaLight::sample_direction area.cpp:121-134 ; returns spec = radiance / pdf (0 if inactive) */
+static v3 area_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
+    const B2Emitter *em = &s->desc->emitters[emitter];
+    int m = em->mesh;
+    const B2Mesh *me = &s->desc->meshes[m];
+    const float *cdf = s->cdf[m];
+    uint32_t face = distr_sample(cdf, me->n_faces, s->cdf_sum[m], sy);
+    /* sample_reuse distr_1d.h:194-204: pmf(index) = pmf[index]*norm ; pmf[i] is the stored face area */
+    const otri *tr = &s->tris[s->mesh_first[m] + face];
+    v3 e0 = v3_sub(tr->p1, tr->p0), e1 = v3_sub(tr->p2, tr->p0);
+    v3 cr = v3_cross(e0, e1);
+    float area = 0.5f * sqrtf(v3_dot(cr, cr));
+    float pmf = area * s->cdf_norm[m];
+    float cdfv = face > 0 ? cdf[face - 1] * s->cdf_norm[m] : 0.f;
+    sy = (sy - cdfv) / pmf;
+    float t = b2o_safe_sqrt(1.f - sx);                      /* warp.h:152-156 */
+    float bx = 1.f - t, by = t * sy;
+    ds->p = v3_add(v3_add(tr->p0, v3_scale(e0, bx)), v3_scale(e1, by));
+    float pdf = s->cdf_norm[m];
+    if (tr->has_normals)
+        ds->n = v3_normalize(v3_add(v3_add(v3_scale(tr->n0, 1.f - bx - by), v3_scale(tr->n1, bx)), v3_scale(tr->n2, by)));
+    else
+        ds->n = v3_normalize(cr);
+    ds->d = v3_sub(ds->p, ref_p);
+    float dist_squared = v3_dot(ds->d, ds->d);
+    ds->dist = sqrtf(dist_squared);
+    ds->d = v3_scale(ds->d, b2o_rcp(ds->dist));
+    float dp = fabsf(v3_dot(ds->d, ds->n));
+    pdf *= dp != 0.f ? dist_squared / dp : 0.f;
+    ds->pdf = pdf; ds->emitter = emitter;
+    int active = v3_dot(ds->d, ds->n) < 0.f && pdf != 0.f;
+    if (!active) return v3_make(0.f, 0.f, 0.f);
+    float ip = b2o_rcp(pdf);
+    return v3_make(em->radiance[0] * ip, em->radiance[1] * ip, em->radiance[2] * ip);
+}
+
+/* Scene::sample_emitter_direction scene.cpp:164-214 (visibility test done by the caller) */
+static v3 scene_sample_emitter_direction(const oscene *s, v3 ref_p, float sx, float sy, ods *ds) {
+    uint32_t ne = s->desc->n_emitters;
+    if (ne == 0) { memset(ds, 0, sizeof *ds); return v3_make(0.f, 0.f, 0.f); }
+    if (ne == 1) return area_sample_direction(s, 0, ref_p, sx, sy, ds);
+    float emitter_pdf = 1.f / (float) ne;
+    uint32_t index = (uint32_t) (sx * (float) ne);
+    if (index > ne - 1) index = ne - 1;
+    sx = (sx - (float) index * emitter_pdf) * (float) ne;
+    v3 spec = area_sample_direction(s, (int) index, ref_p, sx, sy, ds);
+    ds->pdf *= emitter_pdf;
+    return v3_scale(spec, b2o_rcp(emitter_pdf));
+}
+
+/* Scene::pdf_emitter_direction scene.cpp:216-231 -> AreaLight::pdf_direction area.cpp:168-187
+   -> Shape::pdf_direction shape.cpp:312-323 -> Mesh::pdf_position mesh.cpp:417-420 */
+static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 d, v3 n, float dist) {
+    const B2Emitter *em = &s->desc->emitters[emitter];
+    float dp = v3_dot(d, n);
+    if (!(dp < 0.f)) return 0.f;
+    float pdf = s->cdf_norm[em->mesh];
+    float adp = fabsf(dp);
+    pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;
+    if (s->desc->n_emitters != 1) pdf = pdf * (1.f / (float) s->desc->n_emitters);
+    return pdf;
+}
+
+/* ============================================================================================
+ * PathIntegrator::sample — src/integrators/path.cpp:100-227
+ * ============================================================================================ */
+typedef struct { uint64_t segments, shadow_rays; } ocount;
+
+static inline float mis_weight(float a, float b) {   /* path.cpp:223-227 */
+    a *= a; b *= b;
+    return a > 0.f ? a / (a + b) : 0.f;
+}
+
+static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, oray ray, int *valid_ray,
+                      int brute, ocount *cnt) {
+    const B2SceneDesc *d = s->desc;
+    float eta = 1.f, emission_weight = 1.f;
+    v3 throughput = v3_make(1.f, 1.f, 1.f), result = v3_make(0.f, 0.f, 0.f);
+    ohit h = scene_intersect(s, &ray, brute); cnt->segments++;
+    osi si; si_fill(s, &ray, &h, &si);
+    *valid_ray = h.t < INFINITY;
+    int emitter = (si.mesh >= 0) ? d->meshes[si.mesh].emitter : -1;     /* scene.h:243-253 (no envmap yet) */
+    int active = 1;
+    for (int depth = 1;; ++depth) {
+        if (emitter >= 0) {                                               /* path.cpp:128-129 */
+            const B2Emitter *em = &d->emitters[emitter];
+            v3 ev = si.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f); /* area.cpp:63-71 */
+            v3 wt = v3_scale(throughput, emission_weight);
+            result = v3_add(result, v3_mul(wt, ev));
+        }
+        active &= si.t < INFINITY;                                        /* path.cpp:131 */
+        if (depth > rp->rr_depth) {                                       /* path.cpp:137-141 */
+            float q = b2o_min(v3_hmax(throughput) * b2o_sqr(eta), .95f);
+            if (active) active &= pcg32_next_float(rng) < q;
+            throughput = v3_scale(throughput, b2o_rcp(q));
+        }
+        if ((uint32_t) depth >= (uint32_t) rp->max_depth || !active) break;   /* path.cpp:147-149 */
+
+        const B2Bsdf *bsdf = &d->bsdfs[d->meshes[si.mesh].bsdf];
+        if (bsdf_is_smooth(bsdf)) {                                       /* path.cpp:153-172 */
+            float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
+            ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
+            if (ds.pdf != 0.f) {
+                int visible = 1;
+                if (emitter_val.x != 0.f || emitter_val.y != 0.f || emitter_val.z != 0.f) {
+                    /* scene.cpp:203-207 (the reference also traces when spec is already 0; the
+                       outcome cannot change the result then, so the oracle skips it) */
+                    oray sr; sr.o = si.p; sr.d = ds.d;
+                    sr.mint = B2O_RAY_EPS * (1.f + v3_hmax_abs(si.p));
+                    sr.maxt = ds.dist * (1.f - B2O_SHADOW_EPS);
+                    cnt->shadow_rays++;
+                    visible = !scene_occluded(s, &sr, brute);
+                }
+                if (!visible) emitter_val = v3_make(0.f, 0.f, 0.f);
+                v3 wo = to_local(&si, ds.d);
+                v3 bsdf_val = bsdf_eval(bsdf, &si, wo);
+                float bpdf = bsdf_pdf(bsdf, &si, wo);
+                float mis = mis_weight(ds.pdf, bpdf);
+                v3 c = v3_mul(v3_mul(v3_scale(throughput, mis), bsdf_val), emitter_val);
+                result = v3_add(result, c);
+            }
+        }
+        /* BSDF sampling: g++ evaluates the arguments right to left, so next_2d is drawn
+           BEFORE next_1d (path.cpp:177-178) */
+        float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
+        float s1 = pcg32_next_float(rng);
+        obs bs; v3 bsdf_val = bsdf_sample(bsdf, &si, s1, s2x, s2y, &bs);
+        throughput = v3_mul(throughput, bsdf_val);
+        active &= throughput.x != 0.f || throughput.y != 0.f || throughput.z != 0.f;
+        if (!active) break;
+        eta *= bs.eta;
+        oray nr; nr.o = si.p; nr.d = to_world(&si, bs.wo);                 /* interaction.h:58-61 */
+        nr.mint = (1.f + v3_hmax_abs(si.p)) * B2O_RAY_EPS; nr.maxt = INFINITY;
+        ohit h2 = scene_intersect(s, &nr, brute); cnt->segments++;
+        osi si2; si_fill(s, &nr, &h2, &si2);
+        emitter = (si2.mesh >= 0) ? d->meshes[si2.mesh].emitter : -1;
+        if (emitter >= 0) {                                               /* path.cpp:194-205, records.h:168-174 */
+            v3 dd = v3_sub(si2.p, si.p);
+            float dist = sqrtf(v3_dot(dd, dd));
+            dd = v3_scale(dd, b2o_rcp(dist));
+            float emitter_pdf = !bs.delta ? scene_pdf_emitter_direction(s, emitter, dd, si2.sh_n, dist) : 0.f;
+            emission_weight = mis_weight(bs.pdf, emitter_pdf);
+        }
+        ray = nr; si = si2;
+    }
+    return result;
+}
+
+/* ============================================================================================
+ * Sensor + render driver — perspective.cpp:182-216, integrator.cpp:181-288, imageblock.cpp:79-172
+ * ============================================================================================ */
+static oray sensor_sample_ray(const B2Sensor *sn, float sx, float sy) {
+    const float *M = sn->sample_to_camera;
+    float px = sx + sn->principal_point_offset[0], py = sy + sn->principal_point_offset[1];
+    /* Transform * Point (transform.h:103-111): result = col3; fmadd(col_i, arg_i, result); / w.
+       arg.z = 0 contributes fmadd(col2, 0, r) = r. */
+    float r[4];
+    for (int k = 0; k < 4; ++k) {
+        float acc = M[4 * k + 3];
+        acc = b2o_fma(M[4 * k + 0], px, acc);
+        acc = b2o_fma(M[4 * k + 1], py, acc);
+        acc = b2o_fma(M[4 * k + 2], 0.f, acc);
+        r[k] = acc;
+    }
+    float iw = b2o_rcp(r[3]);
+    v3 near_p = v3_make(r[0] * iw, r[1] * iw, r[2] * iw);
+    v3 d = v3_normalize(near_p);
+    float inv_z = b2o_rcp(d.z);
+    oray ray;
+    ray.mint = sn->near_clip * inv_z; ray.maxt = sn->far_clip * inv_z;
+    const float *T = sn->to_world;
+    ray.o = v3_make(T[3], T[7], T[11]);                                    /* transform_affine(Point(0)) */
+    /* Transform * Vector (transform.h:117-125) */
+    ray.d.x = b2o_fma(T[2], d.z, b2o_fma(T[1], d.y, T[0] * d.x));
+    ray.d.y = b2o_fma(T[6], d.z, b2o_fma(T[5], d.y, T[4] * d.x));
+    ray.d.z = b2o_fma(T[10], d.z, b2o_fma(T[9], d.y, T[8] * d.x));
+    return ray;
+}
+
+static inline uint32_t compact1by1(uint32_t x) {    /* morton_decode: even bits -> x, odd bits -> y */
+    x &= 0x55555555u; x = (x ^ (x >> 1)) & 0x33333333u; x = (x ^ (x >> 2)) & 0x0f0f0f0fu;
+    x = (x ^ (x >> 4)) & 0x00ff00ffu; x = (x ^ (x >> 8)) & 0x0000ffffu; return x;
+}
+
+typedef struct {
+    int ox, oy, w, h, border;       /* block offset (film coords), size */
+    float *data;                    /* (h+2b) x (w+2b) x 5 */
+} oblock;
+
+/* ImageBlock::put(pos, value) — imageblock.cpp:79-172 (m_normalize = false, warn flags on) */
+static int block_put(oblock *blk, const B2Film *film, float posx, float posy, const float value[5]) {
+    for (int k = 0; k < 5; ++k) {
+        if (!(value[k] >= -1e-5f)) return 0;
+        if (!(fabsf(value[k]) < INFINITY)) return 0;
+    }
+    float radius = film->filter_radius;
+    int sx = blk->w + 2 * blk->border, sy = blk->h + 2 * blk->border;
+    float px = posx - ((float) (blk->ox - blk->border) + .5f), py = posy - ((float) (blk->oy - blk->border) + .5f);
+    if (radius > 0.5f + B2O_RAY_EPS) {
+        int lox = (int) ceilf(px - radius), loy = (int) ceilf(py - radius);
+        int hix = (int) floorf(px + radius), hiy = (int) floorf(py + radius);
+        if (lox < 0) lox = 0;
+        if (loy < 0) loy = 0;
+        if (hix > sx - 1) hix = sx - 1;
+        if (hiy > sy - 1) hiy = sy - 1;
+        uint32_t n = (uint32_t) ceilf((radius - 2.f * B2O_RAY_EPS) * 2.f);
+        float basex = (float) lox - px, basey = (float) loy - py;
+        float wx[16], wy[16];
+        for (uint32_t i = 0; i < n && i < 16; ++i) {
+            float fx = basex + (float) i, fy = basey + (float) i;
+            int ix = (int) fabsf(fx * film->filter_scale), iy = (int) fabsf(fy * film->filter_scale);
+            if (ix > B2_FILTER_RESOLUTION) ix = B2_FILTER_RESOLUTION;
+            if (iy > B2_FILTER_RESOLUTION) iy = B2_FILTER_RESOLUTION;
+            wx[i] = film->filter_lut[ix]; wy[i] = film->filter_lut[iy];
+        }
+        for (uint32_t yr = 0; yr < n; ++yr) {
+            int y = loy + (int) yr;
+            int enabled = y <= hiy;
+            for (uint32_t xr = 0; xr < n; ++xr) {
+                int x = lox + (int) xr;
+                float weight = wy[yr] * wx[xr];
+                enabled &= x <= hix;          /* imageblock.cpp:158 */
+                if (enabled) {
+                    float *dst = blk->data + 5 * ((size_t) y * sx + x);
+                    for (int k = 0; k < 5; ++k) dst[k] += value[k] * weight;
+                }
+            }
+        }
+    } else {
+        int lox = (int) ceilf(px - .5f), loy = (int) ceilf(py - .5f);
+        if (lox >= 0 && loy >= 0 && lox < sx && loy < sy) {
+            float *dst = blk->data + 5 * ((size_t) loy * sx + lox);
+            for (int k = 0; k < 5; ++k) dst[k] += value[k];
+        }
+    }
+    return 1;
+}
+
+typedef struct {
+    const oscene *s; const B2RenderParams *rp;
+    uint32_t n_blocks; const int32_t *order; uint32_t n_passes, spp_pass;
+    oblock *blocks;           /* one per (pass, block) work item */
+    uint32_t next, total; pthread_mutex_t mu;
+    int brute;
+    ocount cnt; uint64_t invalid, samples;
+} ojob;
+
+/* render_block (integrator.cpp:181-209) + render_sample (:233-288) for work item `w` */
+static void render_item(ojob *j, uint32_t w, ocount *cnt, uint64_t *invalid, uint64_t *samples) {
+    const B2SceneDesc *d = j->s->desc; const B2Film *film = &d->film; const B2RenderParams *rp = j->rp;
+    uint32_t pass = w / j->n_blocks, b = w % j->n_blocks;        /* pass 0 runs first: remaining_passes = n_passes */
+    uint32_t bs = rp->block_size;
+    uint64_t block_id = (uint64_t) b + (uint64_t) (j->n_passes - pass - 1) * j->n_blocks;    /* spiral.cpp:41 */
+    oblock *blk = &j->blocks[w];
+    blk->ox = j->order[2 * b] * (int) bs; blk->oy = j->order[2 * b + 1] * (int) bs;
+    blk->w = (int) bs < film->crop_size[0] - blk->ox ? (int) bs : film->crop_size[0] - blk->ox;
+    blk->h = (int) bs < film->crop_size[1] - blk->oy ? (int) bs : film->crop_size[1] - blk->oy;
+    blk->ox += film->crop_offset[0]; blk->oy += film->crop_offset[1];
+    blk->border = film->border;
+    blk->data = (float *) calloc((size_t) 5 * (blk->w + 2 * blk->border) * (blk->h + 2 * blk->border), sizeof(float));
+    uint32_t pixel_count = bs * bs;
+    for (uint32_t i = 0; i < pixel_count; ++i) {
+        pcg32 rng; sampler_seed(&rng, rp->seed, block_id * pixel_count + i);                /* integrator.cpp:198 */
+        uint32_t mx = compact1by1(i), my = compact1by1(i >> 1);
+        if ((int) mx >= blk->w || (int) my >= blk->h) continue;
+        float posx = (float) (mx + (uint32_t) blk->ox), posy = (float) (my + (uint32_t) blk->oy);
+        for (uint32_t k = 0; k < j->spp_pass; ++k) {
+            float jx = pcg32_next_float(&rng), jy = pcg32_next_float(&rng);                  /* :242 */
+            float psx = posx + jx, psy = posy + jy;
+            (void) pcg32_next_float(&rng);                                                   /* :252 wavelength sample */
+            float ax = (psx - (float) film->crop_offset[0]) / (float) film->crop_size[0],
+                  ay = (psy - (float) film->crop_offset[1]) / (float) film->crop_size[1];   /* :254-256 */
+            oray ray = sensor_sample_ray(&d->sensor, ax, ay);
+            int valid;
+            v3 L = path_sample(j->s, rp, &rng, ray, &valid, j->brute, cnt);
+            /* ray_weight = 1 in rgb mode ; srgb_to_xyz spectrum.h:221-228 (M * rgb, matrix.h:170-177) */
+            float val[5];
+            val[0] = b2o_fma(0.180423f, L.z, b2o_fma(0.357580f, L.y, 0.412453f * L.x));
+            val[1] = b2o_fma(0.072169f, L.z, b2o_fma(0.715160f, L.y, 0.212671f * L.x));
+            val[2] = b2o_fma(0.950227f, L.z, b2o_fma(0.119193f, L.y, 0.019334f * L.x));
+            val[3] = valid ? 1.f : 0.f; val[4] = 1.f;
+            if (!block_put(blk, film, psx, psy, val)) (*invalid)++;
+            (*samples)++;
+        }
+    }
+}
+
+static void *worker(void *arg) {
+    ojob *j = (ojob *) arg;
+    ocount cnt = { 0, 0 }; uint64_t invalid = 0, samples = 0;
+    for (;;) {
+        pthread_mutex_lock(&j->mu);
+        uint32_t w = j->next < j->total ? j->next++ : 0xffffffffu;
+        pthread_mutex_unlock(&j->mu);
+        if (w == 0xffffffffu) break;
+        render_item(j, w, &cnt, &invalid, &samples);
+    }
+    pthread_mutex_lock(&j->mu);
+    j->cnt.segments += cnt.segments; j->cnt.shadow_rays += cnt.shadow_rays; j->invalid += invalid; j->samples += samples;
+    pthread_mutex_unlock(&j->mu);
+    return NULL;
+}
+
+/* SamplingIntegrator::render (integrator.cpp:51-179) + HDRFilm::put (hdrfilm.cpp:207-211).
+   Blocks are rendered by `threads` workers into private buffers and merged into the film in
+   the reference's single-thread order (pass by pass, spiral order), so the result does not
+   depend on the thread count. Honors rank/world_size (blocks b % world == rank). */
+B2O_API int b2o_render(const B2SceneDesc *d, const B2RenderParams *rp, float *xyzaw, B2Stats *stats,
+                       int threads, int brute) {
+    oscene *s = oscene_create(d);
+    const B2Film *film = &d->film;
+    uint32_t nb = 0; b2o_spiral(film->crop_size[0], film->crop_size[1], (int) rp->block_size, &nb, NULL);
+    int32_t *order = (int32_t *) malloc(sizeof(int32_t) * 2 * nb);
+    b2o_spiral(film->crop_size[0], film->crop_size[1], (int) rp->block_size, &nb, order);
+    uint32_t spp_pass = rp->samples_per_pass ? (rp->samples_per_pass < rp->spp ? rp->samples_per_pass : rp->spp) : rp->spp;
+    if (rp->spp % spp_pass) { free(order); oscene_destroy(s); return B2_ERR_INVALID; }
+    ojob j; memset(&j, 0, sizeof j);
+    j.s = s; j.rp = rp; j.n_blocks = nb; j.order = order; j.n_passes = rp->spp / spp_pass; j.spp_pass = spp_pass;
+    j.total = nb * j.n_passes; j.brute = brute;
+    j.blocks = (oblock *) calloc(j.total, sizeof(oblock));
+    pthread_mutex_init(&j.mu, NULL);
+    int world = rp->world_size > 0 ? rp->world_size : 1;
+    if (threads < 1) threads = 1;
+    /* rank filter: render only owned blocks (others stay empty) */
+    if (world > 1) {
+        /* simple: single-threaded loop over owned items */
+        ocount cnt = { 0, 0 }; uint64_t inv = 0, smp = 0;
+        for (uint32_t w = 0; w < j.total; ++w)
+            if ((int) ((w % nb) % (uint32_t) world) == rp->rank) render_item(&j, w, &cnt, &inv, &smp);
+        j.cnt = cnt; j.invalid = inv; j.samples = smp;
+    } else if (threads == 1) {
+        j.next = 0; worker(&j);
+    } else {
+        pthread_t *th = (pthread_t *) malloc(sizeof(pthread_t) * (size_t) threads);
+        for (int t = 0; t < threads; ++t) pthread_create(&th[t], NULL, worker, &j);
+        for (int t = 0; t < threads; ++t) pthread_join(th[t], NULL);
+        free(th);
+    }
+    /* merge: ImageBlock::put(block) imageblock.cpp:49-77 — film += block over the overlap */
+    int W = film->crop_size[0], H = film->crop_size[1];
+    memset(xyzaw, 0, sizeof(float) * 5 * (size_t) W * H);
+    for (uint32_t w = 0; w < j.total; ++w) {
+        oblock *blk = &j.blocks[w];
+        if (!blk->data) continue;
+        int sx = blk->w + 2 * blk->border, sy = blk->h + 2 * blk->border;
+        for (int y = 0; y < sy; ++y) {
+            int fy = blk->oy - film->crop_offset[1] - blk->border + y;
+            if (fy < 0 || fy >= H) continue;
+            for (int x = 0; x < sx; ++x) {
+                int fx = blk->ox - film->crop_offset[0] - blk->border + x;
+                if (fx < 0 || fx >= W) continue;
+                const float *src = blk->data + 5 * ((size_t) y * sx + x);
+                float *dst = xyzaw + 5 * ((size_t) fy * W + fx);
+                for (int k = 0; k < 5; ++k) dst[k] += src[k];
+            }
+        }
+        free(blk->data);
+    }
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        stats->n_samples = j.samples; stats->n_segments = j.cnt.segments; stats->n_shadow_rays = j.cnt.shadow_rays;
+        stats->n_invalid = j.invalid; stats->bvh_nodes = (uint64_t) s->n_nodes; stats->bvh_tris = s->n_tris;
+    }
+    free(j.blocks); free(order); pthread_mutex_destroy(&j.mu);
+    oscene_destroy(s);
+    return 0;
+}
+
+/* HDRFilm::bitmap(): XYZAW -> RGB — hdrfilm.cpp:251-322, bitmap.cpp:420-427, struct.cpp:1750-1812
+   (value = sum coef*channel in fp32, then * (1/W)) */
+B2O_API int b2o_develop(const float *xyzaw, int n_pixels, float *rgb) {
+    for (int i = 0; i < n_pixels; ++i) {
+        const float *p = xyzaw + 5 * (size_t) i;
+        float iw = 1.f / p[4];
+        float r = 0.f, g = 0.f, b = 0.f;
+        r += 3.240479f * p[0]; r += -1.537150f * p[1]; r += -0.498535f * p[2];
+        g += -0.969256f * p[0]; g += 1.875991f * p[1]; g += 0.041556f * p[2];
+        b += 0.055648f * p[0]; b += -0.204043f * p[1]; b += 1.057311f * p[2];
+        rgb[3 * i] = r * iw; rgb[3 * i + 1] = g * iw; rgb[3 * i + 2] = b * iw;
+    }
+    return 0;
+}
+
+/* ============================================================================================
+ * Stage-level entry points (same signatures as include/b2pt.h b2_stage_*, scene passed as desc)
+ * ============================================================================================ */
+B2O_API int b2o_stage_raygen(const B2SceneDesc *d, uint32_t n, const uint32_t *px, const uint32_t *py,
+                             const uint64_t *seed_offset, uint64_t base_seed,
+                             float *ray_o, float *ray_d, uint64_t *rng_state, float *pos) {
+    const B2Film *film = &d->film;
+    for (uint32_t i = 0; i < n; ++i) {
+        pcg32 rng; sampler_seed(&rng, base_seed, seed_offset[i]);
+        float jx = pcg32_next_float(&rng), jy = pcg32_next_float(&rng);
+        float psx = (float) px[i] + jx, psy = (float) py[i] + jy;
+        (void) pcg32_next_float(&rng);
+        float ax = (psx - (float) film->crop_offset[0]) / (float) film->crop_size[0],
+              ay = (psy - (float) film->crop_offset[1]) / (float) film->crop_size[1];
+        oray r = sensor_sample_ray(&d->sensor, ax, ay);
+        ray_o[4 * i] = r.o.x; ray_o[4 * i + 1] = r.o.y; ray_o[4 * i + 2] = r.o.z; ray_o[4 * i + 3] = r.mint;
+        ray_d[4 * i] = r.d.x; ray_d[4 * i + 1] = r.d.y; ray_d[4 * i + 2] = r.d.z; ray_d[4 * i + 3] = r.maxt;
+        rng_state[i] = rng.state; pos[2 * i] = psx; pos[2 * i + 1] = psy;
+    }
+    return 0;
+}
+static oray load_ray(const float *ray_o, const float *ray_d, uint32_t i) {
+    oray r; r.o = v3_make(ray_o[4 * i], ray_o[4 * i + 1], ray_o[4 * i + 2]); r.mint = ray_o[4 * i + 3];
+    r.d = v3_make(ray_d[4 * i], ray_d[4 * i + 1], ray_d[4 * i + 2]); r.maxt = ray_d[4 * i + 3];
+    return r;
+}
+B2O_API int b2o_stage_intersect(const B2SceneDesc *d, uint32_t n, const float *ray_o, const float *ray_d,
+                                float *hit, int32_t *inst, int brute) {
+    oscene *s = oscene_create(d);
+    for (uint32_t i = 0; i < n; ++i) {
+        oray r = load_ray(ray_o, ray_d, i);
+        ohit h = scene_intersect(s, &r, brute);
+        hit[4 * i] = h.t; hit[4 * i + 1] = h.u; hit[4 * i + 2] = h.v; hit[4 * i + 3] = b2o_u2f(h.prim);
+        if (inst) inst[i] = -1;
+    }
+    oscene_destroy(s);
+    return 0;
+}
+B2O_API int b2o_stage_occluded(const B2SceneDesc *d, uint32_t n, const float *ray_o, const float *ray_d,
+                               uint8_t *occluded, int brute) {
+    oscene *s = oscene_create(d);
+    for (uint32_t i = 0; i < n; ++i) {
+        oray r = load_ray(ray_o, ray_d, i);
+        occluded[i] = (uint8_t) scene_occluded(s, &r, brute);
+    }
+    oscene_destroy(s);
+    return 0;
+}
+B2O_API int b2o_stage_si_fill(const B2SceneDesc *d, uint32_t n, const float *ray_o, const float *ray_d,
+                              const float *hit, const int32_t *inst, float *si_out) {
+    (void) inst;
+    oscene *s = oscene_create(d);
+    for (uint32_t i = 0; i < n; ++i) {
+        oray r = load_ray(ray_o, ray_d, i);
+        ohit h; h.t = hit[4 * i]; h.u = hit[4 * i + 1]; h.v = hit[4 * i + 2]; h.prim = b2o_f2u(hit[4 * i + 3]);
+        osi si; si_fill(s, &r, &h, &si);
+        float *o = si_out + 16 * (size_t) i;
+        o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z;
+        o[3] = si.n.x; o[4] = si.n.y; o[5] = si.n.z;
+        o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z;
+        o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
+        o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z;
+        o[15] = b2o_u2f(si.mesh >= 0 ? (uint32_t) d->meshes[si.mesh].bsdf : 0xffffffffu);
+    }
+    oscene_destroy(s);
+    return 0;
+}
+
+/* ============================================================================================
+ * BSDF unit entry points (for the reference's closed-form tests: test_diffuse.py,
+ * test_dielectric.py, test_microfacet.py, test_fresnel.py). wi/wo in local coordinates.
+ * ============================================================================================ */
+static osi local_si(const float wi[3]) {
+    osi si; memset(&si, 0, sizeof si);
+    si.t = 1.f; si.sh_n = v3_make(0, 0, 1); si.sh_s = v3_make(1, 0, 0); si.sh_t = v3_make(0, 1, 0);
+    si.n = si.sh_n; si.wi = v3_make(wi[0], wi[1], wi[2]);
+    return si;
+}
+B2O_API void b2o_bsdf_eval(const B2Bsdf *b, const float wi[3], const float wo[3], float out_rgb[3], float *out_pdf) {
+    osi si = local_si(wi);
+    v3 w = v3_make(wo[0], wo[1], wo[2]);
+    v3 v = bsdf_eval(b, &si, w);
+    out_rgb[0] = v.x; out_rgb[1] = v.y; out_rgb[2] = v.z;
+    *out_pdf = bsdf_pdf(b, &si, w);
+}
+B2O_API void b2o_bsdf_sample(const B2Bsdf *b, const float wi[3], float sample1, const float sample2[2],
+                             float out_wo[3], float *out_pdf, float *out_eta, int *out_delta, float out_weight[3]) {
+    osi si = local_si(wi);
+    obs bs; v3 w = bsdf_sample(b, &si, sample1, sample2[0], sample2[1], &bs);
+    out_wo[0] = bs.wo.x; out_wo[1] = bs.wo.y; out_wo[2] = bs.wo.z;
+    *out_pdf = bs.pdf; *out_eta = bs.eta; *out_delta = bs.delta;
+    out_weight[0] = w.x; out_weight[1] = w.y; out_weight[2] = w.z;
+}
+B2O_API void b2o_fresnel(float cos_theta_i, float eta, float out[4]) {
+    fresnel(cos_theta_i, eta, &out[0], &out[1], &out[2], &out[3]);
+}
+B2O_API float b2o_fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {
+    return fresnel_conductor(cos_theta_i, eta_r, eta_i);
+}
+B2O_API void b2o_math_probe(float x, float out[6]) {
+    b2o_sincos(x, &out[0], &out[1]);
+    out[2] = b2o_exp(x); out[3] = b2o_log(x); out[4] = b2o_erf(x); out[5] = b2o_erfinv(x);
+}
+B2O_API void b2o_warp_cosine_hemisphere(float sx, float sy, float out[3]) {
+    v3 v = square_to_cosine_hemisphere(sx, sy); out[0] = v.x; out[1] = v.y; out[2] = v.z;
+}

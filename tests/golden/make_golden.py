@@ -1,0 +1,285 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ from the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference for the cbox OBJ data and
+oracle/_ref/dist/mitsuba built by oracle/build_ref.sh). The outputs are small, committed,
+and are what pins the CPU oracle (oracle/b2o.c) to the reference:
+
+  cbox_meshes.npz          the 8 cbox meshes exactly as the reference's OBJ loader produces
+                           them (src/shapes/obj.cpp:150-346: strtof, (v,vt,vn)-keyed vertex
+                           dedup, fan triangulation, to_world applied at load; vertex normals
+                           from the file or angle-weighted, src/librender/mesh.cpp:200-256)
+  ref_<name>.npz           fp32 linear-RGB images rendered by `mitsuba -m scalar_rgb` with
+                           pinned block_size and component_format=float32 / file_format=pfm,
+                           plus the exact CLI parameters used.
+
+Usage:  python tests/golden/make_golden.py [--only NAME]
+"""
+import argparse
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("B2_REFERENCE", "/root/reference")
+DIST = os.path.join(ROOT, "oracle", "_ref", "dist")
+CBOX = os.path.join(REF, "resources", "data", "scenes", "cbox")
+
+f32 = np.float32
+
+
+def load_obj_like_reference(path, translate=(0.0, 0.0, 0.0)):
+    """Mirror of OBJMesh (src/shapes/obj.cpp:150-346) for v / vn / f records."""
+    verts, norms = [], []
+    vmap = {}          # key (v, vt, vn) -> id, ids handed out in order of first use
+    keys = []
+    tris = []
+    t = np.array(translate, dtype=f32)
+    for line in open(path):
+        cur = line.strip()
+        if cur.startswith("v "):
+            p = np.array([f32(x) for x in cur.split()[1:4]], dtype=f32)
+            # Transform4f::translate().transform_affine(p): fmadd(col_i, p_i, col3) == p + t in fp32
+            verts.append((p + t).astype(f32))
+        elif cur.startswith("vn "):
+            n = np.array([f32(x) for x in cur.split()[1:4]], dtype=f32)
+            n = n * f32(1.0) / np.sqrt((n * n).sum(dtype=f32), dtype=f32)
+            norms.append(n.astype(f32))
+        elif cur.startswith("f "):
+            ids = []
+            for tok in cur.split()[1:]:
+                parts = tok.split("/")
+                key = [0, 0, 0]
+                for i, s in enumerate(parts[:3]):
+                    key[i] = int(s) if s else 0
+                key = tuple(key)
+                if key not in vmap:
+                    vmap[key] = len(keys); keys.append(key)
+                ids.append(vmap[key])
+            tri = [0, 0, 0]
+            for vi, idx in enumerate(ids):
+                if vi < 3:
+                    tri[vi] = idx
+                else:
+                    tri[1] = tri[2]; tri[2] = idx
+                if vi >= 2:
+                    tris.append(tuple(tri))
+    positions = np.array([verts[k[0] - 1] for k in keys], dtype=f32)
+    faces = np.array(tris, dtype=np.uint32)
+    if norms:
+        normals = np.array([norms[k[2] - 1] for k in keys], dtype=f32)
+    else:
+        normals = recompute_vertex_normals(positions, faces)
+    return positions, normals, faces
+
+
+def _cross(a, b):
+    return np.array([a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]], dtype=f32)
+
+
+def _normalize(v):
+    return (v * (f32(1.0) / np.sqrt(np.dot(v, v).astype(f32), dtype=f32))).astype(f32)
+
+
+def _unit_angle(u, v):
+    # include/mitsuba/core/vector.h unit_angle(): numerically robust angle between unit vectors
+    d = f32(np.dot(u, v))
+    w = v - (u if d >= 0 else -u)
+    temp = f32(2.0) * np.arcsin(f32(0.5) * np.sqrt(np.dot(w, w).astype(f32), dtype=f32), dtype=f32)
+    return temp if d >= 0 else f32(np.pi) - temp
+
+
+def recompute_vertex_normals(positions, faces):
+    """Mesh::recompute_vertex_normals, scalar branch (src/librender/mesh.cpp:200-256)."""
+    normals = np.zeros_like(positions)
+    for f in faces:
+        v = [positions[f[0]], positions[f[1]], positions[f[2]]]
+        s0, s1 = v[1] - v[0], v[2] - v[0]
+        n = _cross(s0, s1)
+        l2 = f32(np.dot(n, n))
+        if l2 > 0:
+            n = n * (f32(1.0) / np.sqrt(l2, dtype=f32))
+            side1 = [s0, v[2] - v[1], v[0] - v[2]]
+            side2 = [s1, v[0] - v[1], v[1] - v[2]]
+            for j in range(3):
+                ang = _unit_angle(_normalize(side1[j]), _normalize(side2[j]))
+                normals[f[j]] = normals[f[j]] + n * f32(ang)
+    for i in range(len(normals)):
+        ln = np.sqrt(np.dot(normals[i], normals[i]).astype(f32), dtype=f32)
+        normals[i] = normals[i] / ln if ln != 0 else np.array([1, 0, 0], dtype=f32)
+    return normals.astype(f32)
+
+
+# (mesh file, bsdf id) in XML document order: resources/data/scenes/cbox/fragments/shapes.xml
+CBOX_SHAPES = [
+    ("cbox_luminaire.obj", "light", (0.0, -0.5, 0.0)),
+    ("cbox_floor.obj", "white", (0, 0, 0)),
+    ("cbox_ceiling.obj", "white", (0, 0, 0)),
+    ("cbox_back.obj", "white", (0, 0, 0)),
+    ("cbox_greenwall.obj", "green", (0, 0, 0)),
+    ("cbox_redwall.obj", "red", (0, 0, 0)),
+    ("cbox_smallbox.obj", "box", (0, 0, 0)),
+    ("cbox_largebox.obj", "box", (0, 0, 0)),
+]
+
+
+def make_cbox_meshes():
+    out = {}
+    for i, (fn, bsdf, tr) in enumerate(CBOX_SHAPES):
+        p, n, f = load_obj_like_reference(os.path.join(CBOX, "meshes", fn), tr)
+        out[f"m{i}_positions"] = p; out[f"m{i}_normals"] = n; out[f"m{i}_faces"] = f
+        out[f"m{i}_bsdf"] = np.array(bsdf)
+    np.savez_compressed(os.path.join(HERE, "cbox_meshes.npz"), **out)
+    print("cbox_meshes.npz:", sum(len(out[f"m{i}_faces"]) for i in range(len(CBOX_SHAPES))), "triangles")
+
+
+def read_pfm(fn):
+    with open(fn, "rb") as f:
+        hdr = f.readline().strip()
+        w, h = map(int, f.readline().split())
+        scale = float(f.readline())
+        c = 3 if hdr == b"PF" else 1
+        a = np.frombuffer(f.read(), dtype="<f4" if scale < 0 else ">f4").reshape(h, w, c)
+    return np.ascontiguousarray(a[::-1]).astype(np.float32)     # PFM rows are bottom-up
+
+
+CBOX_XML = """<scene version="2.0.0">
+    <integrator type="path">
+        <integer name="max_depth" value="{max_depth}"/>
+        <integer name="rr_depth" value="{rr_depth}"/>
+        <integer name="block_size" value="{block_size}"/>
+        {spp_pass}
+    </integrator>
+    <sensor type="perspective">
+        <string name="fov_axis" value="smaller"/>
+        <float name="near_clip" value="10"/>
+        <float name="far_clip" value="2800"/>
+        <float name="focus_distance" value="1000"/>
+        <float name="fov" value="39.3077"/>
+        <transform name="to_world">
+            <lookat origin="278, 273, -800" target="278, 273, -799" up="0, 1, 0"/>
+        </transform>
+        <sampler type="independent">
+            <integer name="sample_count" value="{spp}"/>
+            <integer name="seed" value="{seed}"/>
+        </sampler>
+        <film type="hdrfilm">
+            <integer name="width" value="{width}"/>
+            <integer name="height" value="{height}"/>
+            {rfilter}
+            <string name="pixel_format" value="rgb"/>
+            <string name="component_format" value="float32"/>
+            <string name="file_format" value="pfm"/>
+        </film>
+    </sensor>
+    {bsdfs}
+    {shapes}
+</scene>
+"""
+
+CBOX_BSDFS = {
+    "box": (0.45, 0.30, 0.90), "white": (0.885809, 0.698859, 0.666422),
+    "red": (0.570068, 0.0430135, 0.0443706), "green": (0.105421, 0.37798, 0.076425),
+    "light": (0.936461, 0.740433, 0.705267),
+}
+CBOX_RADIANCE = (18.387, 10.9873, 2.75357)
+
+
+def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
+             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0):
+    """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
+    bs = []
+    for k, v in CBOX_BSDFS.items():
+        if materials and k in materials:
+            bs.append(materials[k].replace("<bsdf ", f'<bsdf id="{k}" ', 1))
+        else:
+            bs.append(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>')
+    shapes = []
+    for fn, bsdf, tr in CBOX_SHAPES:
+        if lift and bsdf == "box":
+            tr = (0.0, float(lift), 0.0)     # float the two boxes: no face coplanar with the floor
+        t = f'<transform name="to_world"><translate x="{tr[0]}" y="{tr[1]}" z="{tr[2]}"/></transform>' if any(tr) else ""
+        em = ('<emitter type="area"><rgb name="radiance" value="18.387, 10.9873, 2.75357"/></emitter>'
+              if bsdf == "light" else "")
+        path = f"{CBOX}/meshes/{fn}"
+        if no_patch and fn == "cbox_ceiling.obj":
+            # the shipped ceiling has a second quad (f 8 7 6 5) coplanar with the first: z-fighting
+            # whose winner depends on last-ulp rounding (DESIGN.md "Float parity"). Drop it.
+            path = os.path.join(mesh_dir, fn)
+            lines = [l for l in open(f"{CBOX}/meshes/{fn}") if l.strip() != "f 8 7 6 5"]
+            open(path, "w").writelines(lines)
+        shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
+    rf = '<rfilter type="box"/>' if rfilter == "box" else '<rfilter type="gaussian"/>'
+    sp = f'<integer name="samples_per_pass" value="{samples_per_pass}"/>' if samples_per_pass else ""
+    xml = CBOX_XML.format(width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
+                          block_size=block_size, spp_pass=sp, rfilter=rf, seed=seed,
+                          bsdfs="\n    ".join(bs), shapes="\n    ".join(shapes))
+    return xml
+
+
+def run_reference(xml_fn, threads=None):
+    """xml_fn(mesh_dir) -> scene xml"""
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = DIST + ":" + env.get("LD_LIBRARY_PATH", "")
+    with tempfile.TemporaryDirectory() as td:
+        sp = os.path.join(td, "scene.xml")
+        open(sp, "w").write(xml_fn(td))
+        out = os.path.join(td, "out.pfm")
+        cmd = [os.path.join(DIST, "mitsuba"), "-m", "scalar_rgb", "-o", out, sp]
+        if threads:
+            cmd[1:1] = ["-t", str(threads)]
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True)
+        if r.returncode != 0 or not os.path.exists(out):
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("reference render failed")
+        return read_pfm(out), r.stdout + r.stderr
+
+
+DIELECTRIC = '<bsdf type="dielectric"><float name="int_ior" value="1.5"/><float name="ext_ior" value="1.0"/></bsdf>'
+ROUGH_GGX = '<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/></bsdf>'
+ROUGH_BECK = '<bsdf type="roughconductor"><float name="alpha" value="0.2"/></bsdf>'
+
+GOLDEN = {
+    # name: kwargs for cbox_xml
+    "cbox_64_spp16": dict(width=64, height=64, spp=16),
+    "cbox_256_spp16": dict(width=256, height=256, spp=16),                    # BASELINE configs[0] (C1)
+    "cbox_nopatch_256_spp16": dict(width=256, height=256, spp=16, no_patch=True),
+    "cbox_nopatch_64_spp64": dict(width=64, height=64, spp=64, no_patch=True),
+    "cbox_64_spp16_pass1": dict(width=64, height=64, spp=16, samples_per_pass=1),
+    "cbox_64_spp16_pass4": dict(width=64, height=64, spp=16, samples_per_pass=4),
+    "cbox_80x48_spp8": dict(width=80, height=48, spp=8),                      # ragged blocks
+    "cbox_64_spp16_gauss": dict(width=64, height=64, spp=16, rfilter="gaussian"),
+    "cbox_64_spp16_depth3_rr2": dict(width=64, height=64, spp=16, max_depth=3, rr_depth=2),
+    "cbox_64_spp16_bs16_seed7": dict(width=64, height=64, spp=16, block_size=16, seed=7),
+    "cbox_64_spp16_dielectric": dict(width=64, height=64, spp=16, materials={"box": DIELECTRIC}),
+    "cbox_64_spp16_dielectric_lift": dict(width=64, height=64, spp=16, materials={"box": DIELECTRIC}, lift=10.0),
+    "cbox_64_spp16_ggx": dict(width=64, height=64, spp=16, materials={"box": ROUGH_GGX}),
+    "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
+}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default=None)
+    a = ap.parse_args()
+    if not os.path.isdir(REF) or not os.path.exists(os.path.join(DIST, "mitsuba")):
+        sys.exit("needs /root/reference and oracle/_ref/dist/mitsuba (run oracle/build_ref.sh)")
+    if a.only in (None, "meshes"):
+        make_cbox_meshes()
+    info = open(os.path.join(ROOT, "oracle", "_ref", "BUILD_INFO.txt")).read().strip()
+    for name, kw in GOLDEN.items():
+        if a.only and a.only != name:
+            continue
+        img, log = run_reference(lambda td: cbox_xml(mesh_dir=td, **kw))
+        kw_s = {k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in v.items()}) for k, v in kw.items()}
+        np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), rgb=img, params=np.array(repr(kw_s)),
+                            oracle_build=np.array(info))
+        print(f"ref_{name}.npz", img.shape, "mean", img.mean(axis=(0, 1)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""The golden cases of tests/golden/ (rendered by the unmodified reference) and how to
+rebuild each scene + render parameters on our side."""
+import ast
+import os
+
+import numpy as np
+
+from mitsuba2_b200 import abi, scenes
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden")
+
+
+def _materials(spec):
+    if not spec:
+        return None
+    out = {}
+    for name, xml in spec.items():
+        if 'type="dielectric"' in xml:
+            out[name] = lambda sb: sb.add_dielectric(1.5, 1.0)
+        elif 'value="ggx"' in xml:
+            out[name] = lambda sb: sb.add_roughconductor(alpha=0.1, distribution="ggx")
+        else:
+            out[name] = lambda sb: sb.add_roughconductor(alpha=0.2, distribution="beckmann")
+    return out
+
+
+def nopatch_meshes():
+    """cbox meshes without the coplanar ceiling patch quad (faces 2,3 of mesh 2)."""
+    z = dict(np.load(os.path.join(GOLDEN, "cbox_meshes.npz")))
+    z["m2_faces"] = z["m2_faces"][:2]
+    path = os.path.join(GOLDEN, "_cbox_meshes_nopatch.npz")
+    np.savez(path, **z)
+    return path
+
+
+def load(name, host):
+    """-> (SceneBuffers, B2RenderParams, reference rgb image)"""
+    z = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
+    kw = ast.literal_eval(str(z["params"]))
+    sb = scenes.cbox(host, kw["width"], kw["height"], rfilter=kw.get("rfilter", "box"),
+                     materials=_materials(kw.get("materials")),
+                     meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0))
+    rp = abi.render_params(max_depth=kw.get("max_depth", 6), rr_depth=kw.get("rr_depth", 5), spp=kw["spp"],
+                           samples_per_pass=kw.get("samples_per_pass") or 0, block_size=kw.get("block_size", 32),
+                           seed=kw.get("seed", 0))
+    return sb, rp, z["rgb"]
+
+
+def names():
+    return sorted(f[4:-4] for f in os.listdir(GOLDEN) if f.startswith("ref_") and f.endswith(".npz"))
+
+
+def parity_stats(rgb, ref):
+    """rel-L2 plus flip-robust statistics (DESIGN.md 'Float parity')."""
+    rgb = np.asarray(rgb, np.float64); ref = np.asarray(ref, np.float64)
+    d = np.abs(rgb - ref).max(axis=2)
+    rel = np.abs(rgb - ref) / np.maximum(np.abs(ref), 1e-3 * ref.mean())
+    flipped = d > 1e-3 * ref.mean()
+    clean = ~flipped
+    return dict(rel_l2=float(np.linalg.norm(rgb - ref) / np.linalg.norm(ref)),
+                rel_l2_unflipped=float(np.linalg.norm((rgb - ref)[clean]) / np.linalg.norm(ref[clean])),
+                median_rel=float(np.median(rel)), p99_rel=float(np.percentile(rel, 99)),
+                flipped_pixels=int(flipped.sum()), pixels=int(d.size), max_abs=float(d.max()))
