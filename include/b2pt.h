@@ -152,7 +152,11 @@ typedef struct B2RenderParams {
     uint32_t lane_slots;        /* wavefront width (0 = auto)                                  */
     uint64_t seed;              /* sampler 'seed' (m_base_seed)                                */
     int32_t rank, world_size;   /* this process renders spiral blocks b with b % world == rank */
+    uint32_t flags;             /* B2_FLAG_* */
+    uint32_t _pad;
 } B2RenderParams;
+
+#define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */
 
 typedef struct B2Stats {
     uint64_t n_samples;         /* camera samples put on the film                              */

@@ -13,6 +13,7 @@ BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL = range(4)
 MF_BECKMANN, MF_GGX = 0, 1
 EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT = range(3)
 FILTER_RESOLUTION = 31
+FLAG_STAGE_TIMING = 1
 
 
 class B2Bsdf(C.Structure):
@@ -86,6 +87,7 @@ class B2RenderParams(C.Structure):
         ("block_size", C.c_uint32), ("lane_slots", C.c_uint32),
         ("seed", C.c_uint64),
         ("rank", C.c_int32), ("world_size", C.c_int32),
+        ("flags", C.c_uint32), ("_pad", C.c_uint32),
     ]
 
 
@@ -111,8 +113,9 @@ def uptr(a):
 
 
 def render_params(max_depth=6, rr_depth=5, spp=16, samples_per_pass=0, block_size=32, seed=0,
-                  rank=0, world_size=1, lane_slots=0):
-    return B2RenderParams(max_depth, rr_depth, spp, samples_per_pass, block_size, lane_slots, seed, rank, world_size)
+                  rank=0, world_size=1, lane_slots=0, flags=0):
+    return B2RenderParams(max_depth, rr_depth, spp, samples_per_pass, block_size, lane_slots, seed, rank, world_size,
+                          flags, 0)
 
 
 class SceneBuffers:

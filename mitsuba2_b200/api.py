@@ -1,0 +1,207 @@
+"""Python binding of the C-ABI (include/b2pt.h) — thin ctypes layer, no compute here.
+
+Mirrors the reference's host-side interface for the path (same names / meaning):
+  Host                    Transform::look_at, parse_fov, perspective_projection, rfilters
+  Scene(desc)             Scene::Scene + accel_init      (src/librender/scene.cpp:22-103)
+  PathIntegrator.render   SamplingIntegrator::render      (src/librender/integrator.cpp:51)
+  Scene.ray_intersect_preliminary / ray_test             (include/mitsuba/render/scene.h:38-128)
+The CUDA library has no CPU fallback: loading works without a GPU (host helpers, symbol
+checks), every compute call raises B2Error(B2_ERR_NO_DEVICE) when no device is present.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import abi
+
+_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_DIR, "libb2pt.so")
+_LIB = None
+
+EXPORTS = [
+    "b2_scene_create", "b2_scene_destroy", "b2_last_error", "b2_device_count", "b2_render", "b2_render_device",
+    "b2_cancel", "b2_develop", "b2_set_stream", "b2_stage_raygen", "b2_stage_intersect", "b2_stage_occluded",
+    "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
+    "b2_host_film_gaussian", "b2_host_spiral",
+]
+
+
+class B2Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"[b2pt error {code}] {msg}")
+        self.code = code
+
+
+def build(force=False):
+    """Compile libb2pt.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    src = os.path.join(_DIR, "csrc")
+    if force:
+        subprocess.run(["make", "-C", src, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", src], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("libb2pt build failed:\n" + r.stdout + r.stderr)
+    return LIB_PATH
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2Error(-1, f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.b2_last_error.restype = C.c_char_p
+        L.b2_host_parse_fov.restype = C.c_float
+        L.b2_host_parse_fov.argtypes = [C.c_float, C.c_char_p, C.c_int, C.c_int]
+        L.b2_host_perspective_sensor.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_float, C.c_float,
+                                                 C.POINTER(abi.B2Film), C.POINTER(abi.B2Sensor)]
+        L.b2_host_film_gaussian.argtypes = [C.c_int, C.c_int, C.c_float, C.POINTER(abi.B2Film)]
+        L.b2_host_film_box.argtypes = [C.c_int, C.c_int, C.POINTER(abi.B2Film)]
+        L.b2_host_spiral.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
+        L.b2_scene_create.argtypes = [C.POINTER(abi.B2SceneDesc), C.POINTER(C.c_void_p)]
+        L.b2_scene_destroy.argtypes = [C.c_void_p]
+        L.b2_render.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.c_void_p, C.POINTER(abi.B2Stats)]
+        L.b2_render_device.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.POINTER(C.c_void_p),
+                                       C.POINTER(abi.B2Stats)]
+        L.b2_cancel.argtypes = [C.c_void_p]
+        L.b2_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2_stage_raygen.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2_stage_intersect.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2_stage_occluded.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.b2_stage_si_fill.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB = L
+    return _LIB
+
+
+def _check(rc):
+    if rc != 0:
+        raise B2Error(rc, lib().b2_last_error().decode())
+
+
+def device_count():
+    return lib().b2_device_count()
+
+
+class Host:
+    """b2_host_*: C++ mirrors of the reference's host-side sensor / film / spiral setup."""
+
+    def look_at(self, origin, target, up):
+        out = (C.c_float * 16)()
+        _check(lib().b2_host_look_at((C.c_float * 3)(*origin), (C.c_float * 3)(*target), (C.c_float * 3)(*up), out))
+        return out
+
+    def parse_fov(self, fov, axis, w, h):
+        return lib().b2_host_parse_fov(fov, axis.encode(), w, h)
+
+    def film_box(self, w, h):
+        f = abi.B2Film(); _check(lib().b2_host_film_box(w, h, C.byref(f))); return f
+
+    def film_gaussian(self, w, h, stddev=0.5):
+        f = abi.B2Film(); _check(lib().b2_host_film_gaussian(w, h, stddev, C.byref(f))); return f
+
+    def perspective_sensor(self, to_world, fov_x, near, far, film):
+        s = abi.B2Sensor()
+        _check(lib().b2_host_perspective_sensor(to_world, fov_x, near, far, C.byref(film), C.byref(s)))
+        return s
+
+    def spiral(self, w, h, bs):
+        n = C.c_uint32()
+        _check(lib().b2_host_spiral(w, h, bs, C.byref(n), None))
+        order = np.zeros((n.value, 2), np.int32)
+        _check(lib().b2_host_spiral(w, h, bs, C.byref(n), order.ctypes.data))
+        return order
+
+
+class Scene:
+    """Device-resident scene (BVH + SoA triangles + materials). Wraps b2_scene_create."""
+
+    def __init__(self, scene_buffers):
+        self.sb = scene_buffers
+        self._desc = scene_buffers.desc()
+        self._h = C.c_void_p()
+        _check(lib().b2_scene_create(C.byref(self._desc), C.byref(self._h)))
+        self.height, self.width = scene_buffers.film.crop_size[1], scene_buffers.film.crop_size[0]
+
+    def close(self):
+        if self._h:
+            lib().b2_scene_destroy(self._h); self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- Scene::ray_intersect_preliminary / ray_test (stage API, host arrays) -----------------
+    def ray_intersect_preliminary(self, ray_o, ray_d):
+        ray_o = np.ascontiguousarray(ray_o, np.float32); ray_d = np.ascontiguousarray(ray_d, np.float32)
+        n = len(ray_o)
+        hit = np.zeros((n, 4), np.float32)
+        _check(lib().b2_stage_intersect(self._h, n, ray_o.ctypes.data, ray_d.ctypes.data, hit.ctypes.data, None))
+        return hit
+
+    def ray_test(self, ray_o, ray_d):
+        ray_o = np.ascontiguousarray(ray_o, np.float32); ray_d = np.ascontiguousarray(ray_d, np.float32)
+        n = len(ray_o)
+        occ = np.zeros(n, np.uint8)
+        _check(lib().b2_stage_occluded(self._h, n, ray_o.ctypes.data, ray_d.ctypes.data, occ.ctypes.data))
+        return occ.astype(bool)
+
+    def compute_surface_interaction(self, ray_o, ray_d, hit):
+        ray_o = np.ascontiguousarray(ray_o, np.float32); ray_d = np.ascontiguousarray(ray_d, np.float32)
+        hit = np.ascontiguousarray(hit, np.float32)
+        n = len(ray_o)
+        si = np.zeros((n, 16), np.float32)
+        _check(lib().b2_stage_si_fill(self._h, n, ray_o.ctypes.data, ray_d.ctypes.data, hit.ctypes.data, None, si.ctypes.data))
+        return si
+
+    def sample_camera_rays(self, px, py, seed_offset, base_seed=0):
+        px = np.ascontiguousarray(px, np.uint32); py = np.ascontiguousarray(py, np.uint32)
+        so = np.ascontiguousarray(seed_offset, np.uint64)
+        n = len(px)
+        ro = np.zeros((n, 4), np.float32); rd = np.zeros((n, 4), np.float32)
+        rng = np.zeros(n, np.uint64); pos = np.zeros((n, 2), np.float32)
+        _check(lib().b2_stage_raygen(self._h, n, px.ctypes.data, py.ctypes.data, so.ctypes.data, base_seed,
+                                     ro.ctypes.data, rd.ctypes.data, rng.ctypes.data, pos.ctypes.data))
+        return ro, rd, rng, pos
+
+    def develop(self, xyzaw):
+        x = np.ascontiguousarray(xyzaw, np.float32)
+        rgb = np.zeros((self.height, self.width, 3), np.float32)
+        _check(lib().b2_develop(self._h, x.ctypes.data, rgb.ctypes.data))
+        return rgb
+
+
+class PathIntegrator:
+    """PathIntegrator (src/integrators/path.cpp) + SamplingIntegrator::render driver."""
+
+    def __init__(self, max_depth=-1, rr_depth=5, samples_per_pass=0, block_size=32):
+        self.max_depth, self.rr_depth = max_depth, rr_depth
+        self.samples_per_pass, self.block_size = samples_per_pass, block_size
+        self.stats = None
+
+    def params(self, spp, seed=0, rank=0, world_size=1, lane_slots=0, flags=0):
+        return abi.render_params(self.max_depth, self.rr_depth, spp, self.samples_per_pass, self.block_size, seed,
+                                 rank, world_size, lane_slots, flags)
+
+    def render(self, scene, spp, seed=0, rank=0, world_size=1, lane_slots=0, out=None):
+        """-> XYZAW film as float32 [H, W, 5] in HOST memory (copies inside the call)."""
+        rp = self.params(spp, seed, rank, world_size, lane_slots)
+        if out is None:
+            out = np.empty((scene.height, scene.width, 5), np.float32)
+        st = abi.B2Stats()
+        _check(lib().b2_render(scene._h, C.byref(rp), out.ctypes.data, C.byref(st)))
+        self.stats = st.as_dict()
+        return out
+
+    def render_device(self, scene, spp, seed=0, rank=0, world_size=1, lane_slots=0, flags=0):
+        """-> device pointer (int) of the XYZAW film; film stays in HBM."""
+        rp = self.params(spp, seed, rank, world_size, lane_slots, flags)
+        st = abi.B2Stats(); ptr = C.c_void_p()
+        _check(lib().b2_render_device(scene._h, C.byref(rp), C.byref(ptr), C.byref(st)))
+        self.stats = st.as_dict()
+        return ptr.value

@@ -1,0 +1,456 @@
+// b2_api.cu — C-ABI implementation (include/b2pt.h): scene flattening + upload, the wavefront
+// driver loop, and the stage-level entry points. There is NO CPU fallback: without a CUDA
+// device every compute entry point fails with B2_ERR_NO_DEVICE.
+#include "../../include/b2pt.h"
+#include "b2_bvh.h"
+#include "b2_kernels.cuh"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? B2_ERR_NO_DEVICE : B2_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T> struct DBuf {
+    T *p = nullptr; size_t n = 0;
+    ~DBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+    cudaError_t upload(const std::vector<T> &h) {
+        cudaError_t e = alloc(h.size());
+        if (e != cudaSuccess || h.empty()) return e;
+        return cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+    }
+};
+
+}  // namespace
+
+struct B2Scene {
+    DScene d{};
+    DBuf<float4> nodes, tri_pos, tri_nrm;
+    DBuf<B2Bsdf> bsdfs;
+    DBuf<DEmitter> emitters;
+    DBuf<float> cdf;
+    DBuf<uint32_t> prim_to_slot;
+    uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
+    int smem_bytes = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::atomic<int> cancel{0};
+    // render state (allocated lazily, reused across renders)
+    DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c;
+    DBuf<uint4> st;
+    DBuf<float2> pos;
+    DBuf<uint32_t> list0, list1, new_list, cnt, item_pixel, item_seed;
+    DBuf<unsigned long long> stats;
+    DBuf<float> film;
+    uint32_t *h_cnt = nullptr;           // pinned readback
+    float *h_film = nullptr; size_t h_film_n = 0;   // pinned staging for b2_render
+    ~B2Scene() {
+        if (h_cnt) cudaFreeHost(h_cnt);
+        if (h_film) cudaFreeHost(h_film);
+    }
+};
+
+extern "C" {
+
+const char *b2_last_error(void) { return g_error.c_str(); }
+
+int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// --------------------------------------------------------------------------------------------
+// Scene flattening: what Scene::Scene / accel_init do on the reference side (scene.cpp:22-103)
+// --------------------------------------------------------------------------------------------
+int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
+    if (!desc || !out) return fail(B2_ERR_INVALID, "b2_scene_create: null argument");
+    *out = nullptr;
+    if (b2_device_count() == 0) return fail(B2_ERR_NO_DEVICE, "b2_scene_create: no CUDA device (libb2pt has no CPU fallback)");
+    if (desc->n_instances || desc->n_groups) return fail(B2_ERR_INVALID, "instancing is not supported yet");
+    for (uint32_t e = 0; e < desc->n_emitters; ++e)
+        if (desc->emitters[e].type != B2_EMITTER_AREA) return fail(B2_ERR_INVALID, "emitter %u: only area emitters are supported", e);
+    for (uint32_t m = 0; m < desc->n_meshes; ++m) {
+        const B2Mesh &me = desc->meshes[m];
+        if (me.bsdf < 0 || (uint32_t) me.bsdf >= desc->n_bsdfs) return fail(B2_ERR_INVALID, "mesh %u: bad bsdf index", m);
+        if (me.emitter >= (int32_t) desc->n_emitters) return fail(B2_ERR_INVALID, "mesh %u: bad emitter index", m);
+        for (uint32_t f = 0; f < 3 * me.n_faces; ++f)
+            if (me.faces[f] >= me.n_vertices) return fail(B2_ERR_INVALID, "mesh %u: face index out of range", m);
+    }
+    if (desc->film.crop_size[0] <= 0 || desc->film.crop_size[1] <= 0 || desc->film.crop_size[0] > 65535 || desc->film.crop_size[1] > 65535)
+        return fail(B2_ERR_INVALID, "film crop size must be in [1, 65535]");
+
+    B2Scene *s = new B2Scene();
+    std::vector<uint32_t> mesh_first(desc->n_meshes + 1, 0);
+    uint32_t nt = 0;
+    for (uint32_t m = 0; m < desc->n_meshes; ++m) { mesh_first[m] = nt; nt += desc->meshes[m].n_faces; }
+    mesh_first[desc->n_meshes] = nt;
+    if (nt >= (1u << 27)) { delete s; return fail(B2_ERR_INVALID, "too many triangles (%u)", nt); }
+
+    std::vector<B2BvhTri> tris(nt);
+    for (uint32_t m = 0; m < desc->n_meshes; ++m) {
+        const B2Mesh &me = desc->meshes[m];
+        for (uint32_t f = 0; f < me.n_faces; ++f)
+            for (int v = 0; v < 3; ++v)
+                std::memcpy(tris[mesh_first[m] + f].p[v], me.positions + 3 * (size_t) me.faces[3 * f + v], 12);
+    }
+    B2Bvh4 bvh; b2_build_bvh4(tris, bvh);
+
+    std::vector<float4> tri_pos(3 * (size_t) nt), tri_nrm(3 * (size_t) nt);
+    std::vector<uint32_t> prim_to_slot(nt);
+    auto u2f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
+    for (uint32_t slot = 0; slot < nt; ++slot) {
+        uint32_t prim = bvh.order[slot];
+        prim_to_slot[prim] = slot;
+        uint32_t m = (uint32_t) (std::upper_bound(mesh_first.begin(), mesh_first.end(), prim) - mesh_first.begin()) - 1;
+        const B2Mesh &me = desc->meshes[m];
+        uint32_t f = prim - mesh_first[m];
+        const float wpos[3] = { u2f(prim), u2f(m), 0.f };
+        const float wnrm[3] = { u2f((uint32_t) me.bsdf), u2f((uint32_t) me.emitter), u2f(me.normals ? 1u : 0u) };
+        for (int v = 0; v < 3; ++v) {
+            const float *p = me.positions + 3 * (size_t) me.faces[3 * f + v];
+            tri_pos[3 * (size_t) slot + v] = make_float4(p[0], p[1], p[2], wpos[v]);
+            if (me.normals) {
+                const float *n = me.normals + 3 * (size_t) me.faces[3 * f + v];
+                tri_nrm[3 * (size_t) slot + v] = make_float4(n[0], n[1], n[2], wnrm[v]);
+            } else
+                tri_nrm[3 * (size_t) slot + v] = make_float4(0.f, 0.f, 0.f, wnrm[v]);
+        }
+    }
+    // emitters: Mesh::build_pmf (mesh.cpp:285-312) + DiscreteDistribution::update (distr_1d.h:49-90)
+    std::vector<DEmitter> ems(desc->n_emitters);
+    std::vector<float> cdf;
+    for (uint32_t e = 0; e < desc->n_emitters; ++e) {
+        const B2Emitter &src = desc->emitters[e];
+        if (src.mesh < 0 || (uint32_t) src.mesh >= desc->n_meshes) { delete s; return fail(B2_ERR_INVALID, "emitter %u: bad mesh index", e); }
+        const B2Mesh &me = desc->meshes[src.mesh];
+        if (me.n_faces == 0) { delete s; return fail(B2_ERR_INVALID, "Cannot create sampling table for an empty mesh"); }
+        DEmitter &d = ems[e];
+        d.type = src.type; d.mesh = src.mesh;
+        std::memcpy(d.radiance, src.radiance, 12);
+        d.first_prim = mesh_first[src.mesh]; d.n_faces = me.n_faces; d.cdf_offset = (uint32_t) cdf.size();
+        double sum = 0.0; d.valid_first = 0xffffffffu; d.valid_last = 0;
+        for (uint32_t f = 0; f < me.n_faces; ++f) {
+            const B2BvhTri &t = tris[d.first_prim + f];
+            float e0[3], e1[3];
+            for (int k = 0; k < 3; ++k) { e0[k] = t.p[1][k] - t.p[0][k]; e1[k] = t.p[2][k] - t.p[0][k]; }
+            float c[3] = { std::fma(e0[1], e1[2], -(e0[2] * e1[1])), std::fma(e0[2], e1[0], -(e0[0] * e1[2])),
+                           std::fma(e0[0], e1[1], -(e0[1] * e1[0])) };
+            float area = 0.5f * std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);   // mesh.h:108-116
+            sum += (double) area;
+            cdf.push_back((float) sum);
+            if (area > 0.f) { if (d.valid_first == 0xffffffffu) d.valid_first = f; d.valid_last = f; }
+        }
+        if (d.valid_first == 0xffffffffu) { delete s; return fail(B2_ERR_INVALID, "DiscreteDistribution: no probability mass found!"); }
+        d.cdf_sum = (float) sum; d.cdf_norm = (float) (1.0 / sum);
+    }
+    std::vector<B2Bsdf> bsdfs(desc->bsdfs, desc->bsdfs + desc->n_bsdfs);
+    std::vector<float4> nodes(bvh.nodes.size() / 4);
+    std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(float));
+
+    cudaError_t e = cudaSuccess;
+    if ((e = s->nodes.upload(nodes)) != cudaSuccess || (e = s->tri_pos.upload(tri_pos)) != cudaSuccess ||
+        (e = s->tri_nrm.upload(tri_nrm)) != cudaSuccess || (e = s->bsdfs.upload(bsdfs)) != cudaSuccess ||
+        (e = s->emitters.upload(ems)) != cudaSuccess || (e = s->cdf.upload(cdf)) != cudaSuccess ||
+        (e = s->prim_to_slot.upload(prim_to_slot)) != cudaSuccess) {
+        delete s;
+        return fail(B2_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
+    }
+    s->n_tris = nt; s->n_nodes = bvh.n_nodes; s->bvh_depth = bvh.depth;
+    DScene &d = s->d;
+    d.nodes = s->nodes.p; d.tri_pos = s->tri_pos.p; d.tri_nrm = s->tri_nrm.p; d.bsdfs = s->bsdfs.p;
+    d.emitters = s->emitters.p; d.cdf = s->cdf.p; d.prim_to_slot = s->prim_to_slot.p;
+    d.n_nodes = bvh.n_nodes; d.n_tris = nt; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
+    d.sensor = desc->sensor; d.film = desc->film;
+    // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
+    const uint32_t budget_all = 48 * 1024, budget_top = 32 * 1024;
+    if (bvh.n_nodes * 128u + nt * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
+    else { d.smem_nodes = std::min<uint32_t>(bvh.n_nodes, budget_top / 128u); d.smem_tris = 0; }
+    s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u));
+    int dev = 0; cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_stage_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_stage_occluded, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    *out = s;
+    return B2_OK;
+}
+
+int b2_scene_destroy(B2Scene *scene) {
+    if (!scene) return B2_OK;
+    cudaDeviceSynchronize();
+    delete scene;
+    return B2_OK;
+}
+
+int b2_set_stream(B2Scene *scene, void *stream) {
+    if (!scene) return fail(B2_ERR_INVALID, "null scene");
+    scene->stream = (cudaStream_t) stream;
+    return B2_OK;
+}
+
+int b2_cancel(B2Scene *scene) {
+    if (scene) scene->cancel.store(1);
+    return B2_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// SamplingIntegrator::render (integrator.cpp:51-179) as a wavefront loop
+// --------------------------------------------------------------------------------------------
+int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2Stats *stats) {
+    if (!s || !rp) return fail(B2_ERR_INVALID, "b2_render: null argument");
+    const B2Film &film = s->d.film;
+    uint32_t bs = rp->block_size;
+    if (bs == 0 || (bs & (bs - 1)) || bs > 256) return fail(B2_ERR_INVALID, "block_size must be a power of two in [1,256] and pinned by the caller");
+    if (rp->spp == 0) return fail(B2_ERR_INVALID, "sample_count must be > 0");
+    uint32_t spp_pass = rp->samples_per_pass ? std::min(rp->samples_per_pass, rp->spp) : rp->spp;
+    if (rp->spp % spp_pass) return fail(B2_ERR_INVALID, "sample_count (%u) must be a multiple of samples_per_pass (%u).", rp->spp, spp_pass);   // integrator.cpp:62-64
+    if (spp_pass > 65535) return fail(B2_ERR_INVALID, "samples_per_pass must be <= 65535");
+    uint32_t n_passes = rp->spp / spp_pass;
+    int W = film.crop_size[0], H = film.crop_size[1];
+    int world = rp->world_size > 0 ? rp->world_size : 1, rank = rp->rank;
+    if (rank < 0 || rank >= world) return fail(B2_ERR_INVALID, "bad rank/world_size");
+    s->cancel.store(0);
+    cudaStream_t stream = s->stream;
+
+    // work-item table of one pass: this rank's blocks in spiral order, Morton order inside a block
+    uint32_t n_blocks = 0;
+    b2_host_spiral(W, H, (int) bs, &n_blocks, nullptr);
+    std::vector<int32_t> order(2 * (size_t) n_blocks);
+    b2_host_spiral(W, H, (int) bs, &n_blocks, order.data());
+    std::vector<uint32_t> item_pixel, item_seed;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        if ((int) (b % (uint32_t) world) != rank) continue;
+        int ox = order[2 * b] * (int) bs, oy = order[2 * b + 1] * (int) bs;
+        int bw = std::min((int) bs, W - ox), bh = std::min((int) bs, H - oy);
+        // enumerate Morton indices in increasing order, skipping pixels outside (integrator.cpp:200-202)
+        for (uint32_t i = 0; i < bs * bs; ++i) {
+            uint32_t mx = 0, my = 0;
+            for (uint32_t bit = 0; bit < 16; ++bit) { mx |= ((i >> (2 * bit)) & 1u) << bit; my |= ((i >> (2 * bit + 1)) & 1u) << bit; }
+            if ((int) mx >= bw || (int) my >= bh) continue;
+            item_pixel.push_back((uint32_t) (ox + (int) mx) | ((uint32_t) (oy + (int) my) << 16));
+            item_seed.push_back(b * bs * bs + i);
+        }
+    }
+    uint64_t total64 = (uint64_t) item_pixel.size() * n_passes;
+    uint32_t n_items_pass = (uint32_t) item_pixel.size();
+    uint32_t slots = rp->lane_slots ? rp->lane_slots : (1u << 22);
+    if ((uint64_t) slots > total64) slots = (uint32_t) std::max<uint64_t>(total64, 1);
+    slots = (slots + 31u) & ~31u;
+    if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
+
+    bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
+    CU(s->ray_o.alloc(slots)); CU(s->ray_d.alloc(slots)); CU(s->hit.alloc(slots)); CU(s->tp.alloc(slots)); CU(s->res.alloc(slots));
+    CU(s->sh_o.alloc(slots)); CU(s->sh_d.alloc(slots)); CU(s->sh_c.alloc(slots)); CU(s->st.alloc(slots));
+    if (wide) CU(s->pos.alloc(slots));
+    CU(s->list0.alloc(slots)); CU(s->list1.alloc(slots)); CU(s->new_list.alloc(slots));
+    CU(s->cnt.alloc(16)); CU(s->stats.alloc(8));
+    CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
+    CU(s->film.alloc((size_t) W * H * 5));
+    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 16 * sizeof(uint32_t)));
+
+    Queues q{};
+    q.ray_o = s->ray_o.p; q.ray_d = s->ray_d.p; q.hit = s->hit.p; q.tp = s->tp.p; q.res = s->res.p; q.st = s->st.p;
+    q.pos = wide ? s->pos.p : nullptr;
+    q.sh_o = s->sh_o.p; q.sh_d = s->sh_d.p; q.sh_c = s->sh_c.p;
+    q.list[0] = s->list0.p; q.list[1] = s->list1.p; q.new_list = s->new_list.p; q.cnt = s->cnt.p; q.stats = s->stats.p;
+    q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
+    q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
+    q.total_items = (uint32_t) total64; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
+
+    cudaEvent_t ev0, ev1, evb[2];
+    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
+    CU(cudaEventCreateWithFlags(&evb[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&evb[1], cudaEventDisableTiming));
+    CU(cudaEventRecord(ev0, stream));
+    CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
+    CU(cudaMemsetAsync(s->cnt.p, 0, 16 * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(s->st.p, 0, (size_t) slots * sizeof(uint4), stream));
+    {   // new_list = iota, cnt[NEW] = slots
+        std::vector<uint32_t> iota(slots);
+        for (uint32_t i = 0; i < slots; ++i) iota[i] = i;
+        CU(cudaMemcpyAsync(s->new_list.p, iota.data(), slots * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        CU(cudaMemcpyAsync(s->cnt.p + CNT_NEW, &slots, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        CU(cudaStreamSynchronize(stream));
+    }
+    const int threads = 256;
+    int grid = s->sm_count * 8;
+    uint32_t need_blocks = (slots + threads - 1) / threads;
+    if ((uint32_t) grid > need_blocks) grid = (int) std::max<uint32_t>(need_blocks, 1);
+    int cur = 0;
+    uint64_t iterations = 0, launches = 0;
+    const int batch = 8;
+    const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
+    std::vector<cudaEvent_t> tev;     // 5 events per iteration when stage timing is on
+    auto tick = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); tev.push_back(e); } };
+    int pending[2] = { 0, 0 };
+    bool done = false;
+    int status = B2_OK;
+    for (int b = 0; !done; ++b) {
+        int slot = b & 1;
+        for (int it = 0; it < batch; ++it) {
+            tick();
+            k_regen<<<grid, threads, 0, stream>>>(s->d, q, cur);
+            tick();
+            k_intersect<<<grid, threads, s->smem_bytes, stream>>>(s->d, q, cur);
+            tick();
+            k_shade<<<grid, threads, 0, stream>>>(s->d, q, cur);
+            tick();
+            k_shadow<<<grid, threads, s->smem_bytes, stream>>>(s->d, q);
+            tick();
+            cur ^= 1; ++iterations; launches += 4;
+        }
+        CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CU(cudaEventRecord(evb[slot], stream));
+        pending[slot] = 1;
+        // wait for the PREVIOUS batch's readback so the GPU always has one batch queued
+        int prev = slot ^ 1;
+        if (pending[prev]) {
+            CU(cudaEventSynchronize(evb[prev]));
+            pending[prev] = 0;
+            const uint32_t *c = s->h_cnt + 16 * prev;
+            if (c[CNT_LIST0] == 0 && c[CNT_LIST1] == 0 && c[CNT_NEW] == 0) done = true;
+        }
+        if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
+        if (cudaPeekAtLastError() != cudaSuccess) break;
+    }
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(ev1, stream));
+    CU(cudaEventSynchronize(ev1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev0, ev1));
+    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evb[0]); cudaEventDestroy(evb[1]);
+    if (stats) {
+        unsigned long long h[8];
+        CU(cudaMemcpy(h, s->stats.p, sizeof h, cudaMemcpyDeviceToHost));
+        std::memset(stats, 0, sizeof *stats);
+        stats->n_samples = h[ST_SAMPLES]; stats->n_segments = h[ST_SEGMENTS]; stats->n_shadow_rays = h[ST_SHADOW];
+        stats->n_invalid = h[ST_INVALID]; stats->n_iterations = iterations; stats->n_launches = launches;
+        stats->ms_total = ms; stats->bvh_nodes = s->n_nodes; stats->bvh_tris = s->n_tris;
+        for (size_t i = 0; i + 4 < tev.size(); i += 5) {
+            float t[4];
+            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[i + k], tev[i + k + 1]);
+            stats->ms_regen += t[0]; stats->ms_intersect += t[1]; stats->ms_shade += t[2]; stats->ms_shadow += t[3];
+        }
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    if (d_xyzaw) *d_xyzaw = s->film.p;
+    if (status == B2_ERR_CANCELLED) return fail(status, "render cancelled");
+    return status;
+}
+
+int b2_render(B2Scene *s, const B2RenderParams *rp, float *xyzaw, B2Stats *stats) {
+    if (!xyzaw) return fail(B2_ERR_INVALID, "b2_render: null output");
+    float *d = nullptr;
+    int rc = b2_render_device(s, rp, &d, stats);
+    if (rc != B2_OK) return rc;
+    size_t n = (size_t) s->d.film.crop_size[0] * s->d.film.crop_size[1] * 5;
+    CU(cudaMemcpyAsync(xyzaw, d, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return B2_OK;
+}
+
+int b2_develop(B2Scene *s, const float *xyzaw, float *rgb) {
+    if (!s || !xyzaw || !rgb) return fail(B2_ERR_INVALID, "b2_develop: null argument");
+    int n = s->d.film.crop_size[0] * s->d.film.crop_size[1];
+    DBuf<float> in, out;
+    CU(in.alloc((size_t) n * 5)); CU(out.alloc((size_t) n * 3));
+    CU(cudaMemcpy(in.p, xyzaw, (size_t) n * 5 * sizeof(float), cudaMemcpyHostToDevice));
+    k_develop<<<(n + 255) / 256, 256, 0, s->stream>>>(in.p, out.p, n);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(rgb, out.p, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// stage-level entry points
+// --------------------------------------------------------------------------------------------
+int b2_stage_raygen(B2Scene *s, uint32_t n, const uint32_t *px, const uint32_t *py, const uint64_t *seed_offset,
+                    uint64_t base_seed, float *ray_o, float *ray_d, uint64_t *rng_state, float *pos) {
+    if (!s || (n && (!px || !py || !seed_offset || !ray_o || !ray_d || !rng_state || !pos))) return fail(B2_ERR_INVALID, "b2_stage_raygen: null argument");
+    if (n == 0) return B2_OK;
+    DBuf<uint32_t> dx, dy; DBuf<uint64_t> ds, dr; DBuf<float4> o, d; DBuf<float2> p;
+    CU(dx.alloc(n)); CU(dy.alloc(n)); CU(ds.alloc(n)); CU(dr.alloc(n)); CU(o.alloc(n)); CU(d.alloc(n)); CU(p.alloc(n));
+    CU(cudaMemcpy(dx.p, px, n * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dy.p, py, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ds.p, seed_offset, n * 8, cudaMemcpyHostToDevice));
+    k_stage_raygen<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, dx.p, dy.p, ds.p, base_seed, o.p, d.p, dr.p, p.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(ray_o, o.p, n * 16, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(ray_d, d.p, n * 16, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(rng_state, dr.p, n * 8, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(pos, p.p, n * 8, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+static int stage_grid(const B2Scene *s, uint32_t n) {
+    uint32_t need = (n + 255) / 256;
+    return (int) std::max<uint32_t>(1, std::min<uint32_t>(need, (uint32_t) s->sm_count * 8));
+}
+
+int b2_stage_intersect(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, float *hit, int32_t *inst) {
+    if (!s || (n && (!ray_o || !ray_d || !hit))) return fail(B2_ERR_INVALID, "b2_stage_intersect: null argument");
+    if (n == 0) return B2_OK;
+    DBuf<float4> o, d, h;
+    CU(o.alloc(n)); CU(d.alloc(n)); CU(h.alloc(n));
+    CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice));
+    k_stage_intersect<<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(hit, h.p, n * 16, cudaMemcpyDeviceToHost));
+    if (inst) for (uint32_t i = 0; i < n; ++i) inst[i] = -1;
+    return B2_OK;
+}
+
+int b2_stage_occluded(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, uint8_t *occluded) {
+    if (!s || (n && (!ray_o || !ray_d || !occluded))) return fail(B2_ERR_INVALID, "b2_stage_occluded: null argument");
+    if (n == 0) return B2_OK;
+    DBuf<float4> o, d; DBuf<uint8_t> r;
+    CU(o.alloc(n)); CU(d.alloc(n)); CU(r.alloc(n));
+    CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice));
+    k_stage_occluded<<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(occluded, r.p, n, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+int b2_stage_si_fill(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, const float *hit, const int32_t *inst, float *si) {
+    (void) ray_o; (void) inst;
+    if (!s || (n && (!ray_d || !hit || !si))) return fail(B2_ERR_INVALID, "b2_stage_si_fill: null argument");
+    if (n == 0) return B2_OK;
+    DBuf<float4> d, h; DBuf<float> out;
+    CU(d.alloc(n)); CU(h.alloc(n)); CU(out.alloc((size_t) n * 16));
+    CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(h.p, hit, n * 16, cudaMemcpyHostToDevice));
+    k_stage_si_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, d.p, h.p, out.p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(si, out.p, (size_t) n * 64, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+}  // extern "C"

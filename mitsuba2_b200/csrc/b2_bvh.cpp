@@ -1,0 +1,157 @@
+// b2_bvh.cpp — see b2_bvh.h
+#include "b2_bvh.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+namespace {
+
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int k = 0; k < 3; ++k) { lo[k] = std::numeric_limits<float>::infinity(); hi[k] = -lo[k]; } }
+    void grow(const Box &b) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+    void grow(const float *p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+    float area() const {
+        float d[3] = { hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2] };
+        if (d[0] < 0) return 0.f;
+        return 2.f * (d[0] * d[1] + d[1] * d[2] + d[2] * d[0]);
+    }
+};
+
+struct Node2 { Box box; int left = -1, right = -1; uint32_t first = 0, count = 0; };
+
+struct Builder {
+    const std::vector<B2BvhTri> &tris;
+    std::vector<Box> tbox;
+    std::vector<float> cent;        // 3 per tri
+    std::vector<uint32_t> idx;
+    std::vector<Node2> nodes;
+    static constexpr int kBins = 16, kMaxLeaf = 4;
+
+    explicit Builder(const std::vector<B2BvhTri> &t) : tris(t) {}
+
+    int build(uint32_t first, uint32_t count) {
+        int id = (int) nodes.size();
+        nodes.emplace_back();
+        Box box; box.reset();
+        Box cbox; cbox.reset();
+        for (uint32_t i = first; i < first + count; ++i) {
+            box.grow(tbox[idx[i]]);
+            cbox.grow(&cent[3 * idx[i]]);
+        }
+        nodes[id].box = box; nodes[id].first = first; nodes[id].count = count;
+        if (count <= (uint32_t) kMaxLeaf) return id;
+        // binned SAH over the 3 axes
+        float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
+        for (int ax = 0; ax < 3; ++ax) {
+            float lo = cbox.lo[ax], ext = cbox.hi[ax] - lo;
+            if (!(ext > 0.f)) continue;
+            Box bb[kBins]; uint32_t bc[kBins];
+            for (int b = 0; b < kBins; ++b) { bb[b].reset(); bc[b] = 0; }
+            float scale = kBins / ext;
+            for (uint32_t i = first; i < first + count; ++i) {
+                int b = std::min(kBins - 1, (int) ((cent[3 * idx[i] + ax] - lo) * scale));
+                bb[b].grow(tbox[idx[i]]); bc[b]++;
+            }
+            float ra[kBins]; uint32_t rc[kBins];
+            Box acc; acc.reset(); uint32_t c = 0;
+            for (int b = kBins - 1; b > 0; --b) { acc.grow(bb[b]); c += bc[b]; ra[b] = acc.area(); rc[b] = c; }
+            acc.reset(); c = 0;
+            for (int b = 0; b < kBins - 1; ++b) {
+                acc.grow(bb[b]); c += bc[b];
+                if (c == 0 || rc[b + 1] == 0) continue;
+                float cost = acc.area() * (float) c + ra[b + 1] * (float) rc[b + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
+            }
+        }
+        uint32_t mid;
+        if (best_axis < 0) {
+            mid = first + count / 2;            // all centroids coincide: split in the middle
+        } else {
+            float lo = cbox.lo[best_axis], scale = kBins / (cbox.hi[best_axis] - lo);
+            auto it = std::partition(idx.begin() + first, idx.begin() + first + count, [&](uint32_t t) {
+                int b = std::min(kBins - 1, (int) ((cent[3 * t + best_axis] - lo) * scale));
+                return b <= best_bin;
+            });
+            mid = (uint32_t) (it - idx.begin());
+            if (mid == first || mid == first + count) mid = first + count / 2;
+        }
+        int l = build(first, mid - first);
+        int r = build(mid, first + count - mid);
+        nodes[id].left = l; nodes[id].right = r; nodes[id].count = 0;
+        return id;
+    }
+};
+
+}  // namespace
+
+void b2_build_bvh4(const std::vector<B2BvhTri> &tris, B2Bvh4 &out) {
+    out.nodes.clear(); out.order.clear(); out.n_nodes = 0; out.depth = 0;
+    uint32_t n = (uint32_t) tris.size();
+    if (n == 0) {
+        out.nodes.assign(32, 0.f); out.n_nodes = 1;
+        for (int k = 0; k < 12; ++k) out.nodes[k] = std::numeric_limits<float>::infinity();
+        for (int k = 12; k < 24; ++k) out.nodes[k] = -std::numeric_limits<float>::infinity();
+        return;
+    }
+    Builder b(tris);
+    b.tbox.resize(n); b.cent.resize(3 * (size_t) n); b.idx.resize(n);
+    Box scene; scene.reset();
+    for (uint32_t i = 0; i < n; ++i) {
+        Box bx; bx.reset();
+        for (int v = 0; v < 3; ++v) bx.grow(tris[i].p[v]);
+        b.tbox[i] = bx; scene.grow(bx);
+        for (int k = 0; k < 3; ++k) b.cent[3 * (size_t) i + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
+        b.idx[i] = i;
+    }
+    b.nodes.reserve(2 * (size_t) n);
+    b.build(0, n);
+    out.order = b.idx;
+
+    // conservative inflation of every child box: the fp32 triangle test can accept hits a few
+    // ulp outside the exact bounds; 1e-5 relative + 1e-7 of the scene size covers that.
+    float diag = 0.f;
+    for (int k = 0; k < 3; ++k) diag = std::max(diag, scene.hi[k] - scene.lo[k]);
+    auto pad = [&](float v) { return 1e-5f * std::fabs(v) + 1e-7f * diag + 1e-30f; };
+
+    // collapse BVH2 -> BVH4, breadth-first
+    struct Item { int n2; };
+    std::vector<int> queue; queue.push_back(0);
+    std::vector<int> level_of; level_of.push_back(0);
+    // each queue entry becomes one BVH4 node (root may be a leaf: wrap it)
+    size_t head = 0;
+    std::vector<float> &N = out.nodes;
+    while (head < queue.size()) {
+        int n2 = queue[head]; int level = level_of[head]; ++head;
+        out.depth = std::max<uint32_t>(out.depth, (uint32_t) level + 1);
+        int kids[4]; int nk = 0;
+        if (b.nodes[n2].left < 0) kids[nk++] = n2;       // leaf root
+        else { kids[nk++] = b.nodes[n2].left; kids[nk++] = b.nodes[n2].right; }
+        while (nk < 4) {
+            int best = -1; float ba = -1.f;
+            for (int k = 0; k < nk; ++k)
+                if (b.nodes[kids[k]].left >= 0 && b.nodes[kids[k]].box.area() > ba) { ba = b.nodes[kids[k]].box.area(); best = k; }
+            if (best < 0) break;
+            int c = kids[best];
+            kids[best] = b.nodes[c].left; kids[nk++] = b.nodes[c].right;
+        }
+        size_t base = N.size(); N.resize(base + 32, 0.f);
+        const float inf = std::numeric_limits<float>::infinity();
+        for (int k = 0; k < 4; ++k) {
+            int32_t code = 0;
+            float lo[3] = { inf, inf, inf }, hi[3] = { -inf, -inf, -inf };
+            if (k < nk) {
+                const Node2 &c = b.nodes[kids[k]];
+                for (int a = 0; a < 3; ++a) { lo[a] = c.box.lo[a] - pad(c.box.lo[a]); hi[a] = c.box.hi[a] + pad(c.box.hi[a]); }
+                if (c.left < 0) code = (int32_t) (0x80000000u | (c.count << 27) | c.first);
+                else { code = (int32_t) queue.size(); queue.push_back(kids[k]); level_of.push_back(level + 1); }
+            }
+            N[base + 0 + k] = lo[0]; N[base + 4 + k] = lo[1]; N[base + 8 + k] = lo[2];
+            N[base + 12 + k] = hi[0]; N[base + 16 + k] = hi[1]; N[base + 20 + k] = hi[2];
+            std::memcpy(&N[base + 24 + k], &code, 4);
+        }
+    }
+    out.n_nodes = (uint32_t) (N.size() / 32);
+}

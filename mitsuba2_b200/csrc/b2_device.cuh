@@ -1,0 +1,406 @@
+// b2_device.cuh — device-side scene layout and the per-lane shading functions of the
+// wavefront stages (SurfaceInteraction fill, BSDFs, emitter sampling, MIS).
+// Citations are reference file:line (mitsuba2 @ 62863cb3).
+#pragma once
+#include "../../include/b2pt.h"
+#include "b2_math.cuh"
+
+// ---- scene layout in HBM --------------------------------------------------------------------
+// Triangles are stored in BVH leaf order ("slots"), two SoA streams of 3 x float4 per slot:
+//   tri_pos[3*s + 0] = (p0.xyz, prim id bits)     prim = global triangle index (mesh order, face order)
+//   tri_pos[3*s + 1] = (p1.xyz, mesh id bits)
+//   tri_pos[3*s + 2] = (p2.xyz, 0)
+//   tri_nrm[3*s + 0] = (n0.xyz, bsdf index bits)  vertex normals (mesh.h:344-348)
+//   tri_nrm[3*s + 1] = (n1.xyz, emitter index bits or -1)
+//   tri_nrm[3*s + 2] = (n2.xyz, has_normals flag bits)
+// BVH4 node = 8 x float4 = 128 B (one cache line):
+//   [0] lo.x of children 0..3   [1] lo.y   [2] lo.z   [3] hi.x   [4] hi.y   [5] hi.z
+//   [6] child[0..3] as int bits: 0 = empty, > 0 = inner node index, < 0 = leaf:
+//       first slot = c & 0x07ffffff, count = (c >> 27) & 0xf
+//   [7] unused
+struct DEmitter {
+    int32_t type, mesh;
+    float radiance[3];
+    uint32_t first_prim, n_faces, cdf_offset;
+    float cdf_sum, cdf_norm;
+    uint32_t valid_first, valid_last;
+};
+
+struct DScene {
+    const float4 *nodes;
+    const float4 *tri_pos;
+    const float4 *tri_nrm;
+    const B2Bsdf *bsdfs;
+    const DEmitter *emitters;
+    const float *cdf;
+    const uint32_t *prim_to_slot;
+    uint32_t n_nodes, n_tris, n_emitters, n_bsdfs;
+    uint32_t smem_nodes;        // nodes [0, smem_nodes) are staged in shared memory
+    uint32_t smem_tris;         // 1: all triangle positions staged in shared memory too
+    B2Sensor sensor;
+    B2Film film;
+};
+
+struct Ray { float3 o, d; float mint, maxt; };
+
+// Mesh::ray_intersect_triangle — include/mitsuba/render/mesh.h:194-226
+B2_D bool tri_intersect(float3 p0, float3 p1, float3 p2, const Ray &ray, float &t, float &u, float &v) {
+    float3 e1 = p1 - p0, e2 = p2 - p0;
+    float3 pvec = cross(ray.d, e2);
+    float inv_det = b2_rcp(dot(e1, pvec));
+    float3 tvec = ray.o - p0;
+    u = dot(tvec, pvec) * inv_det;
+    bool active = u >= 0.f && u <= 1.f;
+    float3 qvec = cross(tvec, e1);
+    v = dot(ray.d, qvec) * inv_det;
+    active &= v >= 0.f && u + v <= 1.f;
+    t = dot(e2, qvec) * inv_det;
+    active &= t >= ray.mint && t <= ray.maxt;
+    return active;
+}
+
+// ---- SurfaceInteraction (mesh.cpp:449-545, interaction.h:153-156,571-596) -------------------
+struct SI {
+    float3 p, n, sh_n, sh_s, sh_t, wi;
+    int bsdf, emitter;
+};
+
+B2_D float3 coordinate_system_s(float3 n) {        // include/mitsuba/core/vector.h:116-136 (first vector)
+    float sign = b2_sign(n.z);
+    float a = -b2_rcp(sign + n.z);
+    float b = (n.x * n.y) * a;
+    return v3(b2_mulsign(b2_sqr(n.x) * a, n.z) + 1.f, b2_mulsign(b, n.z), b2_mulsign_neg(n.x, n.z));
+}
+B2_D float3 to_local(const SI &si, float3 v) { return v3(dot(v, si.sh_s), dot(v, si.sh_t), dot(v, si.sh_n)); }
+B2_D float3 to_world(const SI &si, float3 v) { return (si.sh_s * v.x + si.sh_t * v.y) + si.sh_n * v.z; }   // frame.h:35-37
+
+B2_D void si_fill(const DScene &sc, uint32_t slot, float u, float v, float3 ray_d, SI &si) {
+    float4 a0 = __ldg(&sc.tri_pos[3 * slot]), a1 = __ldg(&sc.tri_pos[3 * slot + 1]), a2 = __ldg(&sc.tri_pos[3 * slot + 2]);
+    float4 m0 = __ldg(&sc.tri_nrm[3 * slot]), m1 = __ldg(&sc.tri_nrm[3 * slot + 1]), m2 = __ldg(&sc.tri_nrm[3 * slot + 2]);
+    float3 p0 = v3(a0), p1 = v3(a1), p2 = v3(a2);
+    float b1 = u, b2 = v, b0 = 1.f - b1 - b2;
+    float3 dp0 = p1 - p0, dp1 = p2 - p0;
+    si.p = (p0 * b0 + p1 * b1) + p2 * b2;                       // mesh.cpp:484
+    si.n = normalize(cross(dp0, dp1));                           // mesh.cpp:487
+    float3 dp_du = coordinate_system_s(si.n);                    // mesh.cpp:491
+    if (__float_as_uint(m2.w))                                   // mesh.cpp:514-519
+        si.sh_n = normalize((v3(m0) * b0 + v3(m1) * b1) + v3(m2) * b2);
+    else
+        si.sh_n = si.n;
+    si.sh_s = normalize(fnmadd(si.sh_n, dot(si.sh_n, dp_du), dp_du));   // interaction.h:153-156
+    si.sh_t = cross(si.sh_n, si.sh_s);
+    si.wi = to_local(si, -ray_d);                                // interaction.h:591
+    si.bsdf = (int) __float_as_uint(m0.w);
+    si.emitter = (int) __float_as_uint(m1.w);
+}
+
+// ---- warps (include/mitsuba/core/warp.h) -----------------------------------------------------
+B2_D void square_to_uniform_disk_concentric(float sx, float sy, float &ox, float &oy) {   // warp.h:53-90
+    float x = b2_fma(2.f, sx, -1.f), y = b2_fma(2.f, sy, -1.f);
+    bool is_zero = x == 0.f && y == 0.f, q13 = fabsf(x) < fabsf(y);
+    float r = q13 ? y : x, rp = q13 ? x : y;
+    float phi = ((.25f * B2_PI) * rp) / r;
+    if (q13) phi = .5f * B2_PI - phi;
+    if (is_zero) phi = 0.f;
+    float s, c; b2_sincos(phi, &s, &c);
+    ox = r * c; oy = r * s;
+}
+B2_D float3 square_to_cosine_hemisphere(float sx, float sy) {   // warp.h:325-333
+    float px, py; square_to_uniform_disk_concentric(sx, sy, px, py);
+    float z = b2_safe_sqrt(1.f - (px * px + py * py));
+    return v3(px, py, z);
+}
+
+// ---- Fresnel (include/mitsuba/render/fresnel.h) -----------------------------------------------
+B2_D void fresnel(float cos_theta_i, float eta, float &r_out, float &cos_theta_t_out, float &eta_it_out, float &eta_ti_out) {
+    bool outside = cos_theta_i >= 0.f;                           // fresnel.h:34-70
+    float rcp_eta = b2_rcp(eta), eta_it = outside ? eta : rcp_eta, eta_ti = outside ? rcp_eta : eta;
+    float cos_theta_t_sqr = b2_fma(-b2_fma(-cos_theta_i, cos_theta_i, 1.f), eta_ti * eta_ti, 1.f);
+    float cos_theta_i_abs = fabsf(cos_theta_i);
+    float cos_theta_t_abs = b2_safe_sqrt(cos_theta_t_sqr);
+    bool index_matched = eta == 1.f, special_case = index_matched || cos_theta_i_abs == 0.f;
+    float r_sc = index_matched ? 0.f : 1.f;
+    float a_s = b2_fma(-eta_it, cos_theta_t_abs, cos_theta_i_abs) / b2_fma(eta_it, cos_theta_t_abs, cos_theta_i_abs);
+    float a_p = b2_fma(-eta_it, cos_theta_i_abs, cos_theta_t_abs) / b2_fma(eta_it, cos_theta_i_abs, cos_theta_t_abs);
+    float r = .5f * (b2_sqr(a_s) + b2_sqr(a_p));
+    if (special_case) r = r_sc;
+    r_out = r; cos_theta_t_out = b2_mulsign_neg(cos_theta_t_abs, cos_theta_i);
+    eta_it_out = eta_it; eta_ti_out = eta_ti;
+}
+B2_D float fresnel_conductor(float cos_theta_i, float eta_r, float eta_i) {   // fresnel.h:92-116
+    float cos_theta_i_2 = cos_theta_i * cos_theta_i, sin_theta_i_2 = 1.f - cos_theta_i_2,
+          sin_theta_i_4 = sin_theta_i_2 * sin_theta_i_2;
+    float temp_1 = eta_r * eta_r - eta_i * eta_i - sin_theta_i_2,
+          a_2_pb_2 = b2_safe_sqrt(temp_1 * temp_1 + 4.f * eta_i * eta_i * eta_r * eta_r),
+          a = b2_safe_sqrt(.5f * (a_2_pb_2 + temp_1));
+    float term_1 = a_2_pb_2 + cos_theta_i_2, term_2 = 2.f * cos_theta_i * a;
+    float r_s = (term_1 - term_2) / (term_1 + term_2);
+    float term_3 = a_2_pb_2 * cos_theta_i_2 + sin_theta_i_4, term_4 = term_2 * sin_theta_i_2;
+    float r_p = r_s * (term_3 - term_4) / (term_3 + term_4);
+    return .5f * (r_s + r_p);
+}
+
+// ---- microfacet distribution (include/mitsuba/render/microfacet.h) ----------------------------
+struct MF { int type; float au, av; };
+B2_D MF mf_make(const B2Bsdf &b) {       // configure(): alpha = max(alpha, 1e-4)
+    MF m; m.type = b.distribution; m.au = b2_max(b.alpha_u, 1e-4f); m.av = b2_max(b.alpha_v, 1e-4f); return m;
+}
+B2_D float mf_eval(const MF &d, float3 m) {     // microfacet.h:184-203
+    float alpha_uv = d.au * d.av, cos_theta = m.z, cos_theta_2 = b2_sqr(cos_theta), result;
+    if (d.type == B2_MF_BECKMANN)
+        result = b2_exp(-(b2_sqr(m.x / d.au) + b2_sqr(m.y / d.av)) / cos_theta_2) / (B2_PI * alpha_uv * b2_sqr(cos_theta_2));
+    else
+        result = b2_rcp(B2_PI * alpha_uv * b2_sqr(b2_sqr(m.x / d.au) + b2_sqr(m.y / d.av) + b2_sqr(m.z)));
+    return result * cos_theta > 1e-20f ? result : 0.f;
+}
+B2_D float mf_smith_g1(const MF &d, float3 v, float3 m) {   // microfacet.h:331-355
+    float xy_alpha_2 = b2_sqr(d.au * v.x) + b2_sqr(d.av * v.y), tan_theta_alpha_2 = xy_alpha_2 / b2_sqr(v.z), result;
+    if (d.type == B2_MF_BECKMANN) {
+        float a = b2_rsqrt(tan_theta_alpha_2), a_sqr = b2_sqr(a);
+        result = a >= 1.6f ? 1.f : (3.535f * a + 2.181f * a_sqr) / (1.f + 2.276f * a + 2.577f * a_sqr);
+    } else
+        result = 2.f / (1.f + sqrtf(1.f + tan_theta_alpha_2));
+    if (xy_alpha_2 == 0.f) result = 1.f;
+    if (dot(v, m) * v.z <= 0.f) result = 0.f;
+    return result;
+}
+B2_D void mf_sample_visible_11(const MF &d, float cos_theta_i, float sx, float sy, float &ox, float &oy) {
+    if (d.type == B2_MF_BECKMANN) {                               // microfacet.h:359-394
+        float tan_theta_i = b2_safe_sqrt(b2_fma(-cos_theta_i, cos_theta_i, 1.f)) / cos_theta_i;
+        float cot_theta_i = b2_rcp(tan_theta_i);
+        float maxval = b2_erf(cot_theta_i);
+        sx = b2_max(b2_min(sx, 1.f - 1e-6f), 1e-6f);
+        sy = b2_max(b2_min(sy, 1.f - 1e-6f), 1e-6f);
+        float x = maxval - (maxval + 1.f) * b2_erf(sqrtf(-b2_log(sx)));
+        sx *= 1.f + maxval + B2_INV_SQRT_PI * tan_theta_i * b2_exp(-b2_sqr(cot_theta_i));
+        #pragma unroll 1
+        for (int i = 0; i < 3; ++i) {
+            float slope = b2_erfinv(x),
+                  value = 1.f + x + B2_INV_SQRT_PI * tan_theta_i * b2_exp(-b2_sqr(slope)) - sx,
+                  derivative = 1.f - slope * tan_theta_i;
+            x -= value / derivative;
+        }
+        ox = b2_erfinv(x); oy = b2_erfinv(b2_fma(2.f, sy, -1.f));
+    } else {                                                       // microfacet.h:395-410
+        float px, py; square_to_uniform_disk_concentric(sx, sy, px, py);
+        float s = .5f * (1.f + cos_theta_i);
+        float a0 = b2_safe_sqrt(1.f - b2_sqr(px));
+        py = b2_fma(py, s, b2_fma(-a0, s, a0));                    // enoki::lerp
+        float x = px, y = py, z = b2_safe_sqrt(1.f - (px * px + py * py));
+        float sin_theta_i = b2_safe_sqrt(1.f - b2_sqr(cos_theta_i));
+        float norm = b2_rcp(b2_fma(sin_theta_i, y, cos_theta_i * z));
+        ox = b2_fma(cos_theta_i, y, -(sin_theta_i * z)) * norm; oy = x * norm;
+    }
+}
+B2_D float3 mf_sample(const MF &d, float3 wi, float sx, float sy, float &pdf) {   // microfacet.h:283-316
+    float3 wi_p = normalize(v3(d.au * wi.x, d.av * wi.y, wi.z));
+    float sin_theta_2 = b2_fma(-wi_p.z, wi_p.z, 1.f), inv_sin_theta = b2_rsqrt(sin_theta_2);   // frame.h sincos_phi
+    float sin_phi = wi_p.y * inv_sin_theta, cos_phi = wi_p.x * inv_sin_theta;
+    if (fabsf(sin_theta_2) <= 4.f * B2_EPS) { sin_phi = 0.f; cos_phi = 1.f; }
+    float slx, sly; mf_sample_visible_11(d, wi_p.z, sx, sy, slx, sly);
+    float s0 = b2_fma(cos_phi, slx, -(sin_phi * sly)) * d.au;
+    float s1 = b2_fma(sin_phi, slx, cos_phi * sly) * d.av;
+    float3 m = normalize(v3(-s0, -s1, 1.f));
+    pdf = mf_eval(d, m) * mf_smith_g1(d, wi, m) * fabsf(dot(wi, m)) / wi.z;
+    return m;
+}
+
+// ---- BSDFs (src/bsdfs/{diffuse,dielectric,roughconductor}.cpp) --------------------------------
+B2_D bool bsdf_is_smooth(const B2Bsdf &b) { return b.type != B2_BSDF_DIELECTRIC; }   // path.cpp:155
+
+B2_D float3 rgb3(const float *p) { return v3(p[0], p[1], p[2]); }
+
+B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo) {
+    float cti = si.wi.z, cto = wo.z;
+    float3 zero = v3(0.f, 0.f, 0.f);
+    switch (b.type) {
+        case B2_BSDF_DIFFUSE: case B2_BSDF_NULL: {                 // diffuse.cpp:104-119
+            if (!(cti > 0.f && cto > 0.f)) return zero;
+            return v3((b.reflectance[0] * B2_INV_PI) * cto, (b.reflectance[1] * B2_INV_PI) * cto, (b.reflectance[2] * B2_INV_PI) * cto);
+        }
+        case B2_BSDF_ROUGHCONDUCTOR: {                              // roughconductor.cpp:277-343
+            if (!(cti > 0.f && cto > 0.f)) return zero;
+            float3 H = normalize(wo + si.wi);
+            MF d = mf_make(b);
+            float D = mf_eval(d, H);
+            if (D == 0.f) return zero;
+            float G = mf_smith_g1(d, si.wi, H) * mf_smith_g1(d, wo, H);
+            float result = D * G / (4.f * cti);
+            float c = dot(si.wi, H);
+            float3 F = v3(fresnel_conductor(c, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(c, b.cond_eta[1], b.cond_k[1]),
+                          fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
+            float3 res = v3(result * b.specular_reflectance[0], result * b.specular_reflectance[1], result * b.specular_reflectance[2]);
+            return F * res;
+        }
+        default: return zero;                                       // dielectric.cpp:312-315
+    }
+}
+B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 wo) {
+    float cti = si.wi.z, cto = wo.z;
+    switch (b.type) {
+        case B2_BSDF_DIFFUSE: case B2_BSDF_NULL:                    // diffuse.cpp:121-135
+            return (cti > 0.f && cto > 0.f) ? B2_INV_PI * cto : 0.f;
+        case B2_BSDF_ROUGHCONDUCTOR: {                              // roughconductor.cpp:345-382
+            float3 m = normalize(wo + si.wi);
+            if (!(cti > 0.f && cto > 0.f && dot(si.wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
+            MF d = mf_make(b);
+            return mf_eval(d, m) * mf_smith_g1(d, si.wi, m) / (4.f * cti);
+        }
+        default: return 0.f;
+    }
+}
+struct BS { float3 wo; float pdf, eta; bool delta; };
+B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x, float s2y, BS &bs) {
+    float3 zero = v3(0.f, 0.f, 0.f);
+    bs.wo = zero; bs.pdf = 0.f; bs.eta = 0.f; bs.delta = false;
+    float cti = si.wi.z;
+    switch (b.type) {
+        case B2_BSDF_DIFFUSE: case B2_BSDF_NULL: {                  // diffuse.cpp:78-102
+            if (!(cti > 0.f)) return zero;
+            bs.wo = square_to_cosine_hemisphere(s2x, s2y);
+            bs.pdf = B2_INV_PI * bs.wo.z;
+            bs.eta = 1.f;
+            if (!(bs.pdf > 0.f)) return zero;
+            return rgb3(b.reflectance);
+        }
+        case B2_BSDF_DIELECTRIC: {                                  // dielectric.cpp:201-310
+            float r_i, cos_theta_t, eta_it, eta_ti;
+            fresnel(cti, b.eta, r_i, cos_theta_t, eta_it, eta_ti);
+            float t_i = 1.f - r_i;
+            bool selected_r = sample1 <= r_i;
+            bs.pdf = selected_r ? r_i : t_i;
+            bs.delta = true;
+            float3 w = v3(1.f, 1.f, 1.f);
+            if (selected_r) {
+                bs.wo = v3(-si.wi.x, -si.wi.y, si.wi.z); bs.eta = 1.f;
+                w = w * rgb3(b.specular_reflectance);
+            } else {
+                bs.wo = v3(-eta_ti * si.wi.x, -eta_ti * si.wi.y, cos_theta_t); bs.eta = eta_it;
+                w = w * rgb3(b.specular_transmittance);
+                w = w * b2_sqr(eta_ti);                              // dielectric.cpp:303-307
+            }
+            return w;
+        }
+        case B2_BSDF_ROUGHCONDUCTOR: {                              // roughconductor.cpp:196-275
+            if (!(cti > 0.f)) return zero;
+            MF d = mf_make(b);
+            float pdf; float3 m = mf_sample(d, si.wi, s2x, s2y, pdf);
+            float dwm = 2.f * dot(si.wi, m);                         // reflect(wi, m) fresnel.h:281-283
+            bs.wo = v3(b2_fma(m.x, dwm, -si.wi.x), b2_fma(m.y, dwm, -si.wi.y), b2_fma(m.z, dwm, -si.wi.z));
+            bs.eta = 1.f;
+            bool active = pdf != 0.f && bs.wo.z > 0.f;
+            float weight = mf_smith_g1(d, bs.wo, m);
+            bs.pdf = pdf / (4.f * dot(bs.wo, m));
+            float c = dot(si.wi, m);
+            float3 F = v3(fresnel_conductor(c, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(c, b.cond_eta[1], b.cond_k[1]),
+                          fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
+            float3 wv = v3(weight * b.specular_reflectance[0], weight * b.specular_reflectance[1], weight * b.specular_reflectance[2]);
+            return active ? F * wv : zero;
+        }
+        default: return zero;
+    }
+}
+
+// ---- emitter sampling (area.cpp, shape.cpp:292-323, mesh.cpp:352-397, scene.cpp:164-231) ------
+struct DS { float3 p, n, d; float pdf, dist; };
+
+B2_D uint32_t distr_sample(const float *cdf, uint32_t first, uint32_t last, float sum, float value) {   // distr_1d.h:144-155
+    value *= sum;
+    uint32_t start = first, end = last;
+    uint32_t iterations = start < end ? (32 - __clz(end - start)) : 0;     // log2i(end-start)+1
+    for (uint32_t i = 0; i < iterations; ++i) {                              // array_utils.h:153-170
+        uint32_t middle = (start + end) >> 1;
+        bool cond = __ldg(&cdf[middle]) < value;
+        if (cond) start = (middle + 1 < end) ? middle + 1 : end; else end = middle;
+    }
+    return start;
+}
+
+B2_D float3 area_sample_direction(const DScene &sc, const DEmitter &em, float3 ref_p, float sx, float sy, DS &ds) {
+    const float *cdf = sc.cdf + em.cdf_offset;
+    uint32_t face = distr_sample(cdf, em.valid_first, em.valid_last, em.cdf_sum, sy);
+    uint32_t slot = __ldg(&sc.prim_to_slot[em.first_prim + face]);
+    float4 a0 = __ldg(&sc.tri_pos[3 * slot]), a1 = __ldg(&sc.tri_pos[3 * slot + 1]), a2 = __ldg(&sc.tri_pos[3 * slot + 2]);
+    float3 p0 = v3(a0), e0 = v3(a1) - p0, e1 = v3(a2) - p0;
+    float3 cr = cross(e0, e1);
+    float area = 0.5f * sqrtf(dot(cr, cr));                      // mesh.h:108-116
+    float pmf = area * em.cdf_norm;                                // distr_1d.h:194-204
+    float cdfv = face > 0 ? __ldg(&cdf[face - 1]) * em.cdf_norm : 0.f;
+    sy = (sy - cdfv) / pmf;
+    float t = b2_safe_sqrt(1.f - sx);                             // warp.h:152-156
+    float bx = 1.f - t, by = t * sy;
+    ds.p = (p0 + e0 * bx) + e1 * by;                               // mesh.cpp:370
+    float pdf = em.cdf_norm;
+    float4 m2 = __ldg(&sc.tri_nrm[3 * slot + 2]);
+    if (__float_as_uint(m2.w)) {                                   // mesh.cpp:386-394
+        float4 m0 = __ldg(&sc.tri_nrm[3 * slot]), m1 = __ldg(&sc.tri_nrm[3 * slot + 1]);
+        ds.n = normalize((v3(m0) * (1.f - bx - by) + v3(m1) * bx) + v3(m2) * by);
+    } else
+        ds.n = normalize(cr);
+    ds.d = ds.p - ref_p;                                           // shape.cpp:298-306
+    float dist_squared = dot(ds.d, ds.d);
+    ds.dist = sqrtf(dist_squared);
+    ds.d = ds.d * b2_rcp(ds.dist);
+    float dp = fabsf(dot(ds.d, ds.n));
+    pdf *= dp != 0.f ? dist_squared / dp : 0.f;
+    ds.pdf = pdf;
+    bool active = dot(ds.d, ds.n) < 0.f && pdf != 0.f;             // area.cpp:132
+    if (!active) return v3(0.f, 0.f, 0.f);
+    float ip = b2_rcp(pdf);
+    return v3(em.radiance[0] * ip, em.radiance[1] * ip, em.radiance[2] * ip);
+}
+
+B2_D float3 scene_sample_emitter_direction(const DScene &sc, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
+    uint32_t ne = sc.n_emitters;
+    if (ne == 0) { ds.pdf = 0.f; ds.dist = 0.f; ds.p = ds.n = ds.d = v3(0.f, 0.f, 0.f); return v3(0.f, 0.f, 0.f); }
+    if (ne == 1) return area_sample_direction(sc, sc.emitters[0], ref_p, sx, sy, ds);
+    float emitter_pdf = 1.f / (float) ne;
+    uint32_t index = (uint32_t) (sx * (float) ne);
+    if (index > ne - 1) index = ne - 1;
+    sx = (sx - (float) index * emitter_pdf) * (float) ne;
+    float3 spec = area_sample_direction(sc, sc.emitters[index], ref_p, sx, sy, ds);
+    ds.pdf *= emitter_pdf;
+    return spec * b2_rcp(emitter_pdf);
+}
+
+B2_D float scene_pdf_emitter_direction(const DScene &sc, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
+    const DEmitter &em = sc.emitters[emitter];
+    float dp = dot(d, n);
+    if (!(dp < 0.f)) return 0.f;                                   // area.cpp:170-171
+    float pdf = em.cdf_norm;                                       // mesh.cpp:417-420
+    float adp = fabsf(dp);
+    pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;                 // shape.cpp:312-323
+    if (sc.n_emitters != 1) pdf = pdf * (1.f / (float) sc.n_emitters);
+    return pdf;
+}
+
+B2_D float mis_weight(float a, float b) {    // path.cpp:223-227
+    a *= a; b *= b;
+    return a > 0.f ? a / (a + b) : 0.f;
+}
+
+// ---- sensor (src/sensors/perspective.cpp:182-216) ---------------------------------------------
+B2_D Ray sensor_sample_ray(const B2Sensor &sn, float sx, float sy) {
+    const float *M = sn.sample_to_camera;
+    float px = sx + sn.principal_point_offset[0], py = sy + sn.principal_point_offset[1];
+    float r[4];
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) {                                  // transform.h:103-111
+        float acc = M[4 * k + 3];
+        acc = b2_fma(M[4 * k + 0], px, acc);
+        acc = b2_fma(M[4 * k + 1], py, acc);
+        acc = b2_fma(M[4 * k + 2], 0.f, acc);
+        r[k] = acc;
+    }
+    float iw = b2_rcp(r[3]);
+    float3 d = normalize(v3(r[0] * iw, r[1] * iw, r[2] * iw));
+    float inv_z = b2_rcp(d.z);
+    Ray ray;
+    ray.mint = sn.near_clip * inv_z; ray.maxt = sn.far_clip * inv_z;
+    const float *T = sn.to_world;
+    ray.o = v3(T[3], T[7], T[11]);
+    ray.d.x = b2_fma(T[2], d.z, b2_fma(T[1], d.y, T[0] * d.x));    // transform.h:117-125
+    ray.d.y = b2_fma(T[6], d.z, b2_fma(T[5], d.y, T[4] * d.x));
+    ray.d.z = b2_fma(T[10], d.z, b2_fma(T[9], d.y, T[8] * d.x));
+    return ray;
+}

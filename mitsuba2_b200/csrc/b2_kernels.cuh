@@ -1,0 +1,526 @@
+// b2_kernels.cuh — the wavefront stage kernels (sm_100a).
+//
+//   K1+K6  k_regen      film put of the finished sample (ImageBlock::put, imageblock.cpp:79-172)
+//                       + next camera sample of the lane's work item (render_sample,
+//                       integrator.cpp:233-262; PerspectiveCamera::sample_ray, perspective.cpp:182-216)
+//   K2     k_intersect  closest hit: BVH4 traversal + Mesh::ray_intersect_triangle (mesh.h:194-226)
+//   K4     k_shade      SI fill fused with one iteration of PathIntegrator::sample's loop body
+//                       (path.cpp:124-208); K5 (warp-ballot compaction) is fused into its tail
+//   K3     k_shadow     any-hit visibility of the emitter sample (scene.cpp:203-207)
+//
+// Queues are SoA float4 / uint4 arrays indexed by lane slot; the lists hold lane indices.
+#pragma once
+#include "b2_device.cuh"
+
+struct Queues {
+    float4 *ray_o, *ray_d;      // (o.xyz, mint), (d.xyz, maxt)                      32 B
+    float4 *hit;                // (t, u, v, slot bits); t = +inf: miss               16 B
+    float4 *tp;                 // (throughput.rgb, eta)                              16 B
+    float4 *res;                // (result.rgb, pdf of the last BSDF sample)          16 B
+    uint4 *st;                  // (rng.lo, rng.hi, work item, depth|flags|samples_left) 16 B
+    float2 *pos;                // position_sample, only for wide (non-box) filters
+    float4 *sh_o, *sh_d, *sh_c; // shadow queue (dense): ray + (contrib.rgb, lane bits) 48 B
+    uint32_t *list[2];          // lanes with an active ray (double buffered)
+    uint32_t *new_list;         // lanes whose path ended (to film + regenerate)
+    uint32_t *cnt;              // [0],[1] = list counts, [2] = new count, [3] = shadow count, [4] = work counter
+    unsigned long long *stats;  // [0] samples, [1] segments, [2] shadow rays, [3] invalid
+    float *film;                // crop_h x crop_w x 5 (X,Y,Z,A,W)
+    const uint32_t *item_pixel; // per work item of ONE pass: x | y << 16 (crop-relative)
+    const uint32_t *item_seed;  // spiral_index * bs^2 + morton index
+    uint32_t n_items_pass;      // work items per pass (this rank's pixels)
+    uint32_t n_passes, spp_pass, block_size, n_blocks_total;
+    uint32_t total_items;       // n_items_pass * n_passes
+    uint64_t base_seed;
+    int32_t max_depth, rr_depth;
+};
+
+enum { CNT_LIST0 = 0, CNT_LIST1 = 1, CNT_NEW = 2, CNT_SHADOW = 3, CNT_WORK = 4 };
+enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3 };
+
+// st.w layout
+#define STW_DEPTH(w)     ((w) & 0xffu)
+#define STW_ALPHA        0x100u      // camera ray hit something (valid_ray, path.cpp:121)
+#define STW_DELTA        0x200u      // last BSDF sample was a delta lobe
+#define STW_FILM_DX      0x400u      // box filter: sample lands on pixel x-1
+#define STW_FILM_DY      0x800u      //             ... y-1
+#define STW_FILM_DROP    0x1000u     // sample falls outside its block (imageblock.cpp:166)
+#define STW_HAS_SAMPLE   0x2000u     // a finished sample is waiting to be put on the film
+#define STW_LEFT(w)      ((w) >> 16)
+
+B2_D uint32_t lane_id() { return threadIdx.x & 31; }
+
+// warp-aggregated append: one atomic per warp, contiguous slots for the set lanes.
+// Must be called by all 32 lanes of the warp.
+B2_D uint32_t warp_append(uint32_t *counter, bool pred) {
+    uint32_t mask = __ballot_sync(0xffffffffu, pred);
+    uint32_t base = 0;
+    if (lane_id() == 0 && mask) base = atomicAdd(counter, __popc(mask));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    return base + __popc(mask & ((1u << lane_id()) - 1u));
+}
+
+// ---- TMA (1-D bulk copy) staging of the BVH top + triangles into shared memory -----------------
+B2_D uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+B2_D void stage_bulk(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *mbar) {
+    // called by ONE thread; bytes is a multiple of 16, both pointers 16-byte aligned
+    uint32_t off = 0;
+    while (off < bytes) {
+        uint32_t chunk = bytes - off > 32768u ? 32768u : bytes - off;
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                     :: "r"(smem_u32((char *) smem_dst + off)), "l"((const char *) gmem_src + off), "r"(chunk),
+                        "r"(smem_u32(mbar)) : "memory");
+        off += chunk;
+    }
+}
+B2_D void mbar_init(uint64_t *mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+B2_D void mbar_expect_tx(uint64_t *mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+B2_D void mbar_wait(uint64_t *mbar, uint32_t parity) {
+    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n"
+                 :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+}
+
+struct SmemScene { const float4 *nodes; const float4 *tris; };
+
+// Stage sc.smem_nodes BVH nodes (+ all triangle positions if sc.smem_tris) with cp.async.bulk.
+B2_D SmemScene stage_scene(const DScene &sc, unsigned char *smem_raw) {
+    SmemScene s; s.nodes = nullptr; s.tris = nullptr;
+    uint32_t node_bytes = sc.smem_nodes * 128u, tri_bytes = sc.smem_tris ? sc.n_tris * 48u : 0u;
+    if (node_bytes + tri_bytes == 0) return s;
+    uint64_t *mbar = (uint64_t *) smem_raw;
+    float4 *dst = (float4 *) (smem_raw + 16);
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(mbar, node_bytes + tri_bytes);
+        if (node_bytes) stage_bulk(dst, sc.nodes, node_bytes, mbar);
+        if (tri_bytes) stage_bulk((char *) dst + node_bytes, sc.tri_pos, tri_bytes, mbar);
+    }
+    mbar_wait(mbar, 0);
+    s.nodes = dst;
+    if (tri_bytes) s.tris = (const float4 *) ((const char *) dst + node_bytes);
+    return s;
+}
+
+// ---- BVH4 traversal ------------------------------------------------------------------------------
+// Closest hit = lexicographic min over (t, -prim) of all triangles passing the Moeller-Trumbore
+// test, i.e. on exact t ties the HIGHER prim index wins (the reference's kd-tree keeps the last
+// primitive of a leaf on `t <= maxt`, kdtree.h:2140-2154). The result does not depend on the
+// traversal order.
+struct Hit { float t, u, v; uint32_t slot, prim; };
+
+template <bool ANY>
+B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
+    best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu;
+    if (sc.n_tris == 0) return false;
+    float tmax = ray.maxt;
+    float3 d = ray.d;
+    // guard zero components: 1/0 -> inf would give NaN on (lo-o)*inf when lo == o
+    float dx = fabsf(d.x) > 1e-20f ? d.x : (d.x < 0.f ? -1e-20f : 1e-20f);
+    float dy = fabsf(d.y) > 1e-20f ? d.y : (d.y < 0.f ? -1e-20f : 1e-20f);
+    float dz = fabsf(d.z) > 1e-20f ? d.z : (d.z < 0.f ? -1e-20f : 1e-20f);
+    float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;
+    int stack_c[24]; float stack_t[24];
+    int sp = 0;
+    int cur = 0;                // node index (inner), or leaf code < 0
+    float cur_t = ray.mint;
+    for (;;) {
+        if (cur >= 0) {
+            const float4 *np = ((uint32_t) cur < sc.smem_nodes) ? sm.nodes + 8 * cur : nullptr;
+            float4 lox, loy, loz, hix, hiy, hiz, chf;
+            if (np) { lox = np[0]; loy = np[1]; loz = np[2]; hix = np[3]; hiy = np[4]; hiz = np[5]; chf = np[6]; }
+            else {
+                const float4 *gp = sc.nodes + 8 * (size_t) cur;
+                lox = __ldg(gp); loy = __ldg(gp + 1); loz = __ldg(gp + 2); hix = __ldg(gp + 3); hiy = __ldg(gp + 4);
+                hiz = __ldg(gp + 5); chf = __ldg(gp + 6);
+            }
+            const float lo_x[4] = { lox.x, lox.y, lox.z, lox.w }, lo_y[4] = { loy.x, loy.y, loy.z, loy.w },
+                        lo_z[4] = { loz.x, loz.y, loz.z, loz.w }, hi_x[4] = { hix.x, hix.y, hix.z, hix.w },
+                        hi_y[4] = { hiy.x, hiy.y, hiy.z, hiy.w }, hi_z[4] = { hiz.x, hiz.y, hiz.z, hiz.w };
+            const int ch[4] = { __float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w) };
+            int hc[4]; float ht[4]; int nh = 0;
+            #pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float t0x = (lo_x[k] - ray.o.x) * idx, t1x = (hi_x[k] - ray.o.x) * idx;
+                float t0y = (lo_y[k] - ray.o.y) * idy, t1y = (hi_y[k] - ray.o.y) * idy;
+                float t0z = (lo_z[k] - ray.o.z) * idz, t1z = (hi_z[k] - ray.o.z) * idz;
+                float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), ray.mint));
+                float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
+                bool h = ch[k] != 0 && tn <= tf * 1.0000004f;
+                if (h) {     // insertion sort, descending tn (nearest popped first)
+                    int j = nh++;
+                    while (j > 0 && ht[j - 1] < tn) { ht[j] = ht[j - 1]; hc[j] = hc[j - 1]; --j; }
+                    ht[j] = tn; hc[j] = ch[k];
+                }
+            }
+            for (int j = 0; j < nh; ++j) { stack_c[sp] = hc[j]; stack_t[sp] = ht[j]; ++sp; }
+        } else {
+            uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
+            for (uint32_t s = first; s < first + count; ++s) {
+                float4 a0, a1, a2;
+                if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
+                else { a0 = __ldg(&sc.tri_pos[3 * (size_t) s]); a1 = __ldg(&sc.tri_pos[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_pos[3 * (size_t) s + 2]); }
+                float t, u, v;
+                Ray r = ray; r.maxt = tmax;
+                if (tri_intersect(v3(a0), v3(a1), v3(a2), r, t, u, v)) {
+                    if (ANY) return true;
+                    uint32_t prim = __float_as_uint(a0.w);
+                    if (t < best.t || (t == best.t && prim > best.prim)) {
+                        best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim;
+                        tmax = t;
+                    }
+                }
+            }
+        }
+        // pop
+        for (;;) {
+            if (sp == 0) return best.t < B2_INF;
+            --sp;
+            cur = stack_c[sp]; cur_t = stack_t[sp];
+            if (cur_t <= tmax * 1.0000004f) break;
+        }
+    }
+}
+
+// ---- K2: closest hit ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_intersect(DScene sc, Queues q, int cur) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    uint32_t count = q.cnt[cur];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[cur ^ 1] = 0; q.cnt[CNT_NEW] = 0; q.cnt[CNT_SHADOW] = 0;
+        atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) count);
+    }
+    const uint32_t *list = q.list[cur];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        uint32_t lane = list[i];
+        float4 ro = q.ray_o[lane], rd = q.ray_d[lane];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Hit h; traverse<false>(sc, sm, ray, h);
+        q.hit[lane] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+    }
+}
+
+// ---- K3: any hit for the emitter samples ----------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    uint32_t count = q.cnt[CNT_SHADOW];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) count);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        float4 ro = q.sh_o[i], rd = q.sh_d[i];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Hit h;
+        if (!traverse<true>(sc, sm, ray, h)) {
+            float4 c = q.sh_c[i];
+            uint32_t lane = __float_as_uint(c.w);
+            float4 r = q.res[lane];
+            r.x += c.x; r.y += c.y; r.z += c.z;            // result += mis*throughput*bsdf_val*emitter_val (path.cpp:171)
+            q.res[lane] = r;
+        }
+    }
+}
+
+// ---- K6: ImageBlock::put (imageblock.cpp:79-172) -----------------------------------------------
+B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint32_t block_size,
+                   uint32_t stw, float2 pos, float3 L, bool alpha) {
+    // srgb_to_xyz (spectrum.h:221-228): M * rgb with fmadd accumulation (matrix.h:170-177)
+    float val[5];
+    val[0] = b2_fma(0.180423f, L.z, b2_fma(0.357580f, L.y, 0.412453f * L.x));
+    val[1] = b2_fma(0.072169f, L.z, b2_fma(0.715160f, L.y, 0.212671f * L.x));
+    val[2] = b2_fma(0.950227f, L.z, b2_fma(0.119193f, L.y, 0.019334f * L.x));
+    val[3] = alpha ? 1.f : 0.f; val[4] = 1.f;
+    #pragma unroll
+    for (int k = 0; k < 5; ++k)                                    // imageblock.cpp:85-109
+        if (!(val[k] >= -1e-5f) || !(fabsf(val[k]) < B2_INF)) return false;
+    const B2Film &f = sc.film;
+    int W = f.crop_size[0], H = f.crop_size[1];
+    if (f.filter_radius > 0.5f + B2_RAY_EPS) {                     // imageblock.cpp:117-161
+        int border = f.border;
+        int ox = (int) (px / block_size) * (int) block_size, oy = (int) (py / block_size) * (int) block_size;
+        int bw = min((int) block_size, W - ox), bh = min((int) block_size, H - oy);
+        int sx = bw + 2 * border, sy = bh + 2 * border;
+        float bx = pos.x - ((float) (ox + f.crop_offset[0] - border) + .5f),
+              by = pos.y - ((float) (oy + f.crop_offset[1] - border) + .5f);
+        float radius = f.filter_radius;
+        int lox = max((int) ceilf(bx - radius), 0), loy = max((int) ceilf(by - radius), 0);
+        int hix = min((int) floorf(bx + radius), sx - 1), hiy = min((int) floorf(by + radius), sy - 1);
+        uint32_t n = (uint32_t) ceilf((radius - 2.f * B2_RAY_EPS) * 2.f);
+        float basex = (float) lox - bx, basey = (float) loy - by;
+        for (uint32_t yr = 0; yr < n; ++yr) {
+            int y = loy + (int) yr;
+            bool enabled = y <= hiy;
+            int iy = min((int) fabsf((basey + (float) yr) * f.filter_scale), B2_FILTER_RESOLUTION);
+            float wy = f.filter_lut[iy];
+            for (uint32_t xr = 0; xr < n; ++xr) {
+                int x = lox + (int) xr;
+                int ix = min((int) fabsf((basex + (float) xr) * f.filter_scale), B2_FILTER_RESOLUTION);
+                float weight = wy * f.filter_lut[ix];
+                enabled &= x <= hix;
+                int fx = ox - border + x, fy = oy - border + y;   // film (crop-relative) coordinates
+                if (enabled && fx >= 0 && fy >= 0 && fx < W && fy < H) {
+                    float *dst = film + 5 * ((size_t) fy * W + fx);
+                    #pragma unroll
+                    for (int k = 0; k < 5; ++k) atomicAdd(dst + k, val[k] * weight);
+                }
+            }
+        }
+    } else {                                                       // imageblock.cpp:162-169
+        if (stw & STW_FILM_DROP) return true;
+        int fx = (int) px - ((stw & STW_FILM_DX) ? 1 : 0), fy = (int) py - ((stw & STW_FILM_DY) ? 1 : 0);
+        float *dst = film + 5 * ((size_t) fy * W + fx);
+        #pragma unroll
+        for (int k = 0; k < 5; ++k) atomicAdd(dst + k, val[k]);
+    }
+    return true;
+}
+
+// ---- K1 (+K6): regenerate ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_regen(DScene sc, Queues q, int cur) {
+    uint32_t count = q.cnt[CNT_NEW];
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const B2Film &film = sc.film;
+    for (uint32_t base = warp * 32; base < count; base += n_warps * 32) {
+        uint32_t i = base + lane_id();
+        bool valid = i < count;
+        uint32_t lane = valid ? q.new_list[i] : 0;
+        uint4 st = valid ? q.st[lane] : make_uint4(0, 0, 0, 0);
+        uint32_t item = st.z, left = STW_LEFT(st.w);
+        uint32_t n_put = 0, n_bad = 0;
+        if (valid && (st.w & STW_HAS_SAMPLE)) {
+            uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
+            float4 r = q.res[lane];
+            float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
+            bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, v3(r), (st.w & STW_ALPHA) != 0);
+            n_put = 1; n_bad = ok ? 0 : 1;
+        }
+        // fetch the next work item if this one is exhausted (warp-aggregated atomic)
+        bool need = valid && left == 0;
+        uint32_t w = warp_append(&q.cnt[CNT_WORK], need);
+        uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+        bool alive = valid;
+        if (need) {
+            if (w >= q.total_items) alive = false;
+            else {
+                item = w; left = q.spp_pass;
+                uint32_t pass = item / q.n_items_pass, j = item % q.n_items_pass;
+                // block_id = spiral index + (remaining_passes - 1) * block_count  (spiral.cpp:41);
+                // seed = block_id * bs^2 + morton index                           (integrator.cpp:198)
+                uint64_t seed_off = (uint64_t) __ldg(&q.item_seed[j]) +
+                                    (uint64_t) (q.n_passes - 1 - pass) * q.n_blocks_total * q.block_size * q.block_size;
+                rng = pcg32_seed(q.base_seed + seed_off);
+            }
+        }
+        if (alive) {
+            uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
+            uint32_t px = pix & 0xffffu, py = pix >> 16;
+            float jx = pcg32_next_float(rng), jy = pcg32_next_float(rng);            // integrator.cpp:242
+            float psx = (float) (px + (uint32_t) film.crop_offset[0]) + jx, psy = (float) (py + (uint32_t) film.crop_offset[1]) + jy;
+            (void) pcg32_next_float(rng);                                              // :252 wavelength sample
+            float ax = (psx - (float) film.crop_offset[0]) / (float) film.crop_size[0],
+                  ay = (psy - (float) film.crop_offset[1]) / (float) film.crop_size[1];   // :254-256
+            Ray ray = sensor_sample_ray(sc.sensor, ax, ay);
+            uint32_t stw = 1u | ((left - 1) << 16);
+            if (!(film.filter_radius > 0.5f + B2_RAY_EPS)) {
+                // box filter target pixel, in block coordinates (imageblock.cpp:112,163-166)
+                uint32_t bs = q.block_size;
+                int ox = (int) (px / bs) * (int) bs, oy = (int) (py / bs) * (int) bs;
+                int bw = min((int) bs, film.crop_size[0] - ox), bh = min((int) bs, film.crop_size[1] - oy);
+                float bx = psx - ((float) (ox + film.crop_offset[0]) + .5f), by = psy - ((float) (oy + film.crop_offset[1]) + .5f);
+                int lox = (int) ceilf(bx - .5f), loy = (int) ceilf(by - .5f);
+                if (lox < 0 || loy < 0 || lox >= bw || loy >= bh) stw |= STW_FILM_DROP;
+                if (lox + ox != (int) px) stw |= STW_FILM_DX;
+                if (loy + oy != (int) py) stw |= STW_FILM_DY;
+                // (lo can only be px or px-1: psx = px + j with j in [0,1) rounds into [px, px+1])
+                if (lox + ox != (int) px && lox + ox != (int) px - 1) stw |= STW_FILM_DROP;
+                if (loy + oy != (int) py && loy + oy != (int) py - 1) stw |= STW_FILM_DROP;
+            } else if (q.pos)
+                q.pos[lane] = make_float2(psx, psy);
+            q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+            q.ray_d[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+            q.tp[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
+            q.res[lane] = make_float4(0.f, 0.f, 0.f, 1.f);
+            q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), item, stw);
+        } else if (valid) {
+            q.st[lane] = make_uint4(0, 0, 0, 0);       // retired
+        }
+        uint32_t slot = warp_append(&q.cnt[cur], alive);
+        if (alive) q.list[cur][slot] = lane;
+        // stats
+        uint32_t tot_put = __reduce_add_sync(0xffffffffu, n_put), tot_bad = __reduce_add_sync(0xffffffffu, n_bad);
+        if (lane_id() == 0) {
+            if (tot_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) tot_put);
+            if (tot_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) tot_bad);
+        }
+    }
+}
+
+// ---- K4: shade (SI fill + one loop body of PathIntegrator::sample) ----------------------------
+__global__ void __launch_bounds__(256) k_shade(DScene sc, Queues q, int cur) {
+    uint32_t count = q.cnt[cur];
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t *list = q.list[cur];
+    uint32_t *list_out = q.list[cur ^ 1];
+    for (uint32_t base = warp * 32; base < count; base += n_warps * 32) {
+        uint32_t i = base + lane_id();
+        bool valid = i < count;
+        uint32_t lane = valid ? list[i] : 0;
+        bool cont = false, term = false, shadow = false;
+        float4 sho, shd, shc;
+        if (valid) {
+            float4 ro = q.ray_o[lane], rd = q.ray_d[lane], h = q.hit[lane], tpe = q.tp[lane], rs = q.res[lane];
+            uint4 st = q.st[lane];
+            uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+            int depth = (int) STW_DEPTH(st.w);
+            float3 throughput = v3(tpe), result = v3(rs);
+            float eta = tpe.w, bs_pdf = rs.w;
+            bool hit_valid = h.x < B2_INF;
+            SI si; si.emitter = -1; si.bsdf = -1;
+            if (hit_valid) si_fill(sc, __float_as_uint(h.w), h.y, h.z, v3(rd), si);
+            if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
+            // ---- intersection with emitters (path.cpp:128-129) ----
+            if (si.emitter >= 0) {
+                float emission_weight = 1.f;
+                if (depth > 1) {                                                    // path.cpp:194-205, records.h:168-174
+                    float emitter_pdf = 0.f;
+                    if (!(st.w & STW_DELTA)) {
+                        float3 dd = si.p - v3(ro);
+                        float dist = sqrtf(dot(dd, dd));
+                        dd = dd * b2_rcp(dist);
+                        emitter_pdf = scene_pdf_emitter_direction(sc, si.emitter, dd, si.sh_n, dist);
+                    }
+                    emission_weight = mis_weight(bs_pdf, emitter_pdf);
+                }
+                const DEmitter &em = sc.emitters[si.emitter];
+                float3 ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
+                result = result + (throughput * emission_weight) * ev;
+            }
+            bool active = hit_valid;                                                // path.cpp:131
+            if (depth > q.rr_depth) {                                               // path.cpp:137-141
+                float qq = b2_min(hmax(throughput) * b2_sqr(eta), .95f);
+                if (active) active = pcg32_next_float(rng) < qq;
+                throughput = throughput * b2_rcp(qq);
+            }
+            if ((uint32_t) depth >= (uint32_t) q.max_depth || !active) term = true;   // path.cpp:147-149
+            else {
+                const B2Bsdf &bsdf = sc.bsdfs[si.bsdf];
+                if (bsdf_is_smooth(bsdf)) {                                         // path.cpp:153-172
+                    float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
+                    DS ds; float3 emitter_val = scene_sample_emitter_direction(sc, si.p, sx, sy, ds);
+                    if (ds.pdf != 0.f) {
+                        float3 wo = to_local(si, ds.d);
+                        float3 bsdf_val = bsdf_eval(bsdf, si, wo);
+                        float bpdf = bsdf_pdf(bsdf, si, wo);
+                        float mis = mis_weight(ds.pdf, bpdf);
+                        float3 c = ((throughput * mis) * bsdf_val) * emitter_val;
+                        if (any_nonzero(c)) {                                       // visibility: scene.cpp:203-207
+                            shadow = true;
+                            sho = make_float4(si.p.x, si.p.y, si.p.z, B2_RAY_EPS * (1.f + hmax_abs(si.p)));
+                            shd = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.dist * (1.f - B2_SHADOW_EPS));
+                            shc = make_float4(c.x, c.y, c.z, __uint_as_float(lane));
+                        }
+                    }
+                }
+                // BSDF sampling — the reference (g++) draws next_2d BEFORE next_1d (path.cpp:177-178)
+                float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
+                float s1 = pcg32_next_float(rng);
+                BS bs; float3 bsdf_val = bsdf_sample(bsdf, si, s1, s2x, s2y, bs);
+                throughput = throughput * bsdf_val;
+                if (!any_nonzero(throughput)) term = true;                         // path.cpp:182-184
+                else {
+                    eta *= bs.eta;
+                    float3 nd = to_world(si, bs.wo);                                // interaction.h:58-61
+                    q.ray_o[lane] = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
+                    q.ray_d[lane] = make_float4(nd.x, nd.y, nd.z, B2_INF);
+                    bs_pdf = bs.pdf;
+                    st.w = (st.w & ~(0xffu | STW_DELTA)) | (uint32_t) (depth + 1) | (bs.delta ? STW_DELTA : 0u);
+                    cont = true;
+                }
+            }
+            if (term) st.w |= STW_HAS_SAMPLE;
+            q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
+            q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
+            q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+        }
+        __syncwarp();
+        // ---- K5: warp-ballot compaction into the next queues ----
+        uint32_t s0 = warp_append(&q.cnt[cur ^ 1], cont);
+        if (cont) list_out[s0] = lane;
+        uint32_t s1 = warp_append(&q.cnt[CNT_NEW], term);
+        if (term) q.new_list[s1] = lane;
+        uint32_t s2 = warp_append(&q.cnt[CNT_SHADOW], shadow);
+        if (shadow) { q.sh_o[s2] = sho; q.sh_d[s2] = shd; q.sh_c[s2] = shc; }
+    }
+}
+
+// ---- HDRFilm::bitmap(): XYZAW -> RGB (hdrfilm.cpp:251-322, struct.cpp:1750-1812) ----------------
+__global__ void k_develop(const float *xyzaw, float *rgb, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float *p = xyzaw + 5 * (size_t) i;
+    float iw = 1.f / p[4];
+    float r = 0.f, g = 0.f, b = 0.f;
+    r += 3.240479f * p[0]; r += -1.537150f * p[1]; r += -0.498535f * p[2];
+    g += -0.969256f * p[0]; g += 1.875991f * p[1]; g += 0.041556f * p[2];
+    b += 0.055648f * p[0]; b += -0.204043f * p[1]; b += 1.057311f * p[2];
+    rgb[3 * i] = r * iw; rgb[3 * i + 1] = g * iw; rgb[3 * i + 2] = b * iw;
+}
+
+// ---- stage-level kernels for b2_stage_* (flat arrays, identity lane mapping) --------------------
+__global__ void k_stage_raygen(DScene sc, uint32_t n, const uint32_t *px, const uint32_t *py, const uint64_t *seed_off,
+                               uint64_t base_seed, float4 *ray_o, float4 *ray_d, uint64_t *rng_out, float2 *pos) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const B2Film &film = sc.film;
+    uint64_t rng = pcg32_seed(base_seed + seed_off[i]);
+    float jx = pcg32_next_float(rng), jy = pcg32_next_float(rng);
+    float psx = (float) px[i] + jx, psy = (float) py[i] + jy;
+    (void) pcg32_next_float(rng);
+    float ax = (psx - (float) film.crop_offset[0]) / (float) film.crop_size[0],
+          ay = (psy - (float) film.crop_offset[1]) / (float) film.crop_size[1];
+    Ray ray = sensor_sample_ray(sc.sensor, ax, ay);
+    ray_o[i] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+    ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+    rng_out[i] = rng; pos[i] = make_float2(psx, psy);
+}
+__global__ void __launch_bounds__(256) k_stage_intersect(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, float4 *hit) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 ro = ray_o[i], rd = ray_d[i];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Hit h; traverse<false>(sc, sm, ray, h);
+        hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));     // prim id (not slot) at the ABI
+    }
+}
+__global__ void __launch_bounds__(256) k_stage_occluded(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, uint8_t *occ) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 ro = ray_o[i], rd = ray_d[i];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Hit h; occ[i] = traverse<true>(sc, sm, ray, h) ? 1 : 0;
+    }
+}
+__global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, const float4 *hit, float *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 h = hit[i];
+    float *o = out + 16 * (size_t) i;
+    if (!(h.x < B2_INF)) {
+        for (int k = 0; k < 12; ++k) o[k] = 0.f;
+        float4 rd = ray_d[i];
+        o[12] = -rd.x; o[13] = -rd.y; o[14] = -rd.z; o[15] = __uint_as_float(0xffffffffu);
+        return;
+    }
+    uint32_t slot = sc.prim_to_slot[__float_as_uint(h.w)];
+    SI si; si_fill(sc, slot, h.y, h.z, v3(ray_d[i]), si);
+    o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z; o[3] = si.n.x; o[4] = si.n.y; o[5] = si.n.z;
+    o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z; o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
+    o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z; o[15] = __uint_as_float((uint32_t) si.bsdf);
+}

@@ -865,23 +865,21 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
             float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
             ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
             if (ds.pdf != 0.f) {
-                int visible = 1;
-                if (emitter_val.x != 0.f || emitter_val.y != 0.f || emitter_val.z != 0.f) {
-                    /* scene.cpp:203-207 (the reference also traces when spec is already 0; the
-                       outcome cannot change the result then, so the oracle skips it) */
-                    oray sr; sr.o = si.p; sr.d = ds.d;
-                    sr.mint = B2O_RAY_EPS * (1.f + v3_hmax_abs(si.p));
-                    sr.maxt = ds.dist * (1.f - B2O_SHADOW_EPS);
-                    cnt->shadow_rays++;
-                    visible = !scene_occluded(s, &sr, brute);
-                }
-                if (!visible) emitter_val = v3_make(0.f, 0.f, 0.f);
                 v3 wo = to_local(&si, ds.d);
                 v3 bsdf_val = bsdf_eval(bsdf, &si, wo);
                 float bpdf = bsdf_pdf(bsdf, &si, wo);
                 float mis = mis_weight(ds.pdf, bpdf);
                 v3 c = v3_mul(v3_mul(v3_scale(throughput, mis), bsdf_val), emitter_val);
-                result = v3_add(result, c);
+                /* scene.cpp:203-207: spec[ray_test(ray)] = 0. The reference traces the shadow ray
+                   whenever ds.pdf != 0; the outcome only matters when the contribution is not
+                   already zero, so the oracle (and the CUDA path) trace it only then. */
+                if (c.x != 0.f || c.y != 0.f || c.z != 0.f) {
+                    oray sr; sr.o = si.p; sr.d = ds.d;
+                    sr.mint = B2O_RAY_EPS * (1.f + v3_hmax_abs(si.p));
+                    sr.maxt = ds.dist * (1.f - B2O_SHADOW_EPS);
+                    cnt->shadow_rays++;
+                    if (!scene_occluded(s, &sr, brute)) result = v3_add(result, c);
+                }
             }
         }
         /* BSDF sampling: g++ evaluates the arguments right to left, so next_2d is drawn
