@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — Msamples/s of the wavefront path tracer on BASELINE.json's configuration.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference ...                      (the reference's own CPU path on the host cores)
+
+A "step" is one full render of the workload (cbox 1024x1024, 256 spp, max_depth 6 — BASELINE
+configs[1]) through the hot path. `value` times the render with scene + queues resident in HBM
+and the film left on the device (CUDA events on the launching stream, max over ranks, incl. the
+final NCCL reduce of the film for N > 1); `e2e` times the public call PathIntegrator.render()
+with a HOST film buffer (per-step host->device work-item tables and device->host film copy
+inside the timed region). Pixel blocks are sharded over ranks (block b -> rank b % N); seeds
+are a pure function of (block, pixel, pass) so the image does not depend on N.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+# SURVEY.md §8(d) algorithmic bytes (per unit, read + write, excluding BVH / geometry)
+B_RAYGEN, B_HIT, B_SHADE, B_SHADOW, B_COMPACT, B_FILM = 80, 52, 224, 68, 8, 40
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2pt", choices=["b2pt", "reference"])
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--spp", type=int, default=256)
+    ap.add_argument("--spp-per-pass", type=int, default=16,
+                    help="integrator 'samples_per_pass' (integrator.cpp:34); 0 = spp")
+    ap.add_argument("--max-depth", type=int, default=6)
+    ap.add_argument("--lane-slots", type=int, default=0)
+    ap.add_argument("--cpu-baseline", type=int, default=1)
+    ap.add_argument("--no-stage-timing", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# reference CPU arm (oracle/_ref = the unmodified reference CLI; falls back to the oracle port)
+# ------------------------------------------------------------------------------------------------
+def _ref_dist():
+    d = os.path.join(ROOT, "oracle", "_ref", "dist")
+    return d if os.path.exists(os.path.join(d, "mitsuba")) else None
+
+
+def _ref_cbox_xml(res, spp, spp_pass, max_depth):
+    mesh_dir = os.path.join(ROOT, "oracle", "_ref", "scenes", "cbox", "meshes")
+    shapes = [("cbox_luminaire.obj", "light", True), ("cbox_floor.obj", "white", False), ("cbox_ceiling.obj", "white", False),
+              ("cbox_back.obj", "white", False), ("cbox_greenwall.obj", "green", False), ("cbox_redwall.obj", "red", False),
+              ("cbox_smallbox.obj", "box", False), ("cbox_largebox.obj", "box", False)]
+    from mitsuba2_b200.scenes import CBOX_BSDFS
+    bs = "".join(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>'
+                 for k, v in CBOX_BSDFS.items())
+    sh = ""
+    for fn, b, lum in shapes:
+        t = '<transform name="to_world"><translate x="0" y="-0.5" z="0"/></transform>' if lum else ""
+        em = '<emitter type="area"><rgb name="radiance" value="18.387, 10.9873, 2.75357"/></emitter>' if lum else ""
+        sh += f'<shape type="obj"><string name="filename" value="{mesh_dir}/{fn}"/>{t}<ref id="{b}"/>{em}</shape>'
+    sp = f'<integer name="samples_per_pass" value="{spp_pass}"/>' if spp_pass and spp_pass < spp else ""
+    return f"""<scene version="2.0.0"><integrator type="path"><integer name="max_depth" value="{max_depth}"/>
+<integer name="block_size" value="32"/>{sp}</integrator>
+<sensor type="perspective"><string name="fov_axis" value="smaller"/><float name="near_clip" value="10"/>
+<float name="far_clip" value="2800"/><float name="fov" value="39.3077"/>
+<transform name="to_world"><lookat origin="278, 273, -800" target="278, 273, -799" up="0, 1, 0"/></transform>
+<sampler type="independent"><integer name="sample_count" value="{spp}"/></sampler>
+<film type="hdrfilm"><integer name="width" value="{res}"/><integer name="height" value="{res}"/><rfilter type="box"/>
+<string name="pixel_format" value="rgb"/><string name="component_format" value="float32"/><string name="file_format" value="pfm"/></film>
+</sensor>{bs}{sh}</scene>"""
+
+
+def run_reference_cli(res, spp, spp_pass, max_depth, threads):
+    """-> (seconds of the render as logged by the reference, samples) or None if it cannot run here."""
+    dist = _ref_dist()
+    if not dist:
+        return None
+    env = dict(os.environ); env["LD_LIBRARY_PATH"] = dist + ":" + env.get("LD_LIBRARY_PATH", "")
+    with tempfile.TemporaryDirectory() as td:
+        sp = os.path.join(td, "s.xml")
+        open(sp, "w").write(_ref_cbox_xml(res, spp, spp_pass, max_depth))
+        try:
+            r = subprocess.run([os.path.join(dist, "mitsuba"), "-m", "scalar_rgb", "-t", str(threads), "-o",
+                                os.path.join(td, "o.pfm"), sp], env=env, capture_output=True, text=True, timeout=1200)
+        except Exception:
+            return None
+        if r.returncode != 0:
+            return None
+        # "Rendering finished. (took 1.23s)"  integrator.cpp:174-176
+        import re
+        m = re.search(r"Rendering finished\. \(took ([0-9.]+)(ms|s|m)", r.stdout + r.stderr)
+        if not m:
+            return None
+        t = float(m.group(1)) * {"ms": 1e-3, "s": 1.0, "m": 60.0}[m.group(2)]
+        return t, res * res * spp
+
+
+def run_oracle_port(res, spp, spp_pass, max_depth, threads):
+    from mitsuba2_b200 import abi, scenes
+    from tests import oracle_lib as O
+    sb = scenes.cbox(O.OracleHost(), res, res)
+    rp = abi.render_params(max_depth=max_depth, rr_depth=5, spp=spp, samples_per_pass=spp_pass, block_size=32)
+    t0 = time.perf_counter()
+    O.render(sb, rp, threads=threads)
+    return time.perf_counter() - t0, res * res * spp
+
+
+def cpu_sample(a, spp):
+    """One bounded CPU sample of the workload: same scene / resolution / depth, fewer spp."""
+    cores = os.cpu_count() or 1
+    spp_pass = min(a.spp_per_pass or spp, spp)
+    r = run_reference_cli(a.res, spp, spp_pass, a.max_depth, cores)
+    kind = "reference"
+    if r is None:
+        r = run_oracle_port(a.res, spp, spp_pass, a.max_depth, cores)
+        kind = "port"
+    t, n = r
+    return dict(value=n / t / 1e6, unit="Msamples/s", cores=cores, kind=kind,
+                sample=f"cbox {a.res}x{a.res}, {spp} spp (samples_per_pass {spp_pass}), max_depth {a.max_depth}, "
+                       f"{'mitsuba -m scalar_rgb -t %d' % cores if kind == 'reference' else 'oracle/b2o.c, %d threads' % cores}, {t:.2f} s")
+
+
+def main_reference(a, rank):
+    if rank != 0:
+        return
+    spp = 4                       # bounded sample per step (~1-3 s of host time)
+    for _ in range(min(a.warmup, 1)):
+        cpu_sample(a, spp)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        vals.append(cpu_sample(a, spp))
+    dt = time.perf_counter() - t0
+    v = float(np.mean([x["value"] for x in vals]))
+    cb = dict(vals[-1]); cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cbox {a.res}x{a.res}, {a.spp} spp (timed on a {spp}-spp sample per step), max_depth {a.max_depth}, "
+                               "diffuse + area emitter, box filter, independent sampler seed 0, block_size 32"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index; self.rows = []; self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower() == "active":
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+from mitsuba2_b200.dist import CudaArray  # noqa: E402,F401
+
+
+def main_b2pt(a, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from mitsuba2_b200 import abi, api, scenes
+
+    if not torch.cuda.is_available() or api.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (libb2pt has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sb = scenes.cbox(api.Host(), a.res, a.res)
+    scene = api.Scene(sb)
+    integ = api.PathIntegrator(max_depth=a.max_depth, rr_depth=5, samples_per_pass=a.spp_per_pass, block_size=32)
+    H = W = a.res
+    n_samples = H * W * a.spp
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # > 126 MB L2
+    host_film = torch.empty((H, W, 5), dtype=torch.float32).pin_memory().numpy()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(flags=0):
+        """-> device ms of this rank's render (+ film reduce), stats"""
+        flush.zero_()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ptr = integ.render_device(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots, flags=flags)
+        if world > 1:
+            film = torch.as_tensor(CudaArray(ptr, (H, W, 5)), device="cuda")
+            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)          # the single collective: film XYZAW -> rank 0
+        e1.record(); e1.synchronize()
+        return e0.elapsed_time(e1), dict(integ.stats)
+
+    def step_e2e():
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        integ.render(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots, out=host_film)
+        if world > 1:      # host-side sum of the rank films happens on the caller side in e2e mode
+            t = torch.from_numpy(host_film).cuda()
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0:
+                host_film[...] = t.cpu().numpy()
+            torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    for _ in range(max(a.warmup, 3)):
+        step_device()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ms_steps, stats = [], []
+    for _ in range(a.steps):
+        ms, st = step_device()
+        ms_steps.append(ms); stats.append(st)
+    barrier()
+    total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clk = clocks.stop() if rank == 0 else None
+
+    # e2e: same metric through the public host-buffer API
+    step_e2e()
+    barrier()
+    e2e_t = []
+    for _ in range(a.steps):
+        e2e_t.append(step_e2e())
+    barrier()
+    e2e_total = torch.tensor([sum(e2e_t)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
+    e2e_total = float(e2e_total.item())
+
+    # per-stage device time: one extra step with every launch bracketed by CUDA events
+    roof = None; stages = None
+    if not a.no_stage_timing:
+        ms_t, st = step_device(flags=abi.FLAG_STAGE_TIMING)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        n_it = st["n_iterations"]
+        units = {"regen": (st["n_samples"], B_RAYGEN + B_FILM), "intersect": (st["n_segments"], B_HIT),
+                 "shade": (st["n_segments"], B_SHADE + B_COMPACT), "shadow": (st["n_shadow_rays"], B_SHADOW)}
+        stages = {}
+        for k, (n, b) in units.items():
+            t = st["ms_" + k]
+            stages[k] = {"ms": t, "units": n, "bytes_per_unit": b, "gbs": (n * b / (t * 1e-3) / 1e9) if t > 0 else None,
+                         "avg_launch_us": t / max(n_it, 1) * 1e3}
+        dom = max(stages, key=lambda k: stages[k]["ms"])
+        ach = stages[dom]["gbs"]
+        tot_bytes = sum(n * b for n, b in units.values())
+        tot_t = sum(stages[k]["ms"] for k in stages)
+        roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak if ach else None, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "all_stages_gbs": tot_bytes / (tot_t * 1e-3) / 1e9 if tot_t > 0 else None,
+                "all_stages_frac": tot_bytes / (tot_t * 1e-3) / 1e9 / peak if tot_t > 0 else None,
+                "step_ms_with_timing": ms_t}
+
+    if rank == 0:
+        st = stats[-1]
+        n_items = st["n_samples"] // max(1, (a.spp_per_pass or a.spp))
+        value = n_samples * a.steps / (total_ms * 1e-3) / 1e6
+        e2e_v = n_samples * a.steps / e2e_total / 1e6
+        line = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cbox {a.res}x{a.res}, {a.spp} spp, max_depth {a.max_depth}, diffuse + area emitter, box filter "
+                                   f"(BASELINE configs[1])", "samples_per_pass": a.spp_per_pass or a.spp, "block_size": 32, "seed": 0,
+                       "parallelism": f"pixel blocks b % {world} == rank, one NCCL reduce of the film" if world > 1 else "1 GPU",
+                       "l2": "256 MB flush between steps; wavefront queues > L2", "lane_slots": a.lane_slots or "auto"},
+            "mean_segments_per_sample": st["n_segments"] * world / n_samples if world == 1 else None,
+            "e2e": {"value": e2e_v, "unit": "Msamples/s",
+                    "h2d_bytes_per_step": int(8 * (H * W // world) + 4 * min(1 << 22, max(1, n_items))),
+                    "d2h_bytes_per_step": int(H * W * 5 * 4 + 64 * st["n_iterations"] // 8)},
+            "gpu_launches": int(sum(s["n_launches"] for s in stats)),
+            "clocks": clk,
+        }
+        if roof:
+            line["roofline"] = roof; line["stages"] = stages
+        if a.cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_sample(a, 4)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    if a.impl == "reference":
+        main_reference(a, rank)
+    else:
+        main_b2pt(a, rank, world, local)
+
+
+if __name__ == "__main__":
+    main()
