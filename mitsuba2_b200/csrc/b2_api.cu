@@ -55,11 +55,9 @@ template <typename T> struct DBuf {
 
 struct B2Scene {
     DScene d{};
-    DBuf<float4> nodes, tri_pos, tri_nrm;
-    DBuf<B2Bsdf> bsdfs;
-    DBuf<DEmitter> emitters;
-    DBuf<float> cdf;
-    DBuf<uint32_t> prim_to_slot;
+    DBuf<float4> nodes, tri_isect;
+    DBuf<unsigned char> blob;       // tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
+    int shade_smem_bytes = 0;
     uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
     int smem_bytes = 0;
     int sm_count = 148;
@@ -126,7 +124,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     }
     B2Bvh4 bvh; b2_build_bvh4(tris, bvh);
 
-    std::vector<float4> tri_pos(3 * (size_t) nt), tri_nrm(3 * (size_t) nt);
+    std::vector<float4> tri_pos(3 * (size_t) nt), tri_nrm(3 * (size_t) nt), tri_isect(3 * (size_t) nt);
     std::vector<uint32_t> prim_to_slot(nt);
     auto u2f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
     for (uint32_t slot = 0; slot < nt; ++slot) {
@@ -137,6 +135,13 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         uint32_t f = prim - mesh_first[m];
         const float wpos[3] = { u2f(prim), u2f(m), 0.f };
         const float wnrm[3] = { u2f((uint32_t) me.bsdf), u2f((uint32_t) me.emitter), u2f(me.normals ? 1u : 0u) };
+        {
+            const float *q0 = me.positions + 3 * (size_t) me.faces[3 * f], *q1 = me.positions + 3 * (size_t) me.faces[3 * f + 1],
+                        *q2 = me.positions + 3 * (size_t) me.faces[3 * f + 2];
+            tri_isect[3 * (size_t) slot] = make_float4(q0[0], q0[1], q0[2], wpos[0]);
+            tri_isect[3 * (size_t) slot + 1] = make_float4(q1[0] - q0[0], q1[1] - q0[1], q1[2] - q0[2], 0.f);
+            tri_isect[3 * (size_t) slot + 2] = make_float4(q2[0] - q0[0], q2[1] - q0[1], q2[2] - q0[2], 0.f);
+        }
         for (int v = 0; v < 3; ++v) {
             const float *p = me.positions + 3 * (size_t) me.faces[3 * f + v];
             tri_pos[3 * (size_t) slot + v] = make_float4(p[0], p[1], p[2], wpos[v]);
@@ -178,18 +183,33 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     std::vector<float4> nodes(bvh.nodes.size() / 4);
     std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(float));
 
+    // one blob for the shading tables (so that small scenes can be staged with one bulk copy)
+    auto align16 = [](size_t x) { return (x + 15) & ~(size_t) 15; };
+    size_t off_pos = 0, off_nrm = off_pos + align16(tri_pos.size() * 16), off_p2s = off_nrm + align16(tri_nrm.size() * 16),
+           off_cdf = off_p2s + align16(prim_to_slot.size() * 4), off_bsdf = off_cdf + align16(cdf.size() * 4),
+           off_em = off_bsdf + align16(bsdfs.size() * sizeof(B2Bsdf)), blob_bytes = off_em + align16(ems.size() * sizeof(DEmitter));
+    std::vector<unsigned char> blob(std::max<size_t>(blob_bytes, 16), 0);
+    if (!tri_pos.empty()) std::memcpy(blob.data() + off_pos, tri_pos.data(), tri_pos.size() * 16);
+    if (!tri_nrm.empty()) std::memcpy(blob.data() + off_nrm, tri_nrm.data(), tri_nrm.size() * 16);
+    if (!prim_to_slot.empty()) std::memcpy(blob.data() + off_p2s, prim_to_slot.data(), prim_to_slot.size() * 4);
+    if (!cdf.empty()) std::memcpy(blob.data() + off_cdf, cdf.data(), cdf.size() * 4);
+    if (!bsdfs.empty()) std::memcpy(blob.data() + off_bsdf, bsdfs.data(), bsdfs.size() * sizeof(B2Bsdf));
+    if (!ems.empty()) std::memcpy(blob.data() + off_em, ems.data(), ems.size() * sizeof(DEmitter));
     cudaError_t e = cudaSuccess;
-    if ((e = s->nodes.upload(nodes)) != cudaSuccess || (e = s->tri_pos.upload(tri_pos)) != cudaSuccess ||
-        (e = s->tri_nrm.upload(tri_nrm)) != cudaSuccess || (e = s->bsdfs.upload(bsdfs)) != cudaSuccess ||
-        (e = s->emitters.upload(ems)) != cudaSuccess || (e = s->cdf.upload(cdf)) != cudaSuccess ||
-        (e = s->prim_to_slot.upload(prim_to_slot)) != cudaSuccess) {
+    if ((e = s->nodes.upload(nodes)) != cudaSuccess || (e = s->tri_isect.upload(tri_isect)) != cudaSuccess ||
+        (e = s->blob.upload(blob)) != cudaSuccess) {
         delete s;
         return fail(B2_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
     s->n_tris = nt; s->n_nodes = bvh.n_nodes; s->bvh_depth = bvh.depth;
     DScene &d = s->d;
-    d.nodes = s->nodes.p; d.tri_pos = s->tri_pos.p; d.tri_nrm = s->tri_nrm.p; d.bsdfs = s->bsdfs.p;
-    d.emitters = s->emitters.p; d.cdf = s->cdf.p; d.prim_to_slot = s->prim_to_slot.p;
+    d.nodes = s->nodes.p; d.tri_isect = s->tri_isect.p;
+    d.blob = s->blob.p; d.blob_bytes = (uint32_t) blob_bytes;
+    d.tri_pos = (const float4 *) (s->blob.p + off_pos); d.tri_nrm = (const float4 *) (s->blob.p + off_nrm);
+    d.prim_to_slot = (const uint32_t *) (s->blob.p + off_p2s); d.cdf = (const float *) (s->blob.p + off_cdf);
+    d.bsdfs = (const B2Bsdf *) (s->blob.p + off_bsdf); d.emitters = (const DEmitter *) (s->blob.p + off_em);
+    d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
+    s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
     d.n_nodes = bvh.n_nodes; d.n_tris = nt; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
     d.sensor = desc->sensor; d.film = desc->film;
     // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
@@ -199,6 +219,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u));
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
     cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
@@ -325,7 +346,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             tick();
             k_intersect<<<grid, threads, s->smem_bytes, stream>>>(s->d, q, cur);
             tick();
-            k_shade<<<grid, threads, 0, stream>>>(s->d, q, cur);
+            k_shade<<<grid, threads, s->shade_smem_bytes, stream>>>(s->d, q, cur);
             tick();
             k_shadow<<<grid, threads, s->smem_bytes, stream>>>(s->d, q);
             tick();

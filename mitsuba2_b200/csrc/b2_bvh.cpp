@@ -28,7 +28,7 @@ struct Builder {
     std::vector<float> cent;        // 3 per tri
     std::vector<uint32_t> idx;
     std::vector<Node2> nodes;
-    static constexpr int kBins = 16, kMaxLeaf = 4;
+    static constexpr int kBins = 16, kMaxLeaf = 2;
 
     explicit Builder(const std::vector<B2BvhTri> &t) : tris(t) {}
 

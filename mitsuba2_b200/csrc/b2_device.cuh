@@ -5,11 +5,16 @@
 #include "../../include/b2pt.h"
 #include "b2_math.cuh"
 
+// Scene-table loads: the tables live in global memory or (small scenes) in a shared-memory copy,
+// so they are read through generic pointers.
+#define B2_LD(p) (*(p))
+
 // ---- scene layout in HBM --------------------------------------------------------------------
 // Triangles are stored in BVH leaf order ("slots"), two SoA streams of 3 x float4 per slot:
 //   tri_pos[3*s + 0] = (p0.xyz, prim id bits)     prim = global triangle index (mesh order, face order)
 //   tri_pos[3*s + 1] = (p1.xyz, mesh id bits)
 //   tri_pos[3*s + 2] = (p2.xyz, 0)
+//   tri_isect[3*s + 0..2] = (p0.xyz, prim id bits), (p1-p0, 0), (p2-p0, 0)   traversal copy
 //   tri_nrm[3*s + 0] = (n0.xyz, bsdf index bits)  vertex normals (mesh.h:344-348)
 //   tri_nrm[3*s + 1] = (n1.xyz, emitter index bits or -1)
 //   tri_nrm[3*s + 2] = (n2.xyz, has_normals flag bits)
@@ -30,6 +35,7 @@ struct DScene {
     const float4 *nodes;
     const float4 *tri_pos;
     const float4 *tri_nrm;
+    const float4 *tri_isect;    // traversal copy: (p0, prim), (e1, -), (e2, -)
     const B2Bsdf *bsdfs;
     const DEmitter *emitters;
     const float *cdf;
@@ -37,6 +43,9 @@ struct DScene {
     uint32_t n_nodes, n_tris, n_emitters, n_bsdfs;
     uint32_t smem_nodes;        // nodes [0, smem_nodes) are staged in shared memory
     uint32_t smem_tris;         // 1: all triangle positions staged in shared memory too
+    const unsigned char *blob;  // one allocation holding tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
+    uint32_t blob_bytes;        // size of the blob (multiple of 16)
+    uint32_t shade_smem;        // 1: k_shade stages the whole blob into shared memory
     B2Sensor sensor;
     B2Film film;
 };
@@ -75,8 +84,8 @@ B2_D float3 to_local(const SI &si, float3 v) { return v3(dot(v, si.sh_s), dot(v,
 B2_D float3 to_world(const SI &si, float3 v) { return (si.sh_s * v.x + si.sh_t * v.y) + si.sh_n * v.z; }   // frame.h:35-37
 
 B2_D void si_fill(const DScene &sc, uint32_t slot, float u, float v, float3 ray_d, SI &si) {
-    float4 a0 = __ldg(&sc.tri_pos[3 * slot]), a1 = __ldg(&sc.tri_pos[3 * slot + 1]), a2 = __ldg(&sc.tri_pos[3 * slot + 2]);
-    float4 m0 = __ldg(&sc.tri_nrm[3 * slot]), m1 = __ldg(&sc.tri_nrm[3 * slot + 1]), m2 = __ldg(&sc.tri_nrm[3 * slot + 2]);
+    float4 a0 = B2_LD(&sc.tri_pos[3 * slot]), a1 = B2_LD(&sc.tri_pos[3 * slot + 1]), a2 = B2_LD(&sc.tri_pos[3 * slot + 2]);
+    float4 m0 = B2_LD(&sc.tri_nrm[3 * slot]), m1 = B2_LD(&sc.tri_nrm[3 * slot + 1]), m2 = B2_LD(&sc.tri_nrm[3 * slot + 2]);
     float3 p0 = v3(a0), p1 = v3(a1), p2 = v3(a2);
     float b1 = u, b2 = v, b0 = 1.f - b1 - b2;
     float3 dp0 = p1 - p0, dp1 = p2 - p0;
@@ -310,7 +319,7 @@ B2_D uint32_t distr_sample(const float *cdf, uint32_t first, uint32_t last, floa
     uint32_t iterations = start < end ? (32 - __clz(end - start)) : 0;     // log2i(end-start)+1
     for (uint32_t i = 0; i < iterations; ++i) {                              // array_utils.h:153-170
         uint32_t middle = (start + end) >> 1;
-        bool cond = __ldg(&cdf[middle]) < value;
+        bool cond = B2_LD(&cdf[middle]) < value;
         if (cond) start = (middle + 1 < end) ? middle + 1 : end; else end = middle;
     }
     return start;
@@ -319,21 +328,21 @@ B2_D uint32_t distr_sample(const float *cdf, uint32_t first, uint32_t last, floa
 B2_D float3 area_sample_direction(const DScene &sc, const DEmitter &em, float3 ref_p, float sx, float sy, DS &ds) {
     const float *cdf = sc.cdf + em.cdf_offset;
     uint32_t face = distr_sample(cdf, em.valid_first, em.valid_last, em.cdf_sum, sy);
-    uint32_t slot = __ldg(&sc.prim_to_slot[em.first_prim + face]);
-    float4 a0 = __ldg(&sc.tri_pos[3 * slot]), a1 = __ldg(&sc.tri_pos[3 * slot + 1]), a2 = __ldg(&sc.tri_pos[3 * slot + 2]);
+    uint32_t slot = B2_LD(&sc.prim_to_slot[em.first_prim + face]);
+    float4 a0 = B2_LD(&sc.tri_pos[3 * slot]), a1 = B2_LD(&sc.tri_pos[3 * slot + 1]), a2 = B2_LD(&sc.tri_pos[3 * slot + 2]);
     float3 p0 = v3(a0), e0 = v3(a1) - p0, e1 = v3(a2) - p0;
     float3 cr = cross(e0, e1);
     float area = 0.5f * sqrtf(dot(cr, cr));                      // mesh.h:108-116
     float pmf = area * em.cdf_norm;                                // distr_1d.h:194-204
-    float cdfv = face > 0 ? __ldg(&cdf[face - 1]) * em.cdf_norm : 0.f;
+    float cdfv = face > 0 ? B2_LD(&cdf[face - 1]) * em.cdf_norm : 0.f;
     sy = (sy - cdfv) / pmf;
     float t = b2_safe_sqrt(1.f - sx);                             // warp.h:152-156
     float bx = 1.f - t, by = t * sy;
     ds.p = (p0 + e0 * bx) + e1 * by;                               // mesh.cpp:370
     float pdf = em.cdf_norm;
-    float4 m2 = __ldg(&sc.tri_nrm[3 * slot + 2]);
+    float4 m2 = B2_LD(&sc.tri_nrm[3 * slot + 2]);
     if (__float_as_uint(m2.w)) {                                   // mesh.cpp:386-394
-        float4 m0 = __ldg(&sc.tri_nrm[3 * slot]), m1 = __ldg(&sc.tri_nrm[3 * slot + 1]);
+        float4 m0 = B2_LD(&sc.tri_nrm[3 * slot]), m1 = B2_LD(&sc.tri_nrm[3 * slot + 1]);
         ds.n = normalize((v3(m0) * (1.f - bx - by) + v3(m1) * bx) + v3(m2) * by);
     } else
         ds.n = normalize(cr);

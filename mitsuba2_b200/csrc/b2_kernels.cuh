@@ -99,7 +99,7 @@ B2_D SmemScene stage_scene(const DScene &sc, unsigned char *smem_raw) {
     if (threadIdx.x == 0) {
         mbar_expect_tx(mbar, node_bytes + tri_bytes);
         if (node_bytes) stage_bulk(dst, sc.nodes, node_bytes, mbar);
-        if (tri_bytes) stage_bulk((char *) dst + node_bytes, sc.tri_pos, tri_bytes, mbar);
+        if (tri_bytes) stage_bulk((char *) dst + node_bytes, sc.tri_isect, tri_bytes, mbar);
     }
     mbar_wait(mbar, 0);
     s.nodes = dst;
@@ -111,63 +111,87 @@ B2_D SmemScene stage_scene(const DScene &sc, unsigned char *smem_raw) {
 // Closest hit = lexicographic min over (t, -prim) of all triangles passing the Moeller-Trumbore
 // test, i.e. on exact t ties the HIGHER prim index wins (the reference's kd-tree keeps the last
 // primitive of a leaf on `t <= maxt`, kdtree.h:2140-2154). The result does not depend on the
-// traversal order.
+// traversal order, so the box tests below are free to be approximate as long as they are
+// conservative (child boxes are inflated at build time, b2_bvh.cpp).
 struct Hit { float t, u, v; uint32_t slot, prim; };
+
+// Triangle test on the traversal copy of the geometry: tri_isect[3*s] = (p0, prim), (e1 = p1-p0, -),
+// (e2 = p2-p0, -). e1/e2 are the same fp32 values Mesh::ray_intersect_triangle computes on the fly
+// (mesh.h:200-203), so the result is bit-identical to tri_intersect().
+B2_D bool tri_isect(float3 p0, float3 e1, float3 e2, const Ray &ray, float tmax, float &t, float &u, float &v) {
+    float3 pvec = cross(ray.d, e2);
+    float inv_det = b2_rcp(dot(e1, pvec));
+    float3 tvec = ray.o - p0;
+    u = dot(tvec, pvec) * inv_det;
+    if (!(u >= 0.f && u <= 1.f)) return false;
+    float3 qvec = cross(tvec, e1);
+    v = dot(ray.d, qvec) * inv_det;
+    if (!(v >= 0.f && u + v <= 1.f)) return false;
+    t = dot(e2, qvec) * inv_det;
+    return t >= ray.mint && t <= tmax;
+}
 
 template <bool ANY>
 B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
     best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu;
     if (sc.n_tris == 0) return false;
     float tmax = ray.maxt;
-    float3 d = ray.d;
-    // guard zero components: 1/0 -> inf would give NaN on (lo-o)*inf when lo == o
-    float dx = fabsf(d.x) > 1e-20f ? d.x : (d.x < 0.f ? -1e-20f : 1e-20f);
-    float dy = fabsf(d.y) > 1e-20f ? d.y : (d.y < 0.f ? -1e-20f : 1e-20f);
-    float dz = fabsf(d.z) > 1e-20f ? d.z : (d.z < 0.f ? -1e-20f : 1e-20f);
-    float idx = 1.f / dx, idy = 1.f / dy, idz = 1.f / dz;
-    int stack_c[24]; float stack_t[24];
-    int sp = 0;
-    int cur = 0;                // node index (inner), or leaf code < 0
-    float cur_t = ray.mint;
-    for (;;) {
-        if (cur >= 0) {
-            const float4 *np = ((uint32_t) cur < sc.smem_nodes) ? sm.nodes + 8 * cur : nullptr;
-            float4 lox, loy, loz, hix, hiy, hiz, chf;
-            if (np) { lox = np[0]; loy = np[1]; loz = np[2]; hix = np[3]; hiy = np[4]; hiz = np[5]; chf = np[6]; }
-            else {
+    // reciprocal direction for the slab tests only (approximate is fine: tests are conservative)
+    float dx = fabsf(ray.d.x) > 1e-20f ? ray.d.x : (ray.d.x < 0.f ? -1e-20f : 1e-20f);
+    float dy = fabsf(ray.d.y) > 1e-20f ? ray.d.y : (ray.d.y < 0.f ? -1e-20f : 1e-20f);
+    float dz = fabsf(ray.d.z) > 1e-20f ? ray.d.z : (ray.d.z < 0.f ? -1e-20f : 1e-20f);
+    float idx = __fdividef(1.f, dx), idy = __fdividef(1.f, dy), idz = __fdividef(1.f, dz);
+    float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
+    // near / far plane rows of the SoA node, selected once per ray by the direction signs
+    const int nxi = dx < 0.f ? 3 : 0, fxi = dx < 0.f ? 0 : 3;
+    const int nyi = dy < 0.f ? 4 : 1, fyi = dy < 0.f ? 1 : 4;
+    const int nzi = dz < 0.f ? 5 : 2, fzi = dz < 0.f ? 2 : 5;
+    // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the
+    // same kind of work; DONE is the stack sentinel.
+    const int DONE = 0x7fffffff;
+    int stack[40];
+    stack[0] = DONE;
+    int sp = 1;
+    int cur = 0;                // [0, DONE): inner node index, < 0: leaf code
+    while (cur != DONE) {
+        while ((uint32_t) cur < (uint32_t) DONE) {
+            float4 nx, ny, nz, fx, fy, fz, chf;
+            if ((uint32_t) cur < sc.smem_nodes) {
+                const float4 *np = sm.nodes + 8 * cur;
+                nx = np[nxi]; ny = np[nyi]; nz = np[nzi]; fx = np[fxi]; fy = np[fyi]; fz = np[fzi]; chf = np[6];
+            } else {
                 const float4 *gp = sc.nodes + 8 * (size_t) cur;
-                lox = __ldg(gp); loy = __ldg(gp + 1); loz = __ldg(gp + 2); hix = __ldg(gp + 3); hiy = __ldg(gp + 4);
-                hiz = __ldg(gp + 5); chf = __ldg(gp + 6);
+                nx = __ldg(gp + nxi); ny = __ldg(gp + nyi); nz = __ldg(gp + nzi);
+                fx = __ldg(gp + fxi); fy = __ldg(gp + fyi); fz = __ldg(gp + fzi); chf = __ldg(gp + 6);
             }
-            const float lo_x[4] = { lox.x, lox.y, lox.z, lox.w }, lo_y[4] = { loy.x, loy.y, loy.z, loy.w },
-                        lo_z[4] = { loz.x, loz.y, loz.z, loz.w }, hi_x[4] = { hix.x, hix.y, hix.z, hix.w },
-                        hi_y[4] = { hiy.x, hiy.y, hiy.z, hiy.w }, hi_z[4] = { hiz.x, hiz.y, hiz.z, hiz.w };
-            const int ch[4] = { __float_as_int(chf.x), __float_as_int(chf.y), __float_as_int(chf.z), __float_as_int(chf.w) };
-            int hc[4]; float ht[4]; int nh = 0;
-            #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float t0x = (lo_x[k] - ray.o.x) * idx, t1x = (hi_x[k] - ray.o.x) * idx;
-                float t0y = (lo_y[k] - ray.o.y) * idy, t1y = (hi_y[k] - ray.o.y) * idy;
-                float t0z = (lo_z[k] - ray.o.z) * idz, t1z = (hi_z[k] - ray.o.z) * idz;
-                float tn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fmaxf(fminf(t0z, t1z), ray.mint));
-                float tf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fminf(fmaxf(t0z, t1z), tmax));
-                bool h = ch[k] != 0 && tn <= tf * 1.0000004f;
-                if (h) {     // insertion sort, descending tn (nearest popped first)
-                    int j = nh++;
-                    while (j > 0 && ht[j - 1] < tn) { ht[j] = ht[j - 1]; hc[j] = hc[j - 1]; --j; }
-                    ht[j] = tn; hc[j] = ch[k];
-                }
-            }
-            for (int j = 0; j < nh; ++j) { stack_c[sp] = hc[j]; stack_t[sp] = ht[j]; ++sp; }
-        } else {
+            const float tlim = tmax * 1.0000004f;
+            #define B2_SLAB(k) \
+                float tn##k = fmaxf(fmaxf(b2_fma(nx.k, idx, oox), b2_fma(ny.k, idy, ooy)), fmaxf(b2_fma(nz.k, idz, ooz), ray.mint)); \
+                float tf##k = fminf(fminf(b2_fma(fx.k, idx, oox), b2_fma(fy.k, idy, ooy)), fminf(b2_fma(fz.k, idz, ooz), tlim)); \
+                int c##k = __float_as_int(chf.k); \
+                bool h##k = c##k != 0 && tn##k <= tf##k;
+            B2_SLAB(x) B2_SLAB(y) B2_SLAB(z) B2_SLAB(w)
+            #undef B2_SLAB
+            // nearest hit child first; the others go on the stack (unordered)
+            float bd = B2_INF; int bc = 0;
+            if (hx) { bd = tnx; bc = cx; }
+            if (hy && tny < bd) { bd = tny; bc = cy; }
+            if (hz && tnz < bd) { bd = tnz; bc = cz; }
+            if (hw && tnw < bd) { bd = tnw; bc = cw; }
+            if (hx && cx != bc) stack[sp++] = cx;
+            if (hy && cy != bc) stack[sp++] = cy;
+            if (hz && cz != bc) stack[sp++] = cz;
+            if (hw && cw != bc) stack[sp++] = cw;
+            cur = bc != 0 ? bc : stack[--sp];
+        }
+        while (cur < 0) {
             uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
             for (uint32_t s = first; s < first + count; ++s) {
                 float4 a0, a1, a2;
                 if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
-                else { a0 = __ldg(&sc.tri_pos[3 * (size_t) s]); a1 = __ldg(&sc.tri_pos[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_pos[3 * (size_t) s + 2]); }
+                else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
                 float t, u, v;
-                Ray r = ray; r.maxt = tmax;
-                if (tri_intersect(v3(a0), v3(a1), v3(a2), r, t, u, v)) {
+                if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
                     if (ANY) return true;
                     uint32_t prim = __float_as_uint(a0.w);
                     if (t < best.t || (t == best.t && prim > best.prim)) {
@@ -176,15 +200,10 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
                     }
                 }
             }
-        }
-        // pop
-        for (;;) {
-            if (sp == 0) return best.t < B2_INF;
-            --sp;
-            cur = stack_c[sp]; cur_t = stack_t[sp];
-            if (cur_t <= tmax * 1.0000004f) break;
+            cur = stack[--sp];
         }
     }
+    return best.t < B2_INF;
 }
 
 // ---- K2: closest hit ----------------------------------------------------------------------------
@@ -361,7 +380,28 @@ __global__ void __launch_bounds__(256) k_regen(DScene sc, Queues q, int cur) {
 }
 
 // ---- K4: shade (SI fill + one loop body of PathIntegrator::sample) ----------------------------
-__global__ void __launch_bounds__(256) k_shade(DScene sc, Queues q, int cur) {
+// Small scenes: stage the shading tables (triangles, normals, CDFs, BSDF + emitter records) into
+// shared memory with one bulk copy and rebase the table pointers onto the copy.
+B2_D void stage_shade_tables(DScene &sc, unsigned char *smem_raw) {
+    if (!sc.shade_smem) return;
+    uint64_t *mbar = (uint64_t *) smem_raw;
+    unsigned char *dst = smem_raw + 16;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { mbar_expect_tx(mbar, sc.blob_bytes); stage_bulk(dst, sc.blob, sc.blob_bytes, mbar); }
+    mbar_wait(mbar, 0);
+    const unsigned char *g = sc.blob;
+    sc.tri_pos = (const float4 *) (dst + ((const unsigned char *) sc.tri_pos - g));
+    sc.tri_nrm = (const float4 *) (dst + ((const unsigned char *) sc.tri_nrm - g));
+    sc.prim_to_slot = (const uint32_t *) (dst + ((const unsigned char *) sc.prim_to_slot - g));
+    sc.cdf = (const float *) (dst + ((const unsigned char *) sc.cdf - g));
+    sc.bsdfs = (const B2Bsdf *) (dst + ((const unsigned char *) sc.bsdfs - g));
+    sc.emitters = (const DEmitter *) (dst + ((const unsigned char *) sc.emitters - g));
+}
+
+__global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q, int cur) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    stage_shade_tables(sc, smem_raw);
     uint32_t count = q.cnt[cur];
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const uint32_t *list = q.list[cur];
