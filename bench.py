@@ -287,13 +287,22 @@ def main_b2pt(a, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         n_it = st["n_iterations"]
-        units = {"regen": (st["n_samples"], B_RAYGEN + B_FILM), "intersect": (st["n_segments"], B_HIT),
-                 "shade": (st["n_segments"], B_SHADE + B_COMPACT), "shadow": (st["n_shadow_rays"], B_SHADOW)}
+        # algorithmic bytes per stage: K2 52 B/ray; K4 224 + K5 8 B/segment, plus — fused into the
+        # same launch — K1 80 B/regenerated sample and K6 40 B/sample put; K3 68 B/shadow ray (+ K6 for the
+        # samples it completes)
+        put_sh = st.get("n_put_shadow", 0)
+        stage_bytes = {
+            "intersect": st["n_segments"] * B_HIT,
+            "shade": st["n_segments"] * (B_SHADE + B_COMPACT) + st["n_samples"] * B_RAYGEN + (st["n_samples"] - put_sh) * B_FILM,
+            "shadow": st["n_shadow_rays"] * B_SHADOW + put_sh * B_FILM,
+        }
+        stage_units = {"intersect": st["n_segments"], "shade": st["n_segments"], "shadow": st["n_shadow_rays"]}
         stages = {}
-        for k, (n, b) in units.items():
+        for k, nbytes in stage_bytes.items():
             t = st["ms_" + k]
-            stages[k] = {"ms": t, "units": n, "bytes_per_unit": b, "gbs": (n * b / (t * 1e-3) / 1e9) if t > 0 else None,
+            stages[k] = {"ms": t, "units": stage_units[k], "bytes": nbytes, "gbs": (nbytes / (t * 1e-3) / 1e9) if t > 0 else None,
                          "avg_launch_us": t / max(n_it, 1) * 1e3}
+        units = {k: (1, v) for k, v in stage_bytes.items()}
         dom = max(stages, key=lambda k: stages[k]["ms"])
         ach = stages[dom]["gbs"]
         tot_bytes = sum(n * b for n, b in units.values())

@@ -98,6 +98,7 @@ class B2Stats(C.Structure):
         ("ms_total", C.c_float),
         ("ms_regen", C.c_float), ("ms_intersect", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float),
         ("bvh_nodes", C.c_uint64), ("bvh_tris", C.c_uint64),
+        ("n_put_shadow", C.c_uint64),
     ]
 
     def as_dict(self):

@@ -64,10 +64,10 @@ struct B2Scene {
     cudaStream_t stream = nullptr;
     std::atomic<int> cancel{0};
     // render state (allocated lazily, reused across renders)
-    DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c;
+    DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c, sh_r;
     DBuf<uint4> st;
-    DBuf<float2> pos;
-    DBuf<uint32_t> list0, list1, new_list, cnt, item_pixel, item_seed;
+    DBuf<float2> pos, sh_p;
+    DBuf<uint32_t> sh_f, cnt, item_pixel, item_seed;
     DBuf<unsigned long long> stats;
     DBuf<float> film;
     uint32_t *h_cnt = nullptr;           // pinned readback
@@ -293,9 +293,9 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
 
     bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
     CU(s->ray_o.alloc(slots)); CU(s->ray_d.alloc(slots)); CU(s->hit.alloc(slots)); CU(s->tp.alloc(slots)); CU(s->res.alloc(slots));
-    CU(s->sh_o.alloc(slots)); CU(s->sh_d.alloc(slots)); CU(s->sh_c.alloc(slots)); CU(s->st.alloc(slots));
-    if (wide) CU(s->pos.alloc(slots));
-    CU(s->list0.alloc(slots)); CU(s->list1.alloc(slots)); CU(s->new_list.alloc(slots));
+    CU(s->sh_o.alloc(slots)); CU(s->sh_d.alloc(slots)); CU(s->sh_c.alloc(slots)); CU(s->sh_r.alloc(slots)); CU(s->sh_f.alloc(slots));
+    CU(s->st.alloc(slots));
+    if (wide) { CU(s->pos.alloc(slots)); CU(s->sh_p.alloc(slots)); }
     CU(s->cnt.alloc(16)); CU(s->stats.alloc(8));
     CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
     CU(s->film.alloc((size_t) W * H * 5));
@@ -303,12 +303,12 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
 
     Queues q{};
     q.ray_o = s->ray_o.p; q.ray_d = s->ray_d.p; q.hit = s->hit.p; q.tp = s->tp.p; q.res = s->res.p; q.st = s->st.p;
-    q.pos = wide ? s->pos.p : nullptr;
-    q.sh_o = s->sh_o.p; q.sh_d = s->sh_d.p; q.sh_c = s->sh_c.p;
-    q.list[0] = s->list0.p; q.list[1] = s->list1.p; q.new_list = s->new_list.p; q.cnt = s->cnt.p; q.stats = s->stats.p;
+    q.pos = wide ? s->pos.p : nullptr; q.sh_p = wide ? s->sh_p.p : nullptr;
+    q.sh_o = s->sh_o.p; q.sh_d = s->sh_d.p; q.sh_c = s->sh_c.p; q.sh_r = s->sh_r.p; q.sh_f = s->sh_f.p;
+    q.cnt = s->cnt.p; q.stats = s->stats.p;
     q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
     q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
-    q.total_items = (uint32_t) total64; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
+    q.total_items = (uint32_t) total64; q.n_slots = slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
 
     cudaEvent_t ev0, ev1, evb[2];
     CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
@@ -317,24 +317,20 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     CU(cudaMemsetAsync(s->cnt.p, 0, 16 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
-    CU(cudaMemsetAsync(s->st.p, 0, (size_t) slots * sizeof(uint4), stream));
-    {   // new_list = iota, cnt[NEW] = slots
-        std::vector<uint32_t> iota(slots);
-        for (uint32_t i = 0; i < slots; ++i) iota[i] = i;
-        CU(cudaMemcpyAsync(s->new_list.p, iota.data(), slots * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        CU(cudaMemcpyAsync(s->cnt.p + CNT_NEW, &slots, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-        CU(cudaStreamSynchronize(stream));
-    }
     const int threads = 256;
     int grid = s->sm_count * 8;
     uint32_t need_blocks = (slots + threads - 1) / threads;
     if ((uint32_t) grid > need_blocks) grid = (int) std::max<uint32_t>(need_blocks, 1);
-    int cur = 0;
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
-    std::vector<cudaEvent_t> tev;     // 5 events per iteration when stage timing is on
+    std::vector<cudaEvent_t> tev;     // 4 events per iteration when stage timing is on
     auto tick = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); tev.push_back(e); } };
+    cudaEvent_t evi0 = nullptr, evi1 = nullptr;
+    if (timing) { cudaEventCreate(&evi0); cudaEventCreate(&evi1); cudaEventRecord(evi0, stream); }
+    k_init<<<grid, threads, 0, stream>>>(s->d, q);
+    if (timing) cudaEventRecord(evi1, stream);
+    ++launches;
     int pending[2] = { 0, 0 };
     bool done = false;
     int status = B2_OK;
@@ -342,15 +338,13 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         int slot = b & 1;
         for (int it = 0; it < batch; ++it) {
             tick();
-            k_regen<<<grid, threads, 0, stream>>>(s->d, q, cur);
+            k_intersect<<<grid, threads, s->smem_bytes, stream>>>(s->d, q);
             tick();
-            k_intersect<<<grid, threads, s->smem_bytes, stream>>>(s->d, q, cur);
-            tick();
-            k_shade<<<grid, threads, s->shade_smem_bytes, stream>>>(s->d, q, cur);
+            k_shade<<<grid, threads, s->shade_smem_bytes, stream>>>(s->d, q);
             tick();
             k_shadow<<<grid, threads, s->smem_bytes, stream>>>(s->d, q);
             tick();
-            cur ^= 1; ++iterations; launches += 4;
+            ++iterations; launches += 3;
         }
         CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
@@ -360,8 +354,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (pending[prev]) {
             CU(cudaEventSynchronize(evb[prev]));
             pending[prev] = 0;
-            const uint32_t *c = s->h_cnt + 16 * prev;
-            if (c[CNT_LIST0] == 0 && c[CNT_LIST1] == 0 && c[CNT_NEW] == 0) done = true;
+            if (s->h_cnt[16 * prev + CNT_ALIVE] == 0) done = true;
         }
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
         if (cudaPeekAtLastError() != cudaSuccess) break;
@@ -378,12 +371,15 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         stats->n_samples = h[ST_SAMPLES]; stats->n_segments = h[ST_SEGMENTS]; stats->n_shadow_rays = h[ST_SHADOW];
         stats->n_invalid = h[ST_INVALID]; stats->n_iterations = iterations; stats->n_launches = launches;
         stats->ms_total = ms; stats->bvh_nodes = s->n_nodes; stats->bvh_tris = s->n_tris;
-        for (size_t i = 0; i + 4 < tev.size(); i += 5) {
-            float t[4];
-            for (int k = 0; k < 4; ++k) cudaEventElapsedTime(&t[k], tev[i + k], tev[i + k + 1]);
-            stats->ms_regen += t[0]; stats->ms_intersect += t[1]; stats->ms_shade += t[2]; stats->ms_shadow += t[3];
+        for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+            float t[3];
+            for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], tev[i + k], tev[i + k + 1]);
+            stats->ms_intersect += t[0]; stats->ms_shade += t[1]; stats->ms_shadow += t[2];
         }
+        if (timing) cudaEventElapsedTime(&stats->ms_regen, evi0, evi1);      // k_init
+        stats->n_put_shadow = h[4];
     }
+    if (evi0) { cudaEventDestroy(evi0); cudaEventDestroy(evi1); }
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
     if (d_xyzaw) *d_xyzaw = s->film.p;
     if (status == B2_ERR_CANCELLED) return fail(status, "render cancelled");

@@ -1,28 +1,37 @@
 // b2_kernels.cuh — the wavefront stage kernels (sm_100a).
 //
-//   K1+K6  k_regen      film put of the finished sample (ImageBlock::put, imageblock.cpp:79-172)
-//                       + next camera sample of the lane's work item (render_sample,
-//                       integrator.cpp:233-262; PerspectiveCamera::sample_ray, perspective.cpp:182-216)
-//   K2     k_intersect  closest hit: BVH4 traversal + Mesh::ray_intersect_triangle (mesh.h:194-226)
-//   K4     k_shade      SI fill fused with one iteration of PathIntegrator::sample's loop body
-//                       (path.cpp:124-208); K5 (warp-ballot compaction) is fused into its tail
-//   K3     k_shadow     any-hit visibility of the emitter sample (scene.cpp:203-207)
+// One wavefront iteration = three launches over the SoA lane queues (a lane slot keeps its
+// index for its whole life, so every queue access is a direct, coalesced float4 access):
 //
-// Queues are SoA float4 / uint4 arrays indexed by lane slot; the lists hold lane indices.
+//   K2        k_intersect  closest hit of every live lane's ray: BVH4 traversal +
+//                          Mesh::ray_intersect_triangle (mesh.h:194-226)
+//   K4+K1+K6  k_shade      SI fill fused with one iteration of PathIntegrator::sample's loop body
+//                          (path.cpp:124-208); a path that ends is put on the film
+//                          (ImageBlock::put, imageblock.cpp:79-172) and the lane regenerates the
+//                          next camera sample of its work item in place (render_sample,
+//                          integrator.cpp:233-262; perspective.cpp:182-216) or fetches the next
+//                          work item; K5: warp-ballot compaction of the emitter samples into the
+//                          dense shadow queue (one atomic per warp)
+//   K3(+K6)   k_shadow     any-hit visibility of the emitter samples (scene.cpp:203-207);
+//                          `result += contribution`, and for a path that ended on this bounce
+//                          the film put of the completed sample
+//   (k_init = the regenerate step alone, run once to fill the lanes)
 #pragma once
 #include "b2_device.cuh"
 
 struct Queues {
-    float4 *ray_o, *ray_d;      // (o.xyz, mint), (d.xyz, maxt)                      32 B
-    float4 *hit;                // (t, u, v, slot bits); t = +inf: miss               16 B
-    float4 *tp;                 // (throughput.rgb, eta)                              16 B
-    float4 *res;                // (result.rgb, pdf of the last BSDF sample)          16 B
-    uint4 *st;                  // (rng.lo, rng.hi, work item, depth|flags|samples_left) 16 B
+    float4 *ray_o, *ray_d;      // (o.xyz, mint), (d.xyz, maxt); maxt < 0 marks a retired lane   32 B
+    float4 *hit;                // (t, u, v, slot bits); t = +inf: miss                           16 B
+    float4 *tp;                 // (throughput.rgb, eta)                                          16 B
+    float4 *res;                // (result.rgb, pdf of the last BSDF sample)                      16 B
+    uint4 *st;                  // (rng.lo, rng.hi, work item, depth|flags|samples_left)          16 B
     float2 *pos;                // position_sample, only for wide (non-box) filters
-    float4 *sh_o, *sh_d, *sh_c; // shadow queue (dense): ray + (contrib.rgb, lane bits) 48 B
-    uint32_t *list[2];          // lanes with an active ray (double buffered)
-    uint32_t *new_list;         // lanes whose path ended (to film + regenerate)
-    uint32_t *cnt;              // [0],[1] = list counts, [2] = new count, [3] = shadow count, [4] = work counter
+    // shadow queue (dense): ray + (contrib.rgb, lane bits | FINAL) [+ final entries only:
+    // (result.rgb, film word) and, for wide filters, position_sample]
+    float4 *sh_o, *sh_d, *sh_c, *sh_r;
+    uint32_t *sh_f;             // final entries: st.w flags (alpha, box-filter target)
+    float2 *sh_p;               // final entries, wide filters: position_sample
+    uint32_t *cnt;              // [CNT_SHADOW] shadow count, [CNT_WORK] work counter, [CNT_ALIVE] live lanes
     unsigned long long *stats;  // [0] samples, [1] segments, [2] shadow rays, [3] invalid
     float *film;                // crop_h x crop_w x 5 (X,Y,Z,A,W)
     const uint32_t *item_pixel; // per work item of ONE pass: x | y << 16 (crop-relative)
@@ -30,12 +39,13 @@ struct Queues {
     uint32_t n_items_pass;      // work items per pass (this rank's pixels)
     uint32_t n_passes, spp_pass, block_size, n_blocks_total;
     uint32_t total_items;       // n_items_pass * n_passes
+    uint32_t n_slots;
     uint64_t base_seed;
     int32_t max_depth, rr_depth;
 };
 
-enum { CNT_LIST0 = 0, CNT_LIST1 = 1, CNT_NEW = 2, CNT_SHADOW = 3, CNT_WORK = 4 };
-enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3 };
+enum { CNT_SHADOW = 0, CNT_WORK = 1, CNT_ALIVE = 2 };
+enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_PUT_SHADOW = 4 };
 
 // st.w layout
 #define STW_DEPTH(w)     ((w) & 0xffu)
@@ -44,8 +54,8 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3 };
 #define STW_FILM_DX      0x400u      // box filter: sample lands on pixel x-1
 #define STW_FILM_DY      0x800u      //             ... y-1
 #define STW_FILM_DROP    0x1000u     // sample falls outside its block (imageblock.cpp:166)
-#define STW_HAS_SAMPLE   0x2000u     // a finished sample is waiting to be put on the film
 #define STW_LEFT(w)      ((w) >> 16)
+#define SH_FINAL         0x80000000u // shadow entry of a path that ended: k_shadow puts the sample on the film
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
 
@@ -207,47 +217,29 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
 }
 
 // ---- K2: closest hit ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_intersect(DScene sc, Queues q, int cur) {
+__global__ void __launch_bounds__(256) k_intersect(DScene sc, Queues q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    uint32_t count = q.cnt[cur];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.cnt[cur ^ 1] = 0; q.cnt[CNT_NEW] = 0; q.cnt[CNT_SHADOW] = 0;
-        atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) count);
-    }
-    const uint32_t *list = q.list[cur];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        uint32_t lane = list[i];
-        float4 ro = q.ray_o[lane], rd = q.ray_d[lane];
+    uint32_t n_seg = 0;
+    for (uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x; lane < q.n_slots; lane += gridDim.x * blockDim.x) {
+        float4 rd = q.ray_d[lane];
+        if (rd.w < 0.f) continue;                                  // retired lane
+        float4 ro = q.ray_o[lane];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
         Hit h; traverse<false>(sc, sm, ray, h);
         q.hit[lane] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+        ++n_seg;
     }
-}
-
-// ---- K3: any hit for the emitter samples ----------------------------------------------------------
-__global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemScene sm = stage_scene(sc, smem_raw);
-    uint32_t count = q.cnt[CNT_SHADOW];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) count);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        float4 ro = q.sh_o[i], rd = q.sh_d[i];
-        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h;
-        if (!traverse<true>(sc, sm, ray, h)) {
-            float4 c = q.sh_c[i];
-            uint32_t lane = __float_as_uint(c.w);
-            float4 r = q.res[lane];
-            r.x += c.x; r.y += c.y; r.z += c.z;            // result += mis*throughput*bsdf_val*emitter_val (path.cpp:171)
-            q.res[lane] = r;
-        }
-    }
+    n_seg = __reduce_add_sync(0xffffffffu, n_seg);
+    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+    if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_SHADOW] = 0;      // consumed by the previous k_shadow
 }
 
 // ---- K6: ImageBlock::put (imageblock.cpp:79-172) -----------------------------------------------
+// film word: x | y << 16 of the work item's pixel in bits 0..27 is not enough for 65535^2, so the
+// word is the pixel's linear index (crop-relative) and the box-filter flags travel in `flags`.
 B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint32_t block_size,
-                   uint32_t stw, float2 pos, float3 L, bool alpha) {
+                   uint32_t flags, float2 pos, float3 L, bool alpha) {
     // srgb_to_xyz (spectrum.h:221-228): M * rgb with fmadd accumulation (matrix.h:170-177)
     float val[5];
     val[0] = b2_fma(0.180423f, L.z, b2_fma(0.357580f, L.y, 0.412453f * L.x));
@@ -290,8 +282,8 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
             }
         }
     } else {                                                       // imageblock.cpp:162-169
-        if (stw & STW_FILM_DROP) return true;
-        int fx = (int) px - ((stw & STW_FILM_DX) ? 1 : 0), fy = (int) py - ((stw & STW_FILM_DY) ? 1 : 0);
+        if (flags & STW_FILM_DROP) return true;
+        int fx = (int) px - ((flags & STW_FILM_DX) ? 1 : 0), fy = (int) py - ((flags & STW_FILM_DY) ? 1 : 0);
         float *dst = film + 5 * ((size_t) fy * W + fx);
         #pragma unroll
         for (int k = 0; k < 5; ++k) atomicAdd(dst + k, val[k]);
@@ -299,87 +291,71 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
     return true;
 }
 
-// ---- K1 (+K6): regenerate ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_regen(DScene sc, Queues q, int cur) {
-    uint32_t count = q.cnt[CNT_NEW];
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+// ---- K1: regenerate — next camera sample of the lane's work item (integrator.cpp:233-262) ------
+// `item`/`left`/`rng` are the lane's work-item state (left == 0: `w` is the freshly fetched work
+// item). Returns false if the work is exhausted (lane retires).
+B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_t w, uint32_t &item, uint32_t &left,
+                       uint64_t &rng, Ray &ray, uint32_t &stw) {
     const B2Film &film = sc.film;
-    for (uint32_t base = warp * 32; base < count; base += n_warps * 32) {
-        uint32_t i = base + lane_id();
-        bool valid = i < count;
-        uint32_t lane = valid ? q.new_list[i] : 0;
-        uint4 st = valid ? q.st[lane] : make_uint4(0, 0, 0, 0);
-        uint32_t item = st.z, left = STW_LEFT(st.w);
-        uint32_t n_put = 0, n_bad = 0;
-        if (valid && (st.w & STW_HAS_SAMPLE)) {
-            uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
-            float4 r = q.res[lane];
-            float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
-            bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, v3(r), (st.w & STW_ALPHA) != 0);
-            n_put = 1; n_bad = ok ? 0 : 1;
-        }
-        // fetch the next work item if this one is exhausted (warp-aggregated atomic)
-        bool need = valid && left == 0;
-        uint32_t w = warp_append(&q.cnt[CNT_WORK], need);
-        uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
-        bool alive = valid;
-        if (need) {
-            if (w >= q.total_items) alive = false;
-            else {
-                item = w; left = q.spp_pass;
-                uint32_t pass = item / q.n_items_pass, j = item % q.n_items_pass;
-                // block_id = spiral index + (remaining_passes - 1) * block_count  (spiral.cpp:41);
-                // seed = block_id * bs^2 + morton index                           (integrator.cpp:198)
-                uint64_t seed_off = (uint64_t) __ldg(&q.item_seed[j]) +
-                                    (uint64_t) (q.n_passes - 1 - pass) * q.n_blocks_total * q.block_size * q.block_size;
-                rng = pcg32_seed(q.base_seed + seed_off);
-            }
-        }
+    if (left == 0) {
+        if (w >= q.total_items) return false;
+        item = w; left = q.spp_pass;
+        uint32_t pass = item / q.n_items_pass, j = item % q.n_items_pass;
+        // block_id = spiral index + (remaining_passes - 1) * block_count  (spiral.cpp:41);
+        // seed = block_id * bs^2 + morton index                           (integrator.cpp:198)
+        uint64_t seed_off = (uint64_t) __ldg(&q.item_seed[j]) +
+                            (uint64_t) (q.n_passes - 1 - pass) * q.n_blocks_total * q.block_size * q.block_size;
+        rng = pcg32_seed(q.base_seed + seed_off);
+    }
+    uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
+    uint32_t px = pix & 0xffffu, py = pix >> 16;
+    float jx = pcg32_next_float(rng), jy = pcg32_next_float(rng);            // integrator.cpp:242
+    float psx = (float) (px + (uint32_t) film.crop_offset[0]) + jx, psy = (float) (py + (uint32_t) film.crop_offset[1]) + jy;
+    (void) pcg32_next_float(rng);                                              // :252 wavelength sample
+    float ax = (psx - (float) film.crop_offset[0]) / (float) film.crop_size[0],
+          ay = (psy - (float) film.crop_offset[1]) / (float) film.crop_size[1];   // :254-256
+    ray = sensor_sample_ray(sc.sensor, ax, ay);
+    stw = 1u | ((left - 1) << 16);
+    if (!(film.filter_radius > 0.5f + B2_RAY_EPS)) {
+        // box filter target pixel, in block coordinates (imageblock.cpp:112,163-166)
+        uint32_t bs = q.block_size;
+        int ox = (int) (px / bs) * (int) bs, oy = (int) (py / bs) * (int) bs;
+        int bw = min((int) bs, film.crop_size[0] - ox), bh = min((int) bs, film.crop_size[1] - oy);
+        float bx = psx - ((float) (ox + film.crop_offset[0]) + .5f), by = psy - ((float) (oy + film.crop_offset[1]) + .5f);
+        int lox = (int) ceilf(bx - .5f), loy = (int) ceilf(by - .5f);
+        if (lox < 0 || loy < 0 || lox >= bw || loy >= bh) stw |= STW_FILM_DROP;
+        if (lox + ox != (int) px) stw |= STW_FILM_DX;
+        if (loy + oy != (int) py) stw |= STW_FILM_DY;
+        // (lo can only be px or px-1: psx = px + j with j in [0,1) rounds into [px, px+1])
+        if (lox + ox != (int) px && lox + ox != (int) px - 1) stw |= STW_FILM_DROP;
+        if (loy + oy != (int) py && loy + oy != (int) py - 1) stw |= STW_FILM_DROP;
+    } else if (q.pos)
+        q.pos[lane] = make_float2(psx, psy);
+    return true;
+}
+
+// fill every lane with its first camera sample
+__global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
+    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
+        uint32_t lane = base + lane_id();
+        bool valid = lane < q.n_slots;
+        uint32_t w = warp_append(&q.cnt[CNT_WORK], valid);
+        uint32_t item = 0, left = 0, stw = 0; uint64_t rng = 0; Ray ray;
+        bool alive = valid && regen_sample(sc, q, lane, w, item, left, rng, ray, stw);
         if (alive) {
-            uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
-            uint32_t px = pix & 0xffffu, py = pix >> 16;
-            float jx = pcg32_next_float(rng), jy = pcg32_next_float(rng);            // integrator.cpp:242
-            float psx = (float) (px + (uint32_t) film.crop_offset[0]) + jx, psy = (float) (py + (uint32_t) film.crop_offset[1]) + jy;
-            (void) pcg32_next_float(rng);                                              // :252 wavelength sample
-            float ax = (psx - (float) film.crop_offset[0]) / (float) film.crop_size[0],
-                  ay = (psy - (float) film.crop_offset[1]) / (float) film.crop_size[1];   // :254-256
-            Ray ray = sensor_sample_ray(sc.sensor, ax, ay);
-            uint32_t stw = 1u | ((left - 1) << 16);
-            if (!(film.filter_radius > 0.5f + B2_RAY_EPS)) {
-                // box filter target pixel, in block coordinates (imageblock.cpp:112,163-166)
-                uint32_t bs = q.block_size;
-                int ox = (int) (px / bs) * (int) bs, oy = (int) (py / bs) * (int) bs;
-                int bw = min((int) bs, film.crop_size[0] - ox), bh = min((int) bs, film.crop_size[1] - oy);
-                float bx = psx - ((float) (ox + film.crop_offset[0]) + .5f), by = psy - ((float) (oy + film.crop_offset[1]) + .5f);
-                int lox = (int) ceilf(bx - .5f), loy = (int) ceilf(by - .5f);
-                if (lox < 0 || loy < 0 || lox >= bw || loy >= bh) stw |= STW_FILM_DROP;
-                if (lox + ox != (int) px) stw |= STW_FILM_DX;
-                if (loy + oy != (int) py) stw |= STW_FILM_DY;
-                // (lo can only be px or px-1: psx = px + j with j in [0,1) rounds into [px, px+1])
-                if (lox + ox != (int) px && lox + ox != (int) px - 1) stw |= STW_FILM_DROP;
-                if (loy + oy != (int) py && loy + oy != (int) py - 1) stw |= STW_FILM_DROP;
-            } else if (q.pos)
-                q.pos[lane] = make_float2(psx, psy);
             q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
             q.ray_d[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
             q.tp[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
             q.res[lane] = make_float4(0.f, 0.f, 0.f, 1.f);
             q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), item, stw);
-        } else if (valid) {
-            q.st[lane] = make_uint4(0, 0, 0, 0);       // retired
-        }
-        uint32_t slot = warp_append(&q.cnt[cur], alive);
-        if (alive) q.list[cur][slot] = lane;
-        // stats
-        uint32_t tot_put = __reduce_add_sync(0xffffffffu, n_put), tot_bad = __reduce_add_sync(0xffffffffu, n_bad);
-        if (lane_id() == 0) {
-            if (tot_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) tot_put);
-            if (tot_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) tot_bad);
-        }
+        } else if (valid)
+            q.ray_d[lane] = make_float4(0.f, 0.f, 0.f, -1.f);
+        uint32_t n_alive = __popc(__ballot_sync(0xffffffffu, alive));
+        if (lane_id() == 0 && n_alive) atomicAdd(&q.cnt[CNT_ALIVE], n_alive);
     }
 }
 
-// ---- K4: shade (SI fill + one loop body of PathIntegrator::sample) ----------------------------
 // Small scenes: stage the shading tables (triangles, normals, CDFs, BSDF + emitter records) into
 // shared memory with one bulk copy and rebase the table pointers onto the copy.
 B2_D void stage_shade_tables(DScene &sc, unsigned char *smem_raw) {
@@ -399,26 +375,29 @@ B2_D void stage_shade_tables(DScene &sc, unsigned char *smem_raw) {
     sc.emitters = (const DEmitter *) (dst + ((const unsigned char *) sc.emitters - g));
 }
 
-__global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q, int cur) {
+// ---- K4 (+K1, K5, K6): shade -----------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     stage_shade_tables(sc, smem_raw);
-    uint32_t count = q.cnt[cur];
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t *list = q.list[cur];
-    uint32_t *list_out = q.list[cur ^ 1];
-    for (uint32_t base = warp * 32; base < count; base += n_warps * 32) {
-        uint32_t i = base + lane_id();
-        bool valid = i < count;
-        uint32_t lane = valid ? list[i] : 0;
+    uint32_t n_put = 0, n_bad = 0;
+    for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
+        uint32_t lane = base + lane_id();
+        float4 rd = lane < q.n_slots ? q.ray_d[lane] : make_float4(0.f, 0.f, 0.f, -1.f);
+        bool valid = rd.w >= 0.f;
         bool cont = false, term = false, shadow = false;
         float4 sho, shd, shc;
+        float3 throughput, result; float eta = 1.f, bs_pdf = 1.f;
+        float4 nro, nrd;                 // next ray
+        uint4 st = make_uint4(0, 0, 0, 0);
+        uint64_t rng = 0;
         if (valid) {
-            float4 ro = q.ray_o[lane], rd = q.ray_d[lane], h = q.hit[lane], tpe = q.tp[lane], rs = q.res[lane];
-            uint4 st = q.st[lane];
-            uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+            float4 ro = q.ray_o[lane], h = q.hit[lane], tpe = q.tp[lane], rs = q.res[lane];
+            st = q.st[lane];
+            rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
             int depth = (int) STW_DEPTH(st.w);
-            float3 throughput = v3(tpe), result = v3(rs);
-            float eta = tpe.w, bs_pdf = rs.w;
+            throughput = v3(tpe); result = v3(rs);
+            eta = tpe.w; bs_pdf = rs.w;
             bool hit_valid = h.x < B2_INF;
             SI si; si.emitter = -1; si.bsdf = -1;
             if (hit_valid) si_fill(sc, __float_as_uint(h.w), h.y, h.z, v3(rd), si);
@@ -475,26 +454,101 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q, int cur) 
                 else {
                     eta *= bs.eta;
                     float3 nd = to_world(si, bs.wo);                                // interaction.h:58-61
-                    q.ray_o[lane] = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
-                    q.ray_d[lane] = make_float4(nd.x, nd.y, nd.z, B2_INF);
+                    nro = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
+                    nrd = make_float4(nd.x, nd.y, nd.z, B2_INF);
                     bs_pdf = bs.pdf;
                     st.w = (st.w & ~(0xffu | STW_DELTA)) | (uint32_t) (depth + 1) | (bs.delta ? STW_DELTA : 0u);
                     cont = true;
                 }
             }
-            if (term) st.w |= STW_HAS_SAMPLE;
-            q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
-            q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
-            q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
         }
         __syncwarp();
-        // ---- K5: warp-ballot compaction into the next queues ----
-        uint32_t s0 = warp_append(&q.cnt[cur ^ 1], cont);
-        if (cont) list_out[s0] = lane;
-        uint32_t s1 = warp_append(&q.cnt[CNT_NEW], term);
-        if (term) q.new_list[s1] = lane;
-        uint32_t s2 = warp_append(&q.cnt[CNT_SHADOW], shadow);
-        if (shadow) { q.sh_o[s2] = sho; q.sh_d[s2] = shd; q.sh_c[s2] = shc; }
+        // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue ----
+        uint32_t sq = warp_append(&q.cnt[CNT_SHADOW], shadow);
+        // ---- path ended: film put (now, or by k_shadow once the emitter sample is resolved) ----
+        uint32_t item = st.z, left = STW_LEFT(st.w);
+        if (term) {
+            uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
+            if (shadow) {
+                shc.w = __uint_as_float(lane | SH_FINAL);
+                q.sh_r[sq] = make_float4(result.x, result.y, result.z, __uint_as_float(pix));
+                q.sh_f[sq] = st.w;
+                if (q.pos) q.sh_p[sq] = q.pos[lane];
+            } else {
+                float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
+                bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, result, (st.w & STW_ALPHA) != 0);
+                ++n_put; n_bad += ok ? 0 : 1;
+            }
+        }
+        if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
+        // ---- K1: regenerate the lanes whose path ended ----
+        bool need = term && left == 0;
+        uint32_t w = warp_append(&q.cnt[CNT_WORK], need);
+        bool retire = false;
+        if (term) {
+            Ray ray; uint32_t stw;
+            if (regen_sample(sc, q, lane, w, item, left, rng, ray, stw)) {
+                nro = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+                nrd = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+                throughput = v3(1.f, 1.f, 1.f); eta = 1.f; result = v3(0.f, 0.f, 0.f); bs_pdf = 1.f;
+                st.z = item; st.w = stw;
+            } else { retire = true; nrd = make_float4(0.f, 0.f, 0.f, -1.f); nro = nrd; }
+        }
+        if (valid) {
+            q.ray_o[lane] = nro; q.ray_d[lane] = nrd;
+            if (!retire) {
+                q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
+                q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
+                q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+            }
+        }
+        uint32_t n_ret = __popc(__ballot_sync(0xffffffffu, retire));
+        if (lane_id() == 0 && n_ret) atomicSub(&q.cnt[CNT_ALIVE], n_ret);
+        (void) cont;
+    }
+    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+    if (lane_id() == 0) {
+        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
+        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
+    }
+}
+
+// ---- K3 (+K6): any hit for the emitter samples ----------------------------------------------------
+__global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    uint32_t count = q.cnt[CNT_SHADOW];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) count);
+    uint32_t n_put = 0, n_bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        float4 ro = q.sh_o[i], rd = q.sh_d[i];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Hit h;
+        bool occluded = traverse<true>(sc, sm, ray, h);
+        float4 c = q.sh_c[i];
+        uint32_t lw = __float_as_uint(c.w);
+        if (lw & SH_FINAL) {
+            // the path ended on this bounce: result += contribution (path.cpp:171), then ImageBlock::put
+            float4 r = q.sh_r[i];
+            float2 p = q.pos ? q.sh_p[i] : make_float2(0.f, 0.f);
+            float3 L = v3(r);
+            if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
+            uint32_t pix = __float_as_uint(r.w);
+            uint32_t flags = q.sh_f[i];
+            bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
+            ++n_put; n_bad += ok ? 0 : 1;
+        } else if (!occluded) {
+            uint32_t lane = lw;
+            float4 r = q.res[lane];
+            r.x += c.x; r.y += c.y; r.z += c.z;                    // result += mis*throughput*bsdf_val*emitter_val (path.cpp:171)
+            q.res[lane] = r;
+        }
+    }
+    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+    if (lane_id() == 0) {
+        if (n_put) atomicAdd(&q.stats[ST_PUT_SHADOW], (unsigned long long) n_put);
+        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
+        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
     }
 }
 
