@@ -50,6 +50,21 @@ struct DScene {
     B2Film film;
 };
 
+// The shading tables as seen by one kernel: pointers into global memory or into the CTA's
+// shared-memory copy (kept in registers; the kernel parameter block itself is never written).
+struct Tables {
+    const float4 *tri_pos, *tri_nrm;
+    const uint32_t *prim_to_slot;
+    const float *cdf;
+    const B2Bsdf *bsdfs;
+    const DEmitter *emitters;
+    uint32_t n_emitters;
+};
+B2_D Tables make_tables(const DScene &sc) {
+    Tables t; t.tri_pos = sc.tri_pos; t.tri_nrm = sc.tri_nrm; t.prim_to_slot = sc.prim_to_slot; t.cdf = sc.cdf;
+    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.n_emitters = sc.n_emitters; return t;
+}
+
 struct Ray { float3 o, d; float mint, maxt; };
 
 // Mesh::ray_intersect_triangle — include/mitsuba/render/mesh.h:194-226
@@ -83,7 +98,7 @@ B2_D float3 coordinate_system_s(float3 n) {        // include/mitsuba/core/vecto
 B2_D float3 to_local(const SI &si, float3 v) { return v3(dot(v, si.sh_s), dot(v, si.sh_t), dot(v, si.sh_n)); }
 B2_D float3 to_world(const SI &si, float3 v) { return (si.sh_s * v.x + si.sh_t * v.y) + si.sh_n * v.z; }   // frame.h:35-37
 
-B2_D void si_fill(const DScene &sc, uint32_t slot, float u, float v, float3 ray_d, SI &si) {
+B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_d, SI &si) {
     float4 a0 = B2_LD(&sc.tri_pos[3 * slot]), a1 = B2_LD(&sc.tri_pos[3 * slot + 1]), a2 = B2_LD(&sc.tri_pos[3 * slot + 2]);
     float4 m0 = B2_LD(&sc.tri_nrm[3 * slot]), m1 = B2_LD(&sc.tri_nrm[3 * slot + 1]), m2 = B2_LD(&sc.tri_nrm[3 * slot + 2]);
     float3 p0 = v3(a0), p1 = v3(a1), p2 = v3(a2);
@@ -325,7 +340,7 @@ B2_D uint32_t distr_sample(const float *cdf, uint32_t first, uint32_t last, floa
     return start;
 }
 
-B2_D float3 area_sample_direction(const DScene &sc, const DEmitter &em, float3 ref_p, float sx, float sy, DS &ds) {
+B2_D float3 area_sample_direction(const Tables &sc, const DEmitter &em, float3 ref_p, float sx, float sy, DS &ds) {
     const float *cdf = sc.cdf + em.cdf_offset;
     uint32_t face = distr_sample(cdf, em.valid_first, em.valid_last, em.cdf_sum, sy);
     uint32_t slot = B2_LD(&sc.prim_to_slot[em.first_prim + face]);
@@ -359,7 +374,7 @@ B2_D float3 area_sample_direction(const DScene &sc, const DEmitter &em, float3 r
     return v3(em.radiance[0] * ip, em.radiance[1] * ip, em.radiance[2] * ip);
 }
 
-B2_D float3 scene_sample_emitter_direction(const DScene &sc, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
+B2_D float3 scene_sample_emitter_direction(const Tables &sc, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
     uint32_t ne = sc.n_emitters;
     if (ne == 0) { ds.pdf = 0.f; ds.dist = 0.f; ds.p = ds.n = ds.d = v3(0.f, 0.f, 0.f); return v3(0.f, 0.f, 0.f); }
     if (ne == 1) return area_sample_direction(sc, sc.emitters[0], ref_p, sx, sy, ds);
@@ -372,7 +387,7 @@ B2_D float3 scene_sample_emitter_direction(const DScene &sc, float3 ref_p, float
     return spec * b2_rcp(emitter_pdf);
 }
 
-B2_D float scene_pdf_emitter_direction(const DScene &sc, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
+B2_D float scene_pdf_emitter_direction(const Tables &sc, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
     const DEmitter &em = sc.emitters[emitter];
     float dp = dot(d, n);
     if (!(dp < 0.f)) return 0.f;                                   // area.cpp:170-171

@@ -294,7 +294,7 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
 // ---- K1: regenerate — next camera sample of the lane's work item (integrator.cpp:233-262) ------
 // `item`/`left`/`rng` are the lane's work-item state (left == 0: `w` is the freshly fetched work
 // item). Returns false if the work is exhausted (lane retires).
-B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_t w, uint32_t &item, uint32_t &left,
+B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_t w, uint32_t pix, uint32_t &item, uint32_t &left,
                        uint64_t &rng, Ray &ray, uint32_t &stw) {
     const B2Film &film = sc.film;
     if (left == 0) {
@@ -306,8 +306,8 @@ B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_
         uint64_t seed_off = (uint64_t) __ldg(&q.item_seed[j]) +
                             (uint64_t) (q.n_passes - 1 - pass) * q.n_blocks_total * q.block_size * q.block_size;
         rng = pcg32_seed(q.base_seed + seed_off);
+        pix = __ldg(&q.item_pixel[j]);
     }
-    uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
     uint32_t px = pix & 0xffffu, py = pix >> 16;
     float jx = pcg32_next_float(rng), jy = pcg32_next_float(rng);            // integrator.cpp:242
     float psx = (float) (px + (uint32_t) film.crop_offset[0]) + jx, psy = (float) (py + (uint32_t) film.crop_offset[1]) + jy;
@@ -342,7 +342,7 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
         bool valid = lane < q.n_slots;
         uint32_t w = warp_append(&q.cnt[CNT_WORK], valid);
         uint32_t item = 0, left = 0, stw = 0; uint64_t rng = 0; Ray ray;
-        bool alive = valid && regen_sample(sc, q, lane, w, item, left, rng, ray, stw);
+        bool alive = valid && regen_sample(sc, q, lane, w, 0u, item, left, rng, ray, stw);
         if (alive) {
             q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
             q.ray_d[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
@@ -358,8 +358,9 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
 
 // Small scenes: stage the shading tables (triangles, normals, CDFs, BSDF + emitter records) into
 // shared memory with one bulk copy and rebase the table pointers onto the copy.
-B2_D void stage_shade_tables(DScene &sc, unsigned char *smem_raw) {
-    if (!sc.shade_smem) return;
+B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
+    Tables tb = make_tables(sc);
+    if (!sc.shade_smem) return tb;
     uint64_t *mbar = (uint64_t *) smem_raw;
     unsigned char *dst = smem_raw + 16;
     if (threadIdx.x == 0) mbar_init(mbar, 1);
@@ -367,40 +368,41 @@ B2_D void stage_shade_tables(DScene &sc, unsigned char *smem_raw) {
     if (threadIdx.x == 0) { mbar_expect_tx(mbar, sc.blob_bytes); stage_bulk(dst, sc.blob, sc.blob_bytes, mbar); }
     mbar_wait(mbar, 0);
     const unsigned char *g = sc.blob;
-    sc.tri_pos = (const float4 *) (dst + ((const unsigned char *) sc.tri_pos - g));
-    sc.tri_nrm = (const float4 *) (dst + ((const unsigned char *) sc.tri_nrm - g));
-    sc.prim_to_slot = (const uint32_t *) (dst + ((const unsigned char *) sc.prim_to_slot - g));
-    sc.cdf = (const float *) (dst + ((const unsigned char *) sc.cdf - g));
-    sc.bsdfs = (const B2Bsdf *) (dst + ((const unsigned char *) sc.bsdfs - g));
-    sc.emitters = (const DEmitter *) (dst + ((const unsigned char *) sc.emitters - g));
+    tb.tri_pos = (const float4 *) (dst + ((const unsigned char *) sc.tri_pos - g));
+    tb.tri_nrm = (const float4 *) (dst + ((const unsigned char *) sc.tri_nrm - g));
+    tb.prim_to_slot = (const uint32_t *) (dst + ((const unsigned char *) sc.prim_to_slot - g));
+    tb.cdf = (const float *) (dst + ((const unsigned char *) sc.cdf - g));
+    tb.bsdfs = (const B2Bsdf *) (dst + ((const unsigned char *) sc.bsdfs - g));
+    tb.emitters = (const DEmitter *) (dst + ((const unsigned char *) sc.emitters - g));
+    return tb;
 }
 
 // ---- K4 (+K1, K5, K6): shade -----------------------------------------------------------------
 __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    stage_shade_tables(sc, smem_raw);
+    const Tables tb = stage_shade_tables(sc, smem_raw);
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t n_put = 0, n_bad = 0;
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         uint32_t lane = base + lane_id();
-        float4 rd = lane < q.n_slots ? q.ray_d[lane] : make_float4(0.f, 0.f, 0.f, -1.f);
-        bool valid = rd.w >= 0.f;
-        bool cont = false, term = false, shadow = false;
+        // all queue loads are issued up front (one round trip), retired lanes included
+        uint32_t ld = lane < q.n_slots ? lane : q.n_slots - 1;
+        float4 rd = q.ray_d[ld], ro = q.ray_o[ld], h = q.hit[ld], tpe = q.tp[ld], rs = q.res[ld];
+        uint4 st = q.st[ld];
+        uint32_t pix = __ldg(&q.item_pixel[st.z % q.n_items_pass]);       // pixel of the lane's work item
+        bool valid = lane < q.n_slots && rd.w >= 0.f;
+        bool term = false, shadow = false, do_bsdf = false;
         float4 sho, shd, shc;
-        float3 throughput, result; float eta = 1.f, bs_pdf = 1.f;
         float4 nro, nrd;                 // next ray
-        uint4 st = make_uint4(0, 0, 0, 0);
-        uint64_t rng = 0;
+        uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+        int depth = (int) STW_DEPTH(st.w);
+        float3 throughput = v3(tpe), result = v3(rs);
+        float eta = tpe.w, bs_pdf = rs.w;
+        SI si; si.emitter = -1; si.bsdf = 0;
+        // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling ----
         if (valid) {
-            float4 ro = q.ray_o[lane], h = q.hit[lane], tpe = q.tp[lane], rs = q.res[lane];
-            st = q.st[lane];
-            rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
-            int depth = (int) STW_DEPTH(st.w);
-            throughput = v3(tpe); result = v3(rs);
-            eta = tpe.w; bs_pdf = rs.w;
             bool hit_valid = h.x < B2_INF;
-            SI si; si.emitter = -1; si.bsdf = -1;
-            if (hit_valid) si_fill(sc, __float_as_uint(h.w), h.y, h.z, v3(rd), si);
+            if (hit_valid) si_fill(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), si);
             if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
             // ---- intersection with emitters (path.cpp:128-129) ----
             if (si.emitter >= 0) {
@@ -411,11 +413,11 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
                         float3 dd = si.p - v3(ro);
                         float dist = sqrtf(dot(dd, dd));
                         dd = dd * b2_rcp(dist);
-                        emitter_pdf = scene_pdf_emitter_direction(sc, si.emitter, dd, si.sh_n, dist);
+                        emitter_pdf = scene_pdf_emitter_direction(tb, si.emitter, dd, si.sh_n, dist);
                     }
                     emission_weight = mis_weight(bs_pdf, emitter_pdf);
                 }
-                const DEmitter &em = sc.emitters[si.emitter];
+                const DEmitter &em = tb.emitters[si.emitter];
                 float3 ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
                 result = result + (throughput * emission_weight) * ev;
             }
@@ -427,10 +429,11 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
             }
             if ((uint32_t) depth >= (uint32_t) q.max_depth || !active) term = true;   // path.cpp:147-149
             else {
-                const B2Bsdf &bsdf = sc.bsdfs[si.bsdf];
+                do_bsdf = true;
+                const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
                 if (bsdf_is_smooth(bsdf)) {                                         // path.cpp:153-172
                     float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
-                    DS ds; float3 emitter_val = scene_sample_emitter_direction(sc, si.p, sx, sy, ds);
+                    DS ds; float3 emitter_val = scene_sample_emitter_direction(tb, si.p, sx, sy, ds);
                     if (ds.pdf != 0.f) {
                         float3 wo = to_local(si, ds.d);
                         float3 bsdf_val = bsdf_eval(bsdf, si, wo);
@@ -445,30 +448,36 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
                         }
                     }
                 }
-                // BSDF sampling — the reference (g++) draws next_2d BEFORE next_1d (path.cpp:177-178)
-                float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
-                float s1 = pcg32_next_float(rng);
-                BS bs; float3 bsdf_val = bsdf_sample(bsdf, si, s1, s2x, s2y, bs);
-                throughput = throughput * bsdf_val;
-                if (!any_nonzero(throughput)) term = true;                         // path.cpp:182-184
-                else {
-                    eta *= bs.eta;
-                    float3 nd = to_world(si, bs.wo);                                // interaction.h:58-61
-                    nro = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
-                    nrd = make_float4(nd.x, nd.y, nd.z, B2_INF);
-                    bs_pdf = bs.pdf;
-                    st.w = (st.w & ~(0xffu | STW_DELTA)) | (uint32_t) (depth + 1) | (bs.delta ? STW_DELTA : 0u);
-                    cont = true;
-                }
             }
         }
         __syncwarp();
-        // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue ----
-        uint32_t sq = warp_append(&q.cnt[CNT_SHADOW], shadow);
+        // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue. The
+        // atomic is issued here and its result is only consumed after phase 2 (latency hidden). ----
+        uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
+        uint32_t sq_base = 0;
+        if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW], __popc(sh_mask));
+        // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
+        if (do_bsdf) {
+            const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
+            float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
+            float s1 = pcg32_next_float(rng);
+            BS bs; float3 bsdf_val = bsdf_sample(bsdf, si, s1, s2x, s2y, bs);
+            throughput = throughput * bsdf_val;
+            if (!any_nonzero(throughput)) term = true;                             // path.cpp:182-184
+            else {
+                eta *= bs.eta;
+                float3 nd = to_world(si, bs.wo);                                    // interaction.h:58-61
+                nro = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
+                nrd = make_float4(nd.x, nd.y, nd.z, B2_INF);
+                bs_pdf = bs.pdf;
+                st.w = (st.w & ~(0xffu | STW_DELTA)) | (uint32_t) (depth + 1) | (bs.delta ? STW_DELTA : 0u);
+            }
+        }
+        __syncwarp();
+        uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
         // ---- path ended: film put (now, or by k_shadow once the emitter sample is resolved) ----
         uint32_t item = st.z, left = STW_LEFT(st.w);
         if (term) {
-            uint32_t pix = __ldg(&q.item_pixel[item % q.n_items_pass]);
             if (shadow) {
                 shc.w = __uint_as_float(lane | SH_FINAL);
                 q.sh_r[sq] = make_float4(result.x, result.y, result.z, __uint_as_float(pix));
@@ -487,7 +496,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
         bool retire = false;
         if (term) {
             Ray ray; uint32_t stw;
-            if (regen_sample(sc, q, lane, w, item, left, rng, ray, stw)) {
+            if (regen_sample(sc, q, lane, w, pix, item, left, rng, ray, stw)) {
                 nro = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
                 nrd = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
                 throughput = v3(1.f, 1.f, 1.f); eta = 1.f; result = v3(0.f, 0.f, 0.f); bs_pdf = 1.f;
@@ -504,7 +513,6 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
         }
         uint32_t n_ret = __popc(__ballot_sync(0xffffffffu, retire));
         if (lane_id() == 0 && n_ret) atomicSub(&q.cnt[CNT_ALIVE], n_ret);
-        (void) cont;
     }
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {
@@ -613,7 +621,7 @@ __global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, cons
         return;
     }
     uint32_t slot = sc.prim_to_slot[__float_as_uint(h.w)];
-    SI si; si_fill(sc, slot, h.y, h.z, v3(ray_d[i]), si);
+    SI si; si_fill(make_tables(sc), slot, h.y, h.z, v3(ray_d[i]), si);
     o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z; o[3] = si.n.x; o[4] = si.n.y; o[5] = si.n.z;
     o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z; o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
     o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z; o[15] = __uint_as_float((uint32_t) si.bsdf);

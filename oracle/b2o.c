@@ -265,12 +265,16 @@ typedef struct {
 
 typedef struct { float lo[3], hi[3]; int left, right, first, count; } onode;
 
+/* a BVH over the contiguous triangle range [first, first+count) of oscene.tris */
+typedef struct { onode *nodes; int n_nodes; uint32_t *order; uint32_t first, count; } obvh;
+
 typedef struct {
     const B2SceneDesc *desc;
     uint32_t n_tris;
     otri *tris;
-    uint32_t *order;      /* BVH leaf order -> prim */
-    onode *nodes; int n_nodes;
+    obvh top;             /* top-level meshes [0, n_top_meshes) */
+    obvh *groups;         /* one per shapegroup (shapegroup.cpp:7-47) */
+    float (*inst_lo)[3], (*inst_hi)[3];   /* world bounds of the instances (instance.cpp:83-94) */
     /* per-mesh area distribution (mesh.cpp:285-312, distr_1d.h:49-90) */
     float **cdf; float *cdf_sum, *cdf_norm; uint32_t *mesh_first;
 } oscene;
@@ -291,28 +295,37 @@ static int cmp_centroid(const void *a, const void *b) {
     float ca = la[g_axis] + ha[g_axis], cb = lb[g_axis] + hb[g_axis];
     return (ca > cb) - (ca < cb);
 }
-static int build_node(oscene *s, int first, int count) {
+static int build_node(const otri *tris, obvh *s, int first, int count) {
     int id = s->n_nodes++;
     onode *n = &s->nodes[id];
     for (int k = 0; k < 3; ++k) { n->lo[k] = INFINITY; n->hi[k] = -INFINITY; }
     for (int i = first; i < first + count; ++i) {
-        float lo[3], hi[3]; tri_bounds(&s->tris[s->order[i]], lo, hi);
+        float lo[3], hi[3]; tri_bounds(&tris[s->order[i]], lo, hi);
         for (int k = 0; k < 3; ++k) { if (lo[k] < n->lo[k]) n->lo[k] = lo[k]; if (hi[k] > n->hi[k]) n->hi[k] = hi[k]; }
     }
     n->first = first; n->count = count; n->left = n->right = -1;
     if (count > 4) {
         int ax = 0; float ext = n->hi[0] - n->lo[0];
         for (int k = 1; k < 3; ++k) if (n->hi[k] - n->lo[k] > ext) { ext = n->hi[k] - n->lo[k]; ax = k; }
-        g_axis = ax; g_tris = s->tris;
+        g_axis = ax; g_tris = tris;
         qsort(s->order + first, (size_t) count, sizeof(uint32_t), cmp_centroid);
         int half = count / 2;
-        int l = build_node(s, first, half);
-        int r = build_node(s, first + half, count - half);
+        int l = build_node(tris, s, first, half);
+        int r = build_node(tris, s, first + half, count - half);
         n = &s->nodes[id];
         n->left = l; n->right = r; n->count = 0;
     }
     return id;
 }
+
+static void obvh_build(const otri *tris, obvh *b, uint32_t first, uint32_t count) {
+    b->first = first; b->count = count; b->n_nodes = 0;
+    b->order = (uint32_t *) calloc(count ? count : 1, sizeof(uint32_t));
+    b->nodes = (onode *) calloc(2 * (count ? count : 1) + 1, sizeof(onode));
+    for (uint32_t i = 0; i < count; ++i) b->order[i] = first + i;
+    if (count) build_node(tris, b, 0, (int) count);
+}
+static void obvh_free(obvh *b) { free(b->order); free(b->nodes); }
 
 static void mesh_vertex(const B2Mesh *m, const float *buf, uint32_t i, v3 *out) {
     out->x = buf[3 * i]; out->y = buf[3 * i + 1]; out->z = buf[3 * i + 2]; (void) m;
@@ -327,7 +340,6 @@ static oscene *oscene_create(const B2SceneDesc *d) {
     s->mesh_first[d->n_meshes] = nt;
     s->n_tris = nt;
     s->tris = (otri *) calloc(nt ? nt : 1, sizeof(otri));
-    s->order = (uint32_t *) calloc(nt ? nt : 1, sizeof(uint32_t));
     s->cdf = (float **) calloc(d->n_meshes, sizeof(float *));
     s->cdf_sum = (float *) calloc(d->n_meshes, sizeof(float));
     s->cdf_norm = (float *) calloc(d->n_meshes, sizeof(float));
@@ -363,21 +375,46 @@ static oscene *oscene_create(const B2SceneDesc *d) {
             s->cdf_norm[m] = (float) (1.0 / sum);
         }
     }
-    for (uint32_t i = 0; i < nt; ++i) s->order[i] = i;
-    s->nodes = (onode *) calloc(2 * (nt ? nt : 1) + 1, sizeof(onode));
-    s->n_nodes = 0;
-    if (nt) build_node(s, 0, (int) nt);
+    /* top-level BVH over the meshes [0, n_top_meshes); one BVH per shapegroup; instance bounds */
+    uint32_t n_top = d->n_groups ? d->n_top_meshes : d->n_meshes;
+    obvh_build(s->tris, &s->top, 0, s->mesh_first[n_top]);
+    s->groups = (obvh *) calloc(d->n_groups ? d->n_groups : 1, sizeof(obvh));
+    for (uint32_t g = 0; g < d->n_groups; ++g) {
+        uint32_t m0 = d->group_first[g], m1 = d->group_first[g + 1];
+        obvh_build(s->tris, &s->groups[g], s->mesh_first[m0], s->mesh_first[m1] - s->mesh_first[m0]);
+    }
+    s->inst_lo = calloc(d->n_instances ? d->n_instances : 1, sizeof(float[3]));
+    s->inst_hi = calloc(d->n_instances ? d->n_instances : 1, sizeof(float[3]));
+    for (uint32_t i = 0; i < d->n_instances; ++i) {
+        const B2Instance *in = &d->instances[i];
+        const obvh *g = &s->groups[in->group];
+        for (int k = 0; k < 3; ++k) { s->inst_lo[i][k] = INFINITY; s->inst_hi[i][k] = -INFINITY; }
+        if (!g->count) continue;
+        const onode *root = &g->nodes[0];
+        for (int c = 0; c < 8; ++c) {
+            float p[3] = { c & 1 ? root->hi[0] : root->lo[0], c & 2 ? root->hi[1] : root->lo[1], c & 4 ? root->hi[2] : root->lo[2] };
+            for (int r = 0; r < 3; ++r) {
+                const float *M = in->to_world + 4 * r;
+                float w = M[3] + M[0] * p[0] + M[1] * p[1] + M[2] * p[2];
+                if (w < s->inst_lo[i][r]) s->inst_lo[i][r] = w;
+                if (w > s->inst_hi[i][r]) s->inst_hi[i][r] = w;
+            }
+        }
+    }
     return s;
 }
 static void oscene_destroy(oscene *s) {
     if (!s) return;
     for (uint32_t m = 0; m < s->desc->n_meshes; ++m) free(s->cdf[m]);
     free(s->cdf); free(s->cdf_sum); free(s->cdf_norm); free(s->mesh_first);
-    free(s->tris); free(s->order); free(s->nodes); free(s);
+    obvh_free(&s->top);
+    for (uint32_t g = 0; g < s->desc->n_groups; ++g) obvh_free(&s->groups[g]);
+    free(s->groups); free(s->inst_lo); free(s->inst_hi);
+    free(s->tris); free(s);
 }
 
 typedef struct { v3 o, d; float mint, maxt; } oray;
-typedef struct { float t, u, v; uint32_t prim; } ohit;   /* t = +inf: miss */
+typedef struct { float t, u, v; uint32_t prim; int inst; } ohit;   /* t = +inf: miss; inst = -1: top-level shape */
 
 /* Mesh::ray_intersect_triangle — include/mitsuba/render/mesh.h:194-226 */
 static inline int tri_intersect(const otri *tr, const oray *ray, float *t_out, float *u_out, float *v_out) {
@@ -413,51 +450,109 @@ static inline int box_hit(const onode *n, const oray *r, float tmax) {
     return 1;
 }
 
-/* Scene::ray_intersect_preliminary (scene.cpp:131-137) with the order-independent tie rule */
-static ohit scene_intersect(const oscene *s, const oray *ray, int brute) {
-    ohit best; best.t = INFINITY; best.u = best.v = 0.f; best.prim = 0xffffffffu;
-    if (!s->n_tris) return best;
+/* tie rule: smaller t wins; on exactly equal t the larger (instance + 1, prim) key wins */
+static inline int hit_better(float t, int inst, uint32_t prim, const ohit *best) {
+    if (t < best->t) return 1;
+    if (t > best->t || best->prim == 0xffffffffu) return t == best->t;
+    uint64_t k = ((uint64_t) (inst + 1) << 32) | prim, kb = ((uint64_t) (best->inst + 1) << 32) | best->prim;
+    return k > kb;
+}
+
+static void bvh_intersect(const oscene *s, const obvh *b, const oray *ray, int inst, int brute, ohit *best) {
+    if (!b->count) return;
+    float t, u, v;
     if (brute) {
-        for (uint32_t i = 0; i < s->n_tris; ++i) {
-            float t, u, v;
-            if (tri_intersect(&s->tris[i], ray, &t, &u, &v) && (t < best.t || (t == best.t && (best.prim == 0xffffffffu || i > best.prim)))) {
-                best.t = t; best.u = u; best.v = v; best.prim = i;
+        for (uint32_t i = b->first; i < b->first + b->count; ++i)
+            if (tri_intersect(&s->tris[i], ray, &t, &u, &v) && hit_better(t, inst, i, best)) {
+                best->t = t; best->u = u; best->v = v; best->prim = i; best->inst = inst;
             }
-        }
-        return best;
+        return;
     }
     int stack[128], sp = 0; stack[sp++] = 0;
     while (sp) {
-        const onode *n = &s->nodes[stack[--sp]];
-        if (!box_hit(n, ray, best.t < ray->maxt ? best.t : ray->maxt)) continue;
+        const onode *n = &b->nodes[stack[--sp]];
+        if (!box_hit(n, ray, best->t < ray->maxt ? best->t : ray->maxt)) continue;
         if (n->left < 0) {
             for (int i = n->first; i < n->first + n->count; ++i) {
-                uint32_t prim = s->order[i];
-                float t, u, v;
-                if (tri_intersect(&s->tris[prim], ray, &t, &u, &v) && (t < best.t || (t == best.t && (best.prim == 0xffffffffu || prim > best.prim)))) {
-                    best.t = t; best.u = u; best.v = v; best.prim = prim;
+                uint32_t prim = b->order[i];
+                if (tri_intersect(&s->tris[prim], ray, &t, &u, &v) && hit_better(t, inst, prim, best)) {
+                    best->t = t; best->u = u; best->v = v; best->prim = prim; best->inst = inst;
                 }
             }
         } else { stack[sp++] = n->left; stack[sp++] = n->right; }
+    }
+}
+static int bvh_occluded(const oscene *s, const obvh *b, const oray *ray, int brute) {
+    if (!b->count) return 0;
+    float t, u, v;
+    if (brute) {
+        for (uint32_t i = b->first; i < b->first + b->count; ++i) if (tri_intersect(&s->tris[i], ray, &t, &u, &v)) return 1;
+        return 0;
+    }
+    int stack[128], sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const onode *n = &b->nodes[stack[--sp]];
+        if (!box_hit(n, ray, ray->maxt)) continue;
+        if (n->left < 0) {
+            for (int i = n->first; i < n->first + n->count; ++i)
+                if (tri_intersect(&s->tris[b->order[i]], ray, &t, &u, &v)) return 1;
+        } else { stack[sp++] = n->left; stack[sp++] = n->right; }
+    }
+    return 0;
+}
+
+/* Transform::transform_affine for points / vectors / normals (transform.h:88-151): row-major M */
+static inline v3 xf_point(const float *M, v3 p) {
+    v3 r;
+    r.x = b2o_fma(M[2], p.z, b2o_fma(M[1], p.y, b2o_fma(M[0], p.x, M[3])));
+    r.y = b2o_fma(M[6], p.z, b2o_fma(M[5], p.y, b2o_fma(M[4], p.x, M[7])));
+    r.z = b2o_fma(M[10], p.z, b2o_fma(M[9], p.y, b2o_fma(M[8], p.x, M[11])));
+    return r;
+}
+static inline v3 xf_vector(const float *M, v3 d) {
+    v3 r;
+    r.x = b2o_fma(M[2], d.z, b2o_fma(M[1], d.y, M[0] * d.x));
+    r.y = b2o_fma(M[6], d.z, b2o_fma(M[5], d.y, M[4] * d.x));
+    r.z = b2o_fma(M[10], d.z, b2o_fma(M[9], d.y, M[8] * d.x));
+    return r;
+}
+/* normals use the inverse transpose: columns of `inv` (the inverse matrix, row-major) */
+static inline v3 xf_normal(const float *inv, v3 n) {
+    v3 r;
+    r.x = b2o_fma(inv[8], n.z, b2o_fma(inv[4], n.y, inv[0] * n.x));
+    r.y = b2o_fma(inv[9], n.z, b2o_fma(inv[5], n.y, inv[1] * n.x));
+    r.z = b2o_fma(inv[10], n.z, b2o_fma(inv[6], n.y, inv[2] * n.x));
+    return r;
+}
+/* Instance::ray_intersect_preliminary: m_to_object.transform_affine(ray) — origin as a point,
+   direction as an UN-normalised vector, mint/maxt unchanged (instance.cpp:107-117) */
+static inline oray instance_ray(const B2Instance *in, const oray *ray) {
+    oray r; r.o = xf_point(in->to_object, ray->o); r.d = xf_vector(in->to_object, ray->d);
+    r.mint = ray->mint; r.maxt = ray->maxt; return r;
+}
+static inline int inst_box_hit(const oscene *s, uint32_t i, const oray *ray, float tmax) {
+    onode n; for (int k = 0; k < 3; ++k) { n.lo[k] = s->inst_lo[i][k] - 1e-4f * (fabsf(s->inst_lo[i][k]) + 1.f); n.hi[k] = s->inst_hi[i][k] + 1e-4f * (fabsf(s->inst_hi[i][k]) + 1.f); }
+    return box_hit(&n, ray, tmax);
+}
+
+/* Scene::ray_intersect_preliminary (scene.cpp:131-137) with the order-independent tie rule */
+static ohit scene_intersect(const oscene *s, const oray *ray, int brute) {
+    ohit best; best.t = INFINITY; best.u = best.v = 0.f; best.prim = 0xffffffffu; best.inst = -1;
+    bvh_intersect(s, &s->top, ray, -1, brute, &best);
+    for (uint32_t i = 0; i < s->desc->n_instances; ++i) {
+        if (!brute && !inst_box_hit(s, i, ray, best.t < ray->maxt ? best.t : ray->maxt)) continue;
+        oray ro = instance_ray(&s->desc->instances[i], ray);
+        bvh_intersect(s, &s->groups[s->desc->instances[i].group], &ro, (int) i, brute, &best);
     }
     return best;
 }
 /* Scene::ray_test (scene.cpp:154-162) */
 static int scene_occluded(const oscene *s, const oray *ray, int brute) {
-    if (!s->n_tris) return 0;
-    float t, u, v;
-    if (brute) {
-        for (uint32_t i = 0; i < s->n_tris; ++i) if (tri_intersect(&s->tris[i], ray, &t, &u, &v)) return 1;
-        return 0;
-    }
-    int stack[128], sp = 0; stack[sp++] = 0;
-    while (sp) {
-        const onode *n = &s->nodes[stack[--sp]];
-        if (!box_hit(n, ray, ray->maxt)) continue;
-        if (n->left < 0) {
-            for (int i = n->first; i < n->first + n->count; ++i)
-                if (tri_intersect(&s->tris[s->order[i]], ray, &t, &u, &v)) return 1;
-        } else { stack[sp++] = n->left; stack[sp++] = n->right; }
+    if (bvh_occluded(s, &s->top, ray, brute)) return 1;
+    for (uint32_t i = 0; i < s->desc->n_instances; ++i) {
+        if (!brute && !inst_box_hit(s, i, ray, ray->maxt)) continue;
+        oray ro = instance_ray(&s->desc->instances[i], ray);
+        if (bvh_occluded(s, &s->groups[s->desc->instances[i].group], &ro, brute)) return 1;
     }
     return 0;
 }
@@ -505,7 +600,15 @@ static void si_fill(const oscene *s, const oray *ray, const ohit *h, osi *si) {
         si->sh_n = v3_normalize(v3_add(v3_add(v3_scale(tr->n0, b0), v3_scale(tr->n1, b1)), v3_scale(tr->n2, b2)));
     else
         si->sh_n = si->n;
-    /* initialize_sh_frame interaction.h:153-156 */
+    if (h->inst >= 0) {      /* Instance::compute_surface_interaction instance.cpp:124-142 */
+        const B2Instance *in = &s->desc->instances[h->inst];
+        si->p = xf_point(in->to_world, si->p);
+        si->n = v3_normalize(xf_normal(in->to_object, si->n));
+        si->sh_n = v3_normalize(xf_normal(in->to_object, si->sh_n));
+        dp_du = xf_vector(in->to_world, dp_du);
+    }
+    /* initialize_sh_frame interaction.h:153-156 (for instances: the call in interaction.h:587-588,
+       made after dp_du was mapped to world space) */
     si->sh_s = v3_normalize(v3_fnmadd(si->sh_n, v3_dot(si->sh_n, dp_du), dp_du));
     si->sh_t = v3_cross(si->sh_n, si->sh_s);
     si->wi = to_local(si, v3_neg(ray->d));                                                       /* interaction.h:591 */
@@ -1121,7 +1224,7 @@ B2O_API int b2o_render(const B2SceneDesc *d, const B2RenderParams *rp, float *xy
     if (stats) {
         memset(stats, 0, sizeof *stats);
         stats->n_samples = j.samples; stats->n_segments = j.cnt.segments; stats->n_shadow_rays = j.cnt.shadow_rays;
-        stats->n_invalid = j.invalid; stats->bvh_nodes = (uint64_t) s->n_nodes; stats->bvh_tris = s->n_tris;
+        stats->n_invalid = j.invalid; stats->bvh_nodes = (uint64_t) s->top.n_nodes; stats->bvh_tris = s->n_tris;
     }
     free(j.blocks); free(order); pthread_mutex_destroy(&j.mu);
     oscene_destroy(s);
@@ -1176,7 +1279,7 @@ B2O_API int b2o_stage_intersect(const B2SceneDesc *d, uint32_t n, const float *r
         oray r = load_ray(ray_o, ray_d, i);
         ohit h = scene_intersect(s, &r, brute);
         hit[4 * i] = h.t; hit[4 * i + 1] = h.u; hit[4 * i + 2] = h.v; hit[4 * i + 3] = b2o_u2f(h.prim);
-        if (inst) inst[i] = -1;
+        if (inst) inst[i] = h.inst;
     }
     oscene_destroy(s);
     return 0;
@@ -1193,11 +1296,10 @@ B2O_API int b2o_stage_occluded(const B2SceneDesc *d, uint32_t n, const float *ra
 }
 B2O_API int b2o_stage_si_fill(const B2SceneDesc *d, uint32_t n, const float *ray_o, const float *ray_d,
                               const float *hit, const int32_t *inst, float *si_out) {
-    (void) inst;
     oscene *s = oscene_create(d);
     for (uint32_t i = 0; i < n; ++i) {
         oray r = load_ray(ray_o, ray_d, i);
-        ohit h; h.t = hit[4 * i]; h.u = hit[4 * i + 1]; h.v = hit[4 * i + 2]; h.prim = b2o_f2u(hit[4 * i + 3]);
+        ohit h; h.t = hit[4 * i]; h.u = hit[4 * i + 1]; h.v = hit[4 * i + 2]; h.prim = b2o_f2u(hit[4 * i + 3]); h.inst = inst ? inst[i] : -1;
         osi si; si_fill(s, &r, &h, &si);
         float *o = si_out + 16 * (size_t) i;
         o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z;

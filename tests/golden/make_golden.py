@@ -189,8 +189,17 @@ CBOX_BSDFS = {
 CBOX_RADIANCE = (18.387, 10.9873, 2.75357)
 
 
+EXTRA_EMITTER_OBJ = """v 150 420 150
+v 260 420 150
+v 260 420 270
+v 150 420 270
+f 1 2 3 4
+"""
+EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
+
+
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
-             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0):
+             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -213,6 +222,12 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             lines = [l for l in open(f"{CBOX}/meshes/{fn}") if l.strip() != "f 8 7 6 5"]
             open(path, "w").writelines(lines)
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
+    if extra_emitter:
+        # a second area emitter (scene.cpp:176-198: uniform emitter selection): a small quad facing down
+        path = os.path.join(mesh_dir, "extra_emitter.obj")
+        open(path, "w").write(EXTRA_EMITTER_OBJ)
+        shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/><ref id="white"/>'
+                      '<emitter type="area"><rgb name="radiance" value="4.0, 16.0, 6.0"/></emitter></shape>')
     rf = '<rfilter type="box"/>' if rfilter == "box" else '<rfilter type="gaussian"/>'
     sp = f'<integer name="samples_per_pass" value="{samples_per_pass}"/>' if samples_per_pass else ""
     xml = CBOX_XML.format(width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
@@ -257,6 +272,7 @@ GOLDEN = {
     "cbox_64_spp16_bs16_seed7": dict(width=64, height=64, spp=16, block_size=16, seed=7),
     "cbox_64_spp16_dielectric": dict(width=64, height=64, spp=16, materials={"box": DIELECTRIC}),
     "cbox_64_spp16_dielectric_lift": dict(width=64, height=64, spp=16, materials={"box": DIELECTRIC}, lift=10.0),
+    "cbox_64_spp16_two_emitters": dict(width=64, height=64, spp=16, no_patch=True, extra_emitter=True),
     "cbox_64_spp16_ggx": dict(width=64, height=64, spp=16, materials={"box": ROUGH_GGX}),
     "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
 }
@@ -276,8 +292,14 @@ def main():
             continue
         img, log = run_reference(lambda td: cbox_xml(mesh_dir=td, **kw))
         kw_s = {k: (v if not isinstance(v, dict) else {kk: vv for kk, vv in v.items()}) for k, v in kw.items()}
+        extra = {}
+        if kw.get("extra_emitter"):
+            with tempfile.TemporaryDirectory() as td:
+                p = os.path.join(td, "e.obj"); open(p, "w").write(EXTRA_EMITTER_OBJ)
+                ep, en, ef = load_obj_like_reference(p)
+            extra = dict(extra_positions=ep, extra_normals=en, extra_faces=ef, extra_radiance=np.array(EXTRA_EMITTER_RADIANCE, np.float32))
         np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), rgb=img, params=np.array(repr(kw_s)),
-                            oracle_build=np.array(info))
+                            oracle_build=np.array(info), **extra)
         print(f"ref_{name}.npz", img.shape, "mean", img.mean(axis=(0, 1)))
 
 

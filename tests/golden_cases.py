@@ -41,6 +41,9 @@ def load(name, host):
     sb = scenes.cbox(host, kw["width"], kw["height"], rfilter=kw.get("rfilter", "box"),
                      materials=_materials(kw.get("materials")),
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0))
+    if kw.get("extra_emitter"):
+        mi = sb.add_mesh(z["extra_positions"], z["extra_faces"], z["extra_normals"], bsdf=1)     # 'white'
+        sb.add_area_emitter(mi, tuple(float(x) for x in z["extra_radiance"]))
     rp = abi.render_params(max_depth=kw.get("max_depth", 6), rr_depth=kw.get("rr_depth", 5), spp=kw["spp"],
                            samples_per_pass=kw.get("samples_per_pass") or 0, block_size=kw.get("block_size", 32),
                            seed=kw.get("seed", 0))
