@@ -89,6 +89,7 @@ typedef struct B2Emitter {
     const float *envmap;        /* envmap: RGBA fp32 texels, (height x width x 4), row-major   */
     int32_t env_width, env_height;
     float env_to_world[16];     /* envmap to_world, row-major 4x4                              */
+    float env_to_object[16];    /* its inverse, as the reference's Transform stores it         */
 } B2Emitter;
 
 /* ---- meshes (include/mitsuba/render/mesh.h:344-361) ------------------------------------- */

@@ -33,7 +33,7 @@ class B2Emitter(C.Structure):
         ("radiance", C.c_float * 3), ("scale", C.c_float),
         ("envmap", C.POINTER(C.c_float)),
         ("env_width", C.c_int32), ("env_height", C.c_int32),
-        ("env_to_world", C.c_float * 16),
+        ("env_to_world", C.c_float * 16), ("env_to_object", C.c_float * 16),
     ]
 
 
@@ -129,6 +129,8 @@ class SceneBuffers:
         self.emitters = []    # B2Emitter
         self.sensor = B2Sensor()
         self.film = B2Film()
+        self.groups = []      # list of lists of mesh indices (shapegroups, src/librender/shapegroup.cpp)
+        self.instances = []   # (group index, to_world 4x4, to_object 4x4)   (src/shapes/instance.cpp)
         self._keep = []
 
     # -- BSDF / emitter constructors with the reference plugins' defaults --------------------
@@ -163,6 +165,21 @@ class SceneBuffers:
         self.meshes[mesh_index]["emitter"] = len(self.emitters) - 1
         return len(self.emitters) - 1
 
+    def add_envmap(self, rgb, scale=1.0, to_world=None):
+        """EnvironmentMapEmitter (src/emitters/envmap.cpp): rgb = float32 [H, W, 3] lat-long image."""
+        rgb = np.asarray(rgb, np.float32)
+        H, W = rgb.shape[:2]
+        rgba = np.ones((H, W, 4), np.float32); rgba[..., :3] = rgb[..., :3]
+        self._env_data = np.ascontiguousarray(rgba)
+        e = B2Emitter(); e.type = EMITTER_ENVMAP; e.mesh = -1; e.scale = scale
+        e.envmap = fptr(self._env_data); e.env_width = W; e.env_height = H
+        m = np.eye(4, dtype=np.float32) if to_world is None else np.asarray(to_world, np.float32).reshape(4, 4)
+        inv = np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+        e.env_to_world[:] = [float(x) for x in m.reshape(-1)]
+        e.env_to_object[:] = [float(x) for x in inv.reshape(-1)]
+        self.emitters.append(e)
+        return len(self.emitters) - 1
+
     def add_mesh(self, positions, faces, normals=None, bsdf=0):
         m = dict(positions=np.ascontiguousarray(positions, np.float32).reshape(-1, 3),
                  faces=np.ascontiguousarray(faces, np.uint32).reshape(-1, 3),
@@ -170,27 +187,58 @@ class SceneBuffers:
                  bsdf=bsdf, emitter=-1)
         self.meshes.append(m); return len(self.meshes) - 1
 
+    def add_shapegroup(self, mesh_indices):
+        """Move the given meshes (added with add_mesh) into a new shapegroup; returns its index."""
+        self.groups.append(list(mesh_indices)); return len(self.groups) - 1
+
+    def add_instance(self, group, to_world):
+        """to_world: 4x4 (row-major). The inverse is computed in fp64 and rounded to fp32 — exact for
+        the rigid / axis-permuting / power-of-two transforms used by the parity scenes."""
+        m = np.asarray(to_world, np.float32).reshape(4, 4)
+        inv = np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+        self.instances.append((group, m, inv)); return len(self.instances) - 1
+
     @property
     def n_triangles(self):
         return int(sum(len(m["faces"]) for m in self.meshes))
 
     def desc(self):
         d = B2SceneDesc()
+        # top-level meshes first, then the shapegroups' meshes (B2SceneDesc.group_first)
+        grouped = [m for g in self.groups for m in g]
+        order = [i for i in range(len(self.meshes)) if i not in grouped] + grouped
+        remap = {old: new for new, old in enumerate(order)}
+        n_top = len(self.meshes) - len(grouped)
         ms = (B2Mesh * max(1, len(self.meshes)))()
-        for i, m in enumerate(self.meshes):
-            ms[i].n_vertices = len(m["positions"]); ms[i].n_faces = len(m["faces"])
-            ms[i].positions = fptr(m["positions"])
-            ms[i].normals = fptr(m["normals"]) if m["normals"] is not None else None
-            ms[i].texcoords = None
-            ms[i].faces = uptr(m["faces"])
-            ms[i].bsdf = m["bsdf"]; ms[i].emitter = m["emitter"]
+        for new, old in enumerate(order):
+            m = self.meshes[old]
+            ms[new].n_vertices = len(m["positions"]); ms[new].n_faces = len(m["faces"])
+            ms[new].positions = fptr(m["positions"])
+            ms[new].normals = fptr(m["normals"]) if m["normals"] is not None else None
+            ms[new].texcoords = None
+            ms[new].faces = uptr(m["faces"])
+            ms[new].bsdf = m["bsdf"]; ms[new].emitter = m["emitter"]
         bs = (B2Bsdf * max(1, len(self.bsdfs)))(*self.bsdfs)
-        es = (B2Emitter * max(1, len(self.emitters)))(*self.emitters)
+        es = (B2Emitter * max(1, len(self.emitters)))()
+        for i, e in enumerate(self.emitters):
+            C.memmove(C.byref(es[i]), C.byref(e), C.sizeof(B2Emitter))
+            es[i].mesh = remap[e.mesh] if e.mesh >= 0 else -1
         d.n_meshes = len(self.meshes); d.meshes = ms
         d.n_bsdfs = len(self.bsdfs); d.bsdfs = bs
         d.n_emitters = len(self.emitters); d.emitters = es
-        d.n_groups = 0; d.group_first = None; d.n_instances = 0; d.instances = None
-        d.n_top_meshes = len(self.meshes)
+        gf = (C.c_uint32 * (len(self.groups) + 1))()
+        pos = n_top
+        for gi, g in enumerate(self.groups):
+            gf[gi] = pos; pos += len(g)
+        gf[len(self.groups)] = pos
+        ins = (B2Instance * max(1, len(self.instances)))()
+        for i, (g, m, inv) in enumerate(self.instances):
+            ins[i].group = g
+            ins[i].to_world[:] = [float(x) for x in m.reshape(-1)]
+            ins[i].to_object[:] = [float(x) for x in inv.reshape(-1)]
+        d.n_groups = len(self.groups); d.group_first = gf if self.groups else None
+        d.n_instances = len(self.instances); d.instances = ins if self.instances else None
+        d.n_top_meshes = n_top
         d.sensor = self.sensor; d.film = self.film
-        self._keep = [ms, bs, es]
+        self._keep = [ms, bs, es, gf, ins]
         return d

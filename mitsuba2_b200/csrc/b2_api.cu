@@ -56,6 +56,9 @@ template <typename T> struct DBuf {
 struct B2Scene {
     DScene d{};
     DBuf<float4> nodes, tri_isect;
+    DBuf<DInstance> instances;
+    DBuf<uint32_t> inst_order;
+    DBuf<int32_t> hit_inst;
     DBuf<unsigned char> blob;       // tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
     int shade_smem_bytes = 0;
     uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
@@ -95,7 +98,16 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     if (!desc || !out) return fail(B2_ERR_INVALID, "b2_scene_create: null argument");
     *out = nullptr;
     if (b2_device_count() == 0) return fail(B2_ERR_NO_DEVICE, "b2_scene_create: no CUDA device (libb2pt has no CPU fallback)");
-    if (desc->n_instances || desc->n_groups) return fail(B2_ERR_INVALID, "instancing is not supported yet");
+    uint32_t n_top_meshes = desc->n_groups ? desc->n_top_meshes : desc->n_meshes;
+    if (n_top_meshes > desc->n_meshes) return fail(B2_ERR_INVALID, "n_top_meshes out of range");
+    for (uint32_t g = 0; g < desc->n_groups; ++g)
+        if (desc->group_first[g] < n_top_meshes || desc->group_first[g] > desc->group_first[g + 1] || desc->group_first[g + 1] > desc->n_meshes)
+            return fail(B2_ERR_INVALID, "shapegroup %u: bad mesh range", g);
+    for (uint32_t i = 0; i < desc->n_instances; ++i)
+        if (desc->instances[i].group < 0 || (uint32_t) desc->instances[i].group >= desc->n_groups)
+            return fail(B2_ERR_INVALID, "instance %u: bad shapegroup index", i);
+    for (uint32_t m = n_top_meshes; m < desc->n_meshes; ++m)
+        if (desc->meshes[m].emitter >= 0) return fail(B2_ERR_INVALID, "Instancing of emitters is not supported");   // shapegroup.cpp:24-25
     for (uint32_t e = 0; e < desc->n_emitters; ++e)
         if (desc->emitters[e].type != B2_EMITTER_AREA) return fail(B2_ERR_INVALID, "emitter %u: only area emitters are supported", e);
     for (uint32_t m = 0; m < desc->n_meshes; ++m) {
@@ -122,7 +134,63 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
             for (int v = 0; v < 3; ++v)
                 std::memcpy(tris[mesh_first[m] + f].p[v], me.positions + 3 * (size_t) me.faces[3 * f + v], 12);
     }
-    B2Bvh4 bvh; b2_build_bvh4(tris, bvh);
+    // one BVH over the top-level triangles, one per shapegroup, one over the instances' world bounds;
+    // all in one node array (top-level first: it is the part staged into shared memory)
+    uint32_t n_top_tris = mesh_first[n_top_meshes];
+    struct { std::vector<float> nodes; std::vector<uint32_t> order; uint32_t n_nodes = 0, depth = 0; } bvh;
+    uint32_t top_nodes = 0;
+    {
+        std::vector<B2BvhTri> sub(tris.begin(), tris.begin() + n_top_tris);
+        B2Bvh4 b; b2_build_bvh4(sub, b);
+        b2_bvh4_append(bvh.nodes, b, 0);
+        bvh.order = b.order; bvh.depth = b.depth; top_nodes = b.n_nodes;
+    }
+    std::vector<uint32_t> group_root(desc->n_groups, 0);
+    std::vector<B2BvhBox> group_box(desc->n_groups);
+    for (uint32_t g = 0; g < desc->n_groups; ++g) {
+        uint32_t t0 = mesh_first[desc->group_first[g]], t1 = mesh_first[desc->group_first[g + 1]];
+        std::vector<B2BvhTri> sub(tris.begin() + t0, tris.begin() + t1);
+        B2Bvh4 b; b2_build_bvh4(sub, b);
+        group_root[g] = b2_bvh4_append(bvh.nodes, b, (uint32_t) bvh.order.size());
+        for (uint32_t o : b.order) bvh.order.push_back(t0 + o);
+        bvh.depth = std::max(bvh.depth, b.depth);
+        B2BvhBox bx; for (int k = 0; k < 3; ++k) { bx.lo[k] = INFINITY; bx.hi[k] = -INFINITY; }
+        for (const B2BvhTri &t : sub) for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) {
+            bx.lo[k] = std::min(bx.lo[k], t.p[v][k]); bx.hi[k] = std::max(bx.hi[k], t.p[v][k]);
+        }
+        group_box[g] = bx;
+    }
+    std::vector<DInstance> dinst(desc->n_instances);
+    std::vector<uint32_t> inst_order;
+    uint32_t tlas_root = 0;
+    if (desc->n_instances) {
+        std::vector<B2BvhBox> ib(desc->n_instances);
+        for (uint32_t i = 0; i < desc->n_instances; ++i) {
+            const B2Instance &in = desc->instances[i];
+            std::memcpy(dinst[i].to_world, in.to_world, 48); std::memcpy(dinst[i].to_object, in.to_object, 48);
+            dinst[i].root = (int32_t) group_root[in.group];
+            const B2BvhBox &gb = group_box[in.group];
+            B2BvhBox w; for (int k = 0; k < 3; ++k) { w.lo[k] = INFINITY; w.hi[k] = -INFINITY; }
+            for (int c = 0; c < 8; ++c) {                           // Instance::bbox(), instance.cpp:83-94
+                double p[3] = { c & 1 ? gb.hi[0] : gb.lo[0], c & 2 ? gb.hi[1] : gb.lo[1], c & 4 ? gb.hi[2] : gb.lo[2] };
+                for (int r = 0; r < 3; ++r) {
+                    const float *M = in.to_world + 4 * r;
+                    double v = (double) M[3] + (double) M[0] * p[0] + (double) M[1] * p[1] + (double) M[2] * p[2];
+                    float lo = (float) v, hi = (float) v;
+                    lo = std::nextafter(lo, -INFINITY); hi = std::nextafter(hi, INFINITY);
+                    w.lo[r] = std::min(w.lo[r], lo); w.hi[r] = std::max(w.hi[r], hi);
+                }
+            }
+            // the object-space triangle test sees rounded coordinates: pad by 1e-4 of the box size
+            for (int k = 0; k < 3; ++k) { float e = 1e-4f * (std::fabs(w.lo[k]) + std::fabs(w.hi[k]) + 1e-3f); w.lo[k] -= e; w.hi[k] += e; }
+            ib[i] = w;
+        }
+        B2Bvh4 t; b2_build_bvh4_boxes(ib, 1, t);
+        tlas_root = b2_bvh4_append(bvh.nodes, t, 0);
+        inst_order = t.order;
+        bvh.depth += t.depth;
+    }
+    bvh.n_nodes = (uint32_t) (bvh.nodes.size() / 32);
 
     std::vector<float4> tri_pos(3 * (size_t) nt), tri_nrm(3 * (size_t) nt), tri_isect(3 * (size_t) nt);
     std::vector<uint32_t> prim_to_slot(nt);
@@ -197,7 +265,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     if (!ems.empty()) std::memcpy(blob.data() + off_em, ems.data(), ems.size() * sizeof(DEmitter));
     cudaError_t e = cudaSuccess;
     if ((e = s->nodes.upload(nodes)) != cudaSuccess || (e = s->tri_isect.upload(tri_isect)) != cudaSuccess ||
-        (e = s->blob.upload(blob)) != cudaSuccess) {
+        (e = s->blob.upload(blob)) != cudaSuccess || (e = s->instances.upload(dinst)) != cudaSuccess ||
+        (e = s->inst_order.upload(inst_order)) != cudaSuccess) {
         delete s;
         return fail(B2_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
@@ -210,20 +279,26 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.bsdfs = (const B2Bsdf *) (s->blob.p + off_bsdf); d.emitters = (const DEmitter *) (s->blob.p + off_em);
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
+    d.instances = desc->n_instances ? s->instances.p : nullptr; d.inst_order = s->inst_order.p;
+    d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_tris;
     d.n_nodes = bvh.n_nodes; d.n_tris = nt; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
     d.sensor = desc->sensor; d.film = desc->film;
     // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
     const uint32_t budget_all = 48 * 1024, budget_top = 32 * 1024;
     if (bvh.n_nodes * 128u + nt * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
-    else { d.smem_nodes = std::min<uint32_t>(bvh.n_nodes, budget_top / 128u); d.smem_tris = 0; }
+    else { d.smem_nodes = std::min<uint32_t>(top_nodes, budget_top / 128u); d.smem_tris = 0; }
     s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u));
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
-    cudaFuncSetAttribute(k_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_shadow, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_stage_intersect, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_stage_occluded, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_stage_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_stage_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_stage_occluded<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_stage_occluded<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     *out = s;
     return B2_OK;
 }
@@ -286,7 +361,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     }
     uint64_t total64 = (uint64_t) item_pixel.size() * n_passes;
     uint32_t n_items_pass = (uint32_t) item_pixel.size();
-    uint32_t slots = rp->lane_slots ? rp->lane_slots : (1u << 22);
+    // default wavefront width: a whole number of lanes per thread for every stage kernel
+    // (sm_count * 3072 = 3 lanes/thread at 4 CTAs/SM, 4 lanes/thread at 3 CTAs/SM) — and small
+    // enough (71 MB of queues on 148 SMs) to stay resident in the 126 MB L2 between the stages
+    uint32_t slots = rp->lane_slots ? rp->lane_slots : (uint32_t) s->sm_count * 3072u;
     if ((uint64_t) slots > total64) slots = (uint32_t) std::max<uint64_t>(total64, 1);
     slots = (slots + 31u) & ~31u;
     if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
@@ -296,6 +374,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(s->sh_o.alloc(slots)); CU(s->sh_d.alloc(slots)); CU(s->sh_c.alloc(slots)); CU(s->sh_r.alloc(slots)); CU(s->sh_f.alloc(slots));
     CU(s->st.alloc(slots));
     if (wide) { CU(s->pos.alloc(slots)); CU(s->sh_p.alloc(slots)); }
+    if (s->d.n_instances) CU(s->hit_inst.alloc(slots));
     CU(s->cnt.alloc(16)); CU(s->stats.alloc(8));
     CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
     CU(s->film.alloc((size_t) W * H * 5));
@@ -304,6 +383,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     Queues q{};
     q.ray_o = s->ray_o.p; q.ray_d = s->ray_d.p; q.hit = s->hit.p; q.tp = s->tp.p; q.res = s->res.p; q.st = s->st.p;
     q.pos = wide ? s->pos.p : nullptr; q.sh_p = wide ? s->sh_p.p : nullptr;
+    q.hit_inst = s->d.n_instances ? s->hit_inst.p : nullptr;
     q.sh_o = s->sh_o.p; q.sh_d = s->sh_d.p; q.sh_c = s->sh_c.p; q.sh_r = s->sh_r.p; q.sh_f = s->sh_f.p;
     q.cnt = s->cnt.p; q.stats = s->stats.p;
     q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
@@ -317,10 +397,19 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     CU(cudaMemsetAsync(s->cnt.p, 0, 16 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
+    // persistent grids: exactly the number of CTAs that are resident at once, per kernel
     const int threads = 256;
-    int grid = s->sm_count * 8;
+    const bool inst = s->d.n_instances != 0;
     uint32_t need_blocks = (slots + threads - 1) / threads;
-    if ((uint32_t) grid > need_blocks) grid = (int) std::max<uint32_t>(need_blocks, 1);
+    auto resident = [&](auto kernel, int smem) {
+        int per_sm = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+        return (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (s->sm_count * std::max(per_sm, 1)), need_blocks));
+    };
+    int grid = resident(k_init, 0);
+    int grid_int = inst ? resident(k_intersect<true>, s->smem_bytes) : resident(k_intersect<false>, s->smem_bytes);
+    int grid_sha = resident(k_shade, s->shade_smem_bytes);
+    int grid_shw = inst ? resident(k_shadow<true>, s->smem_bytes) : resident(k_shadow<false>, s->smem_bytes);
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
@@ -338,11 +427,13 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         int slot = b & 1;
         for (int it = 0; it < batch; ++it) {
             tick();
-            k_intersect<<<grid, threads, s->smem_bytes, stream>>>(s->d, q);
+            if (inst) k_intersect<true><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q);
+            else k_intersect<false><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q);
             tick();
-            k_shade<<<grid, threads, s->shade_smem_bytes, stream>>>(s->d, q);
+            k_shade<<<grid_sha, threads, s->shade_smem_bytes, stream>>>(s->d, q);
             tick();
-            k_shadow<<<grid, threads, s->smem_bytes, stream>>>(s->d, q);
+            if (inst) k_shadow<true><<<grid_shw, threads, s->smem_bytes, stream>>>(s->d, q);
+            else k_shadow<false><<<grid_shw, threads, s->smem_bytes, stream>>>(s->d, q);
             tick();
             ++iterations; launches += 3;
         }
@@ -435,13 +526,14 @@ static int stage_grid(const B2Scene *s, uint32_t n) {
 int b2_stage_intersect(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, float *hit, int32_t *inst) {
     if (!s || (n && (!ray_o || !ray_d || !hit))) return fail(B2_ERR_INVALID, "b2_stage_intersect: null argument");
     if (n == 0) return B2_OK;
-    DBuf<float4> o, d, h;
-    CU(o.alloc(n)); CU(d.alloc(n)); CU(h.alloc(n));
+    DBuf<float4> o, d, h; DBuf<int32_t> di;
+    CU(o.alloc(n)); CU(d.alloc(n)); CU(h.alloc(n)); CU(di.alloc(n));
     CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice));
-    k_stage_intersect<<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p);
+    if (s->d.n_instances) k_stage_intersect<true><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p, di.p);
+    else k_stage_intersect<false><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p, di.p);
     CU(cudaGetLastError());
     CU(cudaMemcpy(hit, h.p, n * 16, cudaMemcpyDeviceToHost));
-    if (inst) for (uint32_t i = 0; i < n; ++i) inst[i] = -1;
+    if (inst) CU(cudaMemcpy(inst, di.p, n * 4, cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 
@@ -451,20 +543,22 @@ int b2_stage_occluded(B2Scene *s, uint32_t n, const float *ray_o, const float *r
     DBuf<float4> o, d; DBuf<uint8_t> r;
     CU(o.alloc(n)); CU(d.alloc(n)); CU(r.alloc(n));
     CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice));
-    k_stage_occluded<<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
+    if (s->d.n_instances) k_stage_occluded<true><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
+    else k_stage_occluded<false><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
     CU(cudaGetLastError());
     CU(cudaMemcpy(occluded, r.p, n, cudaMemcpyDeviceToHost));
     return B2_OK;
 }
 
 int b2_stage_si_fill(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, const float *hit, const int32_t *inst, float *si) {
-    (void) ray_o; (void) inst;
+    (void) ray_o;
     if (!s || (n && (!ray_d || !hit || !si))) return fail(B2_ERR_INVALID, "b2_stage_si_fill: null argument");
     if (n == 0) return B2_OK;
-    DBuf<float4> d, h; DBuf<float> out;
+    DBuf<float4> d, h; DBuf<float> out; DBuf<int32_t> di;
     CU(d.alloc(n)); CU(h.alloc(n)); CU(out.alloc((size_t) n * 16));
     CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(h.p, hit, n * 16, cudaMemcpyHostToDevice));
-    k_stage_si_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, d.p, h.p, out.p);
+    if (inst) { CU(di.alloc(n)); CU(cudaMemcpy(di.p, inst, n * 4, cudaMemcpyHostToDevice)); }
+    k_stage_si_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, d.p, h.p, inst ? di.p : nullptr, out.p);
     CU(cudaGetLastError());
     CU(cudaMemcpy(si, out.p, (size_t) n * 64, cudaMemcpyDeviceToHost));
     return B2_OK;

@@ -23,14 +23,12 @@ struct Box {
 struct Node2 { Box box; int left = -1, right = -1; uint32_t first = 0, count = 0; };
 
 struct Builder {
-    const std::vector<B2BvhTri> &tris;
     std::vector<Box> tbox;
     std::vector<float> cent;        // 3 per tri
     std::vector<uint32_t> idx;
     std::vector<Node2> nodes;
-    static constexpr int kBins = 16, kMaxLeaf = 2;
-
-    explicit Builder(const std::vector<B2BvhTri> &t) : tris(t) {}
+    static constexpr int kBins = 16;
+    int kMaxLeaf = 2;
 
     int build(uint32_t first, uint32_t count) {
         int id = (int) nodes.size();
@@ -88,20 +86,48 @@ struct Builder {
 }  // namespace
 
 void b2_build_bvh4(const std::vector<B2BvhTri> &tris, B2Bvh4 &out) {
+    std::vector<B2BvhBox> boxes(tris.size());
+    for (size_t i = 0; i < tris.size(); ++i) {
+        Box bx; bx.reset();
+        for (int v = 0; v < 3; ++v) bx.grow(tris[i].p[v]);
+        for (int k = 0; k < 3; ++k) { boxes[i].lo[k] = bx.lo[k]; boxes[i].hi[k] = bx.hi[k]; }
+    }
+    b2_build_bvh4_boxes(boxes, 2, out);
+}
+
+uint32_t b2_bvh4_append(std::vector<float> &dst, const B2Bvh4 &src, uint32_t slot_base) {
+    uint32_t node_base = (uint32_t) (dst.size() / 32);
+    size_t off = dst.size();
+    dst.insert(dst.end(), src.nodes.begin(), src.nodes.end());
+    for (uint32_t n = 0; n < src.n_nodes; ++n)
+        for (int k = 0; k < 4; ++k) {
+            int32_t code; std::memcpy(&code, &dst[off + 32 * (size_t) n + 24 + k], 4);
+            if (code > 0) code += (int32_t) node_base;
+            else if (code < 0) {
+                uint32_t u = (uint32_t) code, first = u & 0x07ffffffu;
+                code = (int32_t) ((u & 0xf8000000u) | ((first + slot_base) & 0x07ffffffu));
+            }
+            std::memcpy(&dst[off + 32 * (size_t) n + 24 + k], &code, 4);
+        }
+    return node_base;
+}
+
+void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh4 &out) {
     out.nodes.clear(); out.order.clear(); out.n_nodes = 0; out.depth = 0;
-    uint32_t n = (uint32_t) tris.size();
+    uint32_t n = (uint32_t) boxes.size();
     if (n == 0) {
         out.nodes.assign(32, 0.f); out.n_nodes = 1;
         for (int k = 0; k < 12; ++k) out.nodes[k] = std::numeric_limits<float>::infinity();
         for (int k = 12; k < 24; ++k) out.nodes[k] = -std::numeric_limits<float>::infinity();
         return;
     }
-    Builder b(tris);
+    Builder b;
+    b.kMaxLeaf = max_leaf;
     b.tbox.resize(n); b.cent.resize(3 * (size_t) n); b.idx.resize(n);
     Box scene; scene.reset();
     for (uint32_t i = 0; i < n; ++i) {
-        Box bx; bx.reset();
-        for (int v = 0; v < 3; ++v) bx.grow(tris[i].p[v]);
+        Box bx;
+        for (int k = 0; k < 3; ++k) { bx.lo[k] = boxes[i].lo[k]; bx.hi[k] = boxes[i].hi[k]; }
         b.tbox[i] = bx; scene.grow(bx);
         for (int k = 0; k < 3; ++k) b.cent[3 * (size_t) i + k] = 0.5f * (bx.lo[k] + bx.hi[k]);
         b.idx[i] = i;

@@ -10,6 +10,7 @@
 #include <vector>
 
 struct B2BvhTri { float p[3][3]; };
+struct B2BvhBox { float lo[3], hi[3]; };
 
 struct B2Bvh4 {
     std::vector<float> nodes;       // 32 floats (128 B) per node, layout in b2_device.cuh
@@ -19,3 +20,9 @@ struct B2Bvh4 {
 };
 
 void b2_build_bvh4(const std::vector<B2BvhTri> &tris, B2Bvh4 &out);
+// Same builder over arbitrary primitive boxes (used for the top-level BVH over instances).
+// max_leaf = primitives per leaf (1..15); pad_scale multiplies the conservative inflation.
+void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh4 &out);
+// Append `src` to the global node array `dst` (32 floats per node): inner child indices are
+// rebased by the node offset, leaf first-slot indices by `slot_base`. Returns the root index.
+uint32_t b2_bvh4_append(std::vector<float> &dst, const B2Bvh4 &src, uint32_t slot_base);

@@ -31,6 +31,14 @@ struct DEmitter {
     uint32_t valid_first, valid_last;
 };
 
+// one-level instancing (src/shapes/instance.cpp): affine 3x4 transforms, row-major
+struct DInstance {
+    float to_world[12];
+    float to_object[12];
+    int32_t root;               // root node of the shapegroup's BVH in DScene.nodes
+    int32_t _pad[3];
+};
+
 struct DScene {
     const float4 *nodes;
     const float4 *tri_pos;
@@ -41,6 +49,9 @@ struct DScene {
     const float *cdf;
     const uint32_t *prim_to_slot;
     uint32_t n_nodes, n_tris, n_emitters, n_bsdfs;
+    const DInstance *instances; // NULL for flat scenes
+    const uint32_t *inst_order; // TLAS leaf order -> instance index
+    uint32_t n_instances, tlas_root, n_top_tris, _pad0;
     uint32_t smem_nodes;        // nodes [0, smem_nodes) are staged in shared memory
     uint32_t smem_tris;         // 1: all triangle positions staged in shared memory too
     const unsigned char *blob;  // one allocation holding tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
@@ -58,11 +69,12 @@ struct Tables {
     const float *cdf;
     const B2Bsdf *bsdfs;
     const DEmitter *emitters;
+    const DInstance *instances;
     uint32_t n_emitters;
 };
 B2_D Tables make_tables(const DScene &sc) {
     Tables t; t.tri_pos = sc.tri_pos; t.tri_nrm = sc.tri_nrm; t.prim_to_slot = sc.prim_to_slot; t.cdf = sc.cdf;
-    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.n_emitters = sc.n_emitters; return t;
+    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.instances = sc.instances; t.n_emitters = sc.n_emitters; return t;
 }
 
 struct Ray { float3 o, d; float mint, maxt; };
@@ -98,7 +110,25 @@ B2_D float3 coordinate_system_s(float3 n) {        // include/mitsuba/core/vecto
 B2_D float3 to_local(const SI &si, float3 v) { return v3(dot(v, si.sh_s), dot(v, si.sh_t), dot(v, si.sh_n)); }
 B2_D float3 to_world(const SI &si, float3 v) { return (si.sh_s * v.x + si.sh_t * v.y) + si.sh_n * v.z; }   // frame.h:35-37
 
-B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_d, SI &si) {
+// Transform::transform_affine for points / vectors / normals (include/mitsuba/core/transform.h:88-151);
+// M = 3x4 row-major; normals use the inverse transpose = columns of the inverse matrix
+B2_D float3 xf_point(const float *M, float3 p) {
+    return v3(b2_fma(M[2], p.z, b2_fma(M[1], p.y, b2_fma(M[0], p.x, M[3]))),
+              b2_fma(M[6], p.z, b2_fma(M[5], p.y, b2_fma(M[4], p.x, M[7]))),
+              b2_fma(M[10], p.z, b2_fma(M[9], p.y, b2_fma(M[8], p.x, M[11]))));
+}
+B2_D float3 xf_vector(const float *M, float3 d) {
+    return v3(b2_fma(M[2], d.z, b2_fma(M[1], d.y, M[0] * d.x)),
+              b2_fma(M[6], d.z, b2_fma(M[5], d.y, M[4] * d.x)),
+              b2_fma(M[10], d.z, b2_fma(M[9], d.y, M[8] * d.x)));
+}
+B2_D float3 xf_normal(const float *inv, float3 n) {
+    return v3(b2_fma(inv[8], n.z, b2_fma(inv[4], n.y, inv[0] * n.x)),
+              b2_fma(inv[9], n.z, b2_fma(inv[5], n.y, inv[1] * n.x)),
+              b2_fma(inv[10], n.z, b2_fma(inv[6], n.y, inv[2] * n.x)));
+}
+
+B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_d, int inst, SI &si) {
     float4 a0 = B2_LD(&sc.tri_pos[3 * slot]), a1 = B2_LD(&sc.tri_pos[3 * slot + 1]), a2 = B2_LD(&sc.tri_pos[3 * slot + 2]);
     float4 m0 = B2_LD(&sc.tri_nrm[3 * slot]), m1 = B2_LD(&sc.tri_nrm[3 * slot + 1]), m2 = B2_LD(&sc.tri_nrm[3 * slot + 2]);
     float3 p0 = v3(a0), p1 = v3(a1), p2 = v3(a2);
@@ -111,6 +141,13 @@ B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_
         si.sh_n = normalize((v3(m0) * b0 + v3(m1) * b1) + v3(m2) * b2);
     else
         si.sh_n = si.n;
+    if (inst >= 0) {                                             // Instance::compute_surface_interaction, instance.cpp:124-142
+        const DInstance &in = sc.instances[inst];
+        si.p = xf_point(in.to_world, si.p);
+        si.n = normalize(xf_normal(in.to_object, si.n));
+        si.sh_n = normalize(xf_normal(in.to_object, si.sh_n));
+        dp_du = xf_vector(in.to_world, dp_du);
+    }
     si.sh_s = normalize(fnmadd(si.sh_n, dot(si.sh_n, dp_du), dp_du));   // interaction.h:153-156
     si.sh_t = cross(si.sh_n, si.sh_s);
     si.wi = to_local(si, -ray_d);                                // interaction.h:591

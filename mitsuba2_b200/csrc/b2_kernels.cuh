@@ -22,6 +22,7 @@
 struct Queues {
     float4 *ray_o, *ray_d;      // (o.xyz, mint), (d.xyz, maxt); maxt < 0 marks a retired lane   32 B
     float4 *hit;                // (t, u, v, slot bits); t = +inf: miss                           16 B
+    int32_t *hit_inst;          // instance index of the hit (-1: top-level shape); NULL for flat scenes
     float4 *tp;                 // (throughput.rgb, eta)                                          16 B
     float4 *res;                // (result.rgb, pdf of the last BSDF sample)                      16 B
     uint4 *st;                  // (rng.lo, rng.hi, work item, depth|flags|samples_left)          16 B
@@ -123,7 +124,7 @@ B2_D SmemScene stage_scene(const DScene &sc, unsigned char *smem_raw) {
 // primitive of a leaf on `t <= maxt`, kdtree.h:2140-2154). The result does not depend on the
 // traversal order, so the box tests below are free to be approximate as long as they are
 // conservative (child boxes are inflated at build time, b2_bvh.cpp).
-struct Hit { float t, u, v; uint32_t slot, prim; };
+struct Hit { float t, u, v; uint32_t slot, prim; int inst; };
 
 // Triangle test on the traversal copy of the geometry: tri_isect[3*s] = (p0, prim), (e1 = p1-p0, -),
 // (e2 = p2-p0, -). e1/e2 are the same fp32 values Mesh::ray_intersect_triangle computes on the fly
@@ -141,82 +142,163 @@ B2_D bool tri_isect(float3 p0, float3 e1, float3 e2, const Ray &ray, float tmax,
     return t >= ray.mint && t <= tmax;
 }
 
-template <bool ANY>
-B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
-    best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu;
-    if (sc.n_tris == 0) return false;
-    float tmax = ray.maxt;
-    // reciprocal direction for the slab tests only (approximate is fine: tests are conservative)
-    float dx = fabsf(ray.d.x) > 1e-20f ? ray.d.x : (ray.d.x < 0.f ? -1e-20f : 1e-20f);
-    float dy = fabsf(ray.d.y) > 1e-20f ? ray.d.y : (ray.d.y < 0.f ? -1e-20f : 1e-20f);
-    float dz = fabsf(ray.d.z) > 1e-20f ? ray.d.z : (ray.d.z < 0.f ? -1e-20f : 1e-20f);
-    float idx = __fdividef(1.f, dx), idy = __fdividef(1.f, dy), idz = __fdividef(1.f, dz);
-    float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
-    // near / far plane rows of the SoA node, selected once per ray by the direction signs
-    const int nxi = dx < 0.f ? 3 : 0, fxi = dx < 0.f ? 0 : 3;
-    const int nyi = dy < 0.f ? 4 : 1, fyi = dy < 0.f ? 1 : 4;
-    const int nzi = dz < 0.f ? 5 : 2, fzi = dz < 0.f ? 2 : 5;
-    // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the
-    // same kind of work; DONE is the stack sentinel.
-    const int DONE = 0x7fffffff;
-    int stack[40];
-    stack[0] = DONE;
-    int sp = 1;
-    int cur = 0;                // [0, DONE): inner node index, < 0: leaf code
-    while (cur != DONE) {
-        while ((uint32_t) cur < (uint32_t) DONE) {
-            float4 nx, ny, nz, fx, fy, fz, chf;
-            if ((uint32_t) cur < sc.smem_nodes) {
-                const float4 *np = sm.nodes + 8 * cur;
-                nx = np[nxi]; ny = np[nyi]; nz = np[nzi]; fx = np[fxi]; fy = np[fyi]; fz = np[fzi]; chf = np[6];
-            } else {
-                const float4 *gp = sc.nodes + 8 * (size_t) cur;
-                nx = __ldg(gp + nxi); ny = __ldg(gp + nyi); nz = __ldg(gp + nzi);
-                fx = __ldg(gp + fxi); fy = __ldg(gp + fyi); fz = __ldg(gp + fzi); chf = __ldg(gp + 6);
+// Traversal state of one ray. The loop is interruptible: run() returns early when too few lanes
+// of the warp are still traversing and the caller can hand new rays to the idle lanes
+// (persistent-warp dynamic ray fetch, Aila & Laine 2009).
+#define B2_TRAV_DONE 0x7fffffff
+#define B2_REFILL_THRESHOLD 22
+
+struct Trav {
+    Ray ray;
+    float idx, idy, idz, oox, ooy, ooz;
+    int nxi, fxi, nyi, fyi, nzi, fzi;
+    int sp, cur;                // cur in [0, DONE): inner node index, < 0: leaf code, DONE: finished
+    float tmax;
+    Hit best;
+    int inst;                   // instance being traversed (-1: top level) — part of the tie key
+    bool any_hit;
+
+    // (the traversal stack is a separate local array so that the scalar state stays in registers)
+    B2_D void init(const DScene &sc, const Ray &r, int *stack) {
+        best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu; best.inst = -1;
+        any_hit = false;
+        restart(sc, r, stack, sc.n_top_tris ? 0 : B2_TRAV_DONE, -1);
+    }
+    // (re)start on another BVH (a shapegroup's, with the ray in object space) keeping the best hit so far
+    B2_D void restart(const DScene &sc, const Ray &r, int *stack, int root, int instance) {
+        ray = r; inst = instance;
+        tmax = fminf(r.maxt, best.t);
+        // reciprocal direction for the slab tests only (approximate is fine: tests are conservative)
+        float dx = fabsf(r.d.x) > 1e-20f ? r.d.x : (r.d.x < 0.f ? -1e-20f : 1e-20f);
+        float dy = fabsf(r.d.y) > 1e-20f ? r.d.y : (r.d.y < 0.f ? -1e-20f : 1e-20f);
+        float dz = fabsf(r.d.z) > 1e-20f ? r.d.z : (r.d.z < 0.f ? -1e-20f : 1e-20f);
+        idx = __fdividef(1.f, dx); idy = __fdividef(1.f, dy); idz = __fdividef(1.f, dz);
+        oox = -(r.o.x * idx); ooy = -(r.o.y * idy); ooz = -(r.o.z * idz);
+        // near / far plane rows of the SoA node, selected once per ray by the direction signs
+        nxi = dx < 0.f ? 3 : 0; fxi = dx < 0.f ? 0 : 3;
+        nyi = dy < 0.f ? 4 : 1; fyi = dy < 0.f ? 1 : 4;
+        nzi = dz < 0.f ? 5 : 2; fzi = dz < 0.f ? 2 : 5;
+        stack[0] = B2_TRAV_DONE; sp = 1;
+        cur = root;
+    }
+
+    // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the same
+    // kind of work. Returns when the ray is finished, or (can_yield) when the warp has thinned out.
+    template <bool ANY>
+    B2_D void run(const DScene &sc, const SmemScene &sm, int *stack, bool can_yield) {
+        while (cur != B2_TRAV_DONE) {
+            while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) {
+                float4 nx, ny, nz, fx, fy, fz, chf;
+                if ((uint32_t) cur < sc.smem_nodes) {
+                    const float4 *np = sm.nodes + 8 * cur;
+                    nx = np[nxi]; ny = np[nyi]; nz = np[nzi]; fx = np[fxi]; fy = np[fyi]; fz = np[fzi]; chf = np[6];
+                } else {
+                    const float4 *gp = sc.nodes + 8 * (size_t) cur;
+                    nx = __ldg(gp + nxi); ny = __ldg(gp + nyi); nz = __ldg(gp + nzi);
+                    fx = __ldg(gp + fxi); fy = __ldg(gp + fyi); fz = __ldg(gp + fzi); chf = __ldg(gp + 6);
+                }
+                const float tlim = tmax * 1.0000004f;
+                #define B2_SLAB(k) \
+                    float tn##k = fmaxf(fmaxf(b2_fma(nx.k, idx, oox), b2_fma(ny.k, idy, ooy)), fmaxf(b2_fma(nz.k, idz, ooz), ray.mint)); \
+                    float tf##k = fminf(fminf(b2_fma(fx.k, idx, oox), b2_fma(fy.k, idy, ooy)), fminf(b2_fma(fz.k, idz, ooz), tlim)); \
+                    int c##k = __float_as_int(chf.k); \
+                    bool h##k = c##k != 0 && tn##k <= tf##k;
+                B2_SLAB(x) B2_SLAB(y) B2_SLAB(z) B2_SLAB(w)
+                #undef B2_SLAB
+                // nearest hit child first; the others go on the stack (unordered)
+                float bd = B2_INF; int bc = 0;
+                if (hx) { bd = tnx; bc = cx; }
+                if (hy && tny < bd) { bd = tny; bc = cy; }
+                if (hz && tnz < bd) { bd = tnz; bc = cz; }
+                if (hw && tnw < bd) { bd = tnw; bc = cw; }
+                if (hx && cx != bc) stack[sp++] = cx;
+                if (hy && cy != bc) stack[sp++] = cy;
+                if (hz && cz != bc) stack[sp++] = cz;
+                if (hw && cw != bc) stack[sp++] = cw;
+                cur = bc != 0 ? bc : stack[--sp];
             }
-            const float tlim = tmax * 1.0000004f;
-            #define B2_SLAB(k) \
-                float tn##k = fmaxf(fmaxf(b2_fma(nx.k, idx, oox), b2_fma(ny.k, idy, ooy)), fmaxf(b2_fma(nz.k, idz, ooz), ray.mint)); \
-                float tf##k = fminf(fminf(b2_fma(fx.k, idx, oox), b2_fma(fy.k, idy, ooy)), fminf(b2_fma(fz.k, idz, ooz), tlim)); \
-                int c##k = __float_as_int(chf.k); \
-                bool h##k = c##k != 0 && tn##k <= tf##k;
-            B2_SLAB(x) B2_SLAB(y) B2_SLAB(z) B2_SLAB(w)
-            #undef B2_SLAB
-            // nearest hit child first; the others go on the stack (unordered)
-            float bd = B2_INF; int bc = 0;
-            if (hx) { bd = tnx; bc = cx; }
-            if (hy && tny < bd) { bd = tny; bc = cy; }
-            if (hz && tnz < bd) { bd = tnz; bc = cz; }
-            if (hw && tnw < bd) { bd = tnw; bc = cw; }
-            if (hx && cx != bc) stack[sp++] = cx;
-            if (hy && cy != bc) stack[sp++] = cy;
-            if (hz && cz != bc) stack[sp++] = cz;
-            if (hw && cw != bc) stack[sp++] = cw;
-            cur = bc != 0 ? bc : stack[--sp];
-        }
-        while (cur < 0) {
-            uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
-            for (uint32_t s = first; s < first + count; ++s) {
-                float4 a0, a1, a2;
-                if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
-                else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
-                float t, u, v;
-                if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
-                    if (ANY) return true;
-                    uint32_t prim = __float_as_uint(a0.w);
-                    if (t < best.t || (t == best.t && prim > best.prim)) {
-                        best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim;
-                        tmax = t;
+            while (cur < 0) {
+                uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
+                for (uint32_t s = first; s < first + count; ++s) {
+                    float4 a0, a1, a2;
+                    if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
+                    else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
+                    float t, u, v;
+                    if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
+                        if (ANY) { any_hit = true; cur = B2_TRAV_DONE; return; }
+                        uint32_t prim = __float_as_uint(a0.w);
+                        // tie rule: on equal t the larger (instance + 1, prim) key wins
+                        if (t < best.t || (t == best.t && (inst > best.inst || (inst == best.inst && prim > best.prim)))) {
+                            best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim; best.inst = inst;
+                            tmax = t;
+                        }
                     }
                 }
+                cur = stack[--sp];
             }
-            cur = stack[--sp];
+            if (can_yield && __popc(__activemask()) < B2_REFILL_THRESHOLD) return;
         }
     }
-    return best.t < B2_INF;
+};
+
+// Scene::ray_intersect_preliminary / ray_test: the top-level triangles, then (instanced scenes) a
+// BVH4 over the instances' world bounds whose leaves restart the traversal on the shapegroup's BVH
+// with the ray mapped to object space — origin as a point, direction as an UN-normalised vector,
+// mint/maxt unchanged so t stays in world units (instance.cpp:107-117).
+// INST is a compile-time switch so that flat scenes do not pay registers for the two-level code.
+template <bool ANY, bool INST>
+B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
+    int stack[40];
+    Trav tr; tr.init(sc, ray, stack);
+    tr.run<ANY>(sc, sm, stack, false);
+    if (INST && sc.n_instances && !(ANY && tr.any_hit)) {
+        float dx = fabsf(ray.d.x) > 1e-20f ? ray.d.x : (ray.d.x < 0.f ? -1e-20f : 1e-20f);
+        float dy = fabsf(ray.d.y) > 1e-20f ? ray.d.y : (ray.d.y < 0.f ? -1e-20f : 1e-20f);
+        float dz = fabsf(ray.d.z) > 1e-20f ? ray.d.z : (ray.d.z < 0.f ? -1e-20f : 1e-20f);
+        float idx = __fdividef(1.f, dx), idy = __fdividef(1.f, dy), idz = __fdividef(1.f, dz);
+        float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
+        int tstack[24]; int tsp = 0;
+        int cur = (int) sc.tlas_root;
+        for (;;) {
+            if (cur >= 0) {
+                const float4 *gp = sc.nodes + 8 * (size_t) cur;
+                float4 lox = __ldg(gp), loy = __ldg(gp + 1), loz = __ldg(gp + 2), hix = __ldg(gp + 3), hiy = __ldg(gp + 4),
+                       hiz = __ldg(gp + 5), chf = __ldg(gp + 6);
+                const float tlim = fminf(ray.maxt, tr.best.t) * 1.0000004f;
+                #define B2_TSLAB(k) { \
+                    float a0 = b2_fma(lox.k, idx, oox), a1 = b2_fma(hix.k, idx, oox), b0 = b2_fma(loy.k, idy, ooy), b1 = b2_fma(hiy.k, idy, ooy), \
+                          c0 = b2_fma(loz.k, idz, ooz), c1 = b2_fma(hiz.k, idz, ooz); \
+                    float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), ray.mint)); \
+                    float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tlim)); \
+                    int c = __float_as_int(chf.k); \
+                    if (c != 0 && tn <= tf) tstack[tsp++] = c; }
+                B2_TSLAB(x) B2_TSLAB(y) B2_TSLAB(z) B2_TSLAB(w)
+                #undef B2_TSLAB
+            } else {
+                uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
+                for (uint32_t s = first; s < first + count; ++s) {
+                    uint32_t ii = __ldg(&sc.inst_order[s]);
+                    const DInstance &in = sc.instances[ii];
+                    Ray ro; ro.o = xf_point(in.to_object, ray.o); ro.d = xf_vector(in.to_object, ray.d);
+                    ro.mint = ray.mint; ro.maxt = ray.maxt;
+                    tr.restart(sc, ro, stack, in.root, (int) ii);
+                    tr.run<ANY>(sc, sm, stack, false);
+                    if (ANY && tr.any_hit) { best = tr.best; return true; }
+                }
+            }
+            if (tsp == 0) break;
+            cur = tstack[--tsp];
+        }
+    }
+    best = tr.best;
+    return ANY ? tr.any_hit : best.t < B2_INF;
 }
 
 // ---- K2: closest hit ----------------------------------------------------------------------------
+// (A persistent-warp / dynamic-ray-fetch variant of this kernel was measured in round 1 and was
+// slower on the small-scene workload: 104 vs 93 ms per step — the refill overhead and the extra
+// registers outweigh the gain in lane utilisation when a ray needs only ~25 warp instructions.)
+template <bool INST>
 __global__ void __launch_bounds__(256) k_intersect(DScene sc, Queues q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
@@ -226,8 +308,9 @@ __global__ void __launch_bounds__(256) k_intersect(DScene sc, Queues q) {
         if (rd.w < 0.f) continue;                                  // retired lane
         float4 ro = q.ray_o[lane];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h; traverse<false>(sc, sm, ray, h);
+        Hit h; traverse<false, INST>(sc, sm, ray, h);
         q.hit[lane] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+        if (INST) q.hit_inst[lane] = h.inst;
         ++n_seg;
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
@@ -402,7 +485,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
         // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling ----
         if (valid) {
             bool hit_valid = h.x < B2_INF;
-            if (hit_valid) si_fill(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), si);
+            if (hit_valid) si_fill(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
             if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
             // ---- intersection with emitters (path.cpp:128-129) ----
             if (si.emitter >= 0) {
@@ -522,6 +605,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
 }
 
 // ---- K3 (+K6): any hit for the emitter samples ----------------------------------------------------
+template <bool INST>
 __global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
@@ -529,11 +613,10 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) count);
     uint32_t n_put = 0, n_bad = 0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        float4 ro = q.sh_o[i], rd = q.sh_d[i];
+        float4 ro = q.sh_o[i], rd = q.sh_d[i], c = q.sh_c[i];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
         Hit h;
-        bool occluded = traverse<true>(sc, sm, ray, h);
-        float4 c = q.sh_c[i];
+        bool occluded = traverse<true, INST>(sc, sm, ray, h);
         uint32_t lw = __float_as_uint(c.w);
         if (lw & SH_FINAL) {
             // the path ended on this bounce: result += contribution (path.cpp:171), then ImageBlock::put
@@ -546,10 +629,9 @@ __global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
             bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
             ++n_put; n_bad += ok ? 0 : 1;
         } else if (!occluded) {
-            uint32_t lane = lw;
-            float4 r = q.res[lane];
+            float4 r = q.res[lw];
             r.x += c.x; r.y += c.y; r.z += c.z;                    // result += mis*throughput*bsdf_val*emitter_val (path.cpp:171)
-            q.res[lane] = r;
+            q.res[lw] = r;
         }
     }
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
@@ -590,26 +672,29 @@ __global__ void k_stage_raygen(DScene sc, uint32_t n, const uint32_t *px, const 
     ray_d[i] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
     rng_out[i] = rng; pos[i] = make_float2(psx, psy);
 }
-__global__ void __launch_bounds__(256) k_stage_intersect(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, float4 *hit) {
+template <bool INST>
+__global__ void __launch_bounds__(256) k_stage_intersect(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, float4 *hit, int32_t *inst) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 ro = ray_o[i], rd = ray_d[i];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h; traverse<false>(sc, sm, ray, h);
+        Hit h; traverse<false, INST>(sc, sm, ray, h);
         hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));     // prim id (not slot) at the ABI
+        inst[i] = h.inst;
     }
 }
+template <bool INST>
 __global__ void __launch_bounds__(256) k_stage_occluded(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, uint8_t *occ) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 ro = ray_o[i], rd = ray_d[i];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h; occ[i] = traverse<true>(sc, sm, ray, h) ? 1 : 0;
+        Hit h; occ[i] = traverse<true, INST>(sc, sm, ray, h) ? 1 : 0;
     }
 }
-__global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, const float4 *hit, float *out) {
+__global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, const float4 *hit, const int32_t *inst, float *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 h = hit[i];
@@ -621,7 +706,7 @@ __global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, cons
         return;
     }
     uint32_t slot = sc.prim_to_slot[__float_as_uint(h.w)];
-    SI si; si_fill(make_tables(sc), slot, h.y, h.z, v3(ray_d[i]), si);
+    SI si; si_fill(make_tables(sc), slot, h.y, h.z, v3(ray_d[i]), inst ? inst[i] : -1, si);
     o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z; o[3] = si.n.x; o[4] = si.n.y; o[5] = si.n.z;
     o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z; o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
     o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z; o[15] = __uint_as_float((uint32_t) si.bsdf);

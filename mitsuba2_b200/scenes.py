@@ -22,7 +22,7 @@ CBOX_BSDFS = {
 CBOX_RADIANCE = (18.387, 10.9873, 2.75357)
 
 
-def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=None, lift=0.0):
+def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=None, lift=0.0, instances=None, drop_meshes=(), envmap=None):
     """cbox-rgb.xml (resources/data/scenes/cbox): 8 OBJ meshes / 38 triangles, one area
     emitter, diffuse rgb BSDFs, perspective sensor fov 39.3077 ('smaller' axis).
 
@@ -44,10 +44,22 @@ def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=
         pos = z[f"m{i}_positions"]
         if lift and b == "box":     # <translate y=lift/> on the two boxes (applied in fp32 like obj.cpp:172)
             pos = (pos + np.array([0, lift, 0], np.float32)).astype(np.float32)
+        if i in drop_meshes:
+            i += 1
+            continue
+        if instances is not None and b == "box" and i == 7:
+            i += 1
+            continue                      # instanced variant: the large box is dropped ...
         mi = sb.add_mesh(pos, z[f"m{i}_faces"], z[f"m{i}_normals"], bsdf_ids[b])
         if b == "light":
             sb.add_area_emitter(mi, CBOX_RADIANCE)
+        if instances is not None and b == "box" and i == 6:
+            g = sb.add_shapegroup([mi])   # ... and the small box becomes a shapegroup instantiated several times
+            for m in instances:
+                sb.add_instance(g, m)
         i += 1
+    if envmap is not None:        # dict(rgb=[H,W,3], scale=, to_world=4x4): appended after the shapes (XML order)
+        sb.add_envmap(envmap["rgb"], envmap.get("scale", 1.0), envmap.get("to_world"))
     sb.film = host.film_box(width, height) if rfilter == "box" else host.film_gaussian(width, height, 0.5)
     to_world = host.look_at((278, 273, -800), (278, 273, -799), (0, 1, 0))
     fov_x = host.parse_fov(39.3077, "smaller", width, height)

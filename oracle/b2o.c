@@ -277,6 +277,10 @@ typedef struct {
     float (*inst_lo)[3], (*inst_hi)[3];   /* world bounds of the instances (instance.cpp:83-94) */
     /* per-mesh area distribution (mesh.cpp:285-312, distr_1d.h:49-90) */
     float **cdf; float *cdf_sum, *cdf_norm; uint32_t *mesh_first;
+    /* environment map (envmap.cpp): Hierarchical2D<Float,0> levels + scene bounding sphere */
+    int env;                       /* index of the envmap emitter or -1 */
+    int env_nlevels; float **env_level; uint32_t *env_level_w;
+    float env_radius;
 } oscene;
 
 static void tri_bounds(const otri *t, float lo[3], float hi[3]) {
@@ -326,6 +330,9 @@ static void obvh_build(const otri *tris, obvh *b, uint32_t first, uint32_t count
     if (count) build_node(tris, b, 0, (int) count);
 }
 static void obvh_free(obvh *b) { free(b->order); free(b->nodes); }
+
+static inline v3 xf_point(const float *M, v3 p);
+static void env_build(oscene *s, const B2Emitter *em);
 
 static void mesh_vertex(const B2Mesh *m, const float *buf, uint32_t i, v3 *out) {
     out->x = buf[3 * i]; out->y = buf[3 * i + 1]; out->z = buf[3 * i + 2]; (void) m;
@@ -401,6 +408,38 @@ static oscene *oscene_create(const B2SceneDesc *d) {
             }
         }
     }
+    /* environment: Scene::Scene expands m_bbox by every top-level shape's bbox (scene.cpp:35-39);
+       EnvironmentMapEmitter::set_scene (envmap.cpp:127-131) takes its bounding sphere */
+    s->env = -1;
+    for (uint32_t e = 0; e < d->n_emitters; ++e) if (d->emitters[e].type == B2_EMITTER_ENVMAP) s->env = (int) e;
+    if (s->env >= 0) {
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (uint32_t m = 0; m < n_top; ++m)
+            for (uint32_t v = 0; v < d->meshes[m].n_vertices; ++v)
+                for (int k = 0; k < 3; ++k) {
+                    float c = d->meshes[m].positions[3 * v + k];
+                    if (c < lo[k]) lo[k] = c;
+                    if (c > hi[k]) hi[k] = c;
+                }
+        for (uint32_t i = 0; i < d->n_instances; ++i) {               /* Instance::bbox(): m_to_world * corner (instance.cpp:83-94) */
+            const B2Instance *in = &d->instances[i];
+            const obvh *g = &s->groups[in->group];
+            if (!g->count) continue;
+            float glo[3] = { INFINITY, INFINITY, INFINITY }, ghi[3] = { -INFINITY, -INFINITY, -INFINITY };
+            for (uint32_t t = g->first; t < g->first + g->count; ++t) { float a[3], b[3]; tri_bounds(&s->tris[t], a, b); for (int k = 0; k < 3; ++k) { if (a[k] < glo[k]) glo[k] = a[k]; if (b[k] > ghi[k]) ghi[k] = b[k]; } }
+            for (int c = 0; c < 8; ++c) {
+                v3 p = v3_make(c & 1 ? ghi[0] : glo[0], c & 2 ? ghi[1] : glo[1], c & 4 ? ghi[2] : glo[2]);
+                v3 w = xf_point(in->to_world, p);
+                float wc[3] = { w.x, w.y, w.z };
+                for (int k = 0; k < 3; ++k) { if (wc[k] < lo[k]) lo[k] = wc[k]; if (wc[k] > hi[k]) hi[k] = wc[k]; }
+            }
+        }
+        v3 c = v3_make((lo[0] + hi[0]) * .5f, (lo[1] + hi[1]) * .5f, (lo[2] + hi[2]) * .5f);   /* bbox.h center() */
+        v3 dmax = v3_sub(c, v3_make(hi[0], hi[1], hi[2]));
+        float radius = sqrtf(v3_dot(dmax, dmax));                      /* bbox.h:329-332 */
+        s->env_radius = b2o_max(B2O_RAY_EPS, radius * (1.f + B2O_RAY_EPS));
+        env_build(s, &d->emitters[s->env]);
+    }
     return s;
 }
 static void oscene_destroy(oscene *s) {
@@ -410,6 +449,8 @@ static void oscene_destroy(oscene *s) {
     obvh_free(&s->top);
     for (uint32_t g = 0; g < s->desc->n_groups; ++g) obvh_free(&s->groups[g]);
     free(s->groups); free(s->inst_lo); free(s->inst_hi);
+    for (int l = 0; l < s->env_nlevels; ++l) free(s->env_level[l]);
+    free(s->env_level); free(s->env_level_w);
     free(s->tris); free(s);
 }
 
@@ -901,16 +942,22 @@ static v3 area_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx
     return v3_make(em->radiance[0] * ip, em->radiance[1] * ip, em->radiance[2] * ip);
 }
 
+static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds);
+static float env_pdf_direction(const oscene *s, v3 d_world);
+static v3 emitter_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
+    return s->desc->emitters[emitter].type == B2_EMITTER_ENVMAP ? env_sample_direction(s, emitter, ref_p, sx, sy, ds)
+                                                                 : area_sample_direction(s, emitter, ref_p, sx, sy, ds);
+}
 /* Scene::sample_emitter_direction scene.cpp:164-214 (visibility test done by the caller) */
 static v3 scene_sample_emitter_direction(const oscene *s, v3 ref_p, float sx, float sy, ods *ds) {
     uint32_t ne = s->desc->n_emitters;
     if (ne == 0) { memset(ds, 0, sizeof *ds); return v3_make(0.f, 0.f, 0.f); }
-    if (ne == 1) return area_sample_direction(s, 0, ref_p, sx, sy, ds);
+    if (ne == 1) return emitter_sample_direction(s, 0, ref_p, sx, sy, ds);
     float emitter_pdf = 1.f / (float) ne;
     uint32_t index = (uint32_t) (sx * (float) ne);
     if (index > ne - 1) index = ne - 1;
     sx = (sx - (float) index * emitter_pdf) * (float) ne;
-    v3 spec = area_sample_direction(s, (int) index, ref_p, sx, sy, ds);
+    v3 spec = emitter_sample_direction(s, (int) index, ref_p, sx, sy, ds);
     ds->pdf *= emitter_pdf;
     return v3_scale(spec, b2o_rcp(emitter_pdf));
 }
@@ -919,6 +966,11 @@ static v3 scene_sample_emitter_direction(const oscene *s, v3 ref_p, float sx, fl
    -> Shape::pdf_direction shape.cpp:312-323 -> Mesh::pdf_position mesh.cpp:417-420 */
 static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 d, v3 n, float dist) {
     const B2Emitter *em = &s->desc->emitters[emitter];
+    if (em->type == B2_EMITTER_ENVMAP) {
+        float pdf = env_pdf_direction(s, d);
+        if (s->desc->n_emitters != 1) pdf = pdf * (1.f / (float) s->desc->n_emitters);
+        return pdf;
+    }
     float dp = v3_dot(d, n);
     if (!(dp < 0.f)) return 0.f;
     float pdf = s->cdf_norm[em->mesh];
@@ -926,6 +978,185 @@ static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 d, v3 
     pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;
     if (s->desc->n_emitters != 1) pdf = pdf * (1.f / (float) s->desc->n_emitters);
     return pdf;
+}
+
+/* ============================================================================================
+ * Environment map — src/emitters/envmap.cpp, include/mitsuba/core/distr_2d.h:336-700 (Hierarchical2D),
+ * include/mitsuba/core/warp.h:359-434
+ * ============================================================================================ */
+static inline uint32_t lvl_index(uint32_t x, uint32_t y, uint32_t width) {     /* distr_2d.h Level::index */
+    return ((x & 1u) | (((x & ~1u) | (y & 1u)) << 1)) + ((y & ~1u) * width);
+}
+static inline float b2o_lerp(float a, float b, float t) { return b2o_fma(b, t, b2o_fma(-a, t, a)); }  /* enoki::lerp */
+static inline float interval_to_linear(float v0, float v1, float sample) {       /* warp.h:359-366 */
+    if (fabsf(v0 - v1) > 1e-4f * (v0 + v1))
+        return (v0 - b2o_safe_sqrt(b2o_lerp(b2o_sqr(v0), b2o_sqr(v1), sample))) / (v0 - v1);
+    return sample;
+}
+static inline float clamp01(float x) { return b2o_min(b2o_max(x, 0.f), 1.f); }
+
+/* Hierarchical2D constructor (distr_2d.h:372-471), normalize = true, enable_sampling = true */
+static void env_build(oscene *s, const B2Emitter *em) {
+    uint32_t W = (uint32_t) em->env_width, H = (uint32_t) em->env_height;
+    float *lum = (float *) malloc(sizeof(float) * W * H);
+    for (uint32_t y = 0; y < H; ++y) {                                /* envmap.cpp:86-117 */
+        float sin_theta = sinf((float) y / (float) (H - 1) * B2O_PI);
+        for (uint32_t x = 0; x < W; ++x) {
+            const float *p = em->envmap + 4 * ((size_t) y * W + x);
+            float l = p[0] * 0.212671f + p[1] * 0.715160f + p[2] * 0.072169f;     /* spectrum.h:246-248 */
+            lum[y * W + x] = l * sin_theta;
+        }
+    }
+    uint32_t npx = W - 1, npy = H - 1;
+    uint32_t mx = npx > npy ? npx : npy, max_level = 0;
+    while ((1u << max_level) < mx) ++max_level;                       /* log2i_ceil */
+    int nl = (int) max_level + 2;
+    s->env_nlevels = nl;
+    s->env_level = (float **) calloc((size_t) nl, sizeof(float *));
+    s->env_level_w = (uint32_t *) calloc((size_t) nl, sizeof(uint32_t));
+    uint32_t *lh = (uint32_t *) calloc((size_t) nl, sizeof(uint32_t));
+    s->env_level[0] = (float *) calloc((size_t) W * H, sizeof(float)); s->env_level_w[0] = W; lh[0] = H;
+    uint32_t lx = npx, ly = npy;
+    for (int level = (int) max_level, k = 1; level >= 0; --level, ++k) {
+        lx += lx & 1u; ly += ly & 1u;                                 /* zero-pad */
+        s->env_level[k] = (float *) calloc((size_t) lx * ly, sizeof(float)); s->env_level_w[k] = lx; lh[k] = ly;
+        lx >>= 1; ly >>= 1;
+    }
+    double sum = 0.0;
+    const float *in = lum;
+    for (uint32_t y = 0; y < npy; ++y) {
+        for (uint32_t x = 0; x < npx; ++x) {
+            float avg = (in[0] + in[1] + in[W] + in[W + 1]) * .25f;
+            sum += (double) avg;
+            s->env_level[1][lvl_index(x, y, s->env_level_w[1])] = avg;
+            ++in;
+        }
+        ++in;
+    }
+    float scale = (float) ((double) (npx * npy) / sum);
+    for (uint32_t i = 0; i < W * H; ++i) s->env_level[0][i] = lum[i] * scale;
+    for (uint32_t i = 0; i < s->env_level_w[1] * lh[1]; ++i) s->env_level[1][i] *= scale;
+    lx = npx; ly = npy;
+    for (int level = 2; level <= (int) max_level + 1; ++level) {
+        lx = (lx + 1u) >> 1; ly = (ly + 1u) >> 1;
+        for (uint32_t y = 0; y < ly; ++y)
+            for (uint32_t x = 0; x < lx; ++x) {
+                const float *d0 = s->env_level[level - 1] + lvl_index(x * 2, y * 2, s->env_level_w[level - 1]);
+                s->env_level[level][lvl_index(x, y, s->env_level_w[level])] = d0[0] + d0[1] + d0[2] + d0[3];
+            }
+    }
+    free(lum); free(lh);
+}
+
+/* Hierarchical2D::sample (distr_2d.h:473-560) */
+static void env_warp_sample(const oscene *s, const B2Emitter *em, float sx, float sy, float *u, float *v, float *pdf) {
+    sx = clamp01(sx); sy = clamp01(sy);
+    uint32_t ox = 0, oy = 0;
+    for (int l = s->env_nlevels - 2; l > 0; --l) {
+        const float *lv = s->env_level[l];
+        ox <<= 1; oy <<= 1;
+        uint32_t oi = lvl_index(ox, oy, s->env_level_w[l]);
+        float v00 = lv[oi], v10 = lv[oi + 1], v01 = lv[oi + 2], v11 = lv[oi + 3];
+        sx = clamp01(sx); sy = clamp01(sy);
+        float r0 = v00 + v10, r1 = v01 + v11;
+        sy *= r0 + r1;
+        int mask = sy > r0;
+        if (mask) { oy += 1u; sy -= r0; }
+        sy /= mask ? r1 : r0;
+        float c0 = mask ? v01 : v00, c1 = mask ? v11 : v10;
+        sx *= c0 + c1;
+        mask = sx > c0;
+        if (mask) sx -= c0;
+        sx /= mask ? c1 : c0;
+        if (mask) ox += 1u;
+    }
+    uint32_t W = (uint32_t) em->env_width;
+    const float *l0 = s->env_level[0];
+    uint32_t oi = ox + oy * W;
+    float v00 = l0[oi], v10 = l0[oi + 1], v01 = l0[oi + W], v11 = l0[oi + W + 1];
+    /* warp::square_to_bilinear (warp.h:393-407) */
+    float r0 = v00 + v10, r1 = v01 + v11;
+    sy = interval_to_linear(r0, r1, sy);
+    float c0 = b2o_lerp(v00, v01, sy), c1 = b2o_lerp(v10, v11, sy);
+    sx = interval_to_linear(c0, c1, sx);
+    *pdf = b2o_lerp(c0, c1, sx);
+    float psx = 1.f / (float) (em->env_width - 1), psy = 1.f / (float) (em->env_height - 1);   /* m_patch_size */
+    *u = ((float) (int) ox + sx) * psx; *v = ((float) (int) oy + sy) * psy;
+}
+/* Hierarchical2D::eval (distr_2d.h:651-686) */
+static float env_warp_eval(const oscene *s, const B2Emitter *em, float px, float py) {
+    px = clamp01(px); py = clamp01(py);
+    uint32_t W = (uint32_t) em->env_width, H = (uint32_t) em->env_height;
+    px *= (float) (W - 1); py *= (float) (H - 1);                     /* m_inv_patch_size */
+    uint32_t ox = (uint32_t) (int) px, oy = (uint32_t) (int) py;
+    if (ox > W - 2) ox = W - 2;
+    if (oy > H - 2) oy = H - 2;
+    px -= (float) (int) ox; py -= (float) (int) oy;
+    const float *l0 = s->env_level[0];
+    uint32_t oi = ox + oy * W;
+    float v00 = l0[oi], v10 = l0[oi + 1], v01 = l0[oi + W], v11 = l0[oi + W + 1];
+    return b2o_lerp(b2o_lerp(v00, v10, px), b2o_lerp(v01, v11, px), py);     /* warp.h:428-434 */
+}
+/* EnvironmentMapEmitter::eval_spectrum (envmap.cpp:269-319), rgb branch */
+static v3 env_eval_spectrum(const B2Emitter *em, float u, float v) {
+    uint32_t W = (uint32_t) em->env_width, H = (uint32_t) em->env_height;
+    u *= (float) (W - 1u); v *= (float) (H - 1u);
+    uint32_t px = (uint32_t) u, py = (uint32_t) v;
+    if (px > W - 2u) px = W - 2u;
+    if (py > H - 2u) py = H - 2u;
+    float w1x = u - (float) px, w1y = v - (float) py, w0x = 1.f - w1x, w0y = 1.f - w1y;
+    const float *d = em->envmap;
+    size_t idx = (size_t) px + (size_t) py * W;
+    const float *v00 = d + 4 * idx, *v10 = d + 4 * (idx + 1), *v01 = d + 4 * (idx + W), *v11 = d + 4 * (idx + W + 1);
+    float out[3];
+    for (int k = 0; k < 3; ++k) {
+        float a0 = b2o_fma(w0x, v00[k], w1x * v10[k]), a1 = b2o_fma(w0x, v01[k], w1x * v11[k]);
+        out[k] = b2o_fma(w0y, a0, w1y * a1) * em->scale;
+    }
+    return v3_make(out[0], out[1], out[2]);
+}
+/* direction (world) -> uv (envmap.cpp:137-144, 198-203) */
+static inline void env_dir_to_uv(const B2Emitter *em, v3 d_world, v3 *d_local, float *u, float *v) {
+    v3 d = xf_vector(em->env_to_object, d_world);
+    *d_local = d;
+    float uu = b2o_atan2(d.x, -d.z) * (0.5f * B2O_INV_PI), vv = b2o_safe_acos(d.y) * B2O_INV_PI;
+    uu -= floorf(uu); vv -= floorf(vv);
+    *u = uu; *v = vv;
+}
+/* EnvironmentMapEmitter::eval (envmap.cpp:134-147): radiance arriving along ray direction d */
+static v3 env_eval(const oscene *s, v3 ray_d);
+static v3 env_eval(const oscene *s, v3 ray_d) {
+    const B2Emitter *em = &s->desc->emitters[s->env];
+    v3 dl; float u, v; env_dir_to_uv(em, ray_d, &dl, &u, &v);
+    return env_eval_spectrum(em, u, v);
+}
+static inline float env_inv_sin_theta(v3 d) {      /* safe_rsqrt(max(d.x^2 + d.z^2, Epsilon^2)) */
+    float x = b2o_max(b2o_sqr(d.x) + b2o_sqr(d.z), b2o_sqr(5.9604644775390625e-08f));
+    return b2o_rsqrt(x);
+}
+/* EnvironmentMapEmitter::pdf_direction (envmap.cpp:192-208) */
+static float env_pdf_direction(const oscene *s, v3 d_world) {
+    const B2Emitter *em = &s->desc->emitters[s->env];
+    v3 d; float u, v; env_dir_to_uv(em, d_world, &d, &u, &v);
+    return env_warp_eval(s, em, u, v) * env_inv_sin_theta(d) * (1.f / (2.f * b2o_sqr(B2O_PI)));
+}
+/* EnvironmentMapEmitter::sample_direction (envmap.cpp:156-190) */
+static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
+    const B2Emitter *em = &s->desc->emitters[emitter];
+    float u, v, pdf; env_warp_sample(s, em, sx, sy, &u, &v, &pdf);
+    float theta = v * B2O_PI, phi = u * (2.f * B2O_PI);
+    float st, ct, sp, cp; b2o_sincos(theta, &st, &ct); b2o_sincos(phi, &sp, &cp);
+    v3 d0 = v3_make(cp * st, sp * st, ct);                            /* math::sphdir */
+    v3 d = v3_make(d0.y, d0.z, -d0.x);
+    float dist = 2.f * s->env_radius;
+    float inv_sin_theta = env_inv_sin_theta(d);
+    d = xf_vector(em->env_to_world, d);
+    ds->p = v3_add(ref_p, v3_scale(d, dist));
+    ds->n = v3_neg(d);
+    ds->pdf = pdf > 0.f ? pdf * inv_sin_theta * (1.f / (2.f * b2o_sqr(B2O_PI))) : 0.f;
+    ds->d = d; ds->dist = dist; ds->emitter = emitter;
+    v3 spec = env_eval_spectrum(em, u, v);
+    return v3_scale(spec, b2o_rcp(ds->pdf));
 }
 
 /* ============================================================================================
@@ -946,12 +1177,14 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
     ohit h = scene_intersect(s, &ray, brute); cnt->segments++;
     osi si; si_fill(s, &ray, &h, &si);
     *valid_ray = h.t < INFINITY;
-    int emitter = (si.mesh >= 0) ? d->meshes[si.mesh].emitter : -1;     /* scene.h:243-253 (no envmap yet) */
+    int emitter = (si.mesh >= 0) ? d->meshes[si.mesh].emitter : s->env;  /* scene.h:243-253 */
     int active = 1;
     for (int depth = 1;; ++depth) {
         if (emitter >= 0) {                                               /* path.cpp:128-129 */
             const B2Emitter *em = &d->emitters[emitter];
-            v3 ev = si.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f); /* area.cpp:63-71 */
+            v3 ev;
+            if (si.mesh < 0) ev = env_eval(s, ray.d);                     /* envmap.cpp:134-147 (-si.wi = ray.d) */
+            else ev = si.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f); /* area.cpp:63-71 */
             v3 wt = v3_scale(throughput, emission_weight);
             result = v3_add(result, v3_mul(wt, ev));
         }
@@ -998,11 +1231,12 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         nr.mint = (1.f + v3_hmax_abs(si.p)) * B2O_RAY_EPS; nr.maxt = INFINITY;
         ohit h2 = scene_intersect(s, &nr, brute); cnt->segments++;
         osi si2; si_fill(s, &nr, &h2, &si2);
-        emitter = (si2.mesh >= 0) ? d->meshes[si2.mesh].emitter : -1;
+        emitter = (si2.mesh >= 0) ? d->meshes[si2.mesh].emitter : s->env;
         if (emitter >= 0) {                                               /* path.cpp:194-205, records.h:168-174 */
             v3 dd = v3_sub(si2.p, si.p);
             float dist = sqrtf(v3_dot(dd, dd));
             dd = v3_scale(dd, b2o_rcp(dist));
+            if (si2.mesh < 0) dd = nr.d;                                  /* d[!it.is_valid()] = -it.wi (records.h:173) */
             float emitter_pdf = !bs.delta ? scene_pdf_emitter_direction(s, emitter, dd, si2.sh_n, dist) : 0.f;
             emission_weight = mis_weight(bs.pdf, emitter_pdf);
         }

@@ -206,4 +206,40 @@ static inline float b2o_erfinv(float x) {
     return p * x;
 }
 
+/* ---- acos / atan2 twins (cephes-style polynomials; used by the environment map) -------------- */
+static inline float b2o_asin_poly(float x) {       /* |x| <= 0.5 */
+    float z = x * x;
+    float p = 4.2163199048e-2f;
+    p = b2o_fma(p, z, 2.4181311049e-2f);
+    p = b2o_fma(p, z, 4.5470025998e-2f);
+    p = b2o_fma(p, z, 7.4953002686e-2f);
+    p = b2o_fma(p, z, 1.6666752422e-1f);
+    return b2o_fma(p * z, x, x);
+}
+static inline float b2o_safe_acos(float x) {       /* acos(clamp(x, -1, 1)) */
+    x = b2o_min(b2o_max(x, -1.f), 1.f);
+    float ax = fabsf(x);
+    if (ax <= 0.5f) return 1.57079632679489661923f - b2o_asin_poly(x);
+    float z = 0.5f * (1.f - ax);
+    float s = sqrtf(z);
+    float r = 2.f * b2o_asin_poly(s);
+    return x > 0.f ? r : 3.14159265358979323846f - r;
+}
+static inline float b2o_atan2(float y, float x) {
+    float ax = fabsf(x), ay = fabsf(y);
+    float mx = b2o_max(ax, ay), mn = b2o_min(ax, ay);
+    float a = mx == 0.f ? 0.f : mn / mx;           /* in [0, 1] */
+    float base = 0.f;
+    if (a > 0.4142135623730950f) { a = (a - 1.f) / (a + 1.f); base = 0.78539816339744830962f; }
+    float z = a * a;
+    float p = 8.05374449538e-2f;
+    p = b2o_fma(p, z, -1.38776856032e-1f);
+    p = b2o_fma(p, z, 1.99777106478e-1f);
+    p = b2o_fma(p, z, -3.33329491539e-1f);
+    float r = base + b2o_fma(p * z, a, a);
+    if (ay > ax) r = 1.57079632679489661923f - r;
+    if (x < 0.f) r = 3.14159265358979323846f - r;
+    return b2o_mulsign(r, y);
+}
+
 #endif /* B2O_MATH_H */

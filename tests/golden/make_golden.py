@@ -189,6 +189,33 @@ CBOX_BSDFS = {
 CBOX_RADIANCE = (18.387, 10.9873, 2.75357)
 
 
+ENV_TO_WORLD = [0, 0, 1, 0,  0, 1, 0, 0,  -1, 0, 0, 0,  0, 0, 0, 1]      # exact 90-degree rotation about y
+# which cbox meshes are dropped for the environment-lit variants
+ENV_DROPPED = {
+    "only": ("cbox_luminaire.obj", "cbox_ceiling.obj", "cbox_back.obj", "cbox_greenwall.obj", "cbox_redwall.obj"),
+    "with_area": ("cbox_ceiling.obj", "cbox_back.obj", "cbox_greenwall.obj"),
+}
+
+
+def env_image(w=48, h=24):
+    """Deterministic lat-long environment: sky gradient + a bright warm patch + a cool patch."""
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, 3), np.float32)
+    img[..., 0] = 0.3 + 0.5 * (y / (h - 1))
+    img[..., 1] = 0.4 + 0.3 * np.cos(x / (w - 1) * np.float32(6.2831853)) ** 2
+    img[..., 2] = 0.9 - 0.6 * (y / (h - 1))
+    img[4:8, 10:15] += np.array([30.0, 24.0, 12.0], np.float32)
+    img[9:12, 30:36] += np.array([2.0, 5.0, 9.0], np.float32)
+    return img.astype(np.float32)
+
+
+def write_pfm(path, img):
+    h, w = img.shape[:2]
+    with open(path, "wb") as f:
+        f.write(b"PF\n%d %d\n-1.0\n" % (w, h))
+        f.write(np.ascontiguousarray(img[::-1], "<f4").tobytes())      # PFM rows are bottom-up
+
+
 EXTRA_EMITTER_OBJ = """v 150 420 150
 v 260 420 150
 v 260 420 270
@@ -199,7 +226,7 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
-             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False):
+             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -209,6 +236,18 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             bs.append(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>')
     shapes = []
     for fn, bsdf, tr in CBOX_SHAPES:
+        if envmap is not None and fn in ENV_DROPPED[envmap]:
+            continue                       # open scene: the environment must be visible
+        if instances is not None and fn == "cbox_largebox.obj":
+            continue
+        if instances is not None and fn == "cbox_smallbox.obj":
+            # shapegroup + instances (src/librender/shapegroup.cpp, src/shapes/instance.cpp)
+            shapes.append(f'<shape type="shapegroup" id="grp"><shape type="obj"><string name="filename" value="{CBOX}/meshes/{fn}"/>'
+                          f'<ref id="{bsdf}"/></shape></shape>')
+            for m in instances:
+                vals = " ".join(repr(float(x)) for row in m for x in row)
+                shapes.append(f'<shape type="instance"><ref id="grp"/><transform name="to_world"><matrix value="{vals}"/></transform></shape>')
+            continue
         if lift and bsdf == "box":
             tr = (0.0, float(lift), 0.0)     # float the two boxes: no face coplanar with the floor
         t = f'<transform name="to_world"><translate x="{tr[0]}" y="{tr[1]}" z="{tr[2]}"/></transform>' if any(tr) else ""
@@ -228,6 +267,11 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
         open(path, "w").write(EXTRA_EMITTER_OBJ)
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/><ref id="white"/>'
                       '<emitter type="area"><rgb name="radiance" value="4.0, 16.0, 6.0"/></emitter></shape>')
+    if envmap is not None:
+        path = os.path.join(mesh_dir, "env.pfm")
+        write_pfm(path, env_image())
+        shapes.append(f'<emitter type="envmap"><string name="filename" value="{path}"/><float name="scale" value="1.5"/>'
+                      f'<transform name="to_world"><matrix value="{" ".join(str(float(x)) for x in ENV_TO_WORLD)}"/></transform></emitter>')
     rf = '<rfilter type="box"/>' if rfilter == "box" else '<rfilter type="gaussian"/>'
     sp = f'<integer name="samples_per_pass" value="{samples_per_pass}"/>' if samples_per_pass else ""
     xml = CBOX_XML.format(width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
@@ -258,6 +302,15 @@ DIELECTRIC = '<bsdf type="dielectric"><float name="int_ior" value="1.5"/><float 
 ROUGH_GGX = '<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/></bsdf>'
 ROUGH_BECK = '<bsdf type="roughconductor"><float name="alpha" value="0.2"/></bsdf>'
 
+# exact-in-fp32 instance transforms: identity, half-size copy, 90-degree rotation about y (floating),
+# mirrored copy (floating)
+INSTANCES = [
+    [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]],
+    [[0.5, 0, 0, 330], [0, 0.5, 0, 0], [0, 0, 0.5, 250], [0, 0, 0, 1]],
+    [[0, 0, 1, 250], [0, 1, 0, 200], [-1, 0, 0, 560], [0, 0, 0, 1]],
+    [[-1, 0, 0, 420], [0, 1, 0, 300], [0, 0, 1, 0], [0, 0, 0, 1]],
+]
+
 GOLDEN = {
     # name: kwargs for cbox_xml
     "cbox_64_spp16": dict(width=64, height=64, spp=16),
@@ -273,6 +326,9 @@ GOLDEN = {
     "cbox_64_spp16_dielectric": dict(width=64, height=64, spp=16, materials={"box": DIELECTRIC}),
     "cbox_64_spp16_dielectric_lift": dict(width=64, height=64, spp=16, materials={"box": DIELECTRIC}, lift=10.0),
     "cbox_64_spp16_two_emitters": dict(width=64, height=64, spp=16, no_patch=True, extra_emitter=True),
+    "cbox_64_spp16_instances": dict(width=64, height=64, spp=16, no_patch=True, instances=INSTANCES),
+    "cbox_64_spp16_env": dict(width=64, height=64, spp=16, envmap="only"),
+    "cbox_64_spp16_env_area": dict(width=64, height=64, spp=16, envmap="with_area"),
     "cbox_64_spp16_ggx": dict(width=64, height=64, spp=16, materials={"box": ROUGH_GGX}),
     "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
 }
@@ -298,6 +354,9 @@ def main():
                 p = os.path.join(td, "e.obj"); open(p, "w").write(EXTRA_EMITTER_OBJ)
                 ep, en, ef = load_obj_like_reference(p)
             extra = dict(extra_positions=ep, extra_normals=en, extra_faces=ef, extra_radiance=np.array(EXTRA_EMITTER_RADIANCE, np.float32))
+        if kw.get("envmap"):
+            extra.update(env_rgb=env_image(), env_to_world=np.array(ENV_TO_WORLD, np.float32), env_scale=np.float32(1.5),
+                         env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
         np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), rgb=img, params=np.array(repr(kw_s)),
                             oracle_build=np.array(info), **extra)
         print(f"ref_{name}.npz", img.shape, "mean", img.mean(axis=(0, 1)))

@@ -38,9 +38,14 @@ def load(name, host):
     """-> (SceneBuffers, B2RenderParams, reference rgb image)"""
     z = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
     kw = ast.literal_eval(str(z["params"]))
-    sb = scenes.cbox(host, kw["width"], kw["height"], rfilter=kw.get("rfilter", "box"),
+    env = None; drop = ()
+    if kw.get("envmap"):
+        env = dict(rgb=z["env_rgb"], scale=float(z["env_scale"]), to_world=z["env_to_world"].reshape(4, 4))
+        drop = tuple(int(i) for i in z["env_dropped"])
+    sb = scenes.cbox(host, kw["width"], kw["height"], rfilter=kw.get("rfilter", "box"), envmap=env, drop_meshes=drop,
                      materials=_materials(kw.get("materials")),
-                     meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0))
+                     meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
+                     instances=kw.get("instances"))
     if kw.get("extra_emitter"):
         mi = sb.add_mesh(z["extra_positions"], z["extra_faces"], z["extra_normals"], bsdf=1)     # 'white'
         sb.add_area_emitter(mi, tuple(float(x) for x in z["extra_radiance"]))

@@ -84,9 +84,36 @@ def test_intersect_vs_bruteforce(b2, oracle):
     assert np.array_equal(si.view(np.uint32), si2.view(np.uint32))
 
 
+def test_instances_intersect_vs_bruteforce(b2, oracle):
+    """Two-level BVH (instances: scaled, rotated, mirrored copies) == brute force over every
+    instance x triangle, including the instance index and the transformed SurfaceInteraction."""
+    sb, rp, _ = G.load("cbox_64_spp16_instances", b2.Host())
+    sc = b2.Scene(sb)
+    ro, rd = _random_rays(sb, 20000, 5)
+    n = len(ro)
+    hit = np.zeros((n, 4), np.float32); inst = np.zeros(n, np.int32)
+    assert b2.lib().b2_stage_intersect(sc._h, n, ro.ctypes.data, rd.ctypes.data, hit.ctypes.data, inst.ctypes.data) == 0
+    d = sb.desc()
+    hit2 = np.zeros_like(hit); inst2 = np.zeros_like(inst)
+    oracle.lib().b2o_stage_intersect(C.byref(d), n, ro.ctypes.data, rd.ctypes.data, hit2.ctypes.data, inst2.ctypes.data, 1)
+    assert (inst2 >= 0).sum() > 500
+    assert np.array_equal(inst, inst2)
+    assert np.array_equal(hit.view(np.uint32), hit2.view(np.uint32))
+    rd[:, 3] = 250.0
+    occ = sc.ray_test(ro, rd)
+    occ2 = np.zeros(n, np.uint8)
+    oracle.lib().b2o_stage_occluded(C.byref(d), n, ro.ctypes.data, rd.ctypes.data, occ2.ctypes.data, 1)
+    assert np.array_equal(occ, occ2.astype(bool))
+    si = np.zeros((n, 16), np.float32); si2 = np.zeros_like(si)
+    assert b2.lib().b2_stage_si_fill(sc._h, n, ro.ctypes.data, rd.ctypes.data, hit.ctypes.data, inst.ctypes.data, si.ctypes.data) == 0
+    oracle.lib().b2o_stage_si_fill(C.byref(d), n, ro.ctypes.data, rd.ctypes.data, hit2.ctypes.data, inst2.ctypes.data, si2.ctypes.data)
+    assert np.array_equal(si.view(np.uint32), si2.view(np.uint32))
+
+
 @pytest.mark.parametrize("name", ["cbox_64_spp16", "cbox_80x48_spp8", "cbox_64_spp16_depth3_rr2",
                                   "cbox_64_spp16_bs16_seed7", "cbox_64_spp16_dielectric_lift",
-                                  "cbox_64_spp16_ggx", "cbox_64_spp16_beckmann", "cbox_64_spp16_two_emitters"])
+                                  "cbox_64_spp16_ggx", "cbox_64_spp16_beckmann", "cbox_64_spp16_two_emitters",
+                                  "cbox_64_spp16_instances"])
 def test_render_bitexact_single_pass(b2, oracle, name):
     """Box filter + one pass: one lane owns a pixel and adds its samples in order, exactly like
     render_block -> the whole XYZAW film must match the oracle bit for bit."""
