@@ -57,6 +57,8 @@ struct B2Scene {
     DScene d{};
     DBuf<float4> nodes, tri_isect;
     DBuf<DInstance> instances;
+    DBuf<float4> env_data;
+    DBuf<float> env_levels;
     DBuf<uint32_t> inst_order;
     DBuf<int32_t> hit_inst;
     DBuf<unsigned char> blob;       // tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
@@ -109,7 +111,17 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     for (uint32_t m = n_top_meshes; m < desc->n_meshes; ++m)
         if (desc->meshes[m].emitter >= 0) return fail(B2_ERR_INVALID, "Instancing of emitters is not supported");   // shapegroup.cpp:24-25
     for (uint32_t e = 0; e < desc->n_emitters; ++e)
-        if (desc->emitters[e].type != B2_EMITTER_AREA) return fail(B2_ERR_INVALID, "emitter %u: only area emitters are supported", e);
+        if (desc->emitters[e].type != B2_EMITTER_AREA && desc->emitters[e].type != B2_EMITTER_ENVMAP)
+            return fail(B2_ERR_INVALID, "emitter %u: only area and envmap emitters are supported", e);
+    {
+        int n_env = 0;
+        for (uint32_t e = 0; e < desc->n_emitters; ++e) {
+            const B2Emitter &em = desc->emitters[e];
+            if (em.type != B2_EMITTER_ENVMAP) continue;
+            if (++n_env > 1) return fail(B2_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:48-49
+            if (!em.envmap || em.env_width < 2 || em.env_height < 2) return fail(B2_ERR_INVALID, "Distribution2D(): input array resolution must be >= 2!");
+        }
+    }
     for (uint32_t m = 0; m < desc->n_meshes; ++m) {
         const B2Mesh &me = desc->meshes[m];
         if (me.bsdf < 0 || (uint32_t) me.bsdf >= desc->n_bsdfs) return fail(B2_ERR_INVALID, "mesh %u: bad bsdf index", m);
@@ -225,6 +237,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     std::vector<float> cdf;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &src = desc->emitters[e];
+        if (src.type == B2_EMITTER_ENVMAP) { std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; continue; }
         if (src.mesh < 0 || (uint32_t) src.mesh >= desc->n_meshes) { delete s; return fail(B2_ERR_INVALID, "emitter %u: bad mesh index", e); }
         const B2Mesh &me = desc->meshes[src.mesh];
         if (me.n_faces == 0) { delete s; return fail(B2_ERR_INVALID, "Cannot create sampling table for an empty mesh"); }
@@ -281,6 +294,86 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
     d.instances = desc->n_instances ? s->instances.p : nullptr; d.inst_order = s->inst_order.p;
     d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_tris;
+    // environment map: Hierarchical2D levels (distr_2d.h:372-471) + scene bounding sphere (envmap.cpp:127-131)
+    d.env.index = -1;
+    for (uint32_t e = 0; e < desc->n_emitters; ++e) {
+        const B2Emitter &em = desc->emitters[e];
+        if (em.type != B2_EMITTER_ENVMAP) continue;
+        uint32_t W = (uint32_t) em.env_width, H = (uint32_t) em.env_height;
+        std::vector<float> lum((size_t) W * H);
+        for (uint32_t y = 0; y < H; ++y) {                            // envmap.cpp:86-117
+            float sin_theta = std::sin((float) y / (float) (H - 1) * 3.14159265358979323846f);
+            for (uint32_t x = 0; x < W; ++x) {
+                const float *p = em.envmap + 4 * ((size_t) y * W + x);
+                float l = p[0] * 0.212671f + p[1] * 0.715160f + p[2] * 0.072169f;
+                lum[(size_t) y * W + x] = l * sin_theta;
+            }
+        }
+        auto lvl_index = [](uint32_t x, uint32_t y, uint32_t width) { return ((x & 1u) | (((x & ~1u) | (y & 1u)) << 1)) + ((y & ~1u) * width); };
+        uint32_t npx = W - 1, npy = H - 1, mx = std::max(npx, npy), max_level = 0;
+        while ((1u << max_level) < mx) ++max_level;
+        int nl = (int) max_level + 2;
+        if (nl > 16) { delete s; return fail(B2_ERR_INVALID, "environment map too large"); }
+        std::vector<uint32_t> lw(nl), lh(nl), loff(nl);
+        lw[0] = W; lh[0] = H;
+        { uint32_t lx = npx, ly = npy; for (int level = (int) max_level, k = 1; level >= 0; --level, ++k) { lx += lx & 1u; ly += ly & 1u; lw[k] = lx; lh[k] = ly; lx >>= 1; ly >>= 1; } }
+        size_t total = 0;
+        for (int k = 0; k < nl; ++k) { loff[k] = (uint32_t) total; total += ((size_t) lw[k] * lh[k] + 3) & ~(size_t) 3; }   // keep 16-byte alignment
+        std::vector<float> lv(total, 0.f);
+        double sum = 0.0;
+        const float *in = lum.data();
+        for (uint32_t y = 0; y < npy; ++y) {
+            for (uint32_t x = 0; x < npx; ++x) {
+                float avg = (in[0] + in[1] + in[W] + in[W + 1]) * .25f;
+                sum += (double) avg;
+                lv[loff[1] + lvl_index(x, y, lw[1])] = avg;
+                ++in;
+            }
+            ++in;
+        }
+        float scale = (float) ((double) (npx * npy) / sum);
+        for (size_t i = 0; i < (size_t) W * H; ++i) lv[loff[0] + i] = lum[i] * scale;
+        for (size_t i = 0; i < (size_t) lw[1] * lh[1]; ++i) lv[loff[1] + i] *= scale;
+        { uint32_t lx = npx, ly = npy;
+          for (int level = 2; level <= (int) max_level + 1; ++level) {
+              lx = (lx + 1u) >> 1; ly = (ly + 1u) >> 1;
+              for (uint32_t y = 0; y < ly; ++y) for (uint32_t x = 0; x < lx; ++x) {
+                  const float *d0 = &lv[loff[level - 1] + lvl_index(x * 2, y * 2, lw[level - 1])];
+                  lv[loff[level] + lvl_index(x, y, lw[level])] = d0[0] + d0[1] + d0[2] + d0[3];
+              }
+          } }
+        std::vector<float4> texels((size_t) W * H);
+        std::memcpy(texels.data(), em.envmap, (size_t) W * H * 16);
+        if (s->env_data.upload(texels) != cudaSuccess || s->env_levels.upload(lv) != cudaSuccess) { delete s; return fail(B2_ERR_CUDA, "envmap upload failed"); }
+        DEnv &v = d.env;
+        v.data = s->env_data.p; v.levels = s->env_levels.p; v.index = (int32_t) e; v.width = (int32_t) W; v.height = (int32_t) H; v.n_levels = nl;
+        for (int k = 0; k < nl; ++k) { v.level_off[k] = loff[k]; v.level_w[k] = lw[k]; }
+        v.scale = em.scale;
+        std::memcpy(v.to_world, em.env_to_world, 48); std::memcpy(v.to_object, em.env_to_object, 48);
+        // scene bbox = union of the top-level shapes' boxes (scene.cpp:35-39); instances: to_world * corner (instance.cpp:83-94)
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (uint32_t m = 0; m < n_top_meshes; ++m)
+            for (uint32_t vtx = 0; vtx < desc->meshes[m].n_vertices; ++vtx)
+                for (int k = 0; k < 3; ++k) { float c = desc->meshes[m].positions[3 * (size_t) vtx + k]; lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c); }
+        for (uint32_t i = 0; i < desc->n_instances; ++i) {
+            const B2Instance &in2 = desc->instances[i];
+            const B2BvhBox &gb = group_box[in2.group];
+            if (!(gb.lo[0] <= gb.hi[0])) continue;
+            for (int c = 0; c < 8; ++c) {
+                float p[3] = { c & 1 ? gb.hi[0] : gb.lo[0], c & 2 ? gb.hi[1] : gb.lo[1], c & 4 ? gb.hi[2] : gb.lo[2] };
+                for (int r = 0; r < 3; ++r) {
+                    const float *M = in2.to_world + 4 * r;
+                    float w = std::fma(M[2], p[2], std::fma(M[1], p[1], std::fma(M[0], p[0], M[3])));
+                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
+                }
+            }
+        }
+        float c[3] = { (lo[0] + hi[0]) * .5f, (lo[1] + hi[1]) * .5f, (lo[2] + hi[2]) * .5f };
+        float dd[3] = { c[0] - hi[0], c[1] - hi[1], c[2] - hi[2] };
+        float radius = std::sqrt((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]);     // bbox.h:329-332
+        const float ray_eps = 1500.0f * 5.9604644775390625e-08f;
+        v.radius = std::max(ray_eps, radius * (1.f + ray_eps));
+    }
     d.n_nodes = bvh.n_nodes; d.n_tris = nt; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
     d.sensor = desc->sensor; d.film = desc->film;
     // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
@@ -407,9 +500,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         return (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (s->sm_count * std::max(per_sm, 1)), need_blocks));
     };
     int grid = resident(k_init, 0);
-    int grid_int = inst ? resident(k_intersect<true>, s->smem_bytes) : resident(k_intersect<false>, s->smem_bytes);
-    int grid_sha = resident(k_shade, s->shade_smem_bytes);
-    int grid_shw = inst ? resident(k_shadow<true>, s->smem_bytes) : resident(k_shadow<false>, s->smem_bytes);
+    int grid_int = s->sm_count * 8, grid_sha = s->sm_count * 8, grid_shw = s->sm_count * 8;   // measured: 8 CTAs/SM queued beats exactly-resident grids
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;

@@ -31,6 +31,18 @@ struct DEmitter {
     uint32_t valid_first, valid_last;
 };
 
+// environment map (src/emitters/envmap.cpp): RGBA texels + the Hierarchical2D<Float,0> MIP levels
+// (include/mitsuba/core/distr_2d.h:372-471) concatenated in one buffer
+struct DEnv {
+    const float4 *data;         // height x width RGBA
+    const float *levels;        // level 0 (normalised luminance*sin(theta)), level 1 (patch averages), ... coarsest
+    int32_t index;              // index of the envmap in the emitter list, -1: no environment
+    int32_t width, height, n_levels;
+    uint32_t level_off[16], level_w[16];
+    float scale, radius;        // 'scale'; bounding-sphere radius of the scene (envmap.cpp:127-131)
+    float to_world[12], to_object[12];
+};
+
 // one-level instancing (src/shapes/instance.cpp): affine 3x4 transforms, row-major
 struct DInstance {
     float to_world[12];
@@ -59,6 +71,7 @@ struct DScene {
     uint32_t shade_smem;        // 1: k_shade stages the whole blob into shared memory
     B2Sensor sensor;
     B2Film film;
+    DEnv env;
 };
 
 // The shading tables as seen by one kernel: pointers into global memory or into the CTA's
@@ -411,20 +424,131 @@ B2_D float3 area_sample_direction(const Tables &sc, const DEmitter &em, float3 r
     return v3(em.radiance[0] * ip, em.radiance[1] * ip, em.radiance[2] * ip);
 }
 
-B2_D float3 scene_sample_emitter_direction(const Tables &sc, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
+// ---- environment map (src/emitters/envmap.cpp, distr_2d.h:473-686, warp.h:359-434) ----------------
+B2_D uint32_t lvl_index(uint32_t x, uint32_t y, uint32_t width) {            // distr_2d.h Level::index
+    return ((x & 1u) | (((x & ~1u) | (y & 1u)) << 1)) + ((y & ~1u) * width);
+}
+B2_D float b2_lerp(float a, float b, float t) { return b2_fma(b, t, b2_fma(-a, t, a)); }   // enoki::lerp
+B2_D float interval_to_linear(float v0, float v1, float sample) {            // warp.h:359-366
+    if (fabsf(v0 - v1) > 1e-4f * (v0 + v1))
+        return (v0 - b2_safe_sqrt(b2_lerp(b2_sqr(v0), b2_sqr(v1), sample))) / (v0 - v1);
+    return sample;
+}
+B2_D float clamp01(float x) { return b2_min(b2_max(x, 0.f), 1.f); }
+
+B2_D void env_warp_sample(const DEnv &env, float sx, float sy, float &u, float &v, float &pdf) {   // distr_2d.h:473-560
+    sx = clamp01(sx); sy = clamp01(sy);
+    uint32_t ox = 0, oy = 0;
+    for (int l = env.n_levels - 2; l > 0; --l) {
+        const float *lv = env.levels + env.level_off[l];
+        ox <<= 1; oy <<= 1;
+        uint32_t oi = lvl_index(ox, oy, env.level_w[l]);
+        float4 q = __ldg((const float4 *) (lv + oi));              // 2x2 patches are contiguous and 16-byte aligned
+        float v00 = q.x, v10 = q.y, v01 = q.z, v11 = q.w;
+        sx = clamp01(sx); sy = clamp01(sy);
+        float r0 = v00 + v10, r1 = v01 + v11;
+        sy *= r0 + r1;
+        bool mask = sy > r0;
+        if (mask) { oy += 1u; sy -= r0; }
+        sy /= mask ? r1 : r0;
+        float c0 = mask ? v01 : v00, c1 = mask ? v11 : v10;
+        sx *= c0 + c1;
+        mask = sx > c0;
+        if (mask) sx -= c0;
+        sx /= mask ? c1 : c0;
+        if (mask) ox += 1u;
+    }
+    uint32_t W = (uint32_t) env.width;
+    const float *l0 = env.levels;
+    uint32_t oi = ox + oy * W;
+    float v00 = __ldg(l0 + oi), v10 = __ldg(l0 + oi + 1), v01 = __ldg(l0 + oi + W), v11 = __ldg(l0 + oi + W + 1);
+    float r0 = v00 + v10, r1 = v01 + v11;                           // warp::square_to_bilinear, warp.h:393-407
+    sy = interval_to_linear(r0, r1, sy);
+    float c0 = b2_lerp(v00, v01, sy), c1 = b2_lerp(v10, v11, sy);
+    sx = interval_to_linear(c0, c1, sx);
+    pdf = b2_lerp(c0, c1, sx);
+    float psx = 1.f / (float) (env.width - 1), psy = 1.f / (float) (env.height - 1);
+    u = ((float) (int) ox + sx) * psx; v = ((float) (int) oy + sy) * psy;
+}
+B2_D float env_warp_eval(const DEnv &env, float px, float py) {               // distr_2d.h:651-686
+    px = clamp01(px); py = clamp01(py);
+    uint32_t W = (uint32_t) env.width, H = (uint32_t) env.height;
+    px *= (float) (W - 1); py *= (float) (H - 1);
+    uint32_t ox = (uint32_t) (int) px, oy = (uint32_t) (int) py;
+    if (ox > W - 2) ox = W - 2;
+    if (oy > H - 2) oy = H - 2;
+    px -= (float) (int) ox; py -= (float) (int) oy;
+    const float *l0 = env.levels;
+    uint32_t oi = ox + oy * W;
+    float v00 = __ldg(l0 + oi), v10 = __ldg(l0 + oi + 1), v01 = __ldg(l0 + oi + W), v11 = __ldg(l0 + oi + W + 1);
+    return b2_lerp(b2_lerp(v00, v10, px), b2_lerp(v01, v11, px), py);        // warp.h:428-434
+}
+B2_D float3 env_eval_spectrum(const DEnv &env, float u, float v) {            // envmap.cpp:269-319 (rgb branch)
+    uint32_t W = (uint32_t) env.width, H = (uint32_t) env.height;
+    u *= (float) (W - 1u); v *= (float) (H - 1u);
+    uint32_t px = (uint32_t) u, py = (uint32_t) v;
+    if (px > W - 2u) px = W - 2u;
+    if (py > H - 2u) py = H - 2u;
+    float w1x = u - (float) px, w1y = v - (float) py, w0x = 1.f - w1x, w0y = 1.f - w1y;
+    size_t idx = (size_t) px + (size_t) py * W;
+    float4 v00 = __ldg(env.data + idx), v10 = __ldg(env.data + idx + 1), v01 = __ldg(env.data + idx + W), v11 = __ldg(env.data + idx + W + 1);
+    float3 a0 = v3(b2_fma(w0x, v00.x, w1x * v10.x), b2_fma(w0x, v00.y, w1x * v10.y), b2_fma(w0x, v00.z, w1x * v10.z));
+    float3 a1 = v3(b2_fma(w0x, v01.x, w1x * v11.x), b2_fma(w0x, v01.y, w1x * v11.y), b2_fma(w0x, v01.z, w1x * v11.z));
+    return v3(b2_fma(w0y, a0.x, w1y * a1.x) * env.scale, b2_fma(w0y, a0.y, w1y * a1.y) * env.scale, b2_fma(w0y, a0.z, w1y * a1.z) * env.scale);
+}
+B2_D void env_dir_to_uv(const DEnv &env, float3 d_world, float3 &d, float &u, float &v) {   // envmap.cpp:137-144
+    d = xf_vector(env.to_object, d_world);
+    u = b2_atan2(d.x, -d.z) * (0.5f * B2_INV_PI); v = b2_safe_acos(d.y) * B2_INV_PI;
+    u -= floorf(u); v -= floorf(v);
+}
+B2_D float3 env_eval(const DEnv &env, float3 ray_d) {                         // envmap.cpp:134-147
+    float3 d; float u, v; env_dir_to_uv(env, ray_d, d, u, v);
+    return env_eval_spectrum(env, u, v);
+}
+B2_D float env_inv_sin_theta(float3 d) { return b2_rsqrt(b2_max(b2_sqr(d.x) + b2_sqr(d.z), b2_sqr(B2_EPS))); }
+B2_D float env_pdf_direction(const DEnv &env, float3 d_world) {               // envmap.cpp:192-208
+    float3 d; float u, v; env_dir_to_uv(env, d_world, d, u, v);
+    return env_warp_eval(env, u, v) * env_inv_sin_theta(d) * (1.f / (2.f * b2_sqr(B2_PI)));
+}
+B2_D float3 env_sample_direction(const DEnv &env, float3 ref_p, float sx, float sy, DS &ds) {   // envmap.cpp:156-190
+    float u, v, pdf; env_warp_sample(env, sx, sy, u, v, pdf);
+    float theta = v * B2_PI, phi = u * (2.f * B2_PI);
+    float st, ct, sp, cp; b2_sincos(theta, &st, &ct); b2_sincos(phi, &sp, &cp);
+    float3 d0 = v3(cp * st, sp * st, ct);                            // math::sphdir
+    float3 d = v3(d0.y, d0.z, -d0.x);
+    float dist = 2.f * env.radius;
+    float inv_sin_theta = env_inv_sin_theta(d);
+    d = xf_vector(env.to_world, d);
+    ds.p = ref_p + d * dist; ds.n = -d;
+    ds.pdf = pdf > 0.f ? pdf * inv_sin_theta * (1.f / (2.f * b2_sqr(B2_PI))) : 0.f;
+    ds.d = d; ds.dist = dist;
+    return env_eval_spectrum(env, u, v) * b2_rcp(ds.pdf);
+}
+
+B2_D float3 emitter_sample_direction(const Tables &sc, const DEnv &env, uint32_t e, float3 ref_p, float sx, float sy, DS &ds) {
+    if ((int) e == env.index) return env_sample_direction(env, ref_p, sx, sy, ds);
+    return area_sample_direction(sc, sc.emitters[e], ref_p, sx, sy, ds);
+}
+
+B2_D float3 scene_sample_emitter_direction(const Tables &sc, const DEnv &env, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
     uint32_t ne = sc.n_emitters;
     if (ne == 0) { ds.pdf = 0.f; ds.dist = 0.f; ds.p = ds.n = ds.d = v3(0.f, 0.f, 0.f); return v3(0.f, 0.f, 0.f); }
-    if (ne == 1) return area_sample_direction(sc, sc.emitters[0], ref_p, sx, sy, ds);
+    if (ne == 1) return emitter_sample_direction(sc, env, 0, ref_p, sx, sy, ds);
     float emitter_pdf = 1.f / (float) ne;
     uint32_t index = (uint32_t) (sx * (float) ne);
     if (index > ne - 1) index = ne - 1;
     sx = (sx - (float) index * emitter_pdf) * (float) ne;
-    float3 spec = area_sample_direction(sc, sc.emitters[index], ref_p, sx, sy, ds);
+    float3 spec = emitter_sample_direction(sc, env, index, ref_p, sx, sy, ds);
     ds.pdf *= emitter_pdf;
     return spec * b2_rcp(emitter_pdf);
 }
 
-B2_D float scene_pdf_emitter_direction(const Tables &sc, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
+B2_D float scene_pdf_emitter_direction(const Tables &sc, const DEnv &env, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
+    if (emitter == env.index) {
+        float pdf = env_pdf_direction(env, d);
+        if (sc.n_emitters != 1) pdf = pdf * (1.f / (float) sc.n_emitters);
+        return pdf;
+    }
     const DEmitter &em = sc.emitters[emitter];
     float dp = dot(d, n);
     if (!(dp < 0.f)) return 0.f;                                   // area.cpp:170-171

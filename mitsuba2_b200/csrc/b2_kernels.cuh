@@ -481,11 +481,12 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
         int depth = (int) STW_DEPTH(st.w);
         float3 throughput = v3(tpe), result = v3(rs);
         float eta = tpe.w, bs_pdf = rs.w;
-        SI si; si.emitter = -1; si.bsdf = 0;
+        SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
         // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling ----
         if (valid) {
             bool hit_valid = h.x < B2_INF;
             if (hit_valid) si_fill(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
+            else si.emitter = sc.env.index;                                         // scene->environment(), scene.h:243-253
             if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
             // ---- intersection with emitters (path.cpp:128-129) ----
             if (si.emitter >= 0) {
@@ -496,12 +497,17 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
                         float3 dd = si.p - v3(ro);
                         float dist = sqrtf(dot(dd, dd));
                         dd = dd * b2_rcp(dist);
-                        emitter_pdf = scene_pdf_emitter_direction(tb, si.emitter, dd, si.sh_n, dist);
+                        if (!hit_valid) dd = v3(rd);                                // d[!it.is_valid()] = -it.wi
+                        emitter_pdf = scene_pdf_emitter_direction(tb, sc.env, si.emitter, dd, si.sh_n, dist);
                     }
                     emission_weight = mis_weight(bs_pdf, emitter_pdf);
                 }
-                const DEmitter &em = tb.emitters[si.emitter];
-                float3 ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
+                float3 ev;
+                if (!hit_valid) ev = env_eval(sc.env, v3(rd));                      // envmap.cpp:134-147
+                else {
+                    const DEmitter &em = tb.emitters[si.emitter];
+                    ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
+                }
                 result = result + (throughput * emission_weight) * ev;
             }
             bool active = hit_valid;                                                // path.cpp:131
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
                 const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
                 if (bsdf_is_smooth(bsdf)) {                                         // path.cpp:153-172
                     float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
-                    DS ds; float3 emitter_val = scene_sample_emitter_direction(tb, si.p, sx, sy, ds);
+                    DS ds; float3 emitter_val = scene_sample_emitter_direction(tb, sc.env, si.p, sx, sy, ds);
                     if (ds.pdf != 0.f) {
                         float3 wo = to_local(si, ds.d);
                         float3 bsdf_val = bsdf_eval(bsdf, si, wo);
