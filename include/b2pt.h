@@ -224,6 +224,12 @@ B2_API int b2_host_film_gaussian(int width, int height, float stddev, B2Film *ou
 B2_API int b2_host_spiral(int width, int height, int block_size, uint32_t *n_blocks,
                           int32_t *order_xy /* 2 * n_blocks or NULL to query n_blocks */);
 
+/* Debug / inspection: build the BVH4 the library would use for a triangle soup (host only).
+   tri_vertices: n * 9 floats. nodes_out: capacity node_cap * 32 floats (layout in
+   mitsuba2_b200/csrc/b2_device.cuh); order_out[n]: slot -> triangle. */
+B2_API int b2_host_build_bvh4(const float *tri_vertices, uint32_t n, float *nodes_out, uint32_t node_cap,
+                              uint32_t *n_nodes, uint32_t *order_out);
+
 #ifdef __cplusplus
 }
 #endif

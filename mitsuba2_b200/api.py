@@ -24,7 +24,7 @@ EXPORTS = [
     "b2_scene_create", "b2_scene_destroy", "b2_last_error", "b2_device_count", "b2_render", "b2_render_device",
     "b2_cancel", "b2_develop", "b2_set_stream", "b2_stage_raygen", "b2_stage_intersect", "b2_stage_occluded",
     "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
-    "b2_host_film_gaussian", "b2_host_spiral",
+    "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4",
 ]
 
 

@@ -181,3 +181,19 @@ void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh
     }
     out.n_nodes = (uint32_t) (N.size() / 32);
 }
+
+#include "../../include/b2pt.h"
+extern "C" int b2_host_build_bvh4(const float *tri_vertices, uint32_t n, float *nodes_out, uint32_t node_cap,
+                                  uint32_t *n_nodes, uint32_t *order_out) {
+    if ((n && !tri_vertices) || !n_nodes) return B2_ERR_INVALID;
+    std::vector<B2BvhTri> tris(n);
+    for (uint32_t i = 0; i < n; ++i) std::memcpy(tris[i].p, tri_vertices + 9 * (size_t) i, 36);
+    B2Bvh4 b; b2_build_bvh4(tris, b);
+    *n_nodes = b.n_nodes;
+    if (nodes_out) {
+        if (node_cap < b.n_nodes) return B2_ERR_INVALID;
+        std::memcpy(nodes_out, b.nodes.data(), b.nodes.size() * sizeof(float));
+    }
+    if (order_out && n) std::memcpy(order_out, b.order.data(), n * sizeof(uint32_t));
+    return B2_OK;
+}

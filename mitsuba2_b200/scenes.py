@@ -65,3 +65,132 @@ def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=
     fov_x = host.parse_fov(39.3077, "smaller", width, height)
     sb.sensor = host.perspective_sensor(to_world, fov_x, 10.0, 2800.0, sb.film)
     return sb
+
+
+# ---------------------------------------------------------------------------------------------
+# "veach-mis"-class scene (BASELINE configs[3]): the meshes of the reference's doc scene
+# (resources/data/docs/scenes/include/veach_mis.xml) are not shipped, so the scene is synthesised:
+# four tilted plates (rough conductors of graded roughness + one dielectric), a diffuse floor and
+# four spherical area emitters (tessellated icospheres) of graded size / radiance.
+# ---------------------------------------------------------------------------------------------
+def _icosphere(center, radius, level=1):
+    t = (1.0 + 5 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], np.float64)
+    f = [[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2], [10, 7, 6], [7, 1, 8],
+         [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]]
+    v = list(v / np.linalg.norm(v, axis=1, keepdims=True))
+    for _ in range(level):
+        cache = {}; nf = []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = (v[a] + v[b]) * 0.5
+                v.append(m / np.linalg.norm(m)); cache[key] = len(v) - 1
+            return cache[key]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        f = nf
+    n = np.array(v, np.float64)
+    pos = (np.array(center, np.float64) + radius * n).astype(np.float32)
+    return pos, n.astype(np.float32), np.array(f, np.uint32)
+
+
+def _quad(p0, p1, p2, p3):
+    pos = np.array([p0, p1, p2, p3], np.float32)
+    e0, e1 = pos[1] - pos[0], pos[3] - pos[0]
+    n = np.cross(e0.astype(np.float64), e1.astype(np.float64)); n = (n / np.linalg.norm(n)).astype(np.float32)
+    return pos, np.tile(n, (4, 1)).astype(np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+
+
+VEACH_EMITTERS = [  # centre, radius, radiance — graded like veach_mis.xml:20-70
+    ((-3.75, 0.0, 0.0), 0.0333 * 3, (901.803, 901.803, 901.803)),
+    ((-1.25, 0.0, 0.0), 0.1 * 3, (100.0, 100.0, 100.0)),
+    ((1.25, 0.0, 0.0), 0.3 * 3, (11.1111, 11.1111, 11.1111)),
+    ((3.75, 0.0, 0.0), 0.9 * 1.2, (1.23457, 1.23457, 1.23457)),
+]
+
+
+def veach_mis_meshes():
+    """-> list of dicts(name, positions, normals, faces, material) — deterministic."""
+    out = []
+    out.append(dict(name="floor", material=("diffuse", (0.4, 0.4, 0.4)),
+                    mesh=_quad((-10, -4.15, -10), (-10, -4.15, 10), (10, -4.15, 10), (10, -4.15, -10))))
+    out.append(dict(name="backwall", material=("diffuse", (0.4, 0.4, 0.4)),
+                    mesh=_quad((-10, -4.15, -2), (10, -4.15, -2), (10, 10, -2), (-10, 10, -2))))
+    plates = [(-2.6, 5.0, 0.35, ("roughconductor", "ggx", 0.01)), (-3.0, 3.9, 0.55, ("roughconductor", "beckmann", 0.05)),
+              (-3.4, 2.8, 0.8, ("dielectric", 1.5)), (-3.8, 1.6, 1.1, ("roughconductor", "ggx", 0.1))]
+    for i, (y, z, tilt, mat) in enumerate(plates):
+        dy, dz = 0.55 * np.sin(tilt), 0.55 * np.cos(tilt)
+        out.append(dict(name=f"plate{i}", material=mat,
+                        mesh=_quad((-4, y - dy, z + dz), (4, y - dy, z + dz), (4, y + dy, z - dz), (-4, y + dy, z - dz))))
+    for i, (c, r, rad) in enumerate(VEACH_EMITTERS):
+        out.append(dict(name=f"emitter{i}", material=("diffuse", (0.0, 0.0, 0.0)), mesh=_icosphere(c, r, 1), radiance=rad))
+    return out
+
+
+def veach_mis(host, width=1280, height=720, rfilter="box"):
+    sb = abi.SceneBuffers()
+    for m in veach_mis_meshes():
+        mat = m["material"]
+        if mat[0] == "diffuse":
+            b = sb.add_diffuse(mat[1])
+        elif mat[0] == "dielectric":
+            b = sb.add_dielectric(mat[1], 1.0)
+        else:
+            b = sb.add_roughconductor(alpha=mat[2], distribution=mat[1])
+        pos, nrm, faces = m["mesh"]
+        mi = sb.add_mesh(pos, faces, nrm, b)
+        if "radiance" in m:
+            sb.add_area_emitter(mi, m["radiance"])
+    sb.film = host.film_box(width, height) if rfilter == "box" else host.film_gaussian(width, height, 0.5)
+    to_world = host.look_at((0, 2, 15), (0, -2, 2.5), (0, 1, 0))
+    fov_x = host.parse_fov(28.0, "x", width, height)
+    sb.sensor = host.perspective_sensor(to_world, fov_x, 0.1, 100.0, sb.film)
+    return sb
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[4]: procedural instanced mesh — one displaced-grid mesh in a shapegroup,
+# instantiated on an n^3 lattice with a per-instance rotation drawn from a seeded generator;
+# one 2-triangle area emitter above; diffuse 0.5.
+# ---------------------------------------------------------------------------------------------
+def instanced_grid(host, width=2048, height=2048, grid=71, lattice=10, seed=1234, rfilter="box"):
+    """grid x grid vertices -> 2 (grid-1)^2 triangles per instance (71 -> 9800), lattice^3 instances."""
+    sb = abi.SceneBuffers()
+    diffuse = sb.add_diffuse((0.5, 0.5, 0.5))
+    light_b = sb.add_diffuse((0.0, 0.0, 0.0))
+    # displaced unit grid in the xy plane, z = 0.05 sin(13 x) cos(17 y)
+    u = np.linspace(-0.5, 0.5, grid, dtype=np.float64)
+    X, Y = np.meshgrid(u, u, indexing="xy")
+    Z = 0.05 * np.sin(13 * X) * np.cos(17 * Y)
+    pos = np.stack([X, Y, Z], -1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(grid * grid).reshape(grid, grid)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel(), idx[1:, :-1].ravel()
+    faces = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
+    gm = sb.add_mesh(pos, faces, None, diffuse)
+    g = sb.add_shapegroup([gm])
+    rng = np.random.default_rng(seed)
+    span = float(lattice) * 1.5
+    for i in range(lattice ** 3):
+        ix, iy, iz = i % lattice, (i // lattice) % lattice, i // (lattice * lattice)
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        w, x, y, z = q
+        R = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                      [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                      [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        M = np.eye(4); M[:3, :3] = R
+        M[:3, 3] = [(ix + 0.5) * 1.5 - span / 2, (iy + 0.5) * 1.5 - span / 2, (iz + 0.5) * 1.5 - span / 2]
+        sb.add_instance(g, M.astype(np.float32))
+    # area emitter above the lattice, facing down
+    s = span * 0.35; yl = span / 2 + 1.0
+    lp = np.array([[-s, yl, -s], [s, yl, -s], [s, yl, s], [-s, yl, s]], np.float32)
+    lm = sb.add_mesh(lp, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), None, light_b)
+    sb.add_area_emitter(lm, (40.0, 40.0, 40.0))
+    sb.film = host.film_box(width, height) if rfilter == "box" else host.film_gaussian(width, height, 0.5)
+    cam = span * 1.4
+    to_world = host.look_at((cam * 0.8, cam * 0.55, cam), (0, 0, 0), (0, 1, 0))
+    sb.sensor = host.perspective_sensor(to_world, host.parse_fov(40.0, "x", width, height), 0.05, 1000.0, sb.film)
+    return sb

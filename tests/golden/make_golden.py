@@ -329,9 +329,54 @@ GOLDEN = {
     "cbox_64_spp16_instances": dict(width=64, height=64, spp=16, no_patch=True, instances=INSTANCES),
     "cbox_64_spp16_env": dict(width=64, height=64, spp=16, envmap="only"),
     "cbox_64_spp16_env_area": dict(width=64, height=64, spp=16, envmap="with_area"),
+    # BASELINE configs[2] in miniature: rough conductor (GGX) lit by an environment map
+    "cbox_64_spp16_env_ggx": dict(width=64, height=64, spp=16, envmap="only", materials={"box": ROUGH_GGX}),
     "cbox_64_spp16_ggx": dict(width=64, height=64, spp=16, materials={"box": ROUGH_GGX}),
     "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
 }
+
+
+def write_obj(path, pos, nrm, faces):
+    with open(path, "w") as f:
+        for p in pos:
+            f.write("v %s %s %s\n" % tuple(repr(float(x)) for x in p))
+        for n in nrm:
+            f.write("vn %s %s %s\n" % tuple(repr(float(x)) for x in n))
+        for a, b, c in faces:
+            f.write("f %d//%d %d//%d %d//%d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1, c + 1))
+
+
+def veach_xml(mesh_dir, width, height, spp):
+    sys.path.insert(0, ROOT)
+    from mitsuba2_b200 import scenes
+    shapes = []
+    for m in scenes.veach_mis_meshes():
+        pos, nrm, faces = m["mesh"]
+        path = os.path.join(mesh_dir, m["name"] + ".obj")
+        write_obj(path, pos, nrm, faces)
+        mat = m["material"]
+        if mat[0] == "diffuse":
+            b = f'<bsdf type="diffuse"><rgb name="reflectance" value="{mat[1][0]}, {mat[1][1]}, {mat[1][2]}"/></bsdf>'
+        elif mat[0] == "dielectric":
+            b = f'<bsdf type="dielectric"><float name="int_ior" value="{mat[1]}"/><float name="ext_ior" value="1.0"/></bsdf>'
+        else:
+            b = f'<bsdf type="roughconductor"><string name="distribution" value="{mat[1]}"/><float name="alpha" value="{mat[2]}"/></bsdf>'
+        em = ""
+        if "radiance" in m:
+            r = m["radiance"]
+            em = f'<emitter type="area"><rgb name="radiance" value="{r[0]}, {r[1]}, {r[2]}"/></emitter>'
+        shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{b}{em}</shape>')
+    return f"""<scene version="2.0.0">
+    <integrator type="path"><integer name="max_depth" value="6"/><integer name="block_size" value="32"/></integrator>
+    <sensor type="perspective"><string name="fov_axis" value="x"/><float name="near_clip" value="0.1"/><float name="far_clip" value="100"/>
+        <float name="fov" value="28"/>
+        <transform name="to_world"><lookat origin="0, 2, 15" target="0, -2, 2.5" up="0, 1, 0"/></transform>
+        <sampler type="independent"><integer name="sample_count" value="{spp}"/></sampler>
+        <film type="hdrfilm"><integer name="width" value="{width}"/><integer name="height" value="{height}"/><rfilter type="box"/>
+            <string name="pixel_format" value="rgb"/><string name="component_format" value="float32"/><string name="file_format" value="pfm"/></film>
+    </sensor>
+    {"".join(shapes)}
+</scene>"""
 
 
 def main():
@@ -343,6 +388,11 @@ def main():
     if a.only in (None, "meshes"):
         make_cbox_meshes()
     info = open(os.path.join(ROOT, "oracle", "_ref", "BUILD_INFO.txt")).read().strip()
+    if a.only in (None, "veach_96x54_spp16"):
+        img, log = run_reference(lambda td: veach_xml(td, 96, 54, 16))
+        np.savez_compressed(os.path.join(HERE, "ref_veach_96x54_spp16.npz"), rgb=img,
+                            params=np.array(repr(dict(scene="veach", width=96, height=54, spp=16))), oracle_build=np.array(info))
+        print("ref_veach_96x54_spp16.npz", img.shape, "mean", img.mean(axis=(0, 1)))
     for name, kw in GOLDEN.items():
         if a.only and a.only != name:
             continue

@@ -38,6 +38,9 @@ def load(name, host):
     """-> (SceneBuffers, B2RenderParams, reference rgb image)"""
     z = np.load(os.path.join(GOLDEN, f"ref_{name}.npz"))
     kw = ast.literal_eval(str(z["params"]))
+    if kw.get("scene") == "veach":       # BASELINE configs[3] in miniature (mitsuba2_b200.scenes.veach_mis)
+        sb = scenes.veach_mis(host, kw["width"], kw["height"])
+        return sb, abi.render_params(max_depth=6, rr_depth=5, spp=kw["spp"], block_size=32), z["rgb"]
     env = None; drop = ()
     if kw.get("envmap"):
         env = dict(rgb=z["env_rgb"], scale=float(z["env_scale"]), to_world=z["env_to_world"].reshape(4, 4))

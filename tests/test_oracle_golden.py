@@ -21,6 +21,8 @@ def test_oracle_vs_reference(oracle, name):
         assert s["rel_l2"] < 1e-4, s                      # north_star tolerance
     if name == "cbox_64_spp16_dielectric":               # box bottoms coplanar with the floor: z-fighting
         assert s["rel_l2_unflipped"] < 1e-4
+    elif name.startswith("veach"):                        # alpha = 0.01 lobes x radiance 900: near-singular weights
+        assert s["rel_l2_unflipped"] < 5e-5 and s["flipped_pixels"] <= 20, s
     else:
         assert s["rel_l2_unflipped"] < 1e-5, s
         assert s["flipped_pixels"] <= max(60, s["pixels"] // 300), s
