@@ -1,0 +1,270 @@
+// b2path.cpp — the reference-side binding of libb2pt: a Mitsuba 2 integrator plugin.
+//
+//     <integrator type="b2path"> <integer name="max_depth" value="6"/> <integer name="block_size" value="32"/> </integrator>
+//
+// is a drop-in for <integrator type="path"> on the scalar_rgb variant: the scene is loaded by the
+// reference's own XML / plugin / OBJ code, this adapter flattens the loaded object graph into a
+// B2SceneDesc (include/b2pt.h), b2_render() runs the wavefront path tracer on the GPU, and the
+// XYZAW film goes back through the reference's Film::put / develop.
+//
+// Built by integration/build_plugin.sh against the reference's headers (compiled with the same
+// flags as src/integrators/path.cpp) and installed next to the reference's plugins in
+// oracle/_ref/dist/plugins/. This file is written against the reference's public plugin API
+// (include/mitsuba/render/*.h); nothing is copied from it.
+#include <mitsuba/core/properties.h>
+#include <mitsuba/core/transform.h>
+#include <mitsuba/render/bsdf.h>
+#include <mitsuba/render/emitter.h>
+#include <mitsuba/render/film.h>
+#include <mitsuba/render/imageblock.h>
+#include <mitsuba/render/integrator.h>
+#include <mitsuba/render/mesh.h>
+#include <mitsuba/render/sampler.h>
+#include <mitsuba/render/scene.h>
+#include <mitsuba/render/sensor.h>
+#include <mitsuba/render/spiral.h>
+#include <mitsuba/render/texture.h>
+
+#include <atomic>
+#include <cstring>
+#include <map>
+#include <typeinfo>
+
+#include <b2pt.h>
+
+NAMESPACE_BEGIN(mitsuba)
+
+namespace {
+/// Collects what Object::traverse() exposes (diffuse.cpp:137-139, dielectric.cpp:322-328, ...)
+struct ParamCollector : TraversalCallback {
+    std::map<std::string, Object *> objects;
+    std::map<std::string, std::pair<const std::type_info *, void *>> params;
+    void put_object(const std::string &name, Object *obj) override { objects[name] = obj; }
+    void put_parameter_impl(const std::string &name, const std::type_info &type, void *ptr) override {
+        params[name] = { &type, ptr };
+    }
+    float get_float(const std::string &name, float def) const {
+        auto it = params.find(name);
+        if (it == params.end() || *it->second.first != typeid(float)) return def;
+        return *(float *) it->second.second;
+    }
+};
+}  // namespace
+
+template <typename Float, typename Spectrum>
+class B2PathIntegrator final : public MonteCarloIntegrator<Float, Spectrum> {
+public:
+    MTS_IMPORT_BASE(MonteCarloIntegrator, m_max_depth, m_rr_depth, m_block_size, m_samples_per_pass, m_stop)
+    MTS_IMPORT_TYPES(Scene, Sensor, Film, Sampler, Mesh, BSDF, Emitter, Texture, ImageBlock, Shape, Medium)
+
+    B2PathIntegrator(const Properties &props) : Base(props) {
+        // the sampler keeps its base seed protected; mirror it here (default 0, like 'independent')
+        m_seed = (uint64_t) props.size_("seed", 0);
+    }
+
+    bool render(Scene *scene, Sensor *sensor) override {
+        if constexpr (is_array_v<Float> || !is_rgb_v<Spectrum>) {
+            NotImplementedError("b2path: scalar_rgb only");
+        } else {
+            m_stop = false;
+            ref<Film> film = sensor->film();
+            SurfaceInteraction3f si0 = zero<SurfaceInteraction3f>();
+
+            // ---- flatten the loaded object graph (scene.cpp:23-59 order) -------------------
+            std::vector<B2Mesh> meshes;
+            std::vector<B2Bsdf> bsdfs;
+            std::vector<B2Emitter> emitters;
+            std::map<const BSDF *, int> bsdf_index;
+            std::map<const Emitter *, int> emitter_of_mesh;
+            for (auto &shape : scene->shapes()) {
+                const Mesh *mesh = dynamic_cast<const Mesh *>(shape.get());
+                if (!mesh)
+                    Throw("b2path: only triangle meshes are supported (got %s)", shape->class_()->name());
+                B2Mesh d;
+                std::memset(&d, 0, sizeof d);
+                d.n_vertices = (uint32_t) mesh->vertex_count();
+                d.n_faces = (uint32_t) mesh->face_count();
+                d.positions = mesh->vertex_positions_buffer().data();
+                d.normals = mesh->has_vertex_normals() ? mesh->vertex_normals_buffer().data() : nullptr;
+                d.texcoords = nullptr;
+                d.faces = (const uint32_t *) mesh->faces_buffer().data();
+                const BSDF *bsdf = mesh->bsdf();
+                auto it = bsdf_index.find(bsdf);
+                if (it == bsdf_index.end()) {
+                    bsdfs.push_back(convert_bsdf(bsdf, si0));
+                    it = bsdf_index.emplace(bsdf, (int) bsdfs.size() - 1).first;
+                }
+                d.bsdf = it->second;
+                d.emitter = -1;
+                if (mesh->is_emitter())
+                    emitter_of_mesh[mesh->emitter()] = (int) meshes.size();
+                meshes.push_back(d);
+            }
+            // emitters in scene->emitters() order (uniform selection index, scene.cpp:176-198)
+            for (auto &em : scene->emitters()) {
+                B2Emitter e;
+                std::memset(&e, 0, sizeof e);
+                ParamCollector pc;
+                const_cast<Emitter *>(em.get())->traverse(&pc);
+                if (em->is_environment()) {
+                    if (pc.params.count("data") == 0 || pc.params.count("resolution") == 0)
+                        Throw("b2path: unsupported environment emitter %s", em->class_()->name());
+                    auto &data = *(DynamicBuffer<Float> *) pc.params["data"].second;
+                    auto &res = *(ScalarVector2u *) pc.params["resolution"].second;
+                    e.type = B2_EMITTER_ENVMAP; e.mesh = -1;
+                    e.scale = pc.get_float("scale", 1.f);
+                    e.envmap = data.data(); e.env_width = (int32_t) res.x(); e.env_height = (int32_t) res.y();
+                    auto trafo = em->world_transform()->eval(0.f);
+                    store_row_major(trafo.matrix, e.env_to_world);
+                    store_row_major(trafo.inverse().matrix, e.env_to_object);
+                } else {
+                    auto it = emitter_of_mesh.find(em.get());
+                    if (it == emitter_of_mesh.end() || pc.objects.count("radiance") == 0)
+                        Throw("b2path: only area and envmap emitters are supported (got %s)", em->class_()->name());
+                    e.type = B2_EMITTER_AREA; e.mesh = it->second; e.scale = 1.f;
+                    Color3f rad = ((Texture *) pc.objects["radiance"])->eval(si0);
+                    for (int k = 0; k < 3; ++k) e.radiance[k] = rad[k];
+                    meshes[it->second].emitter = (int32_t) emitters.size();
+                }
+                emitters.push_back(e);
+            }
+
+            B2SceneDesc desc;
+            std::memset(&desc, 0, sizeof desc);
+            desc.n_meshes = (uint32_t) meshes.size(); desc.meshes = meshes.data(); desc.n_top_meshes = desc.n_meshes;
+            desc.n_bsdfs = (uint32_t) bsdfs.size(); desc.bsdfs = bsdfs.data();
+            desc.n_emitters = (uint32_t) emitters.size(); desc.emitters = emitters.data();
+
+            // ---- film + reconstruction filter LUT (rfilter.h:62-65) -------------------------
+            B2Film &f = desc.film;
+            ScalarVector2i size = film->size(), crop_size = film->crop_size();
+            ScalarPoint2i crop_offset = film->crop_offset();
+            f.width = size.x(); f.height = size.y();
+            f.crop_offset[0] = crop_offset.x(); f.crop_offset[1] = crop_offset.y();
+            f.crop_size[0] = crop_size.x(); f.crop_size[1] = crop_size.y();
+            const auto *rf = film->reconstruction_filter();
+            f.filter_radius = rf->radius();
+            f.filter_scale = (float) B2_FILTER_RESOLUTION / f.filter_radius;
+            for (int i = 0; i <= B2_FILTER_RESOLUTION; ++i)
+                f.filter_lut[i] = rf->eval_discretized(((float) i + .5f) / f.filter_scale);
+            f.border = (int32_t) rf->border_size();
+
+            // ---- sensor: same derivation as PerspectiveCamera::update_camera_transforms -----
+            ParamCollector spc;
+            sensor->traverse(&spc);
+            if (spc.params.count("x_fov") == 0)
+                Throw("b2path: only the perspective sensor is supported");
+            const auto *cam = dynamic_cast<const ProjectiveCamera<Float, Spectrum> *>(sensor);
+            float x_fov = spc.get_float("x_fov", 0.f);
+            auto c2s = perspective_projection<ScalarFloat>(size, crop_size, ScalarVector2i(crop_offset), x_fov,
+                                                           cam->near_clip(), cam->far_clip());
+            store_row_major(c2s.inverse().matrix, desc.sensor.sample_to_camera);
+            store_row_major(sensor->world_transform()->eval(0.f).matrix, desc.sensor.to_world);
+            desc.sensor.near_clip = cam->near_clip(); desc.sensor.far_clip = cam->far_clip();
+
+            B2Scene *handle = nullptr;
+            if (b2_scene_create(&desc, &handle) != B2_OK)
+                Throw("b2path: %s", b2_last_error());
+
+            // ---- render ---------------------------------------------------------------------
+            B2RenderParams rp;
+            std::memset(&rp, 0, sizeof rp);
+            rp.max_depth = m_max_depth; rp.rr_depth = m_rr_depth;
+            rp.spp = (uint32_t) sensor->sampler()->sample_count();
+            rp.samples_per_pass = m_samples_per_pass == (uint32_t) -1 ? 0 : m_samples_per_pass;
+            rp.block_size = m_block_size ? m_block_size : MTS_BLOCK_SIZE;   // pin it: it feeds the seed (integrator.cpp:198)
+            rp.seed = m_seed; rp.rank = 0; rp.world_size = 1;
+
+            film->prepare({ "X", "Y", "Z", "A", "W" });                  // integrator.cpp:71-73
+            ref<ImageBlock> block = new ImageBlock(crop_size, 5, film->reconstruction_filter(), false, false, false);
+            block->set_offset(crop_offset);
+            block->clear();
+            m_handle = handle;
+            B2Stats stats;
+            int rc = b2_render(handle, &rp, block->data().data(), &stats);
+            m_handle = nullptr;
+            b2_scene_destroy(handle);
+            if (rc == B2_ERR_CANCELLED)
+                return false;                                            // integrator.cpp:174-178
+            if (rc != B2_OK)
+                Throw("b2path: %s", b2_last_error());
+            film->put(block);                                            // hdrfilm.cpp:207-211
+            Log(Info, "b2path: %i samples, %i segments, %i shadow rays, %.1f ms on the GPU (%.1f Msamples/s)",
+                stats.n_samples, stats.n_segments, stats.n_shadow_rays, stats.ms_total,
+                stats.n_samples / (stats.ms_total * 1e3f));
+            return true;
+        }
+    }
+
+    void cancel() override {
+        B2Scene *h = m_handle.load();
+        if (h) b2_cancel(h);
+        Base::cancel();
+    }
+
+    std::pair<Spectrum, Mask> sample(const Scene *, Sampler *, const RayDifferential3f &, const Medium *,
+                                     Float *, Mask) const override {
+        NotImplementedError("sample");       // the whole render() runs on the GPU
+    }
+
+    std::string to_string() const override {
+        return tfm::format("B2PathIntegrator[\n  max_depth = %i,\n  rr_depth = %i\n]", m_max_depth, m_rr_depth);
+    }
+
+    MTS_DECLARE_CLASS()
+private:
+    template <typename Matrix> static void store_row_major(const Matrix &m, float *out) {
+        for (int r = 0; r < 4; ++r)
+            for (int c = 0; c < 4; ++c)
+                out[4 * r + c] = (float) m(r, c);
+    }
+
+    static void eval3(Object *tex, const SurfaceInteraction3f &si, float out[3], float def) {
+        if (!tex) { out[0] = out[1] = out[2] = def; return; }
+        Color3f v = ((Texture *) tex)->eval(si);
+        for (int k = 0; k < 3; ++k) out[k] = v[k];
+    }
+
+    /// SmoothDiffuse / SmoothDielectric / RoughConductor -> B2Bsdf, anything else: NotImplemented
+    B2Bsdf convert_bsdf(const BSDF *bsdf, const SurfaceInteraction3f &si) const {
+        B2Bsdf b;
+        std::memset(&b, 0, sizeof b);
+        for (int k = 0; k < 3; ++k) b.specular_reflectance[k] = b.specular_transmittance[k] = 1.f;
+        if (!bsdf) { b.type = B2_BSDF_NULL; return b; }
+        ParamCollector pc;
+        const_cast<BSDF *>(bsdf)->traverse(&pc);
+        std::string cls = bsdf->class_()->name();
+        auto obj = [&](const char *n) -> Object * { auto it = pc.objects.find(n); return it == pc.objects.end() ? nullptr : it->second; };
+        if (cls == "SmoothDiffuse") {
+            b.type = B2_BSDF_DIFFUSE;
+            eval3(obj("reflectance"), si, b.reflectance, .5f);
+        } else if (cls == "SmoothDielectric") {
+            b.type = B2_BSDF_DIELECTRIC;
+            b.eta = pc.get_float("eta", 1.5046f / 1.000277f);
+            eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
+            eval3(obj("specular_transmittance"), si, b.specular_transmittance, 1.f);
+        } else if (cls == "RoughConductor") {
+            b.type = B2_BSDF_ROUGHCONDUCTOR;
+            std::string s = bsdf->to_string();                       // distribution / sample_visible are only printed
+            b.distribution = s.find("ggx") != std::string::npos ? B2_MF_GGX : B2_MF_BECKMANN;
+            b.sample_visible = s.find("sample_visible = 0") != std::string::npos ? 0 : 1;
+            Object *au = obj("alpha") ? obj("alpha") : obj("alpha_u"), *av = obj("alpha") ? obj("alpha") : obj("alpha_v");
+            b.alpha_u = au ? ((Texture *) au)->eval_1(si) : .1f;
+            b.alpha_v = av ? ((Texture *) av)->eval_1(si) : .1f;
+            eval3(obj("eta"), si, b.cond_eta, 0.f);
+            eval3(obj("k"), si, b.cond_k, 1.f);
+            eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
+            if (!b.sample_visible) NotImplementedError("b2path: roughconductor with sample_visible=false");
+        } else {
+            Throw("b2path: BSDF \"%s\" is not supported (diffuse, dielectric, roughconductor are)", cls);
+        }
+        return b;
+    }
+
+    uint64_t m_seed;
+    std::atomic<B2Scene *> m_handle { nullptr };
+};
+
+MTS_IMPLEMENT_CLASS_VARIANT(B2PathIntegrator, MonteCarloIntegrator)
+MTS_EXPORT_PLUGIN(B2PathIntegrator, "B200 wavefront path tracer (libb2pt)")
+NAMESPACE_END(mitsuba)
