@@ -291,15 +291,15 @@ def main_b2pt(a, rank, world, local_rank):
         # same launch — K1 80 B/regenerated sample and K6 40 B/sample put; K3 68 B/shadow ray (+ K6 for the
         # samples it completes)
         put_sh = st.get("n_put_shadow", 0)
-        stage_bytes = {
-            "intersect": st["n_segments"] * B_HIT,
+        stage_bytes = {     # k_trace = K2 + K3 (+ K6 for the samples it completes); k_shade = K4 + K5 + K1 + K6
+            "trace": st["n_segments"] * B_HIT + st["n_shadow_rays"] * B_SHADOW + put_sh * B_FILM,
             "shade": st["n_segments"] * (B_SHADE + B_COMPACT) + st["n_samples"] * B_RAYGEN + (st["n_samples"] - put_sh) * B_FILM,
-            "shadow": st["n_shadow_rays"] * B_SHADOW + put_sh * B_FILM,
         }
-        stage_units = {"intersect": st["n_segments"], "shade": st["n_segments"], "shadow": st["n_shadow_rays"]}
+        stage_units = {"trace": st["n_segments"] + st["n_shadow_rays"], "shade": st["n_segments"]}
+        stage_ms = {"trace": st["ms_intersect"], "shade": st["ms_shade"]}
         stages = {}
         for k, nbytes in stage_bytes.items():
-            t = st["ms_" + k]
+            t = stage_ms[k]
             stages[k] = {"ms": t, "units": stage_units[k], "bytes": nbytes, "gbs": (nbytes / (t * 1e-3) / 1e9) if t > 0 else None,
                          "avg_launch_us": t / max(n_it, 1) * 1e3}
         units = {k: (1, v) for k, v in stage_bytes.items()}

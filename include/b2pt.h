@@ -167,7 +167,8 @@ typedef struct B2Stats {
     uint64_t n_iterations;      /* wavefront iterations                                        */
     uint64_t n_launches;        /* kernels launched                                            */
     float ms_total;             /* device time of the whole render (CUDA events)               */
-    float ms_regen, ms_intersect, ms_shade, ms_shadow;   /* per-stage device time (ms_regen = k_init) */
+    float ms_regen, ms_intersect, ms_shade, ms_shadow;   /* per-stage device time: ms_regen = k_init,
+                                                            ms_intersect = k_trace (closest + any hit), ms_shadow unused */
     uint64_t bvh_nodes, bvh_tris;
     uint64_t n_put_shadow;      /* samples put on the film by k_shadow (rest: k_shade)          */
 } B2Stats;

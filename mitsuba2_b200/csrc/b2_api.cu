@@ -76,10 +76,8 @@ struct B2Scene {
     DBuf<unsigned long long> stats;
     DBuf<float> film;
     uint32_t *h_cnt = nullptr;           // pinned readback
-    float *h_film = nullptr; size_t h_film_n = 0;   // pinned staging for b2_render
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
-        if (h_film) cudaFreeHost(h_film);
     }
 };
 
@@ -384,10 +382,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
-    cudaFuncSetAttribute(k_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_shadow<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_shadow<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_occluded<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
@@ -500,7 +496,8 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         return (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (s->sm_count * std::max(per_sm, 1)), need_blocks));
     };
     int grid = resident(k_init, 0);
-    int grid_int = s->sm_count * 8, grid_sha = s->sm_count * 8, grid_shw = s->sm_count * 8;   // measured: 8 CTAs/SM queued beats exactly-resident grids
+    // measured: 8 CTAs/SM queued beats exactly-resident grids
+    int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks);
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
@@ -514,19 +511,19 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     int pending[2] = { 0, 0 };
     bool done = false;
     int status = B2_OK;
+    int parity = 0;         // k_shade of iteration k appends its emitter samples to cnt[CNT_SHADOW + (k & 1)]
     for (int b = 0; !done; ++b) {
         int slot = b & 1;
         for (int it = 0; it < batch; ++it) {
+            // iteration: trace (closest hit of every live lane + the previous iteration's emitter samples) -> shade
             tick();
-            if (inst) k_intersect<true><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q);
-            else k_intersect<false><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q);
+            if (inst) k_trace<true><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q, parity ^ 1);
+            else k_trace<false><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q, parity ^ 1);
             tick();
-            k_shade<<<grid_sha, threads, s->shade_smem_bytes, stream>>>(s->d, q);
+            k_shade<<<grid_sha, threads, s->shade_smem_bytes, stream>>>(s->d, q, parity);
             tick();
-            if (inst) k_shadow<true><<<grid_shw, threads, s->smem_bytes, stream>>>(s->d, q);
-            else k_shadow<false><<<grid_shw, threads, s->smem_bytes, stream>>>(s->d, q);
-            tick();
-            ++iterations; launches += 3;
+            parity ^= 1;
+            ++iterations; launches += 2;
         }
         CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
@@ -536,7 +533,9 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (pending[prev]) {
             CU(cudaEventSynchronize(evb[prev]));
             pending[prev] = 0;
-            if (s->h_cnt[16 * prev + CNT_ALIVE] == 0) done = true;
+            const uint32_t *c = s->h_cnt + 16 * prev;
+            // finished when every lane retired and the last k_shade left no emitter sample unresolved
+            if (c[CNT_ALIVE] == 0 && c[CNT_SHADOW] == 0 && c[CNT_SHADOW + 1] == 0) done = true;
         }
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
         if (cudaPeekAtLastError() != cudaSuccess) break;
@@ -553,10 +552,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         stats->n_samples = h[ST_SAMPLES]; stats->n_segments = h[ST_SEGMENTS]; stats->n_shadow_rays = h[ST_SHADOW];
         stats->n_invalid = h[ST_INVALID]; stats->n_iterations = iterations; stats->n_launches = launches;
         stats->ms_total = ms; stats->bvh_nodes = s->n_nodes; stats->bvh_tris = s->n_tris;
-        for (size_t i = 0; i + 3 < tev.size(); i += 4) {
-            float t[3];
-            for (int k = 0; k < 3; ++k) cudaEventElapsedTime(&t[k], tev[i + k], tev[i + k + 1]);
-            stats->ms_intersect += t[0]; stats->ms_shade += t[1]; stats->ms_shadow += t[2];
+        for (size_t i = 0; i + 2 < tev.size(); i += 3) {
+            float t[2];
+            for (int k = 0; k < 2; ++k) cudaEventElapsedTime(&t[k], tev[i + k], tev[i + k + 1]);
+            stats->ms_intersect += t[0]; stats->ms_shade += t[1];     // ms_intersect = k_trace (closest + any hit)
         }
         if (timing) cudaEventElapsedTime(&stats->ms_regen, evi0, evi1);      // k_init
         stats->n_put_shadow = h[4];

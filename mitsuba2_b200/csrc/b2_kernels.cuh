@@ -32,7 +32,7 @@ struct Queues {
     float4 *sh_o, *sh_d, *sh_c, *sh_r;
     uint32_t *sh_f;             // final entries: st.w flags (alpha, box-filter target)
     float2 *sh_p;               // final entries, wide filters: position_sample
-    uint32_t *cnt;              // [CNT_SHADOW] shadow count, [CNT_WORK] work counter, [CNT_ALIVE] live lanes
+    uint32_t *cnt;              // [CNT_SHADOW + parity] shadow counts, [CNT_WORK] work counter, [CNT_ALIVE] live lanes
     unsigned long long *stats;  // [0] samples, [1] segments, [2] shadow rays, [3] invalid
     float *film;                // crop_h x crop_w x 5 (X,Y,Z,A,W)
     const uint32_t *item_pixel; // per work item of ONE pass: x | y << 16 (crop-relative)
@@ -45,7 +45,7 @@ struct Queues {
     int32_t max_depth, rr_depth;
 };
 
-enum { CNT_SHADOW = 0, CNT_WORK = 1, CNT_ALIVE = 2 };
+enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_WORK = 2, CNT_ALIVE = 3 };
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_PUT_SHADOW = 4 };
 
 // st.w layout
@@ -294,30 +294,6 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
     return ANY ? tr.any_hit : best.t < B2_INF;
 }
 
-// ---- K2: closest hit ----------------------------------------------------------------------------
-// (A persistent-warp / dynamic-ray-fetch variant of this kernel was measured in round 1 and was
-// slower on the small-scene workload: 104 vs 93 ms per step — the refill overhead and the extra
-// registers outweigh the gain in lane utilisation when a ray needs only ~25 warp instructions.)
-template <bool INST>
-__global__ void __launch_bounds__(256) k_intersect(DScene sc, Queues q) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemScene sm = stage_scene(sc, smem_raw);
-    uint32_t n_seg = 0;
-    for (uint32_t lane = blockIdx.x * blockDim.x + threadIdx.x; lane < q.n_slots; lane += gridDim.x * blockDim.x) {
-        float4 rd = q.ray_d[lane];
-        if (rd.w < 0.f) continue;                                  // retired lane
-        float4 ro = q.ray_o[lane];
-        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h; traverse<false, INST>(sc, sm, ray, h);
-        q.hit[lane] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
-        if (INST) q.hit_inst[lane] = h.inst;
-        ++n_seg;
-    }
-    n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
-    if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_SHADOW] = 0;      // consumed by the previous k_shadow
-}
-
 // ---- K6: ImageBlock::put (imageblock.cpp:79-172) -----------------------------------------------
 // film word: x | y << 16 of the work item's pixel in bits 0..27 is not enough for 65535^2, so the
 // word is the pixel's linear index (crop-relative) and the box-filter flags travel in `flags`.
@@ -372,6 +348,69 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
         for (int k = 0; k < 5; ++k) atomicAdd(dst + k, val[k]);
     }
     return true;
+}
+
+// ---- K2 + K3 (+K6): one traversal launch per iteration ---------------------------------------------
+// Work items [0, n_slots) are the live lanes' rays (closest hit, BVH4 + Mesh::ray_intersect_triangle,
+// mesh.h:194-226); items [n_slots, n_slots + n_shadow) are the emitter samples queued by the previous
+// k_shade (any hit, scene.cpp:203-207): unoccluded => `result += contribution` (path.cpp:171), and for
+// a path that ended on that bounce the completed sample is put on the film. Both kinds are
+// independent (a lane's shadow entry only touches `res`, which the closest-hit part does not read),
+// so they share one launch: one tail and one shared-memory staging instead of two.
+// (A persistent-warp / dynamic-ray-fetch variant of the traversal was measured in round 1 and was
+// slower on the small-scene workload: 104 vs 93 ms per step.)
+template <bool INST>
+__global__ void __launch_bounds__(256) k_trace(DScene sc, Queues q, int parity) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + parity];               // filled by the previous k_shade
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[CNT_SHADOW + (parity ^ 1)] = 0;                            // the next k_shade appends there
+        atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+    }
+    const uint32_t total = q.n_slots + n_shadow;
+    uint32_t n_seg = 0, n_put = 0, n_bad = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        if (i < q.n_slots) {
+            float4 rd = q.ray_d[i];
+            if (rd.w < 0.f) continue;                                  // retired lane
+            float4 ro = q.ray_o[i];
+            Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+            Hit h; traverse<false, INST>(sc, sm, ray, h);
+            q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+            if (INST) q.hit_inst[i] = h.inst;
+            ++n_seg;
+        } else {
+            uint32_t j = i - q.n_slots;
+            float4 ro = q.sh_o[j], rd = q.sh_d[j], c = q.sh_c[j];
+            Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+            Hit h;
+            bool occluded = traverse<true, INST>(sc, sm, ray, h);
+            uint32_t lw = __float_as_uint(c.w);
+            if (lw & SH_FINAL) {
+                float4 r = q.sh_r[j];
+                float2 p = q.pos ? q.sh_p[j] : make_float2(0.f, 0.f);
+                float3 L = v3(r);
+                if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
+                uint32_t pix = __float_as_uint(r.w);
+                uint32_t flags = q.sh_f[j];
+                bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
+                ++n_put; n_bad += ok ? 0 : 1;
+            } else if (!occluded) {
+                float4 r = q.res[lw];
+                r.x += c.x; r.y += c.y; r.z += c.z;
+                q.res[lw] = r;
+            }
+        }
+    }
+    n_seg = __reduce_add_sync(0xffffffffu, n_seg);
+    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+    if (lane_id() == 0) {
+        if (n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+        if (n_put) atomicAdd(&q.stats[ST_PUT_SHADOW], (unsigned long long) n_put);
+        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
+        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
+    }
 }
 
 // ---- K1: regenerate — next camera sample of the lane's work item (integrator.cpp:233-262) ------
@@ -461,7 +500,7 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
 }
 
 // ---- K4 (+K1, K5, K6): shade -----------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
+__global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tables tb = stage_shade_tables(sc, smem_raw);
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -544,7 +583,7 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
         // atomic is issued here and its result is only consumed after phase 2 (latency hidden). ----
         uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
         uint32_t sq_base = 0;
-        if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW], __popc(sh_mask));
+        if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
         // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
         if (do_bsdf) {
             const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
@@ -605,44 +644,6 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q) {
     }
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {
-        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
-        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
-    }
-}
-
-// ---- K3 (+K6): any hit for the emitter samples ----------------------------------------------------
-template <bool INST>
-__global__ void __launch_bounds__(256) k_shadow(DScene sc, Queues q) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    SmemScene sm = stage_scene(sc, smem_raw);
-    uint32_t count = q.cnt[CNT_SHADOW];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) count);
-    uint32_t n_put = 0, n_bad = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        float4 ro = q.sh_o[i], rd = q.sh_d[i], c = q.sh_c[i];
-        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h;
-        bool occluded = traverse<true, INST>(sc, sm, ray, h);
-        uint32_t lw = __float_as_uint(c.w);
-        if (lw & SH_FINAL) {
-            // the path ended on this bounce: result += contribution (path.cpp:171), then ImageBlock::put
-            float4 r = q.sh_r[i];
-            float2 p = q.pos ? q.sh_p[i] : make_float2(0.f, 0.f);
-            float3 L = v3(r);
-            if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
-            uint32_t pix = __float_as_uint(r.w);
-            uint32_t flags = q.sh_f[i];
-            bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
-            ++n_put; n_bad += ok ? 0 : 1;
-        } else if (!occluded) {
-            float4 r = q.res[lw];
-            r.x += c.x; r.y += c.y; r.z += c.z;                    // result += mis*throughput*bsdf_val*emitter_val (path.cpp:171)
-            q.res[lw] = r;
-        }
-    }
-    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
-    if (lane_id() == 0) {
-        if (n_put) atomicAdd(&q.stats[ST_PUT_SHADOW], (unsigned long long) n_put);
         if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
         if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
     }
