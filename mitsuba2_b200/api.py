@@ -17,7 +17,7 @@ import numpy as np
 from . import abi
 
 _DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_DIR, "libb2pt.so")
+LIB_PATH = os.environ.get("B2PT_LIB", os.path.join(_DIR, "libb2pt.so"))     # B2PT_LIB: A/B builds of the same ABI
 _LIB = None
 
 EXPORTS = [

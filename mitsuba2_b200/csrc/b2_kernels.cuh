@@ -500,7 +500,10 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
 }
 
 // ---- K4 (+K1, K5, K6): shade -----------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q, int parity) {
+#ifndef B2_SHADE_MINBLOCKS
+#define B2_SHADE_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tables tb = stage_shade_tables(sc, smem_raw);
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -583,7 +586,11 @@ __global__ void __launch_bounds__(256, 3) k_shade(DScene sc, Queues q, int parit
         // atomic is issued here and its result is only consumed after phase 2 (latency hidden). ----
         uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
         uint32_t sq_base = 0;
+#ifdef B2_EXPERIMENT_NO_SHADOW_ATOMIC      // timing experiment only (WRONG results): how much does the atomic cost?
+        if (lane_id() == 0 && sh_mask) { sq_base = base; if (base == 0) q.cnt[CNT_SHADOW + parity] = q.n_slots / 2; }
+#else
         if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
+#endif
         // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
         if (do_bsdf) {
             const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
