@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--lane-slots", type=int, default=0)
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--single-set", action="store_true", help="one lane set on one stream (A/B of the two-stream overlap)")
     return ap.parse_args()
 
 
@@ -226,7 +227,8 @@ def main_b2pt(a, rank, world, local_rank):
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        ptr = integ.render_device(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots, flags=flags)
+        ptr = integ.render_device(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots,
+                                  flags=flags | (abi.FLAG_SINGLE_SET if a.single_set else 0))
         if world > 1:
             film = torch.as_tensor(CudaArray(ptr, (H, W, 5)), device="cuda")
             dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)          # the single collective: film XYZAW -> rank 0
@@ -335,6 +337,12 @@ def main_b2pt(a, rank, world, local_rank):
             "clocks": clk,
         }
         if roof:
+            # whole-step view: algorithmic bytes of all stages / the timed step (two lane sets overlapped)
+            spp_seg = stats[-1]["n_segments"] / max(1, stats[-1]["n_samples"]); spp_sh = stats[-1]["n_shadow_rays"] / max(1, stats[-1]["n_samples"])
+            b_sample = B_RAYGEN + B_FILM + spp_seg * (B_HIT + B_SHADE + B_COMPACT) + spp_sh * B_SHADOW
+            roof["bytes_per_sample"] = b_sample
+            roof["step_gbs"] = value * 1e6 * b_sample / 1e9
+            roof["step_frac"] = roof["step_gbs"] / roof["peak"]
             line["roofline"] = roof; line["stages"] = stages
         if a.cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_sample(a, 4)

@@ -157,6 +157,7 @@ typedef struct B2RenderParams {
     uint32_t _pad;
 } B2RenderParams;
 
+#define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */
 #define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */
 
 typedef struct B2Stats {

@@ -14,6 +14,7 @@ MF_BECKMANN, MF_GGX = 0, 1
 EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT = range(3)
 FILTER_RESOLUTION = 31
 FLAG_STAGE_TIMING = 1
+FLAG_SINGLE_SET = 2
 
 
 class B2Bsdf(C.Structure):

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -53,6 +54,20 @@ template <typename T> struct DBuf {
 
 }  // namespace
 
+// ---- kernel variants by scene features (b2_device.cuh F_*) -----------------------------------------
+using ShadeFn = void (*)(DScene, Queues, int);
+using TraceFn = void (*)(DScene, Queues, int);
+template <uint32_t... I> static void fill_shade(ShadeFn *t, std::integer_sequence<uint32_t, I...>) { ((t[I] = k_shade<I>), ...); }
+static ShadeFn shade_variant(uint32_t features) {
+    static ShadeFn table[F_COUNT];
+    static bool init = false;
+    if (!init) { fill_shade(table, std::make_integer_sequence<uint32_t, F_COUNT>{}); init = true; }
+    return table[features & (F_COUNT - 1)];
+}
+static TraceFn trace_variant(bool inst, bool wide) {
+    return inst ? (wide ? k_trace<true, true> : k_trace<true, false>) : (wide ? k_trace<false, true> : k_trace<false, false>);
+}
+
 struct B2Scene {
     DScene d{};
     DBuf<float4> nodes, tri_isect;
@@ -63,10 +78,12 @@ struct B2Scene {
     DBuf<int32_t> hit_inst;
     DBuf<unsigned char> blob;       // tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
     int shade_smem_bytes = 0;
+    uint32_t features = 0;          // F_* of this scene
     uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
     int smem_bytes = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;     // second lane set
     std::atomic<int> cancel{0};
     // render state (allocated lazily, reused across renders)
     DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c, sh_r;
@@ -78,6 +95,7 @@ struct B2Scene {
     uint32_t *h_cnt = nullptr;           // pinned readback
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
+        if (stream2) cudaStreamDestroy(stream2);
     }
 };
 
@@ -290,10 +308,16 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.bsdfs = (const B2Bsdf *) (s->blob.p + off_bsdf); d.emitters = (const DEmitter *) (s->blob.p + off_em);
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
+    for (const B2Bsdf &b : bsdfs) {
+        if (b.type == B2_BSDF_ROUGHCONDUCTOR) s->features |= F_ROUGH;
+        if (b.type == B2_BSDF_DIELECTRIC) s->features |= F_DIELECTRIC;
+    }
+    if (desc->film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f) s->features |= F_WIDE;
     d.instances = desc->n_instances ? s->instances.p : nullptr; d.inst_order = s->inst_order.p;
     d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_tris;
     // environment map: Hierarchical2D levels (distr_2d.h:372-471) + scene bounding sphere (envmap.cpp:127-131)
     d.env.index = -1;
+    for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type == B2_EMITTER_ENVMAP) s->features |= F_ENV;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &em = desc->emitters[e];
         if (em.type != B2_EMITTER_ENVMAP) continue;
@@ -381,9 +405,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u));
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
-    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_trace<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    cudaFuncSetAttribute(shade_variant(s->features), cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
+    cudaFuncSetAttribute(trace_variant(desc->n_instances != 0, (s->features & F_WIDE) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_occluded<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
@@ -459,55 +482,68 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
 
     bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
-    CU(s->ray_o.alloc(slots)); CU(s->ray_d.alloc(slots)); CU(s->hit.alloc(slots)); CU(s->tp.alloc(slots)); CU(s->res.alloc(slots));
-    CU(s->sh_o.alloc(slots)); CU(s->sh_d.alloc(slots)); CU(s->sh_c.alloc(slots)); CU(s->sh_r.alloc(slots)); CU(s->sh_f.alloc(slots));
-    CU(s->st.alloc(slots));
-    if (wide) { CU(s->pos.alloc(slots)); CU(s->sh_p.alloc(slots)); }
-    if (s->d.n_instances) CU(s->hit_inst.alloc(slots));
+    const size_t cap = (size_t) slots + 64;      // two lane sets, each rounded up to a multiple of 32
+    CU(s->ray_o.alloc(cap)); CU(s->ray_d.alloc(cap)); CU(s->hit.alloc(cap)); CU(s->tp.alloc(cap)); CU(s->res.alloc(cap));
+    CU(s->sh_o.alloc(cap)); CU(s->sh_d.alloc(cap)); CU(s->sh_c.alloc(cap)); CU(s->sh_r.alloc(cap)); CU(s->sh_f.alloc(cap));
+    CU(s->st.alloc(cap));
+    if (wide) { CU(s->pos.alloc(cap)); CU(s->sh_p.alloc(cap)); }
+    if (s->d.n_instances) CU(s->hit_inst.alloc(cap));
     CU(s->cnt.alloc(16)); CU(s->stats.alloc(8));
     CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
     CU(s->film.alloc((size_t) W * H * 5));
     if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 16 * sizeof(uint32_t)));
 
-    Queues q{};
-    q.ray_o = s->ray_o.p; q.ray_d = s->ray_d.p; q.hit = s->hit.p; q.tp = s->tp.p; q.res = s->res.p; q.st = s->st.p;
-    q.pos = wide ? s->pos.p : nullptr; q.sh_p = wide ? s->sh_p.p : nullptr;
-    q.hit_inst = s->d.n_instances ? s->hit_inst.p : nullptr;
-    q.sh_o = s->sh_o.p; q.sh_d = s->sh_d.p; q.sh_c = s->sh_c.p; q.sh_r = s->sh_r.p; q.sh_f = s->sh_f.p;
-    q.cnt = s->cnt.p; q.stats = s->stats.p;
-    q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
-    q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
-    q.total_items = (uint32_t) total64; q.n_slots = slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
+    // The lane slots are split into independent lane SETS, each with its own counters and shadow
+    // queue, driven on its own stream: while one set is in its (issue-bound) traversal launch the
+    // other is in its (latency-bound) shading launch, so the two kinds of kernel share the SMs and the
+    // launch tails of one set are filled by the other. All sets pull work items from one counter.
+    // (per-stage timing runs the sets one at a time so that a stage's time is its own)
+    const int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
+    uint32_t set_slots = ((slots / n_sets) + 31u) & ~31u;
+    if (n_sets > 1) slots = set_slots * n_sets;     // (allocations below were sized with the rounded-up count)
+    Queues qs[2];
+    for (int k = 0; k < n_sets; ++k) {
+        Queues &q = qs[k];
+        q = Queues{};
+        size_t o = (size_t) k * set_slots;
+        q.ray_o = s->ray_o.p + o; q.ray_d = s->ray_d.p + o; q.hit = s->hit.p + o; q.tp = s->tp.p + o; q.res = s->res.p + o; q.st = s->st.p + o;
+        q.pos = wide ? s->pos.p + o : nullptr; q.sh_p = wide ? s->sh_p.p + o : nullptr;
+        q.hit_inst = s->d.n_instances ? s->hit_inst.p + o : nullptr;
+        q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o; q.sh_r = s->sh_r.p + o; q.sh_f = s->sh_f.p + o;
+        q.cnt = s->cnt.p + 4 * k; q.work = s->cnt.p + 12; q.stats = s->stats.p;
+        q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
+        q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
+        q.total_items = (uint32_t) total64; q.n_slots = set_slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
+    }
 
-    cudaEvent_t ev0, ev1, evb[2];
+    cudaEvent_t ev0, ev1, evb[2], evs;
     CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
     CU(cudaEventCreateWithFlags(&evb[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&evb[1], cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
+    if (n_sets > 1 && !s->stream2) CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
+    cudaStream_t streams[2] = { stream, n_sets > 1 ? s->stream2 : stream };
     CU(cudaEventRecord(ev0, stream));
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     CU(cudaMemsetAsync(s->cnt.p, 0, 16 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
-    // persistent grids: exactly the number of CTAs that are resident at once, per kernel
     const int threads = 256;
     const bool inst = s->d.n_instances != 0;
-    uint32_t need_blocks = (slots + threads - 1) / threads;
-    auto resident = [&](auto kernel, int smem) {
-        int per_sm = 1;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-        return (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) (s->sm_count * std::max(per_sm, 1)), need_blocks));
-    };
-    int grid = resident(k_init, 0);
+    const ShadeFn shade_fn = shade_variant(s->features);
+    const TraceFn trace_fn = trace_variant(inst, wide);
+    uint32_t need_blocks = (set_slots + threads - 1) / threads;
+    int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids
-    int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks);
+    int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = grid;
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
-    std::vector<cudaEvent_t> tev;     // 4 events per iteration when stage timing is on
-    auto tick = [&]() { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, stream); tev.push_back(e); } };
+    std::vector<cudaEvent_t> tev;     // 3 events per iteration and set when stage timing is on
+    auto tick = [&](cudaStream_t st) { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;
     if (timing) { cudaEventCreate(&evi0); cudaEventCreate(&evi1); cudaEventRecord(evi0, stream); }
-    k_init<<<grid, threads, 0, stream>>>(s->d, q);
+    for (int k = 0; k < n_sets; ++k) { k_init<<<grid, threads, 0, stream>>>(s->d, qs[k]); ++launches; }
     if (timing) cudaEventRecord(evi1, stream);
-    ++launches;
+    if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); CU(cudaStreamWaitEvent(streams[1], evs, 0)); }
     int pending[2] = { 0, 0 };
     bool done = false;
     int status = B2_OK;
@@ -516,17 +552,22 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         int slot = b & 1;
         for (int it = 0; it < batch; ++it) {
             // iteration: trace (closest hit of every live lane + the previous iteration's emitter samples) -> shade
-            tick();
-            if (inst) k_trace<true><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q, parity ^ 1);
-            else k_trace<false><<<grid_int, threads, s->smem_bytes, stream>>>(s->d, q, parity ^ 1);
-            tick();
-            k_shade<<<grid_sha, threads, s->shade_smem_bytes, stream>>>(s->d, q, parity);
-            tick();
+            for (int k = 0; k < n_sets; ++k) {
+                cudaStream_t st = streams[k];
+                tick(st);
+                trace_fn<<<grid_int, threads, s->smem_bytes, st>>>(s->d, qs[k], parity ^ 1);
+                tick(st);
+                shade_fn<<<grid_sha, threads, s->shade_smem_bytes, st>>>(s->d, qs[k], parity);
+                tick(st);
+                launches += 2;
+            }
             parity ^= 1;
-            ++iterations; launches += 2;
+            ++iterations;
         }
-        CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        if (n_sets > 1) { CU(cudaEventRecord(evs, streams[1])); CU(cudaStreamWaitEvent(stream, evs, 0)); }
+        CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
+        if (n_sets > 1) CU(cudaStreamWaitEvent(streams[1], evb[slot], 0));     // keep the two streams within one batch of each other
         pending[slot] = 1;
         // wait for the PREVIOUS batch's readback so the GPU always has one batch queued
         int prev = slot ^ 1;
@@ -535,11 +576,16 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             pending[prev] = 0;
             const uint32_t *c = s->h_cnt + 16 * prev;
             // finished when every lane retired and the last k_shade left no emitter sample unresolved
-            if (c[CNT_ALIVE] == 0 && c[CNT_SHADOW] == 0 && c[CNT_SHADOW + 1] == 0) done = true;
+            bool all = true;
+            for (int k = 0; k < n_sets; ++k)
+                all = all && c[4 * k + CNT_ALIVE] == 0 && c[4 * k + CNT_SHADOW] == 0 && c[4 * k + CNT_SHADOW + 1] == 0;
+            if (all) done = true;
         }
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
         if (cudaPeekAtLastError() != cudaSuccess) break;
     }
+    if (n_sets > 1) { CU(cudaEventRecord(evs, streams[1])); CU(cudaStreamWaitEvent(stream, evs, 0)); }
+    cudaEventDestroy(evs);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev1, stream));
     CU(cudaEventSynchronize(ev1));

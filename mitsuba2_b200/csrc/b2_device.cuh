@@ -90,6 +90,10 @@ B2_D Tables make_tables(const DScene &sc) {
     t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.instances = sc.instances; t.n_emitters = sc.n_emitters; return t;
 }
 
+// Compile-time scene features: the stage kernels are instantiated per feature set so that a scene
+// pays (instruction cache, registers) only for the BSDFs / emitters / filter it contains.
+enum : uint32_t { F_ROUGH = 1u, F_DIELECTRIC = 2u, F_ENV = 4u, F_WIDE = 8u, F_COUNT = 16u };
+
 struct Ray { float3 o, d; float mint, maxt; };
 
 // Mesh::ray_intersect_triangle — include/mitsuba/render/mesh.h:194-226
@@ -280,11 +284,11 @@ B2_D float3 mf_sample(const MF &d, float3 wi, float sx, float sy, float &pdf) { 
 }
 
 // ---- BSDFs (src/bsdfs/{diffuse,dielectric,roughconductor}.cpp) --------------------------------
-B2_D bool bsdf_is_smooth(const B2Bsdf &b) { return b.type != B2_BSDF_DIELECTRIC; }   // path.cpp:155
+template <uint32_t F> B2_D bool bsdf_is_smooth(const B2Bsdf &b) { return !(F & F_DIELECTRIC) || b.type != B2_BSDF_DIELECTRIC; }   // path.cpp:155
 
 B2_D float3 rgb3(const float *p) { return v3(p[0], p[1], p[2]); }
 
-B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo) {
+template <uint32_t F> B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo) {
     float cti = si.wi.z, cto = wo.z;
     float3 zero = v3(0.f, 0.f, 0.f);
     switch (b.type) {
@@ -292,7 +296,7 @@ B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo) {
             if (!(cti > 0.f && cto > 0.f)) return zero;
             return v3((b.reflectance[0] * B2_INV_PI) * cto, (b.reflectance[1] * B2_INV_PI) * cto, (b.reflectance[2] * B2_INV_PI) * cto);
         }
-        case B2_BSDF_ROUGHCONDUCTOR: {                              // roughconductor.cpp:277-343
+        case B2_BSDF_ROUGHCONDUCTOR: if constexpr ((F & F_ROUGH) != 0) {   // roughconductor.cpp:277-343
             if (!(cti > 0.f && cto > 0.f)) return zero;
             float3 H = normalize(wo + si.wi);
             MF d = mf_make(b);
@@ -301,30 +305,30 @@ B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo) {
             float G = mf_smith_g1(d, si.wi, H) * mf_smith_g1(d, wo, H);
             float result = D * G / (4.f * cti);
             float c = dot(si.wi, H);
-            float3 F = v3(fresnel_conductor(c, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(c, b.cond_eta[1], b.cond_k[1]),
-                          fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
+            float3 Fr = v3(fresnel_conductor(c, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(c, b.cond_eta[1], b.cond_k[1]),
+                           fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
             float3 res = v3(result * b.specular_reflectance[0], result * b.specular_reflectance[1], result * b.specular_reflectance[2]);
-            return F * res;
-        }
+            return Fr * res;
+        } else return zero;
         default: return zero;                                       // dielectric.cpp:312-315
     }
 }
-B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 wo) {
+template <uint32_t F> B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 wo) {
     float cti = si.wi.z, cto = wo.z;
     switch (b.type) {
         case B2_BSDF_DIFFUSE: case B2_BSDF_NULL:                    // diffuse.cpp:121-135
             return (cti > 0.f && cto > 0.f) ? B2_INV_PI * cto : 0.f;
-        case B2_BSDF_ROUGHCONDUCTOR: {                              // roughconductor.cpp:345-382
+        case B2_BSDF_ROUGHCONDUCTOR: if constexpr ((F & F_ROUGH) != 0) {   // roughconductor.cpp:345-382
             float3 m = normalize(wo + si.wi);
             if (!(cti > 0.f && cto > 0.f && dot(si.wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
             MF d = mf_make(b);
             return mf_eval(d, m) * mf_smith_g1(d, si.wi, m) / (4.f * cti);
-        }
+        } else return 0.f;
         default: return 0.f;
     }
 }
 struct BS { float3 wo; float pdf, eta; bool delta; };
-B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x, float s2y, BS &bs) {
+template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x, float s2y, BS &bs) {
     float3 zero = v3(0.f, 0.f, 0.f);
     bs.wo = zero; bs.pdf = 0.f; bs.eta = 0.f; bs.delta = false;
     float cti = si.wi.z;
@@ -337,7 +341,7 @@ B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x,
             if (!(bs.pdf > 0.f)) return zero;
             return rgb3(b.reflectance);
         }
-        case B2_BSDF_DIELECTRIC: {                                  // dielectric.cpp:201-310
+        case B2_BSDF_DIELECTRIC: if constexpr ((F & F_DIELECTRIC) != 0) {   // dielectric.cpp:201-310
             float r_i, cos_theta_t, eta_it, eta_ti;
             fresnel(cti, b.eta, r_i, cos_theta_t, eta_it, eta_ti);
             float t_i = 1.f - r_i;
@@ -354,8 +358,8 @@ B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x,
                 w = w * b2_sqr(eta_ti);                              // dielectric.cpp:303-307
             }
             return w;
-        }
-        case B2_BSDF_ROUGHCONDUCTOR: {                              // roughconductor.cpp:196-275
+        } else return zero;
+        case B2_BSDF_ROUGHCONDUCTOR: if constexpr ((F & F_ROUGH) != 0) {   // roughconductor.cpp:196-275
             if (!(cti > 0.f)) return zero;
             MF d = mf_make(b);
             float pdf; float3 m = mf_sample(d, si.wi, s2x, s2y, pdf);
@@ -366,11 +370,11 @@ B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x,
             float weight = mf_smith_g1(d, bs.wo, m);
             bs.pdf = pdf / (4.f * dot(bs.wo, m));
             float c = dot(si.wi, m);
-            float3 F = v3(fresnel_conductor(c, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(c, b.cond_eta[1], b.cond_k[1]),
-                          fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
+            float3 Fr = v3(fresnel_conductor(c, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(c, b.cond_eta[1], b.cond_k[1]),
+                           fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
             float3 wv = v3(weight * b.specular_reflectance[0], weight * b.specular_reflectance[1], weight * b.specular_reflectance[2]);
-            return active ? F * wv : zero;
-        }
+            return active ? Fr * wv : zero;
+        } else return zero;
         default: return zero;
     }
 }
@@ -525,26 +529,26 @@ B2_D float3 env_sample_direction(const DEnv &env, float3 ref_p, float sx, float 
     return env_eval_spectrum(env, u, v) * b2_rcp(ds.pdf);
 }
 
-B2_D float3 emitter_sample_direction(const Tables &sc, const DEnv &env, uint32_t e, float3 ref_p, float sx, float sy, DS &ds) {
-    if ((int) e == env.index) return env_sample_direction(env, ref_p, sx, sy, ds);
+template <uint32_t F> B2_D float3 emitter_sample_direction(const Tables &sc, const DEnv &env, uint32_t e, float3 ref_p, float sx, float sy, DS &ds) {
+    if constexpr ((F & F_ENV) != 0) if ((int) e == env.index) return env_sample_direction(env, ref_p, sx, sy, ds);
     return area_sample_direction(sc, sc.emitters[e], ref_p, sx, sy, ds);
 }
 
-B2_D float3 scene_sample_emitter_direction(const Tables &sc, const DEnv &env, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
+template <uint32_t F> B2_D float3 scene_sample_emitter_direction(const Tables &sc, const DEnv &env, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
     uint32_t ne = sc.n_emitters;
     if (ne == 0) { ds.pdf = 0.f; ds.dist = 0.f; ds.p = ds.n = ds.d = v3(0.f, 0.f, 0.f); return v3(0.f, 0.f, 0.f); }
-    if (ne == 1) return emitter_sample_direction(sc, env, 0, ref_p, sx, sy, ds);
+    if (ne == 1) return emitter_sample_direction<F>(sc, env, 0, ref_p, sx, sy, ds);
     float emitter_pdf = 1.f / (float) ne;
     uint32_t index = (uint32_t) (sx * (float) ne);
     if (index > ne - 1) index = ne - 1;
     sx = (sx - (float) index * emitter_pdf) * (float) ne;
-    float3 spec = emitter_sample_direction(sc, env, index, ref_p, sx, sy, ds);
+    float3 spec = emitter_sample_direction<F>(sc, env, index, ref_p, sx, sy, ds);
     ds.pdf *= emitter_pdf;
     return spec * b2_rcp(emitter_pdf);
 }
 
-B2_D float scene_pdf_emitter_direction(const Tables &sc, const DEnv &env, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
-    if (emitter == env.index) {
+template <uint32_t F> B2_D float scene_pdf_emitter_direction(const Tables &sc, const DEnv &env, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
+    if constexpr ((F & F_ENV) != 0) if (emitter == env.index) {
         float pdf = env_pdf_direction(env, d);
         if (sc.n_emitters != 1) pdf = pdf * (1.f / (float) sc.n_emitters);
         return pdf;

@@ -32,7 +32,8 @@ struct Queues {
     float4 *sh_o, *sh_d, *sh_c, *sh_r;
     uint32_t *sh_f;             // final entries: st.w flags (alpha, box-filter target)
     float2 *sh_p;               // final entries, wide filters: position_sample
-    uint32_t *cnt;              // [CNT_SHADOW + parity] shadow counts, [CNT_WORK] work counter, [CNT_ALIVE] live lanes
+    uint32_t *cnt;              // per lane set: [CNT_SHADOW + parity] shadow counts, [CNT_ALIVE] live lanes
+    uint32_t *work;             // global work-item counter (shared by the lane sets)
     unsigned long long *stats;  // [0] samples, [1] segments, [2] shadow rays, [3] invalid
     float *film;                // crop_h x crop_w x 5 (X,Y,Z,A,W)
     const uint32_t *item_pixel; // per work item of ONE pass: x | y << 16 (crop-relative)
@@ -45,7 +46,7 @@ struct Queues {
     int32_t max_depth, rr_depth;
 };
 
-enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_WORK = 2, CNT_ALIVE = 3 };
+enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2 };
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_PUT_SHADOW = 4 };
 
 // st.w layout
@@ -297,6 +298,7 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
 // ---- K6: ImageBlock::put (imageblock.cpp:79-172) -----------------------------------------------
 // film word: x | y << 16 of the work item's pixel in bits 0..27 is not enough for 65535^2, so the
 // word is the pixel's linear index (crop-relative) and the box-filter flags travel in `flags`.
+template <bool WIDE>
 B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint32_t block_size,
                    uint32_t flags, float2 pos, float3 L, bool alpha) {
     // srgb_to_xyz (spectrum.h:221-228): M * rgb with fmadd accumulation (matrix.h:170-177)
@@ -310,7 +312,7 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
         if (!(val[k] >= -1e-5f) || !(fabsf(val[k]) < B2_INF)) return false;
     const B2Film &f = sc.film;
     int W = f.crop_size[0], H = f.crop_size[1];
-    if (f.filter_radius > 0.5f + B2_RAY_EPS) {                     // imageblock.cpp:117-161
+    if constexpr (WIDE) {                                          // imageblock.cpp:117-161 (radius > 0.5 + RayEpsilon)
         int border = f.border;
         int ox = (int) (px / block_size) * (int) block_size, oy = (int) (py / block_size) * (int) block_size;
         int bw = min((int) block_size, W - ox), bh = min((int) block_size, H - oy);
@@ -359,7 +361,7 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
 // so they share one launch: one tail and one shared-memory staging instead of two.
 // (A persistent-warp / dynamic-ray-fetch variant of the traversal was measured in round 1 and was
 // slower on the small-scene workload: 104 vs 93 ms per step.)
-template <bool INST>
+template <bool INST, bool WIDE>
 __global__ void __launch_bounds__(256) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
@@ -389,12 +391,12 @@ __global__ void __launch_bounds__(256) k_trace(DScene sc, Queues q, int parity) 
             uint32_t lw = __float_as_uint(c.w);
             if (lw & SH_FINAL) {
                 float4 r = q.sh_r[j];
-                float2 p = q.pos ? q.sh_p[j] : make_float2(0.f, 0.f);
+                float2 p = WIDE ? q.sh_p[j] : make_float2(0.f, 0.f);
                 float3 L = v3(r);
                 if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
                 uint32_t pix = __float_as_uint(r.w);
                 uint32_t flags = q.sh_f[j];
-                bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
+                bool ok = film_put<WIDE>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
                 ++n_put; n_bad += ok ? 0 : 1;
             } else if (!occluded) {
                 float4 r = q.res[lw];
@@ -462,7 +464,7 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         uint32_t lane = base + lane_id();
         bool valid = lane < q.n_slots;
-        uint32_t w = warp_append(&q.cnt[CNT_WORK], valid);
+        uint32_t w = warp_append(q.work, valid);
         uint32_t item = 0, left = 0, stw = 0; uint64_t rng = 0; Ray ray;
         bool alive = valid && regen_sample(sc, q, lane, w, 0u, item, left, rng, ray, stw);
         if (alive) {
@@ -503,6 +505,7 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
 #ifndef B2_SHADE_MINBLOCKS
 #define B2_SHADE_MINBLOCKS 3
 #endif
+template <uint32_t F>
 __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tables tb = stage_shade_tables(sc, smem_raw);
@@ -528,7 +531,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         if (valid) {
             bool hit_valid = h.x < B2_INF;
             if (hit_valid) si_fill(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
-            else si.emitter = sc.env.index;                                         // scene->environment(), scene.h:243-253
+            else if constexpr ((F & F_ENV) != 0) si.emitter = sc.env.index;                // scene->environment(), scene.h:243-253
             if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
             // ---- intersection with emitters (path.cpp:128-129) ----
             if (si.emitter >= 0) {
@@ -540,12 +543,14 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                         float dist = sqrtf(dot(dd, dd));
                         dd = dd * b2_rcp(dist);
                         if (!hit_valid) dd = v3(rd);                                // d[!it.is_valid()] = -it.wi
-                        emitter_pdf = scene_pdf_emitter_direction(tb, sc.env, si.emitter, dd, si.sh_n, dist);
+                        emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, dd, si.sh_n, dist);
                     }
                     emission_weight = mis_weight(bs_pdf, emitter_pdf);
                 }
                 float3 ev;
-                if (!hit_valid) ev = env_eval(sc.env, v3(rd));                      // envmap.cpp:134-147
+                bool miss = false;
+                if constexpr ((F & F_ENV) != 0) miss = !hit_valid;
+                if (miss) ev = env_eval(sc.env, v3(rd));                            // envmap.cpp:134-147
                 else {
                     const DEmitter &em = tb.emitters[si.emitter];
                     ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
@@ -562,13 +567,13 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
             else {
                 do_bsdf = true;
                 const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
-                if (bsdf_is_smooth(bsdf)) {                                         // path.cpp:153-172
+                if (bsdf_is_smooth<F>(bsdf)) {                                         // path.cpp:153-172
                     float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
-                    DS ds; float3 emitter_val = scene_sample_emitter_direction(tb, sc.env, si.p, sx, sy, ds);
+                    DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, sx, sy, ds);
                     if (ds.pdf != 0.f) {
                         float3 wo = to_local(si, ds.d);
-                        float3 bsdf_val = bsdf_eval(bsdf, si, wo);
-                        float bpdf = bsdf_pdf(bsdf, si, wo);
+                        float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo);
+                        float bpdf = bsdf_pdf<F>(bsdf, si, wo);
                         float mis = mis_weight(ds.pdf, bpdf);
                         float3 c = ((throughput * mis) * bsdf_val) * emitter_val;
                         if (any_nonzero(c)) {                                       // visibility: scene.cpp:203-207
@@ -596,7 +601,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
             const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
             float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
             float s1 = pcg32_next_float(rng);
-            BS bs; float3 bsdf_val = bsdf_sample(bsdf, si, s1, s2x, s2y, bs);
+            BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs);
             throughput = throughput * bsdf_val;
             if (!any_nonzero(throughput)) term = true;                             // path.cpp:182-184
             else {
@@ -620,14 +625,14 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                 if (q.pos) q.sh_p[sq] = q.pos[lane];
             } else {
                 float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
-                bool ok = film_put(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, result, (st.w & STW_ALPHA) != 0);
+                bool ok = film_put<(F & F_WIDE) != 0>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, result, (st.w & STW_ALPHA) != 0);
                 ++n_put; n_bad += ok ? 0 : 1;
             }
         }
         if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
         // ---- K1: regenerate the lanes whose path ended ----
         bool need = term && left == 0;
-        uint32_t w = warp_append(&q.cnt[CNT_WORK], need);
+        uint32_t w = warp_append(q.work, need);
         bool retire = false;
         if (term) {
             Ray ray; uint32_t stw;
