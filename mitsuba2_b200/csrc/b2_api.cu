@@ -84,6 +84,7 @@ struct B2Scene {
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // second lane set
+    cudaStream_t stream_extra[2] = { nullptr, nullptr };
     std::atomic<int> cancel{0};
     // render state (allocated lazily, reused across renders)
     DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c, sh_r;
@@ -96,6 +97,7 @@ struct B2Scene {
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
         if (stream2) cudaStreamDestroy(stream2);
+        for (cudaStream_t st : stream_extra) if (st) cudaStreamDestroy(st);
     }
 };
 
@@ -482,13 +484,13 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
 
     bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
-    const size_t cap = (size_t) slots + 64;      // two lane sets, each rounded up to a multiple of 32
+    const size_t cap = (size_t) slots + 128;      // two lane sets, each rounded up to a multiple of 32
     CU(s->ray_o.alloc(cap)); CU(s->ray_d.alloc(cap)); CU(s->hit.alloc(cap)); CU(s->tp.alloc(cap)); CU(s->res.alloc(cap));
     CU(s->sh_o.alloc(cap)); CU(s->sh_d.alloc(cap)); CU(s->sh_c.alloc(cap)); CU(s->sh_r.alloc(cap)); CU(s->sh_f.alloc(cap));
     CU(s->st.alloc(cap));
     if (wide) { CU(s->pos.alloc(cap)); CU(s->sh_p.alloc(cap)); }
     if (s->d.n_instances) CU(s->hit_inst.alloc(cap));
-    CU(s->cnt.alloc(16)); CU(s->stats.alloc(8));
+    CU(s->cnt.alloc(32)); CU(s->stats.alloc(8));
     CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
     CU(s->film.alloc((size_t) W * H * 5));
     if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 16 * sizeof(uint32_t)));
@@ -498,10 +500,11 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // other is in its (latency-bound) shading launch, so the two kinds of kernel share the SMs and the
     // launch tails of one set are filled by the other. All sets pull work items from one counter.
     // (per-stage timing runs the sets one at a time so that a stage's time is its own)
-    const int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
+    int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
+    if (n_sets > 1) { const char *e = getenv("B2_LANE_SETS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) n_sets = atoi(e); }   // tuning knob
     uint32_t set_slots = ((slots / n_sets) + 31u) & ~31u;
     if (n_sets > 1) slots = set_slots * n_sets;     // (allocations below were sized with the rounded-up count)
-    Queues qs[2];
+    Queues qs[4];
     for (int k = 0; k < n_sets; ++k) {
         Queues &q = qs[k];
         q = Queues{};
@@ -510,7 +513,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.pos = wide ? s->pos.p + o : nullptr; q.sh_p = wide ? s->sh_p.p + o : nullptr;
         q.hit_inst = s->d.n_instances ? s->hit_inst.p + o : nullptr;
         q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o; q.sh_r = s->sh_r.p + o; q.sh_f = s->sh_f.p + o;
-        q.cnt = s->cnt.p + 4 * k; q.work = s->cnt.p + 12; q.stats = s->stats.p;
+        q.cnt = s->cnt.p + 4 * k; q.work = s->cnt.p + 16; q.stats = s->stats.p;
         q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
         q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
         q.total_items = (uint32_t) total64; q.n_slots = set_slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
@@ -520,11 +523,14 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
     CU(cudaEventCreateWithFlags(&evb[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&evb[1], cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
+    cudaEvent_t evx[4] = { nullptr, nullptr, nullptr, nullptr };
+    for (int k = 1; k < 4; ++k) CU(cudaEventCreateWithFlags(&evx[k], cudaEventDisableTiming));
     if (n_sets > 1 && !s->stream2) CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-    cudaStream_t streams[2] = { stream, n_sets > 1 ? s->stream2 : stream };
+    for (int k = 2; k < n_sets; ++k) if (!s->stream_extra[k - 2]) CU(cudaStreamCreateWithFlags(&s->stream_extra[k - 2], cudaStreamNonBlocking));
+    cudaStream_t streams[4] = { stream, n_sets > 1 ? s->stream2 : stream, s->stream_extra[0], s->stream_extra[1] };
     CU(cudaEventRecord(ev0, stream));
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
-    CU(cudaMemsetAsync(s->cnt.p, 0, 16 * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
     const bool inst = s->d.n_instances != 0;
@@ -543,7 +549,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     if (timing) { cudaEventCreate(&evi0); cudaEventCreate(&evi1); cudaEventRecord(evi0, stream); }
     for (int k = 0; k < n_sets; ++k) { k_init<<<grid, threads, 0, stream>>>(s->d, qs[k]); ++launches; }
     if (timing) cudaEventRecord(evi1, stream);
-    if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); CU(cudaStreamWaitEvent(streams[1], evs, 0)); }
+    if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); for (int k = 1; k < n_sets; ++k) CU(cudaStreamWaitEvent(streams[k], evs, 0)); }
     int pending[2] = { 0, 0 };
     bool done = false;
     int status = B2_OK;
@@ -564,10 +570,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             parity ^= 1;
             ++iterations;
         }
-        if (n_sets > 1) { CU(cudaEventRecord(evs, streams[1])); CU(cudaStreamWaitEvent(stream, evs, 0)); }
+        for (int k = 1; k < n_sets; ++k) { CU(cudaEventRecord(evx[k], streams[k])); CU(cudaStreamWaitEvent(stream, evx[k], 0)); }
         CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
-        if (n_sets > 1) CU(cudaStreamWaitEvent(streams[1], evb[slot], 0));     // keep the two streams within one batch of each other
+        for (int k = 1; k < n_sets; ++k) CU(cudaStreamWaitEvent(streams[k], evb[slot], 0));     // keep the streams within one batch of each other
         pending[slot] = 1;
         // wait for the PREVIOUS batch's readback so the GPU always has one batch queued
         int prev = slot ^ 1;
@@ -584,8 +590,8 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
         if (cudaPeekAtLastError() != cudaSuccess) break;
     }
-    if (n_sets > 1) { CU(cudaEventRecord(evs, streams[1])); CU(cudaStreamWaitEvent(stream, evs, 0)); }
-    cudaEventDestroy(evs);
+    for (int k = 1; k < n_sets; ++k) { CU(cudaEventRecord(evx[k], streams[k])); CU(cudaStreamWaitEvent(stream, evx[k], 0)); }
+    cudaEventDestroy(evs); for (int k = 1; k < 4; ++k) cudaEventDestroy(evx[k]);
     CU(cudaGetLastError());
     CU(cudaEventRecord(ev1, stream));
     CU(cudaEventSynchronize(ev1));
