@@ -70,7 +70,7 @@ static TraceFn trace_variant(bool inst, bool wide) {
 
 struct B2Scene {
     DScene d{};
-    DBuf<float4> nodes, tri_isect;
+    DBuf<float4> nodes, tri_isect, flat_leaves;
     DBuf<DInstance> instances;
     DBuf<float4> env_data;
     DBuf<float> env_levels;
@@ -404,7 +404,23 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     const uint32_t budget_all = 48 * 1024, budget_top = 32 * 1024;
     if (bvh.n_nodes * 128u + nt * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
     else { d.smem_nodes = std::min<uint32_t>(top_nodes, budget_top / 128u); d.smem_tris = 0; }
-    s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u));
+    // tiny flat scenes: list the BVH leaves (box + code) for the exhaustive leaf scan (traverse_flat)
+    d.n_flat_leaves = 0; d.flat_leaves = nullptr;
+    if (d.smem_tris && desc->n_instances == 0 && nt > 0) {
+        std::vector<float4> flat;
+        for (uint32_t n = 0; n < bvh.n_nodes; ++n)
+            for (int k = 0; k < 4; ++k) {
+                const float *N = &bvh.nodes[32 * (size_t) n];
+                int32_t code; std::memcpy(&code, &N[24 + k], 4);
+                if (code < 0) {
+                    float cf; std::memcpy(&cf, &code, 4);
+                    flat.push_back(make_float4(N[0 + k], N[4 + k], N[8 + k], cf));
+                    flat.push_back(make_float4(N[12 + k], N[16 + k], N[20 + k], 0.f));
+                }
+            }
+        if (flat.size() / 2 <= 32 && s->flat_leaves.upload(flat) == cudaSuccess) { d.n_flat_leaves = (uint32_t) (flat.size() / 2); d.flat_leaves = s->flat_leaves.p; }
+    }
+    s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u) + d.n_flat_leaves * 32u);
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(shade_variant(s->features), cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);

@@ -65,6 +65,9 @@ struct DScene {
     const uint32_t *inst_order; // TLAS leaf order -> instance index
     uint32_t n_instances, tlas_root, n_top_tris, _pad0;
     uint32_t smem_nodes;        // nodes [0, smem_nodes) are staged in shared memory
+    const float4 *flat_leaves;  // tiny flat scenes: the BVH leaves as a list, 2 float4 each: (lo.xyz, leaf code), (hi.xyz, -)
+    uint32_t n_flat_leaves;     // 0: use the BVH; 1..32: exhaustive leaf-box scan (no tree, no stack, no divergence)
+    uint32_t _pad1;
     uint32_t smem_tris;         // 1: all triangle positions staged in shared memory too
     const unsigned char *blob;  // one allocation holding tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
     uint32_t blob_bytes;        // size of the blob (multiple of 16)

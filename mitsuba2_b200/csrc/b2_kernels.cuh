@@ -97,25 +97,27 @@ B2_D void mbar_wait(uint64_t *mbar, uint32_t parity) {
                  :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
 }
 
-struct SmemScene { const float4 *nodes; const float4 *tris; };
+struct SmemScene { const float4 *nodes; const float4 *tris; const float4 *flat; };
 
 // Stage sc.smem_nodes BVH nodes (+ all triangle positions if sc.smem_tris) with cp.async.bulk.
 B2_D SmemScene stage_scene(const DScene &sc, unsigned char *smem_raw) {
-    SmemScene s; s.nodes = nullptr; s.tris = nullptr;
-    uint32_t node_bytes = sc.smem_nodes * 128u, tri_bytes = sc.smem_tris ? sc.n_tris * 48u : 0u;
+    SmemScene s; s.nodes = nullptr; s.tris = nullptr; s.flat = nullptr;
+    uint32_t node_bytes = sc.smem_nodes * 128u, tri_bytes = sc.smem_tris ? sc.n_tris * 48u : 0u, flat_bytes = sc.n_flat_leaves * 32u;
     if (node_bytes + tri_bytes == 0) return s;
     uint64_t *mbar = (uint64_t *) smem_raw;
     float4 *dst = (float4 *) (smem_raw + 16);
     if (threadIdx.x == 0) mbar_init(mbar, 1);
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(mbar, node_bytes + tri_bytes);
+        mbar_expect_tx(mbar, node_bytes + tri_bytes + flat_bytes);
         if (node_bytes) stage_bulk(dst, sc.nodes, node_bytes, mbar);
         if (tri_bytes) stage_bulk((char *) dst + node_bytes, sc.tri_isect, tri_bytes, mbar);
+        if (flat_bytes) stage_bulk((char *) dst + node_bytes + tri_bytes, sc.flat_leaves, flat_bytes, mbar);
     }
     mbar_wait(mbar, 0);
     s.nodes = dst;
     if (tri_bytes) s.tris = (const float4 *) ((const char *) dst + node_bytes);
+    if (flat_bytes) s.flat = (const float4 *) ((const char *) dst + node_bytes + tri_bytes);
     return s;
 }
 
@@ -242,6 +244,71 @@ struct Trav {
     }
 };
 
+// Tiny flat scenes (<= 32 leaves, everything in shared memory): no tree at all. Every lane scans ALL
+// leaf boxes with the same slab test (uniform loop: no stack, no divergence), remembers the hit leaves
+// in a bit mask, tests the nearest leaf first and then the remaining ones that are still closer than the
+// best hit. The triangle tests and the tie rule are the same as in the BVH path, so the result is
+// bit-identical; for the 38-triangle Cornell box this replaces ~3.2 node visits + a stack by 19 slab
+// tests at full lane utilisation.
+B2_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+template <bool ANY>
+B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
+    best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu; best.inst = -1;
+    float tmax = ray.maxt;
+    float dx = copysignf(fmaxf(fabsf(ray.d.x), 1e-20f), ray.d.x), dy = copysignf(fmaxf(fabsf(ray.d.y), 1e-20f), ray.d.y),
+          dz = copysignf(fmaxf(fabsf(ray.d.z), 1e-20f), ray.d.z);
+    const float idx = rcp_approx(dx), idy = rcp_approx(dy), idz = rcp_approx(dz);
+    const float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
+    const uint32_t n = sc.n_flat_leaves;
+    uint32_t mask = 0; float near_t = B2_INF; uint32_t near_l = 0;
+    {
+        const float tlim = tmax * 1.0000004f;
+        #pragma unroll 4
+        for (uint32_t l = 0; l < n; ++l) {
+            float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+            float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                  z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+            float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+            float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tlim));
+            bool h = tn <= tf;
+            if (h) mask |= 1u << l;
+            if (h && tn < near_t) { near_t = tn; near_l = l; }
+        }
+    }
+    bool first = mask != 0;
+    while (mask) {
+        uint32_t l;
+        if (first) { l = near_l; first = false; }
+        else {
+            l = (uint32_t) __ffs((int) mask) - 1u;
+            if (!ANY && best.t < B2_INF) {      // still closer than the best hit?
+                float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+                float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                      z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+                float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+                if (tn > tmax * 1.0000004f) { mask &= ~(1u << l); continue; }
+            }
+        }
+        mask &= ~(1u << l);
+        uint32_t code = __float_as_uint(sm.flat[2 * l].w);
+        uint32_t s0 = code & 0x07ffffffu, cnt = (code >> 27) & 0xfu;
+        for (uint32_t s = s0; s < s0 + cnt; ++s) {
+            float4 a0 = sm.tris[3 * s], a1 = sm.tris[3 * s + 1], a2 = sm.tris[3 * s + 2];
+            float t, u, v;
+            if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
+                if (ANY) return true;
+                uint32_t prim = __float_as_uint(a0.w);
+                if (t < best.t || (t == best.t && prim > best.prim)) {
+                    best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim;
+                    tmax = t;
+                }
+            }
+        }
+    }
+    return best.t < B2_INF;
+}
+
 // Scene::ray_intersect_preliminary / ray_test: the top-level triangles, then (instanced scenes) a
 // BVH4 over the instances' world bounds whose leaves restart the traversal on the shapegroup's BVH
 // with the ray mapped to object space — origin as a point, direction as an UN-normalised vector,
@@ -249,6 +316,7 @@ struct Trav {
 // INST is a compile-time switch so that flat scenes do not pay registers for the two-level code.
 template <bool ANY, bool INST>
 B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
+    if (!INST && sc.n_flat_leaves) return traverse_flat<ANY>(sc, sm, ray, best);      // warp-uniform
     int stack[40];
     Trav tr; tr.init(sc, ray, stack);
     tr.run<ANY>(sc, sm, stack, false);
@@ -362,7 +430,7 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
 // (A persistent-warp / dynamic-ray-fetch variant of the traversal was measured in round 1 and was
 // slower on the small-scene workload: 104 vs 93 ms per step.)
 template <bool INST, bool WIDE>
-__global__ void __launch_bounds__(256) k_trace(DScene sc, Queues q, int parity) {
+__global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
     const uint32_t n_shadow = q.cnt[CNT_SHADOW + parity];               // filled by the previous k_shade
