@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--lane-slots", type=int, default=0)
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--no-stage-timing", action="store_true")
+    ap.add_argument("--workload", default="cbox", choices=["cbox", "veach", "grid"],
+                    help="cbox = BASELINE configs[1] (the bench line); veach / grid = configs[3] / configs[4] (extra measurements)")
     ap.add_argument("--single-set", action="store_true", help="one lane set on one stream (A/B of the two-stream overlap)")
     return ap.parse_args()
 
@@ -208,10 +210,15 @@ def main_b2pt(a, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    sb = scenes.cbox(api.Host(), a.res, a.res)
+    if a.workload == "veach":
+        sb = scenes.veach_mis(api.Host(), a.res, a.res * 9 // 16)
+    elif a.workload == "grid":
+        sb = scenes.instanced_grid(api.Host(), a.res, a.res)
+    else:
+        sb = scenes.cbox(api.Host(), a.res, a.res)
     scene = api.Scene(sb)
     integ = api.PathIntegrator(max_depth=a.max_depth, rr_depth=5, samples_per_pass=a.spp_per_pass, block_size=32)
-    H = W = a.res
+    H, W = sb.film.crop_size[1], sb.film.crop_size[0]
     n_samples = H * W * a.spp
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # > 126 MB L2
     host_film = torch.empty((H, W, 5), dtype=torch.float32).pin_memory().numpy()
@@ -325,8 +332,9 @@ def main_b2pt(a, rank, world, local_rank):
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cbox {a.res}x{a.res}, {a.spp} spp, max_depth {a.max_depth}, diffuse + area emitter, box filter "
-                                   f"(BASELINE configs[1])", "samples_per_pass": a.spp_per_pass or a.spp, "block_size": 32, "seed": 0,
+            "config": {"workload": {"cbox": f"cbox {W}x{H}, {a.spp} spp, max_depth {a.max_depth}, diffuse + area emitter, box filter (BASELINE configs[1])",
+                                    "veach": f"veach-mis class {W}x{H}, {a.spp} spp, 4 emitters, dielectric + rough conductors (BASELINE configs[3])",
+                                    "grid": f"instanced displaced grid, {sb.n_triangles} triangles x {len(sb.instances)} instances, {W}x{H}, {a.spp} spp (BASELINE configs[4])"}[a.workload], "samples_per_pass": a.spp_per_pass or a.spp, "block_size": 32, "seed": 0,
                        "parallelism": f"pixel blocks b % {world} == rank, one NCCL reduce of the film" if world > 1 else "1 GPU",
                        "l2": "256 MB flush between steps; wavefront queues > L2", "lane_slots": a.lane_slots or "auto"},
             "mean_segments_per_sample": st["n_segments"] * world / n_samples if world == 1 else None,
@@ -344,7 +352,7 @@ def main_b2pt(a, rank, world, local_rank):
             roof["step_gbs"] = value * 1e6 * b_sample / 1e9
             roof["step_frac"] = roof["step_gbs"] / roof["peak"]
             line["roofline"] = roof; line["stages"] = stages
-        if a.cpu_baseline and world == 1:
+        if a.cpu_baseline and world == 1 and a.workload == "cbox":
             line["cpu_baseline"] = cpu_sample(a, 4)
         print(json.dumps(line))
     if world > 1:

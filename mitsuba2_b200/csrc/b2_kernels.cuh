@@ -326,7 +326,9 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
         float dz = fabsf(ray.d.z) > 1e-20f ? ray.d.z : (ray.d.z < 0.f ? -1e-20f : 1e-20f);
         float idx = __fdividef(1.f, dx), idy = __fdividef(1.f, dy), idz = __fdividef(1.f, dz);
         float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
-        int tstack[24]; int tsp = 0;
+        // front-to-back over the instance boxes: nearest child first, the others are pushed with their
+        // entry distance and culled on pop against the best hit found so far
+        int tstack[32]; float tdist[32]; int tsp = 0;
         int cur = (int) sc.tlas_root;
         for (;;) {
             if (cur >= 0) {
@@ -334,15 +336,19 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
                 float4 lox = __ldg(gp), loy = __ldg(gp + 1), loz = __ldg(gp + 2), hix = __ldg(gp + 3), hiy = __ldg(gp + 4),
                        hiz = __ldg(gp + 5), chf = __ldg(gp + 6);
                 const float tlim = fminf(ray.maxt, tr.best.t) * 1.0000004f;
+                float bd = B2_INF; int bc = 0;
                 #define B2_TSLAB(k) { \
                     float a0 = b2_fma(lox.k, idx, oox), a1 = b2_fma(hix.k, idx, oox), b0 = b2_fma(loy.k, idy, ooy), b1 = b2_fma(hiy.k, idy, ooy), \
                           c0 = b2_fma(loz.k, idz, ooz), c1 = b2_fma(hiz.k, idz, ooz); \
                     float tn = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), ray.mint)); \
                     float tf = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tlim)); \
                     int c = __float_as_int(chf.k); \
-                    if (c != 0 && tn <= tf) tstack[tsp++] = c; }
+                    if (c != 0 && tn <= tf) { \
+                        if (tn < bd) { if (bc != 0) { tstack[tsp] = bc; tdist[tsp] = bd; ++tsp; } bd = tn; bc = c; } \
+                        else { tstack[tsp] = c; tdist[tsp] = tn; ++tsp; } } }
                 B2_TSLAB(x) B2_TSLAB(y) B2_TSLAB(z) B2_TSLAB(w)
                 #undef B2_TSLAB
+                if (bc != 0) { cur = bc; continue; }
             } else {
                 uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
                 for (uint32_t s = first; s < first + count; ++s) {
@@ -355,8 +361,13 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
                     if (ANY && tr.any_hit) { best = tr.best; return true; }
                 }
             }
-            if (tsp == 0) break;
-            cur = tstack[--tsp];
+            // pop the next entry that can still contain a closer hit
+            bool found = false;
+            while (tsp > 0) {
+                --tsp;
+                if (tdist[tsp] <= fminf(ray.maxt, tr.best.t) * 1.0000004f) { cur = tstack[tsp]; found = true; break; }
+            }
+            if (!found) break;
         }
     }
     best = tr.best;
