@@ -65,7 +65,7 @@ static ShadeFn shade_variant(uint32_t features) {
     return table[features & (F_COUNT - 1)];
 }
 static TraceFn trace_variant(bool inst, bool wide) {
-    return inst ? (wide ? k_trace<true, true> : k_trace<true, false>) : (wide ? k_trace<false, true> : k_trace<false, false>);
+    return inst ? (wide ? k_trace_inst<true> : k_trace_inst<false>) : (wide ? k_trace<false, true> : k_trace<false, false>);
 }
 
 struct B2Scene {
@@ -556,6 +556,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids
     int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = grid;
+    if (inst) grid_int = s->sm_count * 3;           // k_trace_inst: persistent warps, 3 CTAs/SM resident
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;

@@ -46,7 +46,7 @@ struct Queues {
     int32_t max_depth, rr_depth;
 };
 
-enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2 };
+enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */ };
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_PUT_SHADOW = 4 };
 
 // st.w layout
@@ -169,7 +169,12 @@ struct Trav {
     }
     // (re)start on another BVH (a shapegroup's, with the ray in object space) keeping the best hit so far
     B2_D void restart(const DScene &sc, const Ray &r, int *stack, int root, int instance) {
-        ray = r; inst = instance;
+        set_ray(r); inst = instance;
+        stack[0] = B2_TRAV_DONE; sp = 1;
+        cur = root;
+    }
+    B2_D void set_ray(const Ray &r) {
+        ray = r;
         tmax = fminf(r.maxt, best.t);
         // reciprocal direction for the slab tests only (approximate is fine: tests are conservative)
         float dx = fabsf(r.d.x) > 1e-20f ? r.d.x : (r.d.x < 0.f ? -1e-20f : 1e-20f);
@@ -181,8 +186,6 @@ struct Trav {
         nxi = dx < 0.f ? 3 : 0; fxi = dx < 0.f ? 0 : 3;
         nyi = dy < 0.f ? 4 : 1; fyi = dy < 0.f ? 1 : 4;
         nzi = dz < 0.f ? 5 : 2; fzi = dz < 0.f ? 2 : 5;
-        stack[0] = B2_TRAV_DONE; sp = 1;
-        cur = root;
     }
 
     // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the same
@@ -494,6 +497,194 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
     }
 }
 
+// ---- instanced scenes: persistent warps, ONE traversal loop over both levels, dynamic ray fetch ----
+// On an instanced scene the cost of a ray varies by orders of magnitude (most camera rays of the
+// BASELINE lattice miss everything, a few cross twenty instances), so a static ray -> lane mapping
+// leaves ~7 of 32 lanes busy (ncu, profiles/r01). Here every lane owns a resumable traversal state:
+// one stack holds the top-level triangles' BVH, the instance BVH (TLAS) and the shapegroup BVHs
+// (same node format); descending into an instance pushes a POP marker and swaps the ray for its
+// object-space image (instance.cpp:107-117: un-normalised direction, so t keeps its meaning), popping
+// the marker swaps the world ray back (re-read from the queue). Stack entries carry their entry
+// distance and are culled on pop. Whenever fewer than B2_REFILL_THRESHOLD lanes of a warp are still
+// traversing, the idle lanes fetch new rays from a global counter (Aila & Laine 2009). The hit is the
+// lexicographic (t, key) minimum, so the result is the same as traverse<ANY, true>() bit for bit.
+#define B2_TRAV_POP 0x7ffffffe
+#define B2_TRAV_NEEDPOP 0x7ffffffd
+#define B2_INST_STACK 64
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256, 3) k_trace_inst(DScene sc, Queues q, int parity) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[CNT_SHADOW + (parity ^ 1)] = 0;
+        atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+    }
+    const uint32_t total = q.n_slots + n_shadow;
+    uint32_t n_seg = 0, n_put = 0, n_bad = 0;
+    int stack[B2_INST_STACK]; float sdist[B2_INST_STACK];
+    Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f;
+    uint32_t item = 0;
+    bool busy = false, exhausted = false;
+    for (;;) {
+        uint32_t act = __ballot_sync(0xffffffffu, busy);
+        if (!exhausted && __popc(act) < B2_REFILL_THRESHOLD) {
+            const uint32_t idle = ~act, n_idle = __popc(idle);
+            uint32_t base = 0;
+            if (lane_id() == 0) base = atomicAdd(&q.cnt[CNT_FETCH], n_idle);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (!busy) {
+                uint32_t i = base + __popc(idle & ((1u << lane_id()) - 1u));
+                if (i < total) {
+                    float4 ro, rd;
+                    if (i < q.n_slots) { rd = q.ray_d[i]; ro = q.ray_o[i]; }
+                    else { rd = q.sh_d[i - q.n_slots]; ro = q.sh_o[i - q.n_slots]; }
+                    if (rd.w >= 0.f) {                                   // (retired lanes carry maxt < 0)
+                        item = i; busy = true;
+                        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+                        tr.best.t = B2_INF; tr.best.u = 0.f; tr.best.v = 0.f; tr.best.slot = 0xffffffffu; tr.best.prim = 0xffffffffu; tr.best.inst = -1;
+                        tr.any_hit = false;
+                        tr.set_ray(ray);
+                        stack[0] = B2_TRAV_DONE; sdist[0] = -B2_INF; tr.sp = 1;
+                        if (sc.n_top_tris) {                             // phase -2: the top-level triangles, then the TLAS
+                            tr.inst = -2; tr.cur = 0;
+                            if (sc.n_instances) { stack[1] = B2_TRAV_POP; sdist[1] = -B2_INF; tr.sp = 2; }
+                        } else { tr.inst = -1; tr.cur = (int) sc.tlas_root; }
+                    }
+                }
+            }
+            if (base + n_idle >= total) exhausted = true;
+            act = __ballot_sync(0xffffffffu, busy);
+        }
+        if (act == 0) { if (exhausted) break; continue; }
+        if (busy) {
+            const bool any_ray = item >= q.n_slots;
+            // ---- inner nodes (either level) ----
+            while ((uint32_t) tr.cur < (uint32_t) B2_TRAV_NEEDPOP) {
+                float4 nx, ny, nz, fx, fy, fz, chf;
+                if ((uint32_t) tr.cur < sc.smem_nodes) {
+                    const float4 *np = sm.nodes + 8 * tr.cur;
+                    nx = np[tr.nxi]; ny = np[tr.nyi]; nz = np[tr.nzi]; fx = np[tr.fxi]; fy = np[tr.fyi]; fz = np[tr.fzi]; chf = np[6];
+                } else {
+                    const float4 *gp = sc.nodes + 8 * (size_t) tr.cur;
+                    nx = __ldg(gp + tr.nxi); ny = __ldg(gp + tr.nyi); nz = __ldg(gp + tr.nzi);
+                    fx = __ldg(gp + tr.fxi); fy = __ldg(gp + tr.fyi); fz = __ldg(gp + tr.fzi); chf = __ldg(gp + 6);
+                }
+                const float tlim = tr.tmax * 1.0000004f;
+                #define B2_SLAB(k) \
+                    float tn##k = fmaxf(fmaxf(b2_fma(nx.k, tr.idx, tr.oox), b2_fma(ny.k, tr.idy, tr.ooy)), fmaxf(b2_fma(nz.k, tr.idz, tr.ooz), tr.ray.mint)); \
+                    float tf##k = fminf(fminf(b2_fma(fx.k, tr.idx, tr.oox), b2_fma(fy.k, tr.idy, tr.ooy)), fminf(b2_fma(fz.k, tr.idz, tr.ooz), tlim)); \
+                    int c##k = __float_as_int(chf.k); \
+                    bool h##k = c##k != 0 && tn##k <= tf##k;
+                B2_SLAB(x) B2_SLAB(y) B2_SLAB(z) B2_SLAB(w)
+                #undef B2_SLAB
+                float bd = B2_INF; int bc = 0;
+                if (hx) { bd = tnx; bc = cx; }
+                if (hy && tny < bd) { bd = tny; bc = cy; }
+                if (hz && tnz < bd) { bd = tnz; bc = cz; }
+                if (hw && tnw < bd) { bd = tnw; bc = cw; }
+                if (hx && cx != bc) { stack[tr.sp] = cx; sdist[tr.sp] = tnx; ++tr.sp; }
+                if (hy && cy != bc) { stack[tr.sp] = cy; sdist[tr.sp] = tny; ++tr.sp; }
+                if (hz && cz != bc) { stack[tr.sp] = cz; sdist[tr.sp] = tnz; ++tr.sp; }
+                if (hw && cw != bc) { stack[tr.sp] = cw; sdist[tr.sp] = tnw; ++tr.sp; }
+                if (bc != 0) { tr.cur = bc; continue; }
+                tr.cur = B2_TRAV_NEEDPOP;
+            }
+            // ---- one leaf ----
+            if (tr.cur < 0) {
+                const uint32_t first = (uint32_t) tr.cur & 0x07ffffffu, count = ((uint32_t) tr.cur >> 27) & 0xfu;
+                if (tr.inst == -1) {
+                    // TLAS leaf: enter the (first) instance, keep the others for later
+                    for (uint32_t s = first + 1; s < first + count; ++s) {
+                        stack[tr.sp] = (int) (0x80000000u | (1u << 27) | s); sdist[tr.sp] = -B2_INF; ++tr.sp;
+                    }
+                    const uint32_t ii = __ldg(&sc.inst_order[first]);
+                    const DInstance &in = sc.instances[ii];
+                    Ray ro; ro.o = xf_point(in.to_object, tr.ray.o); ro.d = xf_vector(in.to_object, tr.ray.d);
+                    ro.mint = tr.ray.mint; ro.maxt = tr.ray.maxt;
+                    tr.set_ray(ro);
+                    tr.inst = (int) ii;
+                    stack[tr.sp] = B2_TRAV_POP; sdist[tr.sp] = -B2_INF; ++tr.sp;
+                    tr.cur = in.root;
+                } else {
+                    const int key_inst = tr.inst < 0 ? -1 : tr.inst;
+                    for (uint32_t s = first; s < first + count; ++s) {
+                        float4 a0 = __ldg(&sc.tri_isect[3 * (size_t) s]), a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]), a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]);
+                        float t, u, v;
+                        if (tri_isect(v3(a0), v3(a1), v3(a2), tr.ray, tr.tmax, t, u, v)) {
+                            if (any_ray) { tr.any_hit = true; break; }
+                            uint32_t prim = __float_as_uint(a0.w);
+                            if (t < tr.best.t || (t == tr.best.t && (key_inst > tr.best.inst || (key_inst == tr.best.inst && prim > tr.best.prim)))) {
+                                tr.best.t = t; tr.best.u = u; tr.best.v = v; tr.best.slot = s; tr.best.prim = prim; tr.best.inst = key_inst;
+                                tr.tmax = t;
+                            }
+                        }
+                    }
+                    tr.cur = tr.any_hit ? B2_TRAV_DONE : B2_TRAV_NEEDPOP;
+                }
+            }
+            // ---- pop the next entry that can still hold a closer hit ----
+            if (tr.cur == B2_TRAV_NEEDPOP) {
+                for (;;) {
+                    --tr.sp;
+                    int c = stack[tr.sp];
+                    if (c == B2_TRAV_DONE) { tr.cur = c; break; }
+                    if (c == B2_TRAV_POP) {
+                        if (tr.inst == -2) { tr.inst = -1; tr.cur = (int) sc.tlas_root; break; }
+                        // back to world space: the ray is re-read from the queue
+                        float4 ro, rd;
+                        if (!any_ray) { rd = q.ray_d[item]; ro = q.ray_o[item]; }
+                        else { rd = q.sh_d[item - q.n_slots]; ro = q.sh_o[item - q.n_slots]; }
+                        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+                        tr.set_ray(ray);
+                        tr.inst = -1;
+                        continue;
+                    }
+                    if (sdist[tr.sp] <= tr.tmax * 1.0000004f) { tr.cur = c; break; }
+                }
+            }
+            // ---- finished: write the result, the lane becomes idle ----
+            if (tr.cur == B2_TRAV_DONE) {
+                busy = false;
+                if (!any_ray) {
+                    const Hit &h = tr.best;
+                    q.hit[item] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+                    q.hit_inst[item] = h.inst;
+                    ++n_seg;
+                } else {
+                    const uint32_t j = item - q.n_slots;
+                    const bool occluded = tr.any_hit;
+                    float4 c = q.sh_c[j];
+                    uint32_t lw = __float_as_uint(c.w);
+                    if (lw & SH_FINAL) {
+                        float4 r = q.sh_r[j];
+                        float2 p = WIDE ? q.sh_p[j] : make_float2(0.f, 0.f);
+                        float3 L = v3(r);
+                        if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
+                        uint32_t pix = __float_as_uint(r.w);
+                        uint32_t flags = q.sh_f[j];
+                        bool ok = film_put<WIDE>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
+                        ++n_put; n_bad += ok ? 0 : 1;
+                    } else if (!occluded) {
+                        float4 r = q.res[lw];
+                        r.x += c.x; r.y += c.y; r.z += c.z;
+                        q.res[lw] = r;
+                    }
+                }
+            }
+        }
+    }
+    n_seg = __reduce_add_sync(0xffffffffu, n_seg);
+    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
+    if (lane_id() == 0) {
+        if (n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+        if (n_put) atomicAdd(&q.stats[ST_PUT_SHADOW], (unsigned long long) n_put);
+        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
+        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
+    }
+}
+
 // ---- K1: regenerate — next camera sample of the lane's work item (integrator.cpp:233-262) ------
 // `item`/`left`/`rng` are the lane's work-item state (left == 0: `w` is the freshly fetched work
 // item). Returns false if the work is exhausted (lane retires).
@@ -590,6 +781,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
     const Tables tb = stage_shade_tables(sc, smem_raw);
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t n_put = 0, n_bad = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_FETCH] = 0;       // ray counter of the next k_trace_inst
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         uint32_t lane = base + lane_id();
         // all queue loads are issued up front (one round trip), retired lanes included
