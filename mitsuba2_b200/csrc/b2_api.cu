@@ -494,7 +494,9 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // default wavefront width: a whole number of lanes per thread for every stage kernel
     // (sm_count * 3072 = 3 lanes/thread at 4 CTAs/SM, 4 lanes/thread at 3 CTAs/SM) — and small
     // enough (71 MB of queues on 148 SMs) to stay resident in the 126 MB L2 between the stages
-    uint32_t slots = rp->lane_slots ? rp->lane_slots : (uint32_t) s->sm_count * 3072u;
+    // (instanced scenes: ray cost varies by orders of magnitude, so the launches are made 16x longer to
+    //  amortise their tails — measured 680 -> 890 Msamples/s on the BASELINE lattice)
+    uint32_t slots = rp->lane_slots ? rp->lane_slots : (uint32_t) s->sm_count * 3072u * (s->d.n_instances ? 16u : 1u);
     if ((uint64_t) slots > total64) slots = (uint32_t) std::max<uint64_t>(total64, 1);
     slots = (slots + 31u) & ~31u;
     if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
@@ -556,7 +558,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids
     int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = grid;
-    if (inst) grid_int = s->sm_count * 3;           // k_trace_inst: persistent warps, 3 CTAs/SM resident
+    if (inst) grid_int = s->sm_count * B2_INST_MINBLOCKS;           // k_trace_inst: persistent warps, 3 CTAs/SM resident
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;

@@ -1,4 +1,5 @@
 // b2_bvh.cpp — see b2_bvh.h
+#include <cstdlib>
 #include "b2_bvh.h"
 
 #include <algorithm>
@@ -92,7 +93,7 @@ void b2_build_bvh4(const std::vector<B2BvhTri> &tris, B2Bvh4 &out) {
         for (int v = 0; v < 3; ++v) bx.grow(tris[i].p[v]);
         for (int k = 0; k < 3; ++k) { boxes[i].lo[k] = bx.lo[k]; boxes[i].hi[k] = bx.hi[k]; }
     }
-    b2_build_bvh4_boxes(boxes, 2, out);
+    b2_build_bvh4_boxes(boxes, 2, out);      // (3- and 4-triangle leaves were measured slower on the 9.8k-triangle lattice mesh)
 }
 
 uint32_t b2_bvh4_append(std::vector<float> &dst, const B2Bvh4 &src, uint32_t slot_base) {

@@ -149,7 +149,9 @@ B2_D bool tri_isect(float3 p0, float3 e1, float3 e2, const Ray &ray, float tmax,
 // of the warp are still traversing and the caller can hand new rays to the idle lanes
 // (persistent-warp dynamic ray fetch, Aila & Laine 2009).
 #define B2_TRAV_DONE 0x7fffffff
+#ifndef B2_REFILL_THRESHOLD
 #define B2_REFILL_THRESHOLD 22
+#endif
 
 struct Trav {
     Ray ray;
@@ -511,9 +513,12 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
 #define B2_TRAV_POP 0x7ffffffe
 #define B2_TRAV_NEEDPOP 0x7ffffffd
 #define B2_INST_STACK 64
+#ifndef B2_INST_MINBLOCKS
+#define B2_INST_MINBLOCKS 4
+#endif
 
 template <bool WIDE>
-__global__ void __launch_bounds__(256, 3) k_trace_inst(DScene sc, Queues q, int parity) {
+__global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
     const uint32_t n_shadow = q.cnt[CNT_SHADOW + parity];
@@ -591,7 +596,7 @@ __global__ void __launch_bounds__(256, 3) k_trace_inst(DScene sc, Queues q, int 
                 if (bc != 0) { tr.cur = bc; continue; }
                 tr.cur = B2_TRAV_NEEDPOP;
             }
-            // ---- one leaf ----
+            // ---- one leaf (looping over consecutive leaves here was measured slower) ----
             if (tr.cur < 0) {
                 const uint32_t first = (uint32_t) tr.cur & 0x07ffffffu, count = ((uint32_t) tr.cur >> 27) & 0xfu;
                 if (tr.inst == -1) {
