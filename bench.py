@@ -108,6 +108,16 @@ def run_reference_cli(res, spp, spp_pass, max_depth, threads):
         return t, res * res * spp
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` captures
+# (cold caches: ncu flushes between replays). Launches of the default two-lane-set configuration.
+NCU_TRAFFIC = {
+    ("cbox", "k_shade"): {"bytes": 51105280 + 7729152, "note": "profiles/r01_ncu_full_v3.md: k_shade<0>, one single-set launch of 454656 lanes (the width the "
+                          "stage timers run), final round-1 build"},
+    ("cbox", "k_trace"): {"bytes": 32300800 + 256, "note": "profiles/r01_ncu_full_v3.md: k_trace<0,0>, one single-set launch of 454656 lanes + its shadow queue"},
+    ("grid", "k_trace"): {"bytes": 11925760 + 118272000, "note": "profiles/r01_ncu_grid.md: k_trace<1,0> (before k_trace_inst), 1024x1024 sample"},
+}
+
+
 def run_oracle_port(res, spp, spp_pass, max_depth, threads):
     from mitsuba2_b200 import abi, scenes
     from tests import oracle_lib as O
@@ -136,7 +146,7 @@ def cpu_sample(a, spp):
 def main_reference(a, rank):
     if rank != 0:
         return
-    spp = 4                       # bounded sample per step (~1-3 s of host time)
+    spp = 16                      # bounded sample per step (~4 s of host time on 128 threads)
     for _ in range(min(a.warmup, 1)):
         cpu_sample(a, spp)
     vals = []
@@ -317,7 +327,9 @@ def main_b2pt(a, rank, world, local_rank):
         tot_bytes = sum(n * b for n, b in units.values())
         tot_t = sum(stages[k]["ms"] for k in stages)
         roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak if ach else None, "traffic": None,
+                "frac": ach / peak if ach else None, "traffic": NCU_TRAFFIC.get((a.workload, "k_" + dom), {}).get("bytes"),
+                "traffic_note": NCU_TRAFFIC.get((a.workload, "k_" + dom), {}).get("note"),
+                "achieved_bytes_per_launch": stage_bytes[dom] / max(n_it, 1),
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
                 "all_stages_gbs": tot_bytes / (tot_t * 1e-3) / 1e9 if tot_t > 0 else None,
                 "all_stages_frac": tot_bytes / (tot_t * 1e-3) / 1e9 / peak if tot_t > 0 else None,
@@ -353,7 +365,7 @@ def main_b2pt(a, rank, world, local_rank):
             roof["step_frac"] = roof["step_gbs"] / roof["peak"]
             line["roofline"] = roof; line["stages"] = stages
         if a.cpu_baseline and world == 1 and a.workload == "cbox":
-            line["cpu_baseline"] = cpu_sample(a, 4)
+            line["cpu_baseline"] = cpu_sample(a, 48)      # ~12 s on 128 host threads
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
