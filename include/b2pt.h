@@ -52,12 +52,14 @@ enum {
     B2_ERR_NO_DEVICE = 4    /* no CUDA device: the product path has NO CPU fallback           */
 };
 
-/* ---- BSDF records (src/bsdfs/{diffuse,dielectric,roughconductor}.cpp) ------------------- */
+/* ---- BSDF records (src/bsdfs/{diffuse,dielectric,roughconductor,conductor,plastic}.cpp) --- */
 enum {
     B2_BSDF_DIFFUSE = 0,        /* SmoothDiffuse      diffuse.cpp:78-135                      */
     B2_BSDF_DIELECTRIC = 1,     /* SmoothDielectric   dielectric.cpp:201-320                  */
     B2_BSDF_ROUGHCONDUCTOR = 2, /* RoughConductor     roughconductor.cpp:196-382              */
-    B2_BSDF_NULL = 3            /* reflectance-0 diffuse given to emitters without a BSDF     */
+    B2_BSDF_NULL = 3,           /* reflectance-0 diffuse given to emitters without a BSDF     */
+    B2_BSDF_CONDUCTOR = 4,      /* SmoothConductor    conductor.cpp:197-258                   */
+    B2_BSDF_PLASTIC = 5         /* SmoothPlastic      plastic.cpp:181-314                     */
 };
 enum { B2_MF_BECKMANN = 0, B2_MF_GGX = 1 };   /* MicrofacetType, microfacet.h:27-33          */
 
@@ -72,10 +74,16 @@ typedef struct B2Bsdf {
     float alpha_u;
     float specular_transmittance[3];  /* dielectric, default 1                                */
     float alpha_v;
-    float cond_eta[3];          /* roughconductor complex IOR, real part (default 0)           */
+    float cond_eta[3];          /* (rough)conductor complex IOR, real part (default 0)         */
     float _pad1;
     float cond_k[3];            /* imaginary part (default 1)                                  */
     float _pad2;
+    /* plastic (plastic.cpp:136-180): reflectance = diffuse_reflectance, eta = int_ior / ext_ior, and the
+       values parameters_changed() derives on the host                                           */
+    float fdr_int;              /* fresnel_diffuse_reflectance(1 / eta), fresnel.h:327-361     */
+    float specular_sampling_weight;   /* s_mean / (d_mean + s_mean), plastic.cpp:174           */
+    float inv_eta_2;            /* 1 / eta^2                                                   */
+    int32_t nonlinear;          /* 'nonlinear' (default 0)                                     */
 } B2Bsdf;
 
 /* ---- emitters (src/emitters/{area,envmap,constant}.cpp) --------------------------------- */

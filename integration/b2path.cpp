@@ -23,6 +23,7 @@
 #include <mitsuba/render/scene.h>
 #include <mitsuba/render/sensor.h>
 #include <mitsuba/render/spiral.h>
+#include <mitsuba/render/fresnel.h>
 #include <mitsuba/render/texture.h>
 
 #include <atomic>
@@ -225,7 +226,7 @@ private:
         for (int k = 0; k < 3; ++k) out[k] = v[k];
     }
 
-    /// SmoothDiffuse / SmoothDielectric / RoughConductor -> B2Bsdf, anything else: NotImplemented
+    /// SmoothDiffuse / SmoothDielectric / RoughConductor / SmoothConductor / SmoothPlastic -> B2Bsdf, anything else: NotImplemented
     B2Bsdf convert_bsdf(const BSDF *bsdf, const SurfaceInteraction3f &si) const {
         B2Bsdf b;
         std::memset(&b, 0, sizeof b);
@@ -255,8 +256,25 @@ private:
             eval3(obj("k"), si, b.cond_k, 1.f);
             eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
             if (!b.sample_visible) NotImplementedError("b2path: roughconductor with sample_visible=false");
+        } else if (cls == "SmoothConductor") {                       // conductor.cpp:160-176, 247-251
+            b.type = B2_BSDF_CONDUCTOR;
+            eval3(obj("eta"), si, b.cond_eta, 0.f);
+            eval3(obj("k"), si, b.cond_k, 1.f);
+            eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
+        } else if (cls == "SmoothPlastic") {                         // plastic.cpp:136-180, 295-301
+            b.type = B2_BSDF_PLASTIC;
+            b.eta = pc.get_float("eta", 1.49f / 1.000277f);
+            eval3(obj("diffuse_reflectance"), si, b.reflectance, .5f);
+            eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
+            // the values parameters_changed() derives (:162-176), with the reference's own functions
+            b.inv_eta_2 = 1.f / (b.eta * b.eta);
+            b.fdr_int = fresnel_diffuse_reflectance(1.f / b.eta);
+            float d_mean = obj("diffuse_reflectance") ? ((Texture *) obj("diffuse_reflectance"))->mean() : .5f,
+                  s_mean = obj("specular_reflectance") ? ((Texture *) obj("specular_reflectance"))->mean() : 1.f;
+            b.specular_sampling_weight = s_mean / (d_mean + s_mean);
+            b.nonlinear = bsdf->to_string().find("nonlinear = 1") != std::string::npos ? 1 : 0;   // only printed
         } else {
-            Throw("b2path: BSDF \"%s\" is not supported (diffuse, dielectric, roughconductor are)", cls);
+            Throw("b2path: BSDF \"%s\" is not supported (diffuse, dielectric, roughconductor, conductor, plastic are)", cls);
         }
         return b;
     }

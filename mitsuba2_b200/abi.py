@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 B2_OK, B2_ERR_INVALID, B2_ERR_CUDA, B2_ERR_CANCELLED, B2_ERR_NO_DEVICE = range(5)
-BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL = range(4)
+BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL, BSDF_CONDUCTOR, BSDF_PLASTIC = range(6)
 MF_BECKMANN, MF_GGX = 0, 1
 EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT = range(3)
 FILTER_RESOLUTION = 31
@@ -25,6 +25,7 @@ class B2Bsdf(C.Structure):
         ("specular_transmittance", C.c_float * 3), ("alpha_v", C.c_float),
         ("cond_eta", C.c_float * 3), ("_pad1", C.c_float),
         ("cond_k", C.c_float * 3), ("_pad2", C.c_float),
+        ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("inv_eta_2", C.c_float), ("nonlinear", C.c_int32),
     ]
 
 
@@ -120,6 +121,29 @@ def render_params(max_depth=6, rr_depth=5, spp=16, samples_per_pass=0, block_siz
                           flags, 0)
 
 
+def fresnel_diffuse_reflectance(eta):
+    """include/mitsuba/render/fresnel.h:327-361 in fp32 (left-to-right evaluation, no contraction)."""
+    f = np.float32
+    eta = f(eta)
+    if eta < f(1):
+        return f(f(f(f(-1.4399) * f(eta * eta)) + f(f(0.7099) * eta)) + f(0.6681)) + f(f(0.0636) / eta)
+    i1 = f(1) / eta; i2 = f(i1 * i1); i3 = f(i2 * i1); i4 = f(i3 * i1); i5 = f(i4 * i1)
+    r = f(f(0.919317) - f(f(3.4793) * i1))
+    r = f(r + f(f(6.75335) * i2)); r = f(r - f(f(7.80989) * i3)); r = f(r + f(f(4.98554) * i4)); r = f(r - f(f(1.36881) * i5))
+    return r
+
+
+def _rgb_mean(c):
+    """Texture::mean() of a constant rgb / uniform texture (srgb.cpp:52-57: hsum * (1/3); uniform: the value)."""
+    f = np.float32
+    if np.isscalar(c):
+        return f(c)
+    c = [f(x) for x in c]
+    if c[0] == c[1] == c[2]:
+        pass
+    return f(f(f(c[0] + c[1]) + c[2]) * f(f(1) / f(3)))
+
+
 class SceneBuffers:
     """Owns the numpy arrays behind a B2SceneDesc (keeps them alive) — the host-side
     flattening of Mitsuba's Scene object graph (scene.cpp:23-59, mesh.h:344-361)."""
@@ -157,6 +181,34 @@ class SceneBuffers:
         b.alpha_u = alpha; b.alpha_v = alpha if alpha_v is None else alpha_v
         b.cond_eta[:] = eta; b.cond_k[:] = k
         b.specular_reflectance[:] = specular_reflectance; b.specular_transmittance[:] = (1, 1, 1)
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def add_conductor(self, eta=(0, 0, 0), k=(1, 1, 1), specular_reflectance=(1, 1, 1)):
+        """SmoothConductor (conductor.cpp:160-176); material 'none' = eta 0, k 1 (a perfect mirror)."""
+        b = B2Bsdf(); b.type = BSDF_CONDUCTOR
+        b.cond_eta[:] = eta; b.cond_k[:] = k
+        b.specular_reflectance[:] = specular_reflectance; b.specular_transmittance[:] = (1, 1, 1)
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def add_plastic(self, diffuse_reflectance=(0.5, 0.5, 0.5), int_ior=1.49, ext_ior=1.000277, specular_reflectance=None,
+                    nonlinear=False):
+        """SmoothPlastic (plastic.cpp:136-180), with the host-side values of parameters_changed()
+        (:162-176) computed in fp32 like the reference: 1/eta^2, the diffuse Fresnel reflectance fit
+        (fresnel.h:327-361) and the specular sampling weight from the textures' means
+        (srgb.cpp:52-57: hmean of the rgb triple; uniform.cpp: the value)."""
+        f = np.float32
+        b = B2Bsdf(); b.type = BSDF_PLASTIC
+        eta = f(int_ior) / f(ext_ior)
+        b.eta = float(eta)
+        b.inv_eta_2 = float(f(1) / (eta * eta))
+        b.fdr_int = float(fresnel_diffuse_reflectance(f(1) / eta))
+        b.reflectance[:] = diffuse_reflectance
+        b.specular_reflectance[:] = (1, 1, 1) if specular_reflectance is None else specular_reflectance
+        b.specular_transmittance[:] = (1, 1, 1)
+        d_mean = _rgb_mean(diffuse_reflectance)
+        s_mean = f(1) if specular_reflectance is None else _rgb_mean(specular_reflectance)
+        b.specular_sampling_weight = float(s_mean / (d_mean + s_mean))
+        b.nonlinear = 1 if nonlinear else 0
         self.bsdfs.append(b); return len(self.bsdfs) - 1
 
     def add_area_emitter(self, mesh_index, radiance):

@@ -312,7 +312,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
     for (const B2Bsdf &b : bsdfs) {
         if (b.type == B2_BSDF_ROUGHCONDUCTOR) s->features |= F_ROUGH;
-        if (b.type == B2_BSDF_DIELECTRIC) s->features |= F_DIELECTRIC;
+        if (b.type == B2_BSDF_DIELECTRIC || b.type == B2_BSDF_CONDUCTOR || b.type == B2_BSDF_PLASTIC) s->features |= F_DIELECTRIC;
     }
     if (desc->film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f) s->features |= F_WIDE;
     d.instances = desc->n_instances ? s->instances.p : nullptr; d.inst_order = s->inst_order.p;

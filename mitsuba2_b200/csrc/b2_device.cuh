@@ -286,8 +286,21 @@ B2_D float3 mf_sample(const MF &d, float3 wi, float sx, float sy, float &pdf) { 
     return m;
 }
 
-// ---- BSDFs (src/bsdfs/{diffuse,dielectric,roughconductor}.cpp) --------------------------------
-template <uint32_t F> B2_D bool bsdf_is_smooth(const B2Bsdf &b) { return !(F & F_DIELECTRIC) || b.type != B2_BSDF_DIELECTRIC; }   // path.cpp:155
+// ---- BSDFs (src/bsdfs/{diffuse,dielectric,roughconductor,conductor,plastic}.cpp) --------------
+// F_DIELECTRIC marks scenes with any of the BSDFs that have a delta lobe (dielectric, conductor, plastic)
+template <uint32_t F> B2_D bool bsdf_is_smooth(const B2Bsdf &b) {     // has_flag(flags, Smooth), path.cpp:155
+    return !(F & F_DIELECTRIC) || (b.type != B2_BSDF_DIELECTRIC && b.type != B2_BSDF_CONDUCTOR);
+}
+// SmoothPlastic: diffuse_reflectance / (1 - fdr_int), optional nonlinear variant (plastic.cpp:231-232, 262-263)
+B2_D float3 plastic_diffuse(const B2Bsdf &b) {
+    float3 d = v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+    if (b.nonlinear)
+        return v3(d.x / (1.f - d.x * b.fdr_int), d.y / (1.f - d.y * b.fdr_int), d.z / (1.f - d.z * b.fdr_int));
+    return d * (1.f / (1.f - b.fdr_int));
+}
+B2_D float fresnel_r(float cos_theta_i, float eta) {
+    float r, ct, eit, eti; fresnel(cos_theta_i, eta, r, ct, eit, eti); return r;
+}
 
 B2_D float3 rgb3(const float *p) { return v3(p[0], p[1], p[2]); }
 
@@ -313,7 +326,14 @@ template <uint32_t F> B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float
             float3 res = v3(result * b.specular_reflectance[0], result * b.specular_reflectance[1], result * b.specular_reflectance[2]);
             return Fr * res;
         } else return zero;
-        default: return zero;                                       // dielectric.cpp:312-315
+        case B2_BSDF_PLASTIC: if constexpr ((F & F_DIELECTRIC) != 0) {     // plastic.cpp:242-266
+            if (!(cti > 0.f && cto > 0.f)) return zero;
+            float f_i = fresnel_r(cti, b.eta), f_o = fresnel_r(cto, b.eta);
+            float3 diff = plastic_diffuse(b);
+            float s = (B2_INV_PI * cto) * b.inv_eta_2 * (1.f - f_i) * (1.f - f_o);
+            return diff * s;
+        } else return zero;
+        default: return zero;                                       // dielectric.cpp:312-315, conductor.cpp:242-245
     }
 }
 template <uint32_t F> B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 wo) {
@@ -326,6 +346,14 @@ template <uint32_t F> B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 
             if (!(cti > 0.f && cto > 0.f && dot(si.wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
             MF d = mf_make(b);
             return mf_eval(d, m) * mf_smith_g1(d, si.wi, m) / (4.f * cti);
+        } else return 0.f;
+        case B2_BSDF_PLASTIC: if constexpr ((F & F_DIELECTRIC) != 0) {     // plastic.cpp:268-293
+            if (!(cti > 0.f && cto > 0.f)) return 0.f;
+            float f_i = fresnel_r(cti, b.eta);
+            float prob_specular = f_i * b.specular_sampling_weight;
+            float prob_diffuse = (1.f - f_i) * (1.f - b.specular_sampling_weight);
+            prob_diffuse = prob_diffuse / (prob_specular + prob_diffuse);
+            return (B2_INV_PI * cto) * prob_diffuse;
         } else return 0.f;
         default: return 0.f;
     }
@@ -377,6 +405,35 @@ template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, flo
                            fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
             float3 wv = v3(weight * b.specular_reflectance[0], weight * b.specular_reflectance[1], weight * b.specular_reflectance[2]);
             return active ? Fr * wv : zero;
+        } else return zero;
+        case B2_BSDF_CONDUCTOR: if constexpr ((F & F_DIELECTRIC) != 0) {   // conductor.cpp:197-240
+            if (!(cti > 0.f)) return zero;
+            bs.wo = v3(-si.wi.x, -si.wi.y, si.wi.z);                 // reflect(wi), fresnel.h:276-278
+            bs.eta = 1.f; bs.pdf = 1.f; bs.delta = true;
+            float3 Fr = v3(fresnel_conductor(cti, b.cond_eta[0], b.cond_k[0]), fresnel_conductor(cti, b.cond_eta[1], b.cond_k[1]),
+                           fresnel_conductor(cti, b.cond_eta[2], b.cond_k[2]));
+            return rgb3(b.specular_reflectance) * Fr;
+        } else return zero;
+        case B2_BSDF_PLASTIC: if constexpr ((F & F_DIELECTRIC) != 0) {     // plastic.cpp:181-240
+            if (!(cti > 0.f)) return zero;
+            float f_i = fresnel_r(cti, b.eta);
+            float prob_specular = f_i * b.specular_sampling_weight;
+            float prob_diffuse = (1.f - f_i) * (1.f - b.specular_sampling_weight);
+            prob_specular = prob_specular / (prob_specular + prob_diffuse);
+            prob_diffuse = 1.f - prob_specular;
+            bs.eta = 1.f;
+            if (sample1 < prob_specular) {
+                bs.wo = v3(-si.wi.x, -si.wi.y, si.wi.z);
+                bs.pdf = prob_specular; bs.delta = true;
+                float value = f_i / bs.pdf;
+                return v3(value * b.specular_reflectance[0], value * b.specular_reflectance[1], value * b.specular_reflectance[2]);
+            }
+            bs.wo = square_to_cosine_hemisphere(s2x, s2y);
+            bs.pdf = prob_diffuse * (B2_INV_PI * bs.wo.z);
+            float f_o = fresnel_r(bs.wo.z, b.eta);
+            float3 value = plastic_diffuse(b);
+            float s = b.inv_eta_2 * (1.f - f_i) * (1.f - f_o) / prob_diffuse;
+            return value * s;
         } else return zero;
         default: return zero;
     }

@@ -783,7 +783,19 @@ static inline v3 mf_sample(const omf *d, v3 wi, float sx, float sy, float *pdf) 
 typedef struct { v3 wo; float pdf, eta; int delta; } obs;
 
 static inline int bsdf_is_smooth(const B2Bsdf *b) {   /* has_flag(flags, BSDFFlags::Smooth), path.cpp:155 */
-    return b->type != B2_BSDF_DIELECTRIC;
+    return b->type != B2_BSDF_DIELECTRIC && b->type != B2_BSDF_CONDUCTOR;    /* delta-only BSDFs */
+}
+
+/* SmoothPlastic: diffuse_reflectance / (1 - fdr_int) with the optional nonlinear variant (plastic.cpp:231-232, 262-263).
+ * Spectrum /= scalar multiplies by the reciprocal; Spectrum / Spectrum divides. */
+static inline v3 plastic_diffuse(const B2Bsdf *b) {
+    v3 d = v3_make(b->reflectance[0], b->reflectance[1], b->reflectance[2]);
+    if (b->nonlinear)
+        return v3_make(d.x / (1.f - d.x * b->fdr_int), d.y / (1.f - d.y * b->fdr_int), d.z / (1.f - d.z * b->fdr_int));
+    return v3_scale(d, 1.f / (1.f - b->fdr_int));
+}
+static inline float fresnel_r(float cos_theta_i, float eta) {
+    float r, ct, eit, eti; fresnel(cos_theta_i, eta, &r, &ct, &eit, &eti); return r;
 }
 
 static v3 bsdf_eval(const B2Bsdf *b, const osi *si, v3 wo) {
@@ -811,7 +823,14 @@ static v3 bsdf_eval(const B2Bsdf *b, const osi *si, v3 wo) {
                              result * b->specular_reflectance[2]);
             return v3_mul(F, res);
         }
-        default: return zero;                                              /* dielectric.cpp:312-315 */
+        case B2_BSDF_PLASTIC: {                                            /* plastic.cpp:242-266 */
+            if (!(cti > 0.f && cto > 0.f)) return zero;
+            float f_i = fresnel_r(cti, b->eta), f_o = fresnel_r(cto, b->eta);
+            v3 diff = plastic_diffuse(b);
+            float s = (B2O_INV_PI * cto) * b->inv_eta_2 * (1.f - f_i) * (1.f - f_o);
+            return v3_scale(diff, s);
+        }
+        default: return zero;                                              /* dielectric.cpp:312-315, conductor.cpp:242-245 */
     }
 }
 static float bsdf_pdf(const B2Bsdf *b, const osi *si, v3 wo) {
@@ -824,6 +843,14 @@ static float bsdf_pdf(const B2Bsdf *b, const osi *si, v3 wo) {
             if (!(cti > 0.f && cto > 0.f && v3_dot(si->wi, m) > 0.f && v3_dot(wo, m) > 0.f)) return 0.f;
             omf d = mf_make(b);
             return mf_eval(&d, m) * mf_smith_g1(&d, si->wi, m) / (4.f * cti);
+        }
+        case B2_BSDF_PLASTIC: {                                            /* plastic.cpp:268-293 */
+            if (!(cti > 0.f && cto > 0.f)) return 0.f;
+            float f_i = fresnel_r(cti, b->eta);
+            float prob_specular = f_i * b->specular_sampling_weight;
+            float prob_diffuse = (1.f - f_i) * (1.f - b->specular_sampling_weight);
+            prob_diffuse = prob_diffuse / (prob_specular + prob_diffuse);
+            return (B2O_INV_PI * cto) * prob_diffuse;
         }
         default: return 0.f;
     }
@@ -877,6 +904,36 @@ static v3 bsdf_sample(const B2Bsdf *b, const osi *si, float sample1, float s2x, 
             v3 wv = v3_make(weight * b->specular_reflectance[0], weight * b->specular_reflectance[1],
                             weight * b->specular_reflectance[2]);
             return active ? v3_mul(F, wv) : zero;
+        }
+        case B2_BSDF_CONDUCTOR: {                                          /* conductor.cpp:197-240 */
+            if (!(cti > 0.f)) return zero;
+            bs->wo = v3_make(-si->wi.x, -si->wi.y, si->wi.z);              /* reflect(wi), fresnel.h:276-278 */
+            bs->eta = 1.f; bs->pdf = 1.f; bs->delta = 1;
+            v3 F = v3_make(fresnel_conductor(cti, b->cond_eta[0], b->cond_k[0]),
+                           fresnel_conductor(cti, b->cond_eta[1], b->cond_k[1]),
+                           fresnel_conductor(cti, b->cond_eta[2], b->cond_k[2]));
+            return v3_mul(v3_make(b->specular_reflectance[0], b->specular_reflectance[1], b->specular_reflectance[2]), F);
+        }
+        case B2_BSDF_PLASTIC: {                                            /* plastic.cpp:181-240 */
+            if (!(cti > 0.f)) return zero;
+            float f_i = fresnel_r(cti, b->eta);
+            float prob_specular = f_i * b->specular_sampling_weight;
+            float prob_diffuse = (1.f - f_i) * (1.f - b->specular_sampling_weight);
+            prob_specular = prob_specular / (prob_specular + prob_diffuse);
+            prob_diffuse = 1.f - prob_specular;
+            bs->eta = 1.f;
+            if (sample1 < prob_specular) {
+                bs->wo = v3_make(-si->wi.x, -si->wi.y, si->wi.z);
+                bs->pdf = prob_specular; bs->delta = 1;
+                float value = f_i / bs->pdf;
+                return v3_make(value * b->specular_reflectance[0], value * b->specular_reflectance[1], value * b->specular_reflectance[2]);
+            }
+            bs->wo = square_to_cosine_hemisphere(s2x, s2y);
+            bs->pdf = prob_diffuse * (B2O_INV_PI * bs->wo.z); bs->delta = 0;
+            float f_o = fresnel_r(bs->wo.z, b->eta);
+            v3 value = plastic_diffuse(b);
+            float s = b->inv_eta_2 * (1.f - f_i) * (1.f - f_o) / prob_diffuse;
+            return v3_scale(value, s);
         }
         default: return zero;
     }

@@ -301,6 +301,13 @@ def run_reference(xml_fn, threads=None):
 DIELECTRIC = '<bsdf type="dielectric"><float name="int_ior" value="1.5"/><float name="ext_ior" value="1.0"/></bsdf>'
 ROUGH_GGX = '<bsdf type="roughconductor"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/></bsdf>'
 ROUGH_BECK = '<bsdf type="roughconductor"><float name="alpha" value="0.2"/></bsdf>'
+CONDUCTOR = '<bsdf type="conductor"><rgb name="eta" value="0.2, 0.92, 1.1"/><rgb name="k" value="3.9, 2.45, 2.14"/></bsdf>'
+MIRROR = '<bsdf type="conductor"><rgb name="specular_reflectance" value="0.9, 0.8, 0.7"/></bsdf>'     # material "none"
+PLASTIC = '<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.1, 0.27, 0.36"/><float name="int_ior" value="1.9"/></bsdf>'
+PLASTIC_SPEC = ('<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.7, 0.6, 0.5"/>'
+                '<rgb name="specular_reflectance" value="0.8, 0.9, 1.0"/><float name="int_ior" value="1.49"/>'
+                '<float name="ext_ior" value="1.000277"/></bsdf>')
+PLASTIC_NONLINEAR = ('<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.8, 0.3, 0.2"/><boolean name="nonlinear" value="true"/></bsdf>')
 
 # exact-in-fp32 instance transforms: identity, half-size copy, 90-degree rotation about y (floating),
 # mirrored copy (floating)
@@ -333,6 +340,9 @@ GOLDEN = {
     "cbox_64_spp16_env_ggx": dict(width=64, height=64, spp=16, envmap="only", materials={"box": ROUGH_GGX}),
     "cbox_64_spp16_ggx": dict(width=64, height=64, spp=16, materials={"box": ROUGH_GGX}),
     "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
+    # smooth conductor / plastic
+    "cbox_64_spp16_conductor": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": CONDUCTOR, "green": MIRROR}),
+    "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
 
 

@@ -2,6 +2,7 @@
 rebuild each scene + render parameters on our side."""
 import ast
 import os
+import re
 
 import numpy as np
 
@@ -11,18 +12,34 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 GOLDEN = os.path.join(HERE, "golden")
 
 
+def _rgb(xml, name, default=None):
+    m = re.search(r'<rgb name="%s" value="([^"]+)"' % name, xml)
+    return tuple(float(x) for x in m.group(1).split(",")) if m else default
+
+
+def _float(xml, name, default):
+    m = re.search(r'<float name="%s" value="([^"]+)"' % name, xml)
+    return float(m.group(1)) if m else default
+
+
+def _material(xml):
+    """The XML fragments of tests/golden/make_golden.py -> SceneBuffers.add_* calls (plugin defaults as in the reference)."""
+    if 'type="dielectric"' in xml:
+        return lambda sb: sb.add_dielectric(_float(xml, "int_ior", 1.5046), _float(xml, "ext_ior", 1.000277))
+    if 'type="roughconductor"' in xml:
+        return lambda sb: sb.add_roughconductor(alpha=_float(xml, "alpha", 0.1), distribution="ggx" if 'value="ggx"' in xml else "beckmann")
+    if 'type="conductor"' in xml:
+        return lambda sb: sb.add_conductor(eta=_rgb(xml, "eta", (0, 0, 0)), k=_rgb(xml, "k", (1, 1, 1)),
+                                           specular_reflectance=_rgb(xml, "specular_reflectance", (1, 1, 1)))
+    if 'type="plastic"' in xml:
+        return lambda sb: sb.add_plastic(_rgb(xml, "diffuse_reflectance", (0.5, 0.5, 0.5)), _float(xml, "int_ior", 1.49),
+                                         _float(xml, "ext_ior", 1.000277), _rgb(xml, "specular_reflectance"),
+                                         nonlinear='name="nonlinear" value="true"' in xml)
+    raise ValueError(xml)
+
+
 def _materials(spec):
-    if not spec:
-        return None
-    out = {}
-    for name, xml in spec.items():
-        if 'type="dielectric"' in xml:
-            out[name] = lambda sb: sb.add_dielectric(1.5, 1.0)
-        elif 'value="ggx"' in xml:
-            out[name] = lambda sb: sb.add_roughconductor(alpha=0.1, distribution="ggx")
-        else:
-            out[name] = lambda sb: sb.add_roughconductor(alpha=0.2, distribution="beckmann")
-    return out
+    return {name: _material(xml) for name, xml in spec.items()} if spec else None
 
 
 def nopatch_meshes():

@@ -62,3 +62,31 @@ def test_plugin_dropin_matches_reference_path(tmp_path):
     s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
     # shipped cbox has coplanar geometry (DESIGN.md 'Float parity'): flip-robust statistics
     assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
+
+
+MATERIALS = {
+    "box": '<bsdf type="plastic" id="box"><rgb name="diffuse_reflectance" value="0.1, 0.27, 0.36"/><float name="int_ior" value="1.9"/></bsdf>',
+    "green": '<bsdf type="conductor" id="green"><rgb name="eta" value="0.2, 0.92, 1.1"/><rgb name="k" value="3.9, 2.45, 2.14"/></bsdf>',
+    "red": '<bsdf type="roughconductor" id="red"><string name="distribution" value="ggx"/><float name="alpha" value="0.15"/></bsdf>',
+}
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_plugin_dropin_materials(tmp_path):
+    """Same, with plastic / conductor / roughconductor BSDFs instantiated by the reference's own plugins and
+    converted by the adapter (parameters_changed() values taken from the reference's functions)."""
+    import re
+    from tests import golden_cases as G
+
+    def xml(integrator):
+        x = _scene_xml(integrator)
+        for k, v in MATERIALS.items():
+            x = re.sub(r'<bsdf type="diffuse" id="%s">.*?</bsdf>' % k, v, x, count=1)
+        return x
+    r0, ref_out = _run(xml("path"), tmp_path, "ref_m")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, b2_out = _run(xml("b2path"), tmp_path, "b2_m")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
