@@ -67,7 +67,8 @@ typedef struct B2Bsdf {
     int32_t type;               /* B2_BSDF_*                                                   */
     int32_t distribution;       /* B2_MF_* (roughconductor)                                    */
     int32_t sample_visible;     /* roughconductor 'sample_visible' (default 1)                 */
-    int32_t _pad;
+    int32_t reflectance_texture;/* 0: 'reflectance' is the constant below; k > 0: B2SceneDesc.textures[k-1]
+                                   (diffuse 'reflectance', plastic 'diffuse_reflectance')        */
     float reflectance[3];       /* diffuse 'reflectance' (constant rgb texture)                */
     float eta;                  /* dielectric int_ior / ext_ior                                */
     float specular_reflectance[3];    /* dielectric / roughconductor, default 1               */
@@ -85,6 +86,22 @@ typedef struct B2Bsdf {
     float inv_eta_2;            /* 1 / eta^2                                                   */
     int32_t nonlinear;          /* 'nonlinear' (default 0)                                     */
 } B2Bsdf;
+
+/* ---- textures (src/textures/{checkerboard,bitmap}.cpp), evaluated at si.uv ----------------- */
+enum { B2_TEX_CHECKERBOARD = 0, B2_TEX_BITMAP = 1 };
+enum { B2_TEXFILTER_NEAREST = 0, B2_TEXFILTER_BILINEAR = 1 };         /* bitmap.cpp:77 */
+enum { B2_WRAP_REPEAT = 0, B2_WRAP_MIRROR = 1, B2_WRAP_CLAMP = 2 };   /* bitmap.cpp:78 */
+
+typedef struct B2Texture {
+    int32_t type;               /* B2_TEX_*                                                    */
+    int32_t filter, wrap;       /* bitmap 'filter_type' (default bilinear), 'wrap_mode' (repeat) */
+    int32_t width, height;      /* bitmap resolution                                           */
+    int32_t channels;           /* bitmap: 1 (Y) or 3 (linear RGB), bitmap.cpp:121-141         */
+    float to_uv[9];             /* row-major 3x3, ScalarTransform3f m_transform ('to_uv')      */
+    float color0[3], color1[3]; /* checkerboard 'color0' (default .4) / 'color1' (.2), constant */
+    const float *data;          /* bitmap texels as the reference holds them after conversion:
+                                   height x width x channels fp32, row-major                   */
+} B2Texture;
 
 /* ---- emitters (src/emitters/{area,envmap,constant}.cpp) --------------------------------- */
 enum { B2_EMITTER_AREA = 0, B2_EMITTER_ENVMAP = 1, B2_EMITTER_CONSTANT = 2 };
@@ -148,6 +165,7 @@ typedef struct B2SceneDesc {
     uint32_t n_top_meshes;              /* meshes [0, n_top_meshes) are top-level shapes       */
     B2Sensor sensor;
     B2Film film;
+    uint32_t n_textures; const B2Texture *textures;
 } B2SceneDesc;
 
 /* ---- render parameters (integrator.cpp:23-40, sampler.cpp:20-30) ------------------------ */

@@ -19,13 +19,27 @@ FLAG_SINGLE_SET = 2
 
 class B2Bsdf(C.Structure):
     _fields_ = [
-        ("type", C.c_int32), ("distribution", C.c_int32), ("sample_visible", C.c_int32), ("_pad", C.c_int32),
+        ("type", C.c_int32), ("distribution", C.c_int32), ("sample_visible", C.c_int32), ("reflectance_texture", C.c_int32),
         ("reflectance", C.c_float * 3), ("eta", C.c_float),
         ("specular_reflectance", C.c_float * 3), ("alpha_u", C.c_float),
         ("specular_transmittance", C.c_float * 3), ("alpha_v", C.c_float),
         ("cond_eta", C.c_float * 3), ("_pad1", C.c_float),
         ("cond_k", C.c_float * 3), ("_pad2", C.c_float),
         ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("inv_eta_2", C.c_float), ("nonlinear", C.c_int32),
+    ]
+
+
+TEX_CHECKERBOARD, TEX_BITMAP = range(2)
+TEXFILTER_NEAREST, TEXFILTER_BILINEAR = range(2)
+WRAP_REPEAT, WRAP_MIRROR, WRAP_CLAMP = range(3)
+
+
+class B2Texture(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("filter", C.c_int32), ("wrap", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32), ("channels", C.c_int32),
+        ("to_uv", C.c_float * 9), ("color0", C.c_float * 3), ("color1", C.c_float * 3),
+        ("data", C.POINTER(C.c_float)),
     ]
 
 
@@ -79,6 +93,7 @@ class B2SceneDesc(C.Structure):
         ("n_instances", C.c_uint32), ("instances", C.POINTER(B2Instance)),
         ("n_top_meshes", C.c_uint32),
         ("sensor", B2Sensor), ("film", B2Film),
+        ("n_textures", C.c_uint32), ("textures", C.POINTER(B2Texture)),
     ]
 
 
@@ -159,9 +174,9 @@ class SceneBuffers:
         self._keep = []
 
     # -- BSDF / emitter constructors with the reference plugins' defaults --------------------
-    def add_diffuse(self, reflectance=(0.5, 0.5, 0.5)):
+    def add_diffuse(self, reflectance=(0.5, 0.5, 0.5), texture=0):
         b = B2Bsdf(); b.type = BSDF_DIFFUSE
-        b.reflectance[:] = reflectance
+        b.reflectance[:] = reflectance; b.reflectance_texture = texture
         b.specular_reflectance[:] = (1, 1, 1); b.specular_transmittance[:] = (1, 1, 1)
         self.bsdfs.append(b); return len(self.bsdfs) - 1
 
@@ -191,7 +206,7 @@ class SceneBuffers:
         self.bsdfs.append(b); return len(self.bsdfs) - 1
 
     def add_plastic(self, diffuse_reflectance=(0.5, 0.5, 0.5), int_ior=1.49, ext_ior=1.000277, specular_reflectance=None,
-                    nonlinear=False):
+                    nonlinear=False, texture=0):
         """SmoothPlastic (plastic.cpp:136-180), with the host-side values of parameters_changed()
         (:162-176) computed in fp32 like the reference: 1/eta^2, the diffuse Fresnel reflectance fit
         (fresnel.h:327-361) and the specular sampling weight from the textures' means
@@ -205,7 +220,8 @@ class SceneBuffers:
         b.reflectance[:] = diffuse_reflectance
         b.specular_reflectance[:] = (1, 1, 1) if specular_reflectance is None else specular_reflectance
         b.specular_transmittance[:] = (1, 1, 1)
-        d_mean = _rgb_mean(diffuse_reflectance)
+        d_mean = self._tex_mean[texture - 1] if texture else _rgb_mean(diffuse_reflectance)
+        b.reflectance_texture = texture
         s_mean = f(1) if specular_reflectance is None else _rgb_mean(specular_reflectance)
         b.specular_sampling_weight = float(s_mean / (d_mean + s_mean))
         b.nonlinear = 1 if nonlinear else 0
@@ -233,11 +249,45 @@ class SceneBuffers:
         self.emitters.append(e)
         return len(self.emitters) - 1
 
-    def add_mesh(self, positions, faces, normals=None, bsdf=0):
+    # -- textures (1-based handles; pass as texture= to add_diffuse / add_plastic) ---------------
+    def _add_texture(self, t, to_uv, mean):
+        m = np.eye(3, dtype=np.float32) if to_uv is None else np.asarray(to_uv, np.float32).reshape(3, 3)
+        t.to_uv[:] = [float(x) for x in m.reshape(-1)]
+        if not hasattr(self, "textures"):
+            self.textures = []; self._tex_mean = []
+        self.textures.append(t); self._tex_mean.append(np.float32(mean))
+        return len(self.textures)
+
+    def add_checkerboard(self, color0=(0.4, 0.4, 0.4), color1=(0.2, 0.2, 0.2), to_uv=None):
+        """Checkerboard (src/textures/checkerboard.cpp:40-44), constant colours; mean() :82-84."""
+        t = B2Texture(); t.type = TEX_CHECKERBOARD
+        t.color0[:] = color0; t.color1[:] = color1
+        return self._add_texture(t, to_uv, np.float32(0.5) * (_rgb_mean(color0) + _rgb_mean(color1)))
+
+    def add_bitmap(self, data, filter_type="bilinear", wrap_mode="repeat", to_uv=None):
+        """BitmapTexture (src/textures/bitmap.cpp): data = float32 [H, W] or [H, W, 3], linear, as the
+        reference holds it after Bitmap::convert; mean() is the mean luminance accumulated in double (:159-205)."""
+        d = np.ascontiguousarray(data, np.float32)
+        if d.ndim == 2:
+            d = d[..., None]
+        t = B2Texture(); t.type = TEX_BITMAP
+        t.filter = TEXFILTER_NEAREST if filter_type == "nearest" else TEXFILTER_BILINEAR
+        t.wrap = {"repeat": WRAP_REPEAT, "mirror": WRAP_MIRROR, "clamp": WRAP_CLAMP}[wrap_mode]
+        t.height, t.width, t.channels = d.shape
+        t.data = fptr(d)
+        if not hasattr(self, "_tex_data"):
+            self._tex_data = []
+        self._tex_data.append(d)
+        lum = d[..., 0] if d.shape[2] == 1 else (np.float32(0.212671) * d[..., 0] + np.float32(0.715160) * d[..., 1]
+                                                  + np.float32(0.072169) * d[..., 2])
+        return self._add_texture(t, to_uv, np.float32(lum.astype(np.float64).mean()))
+
+    def add_mesh(self, positions, faces, normals=None, bsdf=0, texcoords=None):
         m = dict(positions=np.ascontiguousarray(positions, np.float32).reshape(-1, 3),
                  faces=np.ascontiguousarray(faces, np.uint32).reshape(-1, 3),
                  normals=None if normals is None else np.ascontiguousarray(normals, np.float32).reshape(-1, 3),
-                 bsdf=bsdf, emitter=-1)
+                 bsdf=bsdf, emitter=-1,
+                 texcoords=None if texcoords is None else np.ascontiguousarray(texcoords, np.float32).reshape(-1, 2))
         self.meshes.append(m); return len(self.meshes) - 1
 
     def add_shapegroup(self, mesh_indices):
@@ -268,7 +318,7 @@ class SceneBuffers:
             ms[new].n_vertices = len(m["positions"]); ms[new].n_faces = len(m["faces"])
             ms[new].positions = fptr(m["positions"])
             ms[new].normals = fptr(m["normals"]) if m["normals"] is not None else None
-            ms[new].texcoords = None
+            ms[new].texcoords = fptr(m["texcoords"]) if m.get("texcoords") is not None else None
             ms[new].faces = uptr(m["faces"])
             ms[new].bsdf = m["bsdf"]; ms[new].emitter = m["emitter"]
         bs = (B2Bsdf * max(1, len(self.bsdfs)))(*self.bsdfs)
@@ -293,5 +343,8 @@ class SceneBuffers:
         d.n_instances = len(self.instances); d.instances = ins if self.instances else None
         d.n_top_meshes = n_top
         d.sensor = self.sensor; d.film = self.film
-        self._keep = [ms, bs, es, gf, ins]
+        texs = getattr(self, "textures", [])
+        ts = (B2Texture * max(1, len(texs)))(*texs)
+        d.n_textures = len(texs); d.textures = ts if texs else None
+        self._keep = [ms, bs, es, gf, ins, ts]
         return d

@@ -76,7 +76,8 @@ struct B2Scene {
     DBuf<float> env_levels;
     DBuf<uint32_t> inst_order;
     DBuf<int32_t> hit_inst;
-    DBuf<unsigned char> blob;       // tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters
+    DBuf<unsigned char> blob;       // tri_pos | tri_nrm | prim_to_slot | cdf | bsdfs | emitters | tri_uv | textures
+    DBuf<float> tex_data;           // bitmap texels
     int shade_smem_bytes = 0;
     uint32_t features = 0;          // F_* of this scene
     uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
@@ -224,6 +225,9 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
 
     std::vector<float4> tri_pos(3 * (size_t) nt), tri_nrm(3 * (size_t) nt), tri_isect(3 * (size_t) nt);
     std::vector<uint32_t> prim_to_slot(nt);
+    bool any_uv = false;
+    for (uint32_t m = 0; m < desc->n_meshes; ++m) any_uv = any_uv || desc->meshes[m].texcoords != nullptr;
+    std::vector<float4> tri_uv(any_uv ? 2 * (size_t) nt : 0);
     auto u2f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
     for (uint32_t slot = 0; slot < nt; ++slot) {
         uint32_t prim = bvh.order[slot];
@@ -239,6 +243,14 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
             tri_isect[3 * (size_t) slot] = make_float4(q0[0], q0[1], q0[2], wpos[0]);
             tri_isect[3 * (size_t) slot + 1] = make_float4(q1[0] - q0[0], q1[1] - q0[1], q1[2] - q0[2], 0.f);
             tri_isect[3 * (size_t) slot + 2] = make_float4(q2[0] - q0[0], q2[1] - q0[1], q2[2] - q0[2], 0.f);
+        }
+        if (any_uv) {        // vertex texture coordinates (mesh.cpp:492-497): (uv0, uv1), (uv2, has_uv, -)
+            if (me.texcoords) {
+                const float *t0 = me.texcoords + 2 * (size_t) me.faces[3 * f], *t1 = me.texcoords + 2 * (size_t) me.faces[3 * f + 1],
+                            *t2 = me.texcoords + 2 * (size_t) me.faces[3 * f + 2];
+                tri_uv[2 * (size_t) slot] = make_float4(t0[0], t0[1], t1[0], t1[1]);
+                tri_uv[2 * (size_t) slot + 1] = make_float4(t2[0], t2[1], u2f(1u), 0.f);
+            } else { tri_uv[2 * (size_t) slot] = make_float4(0.f, 0.f, 0.f, 0.f); tri_uv[2 * (size_t) slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
         }
         for (int v = 0; v < 3; ++v) {
             const float *p = me.positions + 3 * (size_t) me.faces[3 * f + v];
@@ -279,6 +291,26 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         d.cdf_sum = (float) sum; d.cdf_norm = (float) (1.0 / sum);
     }
     std::vector<B2Bsdf> bsdfs(desc->bsdfs, desc->bsdfs + desc->n_bsdfs);
+    // textures (checkerboard.cpp, bitmap.cpp): texel data of all bitmaps in one device buffer
+    std::vector<B2Texture> texs(desc->textures, desc->textures + (desc->textures ? desc->n_textures : 0));
+    std::vector<float> tex_data; std::vector<size_t> tex_off(texs.size(), 0);
+    for (size_t t = 0; t < texs.size(); ++t) {
+        const B2Texture &tx = texs[t];
+        if (tx.type == B2_TEX_BITMAP) {
+            if (!tx.data || tx.width < 1 || tx.height < 1 || (tx.channels != 1 && tx.channels != 3)) {
+                delete s; return fail(B2_ERR_INVALID, "texture %zu: Unsupported channel count: %d (expected 1 or 3)", t, tx.channels); }
+            tex_off[t] = tex_data.size();
+            tex_data.insert(tex_data.end(), tx.data, tx.data + (size_t) tx.width * tx.height * tx.channels);
+            while (tex_data.size() % 4) tex_data.push_back(0.f);
+        } else if (tx.type != B2_TEX_CHECKERBOARD) { delete s; return fail(B2_ERR_INVALID, "texture %zu: unsupported type %d", t, tx.type); }
+    }
+    for (const B2Bsdf &b : bsdfs)
+        if (b.reflectance_texture < 0 || (uint32_t) b.reflectance_texture > texs.size()) { delete s; return fail(B2_ERR_INVALID, "BSDF references texture %d of %zu", b.reflectance_texture, texs.size()); }
+    if (!tex_data.empty()) {
+        cudaError_t te = s->tex_data.upload(tex_data);
+        if (te != cudaSuccess) { delete s; return fail(B2_ERR_CUDA, "texture upload failed: %s", cudaGetErrorString(te)); }
+        for (size_t t = 0; t < texs.size(); ++t) texs[t].data = texs[t].type == B2_TEX_BITMAP ? s->tex_data.p + tex_off[t] : nullptr;
+    }
     std::vector<float4> nodes(bvh.nodes.size() / 4);
     std::memcpy(nodes.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(float));
 
@@ -286,7 +318,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     auto align16 = [](size_t x) { return (x + 15) & ~(size_t) 15; };
     size_t off_pos = 0, off_nrm = off_pos + align16(tri_pos.size() * 16), off_p2s = off_nrm + align16(tri_nrm.size() * 16),
            off_cdf = off_p2s + align16(prim_to_slot.size() * 4), off_bsdf = off_cdf + align16(cdf.size() * 4),
-           off_em = off_bsdf + align16(bsdfs.size() * sizeof(B2Bsdf)), blob_bytes = off_em + align16(ems.size() * sizeof(DEmitter));
+           off_em = off_bsdf + align16(bsdfs.size() * sizeof(B2Bsdf)), off_uv = off_em + align16(ems.size() * sizeof(DEmitter)),
+           off_tex = off_uv + align16(tri_uv.size() * 16), blob_bytes = off_tex + align16(texs.size() * sizeof(B2Texture));
     std::vector<unsigned char> blob(std::max<size_t>(blob_bytes, 16), 0);
     if (!tri_pos.empty()) std::memcpy(blob.data() + off_pos, tri_pos.data(), tri_pos.size() * 16);
     if (!tri_nrm.empty()) std::memcpy(blob.data() + off_nrm, tri_nrm.data(), tri_nrm.size() * 16);
@@ -294,6 +327,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     if (!cdf.empty()) std::memcpy(blob.data() + off_cdf, cdf.data(), cdf.size() * 4);
     if (!bsdfs.empty()) std::memcpy(blob.data() + off_bsdf, bsdfs.data(), bsdfs.size() * sizeof(B2Bsdf));
     if (!ems.empty()) std::memcpy(blob.data() + off_em, ems.data(), ems.size() * sizeof(DEmitter));
+    if (!tri_uv.empty()) std::memcpy(blob.data() + off_uv, tri_uv.data(), tri_uv.size() * 16);
+    if (!texs.empty()) std::memcpy(blob.data() + off_tex, texs.data(), texs.size() * sizeof(B2Texture));
     cudaError_t e = cudaSuccess;
     if ((e = s->nodes.upload(nodes)) != cudaSuccess || (e = s->tri_isect.upload(tri_isect)) != cudaSuccess ||
         (e = s->blob.upload(blob)) != cudaSuccess || (e = s->instances.upload(dinst)) != cudaSuccess ||
@@ -308,6 +343,9 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.tri_pos = (const float4 *) (s->blob.p + off_pos); d.tri_nrm = (const float4 *) (s->blob.p + off_nrm);
     d.prim_to_slot = (const uint32_t *) (s->blob.p + off_p2s); d.cdf = (const float *) (s->blob.p + off_cdf);
     d.bsdfs = (const B2Bsdf *) (s->blob.p + off_bsdf); d.emitters = (const DEmitter *) (s->blob.p + off_em);
+    d.tri_uv = tri_uv.empty() ? nullptr : (const float4 *) (s->blob.p + off_uv);
+    d.textures = texs.empty() ? nullptr : (const B2Texture *) (s->blob.p + off_tex);
+    if (any_uv || !texs.empty()) s->features |= F_TEX;
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
     for (const B2Bsdf &b : bsdfs) {

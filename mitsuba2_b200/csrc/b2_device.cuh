@@ -60,6 +60,8 @@ struct DScene {
     const DEmitter *emitters;
     const float *cdf;
     const uint32_t *prim_to_slot;
+    const float4 *tri_uv;       // NULL unless a mesh has texture coordinates: (uv0, uv1), (uv2, has_uv, -) per triangle
+    const B2Texture *textures;  // `data` patched to device memory
     uint32_t n_nodes, n_tris, n_emitters, n_bsdfs;
     const DInstance *instances; // NULL for flat scenes
     const uint32_t *inst_order; // TLAS leaf order -> instance index
@@ -87,15 +89,18 @@ struct Tables {
     const DEmitter *emitters;
     const DInstance *instances;
     uint32_t n_emitters;
+    const float4 *tri_uv;
+    const B2Texture *textures;
 };
 B2_D Tables make_tables(const DScene &sc) {
     Tables t; t.tri_pos = sc.tri_pos; t.tri_nrm = sc.tri_nrm; t.prim_to_slot = sc.prim_to_slot; t.cdf = sc.cdf;
-    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.instances = sc.instances; t.n_emitters = sc.n_emitters; return t;
+    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.instances = sc.instances; t.n_emitters = sc.n_emitters; t.tri_uv = sc.tri_uv; t.textures = sc.textures; return t;
 }
 
 // Compile-time scene features: the stage kernels are instantiated per feature set so that a scene
 // pays (instruction cache, registers) only for the BSDFs / emitters / filter it contains.
-enum : uint32_t { F_ROUGH = 1u, F_DIELECTRIC = 2u, F_ENV = 4u, F_WIDE = 8u, F_COUNT = 16u };
+// F_TEX: a mesh has texture coordinates (uv-derived dp_du, mesh.cpp:492-511) and / or a BSDF parameter is textured
+enum : uint32_t { F_ROUGH = 1u, F_DIELECTRIC = 2u, F_ENV = 4u, F_WIDE = 8u, F_TEX = 16u, F_COUNT = 32u };
 
 struct Ray { float3 o, d; float mint, maxt; };
 
@@ -119,6 +124,7 @@ B2_D bool tri_intersect(float3 p0, float3 p1, float3 p2, const Ray &ray, float &
 struct SI {
     float3 p, n, sh_n, sh_s, sh_t, wi;
     int bsdf, emitter;
+    float2 uv;                   // only maintained by si_fill<true>
 };
 
 B2_D float3 coordinate_system_s(float3 n) {        // include/mitsuba/core/vector.h:116-136 (first vector)
@@ -148,6 +154,7 @@ B2_D float3 xf_normal(const float *inv, float3 n) {
               b2_fma(inv[10], n.z, b2_fma(inv[6], n.y, inv[2] * n.x)));
 }
 
+template <bool TEX = false>
 B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_d, int inst, SI &si) {
     float4 a0 = B2_LD(&sc.tri_pos[3 * slot]), a1 = B2_LD(&sc.tri_pos[3 * slot + 1]), a2 = B2_LD(&sc.tri_pos[3 * slot + 2]);
     float4 m0 = B2_LD(&sc.tri_nrm[3 * slot]), m1 = B2_LD(&sc.tri_nrm[3 * slot + 1]), m2 = B2_LD(&sc.tri_nrm[3 * slot + 2]);
@@ -157,6 +164,20 @@ B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_
     si.p = (p0 * b0 + p1 * b1) + p2 * b2;                       // mesh.cpp:484
     si.n = normalize(cross(dp0, dp1));                           // mesh.cpp:487
     float3 dp_du = coordinate_system_s(si.n);                    // mesh.cpp:491
+    if constexpr (TEX) {
+        si.uv = make_float2(b1, b2);                             // mesh.cpp:490
+        if (sc.tri_uv) {
+            float4 t0 = B2_LD(&sc.tri_uv[2 * slot]), t1 = B2_LD(&sc.tri_uv[2 * slot + 1]);
+            if (__float_as_uint(t1.z)) {                         // has_vertex_texcoords(), mesh.cpp:492-511
+                si.uv = make_float2((t0.x * b0 + t0.z * b1) + t1.x * b2, (t0.y * b0 + t0.w * b1) + t1.y * b2);
+                float duv0x = t0.z - t0.x, duv0y = t0.w - t0.y, duv1x = t1.x - t0.x, duv1y = t1.y - t0.y;
+                float det = b2_fma(duv0x, duv1y, -(duv0y * duv1x)), inv_det = b2_rcp(det);
+                if (det != 0.f)                                  // fmsub(duv1.y, dp0, duv0.y * dp1) * inv_det
+                    dp_du = v3(b2_fma(duv1y, dp0.x, -(duv0y * dp1.x)) * inv_det, b2_fma(duv1y, dp0.y, -(duv0y * dp1.y)) * inv_det,
+                               b2_fma(duv1y, dp0.z, -(duv0y * dp1.z)) * inv_det);
+            }
+        }
+    }
     if (__float_as_uint(m2.w))                                   // mesh.cpp:514-519
         si.sh_n = normalize((v3(m0) * b0 + v3(m1) * b1) + v3(m2) * b2);
     else
@@ -286,14 +307,56 @@ B2_D float3 mf_sample(const MF &d, float3 wi, float sx, float sy, float &pdf) { 
     return m;
 }
 
+B2_D float3 rgb3(const float *p) { return v3(p[0], p[1], p[2]); }
+
+// ---- textures (src/textures/checkerboard.cpp:46-63, bitmap.cpp:386-474) ----------------------
+B2_D int tex_wrap(const B2Texture &t, int value, int res) {       // bitmap.cpp:386-401
+    if (t.wrap == B2_WRAP_CLAMP) return max(0, min(value, res - 1));
+    int div = value / res, mod = value - div * res;               // enoki::divisor: truncating division
+    if (mod < 0) mod += res;
+    if (t.wrap == B2_WRAP_MIRROR && !(((div & 1) == 0) != (value < 0))) mod = res - 1 - mod;
+    return mod;
+}
+B2_D float3 tex_fetch(const B2Texture &t, int x, int y) {
+    const float *p = t.data + (size_t) (x + y * t.width) * (size_t) t.channels;
+    float a = __ldg(p);
+    return t.channels == 1 ? v3(a, a, a) : v3(a, __ldg(p + 1), __ldg(p + 2));
+}
+B2_D float3 texture_eval(const B2Texture &t, float2 si_uv) {
+    // Transform3f::transform_affine: result = col2; result = fmadd(col_i, uv_i, result)
+    float u = b2_fma(t.to_uv[1], si_uv.y, b2_fma(t.to_uv[0], si_uv.x, t.to_uv[2]));
+    float v = b2_fma(t.to_uv[4], si_uv.y, b2_fma(t.to_uv[3], si_uv.x, t.to_uv[5]));
+    if (t.type == B2_TEX_CHECKERBOARD) {                          // checkerboard.cpp:46-63
+        bool mx = u - floorf(u) > .5f, my = v - floorf(v) > .5f;
+        return mx == my ? rgb3(t.color0) : rgb3(t.color1);
+    }
+    if (t.filter == B2_TEXFILTER_BILINEAR) {                      // bitmap.cpp:412-457
+        u = b2_fma(u, (float) t.width, -.5f); v = b2_fma(v, (float) t.height, -.5f);
+        int ix = (int) floorf(u), iy = (int) floorf(v);
+        float w1x = u - (float) ix, w1y = v - (float) iy, w0x = 1.f - w1x, w0y = 1.f - w1y;
+        int x0 = tex_wrap(t, ix, t.width), x1 = tex_wrap(t, ix + 1, t.width), y0 = tex_wrap(t, iy, t.height), y1 = tex_wrap(t, iy + 1, t.height);
+        float3 v00 = tex_fetch(t, x0, y0), v10 = tex_fetch(t, x1, y0), v01 = tex_fetch(t, x0, y1), v11 = tex_fetch(t, x1, y1);
+        float3 v0 = v3(b2_fma(w0x, v00.x, w1x * v10.x), b2_fma(w0x, v00.y, w1x * v10.y), b2_fma(w0x, v00.z, w1x * v10.z));
+        float3 v1 = v3(b2_fma(w0x, v01.x, w1x * v11.x), b2_fma(w0x, v01.y, w1x * v11.y), b2_fma(w0x, v01.z, w1x * v11.z));
+        return v3(b2_fma(w0y, v0.x, w1y * v1.x), b2_fma(w0y, v0.y, w1y * v1.y), b2_fma(w0y, v0.z, w1y * v1.z));
+    }
+    u *= (float) t.width; v *= (float) t.height;                  // bitmap.cpp:458-473
+    return tex_fetch(t, tex_wrap(t, (int) floorf(u), t.width), tex_wrap(t, (int) floorf(v), t.height));
+}
+// 'reflectance' of the BSDF at si: the constant, or its texture evaluated at si.uv (Texture::eval(si) inside BSDF::eval / sample)
+template <uint32_t F> B2_D float3 bsdf_reflectance(const Tables &tb, const B2Bsdf &b, const SI &si) {
+    if constexpr ((F & F_TEX) != 0)
+        if (b.reflectance_texture > 0) return texture_eval(tb.textures[b.reflectance_texture - 1], si.uv);
+    return v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+}
+
 // ---- BSDFs (src/bsdfs/{diffuse,dielectric,roughconductor,conductor,plastic}.cpp) --------------
 // F_DIELECTRIC marks scenes with any of the BSDFs that have a delta lobe (dielectric, conductor, plastic)
 template <uint32_t F> B2_D bool bsdf_is_smooth(const B2Bsdf &b) {     // has_flag(flags, Smooth), path.cpp:155
     return !(F & F_DIELECTRIC) || (b.type != B2_BSDF_DIELECTRIC && b.type != B2_BSDF_CONDUCTOR);
 }
 // SmoothPlastic: diffuse_reflectance / (1 - fdr_int), optional nonlinear variant (plastic.cpp:231-232, 262-263)
-B2_D float3 plastic_diffuse(const B2Bsdf &b) {
-    float3 d = v3(b.reflectance[0], b.reflectance[1], b.reflectance[2]);
+B2_D float3 plastic_diffuse(const B2Bsdf &b, float3 d) {
     if (b.nonlinear)
         return v3(d.x / (1.f - d.x * b.fdr_int), d.y / (1.f - d.y * b.fdr_int), d.z / (1.f - d.z * b.fdr_int));
     return d * (1.f / (1.f - b.fdr_int));
@@ -302,15 +365,13 @@ B2_D float fresnel_r(float cos_theta_i, float eta) {
     float r, ct, eit, eti; fresnel(cos_theta_i, eta, r, ct, eit, eti); return r;
 }
 
-B2_D float3 rgb3(const float *p) { return v3(p[0], p[1], p[2]); }
-
-template <uint32_t F> B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo) {
+template <uint32_t F> B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float3 wo, float3 refl) {
     float cti = si.wi.z, cto = wo.z;
     float3 zero = v3(0.f, 0.f, 0.f);
     switch (b.type) {
         case B2_BSDF_DIFFUSE: case B2_BSDF_NULL: {                 // diffuse.cpp:104-119
             if (!(cti > 0.f && cto > 0.f)) return zero;
-            return v3((b.reflectance[0] * B2_INV_PI) * cto, (b.reflectance[1] * B2_INV_PI) * cto, (b.reflectance[2] * B2_INV_PI) * cto);
+            return v3((refl.x * B2_INV_PI) * cto, (refl.y * B2_INV_PI) * cto, (refl.z * B2_INV_PI) * cto);
         }
         case B2_BSDF_ROUGHCONDUCTOR: if constexpr ((F & F_ROUGH) != 0) {   // roughconductor.cpp:277-343
             if (!(cti > 0.f && cto > 0.f)) return zero;
@@ -329,7 +390,7 @@ template <uint32_t F> B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float
         case B2_BSDF_PLASTIC: if constexpr ((F & F_DIELECTRIC) != 0) {     // plastic.cpp:242-266
             if (!(cti > 0.f && cto > 0.f)) return zero;
             float f_i = fresnel_r(cti, b.eta), f_o = fresnel_r(cto, b.eta);
-            float3 diff = plastic_diffuse(b);
+            float3 diff = plastic_diffuse(b, refl);
             float s = (B2_INV_PI * cto) * b.inv_eta_2 * (1.f - f_i) * (1.f - f_o);
             return diff * s;
         } else return zero;
@@ -359,7 +420,7 @@ template <uint32_t F> B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 
     }
 }
 struct BS { float3 wo; float pdf, eta; bool delta; };
-template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x, float s2y, BS &bs) {
+template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, float sample1, float s2x, float s2y, BS &bs, float3 refl) {
     float3 zero = v3(0.f, 0.f, 0.f);
     bs.wo = zero; bs.pdf = 0.f; bs.eta = 0.f; bs.delta = false;
     float cti = si.wi.z;
@@ -370,7 +431,7 @@ template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, flo
             bs.pdf = B2_INV_PI * bs.wo.z;
             bs.eta = 1.f;
             if (!(bs.pdf > 0.f)) return zero;
-            return rgb3(b.reflectance);
+            return refl;
         }
         case B2_BSDF_DIELECTRIC: if constexpr ((F & F_DIELECTRIC) != 0) {   // dielectric.cpp:201-310
             float r_i, cos_theta_t, eta_it, eta_ti;
@@ -431,7 +492,7 @@ template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, flo
             bs.wo = square_to_cosine_hemisphere(s2x, s2y);
             bs.pdf = prob_diffuse * (B2_INV_PI * bs.wo.z);
             float f_o = fresnel_r(bs.wo.z, b.eta);
-            float3 value = plastic_diffuse(b);
+            float3 value = plastic_diffuse(b, refl);
             float s = b.inv_eta_2 * (1.f - f_i) * (1.f - f_o) / prob_diffuse;
             return value * s;
         } else return zero;

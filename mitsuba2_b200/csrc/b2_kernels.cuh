@@ -773,6 +773,8 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
     tb.cdf = (const float *) (dst + ((const unsigned char *) sc.cdf - g));
     tb.bsdfs = (const B2Bsdf *) (dst + ((const unsigned char *) sc.bsdfs - g));
     tb.emitters = (const DEmitter *) (dst + ((const unsigned char *) sc.emitters - g));
+    if (sc.tri_uv) tb.tri_uv = (const float4 *) (dst + ((const unsigned char *) sc.tri_uv - g));
+    if (sc.textures) tb.textures = (const B2Texture *) (dst + ((const unsigned char *) sc.textures - g));
     return tb;
 }
 
@@ -806,7 +808,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling ----
         if (valid) {
             bool hit_valid = h.x < B2_INF;
-            if (hit_valid) si_fill(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
+            if (hit_valid) si_fill<(F & F_TEX) != 0>(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
             else if constexpr ((F & F_ENV) != 0) si.emitter = sc.env.index;                // scene->environment(), scene.h:243-253
             if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
             // ---- intersection with emitters (path.cpp:128-129) ----
@@ -848,7 +850,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                     DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, sx, sy, ds);
                     if (ds.pdf != 0.f) {
                         float3 wo = to_local(si, ds.d);
-                        float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo);
+                        float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo, bsdf_reflectance<F>(tb, bsdf, si));
                         float bpdf = bsdf_pdf<F>(bsdf, si, wo);
                         float mis = mis_weight(ds.pdf, bpdf);
                         float3 c = ((throughput * mis) * bsdf_val) * emitter_val;
@@ -877,7 +879,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
             const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
             float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
             float s1 = pcg32_next_float(rng);
-            BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs);
+            BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs, bsdf_reflectance<F>(tb, bsdf, si));
             throughput = throughput * bsdf_val;
             if (!any_nonzero(throughput)) term = true;                             // path.cpp:182-184
             else {
@@ -1001,7 +1003,7 @@ __global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, cons
         return;
     }
     uint32_t slot = sc.prim_to_slot[__float_as_uint(h.w)];
-    SI si; si_fill(make_tables(sc), slot, h.y, h.z, v3(ray_d[i]), inst ? inst[i] : -1, si);
+    SI si; si_fill<true>(make_tables(sc), slot, h.y, h.z, v3(ray_d[i]), inst ? inst[i] : -1, si);
     o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z; o[3] = si.n.x; o[4] = si.n.y; o[5] = si.n.z;
     o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z; o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
     o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z; o[15] = __uint_as_float((uint32_t) si.bsdf);

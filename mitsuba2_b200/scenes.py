@@ -22,11 +22,13 @@ CBOX_BSDFS = {
 CBOX_RADIANCE = (18.387, 10.9873, 2.75357)
 
 
-def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=None, lift=0.0, instances=None, drop_meshes=(), envmap=None):
+def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=None, lift=0.0, instances=None, drop_meshes=(), envmap=None,
+         texcoords=None):
     """cbox-rgb.xml (resources/data/scenes/cbox): 8 OBJ meshes / 38 triangles, one area
     emitter, diffuse rgb BSDFs, perspective sensor fov 39.3077 ('smaller' axis).
 
     materials: optional {bsdf_id: callable(scene_buffers) -> bsdf index} overriding a BSDF.
+    texcoords: optional {mesh index: [n_vertices, 2] uv array}.
     Mesh data comes from tests/golden/cbox_meshes.npz (generated from the reference's OBJ
     files by tests/golden/make_golden.py).
     """
@@ -50,7 +52,7 @@ def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=
         if instances is not None and b == "box" and i == 7:
             i += 1
             continue                      # instanced variant: the large box is dropped ...
-        mi = sb.add_mesh(pos, z[f"m{i}_faces"], z[f"m{i}_normals"], bsdf_ids[b])
+        mi = sb.add_mesh(pos, z[f"m{i}_faces"], z[f"m{i}_normals"], bsdf_ids[b], texcoords=texcoords.get(i) if texcoords else None)
         if b == "light":
             sb.add_area_emitter(mi, CBOX_RADIANCE)
         if instances is not None and b == "box" and i == 6:

@@ -261,6 +261,7 @@ typedef struct {
     v3 n0, n1, n2;
     int has_normals;
     int mesh;
+    int has_uv; float uv0[2], uv1[2], uv2[2];
 } otri;
 
 typedef struct { float lo[3], hi[3]; int left, right, first, count; } onode;
@@ -365,6 +366,11 @@ static oscene *oscene_create(const B2SceneDesc *d) {
                 mesh_vertex(me, me->normals, i2, &t->n2);
             }
             t->mesh = (int) m;
+            t->has_uv = me->texcoords != NULL;
+            if (me->texcoords)
+                for (int k = 0; k < 2; ++k) {
+                    t->uv0[k] = me->texcoords[2 * i0 + k]; t->uv1[k] = me->texcoords[2 * i1 + k]; t->uv2[k] = me->texcoords[2 * i2 + k];
+                }
         }
         /* area pmf + cdf only needed for emitter meshes: Mesh::build_pmf mesh.cpp:285-312,
            face_area mesh.h:108-116, DiscreteDistribution::update distr_1d.h:49-90 */
@@ -604,6 +610,7 @@ static int scene_occluded(const oscene *s, const oray *ray, int brute) {
 typedef struct {
     float t; v3 p, n, sh_n, sh_s, sh_t, wi;
     uint32_t prim; int mesh;
+    float uv[2];
 } osi;
 
 static inline void coordinate_system_s(v3 n, v3 *s) {   /* vector.h:116-136 (first vector only) */
@@ -637,6 +644,18 @@ static void si_fill(const oscene *s, const oray *ray, const ohit *h, osi *si) {
     si->p = v3_add(v3_add(v3_scale(tr->p0, b0), v3_scale(tr->p1, b1)), v3_scale(tr->p2, b2));  /* mesh.cpp:484 */
     si->n = v3_normalize(v3_cross(dp0, dp1));                                                   /* mesh.cpp:487 */
     v3 dp_du; coordinate_system_s(si->n, &dp_du);                                               /* mesh.cpp:491 */
+    si->uv[0] = b1; si->uv[1] = b2;                                                             /* mesh.cpp:490 */
+    if (tr->has_uv) {                                                                            /* mesh.cpp:492-511 */
+        for (int k = 0; k < 2; ++k) si->uv[k] = (tr->uv0[k] * b0 + tr->uv1[k] * b1) + tr->uv2[k] * b2;
+        float duv0x = tr->uv1[0] - tr->uv0[0], duv0y = tr->uv1[1] - tr->uv0[1],
+              duv1x = tr->uv2[0] - tr->uv0[0], duv1y = tr->uv2[1] - tr->uv0[1];
+        float det = b2o_fma(duv0x, duv1y, -(duv0y * duv1x)), inv_det = b2o_rcp(det);
+        if (det != 0.f) {
+            /* fmsub(duv1.y, dp0, duv0.y * dp1) * inv_det */
+            dp_du = v3_make(b2o_fma(duv1y, dp0.x, -(duv0y * dp1.x)) * inv_det, b2o_fma(duv1y, dp0.y, -(duv0y * dp1.y)) * inv_det,
+                            b2o_fma(duv1y, dp0.z, -(duv0y * dp1.z)) * inv_det);
+        }
+    }
     if (tr->has_normals)                                                                         /* mesh.cpp:514-519 */
         si->sh_n = v3_normalize(v3_add(v3_add(v3_scale(tr->n0, b0), v3_scale(tr->n1, b1)), v3_scale(tr->n2, b2)));
     else
@@ -775,6 +794,57 @@ static inline v3 mf_sample(const omf *d, v3 wi, float sx, float sy, float *pdf) 
     v3 m = v3_normalize(v3_make(-s0, -s1, 1.f));
     *pdf = mf_eval(d, m) * mf_smith_g1(d, wi, m) * fabsf(v3_dot(wi, m)) / wi.z;
     return m;
+}
+
+/* ============================================================================================
+ * Textures — src/textures/checkerboard.cpp:46-63, src/textures/bitmap.cpp:386-474
+ * ============================================================================================ */
+static inline void tex_to_uv(const B2Texture *t, const float uv[2], float *u, float *v) {
+    /* Transform3f::transform_affine (transform.h): result = col2; result = fmadd(col_i, uv_i, result) */
+    const float *M = t->to_uv;
+    *u = b2o_fma(M[1], uv[1], b2o_fma(M[0], uv[0], M[2]));
+    *v = b2o_fma(M[4], uv[1], b2o_fma(M[3], uv[0], M[5]));
+}
+static inline int tex_wrap(const B2Texture *t, int value, int res) {            /* bitmap.cpp:386-401 */
+    if (t->wrap == B2_WRAP_CLAMP) return value < 0 ? 0 : (value > res - 1 ? res - 1 : value);
+    int div = value / res, mod = value - div * res;                             /* enoki::divisor: truncating */
+    if (mod < 0) mod += res;
+    if (t->wrap == B2_WRAP_MIRROR && !(((div & 1) == 0) ^ (value < 0))) mod = res - 1 - mod;
+    return mod;
+}
+static inline v3 tex_fetch(const B2Texture *t, int x, int y) {
+    const float *p = t->data + (size_t) (x + y * t->width) * (size_t) t->channels;
+    return t->channels == 1 ? v3_make(p[0], p[0], p[0]) : v3_make(p[0], p[1], p[2]);
+}
+static v3 texture_eval(const B2Texture *t, const float si_uv[2]) {
+    float u, v; tex_to_uv(t, si_uv, &u, &v);
+    if (t->type == B2_TEX_CHECKERBOARD) {                                       /* checkerboard.cpp:46-63 */
+        int mx = u - floorf(u) > .5f, my = v - floorf(v) > .5f;
+        const float *c = mx == my ? t->color0 : t->color1;
+        return v3_make(c[0], c[1], c[2]);
+    }
+    if (t->filter == B2_TEXFILTER_BILINEAR) {                                   /* bitmap.cpp:412-457 */
+        u = b2o_fma(u, (float) t->width, -.5f); v = b2o_fma(v, (float) t->height, -.5f);
+        int ix = (int) floorf(u), iy = (int) floorf(v);
+        float w1x = u - (float) ix, w1y = v - (float) iy, w0x = 1.f - w1x, w0y = 1.f - w1y;
+        int x0 = tex_wrap(t, ix, t->width), x1 = tex_wrap(t, ix + 1, t->width),
+            y0 = tex_wrap(t, iy, t->height), y1 = tex_wrap(t, iy + 1, t->height);
+        v3 v00 = tex_fetch(t, x0, y0), v10 = tex_fetch(t, x1, y0), v01 = tex_fetch(t, x0, y1), v11 = tex_fetch(t, x1, y1);
+        v3 v0 = v3_make(b2o_fma(w0x, v00.x, w1x * v10.x), b2o_fma(w0x, v00.y, w1x * v10.y), b2o_fma(w0x, v00.z, w1x * v10.z));
+        v3 v1 = v3_make(b2o_fma(w0x, v01.x, w1x * v11.x), b2o_fma(w0x, v01.y, w1x * v11.y), b2o_fma(w0x, v01.z, w1x * v11.z));
+        return v3_make(b2o_fma(w0y, v0.x, w1y * v1.x), b2o_fma(w0y, v0.y, w1y * v1.y), b2o_fma(w0y, v0.z, w1y * v1.z));
+    }
+    u *= (float) t->width; v *= (float) t->height;                              /* bitmap.cpp:458-473 */
+    return tex_fetch(t, tex_wrap(t, (int) floorf(u), t->width), tex_wrap(t, (int) floorf(v), t->height));
+}
+/* the BSDF record with its textured parameters evaluated at si (Texture::eval(si) inside BSDF::eval/sample) */
+static inline B2Bsdf bsdf_at(const B2SceneDesc *d, const B2Bsdf *b, const osi *si) {
+    B2Bsdf r = *b;
+    if (b->reflectance_texture > 0 && (uint32_t) b->reflectance_texture <= d->n_textures) {
+        v3 c = texture_eval(&d->textures[b->reflectance_texture - 1], si->uv);
+        r.reflectance[0] = c.x; r.reflectance[1] = c.y; r.reflectance[2] = c.z;
+    }
+    return r;
 }
 
 /* ============================================================================================
@@ -1253,7 +1323,7 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         }
         if ((uint32_t) depth >= (uint32_t) rp->max_depth || !active) break;   /* path.cpp:147-149 */
 
-        const B2Bsdf *bsdf = &d->bsdfs[d->meshes[si.mesh].bsdf];
+        const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[d->meshes[si.mesh].bsdf], &si), *bsdf = &bsdf_si;
         if (bsdf_is_smooth(bsdf)) {                                       /* path.cpp:153-172 */
             float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
             ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);

@@ -33,8 +33,8 @@ f32 = np.float32
 
 
 def load_obj_like_reference(path, translate=(0.0, 0.0, 0.0)):
-    """Mirror of OBJMesh (src/shapes/obj.cpp:150-346) for v / vn / f records."""
-    verts, norms = [], []
+    """Mirror of OBJMesh (src/shapes/obj.cpp:150-346) for v / vt / vn / f records."""
+    verts, norms, uvs = [], [], []
     vmap = {}          # key (v, vt, vn) -> id, ids handed out in order of first use
     keys = []
     tris = []
@@ -49,6 +49,10 @@ def load_obj_like_reference(path, translate=(0.0, 0.0, 0.0)):
             n = np.array([f32(x) for x in cur.split()[1:4]], dtype=f32)
             n = n * f32(1.0) / np.sqrt((n * n).sum(dtype=f32), dtype=f32)
             norms.append(n.astype(f32))
+        elif cur.startswith("vt "):
+            uv = np.array([f32(x) for x in cur.split()[1:3]], dtype=f32)
+            uv[1] = f32(1.0) - uv[1]                       # flip_tex_coords (default true), obj.cpp:199-200
+            uvs.append(uv)
         elif cur.startswith("f "):
             ids = []
             for tok in cur.split()[1:]:
@@ -74,6 +78,8 @@ def load_obj_like_reference(path, translate=(0.0, 0.0, 0.0)):
         normals = np.array([norms[k[2] - 1] for k in keys], dtype=f32)
     else:
         normals = recompute_vertex_normals(positions, faces)
+    if uvs:
+        return positions, normals, faces, np.array([uvs[k[1] - 1] for k in keys], dtype=f32)
     return positions, normals, faces
 
 
@@ -212,8 +218,67 @@ def env_image(w=48, h=24):
 def write_pfm(path, img):
     h, w = img.shape[:2]
     with open(path, "wb") as f:
-        f.write(b"PF\n%d %d\n-1.0\n" % (w, h))
+        f.write((b"PF" if img.ndim == 3 else b"Pf") + b"\n%d %d\n-1.0\n" % (w, h))
         f.write(np.ascontiguousarray(img[::-1], "<f4").tobytes())      # PFM rows are bottom-up
+
+
+def tex_images():
+    """Deterministic small bitmaps in [0, 1]: an 8x6 RGB one and a 5x7 single-channel one."""
+    y, x = np.mgrid[0:6, 0:8].astype(np.float32)
+    rgb = np.stack([0.15 + 0.1 * x, 0.9 - 0.12 * y, 0.2 + 0.05 * ((x * 3 + y * 5) % 7)], -1).astype(np.float32)
+    y, x = np.mgrid[0:7, 0:5].astype(np.float32)
+    gray = (0.1 + 0.125 * ((x * 2 + y * 3) % 7)).astype(np.float32)
+    return np.clip(rgb, 0, 1), np.clip(gray, 0, 1)
+
+
+# to_uv transforms with exactly representable entries: scale then translate (xml.cpp composes left-multiplying)
+TEX_SPEC = {
+    # bsdf id: (plugin, texture kind, kwargs for SceneBuffers.add_*, xml of the texture)
+    "white": ("diffuse", "checkerboard", dict(color0=(0.8, 0.7, 0.6), color1=(0.2, 0.25, 0.3), scale=(4.0, 4.0), translate=(0.0, 0.0))),
+    "green": ("diffuse", "bitmap_rgb", dict(filter_type="bilinear", wrap_mode="repeat", scale=(2.0, 3.0), translate=(0.25, 0.5))),
+    "red": ("diffuse", "bitmap_gray", dict(filter_type="nearest", wrap_mode="mirror", scale=(3.0, 2.0), translate=(-0.5, 0.25))),
+    "box": ("plastic", "bitmap_rgb", dict(filter_type="bilinear", wrap_mode="clamp", scale=(1.5, 1.5), translate=(-0.25, -0.125))),
+}
+
+
+def tex_bsdf_xml(bsdf_id, mesh_dir):
+    plugin, kind, kw = TEX_SPEC[bsdf_id]
+    sx, sy = kw["scale"]; tx, ty = kw["translate"]
+    xf = f'<transform name="to_uv"><scale x="{sx}" y="{sy}"/><translate x="{tx}" y="{ty}"/></transform>'
+    pname = "reflectance" if plugin == "diffuse" else "diffuse_reflectance"
+    if kind == "checkerboard":
+        c0, c1 = kw["color0"], kw["color1"]
+        tex = (f'<texture type="checkerboard" name="{pname}"><rgb name="color0" value="{c0[0]}, {c0[1]}, {c0[2]}"/>'
+               f'<rgb name="color1" value="{c1[0]}, {c1[1]}, {c1[2]}"/>{xf}</texture>')
+    else:
+        fn = os.path.join(mesh_dir, "tex_rgb.pfm" if kind == "bitmap_rgb" else "tex_gray.pfm")
+        tex = (f'<texture type="bitmap" name="{pname}"><string name="filename" value="{fn}"/>'
+               f'<string name="filter_type" value="{kw["filter_type"]}"/><string name="wrap_mode" value="{kw["wrap_mode"]}"/>'
+               f'<boolean name="raw" value="true"/>{xf}</texture>')
+    extra = '<float name="int_ior" value="1.6"/>' if plugin == "plastic" else ""
+    return f'<bsdf type="{plugin}" id="{bsdf_id}">{tex}{extra}</bsdf>'
+
+
+def write_uv_obj(src, dst):
+    """Copy an OBJ adding one vt per vertex: a generic non-degenerate projection of the position."""
+    out, n = [], 0
+    for line in open(src):
+        cur = line.strip()
+        if cur.startswith("v "):
+            x, y, z = [float(t) for t in cur.split()[1:4]]
+            out.append(line if line.endswith("\n") else line + "\n")
+            out.append("vt %r %r\n" % (float(f32(x / 500.0 + y / 700.0)), float(f32(z / 500.0 + y / 900.0))))
+            n += 1
+        elif cur.startswith("f "):
+            toks = []
+            for t in cur.split()[1:]:
+                p = t.split("/")
+                toks.append(f"{p[0]}/{p[0]}" + (f"/{p[2]}" if len(p) > 2 and p[2] else ""))
+            out.append("f " + " ".join(toks) + "\n")
+        else:
+            out.append(line)
+    # all vt after all v is not required by the format, but keep the indices aligned: vt k belongs to v k
+    open(dst, "w").writelines(out)
 
 
 EXTRA_EMITTER_OBJ = """v 150 420 150
@@ -226,11 +291,14 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
-             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None):
+             rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
+             textures=False):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
-        if materials and k in materials:
+        if textures and k in TEX_SPEC:
+            bs.append(tex_bsdf_xml(k, mesh_dir))
+        elif materials and k in materials:
             bs.append(materials[k].replace("<bsdf ", f'<bsdf id="{k}" ', 1))
         else:
             bs.append(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>')
@@ -260,7 +328,14 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             path = os.path.join(mesh_dir, fn)
             lines = [l for l in open(f"{CBOX}/meshes/{fn}") if l.strip() != "f 8 7 6 5"]
             open(path, "w").writelines(lines)
+        if textures:           # every mesh gets texture coordinates (=> uv-derived dp_du on all surfaces)
+            dst = os.path.join(mesh_dir, "uv_" + fn)
+            write_uv_obj(path, dst)
+            path = dst
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
+    if textures:
+        rgb, gray = tex_images()
+        write_pfm(os.path.join(mesh_dir, "tex_rgb.pfm"), rgb); write_pfm(os.path.join(mesh_dir, "tex_gray.pfm"), gray)
     if extra_emitter:
         # a second area emitter (scene.cpp:176-198: uniform emitter selection): a small quad facing down
         path = os.path.join(mesh_dir, "extra_emitter.obj")
@@ -342,6 +417,7 @@ GOLDEN = {
     "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
     # smooth conductor / plastic
     "cbox_64_spp16_conductor": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": CONDUCTOR, "green": MIRROR}),
+    "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
 
@@ -417,6 +493,17 @@ def main():
         if kw.get("envmap"):
             extra.update(env_rgb=env_image(), env_to_world=np.array(ENV_TO_WORLD, np.float32), env_scale=np.float32(1.5),
                          env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
+        if kw.get("textures"):
+            rgb_t, gray_t = tex_images()
+            extra.update(tex_rgb=rgb_t, tex_gray=gray_t, tex_spec=np.array(repr(TEX_SPEC)))
+            with tempfile.TemporaryDirectory() as td:
+                for i, (fn, _, tr) in enumerate(CBOX_SHAPES):
+                    src = os.path.join(CBOX, "meshes", fn)
+                    if kw.get("no_patch") and fn == "cbox_ceiling.obj":
+                        src2 = os.path.join(td, "np_" + fn)
+                        open(src2, "w").writelines([l for l in open(src) if l.strip() != "f 8 7 6 5"]); src = src2
+                    dst = os.path.join(td, "uv_" + fn); write_uv_obj(src, dst)
+                    extra[f"uv_m{i}"] = load_obj_like_reference(dst, tr)[3]
         np.savez_compressed(os.path.join(HERE, f"ref_{name}.npz"), rgb=img, params=np.array(repr(kw_s)),
                             oracle_build=np.array(info), **extra)
         print(f"ref_{name}.npz", img.shape, "mean", img.mean(axis=(0, 1)))

@@ -38,6 +38,23 @@ def _material(xml):
     raise ValueError(xml)
 
 
+def _tex_materials(z):
+    """TEX_SPEC of tests/golden/make_golden.py -> textured BSDFs (to_uv = translate * scale, exact in fp32)."""
+    spec = ast.literal_eval(str(z["tex_spec"]))
+    out = {}
+    for bsdf_id, (plugin, kind, kw) in spec.items():
+        def make(sb, plugin=plugin, kind=kind, kw=kw):
+            (sx, sy), (tx, ty) = kw["scale"], kw["translate"]
+            to_uv = [[sx, 0, tx], [0, sy, ty], [0, 0, 1]]
+            if kind == "checkerboard":
+                t = sb.add_checkerboard(kw["color0"], kw["color1"], to_uv)
+            else:
+                t = sb.add_bitmap(z["tex_rgb"] if kind == "bitmap_rgb" else z["tex_gray"], kw["filter_type"], kw["wrap_mode"], to_uv)
+            return sb.add_diffuse(texture=t) if plugin == "diffuse" else sb.add_plastic(int_ior=1.6, texture=t)
+        out[bsdf_id] = make
+    return out
+
+
 def _materials(spec):
     return {name: _material(xml) for name, xml in spec.items()} if spec else None
 
@@ -63,7 +80,8 @@ def load(name, host):
         env = dict(rgb=z["env_rgb"], scale=float(z["env_scale"]), to_world=z["env_to_world"].reshape(4, 4))
         drop = tuple(int(i) for i in z["env_dropped"])
     sb = scenes.cbox(host, kw["width"], kw["height"], rfilter=kw.get("rfilter", "box"), envmap=env, drop_meshes=drop,
-                     materials=_materials(kw.get("materials")),
+                     materials=_tex_materials(z) if kw.get("textures") else _materials(kw.get("materials")),
+                     texcoords={i: z[f"uv_m{i}"] for i in range(8)} if kw.get("textures") else None,
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
                      instances=kw.get("instances"))
     if kw.get("extra_emitter"):
