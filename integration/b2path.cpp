@@ -12,6 +12,7 @@
 // oracle/_ref/dist/plugins/. This file is written against the reference's public plugin API
 // (include/mitsuba/render/*.h); nothing is copied from it.
 #include <mitsuba/core/properties.h>
+#include <mitsuba/core/thread.h>
 #include <mitsuba/core/transform.h>
 #include <mitsuba/render/bsdf.h>
 #include <mitsuba/render/emitter.h>
@@ -26,7 +27,9 @@
 #include <mitsuba/render/fresnel.h>
 #include <mitsuba/render/texture.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <typeinfo>
@@ -75,6 +78,7 @@ public:
             std::vector<B2Mesh> meshes;
             std::vector<B2Bsdf> bsdfs;
             std::vector<B2Emitter> emitters;
+            std::vector<B2Texture> textures;
             std::map<const BSDF *, int> bsdf_index;
             std::map<const Emitter *, int> emitter_of_mesh;
             for (auto &shape : scene->shapes()) {
@@ -87,12 +91,12 @@ public:
                 d.n_faces = (uint32_t) mesh->face_count();
                 d.positions = mesh->vertex_positions_buffer().data();
                 d.normals = mesh->has_vertex_normals() ? mesh->vertex_normals_buffer().data() : nullptr;
-                d.texcoords = nullptr;
+                d.texcoords = mesh->has_vertex_texcoords() ? mesh->vertex_texcoords_buffer().data() : nullptr;   // mesh.h:131-136
                 d.faces = (const uint32_t *) mesh->faces_buffer().data();
                 const BSDF *bsdf = mesh->bsdf();
                 auto it = bsdf_index.find(bsdf);
                 if (it == bsdf_index.end()) {
-                    bsdfs.push_back(convert_bsdf(bsdf, si0));
+                    bsdfs.push_back(convert_bsdf(bsdf, si0, textures));
                     it = bsdf_index.emplace(bsdf, (int) bsdfs.size() - 1).first;
                 }
                 d.bsdf = it->second;
@@ -135,6 +139,7 @@ public:
             desc.n_meshes = (uint32_t) meshes.size(); desc.meshes = meshes.data(); desc.n_top_meshes = desc.n_meshes;
             desc.n_bsdfs = (uint32_t) bsdfs.size(); desc.bsdfs = bsdfs.data();
             desc.n_emitters = (uint32_t) emitters.size(); desc.emitters = emitters.data();
+            desc.n_textures = (uint32_t) textures.size(); desc.textures = textures.empty() ? nullptr : textures.data();
 
             // ---- film + reconstruction filter LUT (rfilter.h:62-65) -------------------------
             B2Film &f = desc.film;
@@ -173,7 +178,16 @@ public:
             rp.max_depth = m_max_depth; rp.rr_depth = m_rr_depth;
             rp.spp = (uint32_t) sensor->sampler()->sample_count();
             rp.samples_per_pass = m_samples_per_pass == (uint32_t) -1 ? 0 : m_samples_per_pass;
-            rp.block_size = m_block_size ? m_block_size : MTS_BLOCK_SIZE;   // pin it: it feeds the seed (integrator.cpp:198)
+            // the block size feeds the per-pixel seed (integrator.cpp:198): when it is not given, derive it exactly
+            // like SamplingIntegrator::render() does from the film size and the thread count (integrator.cpp:88-97)
+            uint32_t block_size = m_block_size;
+            if (block_size == 0) {
+                block_size = MTS_BLOCK_SIZE;
+                size_t n_threads = __global_thread_count;
+                while (!(block_size == 1 || (size_t) hprod((crop_size + (int) block_size - 1) / (int) block_size) >= n_threads))
+                    block_size /= 2;
+            }
+            rp.block_size = block_size;
             rp.seed = m_seed; rp.rank = 0; rp.world_size = 1;
 
             film->prepare({ "X", "Y", "Z", "A", "W" });                  // integrator.cpp:71-73
@@ -227,7 +241,84 @@ private:
     }
 
     /// SmoothDiffuse / SmoothDielectric / RoughConductor / SmoothConductor / SmoothPlastic -> B2Bsdf, anything else: NotImplemented
-    B2Bsdf convert_bsdf(const BSDF *bsdf, const SurfaceInteraction3f &si) const {
+    /// Bitmap lookup as libb2pt performs it (bitmap.cpp:386-474), used only to recover filter_type / wrap_mode,
+    /// which BitmapTextureImpl exposes neither through traverse() nor to_string()
+    static void probe_eval(const B2Texture &t, float su, float sv, float out[3]) {
+        auto wrap = [&](int v, int res) {
+            if (t.wrap == B2_WRAP_CLAMP) return std::max(0, std::min(v, res - 1));
+            int div = v / res, mod = v - div * res;
+            if (mod < 0) mod += res;
+            if (t.wrap == B2_WRAP_MIRROR && !(((div & 1) == 0) != (v < 0))) mod = res - 1 - mod;
+            return mod;
+        };
+        auto fetch = [&](int x, int y, int c) { return t.data[(size_t) (x + y * t.width) * t.channels + (t.channels == 1 ? 0 : c)]; };
+        float u = std::fma(t.to_uv[1], sv, std::fma(t.to_uv[0], su, t.to_uv[2])), v = std::fma(t.to_uv[4], sv, std::fma(t.to_uv[3], su, t.to_uv[5]));
+        if (t.filter == B2_TEXFILTER_BILINEAR) {
+            u = std::fma(u, (float) t.width, -.5f); v = std::fma(v, (float) t.height, -.5f);
+            int ix = (int) std::floor(u), iy = (int) std::floor(v);
+            float w1x = u - (float) ix, w1y = v - (float) iy, w0x = 1.f - w1x, w0y = 1.f - w1y;
+            int x0 = wrap(ix, t.width), x1 = wrap(ix + 1, t.width), y0 = wrap(iy, t.height), y1 = wrap(iy + 1, t.height);
+            for (int c = 0; c < 3; ++c) {
+                float v0 = std::fma(w0x, fetch(x0, y0, c), w1x * fetch(x1, y0, c)), v1 = std::fma(w0x, fetch(x0, y1, c), w1x * fetch(x1, y1, c));
+                out[c] = std::fma(w0y, v0, w1y * v1);
+            }
+        } else {
+            int x = wrap((int) std::floor(u * (float) t.width), t.width), y = wrap((int) std::floor(v * (float) t.height), t.height);
+            for (int c = 0; c < 3; ++c) out[c] = fetch(x, y, c);
+        }
+    }
+
+    /// Texture -> 0 (not spatially varying: the caller evaluates it once) or the 1-based index of a B2Texture
+    int convert_texture(Object *obj, std::vector<B2Texture> &textures) const {
+        Texture *tex = (Texture *) obj;
+        if (!tex || !tex->is_spatially_varying()) return 0;
+        SurfaceInteraction3f si = zero<SurfaceInteraction3f>();
+        ParamCollector pc;
+        tex->traverse(&pc);
+        std::string cls = tex->class_()->name();
+        B2Texture t;
+        std::memset(&t, 0, sizeof t);
+        auto tr = pc.params.find("transform");
+        if (tr == pc.params.end()) Throw("b2path: texture \"%s\" is not supported (checkerboard, bitmap are)", cls);
+        const auto &m = ((ScalarTransform3f *) tr->second.second)->matrix;
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) t.to_uv[3 * r + c] = (float) m(r, c);
+        if (cls == "Checkerboard") {                                  // checkerboard.cpp:40-44, 86-90
+            t.type = B2_TEX_CHECKERBOARD;
+            for (const char *n : { "color0", "color1" }) {
+                Texture *c = (Texture *) pc.objects[n];
+                if (!c || c->is_spatially_varying()) Throw("b2path: checkerboard with nested textures is not supported");
+                Color3f v = c->eval(si);
+                for (int k = 0; k < 3; ++k) (n[5] == '0' ? t.color0 : t.color1)[k] = v[k];
+            }
+        } else if (cls.rfind("BitmapTextureImpl", 0) == 0) {          // bitmap.cpp:561-565, 676-688
+            t.type = B2_TEX_BITMAP;
+            t.channels = cls.find("Impl_1") != std::string::npos ? 1 : 3;
+            auto &data = *(DynamicBuffer<Float> *) pc.params["data"].second;
+            auto &res = *(ScalarVector2i *) pc.params["resolution"].second;
+            t.data = data.data(); t.width = res.x(); t.height = res.y();
+            bool found = false;
+            for (int f = 1; f >= 0 && !found; --f)
+                for (int w = 0; w < 3 && !found; ++w) {
+                    t.filter = f; t.wrap = w;
+                    bool ok = true;
+                    for (int i = 0; i < 11 && ok; ++i)
+                        for (int j = 0; j < 11 && ok; ++j) {
+                            si.uv = Point2f(-1.37f + .371f * i, -1.29f + .353f * j);
+                            Color3f ref = tex->eval(si);
+                            float mine[3]; probe_eval(t, si.uv.x(), si.uv.y(), mine);
+                            for (int k = 0; k < 3; ++k) ok = ok && std::abs(mine[k] - ref[k]) <= 1e-5f * std::max(1.f, std::abs(ref[k]));
+                        }
+                    found = ok;
+                }
+            if (!found) Throw("b2path: could not determine filter_type / wrap_mode of %s", tex->to_string());
+        } else {
+            Throw("b2path: texture \"%s\" is not supported (checkerboard, bitmap are)", cls);
+        }
+        textures.push_back(t);
+        return (int) textures.size();
+    }
+
+    B2Bsdf convert_bsdf(const BSDF *bsdf, const SurfaceInteraction3f &si, std::vector<B2Texture> &textures) const {
         B2Bsdf b;
         std::memset(&b, 0, sizeof b);
         for (int k = 0; k < 3; ++k) b.specular_reflectance[k] = b.specular_transmittance[k] = 1.f;
@@ -235,10 +326,16 @@ private:
         ParamCollector pc;
         const_cast<BSDF *>(bsdf)->traverse(&pc);
         std::string cls = bsdf->class_()->name();
+        for (auto &kv : pc.objects) {       // only (diffuse_)reflectance may be spatially varying
+            Texture *t = dynamic_cast<Texture *>(kv.second);
+            if (t && t->is_spatially_varying() && kv.first != "reflectance" && kv.first != "diffuse_reflectance")
+                Throw("b2path: textured BSDF parameter \"%s\" is not supported", kv.first);
+        }
         auto obj = [&](const char *n) -> Object * { auto it = pc.objects.find(n); return it == pc.objects.end() ? nullptr : it->second; };
         if (cls == "SmoothDiffuse") {
             b.type = B2_BSDF_DIFFUSE;
             eval3(obj("reflectance"), si, b.reflectance, .5f);
+            b.reflectance_texture = convert_texture(obj("reflectance"), textures);
         } else if (cls == "SmoothDielectric") {
             b.type = B2_BSDF_DIELECTRIC;
             b.eta = pc.get_float("eta", 1.5046f / 1.000277f);
@@ -265,6 +362,7 @@ private:
             b.type = B2_BSDF_PLASTIC;
             b.eta = pc.get_float("eta", 1.49f / 1.000277f);
             eval3(obj("diffuse_reflectance"), si, b.reflectance, .5f);
+            b.reflectance_texture = convert_texture(obj("diffuse_reflectance"), textures);
             eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
             // the values parameters_changed() derives (:162-176), with the reference's own functions
             b.inv_eta_2 = 1.f / (b.eta * b.eta);

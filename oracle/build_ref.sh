@@ -49,5 +49,6 @@ find "$B/ext_build/libpng" "$B/ext_build/libjpeg" -name '*.so*' -exec cp -P {} "
 # scene DATA needed to drive the CLI on the GPU box (not source code; stays git-ignored)
 mkdir -p "$OUT/scenes"
 cp -r "$REF/resources/data/scenes/cbox" "$OUT/scenes/cbox"
+cp -r "$REF/resources/data/scenes/matpreview" "$OUT/scenes/matpreview"     # shipped scene of the drop-in test (BASELINE configs[2])
 echo "g++ $(g++ -dumpversion); flags: reference defaults (-O3 -march=native -ffp-contract=fast); host: $(grep -m1 'model name' /proc/cpuinfo | cut -d: -f2)" > "$OUT/BUILD_INFO.txt"
 echo "build_ref: installed $OUT/dist"

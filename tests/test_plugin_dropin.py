@@ -90,3 +90,100 @@ def test_plugin_dropin_materials(tmp_path):
     assert r1.returncode == 0, r1.stdout + r1.stderr
     s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
     assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
+
+
+def _matpreview_xml(integrator, width=171, height=128, spp=16):
+    """The SHIPPED resources/data/scenes/matpreview/matpreview.xml (envmap + checkerboard-textured plane + plastic +
+    serialized meshes with texture coordinates, gaussian filter); only the integrator type, the film size and the
+    sample count are edited."""
+    d = os.path.join(ROOT, "oracle", "_ref", "scenes", "matpreview")
+    x = open(os.path.join(d, "matpreview.xml")).read()
+    x = x.replace('<integrator type="path"/>', f'<integrator type="{integrator}"/>')
+    x = x.replace('name="sample_count" value="64"', f'name="sample_count" value="{spp}"')
+    x = x.replace('name="width" value="683"', f'name="width" value="{width}"').replace('name="height" value="512"', f'name="height" value="{height}"')
+    x = x.replace('value="envmap.exr"', f'value="{d}/envmap.exr"').replace('value="matpreview.serialized"', f'value="{d}/matpreview.serialized"')
+    x = x.replace('<string name="pixel_format" value="rgb" />', '<string name="pixel_format" value="rgb" /><string name="component_format" value="float32"/>'
+                  '<string name="file_format" value="pfm"/>')
+    return x
+
+
+needs_matpreview = pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "scenes", "matpreview", "matpreview.xml")),
+                                      reason="oracle/_ref/scenes/matpreview missing (oracle/build_ref.sh)")
+
+
+@needs_ref
+@needs_matpreview
+@pytest.mark.gpu
+def test_plugin_dropin_shipped_matpreview(tmp_path):
+    """BASELINE configs[2]'s scene as shipped: the reference loads it (serialized meshes, EXR envmap, checkerboard,
+    plastic), b2path converts and renders it on the GPU; compared with the reference's own `path` render."""
+    from tests import golden_cases as G
+    r0, ref_out = _run(_matpreview_xml("path"), tmp_path, "ref_mp")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, b2_out = _run(_matpreview_xml("b2path"), tmp_path, "b2_mp")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    # gaussian filter: atomics order differs from the reference's block merge order -> float rounding only
+    assert s["median_rel"] < 5e-6 and s["rel_l2_unflipped"] < 1e-4 and s["flipped_pixels"] <= max(20, s["pixels"] // 100), s
+
+
+def _write_pfm(path, img):
+    h, w = img.shape[:2]
+    with open(path, "wb") as f:
+        f.write((b"PF" if img.ndim == 3 else b"Pf") + b"\n%d %d\n-1.0\n" % (w, h))
+        f.write(np.ascontiguousarray(img[::-1], "<f4").tobytes())
+
+
+def _uv_obj(src, dst):
+    out = []
+    for line in open(src):
+        cur = line.strip()
+        if cur.startswith("v "):
+            x, y, z = [float(t) for t in cur.split()[1:4]]
+            out += [line if line.endswith("\n") else line + "\n", "vt %r %r\n" % (x / 500.0 + y / 700.0, z / 500.0 + y / 900.0)]
+        elif cur.startswith("f "):
+            toks = []
+            for t in cur.split()[1:]:
+                p = t.split("/")
+                toks.append(f"{p[0]}/{p[0]}" + (f"/{p[2]}" if len(p) > 2 and p[2] else ""))
+            out.append("f " + " ".join(toks) + "\n")
+        else:
+            out.append(line)
+    open(dst, "w").writelines(out)
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_plugin_dropin_bitmap_textures(tmp_path):
+    """Bitmap textures loaded by the reference (PFM -> BitmapTextureImpl), meshes with texture coordinates loaded by
+    its OBJ loader; the adapter recovers filter_type / wrap_mode by probing (they are not exposed by traverse())."""
+    import re
+    from tests import golden_cases as G
+    y, x = np.mgrid[0:6, 0:8].astype(np.float32)
+    _write_pfm(str(tmp_path / "rgb.pfm"), np.clip(np.stack([0.15 + 0.1 * x, 0.9 - 0.12 * y, 0.2 + 0.05 * ((x * 3 + y * 5) % 7)], -1), 0, 1).astype(np.float32))
+    y, x = np.mgrid[0:7, 0:5].astype(np.float32)
+    _write_pfm(str(tmp_path / "gray.pfm"), (0.1 + 0.125 * ((x * 2 + y * 3) % 7)).astype(np.float32))
+
+    def tex(fn, name, filt, wrap, sx, sy):
+        return (f'<texture type="bitmap" name="{name}"><string name="filename" value="{tmp_path}/{fn}"/><string name="filter_type" value="{filt}"/>'
+                f'<string name="wrap_mode" value="{wrap}"/><boolean name="raw" value="true"/><transform name="to_uv"><scale x="{sx}" y="{sy}"/>'
+                f'<translate x="-0.25" y="0.5"/></transform></texture>')
+    mats = {"white": f'<bsdf type="diffuse" id="white">{tex("rgb.pfm", "reflectance", "bilinear", "clamp", 1.5, 1.5)}</bsdf>',
+            "green": f'<bsdf type="diffuse" id="green">{tex("gray.pfm", "reflectance", "nearest", "repeat", 3.0, 2.0)}</bsdf>',
+            "box": f'<bsdf type="plastic" id="box">{tex("rgb.pfm", "diffuse_reflectance", "nearest", "mirror", 2.0, 3.0)}<float name="int_ior" value="1.6"/></bsdf>'}
+
+    def xml(integrator):
+        s = _scene_xml(integrator)
+        for k, v in mats.items():
+            s = re.sub(r'<bsdf type="diffuse" id="%s">.*?</bsdf>' % k, v, s, count=1)
+        for fn in set(re.findall(r'value="([^"]+\.obj)"', s)):
+            dst = str(tmp_path / ("uv_" + os.path.basename(fn)))
+            _uv_obj(fn, dst)
+            s = s.replace(fn, dst)
+        return s
+    r0, ref_out = _run(xml("path"), tmp_path, "ref_t")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, b2_out = _run(xml("b2path"), tmp_path, "b2_t")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
