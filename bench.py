@@ -219,6 +219,9 @@ def main_b2pt(a, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (libb2pt has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # stdout must carry exactly ONE line (the JSON): NCCL_DEBUG=VERSION (set in some images) prints there
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if a.workload == "veach":
         sb = scenes.veach_mis(api.Host(), a.res, a.res * 9 // 16)
