@@ -156,7 +156,7 @@ def main_reference(a, rank):
     dt = time.perf_counter() - t0
     v = float(np.mean([x["value"] for x in vals]))
     cb = dict(vals[-1]); cb["value"] = v
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": a.gpus,
         "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -219,9 +219,6 @@ def main_b2pt(a, rank, world, local_rank):
         raise SystemExit("bench.py: no CUDA device (libb2pt has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # stdout must carry exactly ONE line (the JSON): NCCL_DEBUG=VERSION (set in some images) prints there
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     if a.workload == "veach":
         sb = scenes.veach_mis(api.Host(), a.res, a.res * 9 // 16)
@@ -369,12 +366,28 @@ def main_b2pt(a, rank, world, local_rank):
             line["roofline"] = roof; line["stages"] = stages
         if a.cpu_baseline and world == 1 and a.workload == "cbox":
             line["cpu_baseline"] = cpu_sample(a, 48)      # ~12 s on 128 host threads
-        print(json.dumps(line))
+        emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(text):
+    """The ONE stdout line of the contract."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(text, flush=True)
+
+
 def main():
+    # everything else that libraries write to fd 1 (e.g. NCCL's version banner) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
     if a.impl == "reference":
