@@ -23,7 +23,7 @@ CBOX_RADIANCE = (18.387, 10.9873, 2.75357)
 
 
 def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=None, lift=0.0, instances=None, drop_meshes=(), envmap=None,
-         texcoords=None):
+         texcoords=None, crop=None):
     """cbox-rgb.xml (resources/data/scenes/cbox): 8 OBJ meshes / 38 triangles, one area
     emitter, diffuse rgb BSDFs, perspective sensor fov 39.3077 ('smaller' axis).
 
@@ -63,6 +63,8 @@ def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=
     if envmap is not None:        # dict(rgb=[H,W,3], scale=, to_world=4x4): appended after the shapes (XML order)
         sb.add_envmap(envmap["rgb"], envmap.get("scale", 1.0), envmap.get("to_world"))
     sb.film = host.film_box(width, height) if rfilter == "box" else host.film_gaussian(width, height, 0.5)
+    if crop:                      # (offset_x, offset_y, width, height), film.cpp:17-27
+        sb.film.crop_offset[:] = crop[:2]; sb.film.crop_size[:] = crop[2:]
     to_world = host.look_at((278, 273, -800), (278, 273, -799), (0, 1, 0))
     fov_x = host.parse_fov(39.3077, "smaller", width, height)
     sb.sensor = host.perspective_sensor(to_world, fov_x, 10.0, 2800.0, sb.film)

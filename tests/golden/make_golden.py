@@ -176,6 +176,7 @@ CBOX_XML = """<scene version="2.0.0">
         <film type="hdrfilm">
             <integer name="width" value="{width}"/>
             <integer name="height" value="{height}"/>
+            {crop}
             {rfilter}
             <string name="pixel_format" value="rgb"/>
             <string name="component_format" value="float32"/>
@@ -292,7 +293,7 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
              rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
-             textures=False):
+             textures=False, crop=None):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -349,7 +350,11 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
                       f'<transform name="to_world"><matrix value="{" ".join(str(float(x)) for x in ENV_TO_WORLD)}"/></transform></emitter>')
     rf = '<rfilter type="box"/>' if rfilter == "box" else '<rfilter type="gaussian"/>'
     sp = f'<integer name="samples_per_pass" value="{samples_per_pass}"/>' if samples_per_pass else ""
-    xml = CBOX_XML.format(width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
+    cr = ""
+    if crop:          # film.cpp:17-27
+        cr = (f'<integer name="crop_offset_x" value="{crop[0]}"/><integer name="crop_offset_y" value="{crop[1]}"/>'
+              f'<integer name="crop_width" value="{crop[2]}"/><integer name="crop_height" value="{crop[3]}"/>')
+    xml = CBOX_XML.format(crop=cr, width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
                           block_size=block_size, spp_pass=sp, rfilter=rf, seed=seed,
                           bsdfs="\n    ".join(bs), shapes="\n    ".join(shapes))
     return xml
@@ -417,6 +422,12 @@ GOLDEN = {
     "cbox_64_spp16_beckmann": dict(width=64, height=64, spp=16, materials={"box": ROUGH_BECK}),
     # smooth conductor / plastic
     "cbox_64_spp16_conductor": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": CONDUCTOR, "green": MIRROR}),
+    # film crop window, unbounded depth (Russian roulette only), emitter-only / single-bounce depths, 1 spp
+    "cbox_64_spp16_crop": dict(width=64, height=64, spp=16, no_patch=True, crop=(8, 16, 40, 24)),
+    "cbox_64_spp8_depthinf_rr3": dict(width=64, height=64, spp=8, no_patch=True, max_depth=-1, rr_depth=3),
+    "cbox_64_spp16_depth1": dict(width=64, height=64, spp=16, no_patch=True, max_depth=1),
+    "cbox_64_spp16_depth2": dict(width=64, height=64, spp=16, no_patch=True, max_depth=2),
+    "cbox_48_spp1": dict(width=48, height=48, spp=1, no_patch=True),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }

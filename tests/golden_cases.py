@@ -83,7 +83,7 @@ def load(name, host):
                      materials=_tex_materials(z) if kw.get("textures") else _materials(kw.get("materials")),
                      texcoords={i: z[f"uv_m{i}"] for i in range(8)} if kw.get("textures") else None,
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
-                     instances=kw.get("instances"))
+                     instances=kw.get("instances"), crop=kw.get("crop"))
     if kw.get("extra_emitter"):
         mi = sb.add_mesh(z["extra_positions"], z["extra_faces"], z["extra_normals"], bsdf=1)     # 'white'
         sb.add_area_emitter(mi, tuple(float(x) for x in z["extra_radiance"]))
