@@ -1,20 +1,22 @@
 // b2_kernels.cuh — the wavefront stage kernels (sm_100a).
 //
-// One wavefront iteration = three launches over the SoA lane queues (a lane slot keeps its
-// index for its whole life, so every queue access is a direct, coalesced float4 access):
+// One wavefront iteration = TWO launches per lane set over the SoA lane queues (a lane slot keeps
+// its index for its whole life, so every queue access is a direct, coalesced float4 access):
 //
-//   K2        k_intersect  closest hit of every live lane's ray: BVH4 traversal +
-//                          Mesh::ray_intersect_triangle (mesh.h:194-226)
-//   K4+K1+K6  k_shade      SI fill fused with one iteration of PathIntegrator::sample's loop body
+//   K2+K3(+K6)  k_trace / k_trace_inst
+//                          closest hit of every live lane's ray (BVH4 traversal or the flat leaf scan +
+//                          Mesh::ray_intersect_triangle, mesh.h:194-226) AND any-hit visibility of the
+//                          emitter samples queued by the previous k_shade (scene.cpp:203-207):
+//                          `result += contribution`, and for a path that ended on that bounce the
+//                          film put of the completed sample. k_trace_inst is the persistent-warp,
+//                          dynamic-fetch variant for instanced scenes.
+//   K4+K1+K6+K5 k_shade    SI fill fused with one iteration of PathIntegrator::sample's loop body
 //                          (path.cpp:124-208); a path that ends is put on the film
 //                          (ImageBlock::put, imageblock.cpp:79-172) and the lane regenerates the
 //                          next camera sample of its work item in place (render_sample,
 //                          integrator.cpp:233-262; perspective.cpp:182-216) or fetches the next
-//                          work item; K5: warp-ballot compaction of the emitter samples into the
+//                          work item; warp-ballot compaction of the emitter samples into the
 //                          dense shadow queue (one atomic per warp)
-//   K3(+K6)   k_shadow     any-hit visibility of the emitter samples (scene.cpp:203-207);
-//                          `result += contribution`, and for a path that ended on this bounce
-//                          the film put of the completed sample
 //   (k_init = the regenerate step alone, run once to fill the lanes)
 #pragma once
 #include "b2_device.cuh"
