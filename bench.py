@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--lane-slots", type=int, default=0)
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--no-stage-timing", action="store_true")
-    ap.add_argument("--workload", default="cbox", choices=["cbox", "veach", "grid"],
+    ap.add_argument("--workload", default="cbox", choices=["cbox", "veach", "grid", "matball"],
                     help="cbox = BASELINE configs[1] (the bench line); veach / grid = configs[3] / configs[4] (extra measurements)")
     ap.add_argument("--single-set", action="store_true", help="one lane set on one stream (A/B of the two-stream overlap)")
     return ap.parse_args()
@@ -224,6 +224,8 @@ def main_b2pt(a, rank, world, local_rank):
         sb = scenes.veach_mis(api.Host(), a.res, a.res * 9 // 16)
     elif a.workload == "grid":
         sb = scenes.instanced_grid(api.Host(), a.res, a.res)
+    elif a.workload == "matball":
+        sb = scenes.matball(api.Host(), a.res, a.res * 9 // 16)
     else:
         sb = scenes.cbox(api.Host(), a.res, a.res)
     scene = api.Scene(sb)
@@ -346,6 +348,7 @@ def main_b2pt(a, rank, world, local_rank):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": {"cbox": f"cbox {W}x{H}, {a.spp} spp, max_depth {a.max_depth}, diffuse + area emitter, box filter (BASELINE configs[1])",
                                     "veach": f"veach-mis class {W}x{H}, {a.spp} spp, 4 emitters, dielectric + rough conductors (BASELINE configs[3])",
+                                    "matball": f"rough-conductor (GGX) ball on a checkerboard plane under an environment map, {sb.n_triangles} triangles, {W}x{H}, {a.spp} spp, gaussian filter (BASELINE configs[2] class)",
                                     "grid": f"instanced displaced grid, {sb.n_triangles} triangles x {len(sb.instances)} instances, {W}x{H}, {a.spp} spp (BASELINE configs[4])"}[a.workload], "samples_per_pass": a.spp_per_pass or a.spp, "block_size": 32, "seed": 0,
                        "parallelism": f"pixel blocks b % {world} == rank, one NCCL reduce of the film" if world > 1 else "1 GPU",
                        "l2": "256 MB flush between steps; wavefront queues > L2", "lane_slots": a.lane_slots or "auto"},

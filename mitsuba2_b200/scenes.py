@@ -198,3 +198,40 @@ def instanced_grid(host, width=2048, height=2048, grid=71, lattice=10, seed=1234
     to_world = host.look_at((cam * 0.8, cam * 0.55, cam), (0, 0, 0), (0, 1, 0))
     sb.sensor = host.perspective_sensor(to_world, host.parse_fov(40.0, "x", width, height), 0.05, 1000.0, sb.film)
     return sb
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE configs[2] class ("matpreview roughconductor GGX + envmap"): the shipped matpreview meshes
+# are serialized files only the reference can load (they are exercised through the plugin,
+# tests/test_plugin_dropin.py), so the bench workload is synthesised with the same ingredients: a
+# tessellated ball (rough conductor, GGX) + an inner diffuse base on a checkerboard-textured plane
+# with texture coordinates, lit by a lat-long environment map only.
+# ---------------------------------------------------------------------------------------------
+def _env_image(w=256, h=128):
+    y, x = np.mgrid[0:h, 0:w].astype(np.float32)
+    img = np.zeros((h, w, 3), np.float32)
+    img[..., 0] = 0.3 + 0.5 * (y / (h - 1))
+    img[..., 1] = 0.4 + 0.3 * np.cos(x / (w - 1) * np.float32(6.2831853)) ** 2
+    img[..., 2] = 0.9 - 0.6 * (y / (h - 1))
+    img[h // 6:h // 3, w // 5:w // 5 + w // 10] += np.array([30.0, 24.0, 12.0], np.float32)
+    img[h // 3:h // 2, (3 * w) // 5:(3 * w) // 5 + w // 8] += np.array([2.0, 5.0, 9.0], np.float32)
+    return img.astype(np.float32)
+
+
+def matball(host, width=1920, height=1080, rfilter="gaussian", level=5, alpha=0.1):
+    sb = abi.SceneBuffers()
+    tex = sb.add_checkerboard((0.4, 0.4, 0.4), (0.2, 0.2, 0.2), [[8, 0, 0], [0, 8, 0], [0, 0, 1]])
+    plane_b = sb.add_diffuse(texture=tex)
+    ball_b = sb.add_roughconductor(alpha=alpha, distribution="ggx", eta=(0.2, 0.92, 1.1), k=(3.9, 2.45, 2.14))
+    base_b = sb.add_diffuse((0.18, 0.18, 0.18))
+    pos, nrm, faces = _quad((-6, 0, -6), (-6, 0, 6), (6, 0, 6), (6, 0, -6))
+    sb.add_mesh(pos, faces, nrm, plane_b, texcoords=np.array([[0, 0], [0, 1], [1, 1], [1, 0]], np.float32))
+    pos, nrm, faces = _icosphere((0.0, 1.0, 0.0), 1.0, level)          # 20 * 4^level triangles (level 5: 20480)
+    sb.add_mesh(pos, faces, nrm, ball_b)
+    pos, nrm, faces = _icosphere((1.9, 0.45, 0.8), 0.45, max(level - 2, 1))
+    sb.add_mesh(pos, faces, nrm, base_b)
+    sb.add_envmap(_env_image(), 3.0, np.array([[0, 0, 1, 0], [0, 1, 0, 0], [-1, 0, 0, 0], [0, 0, 0, 1]], np.float32))
+    sb.film = host.film_box(width, height) if rfilter == "box" else host.film_gaussian(width, height, 0.5)
+    to_world = host.look_at((3.7, 2.6, 3.5), (0.2, 0.8, 0.0), (0, 1, 0))
+    sb.sensor = host.perspective_sensor(to_world, host.parse_fov(28.8415, "smaller", width, height), 0.1, 100.0, sb.film)
+    return sb

@@ -155,6 +155,17 @@ def test_instanced_grid_bitexact(b2, oracle):
     assert int((gpu.view(np.uint32) != cpu.view(np.uint32)).sum()) == 0
 
 
+def test_matball_bitexact(b2, oracle):
+    """BASELINE configs[2] class in miniature: GGX rough-conductor ball (BVH in global memory, smooth normals) on a
+    checkerboard-textured plane with texture coordinates, environment-map lighting only: film bit-exact vs oracle."""
+    sb = scenes.matball(b2.Host(), 96, 54, rfilter="box", level=3)
+    rp = abi.render_params(max_depth=6, rr_depth=5, spp=8, block_size=32)
+    gpu, gst, sc = _gpu_render(b2, sb, rp)
+    cpu, cst = _oracle_render(oracle, sb, rp)
+    assert gst["n_segments"] == cst["n_segments"] and gst["n_shadow_rays"] == cst["n_shadow_rays"]
+    assert int((gpu.view(np.uint32) != cpu.view(np.uint32)).sum()) == 0
+
+
 def test_develop(b2, oracle):
     sb, rp, ref = G.load("cbox_64_spp16", b2.Host())
     gpu, gst, sc = _gpu_render(b2, sb, rp)
