@@ -42,6 +42,7 @@ def parse():
                     help="integrator 'samples_per_pass' (integrator.cpp:34); 0 = spp")
     ap.add_argument("--max-depth", type=int, default=6)
     ap.add_argument("--lane-slots", type=int, default=0)
+    ap.add_argument("--rfilter", default=None, choices=["box", "gaussian"], help="matball: override the reconstruction filter")
     ap.add_argument("--cpu-baseline", type=int, default=1)
     ap.add_argument("--no-stage-timing", action="store_true")
     ap.add_argument("--workload", default="cbox", choices=["cbox", "veach", "grid", "matball"],
@@ -225,7 +226,7 @@ def main_b2pt(a, rank, world, local_rank):
     elif a.workload == "grid":
         sb = scenes.instanced_grid(api.Host(), a.res, a.res)
     elif a.workload == "matball":
-        sb = scenes.matball(api.Host(), a.res, a.res * 9 // 16)
+        sb = scenes.matball(api.Host(), a.res, a.res * 9 // 16, rfilter=a.rfilter or "gaussian")
     else:
         sb = scenes.cbox(api.Host(), a.res, a.res)
     scene = api.Scene(sb)

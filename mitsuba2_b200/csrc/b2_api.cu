@@ -94,6 +94,7 @@ struct B2Scene {
     DBuf<uint32_t> sh_f, cnt, item_pixel, item_seed;
     DBuf<unsigned long long> stats;
     DBuf<float> film;
+    DBuf<float> film_wide;          // wide filters: padded accumulation film, 8 floats / pixel
     uint32_t *h_cnt = nullptr;           // pinned readback
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
@@ -549,6 +550,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(s->cnt.alloc(32)); CU(s->stats.alloc(8));
     CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
     CU(s->film.alloc((size_t) W * H * 5));
+    if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 16 * sizeof(uint32_t)));
 
     // The lane slots are split into independent lane SETS, each with its own counters and shadow
@@ -570,7 +572,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.hit_inst = s->d.n_instances ? s->hit_inst.p + o : nullptr;
         q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o; q.sh_r = s->sh_r.p + o; q.sh_f = s->sh_f.p + o;
         q.cnt = s->cnt.p + 4 * k; q.work = s->cnt.p + 16; q.stats = s->stats.p;
-        q.film = s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
+        q.film = wide ? s->film_wide.p : s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
         q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
         q.total_items = (uint32_t) total64; q.n_slots = set_slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
     }
@@ -586,6 +588,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     cudaStream_t streams[4] = { stream, n_sets > 1 ? s->stream2 : stream, s->stream_extra[0], s->stream_extra[1] };
     CU(cudaEventRecord(ev0, stream));
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
+    if (wide) CU(cudaMemsetAsync(s->film_wide.p, 0, (size_t) W * H * 8 * sizeof(float), stream));
     CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
@@ -650,6 +653,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     for (int k = 1; k < n_sets; ++k) { CU(cudaEventRecord(evx[k], streams[k])); CU(cudaStreamWaitEvent(stream, evx[k], 0)); }
     cudaEventDestroy(evs); for (int k = 1; k < 4; ++k) cudaEventDestroy(evx[k]);
     CU(cudaGetLastError());
+    if (wide) { size_t np = (size_t) W * H; k_film_compact<<<(unsigned) ((np + 255) / 256), 256, 0, stream>>>(s->film_wide.p, s->film.p, np); ++launches; }
     CU(cudaEventRecord(ev1, stream));
     CU(cudaEventSynchronize(ev1));
     float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev0, ev1));

@@ -422,9 +422,11 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
                 enabled &= x <= hix;
                 int fx = ox - border + x, fy = oy - border + y;   // film (crop-relative) coordinates
                 if (enabled && fx >= 0 && fy >= 0 && fx < W && fy < H) {
-                    float *dst = film + 5 * ((size_t) fy * W + fx);
-                    #pragma unroll
-                    for (int k = 0; k < 5; ++k) atomicAdd(dst + k, val[k] * weight);
+                    // wide filters accumulate into a padded film (8 floats / pixel: X,Y,Z,A | W,-,-,-) so that a tap is
+                    // one 16-byte vector reduction + one scalar one instead of five (k_film_compact packs it at the end)
+                    float *dst = film + 8 * ((size_t) fy * W + fx);
+                    atomicAdd((float4 *) dst, make_float4(val[0] * weight, val[1] * weight, val[2] * weight, val[3] * weight));
+                    atomicAdd(dst + 4, val[4] * weight);
                 }
             }
         }
@@ -939,6 +941,15 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
         if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
     }
+}
+
+// padded accumulation film of the wide-filter path -> the XYZAW film of the C-ABI
+__global__ void k_film_compact(const float *film8, float *film5, size_t n) {
+    size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = *(const float4 *) (film8 + 8 * i); float w = film8[8 * i + 4];
+    float *d = film5 + 5 * i;
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = w;
 }
 
 // ---- HDRFilm::bitmap(): XYZAW -> RGB (hdrfilm.cpp:251-322, struct.cpp:1750-1812) ----------------
