@@ -115,6 +115,8 @@ typedef struct B2Emitter {
     int32_t env_width, env_height;
     float env_to_world[16];     /* envmap to_world, row-major 4x4                              */
     float env_to_object[16];    /* its inverse, as the reference's Transform stores it         */
+    int32_t shape;              /* area: 0 = attached to `mesh`; k > 0 = attached to B2SceneDesc.shapes[k-1] */
+    int32_t _pad;
 } B2Emitter;
 
 /* ---- meshes (include/mitsuba/render/mesh.h:344-361) ------------------------------------- */
@@ -127,6 +129,20 @@ typedef struct B2Mesh {
     int32_t bsdf;               /* index into B2SceneDesc.bsdfs                                */
     int32_t emitter;            /* index into B2SceneDesc.emitters or -1                       */
 } B2Mesh;
+
+/* ---- analytic shapes (src/shapes/rectangle.cpp, src/shapes/sphere.cpp), top level only ---- */
+enum { B2_SHAPE_RECTANGLE = 0, B2_SHAPE_SPHERE = 1 };
+
+typedef struct B2Shape {
+    int32_t type;               /* B2_SHAPE_*                                                  */
+    int32_t bsdf;               /* index into B2SceneDesc.bsdfs                                */
+    int32_t emitter;            /* index into B2SceneDesc.emitters or -1                       */
+    int32_t flip_normals;       /* sphere 'flip_normals' (rectangle folds it into to_world, rectangle.cpp:75-77) */
+    float to_world[16];         /* row-major m_to_world (sphere: as recomposed by update(), sphere.cpp:127) */
+    float to_object[16];        /* its inverse, as the reference's Transform stores it         */
+    float center[3];            /* sphere m_center                                             */
+    float radius;               /* sphere m_radius                                             */
+} B2Shape;
 
 /* one-level instancing (src/shapes/instance.cpp:107-164, src/librender/shapegroup.cpp) */
 typedef struct B2Instance {
@@ -166,6 +182,9 @@ typedef struct B2SceneDesc {
     B2Sensor sensor;
     B2Film film;
     uint32_t n_textures; const B2Texture *textures;
+    /* analytic shapes; in the closest-hit tie rule they follow all mesh triangles (primitive index = total
+       triangle count + shape index, like a ShapeKDTree whose meshes come first) */
+    uint32_t n_shapes; const B2Shape *shapes;
 } B2SceneDesc;
 
 /* ---- render parameters (integrator.cpp:23-40, sampler.cpp:20-30) ------------------------ */

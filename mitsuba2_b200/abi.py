@@ -50,6 +50,7 @@ class B2Emitter(C.Structure):
         ("envmap", C.POINTER(C.c_float)),
         ("env_width", C.c_int32), ("env_height", C.c_int32),
         ("env_to_world", C.c_float * 16), ("env_to_object", C.c_float * 16),
+        ("shape", C.c_int32), ("_pad", C.c_int32),
     ]
 
 
@@ -59,6 +60,17 @@ class B2Mesh(C.Structure):
         ("positions", C.POINTER(C.c_float)), ("normals", C.POINTER(C.c_float)),
         ("texcoords", C.POINTER(C.c_float)), ("faces", C.POINTER(C.c_uint32)),
         ("bsdf", C.c_int32), ("emitter", C.c_int32),
+    ]
+
+
+SHAPE_RECTANGLE, SHAPE_SPHERE = range(2)
+
+
+class B2Shape(C.Structure):
+    _fields_ = [
+        ("type", C.c_int32), ("bsdf", C.c_int32), ("emitter", C.c_int32), ("flip_normals", C.c_int32),
+        ("to_world", C.c_float * 16), ("to_object", C.c_float * 16),
+        ("center", C.c_float * 3), ("radius", C.c_float),
     ]
 
 
@@ -94,6 +106,7 @@ class B2SceneDesc(C.Structure):
         ("n_top_meshes", C.c_uint32),
         ("sensor", B2Sensor), ("film", B2Film),
         ("n_textures", C.c_uint32), ("textures", C.POINTER(B2Texture)),
+        ("n_shapes", C.c_uint32), ("shapes", C.POINTER(B2Shape)),
     ]
 
 
@@ -290,6 +303,43 @@ class SceneBuffers:
                  texcoords=None if texcoords is None else np.ascontiguousarray(texcoords, np.float32).reshape(-1, 2))
         self.meshes.append(m); return len(self.meshes) - 1
 
+    # -- analytic shapes (top level; handles are 0-based indices into B2SceneDesc.shapes) ----------
+    def _add_shape(self, sh, to_world, bsdf):
+        m = np.asarray(to_world, np.float32).reshape(4, 4)
+        inv = np.linalg.inv(m.astype(np.float64)).astype(np.float32)
+        sh.to_world[:] = [float(x) for x in m.reshape(-1)]
+        sh.to_object[:] = [float(x) for x in inv.reshape(-1)]
+        sh.bsdf = bsdf; sh.emitter = -1
+        if not hasattr(self, "shapes"):
+            self.shapes = []
+        self.shapes.append(sh)
+        return len(self.shapes) - 1
+
+    def add_rectangle(self, to_world, bsdf=0, flip_normals=False):
+        """Rectangle (src/shapes/rectangle.cpp): the [-1,1]^2 square of the xy plane under to_world (4x4);
+        flip_normals is folded into the transform like the constructor does (:75-77)."""
+        m = np.asarray(to_world, np.float32).reshape(4, 4)
+        if flip_normals:
+            m = (m.astype(np.float64) @ np.diag([1.0, 1.0, -1.0, 1.0])).astype(np.float32)
+        sh = B2Shape(); sh.type = SHAPE_RECTANGLE
+        return self._add_shape(sh, m, bsdf)
+
+    def add_sphere(self, center=(0.0, 0.0, 0.0), radius=1.0, bsdf=0, flip_normals=False):
+        """Sphere (src/shapes/sphere.cpp) given by 'center' / 'radius': to_world = translate(center) * scale(radius)
+        (:100-101); update() recovers exactly these for a shear-free, uniformly scaled transform (:107-130)."""
+        sh = B2Shape(); sh.type = SHAPE_SPHERE
+        sh.center[:] = center; sh.radius = radius; sh.flip_normals = 1 if flip_normals else 0
+        m = np.eye(4, dtype=np.float32)
+        m[0, 0] = m[1, 1] = m[2, 2] = radius; m[:3, 3] = center
+        return self._add_shape(sh, m, bsdf)
+
+    def add_shape_emitter(self, shape_index, radiance):
+        e = B2Emitter(); e.type = EMITTER_AREA; e.mesh = -1; e.shape = shape_index + 1
+        e.radiance[:] = radiance; e.scale = 1.0
+        self.emitters.append(e)
+        self.shapes[shape_index].emitter = len(self.emitters) - 1
+        return len(self.emitters) - 1
+
     def add_shapegroup(self, mesh_indices):
         """Move the given meshes (added with add_mesh) into a new shapegroup; returns its index."""
         self.groups.append(list(mesh_indices)); return len(self.groups) - 1
@@ -346,5 +396,8 @@ class SceneBuffers:
         texs = getattr(self, "textures", [])
         ts = (B2Texture * max(1, len(texs)))(*texs)
         d.n_textures = len(texs); d.textures = ts if texs else None
-        self._keep = [ms, bs, es, gf, ins, ts]
+        shs = getattr(self, "shapes", [])
+        ss = (B2Shape * max(1, len(shs)))(*shs)
+        d.n_shapes = len(shs); d.shapes = ss if shs else None
+        self._keep = [ms, bs, es, gf, ins, ts, ss]
         return d

@@ -440,6 +440,17 @@ static oscene *oscene_create(const B2SceneDesc *d) {
                 for (int k = 0; k < 3; ++k) { if (wc[k] < lo[k]) lo[k] = wc[k]; if (wc[k] > hi[k]) hi[k] = wc[k]; }
             }
         }
+        for (uint32_t k = 0; k < d->n_shapes; ++k) {                   /* Rectangle::bbox rectangle.cpp:94-101, Sphere::bbox sphere.cpp:131-136 */
+            const B2Shape *sh = &d->shapes[k];
+            for (int cnr = 0; cnr < 4; ++cnr) {
+                v3 w;
+                if (sh->type == B2_SHAPE_RECTANGLE) w = xf_point(sh->to_world, v3_make(cnr & 1 ? 1.f : -1.f, cnr & 2 ? 1.f : -1.f, 0.f));
+                else w = cnr & 1 ? v3_make(sh->center[0] - sh->radius, sh->center[1] - sh->radius, sh->center[2] - sh->radius)
+                                 : v3_make(sh->center[0] + sh->radius, sh->center[1] + sh->radius, sh->center[2] + sh->radius);
+                float wc[3] = { w.x, w.y, w.z };
+                for (int q = 0; q < 3; ++q) { if (wc[q] < lo[q]) lo[q] = wc[q]; if (wc[q] > hi[q]) hi[q] = wc[q]; }
+            }
+        }
         v3 c = v3_make((lo[0] + hi[0]) * .5f, (lo[1] + hi[1]) * .5f, (lo[2] + hi[2]) * .5f);   /* bbox.h center() */
         v3 dmax = v3_sub(c, v3_make(hi[0], hi[1], hi[2]));
         float radius = sqrtf(v3_dot(dmax, dmax));                      /* bbox.h:329-332 */
@@ -503,6 +514,44 @@ static inline int hit_better(float t, int inst, uint32_t prim, const ohit *best)
     if (t > best->t || best->prim == 0xffffffffu) return t == best->t;
     uint64_t k = ((uint64_t) (inst + 1) << 32) | prim, kb = ((uint64_t) (best->inst + 1) << 32) | best->prim;
     return k > kb;
+}
+
+/* ---- analytic shapes: Rectangle::ray_intersect_preliminary (rectangle.cpp:139-158) and
+ *      Sphere::ray_intersect_preliminary (sphere.cpp:273-305, in double; math.h:371-413) ---- */
+static inline v3 xf_point(const float *M, v3 p);
+static inline v3 xf_vector(const float *M, v3 d);
+static int shape_intersect(const B2Shape *sh, const oray *ray, float *t_out, float *u_out, float *v_out) {
+    *u_out = 0.f; *v_out = 0.f;
+    if (sh->type == B2_SHAPE_RECTANGLE) {
+        v3 o = xf_point(sh->to_object, ray->o), d = xf_vector(sh->to_object, ray->d);
+        float t = -o.z * b2o_rcp(d.z);
+        float lx = b2o_fma(d.x, t, o.x), ly = b2o_fma(d.y, t, o.y);
+        *t_out = t; *u_out = lx; *v_out = ly;
+        return t >= ray->mint && t <= ray->maxt && fabsf(lx) <= 1.f && fabsf(ly) <= 1.f;
+    }
+    double mint = (double) ray->mint, maxt = (double) ray->maxt;
+    double ox = (double) ray->o.x - (double) sh->center[0], oy = (double) ray->o.y - (double) sh->center[1],
+           oz = (double) ray->o.z - (double) sh->center[2];
+    double dx = ray->d.x, dy = ray->d.y, dz = ray->d.z;
+    double A = (dx * dx + dy * dy) + dz * dz;
+    double B = 2.0 * ((ox * dx + oy * dy) + oz * dz);
+    double C = ((ox * ox + oy * oy) + oz * oz) - (double) sh->radius * (double) sh->radius;
+    /* solve_quadratic */
+    int linear_case = A == 0.0, valid_linear = linear_case && B != 0.0;
+    double x0 = -C / B, x1 = x0;
+    double discrim = __builtin_fma(B, B, -(4.0 * A * C));
+    int valid_quadratic = !linear_case && discrim >= 0.0;
+    if (valid_quadratic) {
+        double sq = sqrt(discrim);
+        double temp = -0.5 * (B + copysign(sq, B));
+        double x0p = temp / A, x1p = C / temp;
+        double x0m = x0p < x1p ? x0p : x1p, x1m = x0p > x1p ? x0p : x1p;     /* min/max (NaN-free here) */
+        x0 = x0m; x1 = x1m;
+    }
+    int found = valid_linear || valid_quadratic;
+    int out_bounds = !(x0 <= maxt && x1 >= mint), in_bounds = x0 < mint && x1 > maxt;
+    *t_out = x0 < mint ? (float) x1 : (float) x0;
+    return found && !out_bounds && !in_bounds;
 }
 
 static void bvh_intersect(const oscene *s, const obvh *b, const oray *ray, int inst, int brute, ohit *best) {
@@ -591,6 +640,12 @@ static ohit scene_intersect(const oscene *s, const oray *ray, int brute) {
         oray ro = instance_ray(&s->desc->instances[i], ray);
         bvh_intersect(s, &s->groups[s->desc->instances[i].group], &ro, (int) i, brute, &best);
     }
+    for (uint32_t k = 0; k < s->desc->n_shapes; ++k) {          /* primitive index = n_tris + k */
+        float t, u, v;
+        if (shape_intersect(&s->desc->shapes[k], ray, &t, &u, &v) && hit_better(t, -1, s->n_tris + k, &best)) {
+            best.t = t; best.u = u; best.v = v; best.prim = s->n_tris + k; best.inst = -1;
+        }
+    }
     return best;
 }
 /* Scene::ray_test (scene.cpp:154-162) */
@@ -601,6 +656,10 @@ static int scene_occluded(const oscene *s, const oray *ray, int brute) {
         oray ro = instance_ray(&s->desc->instances[i], ray);
         if (bvh_occluded(s, &s->groups[s->desc->instances[i].group], &ro, brute)) return 1;
     }
+    for (uint32_t k = 0; k < s->desc->n_shapes; ++k) {
+        float t, u, v;
+        if (shape_intersect(&s->desc->shapes[k], ray, &t, &u, &v)) return 1;
+    }
     return 0;
 }
 
@@ -609,8 +668,9 @@ static int scene_occluded(const oscene *s, const oray *ray, int brute) {
  * ============================================================================================ */
 typedef struct {
     float t; v3 p, n, sh_n, sh_s, sh_t, wi;
-    uint32_t prim; int mesh;
+    uint32_t prim; int mesh;      /* mesh = -1: miss; -2 - k: analytic shape k */
     float uv[2];
+    int bsdf, emitter;            /* of the shape that was hit (-1: none) */
 } osi;
 
 static inline void coordinate_system_s(v3 n, v3 *s) {   /* vector.h:116-136 (first vector only) */
@@ -633,12 +693,49 @@ static inline v3 to_world(const osi *si, v3 v) {   /* frame.h:35-37: s*v.x + t*v
     return v3_add(v3_add(v3_scale(si->sh_s, v.x), v3_scale(si->sh_t, v.y)), v3_scale(si->sh_n, v.z));
 }
 
+static inline v3 xf_normal(const float *inv, v3 n);
+/* Rectangle::compute_surface_interaction (rectangle.cpp:174-207, frame from update() :82-92) and
+ * Sphere::compute_surface_interaction (sphere.cpp:333-395) */
+static void si_fill_shape(const oscene *s, const oray *ray, const ohit *h, osi *si) {
+    uint32_t k = h->prim - s->n_tris;
+    const B2Shape *sh = &s->desc->shapes[k];
+    si->mesh = -2 - (int) k; si->bsdf = sh->bsdf; si->emitter = sh->emitter;
+    v3 dp_du;
+    v3 hitp = v3_make(b2o_fma(ray->d.x, h->t, ray->o.x), b2o_fma(ray->d.y, h->t, ray->o.y), b2o_fma(ray->d.z, h->t, ray->o.z));
+    if (sh->type == B2_SHAPE_RECTANGLE) {
+        si->p = hitp;
+        si->n = v3_normalize(xf_normal(sh->to_object, v3_make(0.f, 0.f, 1.f)));
+        si->sh_n = si->n;
+        dp_du = xf_vector(sh->to_world, v3_make(2.f, 0.f, 0.f));
+        si->uv[0] = b2o_fma(h->u, .5f, .5f); si->uv[1] = b2o_fma(h->v, .5f, .5f);
+    } else {
+        v3 c = v3_make(sh->center[0], sh->center[1], sh->center[2]);
+        v3 n = v3_normalize(v3_sub(hitp, c));
+        si->p = v3_make(b2o_fma(n.x, sh->radius, c.x), b2o_fma(n.y, sh->radius, c.y), b2o_fma(n.z, sh->radius, c.z));
+        v3 local = xf_point(sh->to_object, si->p);
+        float theta = 2.f * b2o_asin(.5f * sqrtf(b2o_sqr(local.x) + b2o_sqr(local.y) + b2o_sqr(local.z - b2o_sign(local.z))));
+        if (!(local.z >= 0.f)) theta = 3.14159265358979323846f - theta;                 /* unit_angle_z */
+        float phi = b2o_atan2(local.y, local.x);
+        if (phi < 0.f) phi += 2.f * B2O_PI;
+        si->uv[0] = phi * (.5f * B2O_INV_PI); si->uv[1] = theta * B2O_INV_PI;
+        dp_du = v3_scale(xf_vector(sh->to_world, v3_make(-local.y, local.x, 0.f)), 2.f * B2O_PI);
+        if (sh->flip_normals) n = v3_neg(n);
+        si->sh_n = n; si->n = n;
+    }
+    si->sh_s = v3_normalize(v3_fnmadd(si->sh_n, v3_dot(si->sh_n, dp_du), dp_du));    /* interaction.h:153-156 */
+    si->sh_t = v3_cross(si->sh_n, si->sh_s);
+    si->wi = to_local(si, v3_neg(ray->d));
+}
+
 static void si_fill(const oscene *s, const oray *ray, const ohit *h, osi *si) {
     memset(si, 0, sizeof *si);
     si->t = h->t; si->prim = h->prim; si->mesh = -1;
+    si->bsdf = -1; si->emitter = -1;
     if (!(h->t < INFINITY)) { si->wi = v3_neg(ray->d); return; }   /* interaction.h:591 */
+    if (h->prim >= s->n_tris) { si_fill_shape(s, ray, h, si); return; }
     const otri *tr = &s->tris[h->prim];
     si->mesh = tr->mesh;
+    si->bsdf = s->desc->meshes[tr->mesh].bsdf; si->emitter = s->desc->meshes[tr->mesh].emitter;
     float b1 = h->u, b2 = h->v, b0 = 1.f - b1 - b2;
     v3 dp0 = v3_sub(tr->p1, tr->p0), dp1 = v3_sub(tr->p2, tr->p0);
     si->p = v3_add(v3_add(v3_scale(tr->p0, b0), v3_scale(tr->p1, b1)), v3_scale(tr->p2, b2));  /* mesh.cpp:484 */
@@ -1034,8 +1131,82 @@ static uint32_t distr_sample(const float *cdf, uint32_t n, float sum, float valu
 
 /* Mesh::sample_position mesh.cpp:352-397 + Shape::sample_direction shape.cpp:292-310 +
    AreaLight::sample_direction area.cpp:121-134 ; returns spec = radiance / pdf (0 if inactive) */
+/* Rectangle: Shape::sample_direction (shape.cpp:292-323) over Rectangle::sample_position (rectangle.cpp:113-128);
+ * Sphere::sample_direction (sphere.cpp:174-253); then AreaLight::sample_direction (area.cpp:118-141) */
+static inline float rect_inv_area(const B2Shape *sh) {        /* rectangle.cpp:82-92, 103-105 */
+    v3 fs = xf_vector(sh->to_world, v3_make(2.f, 0.f, 0.f)), ft = xf_vector(sh->to_world, v3_make(0.f, 2.f, 0.f));
+    v3 c = v3_cross(fs, ft);
+    return b2o_rcp(sqrtf(v3_dot(c, c)));
+}
+static inline float sphere_inv_area(const B2Shape *sh) { return b2o_rcp(4.f * B2O_PI * sh->radius * sh->radius); }   /* sphere.cpp:138-140 */
+static inline v3 square_to_uniform_sphere(float sx, float sy) {      /* warp.h:255-260 */
+    float z = b2o_fma(-2.f, sy, 1.f), r = b2o_safe_sqrt(b2o_fma(-z, z, 1.f));
+    float sn, cs; b2o_sincos(2.f * B2O_PI * sx, &sn, &cs);
+    return v3_make(r * cs, r * sn, z);
+}
+static v3 shape_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
+    const B2Emitter *em = &s->desc->emitters[emitter];
+    const B2Shape *sh = &s->desc->shapes[em->shape - 1];
+    v3 zero = v3_make(0.f, 0.f, 0.f);
+    ds->emitter = emitter;
+    if (sh->type == B2_SHAPE_RECTANGLE) {
+        ds->p = xf_point(sh->to_world, v3_make(sx * 2.f - 1.f, sy * 2.f - 1.f, 0.f));
+        ds->n = v3_normalize(xf_normal(sh->to_object, v3_make(0.f, 0.f, 1.f)));
+        float pdf = rect_inv_area(sh);
+        ds->d = v3_sub(ds->p, ref_p);
+        float dist_squared = v3_dot(ds->d, ds->d);
+        ds->dist = sqrtf(dist_squared);
+        ds->d = v3_scale(ds->d, b2o_rcp(ds->dist));
+        float dp = fabsf(v3_dot(ds->d, ds->n));
+        pdf *= dp != 0.f ? dist_squared / dp : 0.f;
+        ds->pdf = pdf;
+    } else {
+        v3 c = v3_make(sh->center[0], sh->center[1], sh->center[2]);
+        v3 dc_v = v3_sub(c, ref_p);
+        float dc_2 = v3_dot(dc_v, dc_v);
+        float radius_adj = sh->radius * (sh->flip_normals ? (1.f + B2O_RAY_EPS) : (1.f - B2O_RAY_EPS));
+        v3 d;
+        if (dc_2 > b2o_sqr(radius_adj)) {                               /* reference point outside: cone sampling */
+            float inv_dc = b2o_rsqrt(dc_2), sin_theta_max = sh->radius * inv_dc, sin_theta_max_2 = b2o_sqr(sin_theta_max),
+                  inv_sin_theta_max = b2o_rcp(sin_theta_max), cos_theta_max = b2o_safe_sqrt(1.f - sin_theta_max_2);
+            float sin_theta_2 = sin_theta_max_2 > 0.00068523f ? 1.f - b2o_sqr(b2o_fma(cos_theta_max - 1.f, sx, 1.f)) : sin_theta_max_2 * sx,
+                  cos_theta = b2o_safe_sqrt(1.f - sin_theta_2);
+            float cos_alpha = sin_theta_2 * inv_sin_theta_max + cos_theta * b2o_safe_sqrt(b2o_fma(-sin_theta_2, b2o_sqr(inv_sin_theta_max), 1.f)),
+                  sin_alpha = b2o_safe_sqrt(b2o_fma(-cos_alpha, cos_alpha, 1.f));
+            float sin_phi, cos_phi; b2o_sincos(sy * (2.f * B2O_PI), &sin_phi, &cos_phi);
+            v3 fn = v3_scale(dc_v, -inv_dc), fs, ft;                      /* Frame3f(n): coordinate_system(n) */
+            coordinate_system(fn, &fs, &ft);
+            v3 l = v3_make(cos_phi * sin_alpha, sin_phi * sin_alpha, cos_alpha);
+            d = v3_add(v3_add(v3_scale(fs, l.x), v3_scale(ft, l.y)), v3_scale(fn, l.z));
+            ds->p = v3_make(b2o_fma(d.x, sh->radius, c.x), b2o_fma(d.y, sh->radius, c.y), b2o_fma(d.z, sh->radius, c.z));
+            ds->n = d;
+            ds->d = v3_sub(ds->p, ref_p);
+            float dist2 = v3_dot(ds->d, ds->d);
+            ds->dist = sqrtf(dist2);
+            ds->d = v3_scale(ds->d, b2o_rcp(ds->dist));
+            ds->pdf = (.5f * B2O_INV_PI) / (1.f - cos_theta_max);      /* square_to_uniform_cone_pdf, warp.h:481-490 */
+            if (ds->dist == 0.f) ds->pdf = 0.f;
+        } else {                                                        /* inside: uniform area sampling */
+            d = square_to_uniform_sphere(sx, sy);
+            ds->p = v3_make(b2o_fma(d.x, sh->radius, c.x), b2o_fma(d.y, sh->radius, c.y), b2o_fma(d.z, sh->radius, c.z));
+            ds->n = d;
+            ds->d = v3_sub(ds->p, ref_p);
+            float dist2 = v3_dot(ds->d, ds->d);
+            ds->dist = sqrtf(dist2);
+            ds->d = v3_scale(ds->d, b2o_rcp(ds->dist));
+            ds->pdf = sphere_inv_area(sh) * dist2 / fabsf(v3_dot(ds->d, ds->n));
+        }
+        if (sh->flip_normals) ds->n = v3_neg(ds->n);
+    }
+    int active = v3_dot(ds->d, ds->n) < 0.f && ds->pdf != 0.f;            /* area.cpp:131-134 */
+    if (!active) return zero;
+    float ip = b2o_rcp(ds->pdf);
+    return v3_make(em->radiance[0] * ip, em->radiance[1] * ip, em->radiance[2] * ip);
+}
+
 static v3 area_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
     const B2Emitter *em = &s->desc->emitters[emitter];
+    if (em->shape > 0) return shape_sample_direction(s, emitter, ref_p, sx, sy, ds);
     int m = em->mesh;
     const B2Mesh *me = &s->desc->meshes[m];
     const float *cdf = s->cdf[m];
@@ -1091,7 +1262,7 @@ static v3 scene_sample_emitter_direction(const oscene *s, v3 ref_p, float sx, fl
 
 /* Scene::pdf_emitter_direction scene.cpp:216-231 -> AreaLight::pdf_direction area.cpp:168-187
    -> Shape::pdf_direction shape.cpp:312-323 -> Mesh::pdf_position mesh.cpp:417-420 */
-static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 d, v3 n, float dist) {
+static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 ref_p, v3 d, v3 n, float dist) {
     const B2Emitter *em = &s->desc->emitters[emitter];
     if (em->type == B2_EMITTER_ENVMAP) {
         float pdf = env_pdf_direction(s, d);
@@ -1100,9 +1271,16 @@ static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 d, v3 
     }
     float dp = v3_dot(d, n);
     if (!(dp < 0.f)) return 0.f;
-    float pdf = s->cdf_norm[em->mesh];
-    float adp = fabsf(dp);
-    pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;
+    float pdf, adp = fabsf(dp);
+    if (em->shape > 0 && s->desc->shapes[em->shape - 1].type == B2_SHAPE_SPHERE) {     /* Sphere::pdf_direction sphere.cpp:255-267 */
+        const B2Shape *sh = &s->desc->shapes[em->shape - 1];
+        v3 dc = v3_sub(v3_make(sh->center[0], sh->center[1], sh->center[2]), ref_p);
+        float sin_alpha = sh->radius * b2o_rcp(sqrtf(v3_dot(dc, dc))), cos_alpha = b2o_safe_sqrt(1.f - sin_alpha * sin_alpha);
+        pdf = sin_alpha < B2O_ONE_MINUS_EPS ? (.5f * B2O_INV_PI) / (1.f - cos_alpha) : sphere_inv_area(sh) * b2o_sqr(dist) / adp;
+    } else {
+        pdf = em->shape > 0 ? rect_inv_area(&s->desc->shapes[em->shape - 1]) : s->cdf_norm[em->mesh];
+        pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;                                   /* shape.cpp:325-336 */
+    }
     if (s->desc->n_emitters != 1) pdf = pdf * (1.f / (float) s->desc->n_emitters);
     return pdf;
 }
@@ -1304,13 +1482,13 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
     ohit h = scene_intersect(s, &ray, brute); cnt->segments++;
     osi si; si_fill(s, &ray, &h, &si);
     *valid_ray = h.t < INFINITY;
-    int emitter = (si.mesh >= 0) ? d->meshes[si.mesh].emitter : s->env;  /* scene.h:243-253 */
+    int emitter = (si.mesh != -1) ? si.emitter : s->env;  /* scene.h:243-253 */
     int active = 1;
     for (int depth = 1;; ++depth) {
         if (emitter >= 0) {                                               /* path.cpp:128-129 */
             const B2Emitter *em = &d->emitters[emitter];
             v3 ev;
-            if (si.mesh < 0) ev = env_eval(s, ray.d);                     /* envmap.cpp:134-147 (-si.wi = ray.d) */
+            if (si.mesh == -1) ev = env_eval(s, ray.d);                   /* envmap.cpp:134-147 (-si.wi = ray.d) */
             else ev = si.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f); /* area.cpp:63-71 */
             v3 wt = v3_scale(throughput, emission_weight);
             result = v3_add(result, v3_mul(wt, ev));
@@ -1323,7 +1501,7 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         }
         if ((uint32_t) depth >= (uint32_t) rp->max_depth || !active) break;   /* path.cpp:147-149 */
 
-        const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[d->meshes[si.mesh].bsdf], &si), *bsdf = &bsdf_si;
+        const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[si.bsdf], &si), *bsdf = &bsdf_si;
         if (bsdf_is_smooth(bsdf)) {                                       /* path.cpp:153-172 */
             float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
             ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
@@ -1358,13 +1536,13 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         nr.mint = (1.f + v3_hmax_abs(si.p)) * B2O_RAY_EPS; nr.maxt = INFINITY;
         ohit h2 = scene_intersect(s, &nr, brute); cnt->segments++;
         osi si2; si_fill(s, &nr, &h2, &si2);
-        emitter = (si2.mesh >= 0) ? d->meshes[si2.mesh].emitter : s->env;
+        emitter = (si2.mesh != -1) ? si2.emitter : s->env;
         if (emitter >= 0) {                                               /* path.cpp:194-205, records.h:168-174 */
             v3 dd = v3_sub(si2.p, si.p);
             float dist = sqrtf(v3_dot(dd, dd));
             dd = v3_scale(dd, b2o_rcp(dist));
-            if (si2.mesh < 0) dd = nr.d;                                  /* d[!it.is_valid()] = -it.wi (records.h:173) */
-            float emitter_pdf = !bs.delta ? scene_pdf_emitter_direction(s, emitter, dd, si2.sh_n, dist) : 0.f;
+            if (si2.mesh == -1) dd = nr.d;                                /* d[!it.is_valid()] = -it.wi (records.h:173) */
+            float emitter_pdf = !bs.delta ? scene_pdf_emitter_direction(s, emitter, si.p, dd, si2.sh_n, dist) : 0.f;
             emission_weight = mis_weight(bs.pdf, emitter_pdf);
         }
         ray = nr; si = si2;
@@ -1668,7 +1846,7 @@ B2O_API int b2o_stage_si_fill(const B2SceneDesc *d, uint32_t n, const float *ray
         o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z;
         o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
         o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z;
-        o[15] = b2o_u2f(si.mesh >= 0 ? (uint32_t) d->meshes[si.mesh].bsdf : 0xffffffffu);
+        o[15] = b2o_u2f(si.mesh != -1 ? (uint32_t) si.bsdf : 0xffffffffu);
     }
     oscene_destroy(s);
     return 0;

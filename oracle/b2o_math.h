@@ -32,6 +32,7 @@ typedef struct { float x, y, z; } v3;
 /* include/mitsuba/core/math.h:36-38 */
 #define B2O_RAY_EPS    (1500.0f * 5.9604644775390625e-08f)  /* 1500 * 2^-24 (Epsilon<float> = 2^-24) */
 #define B2O_SHADOW_EPS (B2O_RAY_EPS * 10.0f)
+#define B2O_ONE_MINUS_EPS 0.999999940395355225f                   /* math::OneMinusEpsilon<float>, math.h:31-33 */
 
 static inline float b2o_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
 static inline float b2o_rcp(float x) { return 1.0f / x; }
@@ -224,6 +225,12 @@ static inline float b2o_safe_acos(float x) {       /* acos(clamp(x, -1, 1)) */
     float s = sqrtf(z);
     float r = 2.f * b2o_asin_poly(s);
     return x > 0.f ? r : 3.14159265358979323846f - r;
+}
+static inline float b2o_asin(float x) {            /* |x| <= 1 */
+    float ax = fabsf(x);
+    if (ax <= 0.5f) return b2o_asin_poly(x);
+    float r = 1.57079632679489661923f - 2.f * b2o_asin_poly(sqrtf(0.5f * (1.f - ax)));
+    return b2o_mulsign(r, x);
 }
 static inline float b2o_atan2(float y, float x) {
     float ax = fabsf(x), ay = fabsf(y);

@@ -282,6 +282,34 @@ def write_uv_obj(src, dst):
     open(dst, "w").writelines(out)
 
 
+# analytic shapes variant: the luminaire mesh becomes a rectangle emitter (exactly invertible to_world: the
+# [-1,1]^2 square -> 128 x 64 patch facing down), the small box becomes a diffuse sphere, plus a small
+# emissive sphere (sphere emitter sampling) and a rectangle standing on the floor with flipped normals
+SHAPES_SPEC = dict(
+    rect_light=dict(to_world=[[64, 0, 0, 278], [0, 0, -1, 548], [0, 32, 0, 280], [0, 0, 0, 1]], radiance=(18.387, 10.9873, 2.75357)),
+    sphere=dict(center=(186.0, 64.0, 169.0), radius=64.0, bsdf="box"),
+    sphere_light=dict(center=(420.0, 360.0, 300.0), radius=16.0, radiance=(30.0, 30.0, 60.0)),
+    rect_flip=dict(to_world=[[32, 0, 0, 100], [0, 64, 0, 64], [0, 0, 1, 400], [0, 0, 0, 1]], bsdf="green", flip_normals=True),
+)
+
+
+def shapes_xml():
+    sp = SHAPES_SPEC
+    mat = lambda M: " ".join(repr(float(x)) for row in M for x in row)
+    rl, s1, sl, rf = sp["rect_light"], sp["sphere"], sp["sphere_light"], sp["rect_flip"]
+    return [
+        f'<shape type="rectangle"><transform name="to_world"><matrix value="{mat(rl["to_world"])}"/></transform><ref id="light"/>'
+        f'<emitter type="area"><rgb name="radiance" value="{rl["radiance"][0]}, {rl["radiance"][1]}, {rl["radiance"][2]}"/></emitter></shape>',
+        f'<shape type="sphere"><point name="center" x="{s1["center"][0]}" y="{s1["center"][1]}" z="{s1["center"][2]}"/>'
+        f'<float name="radius" value="{s1["radius"]}"/><ref id="{s1["bsdf"]}"/></shape>',
+        f'<shape type="sphere"><point name="center" x="{sl["center"][0]}" y="{sl["center"][1]}" z="{sl["center"][2]}"/>'
+        f'<float name="radius" value="{sl["radius"]}"/><ref id="light"/>'
+        f'<emitter type="area"><rgb name="radiance" value="{sl["radiance"][0]}, {sl["radiance"][1]}, {sl["radiance"][2]}"/></emitter></shape>',
+        f'<shape type="rectangle"><transform name="to_world"><matrix value="{mat(rf["to_world"])}"/></transform>'
+        f'<boolean name="flip_normals" value="true"/><ref id="{rf["bsdf"]}"/></shape>',
+    ]
+
+
 EXTRA_EMITTER_OBJ = """v 150 420 150
 v 260 420 150
 v 260 420 270
@@ -293,7 +321,7 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
              rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
-             textures=False, crop=None):
+             textures=False, crop=None, analytic=False):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -305,6 +333,8 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             bs.append(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>')
     shapes = []
     for fn, bsdf, tr in CBOX_SHAPES:
+        if analytic and fn in ("cbox_luminaire.obj", "cbox_smallbox.obj"):
+            continue                       # replaced by analytic shapes (appended below)
         if envmap is not None and fn in ENV_DROPPED[envmap]:
             continue                       # open scene: the environment must be visible
         if instances is not None and fn == "cbox_largebox.obj":
@@ -334,6 +364,8 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             write_uv_obj(path, dst)
             path = dst
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
+    if analytic:
+        shapes += shapes_xml()
     if textures:
         rgb, gray = tex_images()
         write_pfm(os.path.join(mesh_dir, "tex_rgb.pfm"), rgb); write_pfm(os.path.join(mesh_dir, "tex_gray.pfm"), gray)
@@ -428,6 +460,8 @@ GOLDEN = {
     "cbox_64_spp16_depth1": dict(width=64, height=64, spp=16, no_patch=True, max_depth=1),
     "cbox_64_spp16_depth2": dict(width=64, height=64, spp=16, no_patch=True, max_depth=2),
     "cbox_48_spp1": dict(width=48, height=48, spp=1, no_patch=True),
+    # analytic shapes: rectangle (emitter + flipped), sphere (diffuse + emitter)
+    "cbox_64_spp16_shapes": dict(width=64, height=64, spp=16, no_patch=True, analytic=True),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
@@ -504,6 +538,8 @@ def main():
         if kw.get("envmap"):
             extra.update(env_rgb=env_image(), env_to_world=np.array(ENV_TO_WORLD, np.float32), env_scale=np.float32(1.5),
                          env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
+        if kw.get("analytic"):
+            extra.update(shapes_spec=np.array(repr(SHAPES_SPEC)))
         if kw.get("textures"):
             rgb_t, gray_t = tex_images()
             extra.update(tex_rgb=rgb_t, tex_gray=gray_t, tex_spec=np.array(repr(TEX_SPEC)))

@@ -75,7 +75,7 @@ def load(name, host):
     if kw.get("scene") == "veach":       # BASELINE configs[3] in miniature (mitsuba2_b200.scenes.veach_mis)
         sb = scenes.veach_mis(host, kw["width"], kw["height"])
         return sb, abi.render_params(max_depth=6, rr_depth=5, spp=kw["spp"], block_size=32), z["rgb"]
-    env = None; drop = ()
+    env = None; drop = (0, 6) if kw.get("analytic") else ()      # analytic: luminaire + small box replaced by shapes
     if kw.get("envmap"):
         env = dict(rgb=z["env_rgb"], scale=float(z["env_scale"]), to_world=z["env_to_world"].reshape(4, 4))
         drop = tuple(int(i) for i in z["env_dropped"])
@@ -84,6 +84,16 @@ def load(name, host):
                      texcoords={i: z[f"uv_m{i}"] for i in range(8)} if kw.get("textures") else None,
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
                      instances=kw.get("instances"), crop=kw.get("crop"))
+    if kw.get("analytic"):              # SHAPES_SPEC of make_golden.py; emitters in XML order: rectangle, then sphere
+        sp = ast.literal_eval(str(z["shapes_spec"]))
+        light = 4                        # CBOX_BSDFS order: box, white, red, green, light
+        ids = {"box": 0, "white": 1, "red": 2, "green": 3, "light": 4}
+        r = sb.add_rectangle(sp["rect_light"]["to_world"], bsdf=light)
+        sb.add_shape_emitter(r, sp["rect_light"]["radiance"])
+        sb.add_sphere(sp["sphere"]["center"], sp["sphere"]["radius"], bsdf=ids[sp["sphere"]["bsdf"]])
+        s2 = sb.add_sphere(sp["sphere_light"]["center"], sp["sphere_light"]["radius"], bsdf=light)
+        sb.add_shape_emitter(s2, sp["sphere_light"]["radius"] and sp["sphere_light"]["radiance"])
+        sb.add_rectangle(sp["rect_flip"]["to_world"], bsdf=ids[sp["rect_flip"]["bsdf"]], flip_normals=True)
     if kw.get("extra_emitter"):
         mi = sb.add_mesh(z["extra_positions"], z["extra_faces"], z["extra_normals"], bsdf=1)     # 'white'
         sb.add_area_emitter(mi, tuple(float(x) for x in z["extra_radiance"]))
