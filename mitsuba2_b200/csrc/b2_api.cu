@@ -149,6 +149,14 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         for (uint32_t f = 0; f < 3 * me.n_faces; ++f)
             if (me.faces[f] >= me.n_vertices) return fail(B2_ERR_INVALID, "mesh %u: face index out of range", m);
     }
+    const uint32_t ns = desc->shapes ? desc->n_shapes : 0;
+    for (uint32_t k = 0; k < ns; ++k) {
+        const B2Shape &sh = desc->shapes[k];
+        if (sh.type != B2_SHAPE_RECTANGLE && sh.type != B2_SHAPE_SPHERE) return fail(B2_ERR_INVALID, "shape %u: unsupported type %d", k, sh.type);
+        if (sh.bsdf < 0 || (uint32_t) sh.bsdf >= desc->n_bsdfs) return fail(B2_ERR_INVALID, "shape %u: bad bsdf index", k);
+        if (sh.emitter >= (int32_t) desc->n_emitters) return fail(B2_ERR_INVALID, "shape %u: bad emitter index", k);
+        if (sh.type == B2_SHAPE_SPHERE && !(sh.radius > 0.f)) return fail(B2_ERR_INVALID, "shape %u: sphere radius must be positive", k);
+    }
     if (desc->film.crop_size[0] <= 0 || desc->film.crop_size[1] <= 0 || desc->film.crop_size[0] > 65535 || desc->film.crop_size[1] > 65535)
         return fail(B2_ERR_INVALID, "film crop size must be in [1, 65535]");
 
@@ -171,12 +179,44 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     uint32_t n_top_tris = mesh_first[n_top_meshes];
     struct { std::vector<float> nodes; std::vector<uint32_t> order; uint32_t n_nodes = 0, depth = 0; } bvh;
     uint32_t top_nodes = 0;
-    {
+    if (ns == 0) {
         std::vector<B2BvhTri> sub(tris.begin(), tris.begin() + n_top_tris);
         B2Bvh4 b; b2_build_bvh4(sub, b);
         b2_bvh4_append(bvh.nodes, b, 0);
         bvh.order = b.order; bvh.depth = b.depth; top_nodes = b.n_nodes;
+    } else {
+        // analytic shapes share the top-level BVH: primitive boxes = the top-level triangles' boxes, then one box per shape
+        // (Rectangle::bbox rectangle.cpp:94-101, Sphere::bbox sphere.cpp:131-136); shape k is primitive nt + k
+        std::vector<B2BvhBox> boxes(n_top_tris + ns);
+        for (uint32_t i = 0; i < n_top_tris; ++i) {
+            B2BvhBox &bx = boxes[i];
+            for (int k = 0; k < 3; ++k) { bx.lo[k] = INFINITY; bx.hi[k] = -INFINITY; }
+            for (int v = 0; v < 3; ++v) for (int k = 0; k < 3; ++k) { bx.lo[k] = std::min(bx.lo[k], tris[i].p[v][k]); bx.hi[k] = std::max(bx.hi[k], tris[i].p[v][k]); }
+        }
+        for (uint32_t k = 0; k < ns; ++k) {
+            const B2Shape &sh = desc->shapes[k];
+            B2BvhBox &bx = boxes[n_top_tris + k];
+            for (int q = 0; q < 3; ++q) { bx.lo[q] = INFINITY; bx.hi[q] = -INFINITY; }
+            if (sh.type == B2_SHAPE_RECTANGLE) {
+                for (int c = 0; c < 4; ++c) for (int r = 0; r < 3; ++r) {
+                    const float *M = sh.to_world + 4 * r;
+                    double w = (double) M[3] + (double) M[0] * (c & 1 ? 1.0 : -1.0) + (double) M[1] * (c & 2 ? 1.0 : -1.0);
+                    bx.lo[r] = std::min(bx.lo[r], std::nextafter((float) w, -INFINITY)); bx.hi[r] = std::max(bx.hi[r], std::nextafter((float) w, INFINITY));
+                }
+            } else {
+                for (int r = 0; r < 3; ++r) {
+                    bx.lo[r] = std::nextafter(sh.center[r] - sh.radius, -INFINITY); bx.hi[r] = std::nextafter(sh.center[r] + sh.radius, INFINITY);
+                }
+            }
+            // the analytic tests work on rounded object-space / double quantities: pad by 1e-4 of the box size
+            for (int q = 0; q < 3; ++q) { float e = 1e-4f * (std::fabs(bx.lo[q]) + std::fabs(bx.hi[q]) + 1e-3f); bx.lo[q] -= e; bx.hi[q] += e; }
+        }
+        B2Bvh4 b; b2_build_bvh4_boxes(boxes, 2, b);
+        b2_bvh4_append(bvh.nodes, b, 0);
+        bvh.order = b.order; bvh.depth = b.depth; top_nodes = b.n_nodes;
+        for (uint32_t &o : bvh.order) if (o >= n_top_tris) o = nt + (o - n_top_tris);
     }
+    const uint32_t n_slots = nt + ns, n_top_prims = n_top_tris + ns;
     std::vector<uint32_t> group_root(desc->n_groups, 0);
     std::vector<B2BvhBox> group_box(desc->n_groups);
     for (uint32_t g = 0; g < desc->n_groups; ++g) {
@@ -224,15 +264,31 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     }
     bvh.n_nodes = (uint32_t) (bvh.nodes.size() / 32);
 
-    std::vector<float4> tri_pos(3 * (size_t) nt), tri_nrm(3 * (size_t) nt), tri_isect(3 * (size_t) nt);
-    std::vector<uint32_t> prim_to_slot(nt);
+    std::vector<float4> tri_pos(3 * (size_t) n_slots), tri_nrm(3 * (size_t) n_slots), tri_isect(3 * (size_t) n_slots);
+    std::vector<uint32_t> prim_to_slot(n_slots);
     bool any_uv = false;
     for (uint32_t m = 0; m < desc->n_meshes; ++m) any_uv = any_uv || desc->meshes[m].texcoords != nullptr;
-    std::vector<float4> tri_uv(any_uv ? 2 * (size_t) nt : 0);
+    std::vector<float4> tri_uv(any_uv ? 2 * (size_t) n_slots : 0);
     auto u2f = [](uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; };
-    for (uint32_t slot = 0; slot < nt; ++slot) {
+    for (uint32_t slot = 0; slot < n_slots; ++slot) {
         uint32_t prim = bvh.order[slot];
         prim_to_slot[prim] = slot;
+        if (prim >= nt) {        // analytic shape: no vertices, (kind, shape index) words instead
+            const uint32_t k = prim - nt;
+            const B2Shape &sh = desc->shapes[k];
+            const uint32_t kind = 1u + (uint32_t) sh.type;
+            tri_isect[3 * (size_t) slot] = make_float4(0.f, 0.f, 0.f, u2f(prim));
+            tri_isect[3 * (size_t) slot + 1] = make_float4(0.f, 0.f, 0.f, u2f(kind));
+            tri_isect[3 * (size_t) slot + 2] = make_float4(0.f, 0.f, 0.f, u2f(k));
+            tri_pos[3 * (size_t) slot] = make_float4(0.f, 0.f, 0.f, u2f(prim));
+            tri_pos[3 * (size_t) slot + 1] = make_float4(0.f, 0.f, 0.f, u2f(0xffffffffu));
+            tri_pos[3 * (size_t) slot + 2] = make_float4(0.f, 0.f, 0.f, u2f(k));
+            tri_nrm[3 * (size_t) slot] = make_float4(0.f, 0.f, 0.f, u2f((uint32_t) sh.bsdf));
+            tri_nrm[3 * (size_t) slot + 1] = make_float4(0.f, 0.f, 0.f, u2f((uint32_t) sh.emitter));
+            tri_nrm[3 * (size_t) slot + 2] = make_float4(0.f, 0.f, 0.f, u2f(1u + kind));      // 2 + type
+            if (any_uv) { tri_uv[2 * (size_t) slot] = make_float4(0.f, 0.f, 0.f, 0.f); tri_uv[2 * (size_t) slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f); }
+            continue;
+        }
         uint32_t m = (uint32_t) (std::upper_bound(mesh_first.begin(), mesh_first.end(), prim) - mesh_first.begin()) - 1;
         const B2Mesh &me = desc->meshes[m];
         uint32_t f = prim - mesh_first[m];
@@ -269,6 +325,13 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &src = desc->emitters[e];
         if (src.type == B2_EMITTER_ENVMAP) { std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; continue; }
+        if (src.shape > 0) {          // area emitter on an analytic shape
+            if ((uint32_t) src.shape > ns) { delete s; return fail(B2_ERR_INVALID, "emitter %u: bad shape index", e); }
+            std::memset(&ems[e], 0, sizeof(DEmitter));
+            ems[e].type = src.type; ems[e].mesh = -1; ems[e].shape = src.shape;
+            std::memcpy(ems[e].radiance, src.radiance, 12);
+            continue;
+        }
         if (src.mesh < 0 || (uint32_t) src.mesh >= desc->n_meshes) { delete s; return fail(B2_ERR_INVALID, "emitter %u: bad mesh index", e); }
         const B2Mesh &me = desc->meshes[src.mesh];
         if (me.n_faces == 0) { delete s; return fail(B2_ERR_INVALID, "Cannot create sampling table for an empty mesh"); }
@@ -290,6 +353,27 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         }
         if (d.valid_first == 0xffffffffu) { delete s; return fail(B2_ERR_INVALID, "DiscreteDistribution: no probability mass found!"); }
         d.cdf_sum = (float) sum; d.cdf_norm = (float) (1.0 / sum);
+    }
+    // analytic shapes: the values Rectangle::update() / Sphere::update() derive (rectangle.cpp:82-92, sphere.cpp:107-130)
+    std::vector<DShape> dshapes(ns);
+    for (uint32_t k = 0; k < ns; ++k) {
+        const B2Shape &sh = desc->shapes[k];
+        DShape &ds = dshapes[k];
+        std::memset(&ds, 0, sizeof ds);
+        ds.type = sh.type; ds.flip_normals = sh.flip_normals; ds.bsdf = sh.bsdf; ds.emitter = sh.emitter;
+        std::memcpy(ds.to_world, sh.to_world, 48); std::memcpy(ds.to_object, sh.to_object, 48);
+        std::memcpy(ds.center, sh.center, 12); ds.radius = sh.radius;
+        if (sh.type == B2_SHAPE_RECTANGLE) {
+            const float *M = sh.to_world, *I = sh.to_object;
+            float fs[3] = { M[0] * 2.f, M[4] * 2.f, M[8] * 2.f }, ft[3] = { M[1] * 2.f, M[5] * 2.f, M[9] * 2.f };     // to_world * (2,0,0) / (0,2,0)
+            float n[3] = { I[8], I[9], I[10] };                                                                       // inverse transpose * (0,0,1)
+            float inv_len = 1.f / std::sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+            for (int q = 0; q < 3; ++q) { ds.n[q] = n[q] * inv_len; ds.dp_du[q] = fs[q]; }
+            float c[3] = { std::fma(fs[1], ft[2], -(fs[2] * ft[1])), std::fma(fs[2], ft[0], -(fs[0] * ft[2])), std::fma(fs[0], ft[1], -(fs[1] * ft[0])) };
+            ds.inv_area = 1.f / std::sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+        } else {
+            ds.inv_area = 1.f / (4.f * 3.14159265358979323846f * sh.radius * sh.radius);
+        }
     }
     std::vector<B2Bsdf> bsdfs(desc->bsdfs, desc->bsdfs + desc->n_bsdfs);
     // textures (checkerboard.cpp, bitmap.cpp): texel data of all bitmaps in one device buffer
@@ -320,7 +404,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     size_t off_pos = 0, off_nrm = off_pos + align16(tri_pos.size() * 16), off_p2s = off_nrm + align16(tri_nrm.size() * 16),
            off_cdf = off_p2s + align16(prim_to_slot.size() * 4), off_bsdf = off_cdf + align16(cdf.size() * 4),
            off_em = off_bsdf + align16(bsdfs.size() * sizeof(B2Bsdf)), off_uv = off_em + align16(ems.size() * sizeof(DEmitter)),
-           off_tex = off_uv + align16(tri_uv.size() * 16), blob_bytes = off_tex + align16(texs.size() * sizeof(B2Texture));
+           off_tex = off_uv + align16(tri_uv.size() * 16), off_shp = off_tex + align16(texs.size() * sizeof(B2Texture)),
+           blob_bytes = off_shp + align16(dshapes.size() * sizeof(DShape));
     std::vector<unsigned char> blob(std::max<size_t>(blob_bytes, 16), 0);
     if (!tri_pos.empty()) std::memcpy(blob.data() + off_pos, tri_pos.data(), tri_pos.size() * 16);
     if (!tri_nrm.empty()) std::memcpy(blob.data() + off_nrm, tri_nrm.data(), tri_nrm.size() * 16);
@@ -330,6 +415,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     if (!ems.empty()) std::memcpy(blob.data() + off_em, ems.data(), ems.size() * sizeof(DEmitter));
     if (!tri_uv.empty()) std::memcpy(blob.data() + off_uv, tri_uv.data(), tri_uv.size() * 16);
     if (!texs.empty()) std::memcpy(blob.data() + off_tex, texs.data(), texs.size() * sizeof(B2Texture));
+    if (!dshapes.empty()) std::memcpy(blob.data() + off_shp, dshapes.data(), dshapes.size() * sizeof(DShape));
     cudaError_t e = cudaSuccess;
     if ((e = s->nodes.upload(nodes)) != cudaSuccess || (e = s->tri_isect.upload(tri_isect)) != cudaSuccess ||
         (e = s->blob.upload(blob)) != cudaSuccess || (e = s->instances.upload(dinst)) != cudaSuccess ||
@@ -346,7 +432,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.bsdfs = (const B2Bsdf *) (s->blob.p + off_bsdf); d.emitters = (const DEmitter *) (s->blob.p + off_em);
     d.tri_uv = tri_uv.empty() ? nullptr : (const float4 *) (s->blob.p + off_uv);
     d.textures = texs.empty() ? nullptr : (const B2Texture *) (s->blob.p + off_tex);
-    if (any_uv || !texs.empty()) s->features |= F_TEX;
+    d.shapes = dshapes.empty() ? nullptr : (const DShape *) (s->blob.p + off_shp);
+    if (any_uv || !texs.empty() || ns) s->features |= F_TEX;
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
     for (const B2Bsdf &b : bsdfs) {
@@ -355,7 +442,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     }
     if (desc->film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f) s->features |= F_WIDE;
     d.instances = desc->n_instances ? s->instances.p : nullptr; d.inst_order = s->inst_order.p;
-    d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_tris;
+    d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_prims;
     // environment map: Hierarchical2D levels (distr_2d.h:372-471) + scene bounding sphere (envmap.cpp:127-131)
     d.env.index = -1;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type == B2_EMITTER_ENVMAP) s->features |= F_ENV;
@@ -431,21 +518,33 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
                 }
             }
         }
+        for (uint32_t k = 0; k < ns; ++k) {                            // Rectangle::bbox rectangle.cpp:94-101, Sphere::bbox sphere.cpp:131-136
+            const B2Shape &sh = desc->shapes[k];
+            for (int cn = 0; cn < 4; ++cn)
+                for (int r = 0; r < 3; ++r) {
+                    float w;
+                    if (sh.type == B2_SHAPE_RECTANGLE) {
+                        const float *M = sh.to_world + 4 * r;
+                        w = std::fma(M[2], 0.f, std::fma(M[1], cn & 2 ? 1.f : -1.f, std::fma(M[0], cn & 1 ? 1.f : -1.f, M[3])));
+                    } else w = cn & 1 ? sh.center[r] - sh.radius : sh.center[r] + sh.radius;
+                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
+                }
+        }
         float c[3] = { (lo[0] + hi[0]) * .5f, (lo[1] + hi[1]) * .5f, (lo[2] + hi[2]) * .5f };
         float dd[3] = { c[0] - hi[0], c[1] - hi[1], c[2] - hi[2] };
         float radius = std::sqrt((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]);     // bbox.h:329-332
         const float ray_eps = 1500.0f * 5.9604644775390625e-08f;
         v.radius = std::max(ray_eps, radius * (1.f + ray_eps));
     }
-    d.n_nodes = bvh.n_nodes; d.n_tris = nt; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
+    d.n_nodes = bvh.n_nodes; d.n_tris = n_slots; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
     d.sensor = desc->sensor; d.film = desc->film;
     // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
     const uint32_t budget_all = 48 * 1024, budget_top = 32 * 1024;
-    if (bvh.n_nodes * 128u + nt * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
+    if (bvh.n_nodes * 128u + n_slots * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
     else { d.smem_nodes = std::min<uint32_t>(top_nodes, budget_top / 128u); d.smem_tris = 0; }
     // tiny flat scenes: list the BVH leaves (box + code) for the exhaustive leaf scan (traverse_flat)
     d.n_flat_leaves = 0; d.flat_leaves = nullptr;
-    if (d.smem_tris && desc->n_instances == 0 && nt > 0) {
+    if (d.smem_tris && desc->n_instances == 0 && nt > 0 && ns == 0) {
         std::vector<float4> flat;
         for (uint32_t n = 0; n < bvh.n_nodes; ++n)
             for (int k = 0; k < 4; ++k) {
@@ -459,7 +558,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
             }
         if (flat.size() / 2 <= 32 && s->flat_leaves.upload(flat) == cudaSuccess) { d.n_flat_leaves = (uint32_t) (flat.size() / 2); d.flat_leaves = s->flat_leaves.p; }
     }
-    s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? nt * 48u : 0u) + d.n_flat_leaves * 32u);
+    s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? n_slots * 48u : 0u) + d.n_flat_leaves * 32u);
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(shade_variant(s->features), cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
@@ -754,14 +853,14 @@ int b2_stage_occluded(B2Scene *s, uint32_t n, const float *ray_o, const float *r
 }
 
 int b2_stage_si_fill(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, const float *hit, const int32_t *inst, float *si) {
-    (void) ray_o;
-    if (!s || (n && (!ray_d || !hit || !si))) return fail(B2_ERR_INVALID, "b2_stage_si_fill: null argument");
+    if (!s || (n && (!ray_o || !ray_d || !hit || !si))) return fail(B2_ERR_INVALID, "b2_stage_si_fill: null argument");
     if (n == 0) return B2_OK;
-    DBuf<float4> d, h; DBuf<float> out; DBuf<int32_t> di;
-    CU(d.alloc(n)); CU(h.alloc(n)); CU(out.alloc((size_t) n * 16));
+    DBuf<float4> o, d, h; DBuf<float> out; DBuf<int32_t> di;
+    CU(o.alloc(n)); CU(d.alloc(n)); CU(h.alloc(n)); CU(out.alloc((size_t) n * 16));
+    CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(h.p, hit, n * 16, cudaMemcpyHostToDevice));
     if (inst) { CU(di.alloc(n)); CU(cudaMemcpy(di.p, inst, n * 4, cudaMemcpyHostToDevice)); }
-    k_stage_si_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, d.p, h.p, inst ? di.p : nullptr, out.p);
+    k_stage_si_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, o.p, d.p, h.p, inst ? di.p : nullptr, out.p);
     CU(cudaGetLastError());
     CU(cudaMemcpy(si, out.p, (size_t) n * 64, cudaMemcpyDeviceToHost));
     return B2_OK;

@@ -29,6 +29,17 @@ struct DEmitter {
     uint32_t first_prim, n_faces, cdf_offset;
     float cdf_sum, cdf_norm;
     uint32_t valid_first, valid_last;
+    int32_t shape;              // 0: attached to a mesh; k > 0: analytic shape k - 1
+    int32_t _pad[3];
+};
+
+// analytic shapes (src/shapes/rectangle.cpp, sphere.cpp): 3x4 row-major transforms + the values update() derives
+struct DShape {
+    int32_t type, flip_normals, bsdf, emitter;
+    float to_world[12], to_object[12];
+    float center[3], radius;
+    float n[3], inv_area;       // rectangle: m_frame.n; both: m_inv_surface_area
+    float dp_du[3], _pad;       // rectangle: m_frame.s
 };
 
 // environment map (src/emitters/envmap.cpp): RGBA texels + the Hierarchical2D<Float,0> MIP levels
@@ -62,6 +73,7 @@ struct DScene {
     const uint32_t *prim_to_slot;
     const float4 *tri_uv;       // NULL unless a mesh has texture coordinates: (uv0, uv1), (uv2, has_uv, -) per triangle
     const B2Texture *textures;  // `data` patched to device memory
+    const DShape *shapes;       // analytic shapes; their slots carry (kind, shape index) instead of vertices
     uint32_t n_nodes, n_tris, n_emitters, n_bsdfs;
     const DInstance *instances; // NULL for flat scenes
     const uint32_t *inst_order; // TLAS leaf order -> instance index
@@ -91,15 +103,17 @@ struct Tables {
     uint32_t n_emitters;
     const float4 *tri_uv;
     const B2Texture *textures;
+    const DShape *shapes;
 };
 B2_D Tables make_tables(const DScene &sc) {
     Tables t; t.tri_pos = sc.tri_pos; t.tri_nrm = sc.tri_nrm; t.prim_to_slot = sc.prim_to_slot; t.cdf = sc.cdf;
-    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.instances = sc.instances; t.n_emitters = sc.n_emitters; t.tri_uv = sc.tri_uv; t.textures = sc.textures; return t;
+    t.bsdfs = sc.bsdfs; t.emitters = sc.emitters; t.instances = sc.instances; t.n_emitters = sc.n_emitters; t.tri_uv = sc.tri_uv; t.textures = sc.textures; t.shapes = sc.shapes; return t;
 }
 
 // Compile-time scene features: the stage kernels are instantiated per feature set so that a scene
 // pays (instruction cache, registers) only for the BSDFs / emitters / filter it contains.
-// F_TEX: a mesh has texture coordinates (uv-derived dp_du, mesh.cpp:492-511) and / or a BSDF parameter is textured
+// F_TEX ("extended scene"): a mesh has texture coordinates (uv-derived dp_du, mesh.cpp:492-511), a BSDF parameter is
+// textured, or the scene contains analytic shapes
 enum : uint32_t { F_ROUGH = 1u, F_DIELECTRIC = 2u, F_ENV = 4u, F_WIDE = 8u, F_TEX = 16u, F_COUNT = 32u };
 
 struct Ray { float3 o, d; float mint, maxt; };
@@ -118,6 +132,40 @@ B2_D bool tri_intersect(float3 p0, float3 p1, float3 p2, const Ray &ray, float &
     t = dot(e2, qvec) * inv_det;
     active &= t >= ray.mint && t <= ray.maxt;
     return active;
+}
+
+// Rectangle::ray_intersect_preliminary (rectangle.cpp:139-158) / Sphere::ray_intersect_preliminary (sphere.cpp:273-305:
+// the quadratic is solved in double, math.h:371-413). M = 3x4 row-major.
+B2_D float3 xf_point(const float *M, float3 p);
+B2_D float3 xf_vector(const float *M, float3 d);
+B2_D bool shape_isect(const DShape &sh, const Ray &ray, float tmax, float &t, float &u, float &v) {
+    u = 0.f; v = 0.f;
+    if (sh.type == B2_SHAPE_RECTANGLE) {
+        float3 o = xf_point(sh.to_object, ray.o), d = xf_vector(sh.to_object, ray.d);
+        t = -o.z * b2_rcp(d.z);
+        u = b2_fma(d.x, t, o.x); v = b2_fma(d.y, t, o.y);
+        return t >= ray.mint && t <= tmax && fabsf(u) <= 1.f && fabsf(v) <= 1.f;
+    }
+    double mint = (double) ray.mint, maxt = (double) tmax;
+    double ox = (double) ray.o.x - (double) sh.center[0], oy = (double) ray.o.y - (double) sh.center[1], oz = (double) ray.o.z - (double) sh.center[2];
+    double dx = ray.d.x, dy = ray.d.y, dz = ray.d.z;
+    double A = (dx * dx + dy * dy) + dz * dz;
+    double B = 2.0 * ((ox * dx + oy * dy) + oz * dz);
+    double C = ((ox * ox + oy * oy) + oz * oz) - (double) sh.radius * (double) sh.radius;
+    bool linear_case = A == 0.0, valid_linear = linear_case && B != 0.0;
+    double x0 = -C / B, x1 = x0;
+    double discrim = fma(B, B, -(4.0 * A * C));
+    bool valid_quadratic = !linear_case && discrim >= 0.0;
+    if (valid_quadratic) {
+        double sq = sqrt(discrim);
+        double temp = -0.5 * (B + copysign(sq, B));
+        double x0p = temp / A, x1p = C / temp;
+        x0 = x0p < x1p ? x0p : x1p; x1 = x0p > x1p ? x0p : x1p;
+    }
+    bool found = valid_linear || valid_quadratic;
+    bool out_bounds = !(x0 <= maxt && x1 >= mint), in_bounds = x0 < mint && x1 > maxt;
+    t = x0 < mint ? (float) x1 : (float) x0;
+    return found && !out_bounds && !in_bounds;
 }
 
 // ---- SurfaceInteraction (mesh.cpp:449-545, interaction.h:153-156,571-596) -------------------
@@ -155,9 +203,40 @@ B2_D float3 xf_normal(const float *inv, float3 n) {
 }
 
 template <bool TEX = false>
-B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_d, int inst, SI &si) {
+B2_D void si_fill(const Tables &sc, uint32_t slot, float t, float u, float v, float3 ray_o, float3 ray_d, int inst, SI &si) {
     float4 a0 = B2_LD(&sc.tri_pos[3 * slot]), a1 = B2_LD(&sc.tri_pos[3 * slot + 1]), a2 = B2_LD(&sc.tri_pos[3 * slot + 2]);
     float4 m0 = B2_LD(&sc.tri_nrm[3 * slot]), m1 = B2_LD(&sc.tri_nrm[3 * slot + 1]), m2 = B2_LD(&sc.tri_nrm[3 * slot + 2]);
+    si.bsdf = (int) __float_as_uint(m0.w);
+    si.emitter = (int) __float_as_uint(m1.w);
+    if constexpr (TEX) if (__float_as_uint(m2.w) >= 2u) {           // analytic shape: tri_nrm[..+2].w = 2 + type, tri_pos[..+2].w = index
+        // Rectangle::compute_surface_interaction (rectangle.cpp:174-207) / Sphere:: (sphere.cpp:333-395); (u, v) = prim_uv
+        const DShape &sh = sc.shapes[__float_as_uint(a2.w)];
+        float3 hitp = v3(b2_fma(ray_d.x, t, ray_o.x), b2_fma(ray_d.y, t, ray_o.y), b2_fma(ray_d.z, t, ray_o.z));
+        float3 dp_du;
+        if (sh.type == B2_SHAPE_RECTANGLE) {
+            si.p = hitp;
+            si.n = v3(sh.n[0], sh.n[1], sh.n[2]); si.sh_n = si.n;
+            dp_du = v3(sh.dp_du[0], sh.dp_du[1], sh.dp_du[2]);
+            si.uv = make_float2(b2_fma(u, .5f, .5f), b2_fma(v, .5f, .5f));
+        } else {
+            float3 c = v3(sh.center[0], sh.center[1], sh.center[2]);
+            float3 n = normalize(hitp - c);
+            si.p = v3(b2_fma(n.x, sh.radius, c.x), b2_fma(n.y, sh.radius, c.y), b2_fma(n.z, sh.radius, c.z));
+            float3 local = xf_point(sh.to_object, si.p);
+            float theta = 2.f * b2_asin(.5f * sqrtf(b2_sqr(local.x) + b2_sqr(local.y) + b2_sqr(local.z - b2_sign(local.z))));
+            if (!(local.z >= 0.f)) theta = 3.14159265358979323846f - theta;          // unit_angle_z
+            float phi = b2_atan2(local.y, local.x);
+            if (phi < 0.f) phi += 2.f * B2_PI;
+            si.uv = make_float2(phi * (.5f * B2_INV_PI), theta * B2_INV_PI);
+            dp_du = xf_vector(sh.to_world, v3(-local.y, local.x, 0.f)) * (2.f * B2_PI);
+            if (sh.flip_normals) n = -n;
+            si.sh_n = n; si.n = n;
+        }
+        si.sh_s = normalize(fnmadd(si.sh_n, dot(si.sh_n, dp_du), dp_du));
+        si.sh_t = cross(si.sh_n, si.sh_s);
+        si.wi = to_local(si, -ray_d);
+        return;
+    }
     float3 p0 = v3(a0), p1 = v3(a1), p2 = v3(a2);
     float b1 = u, b2 = v, b0 = 1.f - b1 - b2;
     float3 dp0 = p1 - p0, dp1 = p2 - p0;
@@ -178,7 +257,7 @@ B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_
             }
         }
     }
-    if (__float_as_uint(m2.w))                                   // mesh.cpp:514-519
+    if (__float_as_uint(m2.w) == 1u)                             // mesh.cpp:514-519
         si.sh_n = normalize((v3(m0) * b0 + v3(m1) * b1) + v3(m2) * b2);
     else
         si.sh_n = si.n;
@@ -192,8 +271,6 @@ B2_D void si_fill(const Tables &sc, uint32_t slot, float u, float v, float3 ray_
     si.sh_s = normalize(fnmadd(si.sh_n, dot(si.sh_n, dp_du), dp_du));   // interaction.h:153-156
     si.sh_t = cross(si.sh_n, si.sh_s);
     si.wi = to_local(si, -ray_d);                                // interaction.h:591
-    si.bsdf = (int) __float_as_uint(m0.w);
-    si.emitter = (int) __float_as_uint(m1.w);
 }
 
 // ---- warps (include/mitsuba/core/warp.h) -----------------------------------------------------
@@ -650,8 +727,78 @@ B2_D float3 env_sample_direction(const DEnv &env, float3 ref_p, float sx, float 
     return env_eval_spectrum(env, u, v) * b2_rcp(ds.pdf);
 }
 
+// Rectangle: Shape::sample_direction (shape.cpp:292-323) over Rectangle::sample_position (rectangle.cpp:113-128);
+// Sphere::sample_direction (sphere.cpp:174-253); then AreaLight::sample_direction (area.cpp:118-141)
+B2_D float3 coordinate_system_t(float3 n) {        // vector.h:116-136 (second vector)
+    float sign = b2_sign(n.z);
+    float a = -b2_rcp(sign + n.z);
+    float b = (n.x * n.y) * a;
+    return v3(b, sign + b2_sqr(n.y) * a, -n.y);
+}
+B2_D float3 square_to_uniform_sphere(float sx, float sy) {      // warp.h:255-260
+    float z = b2_fma(-2.f, sy, 1.f), r = b2_safe_sqrt(b2_fma(-z, z, 1.f));
+    float sn, cs; b2_sincos(2.f * B2_PI * sx, &sn, &cs);
+    return v3(r * cs, r * sn, z);
+}
+B2_D float3 shape_sample_direction(const Tables &sc, const DEmitter &em, float3 ref_p, float sx, float sy, DS &ds) {
+    const DShape &sh = sc.shapes[em.shape - 1];
+    if (sh.type == B2_SHAPE_RECTANGLE) {
+        ds.p = xf_point(sh.to_world, v3(sx * 2.f - 1.f, sy * 2.f - 1.f, 0.f));
+        ds.n = v3(sh.n[0], sh.n[1], sh.n[2]);
+        float pdf = sh.inv_area;
+        ds.d = ds.p - ref_p;
+        float dist_squared = dot(ds.d, ds.d);
+        ds.dist = sqrtf(dist_squared);
+        ds.d = ds.d * b2_rcp(ds.dist);
+        float dp = fabsf(dot(ds.d, ds.n));
+        pdf *= dp != 0.f ? dist_squared / dp : 0.f;
+        ds.pdf = pdf;
+    } else {
+        float3 c = v3(sh.center[0], sh.center[1], sh.center[2]);
+        float3 dc_v = c - ref_p;
+        float dc_2 = dot(dc_v, dc_v);
+        float radius_adj = sh.radius * (sh.flip_normals ? (1.f + B2_RAY_EPS) : (1.f - B2_RAY_EPS));
+        float3 dd;
+        if (dc_2 > b2_sqr(radius_adj)) {                              // reference point outside: cone sampling
+            float inv_dc = b2_rsqrt(dc_2), sin_theta_max = sh.radius * inv_dc, sin_theta_max_2 = b2_sqr(sin_theta_max),
+                  inv_sin_theta_max = b2_rcp(sin_theta_max), cos_theta_max = b2_safe_sqrt(1.f - sin_theta_max_2);
+            float sin_theta_2 = sin_theta_max_2 > 0.00068523f ? 1.f - b2_sqr(b2_fma(cos_theta_max - 1.f, sx, 1.f)) : sin_theta_max_2 * sx,
+                  cos_theta = b2_safe_sqrt(1.f - sin_theta_2);
+            float cos_alpha = sin_theta_2 * inv_sin_theta_max + cos_theta * b2_safe_sqrt(b2_fma(-sin_theta_2, b2_sqr(inv_sin_theta_max), 1.f)),
+                  sin_alpha = b2_safe_sqrt(b2_fma(-cos_alpha, cos_alpha, 1.f));
+            float sin_phi, cos_phi; b2_sincos(sy * (2.f * B2_PI), &sin_phi, &cos_phi);
+            float3 fn = dc_v * (-inv_dc), fs = coordinate_system_s(fn), ft = coordinate_system_t(fn);   // Frame3f(n)
+            float3 l = v3(cos_phi * sin_alpha, sin_phi * sin_alpha, cos_alpha);
+            dd = (fs * l.x + ft * l.y) + fn * l.z;
+            ds.p = v3(b2_fma(dd.x, sh.radius, c.x), b2_fma(dd.y, sh.radius, c.y), b2_fma(dd.z, sh.radius, c.z));
+            ds.n = dd;
+            ds.d = ds.p - ref_p;
+            float dist2 = dot(ds.d, ds.d);
+            ds.dist = sqrtf(dist2);
+            ds.d = ds.d * b2_rcp(ds.dist);
+            ds.pdf = (.5f * B2_INV_PI) / (1.f - cos_theta_max);       // square_to_uniform_cone_pdf, warp.h:481-490
+            if (ds.dist == 0.f) ds.pdf = 0.f;
+        } else {                                                       // inside: uniform area sampling
+            dd = square_to_uniform_sphere(sx, sy);
+            ds.p = v3(b2_fma(dd.x, sh.radius, c.x), b2_fma(dd.y, sh.radius, c.y), b2_fma(dd.z, sh.radius, c.z));
+            ds.n = dd;
+            ds.d = ds.p - ref_p;
+            float dist2 = dot(ds.d, ds.d);
+            ds.dist = sqrtf(dist2);
+            ds.d = ds.d * b2_rcp(ds.dist);
+            ds.pdf = sh.inv_area * dist2 / fabsf(dot(ds.d, ds.n));
+        }
+        if (sh.flip_normals) ds.n = -ds.n;
+    }
+    bool active = dot(ds.d, ds.n) < 0.f && ds.pdf != 0.f;             // area.cpp:131-134
+    if (!active) return v3(0.f, 0.f, 0.f);
+    float ip = b2_rcp(ds.pdf);
+    return v3(em.radiance[0] * ip, em.radiance[1] * ip, em.radiance[2] * ip);
+}
+
 template <uint32_t F> B2_D float3 emitter_sample_direction(const Tables &sc, const DEnv &env, uint32_t e, float3 ref_p, float sx, float sy, DS &ds) {
     if constexpr ((F & F_ENV) != 0) if ((int) e == env.index) return env_sample_direction(env, ref_p, sx, sy, ds);
+    if constexpr ((F & F_TEX) != 0) if (sc.emitters[e].shape > 0) return shape_sample_direction(sc, sc.emitters[e], ref_p, sx, sy, ds);
     return area_sample_direction(sc, sc.emitters[e], ref_p, sx, sy, ds);
 }
 
@@ -668,7 +815,7 @@ template <uint32_t F> B2_D float3 scene_sample_emitter_direction(const Tables &s
     return spec * b2_rcp(emitter_pdf);
 }
 
-template <uint32_t F> B2_D float scene_pdf_emitter_direction(const Tables &sc, const DEnv &env, int emitter, float3 d, float3 n, float dist) {   // scene.cpp:216-231
+template <uint32_t F> B2_D float scene_pdf_emitter_direction(const Tables &sc, const DEnv &env, int emitter, float3 ref_p, float3 d, float3 n, float dist) {   // scene.cpp:216-231
     if constexpr ((F & F_ENV) != 0) if (emitter == env.index) {
         float pdf = env_pdf_direction(env, d);
         if (sc.n_emitters != 1) pdf = pdf * (1.f / (float) sc.n_emitters);
@@ -679,7 +826,18 @@ template <uint32_t F> B2_D float scene_pdf_emitter_direction(const Tables &sc, c
     if (!(dp < 0.f)) return 0.f;                                   // area.cpp:170-171
     float pdf = em.cdf_norm;                                       // mesh.cpp:417-420
     float adp = fabsf(dp);
-    pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;                 // shape.cpp:312-323
+    bool sphere = false;
+    if constexpr ((F & F_TEX) != 0) if (em.shape > 0) {
+        const DShape &sh = sc.shapes[em.shape - 1];
+        pdf = sh.inv_area;
+        if (sh.type == B2_SHAPE_SPHERE) {                          // Sphere::pdf_direction, sphere.cpp:255-267
+            sphere = true;
+            float3 dc = v3(sh.center[0], sh.center[1], sh.center[2]) - ref_p;
+            float sin_alpha = sh.radius * b2_rcp(sqrtf(dot(dc, dc))), cos_alpha = b2_safe_sqrt(1.f - sin_alpha * sin_alpha);
+            pdf = sin_alpha < B2_ONE_MINUS_EPS ? (.5f * B2_INV_PI) / (1.f - cos_alpha) : sh.inv_area * b2_sqr(dist) / adp;
+        }
+    }
+    if (!sphere) pdf *= adp != 0.f ? (dist * dist) / adp : 0.f;    // shape.cpp:312-323
     if (sc.n_emitters != 1) pdf = pdf * (1.f / (float) sc.n_emitters);
     return pdf;
 }

@@ -234,7 +234,10 @@ struct Trav {
                     if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
                     else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
                     float t, u, v;
-                    if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
+                    // a slot with a non-zero kind word holds an analytic shape (rectangle / sphere) instead of a triangle
+                    const bool hit = __float_as_uint(a1.w) ? shape_isect(sc.shapes[__float_as_uint(a2.w)], ray, ray.maxt, t, u, v)
+                                                           : tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v);
+                    if (hit) {
                         if (ANY) { any_hit = true; cur = B2_TRAV_DONE; return; }
                         uint32_t prim = __float_as_uint(a0.w);
                         // tie rule: on equal t the larger (instance + 1, prim) key wins
@@ -621,7 +624,9 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     for (uint32_t s = first; s < first + count; ++s) {
                         float4 a0 = __ldg(&sc.tri_isect[3 * (size_t) s]), a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]), a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]);
                         float t, u, v;
-                        if (tri_isect(v3(a0), v3(a1), v3(a2), tr.ray, tr.tmax, t, u, v)) {
+                        const bool hit = __float_as_uint(a1.w) ? shape_isect(sc.shapes[__float_as_uint(a2.w)], tr.ray, tr.ray.maxt, t, u, v)
+                                                               : tri_isect(v3(a0), v3(a1), v3(a2), tr.ray, tr.tmax, t, u, v);
+                        if (hit) {
                             if (any_ray) { tr.any_hit = true; break; }
                             uint32_t prim = __float_as_uint(a0.w);
                             if (t < tr.best.t || (t == tr.best.t && (key_inst > tr.best.inst || (key_inst == tr.best.inst && prim > tr.best.prim)))) {
@@ -812,7 +817,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling ----
         if (valid) {
             bool hit_valid = h.x < B2_INF;
-            if (hit_valid) si_fill<(F & F_TEX) != 0>(tb, __float_as_uint(h.w), h.y, h.z, v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
+            if (hit_valid) si_fill<(F & F_TEX) != 0>(tb, __float_as_uint(h.w), h.x, h.y, h.z, v3(ro), v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
             else if constexpr ((F & F_ENV) != 0) si.emitter = sc.env.index;                // scene->environment(), scene.h:243-253
             if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
             // ---- intersection with emitters (path.cpp:128-129) ----
@@ -825,7 +830,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                         float dist = sqrtf(dot(dd, dd));
                         dd = dd * b2_rcp(dist);
                         if (!hit_valid) dd = v3(rd);                                // d[!it.is_valid()] = -it.wi
-                        emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, dd, si.sh_n, dist);
+                        emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, v3(ro), dd, si.sh_n, dist);
                     }
                     emission_weight = mis_weight(bs_pdf, emitter_pdf);
                 }
@@ -1004,7 +1009,7 @@ __global__ void __launch_bounds__(256) k_stage_occluded(DScene sc, uint32_t n, c
         Hit h; occ[i] = traverse<true, INST>(sc, sm, ray, h) ? 1 : 0;
     }
 }
-__global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, const float4 *hit, const int32_t *inst, float *out) {
+__global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, const float4 *hit, const int32_t *inst, float *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 h = hit[i];
@@ -1016,7 +1021,7 @@ __global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_d, cons
         return;
     }
     uint32_t slot = sc.prim_to_slot[__float_as_uint(h.w)];
-    SI si; si_fill<true>(make_tables(sc), slot, h.y, h.z, v3(ray_d[i]), inst ? inst[i] : -1, si);
+    SI si; si_fill<true>(make_tables(sc), slot, h.x, h.y, h.z, v3(ray_o[i]), v3(ray_d[i]), inst ? inst[i] : -1, si);
     o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z; o[3] = si.n.x; o[4] = si.n.y; o[5] = si.n.z;
     o[6] = si.sh_n.x; o[7] = si.sh_n.y; o[8] = si.sh_n.z; o[9] = si.sh_s.x; o[10] = si.sh_s.y; o[11] = si.sh_s.z;
     o[12] = si.wi.x; o[13] = si.wi.y; o[14] = si.wi.z; o[15] = __uint_as_float((uint32_t) si.bsdf);

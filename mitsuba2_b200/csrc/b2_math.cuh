@@ -25,6 +25,7 @@
 #define B2_EPS         5.9604644775390625e-08f            /* math::Epsilon<float> = 2^-24 */
 #define B2_RAY_EPS     (1500.0f * 5.9604644775390625e-08f)  /* include/mitsuba/core/math.h:36 */
 #define B2_SHADOW_EPS  (B2_RAY_EPS * 10.0f)                /* math.h:38 */
+#define B2_ONE_MINUS_EPS 0.999999940395355225f              /* math::OneMinusEpsilon<float>, math.h:31-33 */
 #define B2_INF         __int_as_float(0x7f800000)
 
 B2_D float b2_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
@@ -205,6 +206,12 @@ B2_D float b2_safe_acos(float x) {
     float s = sqrtf(z);
     float r = 2.f * b2_asin_poly(s);
     return x > 0.f ? r : 3.14159265358979323846f - r;
+}
+B2_D float b2_asin(float x) {            // |x| <= 1
+    float ax = fabsf(x);
+    if (ax <= 0.5f) return b2_asin_poly(x);
+    float r = 1.57079632679489661923f - 2.f * b2_asin_poly(sqrtf(0.5f * (1.f - ax)));
+    return b2_mulsign(r, x);
 }
 B2_D float b2_atan2(float y, float x) {
     float ax = fabsf(x), ay = fabsf(y);
