@@ -52,7 +52,7 @@ enum {
     B2_ERR_NO_DEVICE = 4    /* no CUDA device: the product path has NO CPU fallback           */
 };
 
-/* ---- BSDF records (src/bsdfs/{diffuse,dielectric,roughconductor,conductor,plastic}.cpp) --- */
+/* ---- BSDF records (src/bsdfs/{diffuse,dielectric,roughconductor,conductor,plastic,twosided}.cpp) */
 enum {
     B2_BSDF_DIFFUSE = 0,        /* SmoothDiffuse      diffuse.cpp:78-135                      */
     B2_BSDF_DIELECTRIC = 1,     /* SmoothDielectric   dielectric.cpp:201-320                  */
@@ -85,6 +85,10 @@ typedef struct B2Bsdf {
     float specular_sampling_weight;   /* s_mean / (d_mean + s_mean), plastic.cpp:174           */
     float inv_eta_2;            /* 1 / eta^2                                                   */
     int32_t nonlinear;          /* 'nonlinear' (default 0)                                     */
+    /* TwoSidedBRDF (twosided.cpp:63-92): 0 = one-sided; k > 0 = this record is the front-side BRDF and
+       bsdfs[k-1] the back-side one (k-1 = own index when a single BRDF is nested)             */
+    int32_t twosided_back;
+    int32_t _pad3[3];
 } B2Bsdf;
 
 /* ---- textures (src/textures/{checkerboard,bitmap}.cpp), evaluated at si.uv ----------------- */

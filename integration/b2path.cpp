@@ -96,8 +96,7 @@ public:
                 const BSDF *bsdf = mesh->bsdf();
                 auto it = bsdf_index.find(bsdf);
                 if (it == bsdf_index.end()) {
-                    bsdfs.push_back(convert_bsdf(bsdf, si0, textures));
-                    it = bsdf_index.emplace(bsdf, (int) bsdfs.size() - 1).first;
+                    it = bsdf_index.emplace(bsdf, add_bsdf(bsdf, si0, bsdfs, textures)).first;
                 }
                 d.bsdf = it->second;
                 d.emitter = -1;
@@ -316,6 +315,23 @@ private:
         }
         textures.push_back(t);
         return (int) textures.size();
+    }
+
+    /// Appends the record(s) of a BSDF and returns the index of its (front) record. TwoSidedBRDF (twosided.cpp:63-92,
+    /// 188-191): the nested BRDFs become ordinary records, the front one pointing at the back one.
+    int add_bsdf(const BSDF *bsdf, const SurfaceInteraction3f &si, std::vector<B2Bsdf> &bsdfs, std::vector<B2Texture> &textures) const {
+        if (bsdf && std::string(bsdf->class_()->name()) == "TwoSidedBRDF") {
+            ParamCollector pc;
+            const_cast<BSDF *>(bsdf)->traverse(&pc);
+            const BSDF *b0 = (const BSDF *) pc.objects["brdf_0"], *b1 = (const BSDF *) pc.objects["brdf_1"];
+            int front = add_bsdf(b0, si, bsdfs, textures);
+            int back = b1 == b0 ? front : add_bsdf(b1, si, bsdfs, textures);
+            if (bsdfs[front].twosided_back || bsdfs[back].twosided_back) Throw("b2path: nested twosided BSDFs are not supported");
+            bsdfs[front].twosided_back = back + 1;
+            return front;
+        }
+        bsdfs.push_back(convert_bsdf(bsdf, si, textures));
+        return (int) bsdfs.size() - 1;
     }
 
     B2Bsdf convert_bsdf(const BSDF *bsdf, const SurfaceInteraction3f &si, std::vector<B2Texture> &textures) const {

@@ -26,6 +26,7 @@ class B2Bsdf(C.Structure):
         ("cond_eta", C.c_float * 3), ("_pad1", C.c_float),
         ("cond_k", C.c_float * 3), ("_pad2", C.c_float),
         ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("inv_eta_2", C.c_float), ("nonlinear", C.c_int32),
+        ("twosided_back", C.c_int32), ("_pad3", C.c_int32 * 3),
     ]
 
 
@@ -239,6 +240,16 @@ class SceneBuffers:
         b.specular_sampling_weight = float(s_mean / (d_mean + s_mean))
         b.nonlinear = 1 if nonlinear else 0
         self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def make_twosided(self, front, back=None):
+        """TwoSidedBRDF (src/bsdfs/twosided.cpp): bsdfs[front] becomes two-sided with bsdfs[back] on the back side
+        (back=None: the same BRDF on both sides). Returns `front`. Transmissive BSDFs cannot be nested (:90-91)."""
+        back = front if back is None else back
+        for i in (front, back):
+            if self.bsdfs[i].type == BSDF_DIELECTRIC:
+                raise ValueError("Only materials without a transmission component can be nested!")
+        self.bsdfs[front].twosided_back = back + 1
+        return front
 
     def add_area_emitter(self, mesh_index, radiance):
         e = B2Emitter(); e.type = EMITTER_AREA; e.mesh = mesh_index

@@ -437,6 +437,12 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
     for (const B2Bsdf &b : bsdfs) {
+        if (b.twosided_back != 0) {                                            // twosided.cpp:63-92
+            if (b.twosided_back < 0 || (uint32_t) b.twosided_back > bsdfs.size()) { delete s; return fail(B2_ERR_INVALID, "twosided BSDF: bad back-side index"); }
+            if (b.type == B2_BSDF_DIELECTRIC || bsdfs[b.twosided_back - 1].type == B2_BSDF_DIELECTRIC) {
+                delete s; return fail(B2_ERR_INVALID, "Only materials without a transmission component can be nested!"); }
+            s->features |= F_TEX;
+        }
         if (b.type == B2_BSDF_ROUGHCONDUCTOR) s->features |= F_ROUGH;
         if (b.type == B2_BSDF_DIELECTRIC || b.type == B2_BSDF_CONDUCTOR || b.type == B2_BSDF_PLASTIC) s->features |= F_DIELECTRIC;
     }

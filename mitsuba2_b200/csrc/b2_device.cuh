@@ -432,6 +432,21 @@ template <uint32_t F> B2_D float3 bsdf_reflectance(const Tables &tb, const B2Bsd
 template <uint32_t F> B2_D bool bsdf_is_smooth(const B2Bsdf &b) {     // has_flag(flags, Smooth), path.cpp:155
     return !(F & F_DIELECTRIC) || (b.type != B2_BSDF_DIELECTRIC && b.type != B2_BSDF_CONDUCTOR);
 }
+// The BSDF record that applies at si. TwoSidedBRDF (twosided.cpp:94-186): the front record for cos_theta(wi) > 0, the
+// back record with wi.z mirrored (and the resulting wo.z mirrored by the caller: `flip`) for cos_theta(wi) < 0; at exactly
+// 0 every nestable BRDF evaluates to zero by itself. `smooth` = has_flag(flags, Smooth) over the union of both sides.
+// si.bsdf is updated to the side record's index, si.wi.z is mirrored in place (nothing after the BSDF phase reads wi).
+template <uint32_t F> B2_D const B2Bsdf &bsdf_side(const Tables &tb, SI &si, bool &flip, bool &smooth) {
+    const B2Bsdf *b = &tb.bsdfs[si.bsdf];
+    smooth = bsdf_is_smooth<F>(*b);
+    flip = false;
+    if constexpr ((F & F_TEX) != 0) if (b->twosided_back > 0) {
+        const int back = b->twosided_back - 1;
+        smooth = smooth || bsdf_is_smooth<F>(tb.bsdfs[back]);
+        if (si.wi.z < 0.f) { si.bsdf = back; b = &tb.bsdfs[back]; flip = true; si.wi.z = -si.wi.z; }
+    }
+    return *b;
+}
 // SmoothPlastic: diffuse_reflectance / (1 - fdr_int), optional nonlinear variant (plastic.cpp:231-232, 262-263)
 B2_D float3 plastic_diffuse(const B2Bsdf &b, float3 d) {
     if (b.nonlinear)

@@ -806,7 +806,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         uint4 st = q.st[ld];
         uint32_t pix = __ldg(&q.item_pixel[st.z % q.n_items_pass]);       // pixel of the lane's work item
         bool valid = lane < q.n_slots && rd.w >= 0.f;
-        bool term = false, shadow = false, do_bsdf = false;
+        bool term = false, shadow = false, do_bsdf = false, flip = false;
         float4 sho, shd, shc;
         float4 nro, nrd;                 // next ray
         uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
@@ -853,12 +853,14 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
             if ((uint32_t) depth >= (uint32_t) q.max_depth || !active) term = true;   // path.cpp:147-149
             else {
                 do_bsdf = true;
-                const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
-                if (bsdf_is_smooth<F>(bsdf)) {                                         // path.cpp:153-172
+                bool smooth;
+                const B2Bsdf &bsdf = bsdf_side<F>(tb, si, flip, smooth);            // (twosided: side record, wi.z mirrored)
+                if (smooth) {                                                          // path.cpp:153-172
                     float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
                     DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, sx, sy, ds);
                     if (ds.pdf != 0.f) {
                         float3 wo = to_local(si, ds.d);
+                        if constexpr ((F & F_TEX) != 0) if (flip) wo.z = -wo.z;
                         float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo, bsdf_reflectance<F>(tb, bsdf, si));
                         float bpdf = bsdf_pdf<F>(bsdf, si, wo);
                         float mis = mis_weight(ds.pdf, bpdf);
@@ -889,6 +891,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
             float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
             float s1 = pcg32_next_float(rng);
             BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs, bsdf_reflectance<F>(tb, bsdf, si));
+            if constexpr ((F & F_TEX) != 0) if (flip) bs.wo.z = -bs.wo.z;          // twosided.cpp:122
             throughput = throughput * bsdf_val;
             if (!any_nonzero(throughput)) term = true;                             // path.cpp:182-184
             else {

@@ -40,6 +40,7 @@ def cbox(host, width=256, height=256, rfilter="box", materials=None, meshes_npz=
             bsdf_ids[name] = materials[name](sb)
         else:
             bsdf_ids[name] = sb.add_diffuse(refl)
+    sb.bsdf_ids = bsdf_ids          # cbox BSDF id -> index of its (front) record
     i = 0
     while f"m{i}_positions" in z:
         b = str(z[f"m{i}_bsdf"])

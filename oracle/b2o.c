@@ -934,9 +934,20 @@ static v3 texture_eval(const B2Texture *t, const float si_uv[2]) {
     u *= (float) t->width; v *= (float) t->height;                              /* bitmap.cpp:458-473 */
     return tex_fetch(t, tex_wrap(t, (int) floorf(u), t->width), tex_wrap(t, (int) floorf(v), t->height));
 }
-/* the BSDF record with its textured parameters evaluated at si (Texture::eval(si) inside BSDF::eval/sample) */
-static inline B2Bsdf bsdf_at(const B2SceneDesc *d, const B2Bsdf *b, const osi *si) {
+/* the BSDF record with its textured parameters evaluated at si (Texture::eval(si) inside BSDF::eval/sample).
+ * TwoSidedBRDF (twosided.cpp:94-186): the front record for cos_theta(wi) > 0, the back record (with wi.z and the
+ * resulting wo.z mirrored: *flip = 1) for cos_theta(wi) < 0, nothing at exactly 0 (*side = 0). */
+static inline B2Bsdf bsdf_at(const B2SceneDesc *d, const B2Bsdf *b, const osi *si, int *flip, int *smooth) {
+    *flip = 0;
+    *smooth = b->type != B2_BSDF_DIELECTRIC && b->type != B2_BSDF_CONDUCTOR;       /* has_flag(flags, Smooth), path.cpp:155 */
+    if (b->twosided_back > 0) {
+        const B2Bsdf *back = &d->bsdfs[b->twosided_back - 1];
+        *smooth = *smooth || (back->type != B2_BSDF_DIELECTRIC && back->type != B2_BSDF_CONDUCTOR);   /* union of the nested flags */
+        if (si->wi.z < 0.f) { b = back; *flip = 1; }
+        else if (!(si->wi.z > 0.f)) { B2Bsdf z; memset(&z, 0, sizeof z); z.type = B2_BSDF_NULL; *flip = 0; return z; }   /* both masks false */
+    }
     B2Bsdf r = *b;
+    r.twosided_back = 0;
     if (b->reflectance_texture > 0 && (uint32_t) b->reflectance_texture <= d->n_textures) {
         v3 c = texture_eval(&d->textures[b->reflectance_texture - 1], si->uv);
         r.reflectance[0] = c.x; r.reflectance[1] = c.y; r.reflectance[2] = c.z;
@@ -1501,14 +1512,18 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         }
         if ((uint32_t) depth >= (uint32_t) rp->max_depth || !active) break;   /* path.cpp:147-149 */
 
-        const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[si.bsdf], &si), *bsdf = &bsdf_si;
-        if (bsdf_is_smooth(bsdf)) {                                       /* path.cpp:153-172 */
+        int flip, smooth;
+        const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[si.bsdf], &si, &flip, &smooth), *bsdf = &bsdf_si;
+        osi sib = si;                                                      /* the interaction as the nested BRDF sees it */
+        if (flip) sib.wi.z = -sib.wi.z;
+        if (smooth) {                                                      /* path.cpp:153-172 */
             float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
             ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
             if (ds.pdf != 0.f) {
                 v3 wo = to_local(&si, ds.d);
-                v3 bsdf_val = bsdf_eval(bsdf, &si, wo);
-                float bpdf = bsdf_pdf(bsdf, &si, wo);
+                if (flip) wo.z = -wo.z;
+                v3 bsdf_val = bsdf_eval(bsdf, &sib, wo);
+                float bpdf = bsdf_pdf(bsdf, &sib, wo);
                 float mis = mis_weight(ds.pdf, bpdf);
                 v3 c = v3_mul(v3_mul(v3_scale(throughput, mis), bsdf_val), emitter_val);
                 /* scene.cpp:203-207: spec[ray_test(ray)] = 0. The reference traces the shadow ray
@@ -1527,7 +1542,8 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
            BEFORE next_1d (path.cpp:177-178) */
         float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
         float s1 = pcg32_next_float(rng);
-        obs bs; v3 bsdf_val = bsdf_sample(bsdf, &si, s1, s2x, s2y, &bs);
+        obs bs; v3 bsdf_val = bsdf_sample(bsdf, &sib, s1, s2x, s2y, &bs);
+        if (flip) bs.wo.z = -bs.wo.z;
         throughput = v3_mul(throughput, bsdf_val);
         active &= throughput.x != 0.f || throughput.y != 0.f || throughput.z != 0.f;
         if (!active) break;

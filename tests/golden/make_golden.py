@@ -419,6 +419,9 @@ PLASTIC = '<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.1, 0.27
 PLASTIC_SPEC = ('<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.7, 0.6, 0.5"/>'
                 '<rgb name="specular_reflectance" value="0.8, 0.9, 1.0"/><float name="int_ior" value="1.49"/>'
                 '<float name="ext_ior" value="1.000277"/></bsdf>')
+TWOSIDED_1 = '<bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.45, 0.3, 0.9"/></bsdf></bsdf>'
+TWOSIDED_2 = ('<bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.1, 0.6, 0.1"/></bsdf>'
+              '<bsdf type="roughconductor"><float name="alpha" value="0.2"/></bsdf></bsdf>')
 PLASTIC_NONLINEAR = ('<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.8, 0.3, 0.2"/><boolean name="nonlinear" value="true"/></bsdf>')
 
 # exact-in-fp32 instance transforms: identity, half-size copy, 90-degree rotation about y (floating),
@@ -462,6 +465,8 @@ GOLDEN = {
     "cbox_48_spp1": dict(width=48, height=48, spp=1, no_patch=True),
     # analytic shapes: rectangle (emitter + flipped), sphere (diffuse + emitter)
     "cbox_64_spp16_shapes": dict(width=64, height=64, spp=16, no_patch=True, analytic=True),
+    # twosided: the free-standing flipped rectangle ("green": diffuse front / rough conductor back) is seen from both sides
+    "cbox_64_spp16_twosided": dict(width=64, height=64, spp=16, no_patch=True, analytic=True, materials={"green": TWOSIDED_2, "box": TWOSIDED_1}),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }

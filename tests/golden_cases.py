@@ -24,6 +24,16 @@ def _float(xml, name, default):
 
 def _material(xml):
     """The XML fragments of tests/golden/make_golden.py -> SceneBuffers.add_* calls (plugin defaults as in the reference)."""
+    if 'type="twosided"' in xml:
+        inner = re.findall(r'<bsdf type="(?!twosided)[^"]+".*?</bsdf>', xml)
+
+        def make(sb):
+            front = _material(inner[0])(sb)
+            back = _material(inner[1])(sb) if len(inner) > 1 else None
+            return sb.make_twosided(front, back)
+        return make
+    if 'type="diffuse"' in xml:
+        return lambda sb: sb.add_diffuse(_rgb(xml, "reflectance", (0.5, 0.5, 0.5)))
     if 'type="dielectric"' in xml:
         return lambda sb: sb.add_dielectric(_float(xml, "int_ior", 1.5046), _float(xml, "ext_ior", 1.000277))
     if 'type="roughconductor"' in xml:
@@ -86,8 +96,7 @@ def load(name, host):
                      instances=kw.get("instances"), crop=kw.get("crop"))
     if kw.get("analytic"):              # SHAPES_SPEC of make_golden.py; emitters in XML order: rectangle, then sphere
         sp = ast.literal_eval(str(z["shapes_spec"]))
-        light = 4                        # CBOX_BSDFS order: box, white, red, green, light
-        ids = {"box": 0, "white": 1, "red": 2, "green": 3, "light": 4}
+        ids = sb.bsdf_ids; light = ids["light"]
         r = sb.add_rectangle(sp["rect_light"]["to_world"], bsdf=light)
         sb.add_shape_emitter(r, sp["rect_light"]["radiance"])
         sb.add_sphere(sp["sphere"]["center"], sp["sphere"]["radius"], bsdf=ids[sp["sphere"]["bsdf"]])

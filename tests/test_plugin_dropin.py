@@ -68,13 +68,15 @@ MATERIALS = {
     "box": '<bsdf type="plastic" id="box"><rgb name="diffuse_reflectance" value="0.1, 0.27, 0.36"/><float name="int_ior" value="1.9"/></bsdf>',
     "green": '<bsdf type="conductor" id="green"><rgb name="eta" value="0.2, 0.92, 1.1"/><rgb name="k" value="3.9, 2.45, 2.14"/></bsdf>',
     "red": '<bsdf type="roughconductor" id="red"><string name="distribution" value="ggx"/><float name="alpha" value="0.15"/></bsdf>',
+    "white": ('<bsdf type="twosided" id="white"><bsdf type="diffuse"><rgb name="reflectance" value="0.885809, 0.698859, 0.666422"/></bsdf>'
+              '<bsdf type="diffuse"><rgb name="reflectance" value="0.2, 0.2, 0.8"/></bsdf></bsdf>'),
 }
 
 
 @needs_ref
 @pytest.mark.gpu
 def test_plugin_dropin_materials(tmp_path):
-    """Same, with plastic / conductor / roughconductor BSDFs instantiated by the reference's own plugins and
+    """Same, with plastic / conductor / roughconductor / twosided BSDFs instantiated by the reference's own plugins and
     converted by the adapter (parameters_changed() values taken from the reference's functions)."""
     import re
     from tests import golden_cases as G
