@@ -64,6 +64,14 @@ public:
     B2PathIntegrator(const Properties &props) : Base(props) {
         // the sampler keeps its base seed protected; mirror it here (default 0, like 'independent')
         m_seed = (uint64_t) props.size_("seed", 0);
+#if defined(B2_DIRECT)
+        // DirectIntegrator (direct.cpp:78-100, 106-196) with its default shading_samples = 1 draws the same random numbers
+        // in the same order, with the same MIS weights, as PathIntegrator with max_depth = 2
+        size_t shading = props.size_("shading_samples", 1);
+        if (props.size_("emitter_samples", shading) != 1 || props.size_("bsdf_samples", shading) != 1)
+            NotImplementedError("b2direct: only emitter_samples = bsdf_samples = 1");
+        m_max_depth = 2; m_rr_depth = 5;
+#endif
     }
 
     bool render(Scene *scene, Sensor *sensor) override {

@@ -16,4 +16,12 @@ g++ -DLITTLE_ENDIAN -D__LINUX__ -I"$SRC/include" -I"$SRC/ext/tinyformat" -I"$SRC
     -fomit-frame-pointer -fno-math-errno -ffp-contract=fast -march=native -finline-limit=150 \
     -shared -Wl,-soname,b2path.so -o "$DIST/plugins/b2path.so" "$HERE/b2path.cpp" \
     -Wl,-rpath,'$ORIGIN/..' -L"$DIST" -lmitsuba-render -lmitsuba-core -lb2pt -ltbb -lpthread -ldl
-echo "build_plugin: installed $DIST/plugins/b2path.so"
+# the same adapter as `<integrator type="b2direct">` (DirectIntegrator with shading_samples = 1 == path with max_depth 2)
+TMPD=$(mktemp -d); sed 's/B2PathIntegrator/B2DirectIntegrator/g' "$HERE/b2path.cpp" > "$TMPD/b2direct.cpp"
+g++ -DB2_DIRECT -DLITTLE_ENDIAN -D__LINUX__ -I"$SRC/include" -I"$SRC/ext/tinyformat" -I"$SRC/ext/enoki/include" -I"$SRC/ext/tbb/include" \
+    -I"$ROOT/include" -fpermissive -Wno-changes-meaning -std=gnu++17 -O3 -DNDEBUG -fPIC -fno-stack-protector \
+    -fomit-frame-pointer -fno-math-errno -ffp-contract=fast -march=native -finline-limit=150 \
+    -shared -Wl,-soname,b2direct.so -o "$DIST/plugins/b2direct.so" "$TMPD/b2direct.cpp" \
+    -Wl,-rpath,'$ORIGIN/..' -L"$DIST" -lmitsuba-render -lmitsuba-core -lb2pt -ltbb -lpthread -ldl
+rm -rf "$TMPD"
+echo "build_plugin: installed $DIST/plugins/b2path.so and b2direct.so"

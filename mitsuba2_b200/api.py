@@ -205,3 +205,16 @@ class PathIntegrator:
         _check(lib().b2_render_device(scene._h, C.byref(rp), C.byref(ptr), C.byref(st)))
         self.stats = st.as_dict()
         return ptr.value
+
+
+class DirectIntegrator(PathIntegrator):
+    """DirectIntegrator (src/integrators/direct.cpp) for its default emitter_samples = bsdf_samples = 1: it consumes the
+    sampler exactly like PathIntegrator with max_depth = 2 and uses the same MIS weights (direct.cpp:106-196 vs
+    path.cpp:124-208; pinned by tests/golden/ref_cbox_64_spp16_direct.npz), so it runs on the same wavefront."""
+
+    def __init__(self, shading_samples=1, emitter_samples=None, bsdf_samples=None, samples_per_pass=0, block_size=32):
+        e = shading_samples if emitter_samples is None else emitter_samples
+        b = shading_samples if bsdf_samples is None else bsdf_samples
+        if e != 1 or b != 1:
+            raise NotImplementedError("DirectIntegrator: only emitter_samples = bsdf_samples = 1")
+        super().__init__(max_depth=2, rr_depth=5, samples_per_pass=samples_per_pass, block_size=block_size)

@@ -17,6 +17,7 @@ Usage:  python tests/golden/make_golden.py [--only NAME]
 """
 import argparse
 import os
+import re
 import subprocess
 import sys
 import tempfile
@@ -321,7 +322,7 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
              rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
-             textures=False, crop=None, analytic=False):
+             textures=False, crop=None, analytic=False, integrator="path"):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -389,6 +390,9 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
     xml = CBOX_XML.format(crop=cr, width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
                           block_size=block_size, spp_pass=sp, rfilter=rf, seed=seed,
                           bsdfs="\n    ".join(bs), shapes="\n    ".join(shapes))
+    if integrator == "direct":         # DirectIntegrator (src/integrators/direct.cpp): no depth parameters
+        xml = xml.replace('<integrator type="path">', '<integrator type="direct">')
+        xml = re.sub(r'\s*<integer name="(max_depth|rr_depth)" value="[^"]*"/>', "", xml)
     return xml
 
 
@@ -467,6 +471,9 @@ GOLDEN = {
     "cbox_64_spp16_shapes": dict(width=64, height=64, spp=16, no_patch=True, analytic=True),
     # twosided: the free-standing flipped rectangle ("green": diffuse front / rough conductor back) is seen from both sides
     "cbox_64_spp16_twosided": dict(width=64, height=64, spp=16, no_patch=True, analytic=True, materials={"green": TWOSIDED_2, "box": TWOSIDED_1}),
+    # the reference's `direct` integrator with its default shading_samples = 1 draws the same numbers in the same order as
+    # `path` with max_depth = 2 (direct.cpp:106-196 vs path.cpp:124-208): rendered by `direct`, loaded as max_depth 2
+    "cbox_64_spp16_direct": dict(width=64, height=64, spp=16, no_patch=True, analytic=True, integrator="direct", max_depth=2),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }

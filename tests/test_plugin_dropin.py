@@ -189,3 +189,22 @@ def test_plugin_dropin_bitmap_textures(tmp_path):
     assert r1.returncode == 0, r1.stdout + r1.stderr
     s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
     assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_plugin_dropin_direct_integrator(tmp_path):
+    """`<integrator type="direct">` (shading_samples = 1) vs `<integrator type="b2direct">`: the reference's direct
+    integrator consumes the sampler exactly like `path` with max_depth = 2, which is what b2direct runs on the GPU."""
+    import re
+    from tests import golden_cases as G
+
+    def xml(integrator):
+        s = _scene_xml("path").replace('<integrator type="path">', f'<integrator type="{integrator}">')
+        return re.sub(r'<integer name="max_depth" value="[^"]*"/>', "", s)
+    r0, ref_out = _run(xml("direct"), tmp_path, "ref_d")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, b2_out = _run(xml("b2direct"), tmp_path, "b2_d")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
