@@ -1,0 +1,120 @@
+"""CPU-only: the C-ABI library (mitsuba2_b200/libb2pt.so) loads, exports every entry point include/b2pt.h declares, its
+structs have the layout the ctypes binding assumes, and its HOST helpers (sensor / film / spiral / BVH build — no GPU
+work) agree with the oracle's restatements of the reference's host code. No compute entry point is called without a GPU,
+except to check that it fails loudly."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from mitsuba2_b200 import abi, api, scenes
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "b2pt.h")
+
+
+def _bytes(x):
+    return bytes(memoryview(x)) if not isinstance(x, np.ndarray) else x.tobytes()
+
+
+def test_exports_every_declared_symbol():
+    names = re.findall(r"B2_API\s+[\w\s\*]+?\b(b2_\w+)\s*\(", open(HEADER).read())
+    assert len(names) >= 20, names
+    L = api.lib()
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_the_header(tmp_path):
+    structs = ["B2Bsdf", "B2Texture", "B2Emitter", "B2Mesh", "B2Shape", "B2Instance", "B2Sensor", "B2Film", "B2SceneDesc",
+               "B2RenderParams", "B2Stats"]
+    src = tmp_path / "sz.c"
+    src.write_text('#include "b2pt.h"\n#include <stdio.h>\nint main(void) {\n' +
+                   "".join(f'  printf("{s} %zu\\n", sizeof({s}));\n' for s in structs) + "  return 0;\n}\n")
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    for s in structs:
+        assert int(out[s]) == C.sizeof(getattr(abi, s)), (s, out[s], C.sizeof(getattr(abi, s)))
+
+
+def test_host_helpers_match_oracle(oracle):
+    H, O = api.Host(), oracle.OracleHost()
+    assert _bytes(H.look_at((278, 273, -800), (278, 273, -799), (0, 1, 0))) == _bytes(O.look_at((278, 273, -800), (278, 273, -799), (0, 1, 0)))
+    assert _bytes(H.look_at((3.7, 2.6, 3.5), (0.2, 0.8, 0.0), (0.1, 1, 0.2))) == _bytes(O.look_at((3.7, 2.6, 3.5), (0.2, 0.8, 0.0), (0.1, 1, 0.2)))
+    for axis in ("x", "y", "diagonal", "smaller", "larger"):
+        for w, h in ((64, 64), (96, 54), (48, 80)):
+            assert np.float32(H.parse_fov(39.3077, axis, w, h)) == np.float32(O.parse_fov(39.3077, axis, w, h)), (axis, w, h)
+    for w, h in ((64, 64), (80, 48)):
+        assert _bytes(H.film_box(w, h)) == _bytes(O.film_box(w, h))
+        assert _bytes(H.film_gaussian(w, h, 0.5)) == _bytes(O.film_gaussian(w, h, 0.5))
+    film = H.film_gaussian(96, 54, 0.5)
+    film.crop_offset[:] = (8, 4); film.crop_size[:] = (40, 30)
+    tw = H.look_at((3.7, 2.6, 3.5), (0.2, 0.8, 0.0), (0, 1, 0))
+    assert _bytes(H.perspective_sensor(tw, 28.0, 0.1, 100.0, film)) == _bytes(O.perspective_sensor(tw, 28.0, 0.1, 100.0, film))
+
+
+def test_spiral_matches_oracle(oracle):
+    L = oracle.lib()
+    for w, h, bs in ((64, 64, 32), (80, 48, 32), (100, 37, 16), (33, 33, 8), (1, 1, 32)):
+        mine = api.Host().spiral(w, h, bs)
+        n = C.c_uint32()
+        L.b2o_spiral(w, h, bs, C.byref(n), None)
+        ref = np.zeros((n.value, 2), np.int32)
+        L.b2o_spiral(w, h, bs, C.byref(n), ref.ctypes.data_as(C.POINTER(C.c_int32)))
+        assert mine.shape == ref.shape and np.array_equal(mine, ref), (w, h, bs)
+        # every block exactly once
+        assert len({tuple(b) for b in mine}) == ((w + bs - 1) // bs) * ((h + bs - 1) // bs)
+
+
+def test_host_bvh_is_a_valid_tree():
+    """b2_host_build_bvh4: every triangle appears in exactly one leaf and lies inside all boxes on its path."""
+    L = api.lib()
+    L.b2_host_build_bvh4.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 38, 500):
+        tri = (rng.normal(size=(n, 1, 3)) * 5 + rng.normal(size=(n, 3, 3)) * 0.3).astype(np.float32)
+        nodes = np.zeros((2 * n + 8, 32), np.float32); order = np.zeros(n, np.uint32); nn = C.c_uint32()
+        assert L.b2_host_build_bvh4(tri.ctypes.data, n, nodes.ctypes.data, len(nodes), C.byref(nn), order.ctypes.data) == 0
+        assert sorted(order.tolist()) == list(range(n))
+        seen = np.zeros(n, np.int32)
+        codes = nodes.view(np.int32)
+
+        def walk(node, boxes):
+            for k in range(4):
+                c = int(codes[node, 24 + k])
+                if c == 0:
+                    continue
+                box = (nodes[node, [0 + k, 4 + k, 8 + k]], nodes[node, [12 + k, 16 + k, 20 + k]])
+                if c > 0:
+                    walk(c, boxes + [box])
+                else:
+                    u = c & 0xffffffff; first, count = u & 0x07ffffff, (u >> 27) & 0xf
+                    assert 1 <= count <= 2
+                    for s in range(first, first + count):
+                        t = tri[order[s]]; seen[order[s]] += 1
+                        for lo, hi in boxes + [box]:
+                            assert (t >= lo).all() and (t <= hi).all()
+        walk(0, [])
+        assert (seen == 1).all()
+
+
+def test_compute_entry_points_fail_loudly_without_a_gpu():
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    sb = scenes.cbox(api.Host(), 16, 16)
+    with pytest.raises(api.B2Error) as e:
+        api.Scene(sb)
+    assert e.value.code == 4 and "no CUDA device" in str(e.value)        # B2_ERR_NO_DEVICE: no CPU fallback
+
+
+def test_scene_builders_reject_bad_input():
+    sb = abi.SceneBuffers()
+    d = sb.add_dielectric(1.5, 1.0)
+    with pytest.raises(ValueError):
+        sb.make_twosided(d)                                               # twosided.cpp:90-91
+    with pytest.raises(NotImplementedError):
+        api.DirectIntegrator(shading_samples=2)
