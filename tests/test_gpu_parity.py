@@ -60,10 +60,12 @@ def _random_rays(sb, n, seed):
     return np.ascontiguousarray(ro, np.float32), np.ascontiguousarray(rd, np.float32)
 
 
-def test_intersect_vs_bruteforce(b2, oracle):
+@pytest.mark.parametrize("name", ["cbox", "cbox_64_spp16_shapes", "cbox_64_spp16_textures"])
+def test_intersect_vs_bruteforce(b2, oracle, name):
     """BVH4 traversal == brute force over all triangles (the reference validates its kd-tree the
-    same way: src/librender/tests/test_kdtrees.py:26-101)."""
-    sb = scenes.cbox(b2.Host(), 64, 64)
+    same way: src/librender/tests/test_kdtrees.py:26-101) — also with analytic rectangles / spheres in the
+    top-level BVH and with texture coordinates (uv-derived dp_du in the SurfaceInteraction)."""
+    sb = scenes.cbox(b2.Host(), 64, 64) if name == "cbox" else G.load(name, b2.Host())[0]
     sc = b2.Scene(sb)
     ro, rd = _random_rays(sb, 20000, 3)
     hit = sc.ray_intersect_preliminary(ro, rd)
@@ -165,6 +167,31 @@ def test_matball_bitexact(b2, oracle):
     cpu, cst = _oracle_render(oracle, sb, rp)
     assert gst["n_segments"] == cst["n_segments"] and gst["n_shadow_rays"] == cst["n_shadow_rays"]
     assert int((gpu.view(np.uint32) != cpu.view(np.uint32)).sum()) == 0
+
+
+@pytest.mark.parametrize("workload", ["cbox", "grid"])
+def test_full_size_properties(b2, workload):
+    """BASELINE configs[1] (cbox 1024^2 x 256 spp) and configs[4] (9802 triangles x 1000 instances, 2048^2 x 64 spp)
+    at FULL size, through size-independent properties: every camera sample lands on the film exactly once (box
+    filter: the W channel of a pixel is exactly spp, whatever the pass / lane-slot schedule), alpha <= weight, all
+    values finite and non-negative, no sample rejected, and the image agrees with a low-resolution render of the
+    same scene (pixel-block means) to Monte Carlo accuracy."""
+    if workload == "cbox":
+        W = H = 1024; spp = 256; sb = scenes.cbox(b2.Host(), W, H); small = scenes.cbox(b2.Host(), 64, 64)
+    else:
+        W = H = 2048; spp = 64; sb = scenes.instanced_grid(b2.Host(), W, H); small = scenes.instanced_grid(b2.Host(), 64, 64)
+    integ = b2.PathIntegrator(max_depth=6, rr_depth=5, samples_per_pass=16, block_size=32)
+    film = integ.render(b2.Scene(sb), spp)
+    st = integ.stats
+    assert st["n_samples"] == W * H * spp and st["n_invalid"] == 0
+    assert np.isfinite(film).all() and (film[..., :3] >= -1e-5).all()
+    assert np.array_equal(film[..., 4], np.full((H, W), float(spp), np.float32))          # W: exactly spp per pixel
+    assert (film[..., 3] <= film[..., 4]).all() and (film[..., 3] >= 0).all()
+    ref = b2.PathIntegrator(max_depth=6, rr_depth=5, block_size=32).render(b2.Scene(small), 1024)
+    a = (film[..., :3] / spp).reshape(64, H // 64, 64, W // 64, 3).mean(axis=(1, 3))
+    b = ref[..., :3] / 1024
+    assert abs(a.mean() - b.mean()) < 0.01 * b.mean()
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 0.05
 
 
 def test_develop(b2, oracle):
