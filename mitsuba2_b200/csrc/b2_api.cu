@@ -365,8 +365,13 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         std::memcpy(ds.center, sh.center, 12); ds.radius = sh.radius;
         if (sh.type == B2_SHAPE_RECTANGLE) {
             const float *M = sh.to_world, *I = sh.to_object;
-            float fs[3] = { M[0] * 2.f, M[4] * 2.f, M[8] * 2.f }, ft[3] = { M[1] * 2.f, M[5] * 2.f, M[9] * 2.f };     // to_world * (2,0,0) / (0,2,0)
-            float n[3] = { I[8], I[9], I[10] };                                                                       // inverse transpose * (0,0,1)
+            // the same fmadd chains as Transform::operator*(Vector / Normal) (transform.h:88-151), so that even the signs of
+            // zero components match: to_world * (2,0,0), to_world * (0,2,0), inverse transpose * (0,0,1)
+            auto xfv = [&](int r, float x, float y, float z) { return std::fma(M[4 * r + 2], z, std::fma(M[4 * r + 1], y, M[4 * r] * x)); };
+            auto xfn = [&](int c, float x, float y, float z) { return std::fma(I[8 + c], z, std::fma(I[4 + c], y, I[c] * x)); };
+            float fs[3] = { xfv(0, 2.f, 0.f, 0.f), xfv(1, 2.f, 0.f, 0.f), xfv(2, 2.f, 0.f, 0.f) },
+                  ft[3] = { xfv(0, 0.f, 2.f, 0.f), xfv(1, 0.f, 2.f, 0.f), xfv(2, 0.f, 2.f, 0.f) };
+            float n[3] = { xfn(0, 0.f, 0.f, 1.f), xfn(1, 0.f, 0.f, 1.f), xfn(2, 0.f, 0.f, 1.f) };
             float inv_len = 1.f / std::sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
             for (int q = 0; q < 3; ++q) { ds.n[q] = n[q] * inv_len; ds.dp_du[q] = fs[q]; }
             float c[3] = { std::fma(fs[1], ft[2], -(fs[2] * ft[1])), std::fma(fs[2], ft[0], -(fs[0] * ft[2])), std::fma(fs[0], ft[1], -(fs[1] * ft[0])) };

@@ -173,7 +173,7 @@ def test_matball_bitexact(b2, oracle):
 def test_full_size_properties(b2, workload):
     """BASELINE configs[1] (cbox 1024^2 x 256 spp) and configs[4] (9802 triangles x 1000 instances, 2048^2 x 64 spp)
     at FULL size, through size-independent properties: every camera sample lands on the film exactly once (box
-    filter: the W channel of a pixel is exactly spp, whatever the pass / lane-slot schedule), alpha <= weight, all
+    filter: the W channel of a pixel is spp up to the filter's epsilon-wide overlap, whatever the pass / lane-slot schedule), alpha <= weight, all
     values finite and non-negative, no sample rejected, and the image agrees with a low-resolution render of the
     same scene (pixel-block means) to Monte Carlo accuracy."""
     if workload == "cbox":
@@ -185,7 +185,11 @@ def test_full_size_properties(b2, workload):
     st = integ.stats
     assert st["n_samples"] == W * H * spp and st["n_invalid"] == 0
     assert np.isfinite(film).all() and (film[..., :3] >= -1e-5).all()
-    assert np.array_equal(film[..., 4], np.full((H, W), float(spp), np.float32))          # W: exactly spp per pixel
+    # W = number of samples that landed on the pixel: spp, except that the box filter's radius is 0.5 + RayEpsilon
+    # (box.cpp:24-29), so a sample within 1e-4 of a pixel edge lands on the neighbour, or is dropped at a block edge
+    # (imageblock.cpp:162-169) -- like in the reference
+    assert np.abs(film[..., 4] - spp).max() <= 4
+    assert abs(film[..., 4].sum(dtype=np.float64) / (float(W) * H * spp) - 1.0) < 1e-4
     assert (film[..., 3] <= film[..., 4]).all() and (film[..., 3] >= 0).all()
     ref = b2.PathIntegrator(max_depth=6, rr_depth=5, block_size=32).render(b2.Scene(small), 1024)
     a = (film[..., :3] / spp).reshape(64, H // 64, 64, W // 64, 3).mean(axis=(1, 3))
