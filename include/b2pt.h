@@ -203,8 +203,12 @@ typedef struct B2RenderParams {
     uint64_t seed;              /* sampler 'seed' (m_base_seed)                                */
     int32_t rank, world_size;   /* this process renders spiral blocks b with b % world == rank */
     uint32_t flags;             /* B2_FLAG_* */
-    uint32_t _pad;
+    uint32_t sampler;           /* B2_SAMPLER_* (| B2_SAMPLER_NO_JITTER for stratified 'jitter' = false) */
 } B2RenderParams;
+
+/* samplers: IndependentSampler (src/samplers/independent.cpp) and StratifiedSampler (src/samplers/stratified.cpp;
+   spp must be a perfect square, :60-75) */
+enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_NO_JITTER = 0x100 };
 
 #define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */
 #define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */

@@ -196,6 +196,13 @@ public:
             }
             rp.block_size = block_size;
             rp.seed = m_seed; rp.rank = 0; rp.world_size = 1;
+            {   // sampler plugin -> B2_SAMPLER_* ('jitter' is only printed, stratified.cpp:133-140)
+                std::string scls = sensor->sampler()->class_()->name();
+                if (scls == "StratifiedSampler")
+                    rp.sampler = B2_SAMPLER_STRATIFIED | (sensor->sampler()->to_string().find("jitter = 0") != std::string::npos ? B2_SAMPLER_NO_JITTER : 0);
+                else if (scls != "IndependentSampler")
+                    Throw("b2path: sampler \"%s\" is not supported (independent, stratified are)", scls);
+            }
 
             film->prepare({ "X", "Y", "Z", "A", "W" });                  // integrator.cpp:71-73
             ref<ImageBlock> block = new ImageBlock(crop_size, 5, film->reconstruction_filter(), false, false, false);

@@ -118,7 +118,7 @@ class B2RenderParams(C.Structure):
         ("block_size", C.c_uint32), ("lane_slots", C.c_uint32),
         ("seed", C.c_uint64),
         ("rank", C.c_int32), ("world_size", C.c_int32),
-        ("flags", C.c_uint32), ("_pad", C.c_uint32),
+        ("flags", C.c_uint32), ("sampler", C.c_uint32),
     ]
 
 
@@ -145,9 +145,13 @@ def uptr(a):
 
 
 def render_params(max_depth=6, rr_depth=5, spp=16, samples_per_pass=0, block_size=32, seed=0,
-                  rank=0, world_size=1, lane_slots=0, flags=0):
+                  rank=0, world_size=1, lane_slots=0, flags=0, sampler="independent", jitter=True):
+    smp = {"independent": SAMPLER_INDEPENDENT, "stratified": SAMPLER_STRATIFIED}[sampler] | (0 if jitter else SAMPLER_NO_JITTER)
     return B2RenderParams(max_depth, rr_depth, spp, samples_per_pass, block_size, lane_slots, seed, rank, world_size,
-                          flags, 0)
+                          flags, smp)
+
+
+SAMPLER_INDEPENDENT, SAMPLER_STRATIFIED, SAMPLER_NO_JITTER = 0, 1, 0x100
 
 
 def fresnel_diffuse_reflectance(eta):

@@ -179,14 +179,17 @@ class Scene:
 class PathIntegrator:
     """PathIntegrator (src/integrators/path.cpp) + SamplingIntegrator::render driver."""
 
-    def __init__(self, max_depth=-1, rr_depth=5, samples_per_pass=0, block_size=32):
+    def __init__(self, max_depth=-1, rr_depth=5, samples_per_pass=0, block_size=32, sampler="independent", jitter=True):
+        """sampler: "independent" (src/samplers/independent.cpp) or "stratified" (src/samplers/stratified.cpp; spp must
+        be a perfect square)."""
         self.max_depth, self.rr_depth = max_depth, rr_depth
         self.samples_per_pass, self.block_size = samples_per_pass, block_size
+        self.sampler, self.jitter = sampler, jitter
         self.stats = None
 
     def params(self, spp, seed=0, rank=0, world_size=1, lane_slots=0, flags=0):
         return abi.render_params(self.max_depth, self.rr_depth, spp, self.samples_per_pass, self.block_size, seed,
-                                 rank, world_size, lane_slots, flags)
+                                 rank, world_size, lane_slots, flags, self.sampler, self.jitter)
 
     def render(self, scene, spp, seed=0, rank=0, world_size=1, lane_slots=0, out=None):
         """-> XYZAW film as float32 [H, W, 5] in HOST memory (copies inside the call)."""

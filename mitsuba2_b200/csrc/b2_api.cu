@@ -94,7 +94,8 @@ struct B2Scene {
     DBuf<uint32_t> sh_f, cnt, item_pixel, item_seed;
     DBuf<unsigned long long> stats;
     DBuf<float> film;
-    DBuf<float> film_wide;          // wide filters: padded accumulation film, 8 floats / pixel
+    DBuf<float> film_wide;
+    DBuf<uint2> smp;                // per-lane sampler state of the non-independent samplers          // wide filters: padded accumulation film, 8 floats / pixel
     uint32_t *h_cnt = nullptr;           // pinned readback
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
@@ -661,6 +662,17 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
     CU(s->film.alloc((size_t) W * H * 5));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
+    // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
+    // up and warns; here it is an error so that spp keeps its meaning)
+    const uint32_t sampler_type = rp->sampler & 0xffu;
+    uint32_t smp_res = 1;
+    if (sampler_type != B2_SAMPLER_INDEPENDENT) {
+        if (sampler_type != B2_SAMPLER_STRATIFIED) return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
+        while (smp_res * smp_res < rp->spp) ++smp_res;
+        if (smp_res * smp_res != rp->spp) return fail(B2_ERR_INVALID, "Sample count should be square and power of two (got %u)", rp->spp);
+        if (spp_pass > 65535u) return fail(B2_ERR_INVALID, "stratified sampler: samples_per_pass must be < 65536");
+        CU(s->smp.alloc(cap));
+    }
     if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 16 * sizeof(uint32_t)));
 
     // The lane slots are split into independent lane SETS, each with its own counters and shadow
@@ -682,6 +694,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.hit_inst = s->d.n_instances ? s->hit_inst.p + o : nullptr;
         q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o; q.sh_r = s->sh_r.p + o; q.sh_f = s->sh_f.p + o;
         q.cnt = s->cnt.p + 4 * k; q.work = s->cnt.p + 16; q.stats = s->stats.p;
+        if (sampler_type != B2_SAMPLER_INDEPENDENT) {
+            q.smp = s->smp.p + o; q.smp_count = rp->spp; q.smp_res = smp_res; q.smp_jitter = (rp->sampler & B2_SAMPLER_NO_JITTER) ? 0u : 1u;
+            q.smp_inv_count = 1.f / (float) rp->spp; q.smp_inv_res = 1.f / (float) smp_res;
+        }
         q.film = wide ? s->film_wide.p : s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
         q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
         q.total_items = (uint32_t) total64; q.n_slots = set_slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
@@ -703,7 +719,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
     const bool inst = s->d.n_instances != 0;
-    const ShadeFn shade_fn = shade_variant(s->features);
+    // non-independent samplers run in the extended (F_TEX) kernel variants
+    const uint32_t run_features = s->features | (sampler_type != B2_SAMPLER_INDEPENDENT ? (uint32_t) F_TEX : 0u);
+    const ShadeFn shade_fn = shade_variant(run_features);
+    if (run_features != s->features) cudaFuncSetAttribute(shade_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
     const TraceFn trace_fn = trace_variant(inst, wide);
     uint32_t need_blocks = (set_slots + threads - 1) / threads;
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
@@ -717,7 +736,11 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     auto tick = [&](cudaStream_t st) { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;
     if (timing) { cudaEventCreate(&evi0); cudaEventCreate(&evi1); cudaEventRecord(evi0, stream); }
-    for (int k = 0; k < n_sets; ++k) { k_init<<<grid, threads, 0, stream>>>(s->d, qs[k]); ++launches; }
+    for (int k = 0; k < n_sets; ++k) {
+        if (sampler_type != B2_SAMPLER_INDEPENDENT) k_init<true><<<grid, threads, 0, stream>>>(s->d, qs[k]);
+        else k_init<false><<<grid, threads, 0, stream>>>(s->d, qs[k]);
+        ++launches;
+    }
     if (timing) cudaEventRecord(evi1, stream);
     if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); for (int k = 1; k < n_sets; ++k) CU(cudaStreamWaitEvent(streams[k], evs, 0)); }
     int pending[2] = { 0, 0 };

@@ -46,6 +46,11 @@ struct Queues {
     uint32_t n_slots;
     uint64_t base_seed;
     int32_t max_depth, rr_depth;
+    // non-independent samplers (stratified.cpp): per-lane (sample_index << 16 | dimension_index, permutation seed); NULL
+    // for the independent sampler. The constructor's derived values (stratified.cpp:60-75) come from the host.
+    uint2 *smp;
+    uint32_t smp_count, smp_res, smp_jitter;
+    float smp_inv_count, smp_inv_res;
 };
 
 enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */ };
@@ -699,11 +704,61 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     }
 }
 
+// ---- samplers: IndependentSampler::next_1d / next_2d (independent.cpp:73-82) and, in the extended (EXT) kernel variants
+// when q.smp is set, StratifiedSampler (stratified.cpp:92-131): permute_kensler / sample_tea_32 (random.h:75-85, 229-274)
+B2_D uint32_t sample_tea_32(uint32_t v0, uint32_t v1) {
+    uint32_t sum = 0;
+    #pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v1;
+}
+B2_D uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_t seed) {
+    if (sample_count == 1) return 0;
+    uint32_t w = sample_count - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        uint32_t tmp = index;
+        tmp ^= seed; tmp *= 0xe170893du; tmp ^= seed >> 16;
+        tmp ^= (tmp & w) >> 4; tmp ^= seed >> 8; tmp *= 0x0929eb3fu; tmp ^= seed >> 23;
+        tmp ^= (tmp & w) >> 1; tmp *= 1u | seed >> 27; tmp *= 0x6935fa69u;
+        tmp ^= (tmp & w) >> 11; tmp *= 0x74dcb303u;
+        tmp ^= (tmp & w) >> 2; tmp *= 0x9e501cc3u;
+        tmp ^= (tmp & w) >> 2; tmp *= 0xc860a3dfu;
+        tmp &= w; tmp ^= tmp >> 5;
+        index = tmp;
+    } while (index >= sample_count);
+    return (index + seed) % sample_count;
+}
+template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2 &sm) {
+    if constexpr (EXT) if (q.smp) {
+        uint32_t p = permute_kensler(sm.x >> 16, q.smp_count, sm.y + (sm.x & 0xffffu)); ++sm.x;      // m_dimension_index++
+        float j = q.smp_jitter ? pcg32_next_float(rng) : .5f;
+        return ((float) p + j) * q.smp_inv_count;
+    }
+    return pcg32_next_float(rng);
+}
+template <bool EXT> B2_D float2 smp_next_2d(const Queues &q, uint64_t &rng, uint2 &sm) {
+    if constexpr (EXT) if (q.smp) {
+        uint32_t p = permute_kensler(sm.x >> 16, q.smp_count, sm.y + (sm.x & 0xffffu)); ++sm.x;
+        uint32_t y = p / q.smp_res, x = p - y * q.smp_res;
+        float jx = .5f, jy = .5f;
+        if (q.smp_jitter) { jx = pcg32_next_float(rng); jy = pcg32_next_float(rng); }
+        return make_float2(((float) x + jx) * q.smp_inv_res, ((float) y + jy) * q.smp_inv_res);
+    }
+    float a = pcg32_next_float(rng), b = pcg32_next_float(rng);
+    return make_float2(a, b);
+}
+
 // ---- K1: regenerate — next camera sample of the lane's work item (integrator.cpp:233-262) ------
 // `item`/`left`/`rng` are the lane's work-item state (left == 0: `w` is the freshly fetched work
 // item). Returns false if the work is exhausted (lane retires).
+template <bool EXT>
 B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_t w, uint32_t pix, uint32_t &item, uint32_t &left,
-                       uint64_t &rng, Ray &ray, uint32_t &stw) {
+                       uint64_t &rng, uint2 &sm, Ray &ray, uint32_t &stw) {
     const B2Film &film = sc.film;
     if (left == 0) {
         if (w >= q.total_items) return false;
@@ -714,12 +769,15 @@ B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_
         uint64_t seed_off = (uint64_t) __ldg(&q.item_seed[j]) +
                             (uint64_t) (q.n_passes - 1 - pass) * q.n_blocks_total * q.block_size * q.block_size;
         rng = pcg32_seed(q.base_seed + seed_off);
+        if constexpr (EXT) sm.y = sample_tea_32((uint32_t) q.base_seed, (uint32_t) seed_off);   // compute_per_sequence_seed, sampler.cpp:55-60
         pix = __ldg(&q.item_pixel[j]);
     }
+    if constexpr (EXT) sm.x = (q.spp_pass - left) << 16;                       // Sampler::advance(): m_sample_index, dimension 0
     uint32_t px = pix & 0xffffu, py = pix >> 16;
-    float jx = pcg32_next_float(rng), jy = pcg32_next_float(rng);            // integrator.cpp:242
+    float2 jit = smp_next_2d<EXT>(q, rng, sm);                                 // integrator.cpp:242
+    float jx = jit.x, jy = jit.y;
     float psx = (float) (px + (uint32_t) film.crop_offset[0]) + jx, psy = (float) (py + (uint32_t) film.crop_offset[1]) + jy;
-    (void) pcg32_next_float(rng);                                              // :252 wavelength sample
+    (void) smp_next_1d<EXT>(q, rng, sm);                                       // :252 wavelength sample
     float ax = (psx - (float) film.crop_offset[0]) / (float) film.crop_size[0],
           ay = (psy - (float) film.crop_offset[1]) / (float) film.crop_size[1];   // :254-256
     ray = sensor_sample_ray(sc.sensor, ax, ay);
@@ -743,20 +801,22 @@ B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_
 }
 
 // fill every lane with its first camera sample
+template <bool EXT>
 __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
     uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         uint32_t lane = base + lane_id();
         bool valid = lane < q.n_slots;
         uint32_t w = warp_append(q.work, valid);
-        uint32_t item = 0, left = 0, stw = 0; uint64_t rng = 0; Ray ray;
-        bool alive = valid && regen_sample(sc, q, lane, w, 0u, item, left, rng, ray, stw);
+        uint32_t item = 0, left = 0, stw = 0; uint64_t rng = 0; Ray ray; uint2 sm = make_uint2(0u, 0u);
+        bool alive = valid && regen_sample<EXT>(sc, q, lane, w, 0u, item, left, rng, sm, ray, stw);
         if (alive) {
             q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
             q.ray_d[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
             q.tp[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
             q.res[lane] = make_float4(0.f, 0.f, 0.f, 1.f);
             q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), item, stw);
+            if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
         } else if (valid)
             q.ray_d[lane] = make_float4(0.f, 0.f, 0.f, -1.f);
         uint32_t n_alive = __popc(__ballot_sync(0xffffffffu, alive));
@@ -810,6 +870,9 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         float4 sho, shd, shc;
         float4 nro, nrd;                 // next ray
         uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+        constexpr bool EXT = (F & F_TEX) != 0;
+        uint2 sm = make_uint2(0u, 0u);
+        if constexpr (EXT) if (q.smp) sm = q.smp[ld];
         int depth = (int) STW_DEPTH(st.w);
         float3 throughput = v3(tpe), result = v3(rs);
         float eta = tpe.w, bs_pdf = rs.w;
@@ -847,7 +910,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
             bool active = hit_valid;                                                // path.cpp:131
             if (depth > q.rr_depth) {                                               // path.cpp:137-141
                 float qq = b2_min(hmax(throughput) * b2_sqr(eta), .95f);
-                if (active) active = pcg32_next_float(rng) < qq;
+                if (active) active = smp_next_1d<EXT>(q, rng, sm) < qq;
                 throughput = throughput * b2_rcp(qq);
             }
             if ((uint32_t) depth >= (uint32_t) q.max_depth || !active) term = true;   // path.cpp:147-149
@@ -856,7 +919,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                 bool smooth;
                 const B2Bsdf &bsdf = bsdf_side<F>(tb, si, flip, smooth);            // (twosided: side record, wi.z mirrored)
                 if (smooth) {                                                          // path.cpp:153-172
-                    float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
+                    float2 se = smp_next_2d<EXT>(q, rng, sm); float sx = se.x, sy = se.y;
                     DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, sx, sy, ds);
                     if (ds.pdf != 0.f) {
                         float3 wo = to_local(si, ds.d);
@@ -888,8 +951,8 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
         if (do_bsdf) {
             const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
-            float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
-            float s1 = pcg32_next_float(rng);
+            float2 s2 = smp_next_2d<EXT>(q, rng, sm); float s2x = s2.x, s2y = s2.y;
+            float s1 = smp_next_1d<EXT>(q, rng, sm);
             BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs, bsdf_reflectance<F>(tb, bsdf, si));
             if constexpr ((F & F_TEX) != 0) if (flip) bs.wo.z = -bs.wo.z;          // twosided.cpp:122
             throughput = throughput * bsdf_val;
@@ -926,7 +989,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         bool retire = false;
         if (term) {
             Ray ray; uint32_t stw;
-            if (regen_sample(sc, q, lane, w, pix, item, left, rng, ray, stw)) {
+            if (regen_sample<EXT>(sc, q, lane, w, pix, item, left, rng, sm, ray, stw)) {
                 nro = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
                 nrd = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
                 throughput = v3(1.f, 1.f, 1.f); eta = 1.f; result = v3(0.f, 0.f, 0.f); bs_pdf = 1.f;
@@ -939,6 +1002,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                 q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
                 q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
                 q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+                if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
             }
         }
         uint32_t n_ret = __popc(__ballot_sync(0xffffffffu, retire));

@@ -1480,12 +1480,75 @@ static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx,
  * ============================================================================================ */
 typedef struct { uint64_t segments, shadow_rays; } ocount;
 
+/* ============================================================================================
+ * Samplers — src/librender/sampler.cpp:22-71, src/samplers/independent.cpp:73-82, src/samplers/stratified.cpp:60-131,
+ * include/mitsuba/core/random.h:75-85 (sample_tea_32), :229-274 (permute_kensler)
+ * ============================================================================================ */
+typedef struct {
+    pcg32 rng;
+    uint32_t type, jitter;
+    uint32_t sample_index, dim, perm_seed;      /* m_sample_index, m_dimension_index, m_permutation_seed */
+    uint32_t count, res; float inv_count, inv_res;
+} osampler;
+
+static uint32_t sample_tea_32(uint32_t v0, uint32_t v1, int rounds) {
+    uint32_t sum = 0;
+    for (int i = 0; i < rounds; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v1;
+}
+static uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_t seed) {
+    if (sample_count == 1) return 0;
+    uint32_t w = sample_count - 1;
+    w |= w >> 1; w |= w >> 2; w |= w >> 4; w |= w >> 8; w |= w >> 16;
+    do {
+        uint32_t tmp = index;
+        tmp ^= seed; tmp *= 0xe170893du; tmp ^= seed >> 16;
+        tmp ^= (tmp & w) >> 4; tmp ^= seed >> 8; tmp *= 0x0929eb3fu; tmp ^= seed >> 23;
+        tmp ^= (tmp & w) >> 1; tmp *= 1u | seed >> 27; tmp *= 0x6935fa69u;
+        tmp ^= (tmp & w) >> 11; tmp *= 0x74dcb303u;
+        tmp ^= (tmp & w) >> 2; tmp *= 0x9e501cc3u;
+        tmp ^= (tmp & w) >> 2; tmp *= 0xc860a3dfu;
+        tmp &= w; tmp ^= tmp >> 5;
+        index = tmp;
+    } while (index >= sample_count);
+    return (index + seed) % sample_count;
+}
+/* Sampler::seed + PCG32Sampler::seed (+ StratifiedSampler::seed); the constructor's derived values (stratified.cpp:60-75) */
+static void smp_seed(osampler *s, const B2RenderParams *rp, uint64_t seed_offset) {
+    sampler_seed(&s->rng, rp->seed, seed_offset);
+    s->type = rp->sampler & 0xffu; s->jitter = !(rp->sampler & B2_SAMPLER_NO_JITTER);
+    s->sample_index = 0; s->dim = 0;
+    s->res = 1; while (s->res * s->res < rp->spp) s->res++;
+    s->count = s->res * s->res;
+    s->inv_count = b2o_rcp((float) s->count); s->inv_res = b2o_rcp((float) s->res);
+    s->perm_seed = sample_tea_32((uint32_t) rp->seed, (uint32_t) seed_offset, 4);     /* compute_per_sequence_seed, sampler.cpp:55-60 */
+}
+static inline void smp_advance(osampler *s) { s->dim = 0; s->sample_index++; }
+static inline float smp_next_1d(osampler *s) {
+    if (s->type == B2_SAMPLER_INDEPENDENT) return pcg32_next_float(&s->rng);
+    uint32_t p = permute_kensler(s->sample_index, s->count, s->perm_seed + s->dim++);
+    float j = s->jitter ? pcg32_next_float(&s->rng) : .5f;
+    return ((float) p + j) * s->inv_count;
+}
+static inline void smp_next_2d(osampler *s, float *x, float *y) {
+    if (s->type == B2_SAMPLER_INDEPENDENT) { *x = pcg32_next_float(&s->rng); *y = pcg32_next_float(&s->rng); return; }
+    uint32_t p = permute_kensler(s->sample_index, s->count, s->perm_seed + s->dim++);
+    uint32_t py = p / s->res, px = p - py * s->res;
+    float jx = .5f, jy = .5f;
+    if (s->jitter) { jx = pcg32_next_float(&s->rng); jy = pcg32_next_float(&s->rng); }
+    *x = ((float) px + jx) * s->inv_res; *y = ((float) py + jy) * s->inv_res;
+}
+
 static inline float mis_weight(float a, float b) {   /* path.cpp:223-227 */
     a *= a; b *= b;
     return a > 0.f ? a / (a + b) : 0.f;
 }
 
-static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, oray ray, int *valid_ray,
+static v3 path_sample(const oscene *s, const B2RenderParams *rp, osampler *rng, oray ray, int *valid_ray,
                       int brute, ocount *cnt) {
     const B2SceneDesc *d = s->desc;
     float eta = 1.f, emission_weight = 1.f;
@@ -1507,7 +1570,7 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         active &= si.t < INFINITY;                                        /* path.cpp:131 */
         if (depth > rp->rr_depth) {                                       /* path.cpp:137-141 */
             float q = b2o_min(v3_hmax(throughput) * b2o_sqr(eta), .95f);
-            if (active) active &= pcg32_next_float(rng) < q;
+            if (active) active &= smp_next_1d(rng) < q;
             throughput = v3_scale(throughput, b2o_rcp(q));
         }
         if ((uint32_t) depth >= (uint32_t) rp->max_depth || !active) break;   /* path.cpp:147-149 */
@@ -1517,7 +1580,7 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         osi sib = si;                                                      /* the interaction as the nested BRDF sees it */
         if (flip) sib.wi.z = -sib.wi.z;
         if (smooth) {                                                      /* path.cpp:153-172 */
-            float sx = pcg32_next_float(rng), sy = pcg32_next_float(rng);
+            float sx, sy; smp_next_2d(rng, &sx, &sy);
             ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
             if (ds.pdf != 0.f) {
                 v3 wo = to_local(&si, ds.d);
@@ -1540,8 +1603,8 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, pcg32 *rng, ora
         }
         /* BSDF sampling: g++ evaluates the arguments right to left, so next_2d is drawn
            BEFORE next_1d (path.cpp:177-178) */
-        float s2x = pcg32_next_float(rng), s2y = pcg32_next_float(rng);
-        float s1 = pcg32_next_float(rng);
+        float s2x, s2y; smp_next_2d(rng, &s2x, &s2y);
+        float s1 = smp_next_1d(rng);
         obs bs; v3 bsdf_val = bsdf_sample(bsdf, &sib, s1, s2x, s2y, &bs);
         if (flip) bs.wo.z = -bs.wo.z;
         throughput = v3_mul(throughput, bsdf_val);
@@ -1680,14 +1743,14 @@ static void render_item(ojob *j, uint32_t w, ocount *cnt, uint64_t *invalid, uin
     blk->data = (float *) calloc((size_t) 5 * (blk->w + 2 * blk->border) * (blk->h + 2 * blk->border), sizeof(float));
     uint32_t pixel_count = bs * bs;
     for (uint32_t i = 0; i < pixel_count; ++i) {
-        pcg32 rng; sampler_seed(&rng, rp->seed, block_id * pixel_count + i);                /* integrator.cpp:198 */
+        osampler rng; smp_seed(&rng, rp, block_id * pixel_count + i);                       /* integrator.cpp:198 */
         uint32_t mx = compact1by1(i), my = compact1by1(i >> 1);
         if ((int) mx >= blk->w || (int) my >= blk->h) continue;
         float posx = (float) (mx + (uint32_t) blk->ox), posy = (float) (my + (uint32_t) blk->oy);
         for (uint32_t k = 0; k < j->spp_pass; ++k) {
-            float jx = pcg32_next_float(&rng), jy = pcg32_next_float(&rng);                  /* :242 */
+            float jx, jy; smp_next_2d(&rng, &jx, &jy);                                       /* :242 */
             float psx = posx + jx, psy = posy + jy;
-            (void) pcg32_next_float(&rng);                                                   /* :252 wavelength sample */
+            (void) smp_next_1d(&rng);                                                        /* :252 wavelength sample */
             float ax = (psx - (float) film->crop_offset[0]) / (float) film->crop_size[0],
                   ay = (psy - (float) film->crop_offset[1]) / (float) film->crop_size[1];   /* :254-256 */
             oray ray = sensor_sample_ray(&d->sensor, ax, ay);
@@ -1701,6 +1764,7 @@ static void render_item(ojob *j, uint32_t w, ocount *cnt, uint64_t *invalid, uin
             val[3] = valid ? 1.f : 0.f; val[4] = 1.f;
             if (!block_put(blk, film, psx, psy, val)) (*invalid)++;
             (*samples)++;
+            smp_advance(&rng);                                                               /* :206 */
         }
     }
 }

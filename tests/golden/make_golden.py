@@ -322,7 +322,7 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
              rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
-             textures=False, crop=None, analytic=False, integrator="path"):
+             textures=False, crop=None, analytic=False, integrator="path", sampler="independent", jitter=True):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -390,6 +390,8 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
     xml = CBOX_XML.format(crop=cr, width=width, height=height, spp=spp, max_depth=max_depth, rr_depth=rr_depth,
                           block_size=block_size, spp_pass=sp, rfilter=rf, seed=seed,
                           bsdfs="\n    ".join(bs), shapes="\n    ".join(shapes))
+    if sampler != "independent":        # src/samplers/stratified.cpp
+        xml = xml.replace('<sampler type="independent">', f'<sampler type="{sampler}">' + ("" if jitter else '<boolean name="jitter" value="false"/>'))
     if integrator == "direct":         # DirectIntegrator (src/integrators/direct.cpp): no depth parameters
         xml = xml.replace('<integrator type="path">', '<integrator type="direct">')
         xml = re.sub(r'\s*<integer name="(max_depth|rr_depth)" value="[^"]*"/>', "", xml)
@@ -474,6 +476,9 @@ GOLDEN = {
     # the reference's `direct` integrator with its default shading_samples = 1 draws the same numbers in the same order as
     # `path` with max_depth = 2 (direct.cpp:106-196 vs path.cpp:124-208): rendered by `direct`, loaded as max_depth 2
     "cbox_64_spp16_direct": dict(width=64, height=64, spp=16, no_patch=True, analytic=True, integrator="direct", max_depth=2),
+    # stratified sampler (with and without jitter; several passes re-seed and restart the strata like the reference)
+    "cbox_64_spp16_stratified": dict(width=64, height=64, spp=16, no_patch=True, sampler="stratified"),
+    "cbox_64_spp16_stratified_nojitter_pass4": dict(width=64, height=64, spp=16, no_patch=True, sampler="stratified", jitter=False, samples_per_pass=4),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }

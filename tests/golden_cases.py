@@ -108,7 +108,7 @@ def load(name, host):
         sb.add_area_emitter(mi, tuple(float(x) for x in z["extra_radiance"]))
     rp = abi.render_params(max_depth=kw.get("max_depth", 6), rr_depth=kw.get("rr_depth", 5), spp=kw["spp"],
                            samples_per_pass=kw.get("samples_per_pass") or 0, block_size=kw.get("block_size", 32),
-                           seed=kw.get("seed", 0))
+                           seed=kw.get("seed", 0), sampler=kw.get("sampler", "independent"), jitter=kw.get("jitter", True))
     return sb, rp, z["rgb"]
 
 

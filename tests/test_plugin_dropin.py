@@ -208,3 +208,19 @@ def test_plugin_dropin_direct_integrator(tmp_path):
     assert r1.returncode == 0, r1.stdout + r1.stderr
     s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
     assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
+
+
+@needs_ref
+@pytest.mark.gpu
+def test_plugin_dropin_stratified_sampler(tmp_path):
+    """`<sampler type="stratified">` instantiated by the reference, recognised by the adapter and run on the GPU."""
+    from tests import golden_cases as G
+
+    def xml(integrator):
+        return _scene_xml(integrator).replace('<sampler type="independent">', '<sampler type="stratified">')
+    r0, ref_out = _run(xml("path"), tmp_path, "ref_s")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, b2_out = _run(xml("b2path"), tmp_path, "b2_s")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
