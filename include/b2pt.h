@@ -207,8 +207,9 @@ typedef struct B2RenderParams {
 } B2RenderParams;
 
 /* samplers: IndependentSampler (src/samplers/independent.cpp) and StratifiedSampler (src/samplers/stratified.cpp;
-   spp must be a perfect square, :60-75) */
-enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_NO_JITTER = 0x100 };
+   spp must be a perfect square, :60-75; multijitter: spp = rx * ry with ry = floor(sqrt(spp)), multijitter.cpp:68-81) */
+enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJITTER = 2 /* src/samplers/multijitter.cpp */,
+       B2_SAMPLER_NO_JITTER = 0x100 };
 
 #define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */
 #define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */

@@ -200,8 +200,10 @@ public:
                 std::string scls = sensor->sampler()->class_()->name();
                 if (scls == "StratifiedSampler")
                     rp.sampler = B2_SAMPLER_STRATIFIED | (sensor->sampler()->to_string().find("jitter = 0") != std::string::npos ? B2_SAMPLER_NO_JITTER : 0);
+                else if (scls == "MultijitterSampler")
+                    rp.sampler = B2_SAMPLER_MULTIJITTER | (sensor->sampler()->to_string().find("jitter = 0") != std::string::npos ? B2_SAMPLER_NO_JITTER : 0);
                 else if (scls != "IndependentSampler")
-                    Throw("b2path: sampler \"%s\" is not supported (independent, stratified are)", scls);
+                    Throw("b2path: sampler \"%s\" is not supported (independent, stratified, multijitter are)", scls);
             }
 
             film->prepare({ "X", "Y", "Z", "A", "W" });                  // integrator.cpp:71-73

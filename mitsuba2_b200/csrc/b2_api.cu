@@ -665,11 +665,17 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
     // up and warns; here it is an error so that spp keeps its meaning)
     const uint32_t sampler_type = rp->sampler & 0xffu;
-    uint32_t smp_res = 1;
+    uint32_t smp_res = 1, smp_res_y = 1;
     if (sampler_type != B2_SAMPLER_INDEPENDENT) {
-        if (sampler_type != B2_SAMPLER_STRATIFIED) return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
-        while (smp_res * smp_res < rp->spp) ++smp_res;
-        if (smp_res * smp_res != rp->spp) return fail(B2_ERR_INVALID, "Sample count should be square and power of two (got %u)", rp->spp);
+        if (sampler_type == B2_SAMPLER_STRATIFIED) {
+            while (smp_res * smp_res < rp->spp) ++smp_res;
+            smp_res_y = smp_res;
+            if (smp_res * smp_res != rp->spp) return fail(B2_ERR_INVALID, "Sample count should be square and power of two (got %u)", rp->spp);
+        } else if (sampler_type == B2_SAMPLER_MULTIJITTER) {           // multijitter.cpp:68-81
+            smp_res_y = (uint32_t) std::sqrt((float) rp->spp);
+            smp_res = (rp->spp + smp_res_y - 1) / smp_res_y;
+            if (smp_res * smp_res_y != rp->spp) return fail(B2_ERR_INVALID, "Sample count rounded up to %u (got %u)", smp_res * smp_res_y, rp->spp);
+        } else return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
         if (spp_pass > 65535u) return fail(B2_ERR_INVALID, "stratified sampler: samples_per_pass must be < 65536");
         CU(s->smp.alloc(cap));
     }
@@ -697,6 +703,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (sampler_type != B2_SAMPLER_INDEPENDENT) {
             q.smp = s->smp.p + o; q.smp_count = rp->spp; q.smp_res = smp_res; q.smp_jitter = (rp->sampler & B2_SAMPLER_NO_JITTER) ? 0u : 1u;
             q.smp_inv_count = 1.f / (float) rp->spp; q.smp_inv_res = 1.f / (float) smp_res;
+            q.smp_type = sampler_type; q.smp_res_y = smp_res_y; q.smp_inv_res_y = 1.f / (float) smp_res_y;
         }
         q.film = wide ? s->film_wide.p : s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
         q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;

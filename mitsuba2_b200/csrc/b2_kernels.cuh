@@ -49,8 +49,8 @@ struct Queues {
     // non-independent samplers (stratified.cpp): per-lane (sample_index << 16 | dimension_index, permutation seed); NULL
     // for the independent sampler. The constructor's derived values (stratified.cpp:60-75) come from the host.
     uint2 *smp;
-    uint32_t smp_count, smp_res, smp_jitter;
-    float smp_inv_count, smp_inv_res;
+    uint32_t smp_count, smp_res, smp_jitter, smp_type, smp_res_y;      // smp_res = m_resolution.x, smp_res_y = .y (multijitter)
+    float smp_inv_count, smp_inv_res, smp_inv_res_y;
 };
 
 enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */ };
@@ -735,7 +735,9 @@ B2_D uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_t se
 }
 template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2 &sm) {
     if constexpr (EXT) if (q.smp) {
-        uint32_t p = permute_kensler(sm.x >> 16, q.smp_count, sm.y + (sm.x & 0xffffu)); ++sm.x;      // m_dimension_index++
+        uint32_t ps = sm.y + (sm.x & 0xffffu);
+        if (q.smp_type == B2_SAMPLER_MULTIJITTER) ps *= 0x45fbe943u;                                  // multijitter.cpp:108
+        uint32_t p = permute_kensler(sm.x >> 16, q.smp_count, ps); ++sm.x;                            // m_dimension_index++
         float j = q.smp_jitter ? pcg32_next_float(rng) : .5f;
         return ((float) p + j) * q.smp_inv_count;
     }
@@ -743,6 +745,17 @@ template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2
 }
 template <bool EXT> B2_D float2 smp_next_2d(const Queues &q, uint64_t &rng, uint2 &sm) {
     if constexpr (EXT) if (q.smp) {
+        if (q.smp_type == B2_SAMPLER_MULTIJITTER) {                                                   // multijitter.cpp:116-144
+            uint32_t ps = sm.y + (sm.x & 0xffffu);
+            uint32_t sq = permute_kensler(sm.x >> 16, q.smp_count, ps * 0x51633e2du); ++sm.x;
+            uint32_t cy = sq / q.smp_res, cx = sq - cy * q.smp_res;
+            uint32_t sx = permute_kensler(cx, q.smp_res, ps * 0x68bc21ebu), sy = permute_kensler(cy, q.smp_res_y, ps * 0x02e5be93u);
+            float jx = .5f, jy = .5f;
+            if (q.smp_jitter) { jx = pcg32_next_float(rng); jy = pcg32_next_float(rng); }
+            // (x + (sy + jx) * inv_res.y) * inv_res.x: the reference's compiler fuses the inner multiply-add
+            return make_float2(b2_fma((float) sy + jx, q.smp_inv_res_y, (float) cx) * q.smp_inv_res,
+                               b2_fma((float) sx + jy, q.smp_inv_res, (float) cy) * q.smp_inv_res_y);
+        }
         uint32_t p = permute_kensler(sm.x >> 16, q.smp_count, sm.y + (sm.x & 0xffffu)); ++sm.x;
         uint32_t y = p / q.smp_res, x = p - y * q.smp_res;
         float jx = .5f, jy = .5f;

@@ -1484,11 +1484,15 @@ typedef struct { uint64_t segments, shadow_rays; } ocount;
  * Samplers — src/librender/sampler.cpp:22-71, src/samplers/independent.cpp:73-82, src/samplers/stratified.cpp:60-131,
  * include/mitsuba/core/random.h:75-85 (sample_tea_32), :229-274 (permute_kensler)
  * ============================================================================================ */
+/* (x + (sy + jx) * inv_res.y) * inv_res.x, multijitter.cpp:142-143: a scalar expression the reference's compiler
+ * (-ffp-contract=fast) fuses into one fmadd */
+#define B2O_MJ_FMA(a, b, c) b2o_fma((a), (b), (c))
 typedef struct {
     pcg32 rng;
     uint32_t type, jitter;
     uint32_t sample_index, dim, perm_seed;      /* m_sample_index, m_dimension_index, m_permutation_seed */
     uint32_t count, res; float inv_count, inv_res;
+    uint32_t res_y; float inv_res_y;             /* multijitter: res = m_resolution.x, res_y = m_resolution.y */
 } osampler;
 
 static uint32_t sample_tea_32(uint32_t v0, uint32_t v1, int rounds) {
@@ -1522,20 +1526,41 @@ static void smp_seed(osampler *s, const B2RenderParams *rp, uint64_t seed_offset
     sampler_seed(&s->rng, rp->seed, seed_offset);
     s->type = rp->sampler & 0xffu; s->jitter = !(rp->sampler & B2_SAMPLER_NO_JITTER);
     s->sample_index = 0; s->dim = 0;
-    s->res = 1; while (s->res * s->res < rp->spp) s->res++;
-    s->count = s->res * s->res;
+    if (s->type == B2_SAMPLER_MULTIJITTER) {                       /* multijitter.cpp:68-81 */
+        s->res_y = (uint32_t) sqrtf((float) rp->spp);
+        s->res = (rp->spp + s->res_y - 1) / s->res_y;
+        s->count = s->res * s->res_y;
+    } else {
+        s->res = 1; while (s->res * s->res < rp->spp) s->res++;
+        s->res_y = s->res;
+        s->count = s->res * s->res;
+    }
+    s->inv_res_y = b2o_rcp((float) s->res_y);
     s->inv_count = b2o_rcp((float) s->count); s->inv_res = b2o_rcp((float) s->res);
     s->perm_seed = sample_tea_32((uint32_t) rp->seed, (uint32_t) seed_offset, 4);     /* compute_per_sequence_seed, sampler.cpp:55-60 */
 }
 static inline void smp_advance(osampler *s) { s->dim = 0; s->sample_index++; }
 static inline float smp_next_1d(osampler *s) {
     if (s->type == B2_SAMPLER_INDEPENDENT) return pcg32_next_float(&s->rng);
-    uint32_t p = permute_kensler(s->sample_index, s->count, s->perm_seed + s->dim++);
+    uint32_t ps = s->perm_seed + s->dim++;
+    if (s->type == B2_SAMPLER_MULTIJITTER) ps *= 0x45fbe943u;       /* multijitter.cpp:108 */
+    uint32_t p = permute_kensler(s->sample_index, s->count, ps);
     float j = s->jitter ? pcg32_next_float(&s->rng) : .5f;
     return ((float) p + j) * s->inv_count;
 }
 static inline void smp_next_2d(osampler *s, float *x, float *y) {
     if (s->type == B2_SAMPLER_INDEPENDENT) { *x = pcg32_next_float(&s->rng); *y = pcg32_next_float(&s->rng); return; }
+    if (s->type == B2_SAMPLER_MULTIJITTER) {                        /* multijitter.cpp:116-144 */
+        uint32_t ps = s->perm_seed + s->dim++;
+        uint32_t sq = permute_kensler(s->sample_index, s->count, ps * 0x51633e2du);
+        uint32_t cy = sq / s->res, cx = sq - cy * s->res;
+        uint32_t sx = permute_kensler(cx, s->res, ps * 0x68bc21ebu), sy = permute_kensler(cy, s->res_y, ps * 0x02e5be93u);
+        float jx = .5f, jy = .5f;
+        if (s->jitter) { jx = pcg32_next_float(&s->rng); jy = pcg32_next_float(&s->rng); }
+        *x = B2O_MJ_FMA(((float) sy + jx), s->inv_res_y, (float) cx) * s->inv_res;
+        *y = B2O_MJ_FMA(((float) sx + jy), s->inv_res, (float) cy) * s->inv_res_y;
+        return;
+    }
     uint32_t p = permute_kensler(s->sample_index, s->count, s->perm_seed + s->dim++);
     uint32_t py = p / s->res, px = p - py * s->res;
     float jx = .5f, jy = .5f;

@@ -479,6 +479,8 @@ GOLDEN = {
     # stratified sampler (with and without jitter; several passes re-seed and restart the strata like the reference)
     "cbox_64_spp16_stratified": dict(width=64, height=64, spp=16, no_patch=True, sampler="stratified"),
     "cbox_64_spp16_stratified_nojitter_pass4": dict(width=64, height=64, spp=16, no_patch=True, sampler="stratified", jitter=False, samples_per_pass=4),
+    "cbox_64_spp16_multijitter": dict(width=64, height=64, spp=16, no_patch=True, sampler="multijitter"),
+    "cbox_64_spp8_multijitter_nojitter": dict(width=64, height=64, spp=8, no_patch=True, sampler="multijitter", jitter=False),   # 4 x 2 strata
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
