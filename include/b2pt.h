@@ -76,7 +76,8 @@ typedef struct B2Bsdf {
     float specular_transmittance[3];  /* dielectric, default 1                                */
     float alpha_v;
     float cond_eta[3];          /* (rough)conductor complex IOR, real part (default 0)         */
-    float _pad1;
+    int32_t twosided_back;      /* TwoSidedBRDF (twosided.cpp:63-92): 0 = one-sided; k > 0 = this record is the front-side
+                                   BRDF and bsdfs[k-1] the back-side one (k-1 = own index when a single BRDF is nested) */
     float cond_k[3];            /* imaginary part (default 1)                                  */
     float _pad2;
     /* plastic (plastic.cpp:136-180): reflectance = diffuse_reflectance, eta = int_ior / ext_ior, and the
@@ -85,10 +86,6 @@ typedef struct B2Bsdf {
     float specular_sampling_weight;   /* s_mean / (d_mean + s_mean), plastic.cpp:174           */
     float inv_eta_2;            /* 1 / eta^2                                                   */
     int32_t nonlinear;          /* 'nonlinear' (default 0)                                     */
-    /* TwoSidedBRDF (twosided.cpp:63-92): 0 = one-sided; k > 0 = this record is the front-side BRDF and
-       bsdfs[k-1] the back-side one (k-1 = own index when a single BRDF is nested)             */
-    int32_t twosided_back;
-    int32_t _pad3[3];
 } B2Bsdf;
 
 /* ---- textures (src/textures/{checkerboard,bitmap}.cpp), evaluated at si.uv ----------------- */

@@ -23,10 +23,9 @@ class B2Bsdf(C.Structure):
         ("reflectance", C.c_float * 3), ("eta", C.c_float),
         ("specular_reflectance", C.c_float * 3), ("alpha_u", C.c_float),
         ("specular_transmittance", C.c_float * 3), ("alpha_v", C.c_float),
-        ("cond_eta", C.c_float * 3), ("_pad1", C.c_float),
+        ("cond_eta", C.c_float * 3), ("twosided_back", C.c_int32),
         ("cond_k", C.c_float * 3), ("_pad2", C.c_float),
         ("fdr_int", C.c_float), ("specular_sampling_weight", C.c_float), ("inv_eta_2", C.c_float), ("nonlinear", C.c_int32),
-        ("twosided_back", C.c_int32), ("_pad3", C.c_int32 * 3),
     ]
 
 

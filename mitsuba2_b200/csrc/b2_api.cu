@@ -64,8 +64,9 @@ static ShadeFn shade_variant(uint32_t features) {
     if (!init) { fill_shade(table, std::make_integer_sequence<uint32_t, F_COUNT>{}); init = true; }
     return table[features & (F_COUNT - 1)];
 }
-static TraceFn trace_variant(bool inst, bool wide) {
-    return inst ? (wide ? k_trace_inst<true> : k_trace_inst<false>) : (wide ? k_trace<false, true> : k_trace<false, false>);
+static TraceFn trace_variant(bool inst, bool wide, bool shp) {
+    if (shp) return inst ? (wide ? k_trace_inst<true, true> : k_trace_inst<false, true>) : (wide ? k_trace<false, true, true> : k_trace<false, false, true>);
+    return inst ? (wide ? k_trace_inst<true, false> : k_trace_inst<false, false>) : (wide ? k_trace<false, true, false> : k_trace<false, false, false>);
 }
 
 struct B2Scene {
@@ -80,6 +81,7 @@ struct B2Scene {
     DBuf<float> tex_data;           // bitmap texels
     int shade_smem_bytes = 0;
     uint32_t features = 0;          // F_* of this scene
+    bool has_shapes = false;        // analytic shapes present (selects the SHP traversal variants)
     uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
     int smem_bytes = 0;
     int sm_count = 148;
@@ -574,7 +576,8 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
     cudaFuncSetAttribute(shade_variant(s->features), cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
-    cudaFuncSetAttribute(trace_variant(desc->n_instances != 0, (s->features & F_WIDE) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    s->has_shapes = ns != 0;
+    cudaFuncSetAttribute(trace_variant(desc->n_instances != 0, (s->features & F_WIDE) != 0, s->has_shapes), cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
     cudaFuncSetAttribute(k_stage_occluded<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
@@ -730,7 +733,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     const uint32_t run_features = s->features | (sampler_type != B2_SAMPLER_INDEPENDENT ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
     if (run_features != s->features) cudaFuncSetAttribute(shade_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
-    const TraceFn trace_fn = trace_variant(inst, wide);
+    const TraceFn trace_fn = trace_variant(inst, wide, s->has_shapes);
     uint32_t need_blocks = (set_slots + threads - 1) / threads;
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids

@@ -199,7 +199,8 @@ struct Trav {
 
     // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the same
     // kind of work. Returns when the ray is finished, or (can_yield) when the warp has thinned out.
-    template <bool ANY>
+    // SHP: the scene has analytic shapes (compile-time, so that plain triangle scenes do not carry the sphere / rectangle code)
+    template <bool ANY, bool SHP>
     B2_D void run(const DScene &sc, const SmemScene &sm, int *stack, bool can_yield) {
         while (cur != B2_TRAV_DONE) {
             while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) {
@@ -240,8 +241,9 @@ struct Trav {
                     else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
                     float t, u, v;
                     // a slot with a non-zero kind word holds an analytic shape (rectangle / sphere) instead of a triangle
-                    const bool hit = __float_as_uint(a1.w) ? shape_isect(sc.shapes[__float_as_uint(a2.w)], ray, ray.maxt, t, u, v)
-                                                           : tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v);
+                    bool hit;
+                    if (SHP && __float_as_uint(a1.w)) hit = shape_isect(sc.shapes[__float_as_uint(a2.w)], ray, ray.maxt, t, u, v);
+                    else hit = tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v);
                     if (hit) {
                         if (ANY) { any_hit = true; cur = B2_TRAV_DONE; return; }
                         uint32_t prim = __float_as_uint(a0.w);
@@ -329,12 +331,12 @@ B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, H
 // with the ray mapped to object space — origin as a point, direction as an UN-normalised vector,
 // mint/maxt unchanged so t stays in world units (instance.cpp:107-117).
 // INST is a compile-time switch so that flat scenes do not pay registers for the two-level code.
-template <bool ANY, bool INST>
+template <bool ANY, bool INST, bool SHP>
 B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
     if (!INST && sc.n_flat_leaves) return traverse_flat<ANY>(sc, sm, ray, best);      // warp-uniform
     int stack[40];
     Trav tr; tr.init(sc, ray, stack);
-    tr.run<ANY>(sc, sm, stack, false);
+    tr.run<ANY, SHP>(sc, sm, stack, false);
     if (INST && sc.n_instances && !(ANY && tr.any_hit)) {
         float dx = fabsf(ray.d.x) > 1e-20f ? ray.d.x : (ray.d.x < 0.f ? -1e-20f : 1e-20f);
         float dy = fabsf(ray.d.y) > 1e-20f ? ray.d.y : (ray.d.y < 0.f ? -1e-20f : 1e-20f);
@@ -372,7 +374,7 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
                     Ray ro; ro.o = xf_point(in.to_object, ray.o); ro.d = xf_vector(in.to_object, ray.d);
                     ro.mint = ray.mint; ro.maxt = ray.maxt;
                     tr.restart(sc, ro, stack, in.root, (int) ii);
-                    tr.run<ANY>(sc, sm, stack, false);
+                    tr.run<ANY, false>(sc, sm, stack, false);       // (shapegroups hold meshes only)
                     if (ANY && tr.any_hit) { best = tr.best; return true; }
                 }
             }
@@ -457,7 +459,7 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
 // so they share one launch: one tail and one shared-memory staging instead of two.
 // (A persistent-warp / dynamic-ray-fetch variant of the traversal was measured in round 1 and was
 // slower on the small-scene workload: 104 vs 93 ms per step.)
-template <bool INST, bool WIDE>
+template <bool INST, bool WIDE, bool SHP>
 __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
@@ -474,7 +476,7 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
             if (rd.w < 0.f) continue;                                  // retired lane
             float4 ro = q.ray_o[i];
             Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-            Hit h; traverse<false, INST>(sc, sm, ray, h);
+            Hit h; traverse<false, INST, SHP>(sc, sm, ray, h);
             q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
             if (INST) q.hit_inst[i] = h.inst;
             ++n_seg;
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
             float4 ro = q.sh_o[j], rd = q.sh_d[j], c = q.sh_c[j];
             Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
             Hit h;
-            bool occluded = traverse<true, INST>(sc, sm, ray, h);
+            bool occluded = traverse<true, INST, SHP>(sc, sm, ray, h);
             uint32_t lw = __float_as_uint(c.w);
             if (lw & SH_FINAL) {
                 float4 r = q.sh_r[j];
@@ -529,7 +531,7 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
 #define B2_INST_MINBLOCKS 4
 #endif
 
-template <bool WIDE>
+template <bool WIDE, bool SHP>
 __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
@@ -629,8 +631,9 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     for (uint32_t s = first; s < first + count; ++s) {
                         float4 a0 = __ldg(&sc.tri_isect[3 * (size_t) s]), a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]), a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]);
                         float t, u, v;
-                        const bool hit = __float_as_uint(a1.w) ? shape_isect(sc.shapes[__float_as_uint(a2.w)], tr.ray, tr.ray.maxt, t, u, v)
-                                                               : tri_isect(v3(a0), v3(a1), v3(a2), tr.ray, tr.tmax, t, u, v);
+                        bool hit;
+                        if (SHP && __float_as_uint(a1.w)) hit = shape_isect(sc.shapes[__float_as_uint(a2.w)], tr.ray, tr.ray.maxt, t, u, v);
+                        else hit = tri_isect(v3(a0), v3(a1), v3(a2), tr.ray, tr.tmax, t, u, v);
                         if (hit) {
                             if (any_ray) { tr.any_hit = true; break; }
                             uint32_t prim = __float_as_uint(a0.w);
@@ -1074,7 +1077,7 @@ __global__ void __launch_bounds__(256) k_stage_intersect(DScene sc, uint32_t n, 
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 ro = ray_o[i], rd = ray_d[i];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h; traverse<false, INST>(sc, sm, ray, h);
+        Hit h; traverse<false, INST, true>(sc, sm, ray, h);
         hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));     // prim id (not slot) at the ABI
         inst[i] = h.inst;
     }
@@ -1086,7 +1089,7 @@ __global__ void __launch_bounds__(256) k_stage_occluded(DScene sc, uint32_t n, c
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 ro = ray_o[i], rd = ray_d[i];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-        Hit h; occ[i] = traverse<true, INST>(sc, sm, ray, h) ? 1 : 0;
+        Hit h; occ[i] = traverse<true, INST, true>(sc, sm, ray, h) ? 1 : 0;
     }
 }
 __global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, const float4 *hit, const int32_t *inst, float *out) {
