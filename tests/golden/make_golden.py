@@ -294,20 +294,31 @@ SHAPES_SPEC = dict(
 )
 
 
-def shapes_xml():
+def shapes_xml(textured=False, mesh_dir=None):
     sp = SHAPES_SPEC
+    if textured:
+        # same shapes, but the sphere carries a checkerboard and the free-standing rectangle a bitmap: exercises the
+        # analytic uv parameterisations (sphere.cpp:352-361, rectangle.cpp:196-197)
+        rgb, _ = tex_images()
+        write_pfm(os.path.join(mesh_dir, "tex_rgb.pfm"), rgb)
     mat = lambda M: " ".join(repr(float(x)) for row in M for x in row)
     rl, s1, sl, rf = sp["rect_light"], sp["sphere"], sp["sphere_light"], sp["rect_flip"]
     return [
         f'<shape type="rectangle"><transform name="to_world"><matrix value="{mat(rl["to_world"])}"/></transform><ref id="light"/>'
         f'<emitter type="area"><rgb name="radiance" value="{rl["radiance"][0]}, {rl["radiance"][1]}, {rl["radiance"][2]}"/></emitter></shape>',
         f'<shape type="sphere"><point name="center" x="{s1["center"][0]}" y="{s1["center"][1]}" z="{s1["center"][2]}"/>'
-        f'<float name="radius" value="{s1["radius"]}"/><ref id="{s1["bsdf"]}"/></shape>',
+        f'<float name="radius" value="{s1["radius"]}"/>' + (
+            '<bsdf type="diffuse"><texture type="checkerboard" name="reflectance"><rgb name="color0" value="0.9, 0.8, 0.2"/>'
+            '<rgb name="color1" value="0.1, 0.2, 0.6"/><transform name="to_uv"><scale x="8" y="4"/></transform></texture></bsdf>'
+            if textured else f'<ref id="{s1["bsdf"]}"/>') + '</shape>',
         f'<shape type="sphere"><point name="center" x="{sl["center"][0]}" y="{sl["center"][1]}" z="{sl["center"][2]}"/>'
         f'<float name="radius" value="{sl["radius"]}"/><ref id="light"/>'
         f'<emitter type="area"><rgb name="radiance" value="{sl["radiance"][0]}, {sl["radiance"][1]}, {sl["radiance"][2]}"/></emitter></shape>',
         f'<shape type="rectangle"><transform name="to_world"><matrix value="{mat(rf["to_world"])}"/></transform>'
-        f'<boolean name="flip_normals" value="true"/><ref id="{rf["bsdf"]}"/></shape>',
+        f'<boolean name="flip_normals" value="true"/>' + (
+            f'<bsdf type="twosided"><bsdf type="diffuse"><texture type="bitmap" name="reflectance"><string name="filename" value="{mesh_dir}/tex_rgb.pfm"/>'
+            '<boolean name="raw" value="true"/><transform name="to_uv"><scale x="2" y="2"/></transform></texture></bsdf></bsdf>'
+            if textured else f'<ref id="{rf["bsdf"]}"/>') + '</shape>',
     ]
 
 
@@ -366,7 +377,7 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             path = dst
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
     if analytic:
-        shapes += shapes_xml()
+        shapes += shapes_xml(textured=analytic == "textured", mesh_dir=mesh_dir)
     if textures:
         rgb, gray = tex_images()
         write_pfm(os.path.join(mesh_dir, "tex_rgb.pfm"), rgb); write_pfm(os.path.join(mesh_dir, "tex_gray.pfm"), gray)
@@ -481,6 +492,7 @@ GOLDEN = {
     "cbox_64_spp16_stratified_nojitter_pass4": dict(width=64, height=64, spp=16, no_patch=True, sampler="stratified", jitter=False, samples_per_pass=4),
     "cbox_64_spp16_multijitter": dict(width=64, height=64, spp=16, no_patch=True, sampler="multijitter"),
     "cbox_64_spp8_multijitter_nojitter": dict(width=64, height=64, spp=8, no_patch=True, sampler="multijitter", jitter=False),   # 4 x 2 strata
+    "cbox_64_spp16_shapes_textured": dict(width=64, height=64, spp=16, no_patch=True, analytic="textured"),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
@@ -559,6 +571,8 @@ def main():
                          env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
         if kw.get("analytic"):
             extra.update(shapes_spec=np.array(repr(SHAPES_SPEC)))
+            if kw["analytic"] == "textured":
+                extra.update(tex_rgb=tex_images()[0])
         if kw.get("textures"):
             rgb_t, gray_t = tex_images()
             extra.update(tex_rgb=rgb_t, tex_gray=gray_t, tex_spec=np.array(repr(TEX_SPEC)))

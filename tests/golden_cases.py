@@ -99,10 +99,17 @@ def load(name, host):
         ids = sb.bsdf_ids; light = ids["light"]
         r = sb.add_rectangle(sp["rect_light"]["to_world"], bsdf=light)
         sb.add_shape_emitter(r, sp["rect_light"]["radiance"])
-        sb.add_sphere(sp["sphere"]["center"], sp["sphere"]["radius"], bsdf=ids[sp["sphere"]["bsdf"]])
+        textured = kw["analytic"] == "textured"
+        sphere_b = ids[sp["sphere"]["bsdf"]]
+        if textured:        # checkerboard on the sphere, two-sided bitmap-textured rectangle (make_golden.shapes_xml)
+            sphere_b = sb.add_diffuse(texture=sb.add_checkerboard((0.9, 0.8, 0.2), (0.1, 0.2, 0.6), [[8, 0, 0], [0, 4, 0], [0, 0, 1]]))
+        sb.add_sphere(sp["sphere"]["center"], sp["sphere"]["radius"], bsdf=sphere_b)
         s2 = sb.add_sphere(sp["sphere_light"]["center"], sp["sphere_light"]["radius"], bsdf=light)
         sb.add_shape_emitter(s2, sp["sphere_light"]["radius"] and sp["sphere_light"]["radiance"])
-        sb.add_rectangle(sp["rect_flip"]["to_world"], bsdf=ids[sp["rect_flip"]["bsdf"]], flip_normals=True)
+        rect_b = ids[sp["rect_flip"]["bsdf"]]
+        if textured:
+            rect_b = sb.make_twosided(sb.add_diffuse(texture=sb.add_bitmap(z["tex_rgb"], "bilinear", "repeat", [[2, 0, 0], [0, 2, 0], [0, 0, 1]])))
+        sb.add_rectangle(sp["rect_flip"]["to_world"], bsdf=rect_b, flip_normals=True)
     if kw.get("extra_emitter"):
         mi = sb.add_mesh(z["extra_positions"], z["extra_faces"], z["extra_normals"], bsdf=1)     # 'white'
         sb.add_area_emitter(mi, tuple(float(x) for x in z["extra_radiance"]))
