@@ -1,5 +1,8 @@
 // b2_bvh.cpp — see b2_bvh.h
 #include <cstdlib>
+#include <thread>
+#include <chrono>
+#include <cstdio>
 #include "b2_bvh.h"
 
 #include <algorithm>
@@ -31,17 +34,16 @@ struct Builder {
     static constexpr int kBins = 16;
     int kMaxLeaf = 2;
 
-    int build(uint32_t first, uint32_t count) {
-        int id = (int) nodes.size();
-        nodes.emplace_back();
+    // One node: bounds + binned-SAH split of idx[first, first+count). Returns false for a leaf.
+    bool make_node(uint32_t first, uint32_t count, Node2 &node, uint32_t &mid) {
         Box box; box.reset();
         Box cbox; cbox.reset();
         for (uint32_t i = first; i < first + count; ++i) {
             box.grow(tbox[idx[i]]);
             cbox.grow(&cent[3 * idx[i]]);
         }
-        nodes[id].box = box; nodes[id].first = first; nodes[id].count = count;
-        if (count <= (uint32_t) kMaxLeaf) return id;
+        node.box = box; node.first = first; node.count = count; node.left = node.right = -1;
+        if (count <= (uint32_t) kMaxLeaf) return false;
         // binned SAH over the 3 axes
         float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
         for (int ax = 0; ax < 3; ++ax) {
@@ -65,7 +67,6 @@ struct Builder {
                 if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
             }
         }
-        uint32_t mid;
         if (best_axis < 0) {
             mid = first + count / 2;            // all centroids coincide: split in the middle
         } else {
@@ -77,10 +78,50 @@ struct Builder {
             mid = (uint32_t) (it - idx.begin());
             if (mid == first || mid == first + count) mid = first + count / 2;
         }
-        int l = build(first, mid - first);
-        int r = build(mid, first + count - mid);
-        nodes[id].left = l; nodes[id].right = r; nodes[id].count = 0;
+        node.count = 0;
+        return true;
+    }
+
+    // serial build into `dst` (pre-order numbering, indices local to dst)
+    static int build_serial(Builder &b, std::vector<Node2> &dst, uint32_t first, uint32_t count) {
+        int id = (int) dst.size();
+        dst.emplace_back();
+        Node2 n; uint32_t mid = 0;
+        bool inner = b.make_node(first, count, n, mid);
+        dst[id] = n;
+        if (!inner) return id;
+        int l = build_serial(b, dst, first, mid - first);
+        int r = build_serial(b, dst, mid, first + count - mid);
+        dst[id].left = l; dst[id].right = r;
         return id;
+    }
+
+    // Parallel build with the SAME result as the serial one: the two subtrees of the top `par_depth` levels are built
+    // concurrently into their own arrays (they partition disjoint ranges of idx) and spliced in pre-order.
+    static void build_parallel(Builder &b, std::vector<Node2> &dst, uint32_t first, uint32_t count, int par_depth) {
+        if (par_depth <= 0 || count < 16384) { build_serial(b, dst, first, count); return; }
+        Node2 n; uint32_t mid = 0;
+        if (!b.make_node(first, count, n, mid)) { dst.push_back(n); return; }
+        std::vector<Node2> L, R;
+        std::thread th([&] { build_parallel(b, L, first, mid - first, par_depth - 1); });
+        build_parallel(b, R, mid, first + count - mid, par_depth - 1);
+        th.join();
+        const int base = (int) dst.size(), lo = base + 1, ro = base + 1 + (int) L.size();
+        n.left = lo; n.right = ro;
+        dst.push_back(n);
+        auto splice = [&](std::vector<Node2> &S, int off) {
+            for (Node2 &c : S) { if (c.left >= 0) { c.left += off; c.right += off; } dst.push_back(c); }
+        };
+        splice(L, lo); splice(R, ro);
+    }
+
+    int build(uint32_t first, uint32_t count) {
+        // B2_BVH_THREADS=1 forces the serial path (the result is identical; tests/test_abi_host.py checks it)
+        int par_depth = 4;       // up to 16 concurrent subtrees
+        if (const char *e = getenv("B2_BVH_THREADS")) { int t = atoi(e); par_depth = t <= 1 ? 0 : (t <= 2 ? 1 : (t <= 4 ? 2 : (t <= 8 ? 3 : 4))); }
+        nodes.clear();
+        build_parallel(*this, nodes, first, count, par_depth);
+        return 0;
     }
 };
 
@@ -134,7 +175,9 @@ void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh
         b.idx[i] = i;
     }
     b.nodes.reserve(2 * (size_t) n);
+    auto T0 = std::chrono::steady_clock::now();
     b.build(0, n);
+    auto T1 = std::chrono::steady_clock::now();
     out.order = b.idx;
 
     // conservative inflation of every child box: the fp32 triangle test can accept hits a few
@@ -181,6 +224,8 @@ void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh
         }
     }
     out.n_nodes = (uint32_t) (N.size() / 32);
+    if (getenv("B2_BVH_PROFILE")) { auto T2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "bvh: build %.0f ms, collapse %.0f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count()); }
 }
 
 #include "../../include/b2pt.h"

@@ -118,3 +118,27 @@ def test_scene_builders_reject_bad_input():
         sb.make_twosided(d)                                               # twosided.cpp:90-91
     with pytest.raises(NotImplementedError):
         api.DirectIntegrator(shading_samples=2)
+
+
+def test_parallel_bvh_build_is_deterministic():
+    """The host BVH build runs its top levels on several threads; the tree must not depend on the thread count
+    (B2_BVH_THREADS=1 forces the serial path)."""
+    import sys
+    code = (
+        "import sys, ctypes as C, hashlib; sys.path.insert(0, %r)\n"
+        "import numpy as np\n"
+        "from mitsuba2_b200 import api\n"
+        "L = api.lib(); L.b2_host_build_bvh4.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]\n"
+        "rng = np.random.default_rng(1); n = 80000\n"
+        "c = rng.normal(size=(n, 3)); c /= np.linalg.norm(c, axis=1, keepdims=True)\n"
+        "tri = (c[:, None, :] + 0.01 * rng.normal(size=(n, 3, 3))).astype(np.float32)\n"
+        "nodes = np.zeros((2 * n + 8, 32), np.float32); order = np.zeros(n, np.uint32); nn = C.c_uint32()\n"
+        "assert L.b2_host_build_bvh4(tri.ctypes.data, n, nodes.ctypes.data, len(nodes), C.byref(nn), order.ctypes.data) == 0\n"
+        "print(nn.value, hashlib.md5(nodes[:nn.value].tobytes() + order.tobytes()).hexdigest())\n" % ROOT)
+    outs = []
+    for threads in ("1", "4", "16"):
+        env = dict(os.environ); env["B2_BVH_THREADS"] = threads
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip())
+    assert outs[0] == outs[1] == outs[2], outs
