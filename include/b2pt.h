@@ -206,6 +206,7 @@ typedef struct B2RenderParams {
 /* samplers: IndependentSampler (src/samplers/independent.cpp) and StratifiedSampler (src/samplers/stratified.cpp;
    spp must be a perfect square, :60-75; multijitter: spp = rx * ry with ry = floor(sqrt(spp)), multijitter.cpp:68-81) */
 enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJITTER = 2 /* src/samplers/multijitter.cpp */,
+       B2_SAMPLER_LOW_DISCREPANCY = 3 /* src/samplers/ldsampler.cpp: (0,2)-sequence; spp = 4^k */,
        B2_SAMPLER_NO_JITTER = 0x100 };
 
 #define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */

@@ -181,7 +181,8 @@ class PathIntegrator:
 
     def __init__(self, max_depth=-1, rr_depth=5, samples_per_pass=0, block_size=32, sampler="independent", jitter=True):
         """sampler: "independent" (src/samplers/independent.cpp), "stratified" (src/samplers/stratified.cpp; spp must be a
-        perfect square) or "multijitter" (src/samplers/multijitter.cpp; spp = rx * ry with ry = floor(sqrt(spp)))."""
+        perfect square) "multijitter" (src/samplers/multijitter.cpp; spp = rx * ry with ry = floor(sqrt(spp))) or "ldsampler"
+        (src/samplers/ldsampler.cpp; spp = 4^k)."""
         self.max_depth, self.rr_depth = max_depth, rr_depth
         self.samples_per_pass, self.block_size = samples_per_pass, block_size
         self.sampler, self.jitter = sampler, jitter

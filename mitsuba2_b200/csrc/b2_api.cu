@@ -678,6 +678,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             smp_res_y = (uint32_t) std::sqrt((float) rp->spp);
             smp_res = (rp->spp + smp_res_y - 1) / smp_res_y;
             if (smp_res * smp_res_y != rp->spp) return fail(B2_ERR_INVALID, "Sample count rounded up to %u (got %u)", smp_res * smp_res_y, rp->spp);
+        } else if (sampler_type == B2_SAMPLER_LOW_DISCREPANCY) {       // ldsampler.cpp:68-78: spp = res^2, res a power of two
+            uint32_t lg = 0; while ((1u << lg) < rp->spp) ++lg;
+            if ((1u << lg) != rp->spp || (lg & 1u) || rp->spp < 4) return fail(B2_ERR_INVALID, "Sample count should be square and power of two (got %u)", rp->spp);
+            smp_res = lg;                                                // log2 of the sample count (permute(), random.h:194-207)
         } else return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
         if (spp_pass > 65535u) return fail(B2_ERR_INVALID, "stratified sampler: samples_per_pass must be < 65536");
         CU(s->smp.alloc(cap));

@@ -736,8 +736,40 @@ B2_D uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_t se
     } while (index >= sample_count);
     return (index + seed) % sample_count;
 }
+// LowDiscrepancySampler (ldsampler.cpp:96-131): permute (random.h:194-207; q.smp_res = log2 of the sample count),
+// radical_inverse_2 / sobol_2 (qmc.h:189-227)
+B2_D uint32_t sample_tea_32_r2(uint32_t v0, uint32_t v1) {
+    uint32_t sum = 0;
+    #pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        sum += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + sum) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + sum) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v1;
+}
+B2_D uint32_t permute_tea(uint32_t index, uint32_t log2_count, uint32_t seed) {
+    for (uint32_t level = 0; level < log2_count; ++level) {
+        uint32_t bit = 1u << level;
+        if ((sample_tea_32_r2(index | bit, seed) & bit) == bit) index ^= bit;
+    }
+    return index;
+}
+B2_D float radical_inverse_2(uint32_t index, uint32_t scramble) {
+    index = __brev(index);
+    return __uint_as_float(((index ^ scramble) >> 9) | 0x3f800000u) - 1.f;
+}
+B2_D float sobol_2(uint32_t index, uint32_t scramble) {
+    for (uint32_t v = 1u << 31; index != 0; index >>= 1, v ^= v >> 1)
+        if (index & 1u) scramble ^= v;
+    return (float) scramble / 4294967296.f;
+}
 template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2 &sm) {
     if constexpr (EXT) if (q.smp) {
+        if (q.smp_type == B2_SAMPLER_LOW_DISCREPANCY) {
+            uint32_t i = permute_tea(sm.x >> 16, q.smp_res, sm.y + (sm.x & 0xffffu)); ++sm.x;
+            return radical_inverse_2(i, sample_tea_32(sm.y, 0x48bc48ebu));
+        }
         uint32_t ps = sm.y + (sm.x & 0xffffu);
         if (q.smp_type == B2_SAMPLER_MULTIJITTER) ps *= 0x45fbe943u;                                  // multijitter.cpp:108
         uint32_t p = permute_kensler(sm.x >> 16, q.smp_count, ps); ++sm.x;                            // m_dimension_index++
@@ -748,6 +780,10 @@ template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2
 }
 template <bool EXT> B2_D float2 smp_next_2d(const Queues &q, uint64_t &rng, uint2 &sm) {
     if constexpr (EXT) if (q.smp) {
+        if (q.smp_type == B2_SAMPLER_LOW_DISCREPANCY) {
+            uint32_t i = permute_tea(sm.x >> 16, q.smp_res, sm.y + (sm.x & 0xffffu)); ++sm.x;
+            return make_float2(radical_inverse_2(i, sample_tea_32(sm.y, 0x98bc51abu)), sobol_2(i, sample_tea_32(sm.y, 0x04223e2du)));
+        }
         if (q.smp_type == B2_SAMPLER_MULTIJITTER) {                                                   // multijitter.cpp:116-144
             uint32_t ps = sm.y + (sm.x & 0xffffu);
             uint32_t sq = permute_kensler(sm.x >> 16, q.smp_count, ps * 0x51633e2du); ++sm.x;

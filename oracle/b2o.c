@@ -1521,6 +1521,29 @@ static uint32_t permute_kensler(uint32_t index, uint32_t sample_count, uint32_t 
     } while (index >= sample_count);
     return (index + seed) % sample_count;
 }
+/* LowDiscrepancySampler (ldsampler.cpp:96-131): permute (random.h:194-207), radical_inverse_2 / sobol_2 (qmc.h:189-227) */
+static uint32_t permute_tea(uint32_t index, uint32_t sample_count, uint32_t seed) {
+    uint32_t n = 0; while ((1u << (n + 1)) <= sample_count) ++n;            /* log2i */
+    for (uint32_t level = 0; level < n; ++level) {
+        uint32_t bit = 1u << level;
+        uint32_t rand = sample_tea_32(index | bit, seed, 2);
+        if ((rand & bit) == bit) index ^= bit;
+    }
+    return index;
+}
+static float radical_inverse_2(uint32_t index, uint32_t scramble) {
+    index = (index << 16) | (index >> 16);
+    index = ((index & 0x00ff00ffu) << 8) | ((index & 0xff00ff00u) >> 8);
+    index = ((index & 0x0f0f0f0fu) << 4) | ((index & 0xf0f0f0f0u) >> 4);
+    index = ((index & 0x33333333u) << 2) | ((index & 0xccccccccu) >> 2);
+    index = ((index & 0x55555555u) << 1) | ((index & 0xaaaaaaaau) >> 1);
+    return b2o_u2f(((index ^ scramble) >> 9) | 0x3f800000u) - 1.f;
+}
+static float sobol_2(uint32_t index, uint32_t scramble) {
+    for (uint32_t v = 1u << 31; index != 0; index >>= 1, v ^= v >> 1)
+        if (index & 1u) scramble ^= v;
+    return (float) scramble / 4294967296.f;
+}
 /* Sampler::seed + PCG32Sampler::seed (+ StratifiedSampler::seed); the constructor's derived values (stratified.cpp:60-75) */
 static void smp_seed(osampler *s, const B2RenderParams *rp, uint64_t seed_offset) {
     sampler_seed(&s->rng, rp->seed, seed_offset);
@@ -1542,6 +1565,10 @@ static void smp_seed(osampler *s, const B2RenderParams *rp, uint64_t seed_offset
 static inline void smp_advance(osampler *s) { s->dim = 0; s->sample_index++; }
 static inline float smp_next_1d(osampler *s) {
     if (s->type == B2_SAMPLER_INDEPENDENT) return pcg32_next_float(&s->rng);
+    if (s->type == B2_SAMPLER_LOW_DISCREPANCY) {
+        uint32_t i = permute_tea(s->sample_index, s->count, s->perm_seed + s->dim++);
+        return radical_inverse_2(i, sample_tea_32(s->perm_seed, 0x48bc48ebu, 4));
+    }
     uint32_t ps = s->perm_seed + s->dim++;
     if (s->type == B2_SAMPLER_MULTIJITTER) ps *= 0x45fbe943u;       /* multijitter.cpp:108 */
     uint32_t p = permute_kensler(s->sample_index, s->count, ps);
@@ -1550,6 +1577,12 @@ static inline float smp_next_1d(osampler *s) {
 }
 static inline void smp_next_2d(osampler *s, float *x, float *y) {
     if (s->type == B2_SAMPLER_INDEPENDENT) { *x = pcg32_next_float(&s->rng); *y = pcg32_next_float(&s->rng); return; }
+    if (s->type == B2_SAMPLER_LOW_DISCREPANCY) {
+        uint32_t i = permute_tea(s->sample_index, s->count, s->perm_seed + s->dim++);
+        *x = radical_inverse_2(i, sample_tea_32(s->perm_seed, 0x98bc51abu, 4));
+        *y = sobol_2(i, sample_tea_32(s->perm_seed, 0x04223e2du, 4));
+        return;
+    }
     if (s->type == B2_SAMPLER_MULTIJITTER) {                        /* multijitter.cpp:116-144 */
         uint32_t ps = s->perm_seed + s->dim++;
         uint32_t sq = permute_kensler(s->sample_index, s->count, ps * 0x51633e2du);

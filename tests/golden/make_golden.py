@@ -493,6 +493,7 @@ GOLDEN = {
     "cbox_64_spp16_multijitter": dict(width=64, height=64, spp=16, no_patch=True, sampler="multijitter"),
     "cbox_64_spp8_multijitter_nojitter": dict(width=64, height=64, spp=8, no_patch=True, sampler="multijitter", jitter=False),   # 4 x 2 strata
     "cbox_64_spp16_shapes_textured": dict(width=64, height=64, spp=16, no_patch=True, analytic="textured"),
+    "cbox_64_spp16_ldsampler": dict(width=64, height=64, spp=16, no_patch=True, sampler="ldsampler"),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
