@@ -118,7 +118,11 @@ public:
                 std::memset(&e, 0, sizeof e);
                 ParamCollector pc;
                 const_cast<Emitter *>(em.get())->traverse(&pc);
-                if (em->is_environment()) {
+                if (em->is_environment() && std::string(em->class_()->name()) == "ConstantBackgroundEmitter") {   // constant.cpp:120-122
+                    e.type = B2_EMITTER_CONSTANT; e.mesh = -1; e.scale = 1.f;
+                    Color3f rad = ((Texture *) pc.objects["radiance"])->eval(si0);
+                    for (int k = 0; k < 3; ++k) e.radiance[k] = rad[k];
+                } else if (em->is_environment()) {
                     if (pc.params.count("data") == 0 || pc.params.count("resolution") == 0)
                         Throw("b2path: unsupported environment emitter %s", em->class_()->name());
                     auto &data = *(DynamicBuffer<Float> *) pc.params["data"].second;

@@ -261,6 +261,13 @@ class SceneBuffers:
         self.meshes[mesh_index]["emitter"] = len(self.emitters) - 1
         return len(self.emitters) - 1
 
+    def add_constant_emitter(self, radiance=(1.0, 1.0, 1.0)):
+        """ConstantBackgroundEmitter (src/emitters/constant.cpp): uniform environment radiance."""
+        e = B2Emitter(); e.type = EMITTER_CONSTANT; e.mesh = -1; e.scale = 1.0
+        e.radiance[:] = radiance
+        self.emitters.append(e)
+        return len(self.emitters) - 1
+
     def add_envmap(self, rgb, scale=1.0, to_world=None):
         """EnvironmentMapEmitter (src/emitters/envmap.cpp): rgb = float32 [H, W, 3] lat-long image."""
         rgb = np.asarray(rgb, np.float32)

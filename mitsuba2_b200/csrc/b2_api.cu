@@ -134,15 +134,15 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     for (uint32_t m = n_top_meshes; m < desc->n_meshes; ++m)
         if (desc->meshes[m].emitter >= 0) return fail(B2_ERR_INVALID, "Instancing of emitters is not supported");   // shapegroup.cpp:24-25
     for (uint32_t e = 0; e < desc->n_emitters; ++e)
-        if (desc->emitters[e].type != B2_EMITTER_AREA && desc->emitters[e].type != B2_EMITTER_ENVMAP)
-            return fail(B2_ERR_INVALID, "emitter %u: only area and envmap emitters are supported", e);
+        if (desc->emitters[e].type != B2_EMITTER_AREA && desc->emitters[e].type != B2_EMITTER_ENVMAP && desc->emitters[e].type != B2_EMITTER_CONSTANT)
+            return fail(B2_ERR_INVALID, "emitter %u: only area, envmap and constant emitters are supported", e);
     {
         int n_env = 0;
         for (uint32_t e = 0; e < desc->n_emitters; ++e) {
             const B2Emitter &em = desc->emitters[e];
-            if (em.type != B2_EMITTER_ENVMAP) continue;
+            if (em.type == B2_EMITTER_AREA) continue;
             if (++n_env > 1) return fail(B2_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:48-49
-            if (!em.envmap || em.env_width < 2 || em.env_height < 2) return fail(B2_ERR_INVALID, "Distribution2D(): input array resolution must be >= 2!");
+            if (em.type == B2_EMITTER_ENVMAP && (!em.envmap || em.env_width < 2 || em.env_height < 2)) return fail(B2_ERR_INVALID, "Distribution2D(): input array resolution must be >= 2!");
         }
     }
     for (uint32_t m = 0; m < desc->n_meshes; ++m) {
@@ -327,7 +327,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     std::vector<float> cdf;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &src = desc->emitters[e];
-        if (src.type == B2_EMITTER_ENVMAP) { std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; continue; }
+        if (src.type != B2_EMITTER_AREA) { std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; std::memcpy(ems[e].radiance, src.radiance, 12); continue; }
         if (src.shape > 0) {          // area emitter on an analytic shape
             if ((uint32_t) src.shape > ns) { delete s; return fail(B2_ERR_INVALID, "emitter %u: bad shape index", e); }
             std::memset(&ems[e], 0, sizeof(DEmitter));
@@ -459,10 +459,13 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_prims;
     // environment map: Hierarchical2D levels (distr_2d.h:372-471) + scene bounding sphere (envmap.cpp:127-131)
     d.env.index = -1;
-    for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type == B2_EMITTER_ENVMAP) s->features |= F_ENV;
+    for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type != B2_EMITTER_AREA) s->features |= F_ENV;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &em = desc->emitters[e];
-        if (em.type != B2_EMITTER_ENVMAP) continue;
+        if (em.type == B2_EMITTER_AREA) continue;
+        DEnv &v = d.env;
+        v.index = (int32_t) e; v.type = em.type; std::memcpy(v.radiance, em.radiance, 12);
+        if (em.type == B2_EMITTER_ENVMAP) {
         uint32_t W = (uint32_t) em.env_width, H = (uint32_t) em.env_height;
         std::vector<float> lum((size_t) W * H);
         for (uint32_t y = 0; y < H; ++y) {                            // envmap.cpp:86-117
@@ -509,11 +512,11 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         std::vector<float4> texels((size_t) W * H);
         std::memcpy(texels.data(), em.envmap, (size_t) W * H * 16);
         if (s->env_data.upload(texels) != cudaSuccess || s->env_levels.upload(lv) != cudaSuccess) { delete s; return fail(B2_ERR_CUDA, "envmap upload failed"); }
-        DEnv &v = d.env;
-        v.data = s->env_data.p; v.levels = s->env_levels.p; v.index = (int32_t) e; v.width = (int32_t) W; v.height = (int32_t) H; v.n_levels = nl;
+        v.data = s->env_data.p; v.levels = s->env_levels.p; v.width = (int32_t) W; v.height = (int32_t) H; v.n_levels = nl;
         for (int k = 0; k < nl; ++k) { v.level_off[k] = loff[k]; v.level_w[k] = lw[k]; }
         v.scale = em.scale;
         std::memcpy(v.to_world, em.env_to_world, 48); std::memcpy(v.to_object, em.env_to_object, 48);
+        }   // (constant background emitter, constant.cpp: only the bounding sphere below)
         // scene bbox = union of the top-level shapes' boxes (scene.cpp:35-39); instances: to_world * corner (instance.cpp:83-94)
         float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
         for (uint32_t m = 0; m < n_top_meshes; ++m)

@@ -51,6 +51,8 @@ struct DEnv {
     int32_t width, height, n_levels;
     uint32_t level_off[16], level_w[16];
     float scale, radius;        // 'scale'; bounding-sphere radius of the scene (envmap.cpp:127-131)
+    int32_t type;               // B2_EMITTER_ENVMAP or B2_EMITTER_CONSTANT (src/emitters/constant.cpp)
+    float radiance[3];          // constant: the radiance
     float to_world[12], to_object[12];
 };
 
@@ -719,15 +721,27 @@ B2_D void env_dir_to_uv(const DEnv &env, float3 d_world, float3 &d, float &u, fl
     u -= floorf(u); v -= floorf(v);
 }
 B2_D float3 env_eval(const DEnv &env, float3 ray_d) {                         // envmap.cpp:134-147
+    if (env.type == B2_EMITTER_CONSTANT) return v3(env.radiance[0], env.radiance[1], env.radiance[2]);   // constant.cpp:54-57
     float3 d; float u, v; env_dir_to_uv(env, ray_d, d, u, v);
     return env_eval_spectrum(env, u, v);
 }
 B2_D float env_inv_sin_theta(float3 d) { return b2_rsqrt(b2_max(b2_sqr(d.x) + b2_sqr(d.z), b2_sqr(B2_EPS))); }
 B2_D float env_pdf_direction(const DEnv &env, float3 d_world) {               // envmap.cpp:192-208
+    if (env.type == B2_EMITTER_CONSTANT) return .25f * B2_INV_PI;             // square_to_uniform_sphere_pdf, constant.cpp:110-114
     float3 d; float u, v; env_dir_to_uv(env, d_world, d, u, v);
     return env_warp_eval(env, u, v) * env_inv_sin_theta(d) * (1.f / (2.f * b2_sqr(B2_PI)));
 }
+B2_D float3 square_to_uniform_sphere(float sx, float sy);
 B2_D float3 env_sample_direction(const DEnv &env, float3 ref_p, float sx, float sy, DS &ds) {   // envmap.cpp:156-190
+    if (env.type == B2_EMITTER_CONSTANT) {                             // ConstantBackgroundEmitter::sample_direction, constant.cpp:83-108
+        float3 dd = square_to_uniform_sphere(sx, sy);
+        float dist0 = 2.f * env.radius;
+        ds.p = ref_p + dd * dist0; ds.n = -dd;
+        ds.pdf = .25f * B2_INV_PI;
+        ds.d = dd; ds.dist = dist0;
+        float ip = b2_rcp(ds.pdf);
+        return v3(env.radiance[0] * ip, env.radiance[1] * ip, env.radiance[2] * ip);
+    }
     float u, v, pdf; env_warp_sample(env, sx, sy, u, v, pdf);
     float theta = v * B2_PI, phi = u * (2.f * B2_PI);
     float st, ct, sp, cp; b2_sincos(theta, &st, &ct); b2_sincos(phi, &sp, &cp);

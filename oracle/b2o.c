@@ -417,7 +417,7 @@ static oscene *oscene_create(const B2SceneDesc *d) {
     /* environment: Scene::Scene expands m_bbox by every top-level shape's bbox (scene.cpp:35-39);
        EnvironmentMapEmitter::set_scene (envmap.cpp:127-131) takes its bounding sphere */
     s->env = -1;
-    for (uint32_t e = 0; e < d->n_emitters; ++e) if (d->emitters[e].type == B2_EMITTER_ENVMAP) s->env = (int) e;
+    for (uint32_t e = 0; e < d->n_emitters; ++e) if (d->emitters[e].type == B2_EMITTER_ENVMAP || d->emitters[e].type == B2_EMITTER_CONSTANT) s->env = (int) e;   /* is_environment() */
     if (s->env >= 0) {
         float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
         for (uint32_t m = 0; m < n_top; ++m)
@@ -455,7 +455,7 @@ static oscene *oscene_create(const B2SceneDesc *d) {
         v3 dmax = v3_sub(c, v3_make(hi[0], hi[1], hi[2]));
         float radius = sqrtf(v3_dot(dmax, dmax));                      /* bbox.h:329-332 */
         s->env_radius = b2o_max(B2O_RAY_EPS, radius * (1.f + B2O_RAY_EPS));
-        env_build(s, &d->emitters[s->env]);
+        if (d->emitters[s->env].type == B2_EMITTER_ENVMAP) env_build(s, &d->emitters[s->env]);
     }
     return s;
 }
@@ -1254,7 +1254,7 @@ static v3 area_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx
 static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds);
 static float env_pdf_direction(const oscene *s, v3 d_world);
 static v3 emitter_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
-    return s->desc->emitters[emitter].type == B2_EMITTER_ENVMAP ? env_sample_direction(s, emitter, ref_p, sx, sy, ds)
+    return s->desc->emitters[emitter].type != B2_EMITTER_AREA ? env_sample_direction(s, emitter, ref_p, sx, sy, ds)
                                                                  : area_sample_direction(s, emitter, ref_p, sx, sy, ds);
 }
 /* Scene::sample_emitter_direction scene.cpp:164-214 (visibility test done by the caller) */
@@ -1275,7 +1275,7 @@ static v3 scene_sample_emitter_direction(const oscene *s, v3 ref_p, float sx, fl
    -> Shape::pdf_direction shape.cpp:312-323 -> Mesh::pdf_position mesh.cpp:417-420 */
 static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 ref_p, v3 d, v3 n, float dist) {
     const B2Emitter *em = &s->desc->emitters[emitter];
-    if (em->type == B2_EMITTER_ENVMAP) {
+    if (em->type != B2_EMITTER_AREA) {
         float pdf = env_pdf_direction(s, d);
         if (s->desc->n_emitters != 1) pdf = pdf * (1.f / (float) s->desc->n_emitters);
         return pdf;
@@ -1443,6 +1443,7 @@ static inline void env_dir_to_uv(const B2Emitter *em, v3 d_world, v3 *d_local, f
 static v3 env_eval(const oscene *s, v3 ray_d);
 static v3 env_eval(const oscene *s, v3 ray_d) {
     const B2Emitter *em = &s->desc->emitters[s->env];
+    if (em->type == B2_EMITTER_CONSTANT) return v3_make(em->radiance[0], em->radiance[1], em->radiance[2]);   /* constant.cpp:54-57 */
     v3 dl; float u, v; env_dir_to_uv(em, ray_d, &dl, &u, &v);
     return env_eval_spectrum(em, u, v);
 }
@@ -1453,12 +1454,23 @@ static inline float env_inv_sin_theta(v3 d) {      /* safe_rsqrt(max(d.x^2 + d.z
 /* EnvironmentMapEmitter::pdf_direction (envmap.cpp:192-208) */
 static float env_pdf_direction(const oscene *s, v3 d_world) {
     const B2Emitter *em = &s->desc->emitters[s->env];
+    if (em->type == B2_EMITTER_CONSTANT) return .25f * B2O_INV_PI;             /* square_to_uniform_sphere_pdf, constant.cpp:110-114 */
     v3 d; float u, v; env_dir_to_uv(em, d_world, &d, &u, &v);
     return env_warp_eval(s, em, u, v) * env_inv_sin_theta(d) * (1.f / (2.f * b2o_sqr(B2O_PI)));
 }
 /* EnvironmentMapEmitter::sample_direction (envmap.cpp:156-190) */
 static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
     const B2Emitter *em = &s->desc->emitters[emitter];
+    if (em->type == B2_EMITTER_CONSTANT) {                                      /* ConstantBackgroundEmitter::sample_direction, constant.cpp:83-108 */
+        v3 dd = square_to_uniform_sphere(sx, sy);
+        float dist0 = 2.f * s->env_radius;
+        ds->p = v3_add(ref_p, v3_scale(dd, dist0));
+        ds->n = v3_neg(dd);
+        ds->pdf = .25f * B2O_INV_PI;
+        ds->d = dd; ds->dist = dist0; ds->emitter = emitter;
+        float ip = b2o_rcp(ds->pdf);
+        return v3_make(em->radiance[0] * ip, em->radiance[1] * ip, em->radiance[2] * ip);
+    }
     float u, v, pdf; env_warp_sample(s, em, sx, sy, &u, &v, &pdf);
     float theta = v * B2O_PI, phi = u * (2.f * B2O_PI);
     float st, ct, sp, cp; b2o_sincos(theta, &st, &ct); b2o_sincos(phi, &sp, &cp);

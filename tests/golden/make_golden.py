@@ -202,7 +202,10 @@ ENV_TO_WORLD = [0, 0, 1, 0,  0, 1, 0, 0,  -1, 0, 0, 0,  0, 0, 0, 1]      # exact
 ENV_DROPPED = {
     "only": ("cbox_luminaire.obj", "cbox_ceiling.obj", "cbox_back.obj", "cbox_greenwall.obj", "cbox_redwall.obj"),
     "with_area": ("cbox_ceiling.obj", "cbox_back.obj", "cbox_greenwall.obj"),
+    "constant": ("cbox_luminaire.obj", "cbox_ceiling.obj", "cbox_back.obj"),      # constant background + nothing else
+    "constant_area": ("cbox_ceiling.obj", "cbox_greenwall.obj"),
 }
+CONSTANT_RADIANCE = (0.8, 1.1, 1.6)
 
 
 def env_image(w=48, h=24):
@@ -387,7 +390,9 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
         open(path, "w").write(EXTRA_EMITTER_OBJ)
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/><ref id="white"/>'
                       '<emitter type="area"><rgb name="radiance" value="4.0, 16.0, 6.0"/></emitter></shape>')
-    if envmap is not None:
+    if envmap is not None and envmap.startswith("constant"):       # ConstantBackgroundEmitter (src/emitters/constant.cpp)
+        shapes.append(f'<emitter type="constant"><rgb name="radiance" value="{CONSTANT_RADIANCE[0]}, {CONSTANT_RADIANCE[1]}, {CONSTANT_RADIANCE[2]}"/></emitter>')
+    elif envmap is not None:
         path = os.path.join(mesh_dir, "env.pfm")
         write_pfm(path, env_image())
         shapes.append(f'<emitter type="envmap"><string name="filename" value="{path}"/><float name="scale" value="1.5"/>'
@@ -494,6 +499,8 @@ GOLDEN = {
     "cbox_64_spp8_multijitter_nojitter": dict(width=64, height=64, spp=8, no_patch=True, sampler="multijitter", jitter=False),   # 4 x 2 strata
     "cbox_64_spp16_shapes_textured": dict(width=64, height=64, spp=16, no_patch=True, analytic="textured"),
     "cbox_64_spp16_ldsampler": dict(width=64, height=64, spp=16, no_patch=True, sampler="ldsampler"),
+    "cbox_64_spp16_constant": dict(width=64, height=64, spp=16, envmap="constant"),
+    "cbox_64_spp16_constant_area": dict(width=64, height=64, spp=16, envmap="constant_area"),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
@@ -567,7 +574,10 @@ def main():
                 p = os.path.join(td, "e.obj"); open(p, "w").write(EXTRA_EMITTER_OBJ)
                 ep, en, ef = load_obj_like_reference(p)
             extra = dict(extra_positions=ep, extra_normals=en, extra_faces=ef, extra_radiance=np.array(EXTRA_EMITTER_RADIANCE, np.float32))
-        if kw.get("envmap"):
+        if kw.get("envmap", "").startswith("constant"):
+            extra.update(const_radiance=np.array(CONSTANT_RADIANCE, np.float32),
+                         env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
+        elif kw.get("envmap"):
             extra.update(env_rgb=env_image(), env_to_world=np.array(ENV_TO_WORLD, np.float32), env_scale=np.float32(1.5),
                          env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
         if kw.get("analytic"):

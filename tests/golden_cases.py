@@ -86,7 +86,10 @@ def load(name, host):
         sb = scenes.veach_mis(host, kw["width"], kw["height"])
         return sb, abi.render_params(max_depth=6, rr_depth=5, spp=kw["spp"], block_size=32), z["rgb"]
     env = None; drop = (0, 6) if kw.get("analytic") else ()      # analytic: luminaire + small box replaced by shapes
-    if kw.get("envmap"):
+    const_env = None
+    if str(kw.get("envmap", "")).startswith("constant"):
+        const_env = tuple(float(x) for x in z["const_radiance"]); drop = tuple(int(i) for i in z["env_dropped"])
+    elif kw.get("envmap"):
         env = dict(rgb=z["env_rgb"], scale=float(z["env_scale"]), to_world=z["env_to_world"].reshape(4, 4))
         drop = tuple(int(i) for i in z["env_dropped"])
     sb = scenes.cbox(host, kw["width"], kw["height"], rfilter=kw.get("rfilter", "box"), envmap=env, drop_meshes=drop,
@@ -94,6 +97,8 @@ def load(name, host):
                      texcoords={i: z[f"uv_m{i}"] for i in range(8)} if kw.get("textures") else None,
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
                      instances=kw.get("instances"), crop=kw.get("crop"))
+    if const_env:                        # after the shapes, like the XML
+        sb.add_constant_emitter(const_env)
     if kw.get("analytic"):              # SHAPES_SPEC of make_golden.py; emitters in XML order: rectangle, then sphere
         sp = ast.literal_eval(str(z["shapes_spec"]))
         ids = sb.bsdf_ids; light = ids["light"]
