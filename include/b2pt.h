@@ -104,17 +104,17 @@ typedef struct B2Texture {
                                    height x width x channels fp32, row-major                   */
 } B2Texture;
 
-/* ---- emitters (src/emitters/{area,envmap,constant}.cpp) --------------------------------- */
-enum { B2_EMITTER_AREA = 0, B2_EMITTER_ENVMAP = 1, B2_EMITTER_CONSTANT = 2 };
+/* ---- emitters (src/emitters/{area,envmap,constant,point}.cpp) --------------------------- */
+enum { B2_EMITTER_AREA = 0, B2_EMITTER_ENVMAP = 1, B2_EMITTER_CONSTANT = 2, B2_EMITTER_POINT = 3 /* src/emitters/point.cpp */ };
 
 typedef struct B2Emitter {
     int32_t type;               /* B2_EMITTER_*                                                */
     int32_t mesh;               /* area: index of the mesh it is attached to                   */
-    float radiance[3];          /* area / constant: rgb radiance (srgb_d65 in rgb mode)        */
+    float radiance[3];          /* area / constant: rgb radiance (srgb_d65 in rgb mode); point: 'intensity' */
     float scale;                /* envmap 'scale'                                              */
     const float *envmap;        /* envmap: RGBA fp32 texels, (height x width x 4), row-major   */
     int32_t env_width, env_height;
-    float env_to_world[16];     /* envmap to_world, row-major 4x4                              */
+    float env_to_world[16];     /* envmap / point to_world, row-major 4x4 (point: its translation is the position) */
     float env_to_object[16];    /* its inverse, as the reference's Transform stores it         */
     int32_t shape;              /* area: 0 = attached to `mesh`; k > 0 = attached to B2SceneDesc.shapes[k-1] */
     int32_t _pad;

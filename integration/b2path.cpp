@@ -122,6 +122,13 @@ public:
                     e.type = B2_EMITTER_CONSTANT; e.mesh = -1; e.scale = 1.f;
                     Color3f rad = ((Texture *) pc.objects["radiance"])->eval(si0);
                     for (int k = 0; k < 3; ++k) e.radiance[k] = rad[k];
+                } else if (std::string(em->class_()->name()) == "PointLight") {                                     // point.cpp:86-113, 128-130
+                    e.type = B2_EMITTER_POINT; e.mesh = -1; e.scale = 1.f;
+                    Color3f in = ((Texture *) pc.objects["intensity"])->eval(si0);
+                    for (int k = 0; k < 3; ++k) e.radiance[k] = in[k];
+                    auto trafo = em->world_transform()->eval(0.f);
+                    store_row_major(trafo.matrix, e.env_to_world);
+                    store_row_major(trafo.inverse().matrix, e.env_to_object);
                 } else if (em->is_environment()) {
                     if (pc.params.count("data") == 0 || pc.params.count("resolution") == 0)
                         Throw("b2path: unsupported environment emitter %s", em->class_()->name());
@@ -136,7 +143,7 @@ public:
                 } else {
                     auto it = emitter_of_mesh.find(em.get());
                     if (it == emitter_of_mesh.end() || pc.objects.count("radiance") == 0)
-                        Throw("b2path: only area and envmap emitters are supported (got %s)", em->class_()->name());
+                        Throw("b2path: only area, envmap, constant and point emitters are supported (got %s)", em->class_()->name());
                     e.type = B2_EMITTER_AREA; e.mesh = it->second; e.scale = 1.f;
                     Color3f rad = ((Texture *) pc.objects["radiance"])->eval(si0);
                     for (int k = 0; k < 3; ++k) e.radiance[k] = rad[k];

@@ -11,7 +11,7 @@ import numpy as np
 B2_OK, B2_ERR_INVALID, B2_ERR_CUDA, B2_ERR_CANCELLED, B2_ERR_NO_DEVICE = range(5)
 BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL, BSDF_CONDUCTOR, BSDF_PLASTIC = range(6)
 MF_BECKMANN, MF_GGX = 0, 1
-EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT = range(3)
+EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT, EMITTER_POINT = range(4)
 FILTER_RESOLUTION = 31
 FLAG_STAGE_TIMING = 1
 FLAG_SINGLE_SET = 2
@@ -265,6 +265,17 @@ class SceneBuffers:
         """ConstantBackgroundEmitter (src/emitters/constant.cpp): uniform environment radiance."""
         e = B2Emitter(); e.type = EMITTER_CONSTANT; e.mesh = -1; e.scale = 1.0
         e.radiance[:] = radiance
+        self.emitters.append(e)
+        return len(self.emitters) - 1
+
+    def add_point_light(self, position, intensity=(1.0, 1.0, 1.0)):
+        """PointLight (src/emitters/point.cpp): isotropic point emitter at `position` (to_world = translate(position))."""
+        e = B2Emitter(); e.type = EMITTER_POINT; e.mesh = -1; e.scale = 1.0
+        e.radiance[:] = intensity
+        m = np.eye(4, dtype=np.float32); m[:3, 3] = position
+        e.env_to_world[:] = [float(x) for x in m.reshape(-1)]
+        inv = np.eye(4, dtype=np.float32); inv[:3, 3] = -np.asarray(position, np.float32)
+        e.env_to_object[:] = [float(x) for x in inv.reshape(-1)]
         self.emitters.append(e)
         return len(self.emitters) - 1
 

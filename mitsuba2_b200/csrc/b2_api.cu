@@ -134,13 +134,14 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     for (uint32_t m = n_top_meshes; m < desc->n_meshes; ++m)
         if (desc->meshes[m].emitter >= 0) return fail(B2_ERR_INVALID, "Instancing of emitters is not supported");   // shapegroup.cpp:24-25
     for (uint32_t e = 0; e < desc->n_emitters; ++e)
-        if (desc->emitters[e].type != B2_EMITTER_AREA && desc->emitters[e].type != B2_EMITTER_ENVMAP && desc->emitters[e].type != B2_EMITTER_CONSTANT)
-            return fail(B2_ERR_INVALID, "emitter %u: only area, envmap and constant emitters are supported", e);
+        if (desc->emitters[e].type != B2_EMITTER_AREA && desc->emitters[e].type != B2_EMITTER_ENVMAP && desc->emitters[e].type != B2_EMITTER_CONSTANT &&
+            desc->emitters[e].type != B2_EMITTER_POINT)
+            return fail(B2_ERR_INVALID, "emitter %u: only area, envmap, constant and point emitters are supported", e);
     {
         int n_env = 0;
         for (uint32_t e = 0; e < desc->n_emitters; ++e) {
             const B2Emitter &em = desc->emitters[e];
-            if (em.type == B2_EMITTER_AREA) continue;
+            if (em.type == B2_EMITTER_AREA || em.type == B2_EMITTER_POINT) continue;
             if (++n_env > 1) return fail(B2_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:48-49
             if (em.type == B2_EMITTER_ENVMAP && (!em.envmap || em.env_width < 2 || em.env_height < 2)) return fail(B2_ERR_INVALID, "Distribution2D(): input array resolution must be >= 2!");
         }
@@ -327,7 +328,11 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     std::vector<float> cdf;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &src = desc->emitters[e];
-        if (src.type != B2_EMITTER_AREA) { std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; std::memcpy(ems[e].radiance, src.radiance, 12); continue; }
+        if (src.type != B2_EMITTER_AREA) {
+            std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; std::memcpy(ems[e].radiance, src.radiance, 12);
+            if (src.type == B2_EMITTER_POINT) { ems[e].position[0] = src.env_to_world[3]; ems[e].position[1] = src.env_to_world[7]; ems[e].position[2] = src.env_to_world[11]; s->features |= F_TEX; }
+            continue;
+        }
         if (src.shape > 0) {          // area emitter on an analytic shape
             if ((uint32_t) src.shape > ns) { delete s; return fail(B2_ERR_INVALID, "emitter %u: bad shape index", e); }
             std::memset(&ems[e], 0, sizeof(DEmitter));
@@ -459,10 +464,10 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_prims;
     // environment map: Hierarchical2D levels (distr_2d.h:372-471) + scene bounding sphere (envmap.cpp:127-131)
     d.env.index = -1;
-    for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type != B2_EMITTER_AREA) s->features |= F_ENV;
+    for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type == B2_EMITTER_ENVMAP || desc->emitters[e].type == B2_EMITTER_CONSTANT) s->features |= F_ENV;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &em = desc->emitters[e];
-        if (em.type == B2_EMITTER_AREA) continue;
+        if (em.type == B2_EMITTER_AREA || em.type == B2_EMITTER_POINT) continue;
         DEnv &v = d.env;
         v.index = (int32_t) e; v.type = em.type; std::memcpy(v.radiance, em.radiance, 12);
         if (em.type == B2_EMITTER_ENVMAP) {

@@ -30,7 +30,7 @@ struct DEmitter {
     float cdf_sum, cdf_norm;
     uint32_t valid_first, valid_last;
     int32_t shape;              // 0: attached to a mesh; k > 0: analytic shape k - 1
-    int32_t _pad[3];
+    float position[3];          // point light: trafo.translation() (point.cpp:92)
 };
 
 // analytic shapes (src/shapes/rectangle.cpp, sphere.cpp): 3x4 row-major transforms + the values update() derives
@@ -595,7 +595,7 @@ template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, flo
 }
 
 // ---- emitter sampling (area.cpp, shape.cpp:292-323, mesh.cpp:352-397, scene.cpp:164-231) ------
-struct DS { float3 p, n, d; float pdf, dist; };
+struct DS { float3 p, n, d; float pdf, dist; bool delta; };
 
 B2_D uint32_t distr_sample(const float *cdf, uint32_t first, uint32_t last, float sum, float value) {   // distr_1d.h:144-155
     value *= sum;
@@ -826,14 +826,29 @@ B2_D float3 shape_sample_direction(const Tables &sc, const DEmitter &em, float3 
 }
 
 template <uint32_t F> B2_D float3 emitter_sample_direction(const Tables &sc, const DEnv &env, uint32_t e, float3 ref_p, float sx, float sy, DS &ds) {
+    ds.delta = false;
     if constexpr ((F & F_ENV) != 0) if ((int) e == env.index) return env_sample_direction(env, ref_p, sx, sy, ds);
-    if constexpr ((F & F_TEX) != 0) if (sc.emitters[e].shape > 0) return shape_sample_direction(sc, sc.emitters[e], ref_p, sx, sy, ds);
+    if constexpr ((F & F_TEX) != 0) {
+        const DEmitter &em = sc.emitters[e];
+        if (em.type == B2_EMITTER_POINT) {                            // PointLight::sample_direction, point.cpp:86-113
+            ds.p = v3(em.position[0], em.position[1], em.position[2]);
+            ds.n = v3(0.f, 0.f, 0.f);
+            ds.pdf = 1.f; ds.delta = true;
+            ds.d = ds.p - ref_p;
+            ds.dist = sqrtf(dot(ds.d, ds.d));
+            float inv_dist = b2_rcp(ds.dist);
+            ds.d = ds.d * inv_dist;
+            float w = b2_sqr(inv_dist);
+            return v3(em.radiance[0] * w, em.radiance[1] * w, em.radiance[2] * w);
+        }
+        if (em.shape > 0) return shape_sample_direction(sc, em, ref_p, sx, sy, ds);
+    }
     return area_sample_direction(sc, sc.emitters[e], ref_p, sx, sy, ds);
 }
 
 template <uint32_t F> B2_D float3 scene_sample_emitter_direction(const Tables &sc, const DEnv &env, float3 ref_p, float sx, float sy, DS &ds) {   // scene.cpp:164-214
     uint32_t ne = sc.n_emitters;
-    if (ne == 0) { ds.pdf = 0.f; ds.dist = 0.f; ds.p = ds.n = ds.d = v3(0.f, 0.f, 0.f); return v3(0.f, 0.f, 0.f); }
+    if (ne == 0) { ds.pdf = 0.f; ds.dist = 0.f; ds.delta = false; ds.p = ds.n = ds.d = v3(0.f, 0.f, 0.f); return v3(0.f, 0.f, 0.f); }
     if (ne == 1) return emitter_sample_direction<F>(sc, env, 0, ref_p, sx, sy, ds);
     float emitter_pdf = 1.f / (float) ne;
     uint32_t index = (uint32_t) (sx * (float) ne);

@@ -979,6 +979,7 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
                         float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo, bsdf_reflectance<F>(tb, bsdf, si));
                         float bpdf = bsdf_pdf<F>(bsdf, si, wo);
                         float mis = mis_weight(ds.pdf, bpdf);
+                        if constexpr ((F & F_TEX) != 0) if (ds.delta) mis = 1.f;                // path.cpp:170
                         float3 c = ((throughput * mis) * bsdf_val) * emitter_val;
                         if (any_nonzero(c)) {                                       // visibility: scene.cpp:203-207
                             shadow = true;

@@ -1121,7 +1121,7 @@ static v3 bsdf_sample(const B2Bsdf *b, const osi *si, float sample1, float s2x, 
  * Emitters — src/emitters/area.cpp, src/librender/shape.cpp:292-323, mesh.cpp:352-397,
  *            scene.cpp:164-231, distr_1d.h:144-204
  * ============================================================================================ */
-typedef struct { v3 p, n, d; float pdf, dist; int emitter; } ods;
+typedef struct { v3 p, n, d; float pdf, dist; int emitter; int delta; } ods;
 
 static uint32_t distr_sample(const float *cdf, uint32_t n, float sum, float value) {   /* distr_1d.h:144-155 */
     value *= sum;
@@ -1254,7 +1254,20 @@ static v3 area_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx
 static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds);
 static float env_pdf_direction(const oscene *s, v3 d_world);
 static v3 emitter_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
-    return s->desc->emitters[emitter].type != B2_EMITTER_AREA ? env_sample_direction(s, emitter, ref_p, sx, sy, ds)
+    ds->delta = 0;
+    if (s->desc->emitters[emitter].type == B2_EMITTER_POINT) {                 /* PointLight::sample_direction, point.cpp:86-113 */
+        const B2Emitter *em = &s->desc->emitters[emitter];
+        ds->p = v3_make(em->env_to_world[3], em->env_to_world[7], em->env_to_world[11]);
+        ds->n = v3_make(0.f, 0.f, 0.f);
+        ds->pdf = 1.f; ds->delta = 1; ds->emitter = emitter;
+        ds->d = v3_sub(ds->p, ref_p);
+        ds->dist = sqrtf(v3_dot(ds->d, ds->d));
+        float inv_dist = b2o_rcp(ds->dist);
+        ds->d = v3_scale(ds->d, inv_dist);
+        float w = b2o_sqr(inv_dist);
+        return v3_make(em->radiance[0] * w, em->radiance[1] * w, em->radiance[2] * w);
+    }
+    return (s->desc->emitters[emitter].type == B2_EMITTER_ENVMAP || s->desc->emitters[emitter].type == B2_EMITTER_CONSTANT) ? env_sample_direction(s, emitter, ref_p, sx, sy, ds)
                                                                  : area_sample_direction(s, emitter, ref_p, sx, sy, ds);
 }
 /* Scene::sample_emitter_direction scene.cpp:164-214 (visibility test done by the caller) */
@@ -1275,7 +1288,7 @@ static v3 scene_sample_emitter_direction(const oscene *s, v3 ref_p, float sx, fl
    -> Shape::pdf_direction shape.cpp:312-323 -> Mesh::pdf_position mesh.cpp:417-420 */
 static float scene_pdf_emitter_direction(const oscene *s, int emitter, v3 ref_p, v3 d, v3 n, float dist) {
     const B2Emitter *em = &s->desc->emitters[emitter];
-    if (em->type != B2_EMITTER_AREA) {
+    if (em->type == B2_EMITTER_ENVMAP || em->type == B2_EMITTER_CONSTANT) {
         float pdf = env_pdf_direction(s, d);
         if (s->desc->n_emitters != 1) pdf = pdf * (1.f / (float) s->desc->n_emitters);
         return pdf;
@@ -1657,7 +1670,7 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, osampler *rng, 
                 if (flip) wo.z = -wo.z;
                 v3 bsdf_val = bsdf_eval(bsdf, &sib, wo);
                 float bpdf = bsdf_pdf(bsdf, &sib, wo);
-                float mis = mis_weight(ds.pdf, bpdf);
+                float mis = ds.delta ? 1.f : mis_weight(ds.pdf, bpdf);             /* path.cpp:170 */
                 v3 c = v3_mul(v3_mul(v3_scale(throughput, mis), bsdf_val), emitter_val);
                 /* scene.cpp:203-207: spec[ray_test(ray)] = 0. The reference traces the shadow ray
                    whenever ds.pdf != 0; the outcome only matters when the contribution is not

@@ -206,6 +206,7 @@ ENV_DROPPED = {
     "constant_area": ("cbox_ceiling.obj", "cbox_greenwall.obj"),
 }
 CONSTANT_RADIANCE = (0.8, 1.1, 1.6)
+POINT_LIGHT = dict(position=(278.0, 500.0, 279.5), intensity=(800000.0, 600000.0, 400000.0))
 
 
 def env_image(w=48, h=24):
@@ -336,7 +337,7 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
              rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
-             textures=False, crop=None, analytic=False, integrator="path", sampler="independent", jitter=True):
+             textures=False, crop=None, analytic=False, integrator="path", sampler="independent", jitter=True, point_light=None):
     """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
     bs = []
     for k, v in CBOX_BSDFS.items():
@@ -348,6 +349,8 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             bs.append(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>')
     shapes = []
     for fn, bsdf, tr in CBOX_SHAPES:
+        if point_light == "only" and fn == "cbox_luminaire.obj":
+            continue                       # lit by the point light alone
         if analytic and fn in ("cbox_luminaire.obj", "cbox_smallbox.obj"):
             continue                       # replaced by analytic shapes (appended below)
         if envmap is not None and fn in ENV_DROPPED[envmap]:
@@ -379,6 +382,10 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             write_uv_obj(path, dst)
             path = dst
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
+    if point_light:                    # PointLight (src/emitters/point.cpp), after the shapes
+        p, i = POINT_LIGHT["position"], POINT_LIGHT["intensity"]
+        shapes.append(f'<emitter type="point"><point name="position" x="{p[0]}" y="{p[1]}" z="{p[2]}"/>'
+                      f'<rgb name="intensity" value="{i[0]}, {i[1]}, {i[2]}"/></emitter>')
     if analytic:
         shapes += shapes_xml(textured=analytic == "textured", mesh_dir=mesh_dir)
     if textures:
@@ -501,6 +508,8 @@ GOLDEN = {
     "cbox_64_spp16_ldsampler": dict(width=64, height=64, spp=16, no_patch=True, sampler="ldsampler"),
     "cbox_64_spp16_constant": dict(width=64, height=64, spp=16, envmap="constant"),
     "cbox_64_spp16_constant_area": dict(width=64, height=64, spp=16, envmap="constant_area"),
+    "cbox_64_spp16_point": dict(width=64, height=64, spp=16, no_patch=True, point_light="only"),
+    "cbox_64_spp16_point_area": dict(width=64, height=64, spp=16, no_patch=True, point_light="with_area"),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
@@ -580,6 +589,8 @@ def main():
         elif kw.get("envmap"):
             extra.update(env_rgb=env_image(), env_to_world=np.array(ENV_TO_WORLD, np.float32), env_scale=np.float32(1.5),
                          env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
+        if kw.get("point_light"):
+            extra.update(point_light=np.array(repr(POINT_LIGHT)))
         if kw.get("analytic"):
             extra.update(shapes_spec=np.array(repr(SHAPES_SPEC)))
             if kw["analytic"] == "textured":

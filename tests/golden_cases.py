@@ -86,6 +86,8 @@ def load(name, host):
         sb = scenes.veach_mis(host, kw["width"], kw["height"])
         return sb, abi.render_params(max_depth=6, rr_depth=5, spp=kw["spp"], block_size=32), z["rgb"]
     env = None; drop = (0, 6) if kw.get("analytic") else ()      # analytic: luminaire + small box replaced by shapes
+    if kw.get("point_light") == "only":
+        drop = (0,)
     const_env = None
     if str(kw.get("envmap", "")).startswith("constant"):
         const_env = tuple(float(x) for x in z["const_radiance"]); drop = tuple(int(i) for i in z["env_dropped"])
@@ -97,6 +99,9 @@ def load(name, host):
                      texcoords={i: z[f"uv_m{i}"] for i in range(8)} if kw.get("textures") else None,
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
                      instances=kw.get("instances"), crop=kw.get("crop"))
+    if kw.get("point_light"):
+        pl = ast.literal_eval(str(z["point_light"]))
+        sb.add_point_light(pl["position"], pl["intensity"])
     if const_env:                        # after the shapes, like the XML
         sb.add_constant_emitter(const_env)
     if kw.get("analytic"):              # SHAPES_SPEC of make_golden.py; emitters in XML order: rectangle, then sphere
