@@ -122,7 +122,8 @@ int b2_device_count(void) {
 int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     if (!desc || !out) return fail(B2_ERR_INVALID, "b2_scene_create: null argument");
     *out = nullptr;
-    if (b2_device_count() == 0) return fail(B2_ERR_NO_DEVICE, "b2_scene_create: no CUDA device (libb2pt has no CPU fallback)");
+    // (the description is validated first, so that malformed input is reported the same way with or without a device;
+    //  a VALID scene then fails loudly without a GPU: there is no CPU fallback)
     uint32_t n_top_meshes = desc->n_groups ? desc->n_top_meshes : desc->n_meshes;
     if (n_top_meshes > desc->n_meshes) return fail(B2_ERR_INVALID, "n_top_meshes out of range");
     for (uint32_t g = 0; g < desc->n_groups; ++g)
@@ -164,6 +165,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     if (desc->film.crop_size[0] <= 0 || desc->film.crop_size[1] <= 0 || desc->film.crop_size[0] > 65535 || desc->film.crop_size[1] > 65535)
         return fail(B2_ERR_INVALID, "film crop size must be in [1, 65535]");
 
+    if (b2_device_count() == 0) return fail(B2_ERR_NO_DEVICE, "b2_scene_create: no CUDA device (libb2pt has no CPU fallback)");
     B2Scene *s = new B2Scene();
     std::vector<uint32_t> mesh_first(desc->n_meshes + 1, 0);
     uint32_t nt = 0;

@@ -142,3 +142,33 @@ def test_parallel_bvh_build_is_deterministic():
         assert r.returncode == 0, r.stderr
         outs.append(r.stdout.strip())
     assert outs[0] == outs[1] == outs[2], outs
+
+
+def _create_error(sb):
+    with pytest.raises(api.B2Error) as e:
+        api.Scene(sb)
+    return e.value
+
+
+def test_scene_description_is_validated_like_the_reference():
+    """b2_scene_create validates the description before it touches the device, with the reference's error wording
+    where it has one (no GPU needed: malformed input never reaches CUDA)."""
+    H = api.Host()
+    sb = scenes.cbox(H, 16, 16); sb.meshes[1]["bsdf"] = 99
+    assert _create_error(sb).code == 1 and "bad bsdf index" in str(_create_error(sb))
+    sb = scenes.cbox(H, 16, 16); sb.meshes[2]["faces"] = sb.meshes[2]["faces"].copy(); sb.meshes[2]["faces"][0, 0] = 10_000
+    assert "face index out of range" in str(_create_error(sb))
+    # two environment emitters (scene.cpp:48-49)
+    sb = scenes.cbox(H, 16, 16); sb.add_constant_emitter((1, 1, 1)); sb.add_constant_emitter((1, 1, 1))
+    assert "Only one environment emitter can be specified per scene." in str(_create_error(sb))
+    # an emitter inside a shapegroup (shapegroup.cpp:24-25)
+    sb = scenes.cbox(H, 16, 16); g = sb.add_shapegroup([0]); sb.add_instance(g, np.eye(4, dtype=np.float32))
+    assert "Instancing of emitters is not supported" in str(_create_error(sb))
+    # analytic shapes
+    sb = scenes.cbox(H, 16, 16); sb.add_sphere((0, 0, 0), 1.0, bsdf=77)
+    assert "shape 0: bad bsdf index" in str(_create_error(sb))
+    sb = scenes.cbox(H, 16, 16); sb.add_sphere((0, 0, 0), -1.0)
+    assert "sphere radius must be positive" in str(_create_error(sb))
+    # film limits
+    sb = scenes.cbox(H, 16, 16); sb.film.crop_size[0] = 0
+    assert "film crop size" in str(_create_error(sb))
