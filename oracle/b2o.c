@@ -2040,6 +2040,26 @@ B2O_API void b2o_bsdf_sample(const B2Bsdf *b, const float wi[3], float sample1, 
     *out_pdf = bs.pdf; *out_eta = bs.eta; *out_delta = bs.delta;
     out_weight[0] = w.x; out_weight[1] = w.y; out_weight[2] = w.z;
 }
+/* unit-test entry points: texture lookups and sampler sequences */
+B2O_API void b2o_texture_eval(const B2Texture *t, uint32_t n, const float *uv, float *out_rgb) {
+    for (uint32_t i = 0; i < n; ++i) {
+        v3 c = texture_eval(t, uv + 2 * (size_t) i);
+        out_rgb[3 * (size_t) i] = c.x; out_rgb[3 * (size_t) i + 1] = c.y; out_rgb[3 * (size_t) i + 2] = c.z;
+    }
+}
+/* the first `n_samples` samples of one pixel's sampler (seed_offset as in render_block): per sample the draws named by
+   `pattern` ('1' = next_1d, '2' = next_2d), written consecutively */
+B2O_API void b2o_sampler_draws(const B2RenderParams *rp, uint64_t seed_offset, uint32_t n_samples, const char *pattern, float *out) {
+    osampler s; smp_seed(&s, rp, seed_offset);
+    size_t k = 0;
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        for (const char *p = pattern; *p; ++p) {
+            if (*p == '2') { smp_next_2d(&s, &out[k], &out[k + 1]); k += 2; }
+            else out[k++] = smp_next_1d(&s);
+        }
+        smp_advance(&s);
+    }
+}
 B2O_API void b2o_fresnel(float cos_theta_i, float eta, float out[4]) {
     fresnel(cos_theta_i, eta, &out[0], &out[1], &out[2], &out[3]);
 }
