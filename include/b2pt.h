@@ -22,6 +22,9 @@
  *        intersect : Scene::ray_intersect_preliminary_gpu   scene.h:196, scene_optix.inl:426
  *        occluded  : Scene::ray_test_gpu                    scene.h:202, scene_optix.inl:554
  *        si_fill   : Mesh::compute_surface_interaction      src/librender/mesh.cpp:449-545
+ *        (+ what widened from there, SURVEY 8(f): textures B2Texture, analytic shapes B2Shape, twosided / conductor /
+ *         plastic BSDFs, constant and point emitters, the direct integrator's default, stratified / multijitter /
+ *         low-discrepancy samplers B2RenderParams.sampler — each citing its reference file below)
  *   b2_develop
  *        HDRFilm::bitmap(): XYZAW -> linear sRGB, divide by W  src/films/hdrfilm.cpp:251-322
  *   b2_host_*            (host-side C++ helpers that mirror reference host code)
