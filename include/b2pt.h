@@ -278,6 +278,14 @@ B2_API float b2_host_parse_fov(float fov_deg, const char *fov_axis, int width, i
 B2_API int b2_host_film_box(int width, int height, B2Film *out);                 /* box.cpp      */
 B2_API int b2_host_film_gaussian(int width, int height, float stddev, B2Film *out); /* gaussian.cpp */
 /* order[i] = (bx, by) of the i-th block handed out by Spiral::next_block */
+/* BSDF / shape records from plugin parameters, for hosts that do not link the reference: the values
+   SmoothPlastic::parameters_changed() derives (plastic.cpp:162-176: 1/eta^2, fresnel_diffuse_reflectance(1/eta) of
+   fresnel.h:327-361, s_mean / (d_mean + s_mean)); Sphere 'center' / 'radius' (sphere.cpp:95-130); Rectangle 'to_world'
+   with 'flip_normals' folded in (rectangle.cpp:75-92). to_world: row-major 4x4, affine. */
+B2_API int b2_host_bsdf_plastic(float int_ior, float ext_ior, const float diffuse_reflectance[3], float diffuse_mean,
+                                const float specular_reflectance[3] /* or NULL */, float specular_mean, int nonlinear, B2Bsdf *out);
+B2_API int b2_host_shape_sphere(const float center[3], float radius, int flip_normals, int bsdf, B2Shape *out);
+B2_API int b2_host_shape_rectangle(const float to_world[16], int flip_normals, int bsdf, B2Shape *out);
 B2_API int b2_host_spiral(int width, int height, int block_size, uint32_t *n_blocks,
                           int32_t *order_xy /* 2 * n_blocks or NULL to query n_blocks */);
 

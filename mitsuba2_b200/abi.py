@@ -188,6 +188,9 @@ class SceneBuffers:
         self.film = B2Film()
         self.groups = []      # list of lists of mesh indices (shapegroups, src/librender/shapegroup.cpp)
         self.instances = []   # (group index, to_world 4x4, to_object 4x4)   (src/shapes/instance.cpp)
+        self.shapes = []      # B2Shape: analytic rectangles / spheres (src/shapes/{rectangle,sphere}.cpp)
+        self.textures = []    # B2Texture (src/textures/{checkerboard,bitmap}.cpp)
+        self._tex_mean = []; self._tex_data = []
         self._keep = []
 
     # -- BSDF / emitter constructors with the reference plugins' defaults --------------------
@@ -298,8 +301,6 @@ class SceneBuffers:
     def _add_texture(self, t, to_uv, mean):
         m = np.eye(3, dtype=np.float32) if to_uv is None else np.asarray(to_uv, np.float32).reshape(3, 3)
         t.to_uv[:] = [float(x) for x in m.reshape(-1)]
-        if not hasattr(self, "textures"):
-            self.textures = []; self._tex_mean = []
         self.textures.append(t); self._tex_mean.append(np.float32(mean))
         return len(self.textures)
 
@@ -320,8 +321,6 @@ class SceneBuffers:
         t.wrap = {"repeat": WRAP_REPEAT, "mirror": WRAP_MIRROR, "clamp": WRAP_CLAMP}[wrap_mode]
         t.height, t.width, t.channels = d.shape
         t.data = fptr(d)
-        if not hasattr(self, "_tex_data"):
-            self._tex_data = []
         self._tex_data.append(d)
         lum = d[..., 0] if d.shape[2] == 1 else (np.float32(0.212671) * d[..., 0] + np.float32(0.715160) * d[..., 1]
                                                   + np.float32(0.072169) * d[..., 2])
@@ -342,8 +341,6 @@ class SceneBuffers:
         sh.to_world[:] = [float(x) for x in m.reshape(-1)]
         sh.to_object[:] = [float(x) for x in inv.reshape(-1)]
         sh.bsdf = bsdf; sh.emitter = -1
-        if not hasattr(self, "shapes"):
-            self.shapes = []
         self.shapes.append(sh)
         return len(self.shapes) - 1
 
@@ -425,10 +422,10 @@ class SceneBuffers:
         d.n_instances = len(self.instances); d.instances = ins if self.instances else None
         d.n_top_meshes = n_top
         d.sensor = self.sensor; d.film = self.film
-        texs = getattr(self, "textures", [])
+        texs = self.textures
         ts = (B2Texture * max(1, len(texs)))(*texs)
         d.n_textures = len(texs); d.textures = ts if texs else None
-        shs = getattr(self, "shapes", [])
+        shs = self.shapes
         ss = (B2Shape * max(1, len(shs)))(*shs)
         d.n_shapes = len(shs); d.shapes = ss if shs else None
         self._keep = [ms, bs, es, gf, ins, ts, ss]

@@ -131,6 +131,70 @@ int b2_host_perspective_sensor(const float to_world[16], float fov_x, float near
     return B2_OK;
 }
 
+// SmoothPlastic (plastic.cpp:136-180) without the reference: parameters_changed()'s derived values in fp32
+static float fresnel_diffuse_reflectance(float eta) {                    // fresnel.h:327-361
+    if (eta < 1.f) return -1.4399f * (eta * eta) + 0.7099f * eta + 0.6681f + 0.0636f / eta;
+    float i1 = 1.f / eta, i2 = i1 * i1, i3 = i2 * i1, i4 = i3 * i1, i5 = i4 * i1;
+    return 0.919317f - 3.4793f * i1 + 6.75335f * i2 - 7.80989f * i3 + 4.98554f * i4 - 1.36881f * i5;
+}
+int b2_host_bsdf_plastic(float int_ior, float ext_ior, const float diffuse_reflectance[3], float diffuse_mean,
+                         const float specular_reflectance[3], float specular_mean, int nonlinear, B2Bsdf *out) {
+    if (!out || !diffuse_reflectance || !(int_ior > 0.f) || !(ext_ior > 0.f)) return B2_ERR_INVALID;   // plastic.cpp:143-145
+    std::memset(out, 0, sizeof *out);
+    out->type = B2_BSDF_PLASTIC;
+    float eta = int_ior / ext_ior;
+    out->eta = eta; out->inv_eta_2 = 1.f / (eta * eta); out->fdr_int = fresnel_diffuse_reflectance(1.f / eta);
+    for (int k = 0; k < 3; ++k) {
+        out->reflectance[k] = diffuse_reflectance[k];
+        out->specular_reflectance[k] = specular_reflectance ? specular_reflectance[k] : 1.f;
+        out->specular_transmittance[k] = 1.f;
+    }
+    float s_mean = specular_reflectance ? specular_mean : 1.f;
+    out->specular_sampling_weight = s_mean / (diffuse_mean + s_mean);
+    out->nonlinear = nonlinear ? 1 : 0;
+    return B2_OK;
+}
+
+// general 4x4 affine inverse (in double, rounded once) for the shape records
+static bool invert_affine(const float M[16], float inv[16]) {
+    double a[3][3], t[3];
+    for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) a[r][c] = M[4 * r + c]; t[r] = M[4 * r + 3]; }
+    double det = a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                 a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]);
+    if (det == 0.0 || !std::isfinite(det)) return false;
+    double id = 1.0 / det, b[3][3];
+    b[0][0] = (a[1][1] * a[2][2] - a[1][2] * a[2][1]) * id; b[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id; b[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+    b[1][0] = (a[1][2] * a[2][0] - a[1][0] * a[2][2]) * id; b[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id; b[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+    b[2][0] = (a[1][0] * a[2][1] - a[1][1] * a[2][0]) * id; b[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id; b[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) inv[4 * r + c] = (float) b[r][c];
+        inv[4 * r + 3] = (float) -(b[r][0] * t[0] + b[r][1] * t[1] + b[r][2] * t[2]);
+    }
+    inv[12] = inv[13] = inv[14] = 0.f; inv[15] = 1.f;
+    return true;
+}
+int b2_host_shape_sphere(const float center[3], float radius, int flip_normals, int bsdf, B2Shape *out) {
+    if (!out || !center || radius == 0.f) return B2_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->type = B2_SHAPE_SPHERE; out->bsdf = bsdf; out->emitter = -1;
+    if (radius < 0.f) { radius = -radius; flip_normals = !flip_normals; }      // sphere.cpp:121-124
+    out->flip_normals = flip_normals ? 1 : 0; out->radius = radius;
+    for (int k = 0; k < 3; ++k) {
+        out->center[k] = center[k];
+        out->to_world[5 * k] = radius; out->to_world[4 * k + 3] = center[k];   // translate(center) * scale(radius), sphere.cpp:100-101
+    }
+    out->to_world[15] = 1.f;
+    return invert_affine(out->to_world, out->to_object) ? B2_OK : B2_ERR_INVALID;
+}
+int b2_host_shape_rectangle(const float to_world[16], int flip_normals, int bsdf, B2Shape *out) {
+    if (!out || !to_world) return B2_ERR_INVALID;
+    std::memset(out, 0, sizeof *out);
+    out->type = B2_SHAPE_RECTANGLE; out->bsdf = bsdf; out->emitter = -1;
+    std::memcpy(out->to_world, to_world, 64);
+    if (flip_normals) for (int r = 0; r < 4; ++r) out->to_world[4 * r + 2] = -out->to_world[4 * r + 2];   // * scale(1, 1, -1), rectangle.cpp:75-77
+    return invert_affine(out->to_world, out->to_object) ? B2_OK : B2_ERR_INVALID;
+}
+
 int b2_host_film_box(int w, int h, B2Film *f) {                          // src/rfilters/box.cpp:24-33
     if (!f || w <= 0 || h <= 0) return B2_ERR_INVALID;
     film_dims(f, w, h);

@@ -172,3 +172,40 @@ def test_scene_description_is_validated_like_the_reference():
     # film limits
     sb = scenes.cbox(H, 16, 16); sb.film.crop_size[0] = 0
     assert "film crop size" in str(_create_error(sb))
+
+
+def test_c_record_builders_match_the_python_ones():
+    """b2_host_bsdf_plastic / b2_host_shape_sphere / b2_host_shape_rectangle (for hosts that do not link the reference)
+    produce the records mitsuba2_b200.abi builds in numpy — the ones the golden scenes are pinned with."""
+    L = api.lib()
+    L.b2_host_bsdf_plastic.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float), C.c_float, C.c_int,
+                                       C.POINTER(abi.B2Bsdf)]
+    L.b2_host_shape_sphere.argtypes = [C.POINTER(C.c_float), C.c_float, C.c_int, C.c_int, C.POINTER(abi.B2Shape)]
+    L.b2_host_shape_rectangle.argtypes = [C.POINTER(C.c_float), C.c_int, C.c_int, C.POINTER(abi.B2Shape)]
+    for kw in (dict(diffuse_reflectance=(0.1, 0.27, 0.36), int_ior=1.9, ext_ior=1.000277),
+               dict(diffuse_reflectance=(0.7, 0.6, 0.5), int_ior=1.49, ext_ior=1.000277, specular_reflectance=(0.8, 0.9, 1.0)),
+               dict(diffuse_reflectance=(0.8, 0.3, 0.2), int_ior=1.49, ext_ior=1.000277, nonlinear=True)):
+        sb = abi.SceneBuffers(); ref = sb.bsdfs[sb.add_plastic(**kw)]
+        d = kw["diffuse_reflectance"]; s = kw.get("specular_reflectance")
+        out = abi.B2Bsdf()
+        assert L.b2_host_bsdf_plastic(kw["int_ior"], kw["ext_ior"], (C.c_float * 3)(*d), abi._rgb_mean(d),
+                                      (C.c_float * 3)(*s) if s else None, abi._rgb_mean(s) if s else 1.0, int(kw.get("nonlinear", False)),
+                                      C.byref(out)) == 0
+        assert _bytes(out) == _bytes(ref), kw
+    sb = abi.SceneBuffers(); sb.add_diffuse()
+    for center, radius, flip in (((186.0, 64.0, 169.0), 64.0, False), ((1.5, -2.25, 0.125), 0.5, True)):
+        idx = sb.add_sphere(center, radius, 0, flip); ref = sb.shapes[idx]
+        out = abi.B2Shape()
+        assert L.b2_host_shape_sphere((C.c_float * 3)(*center), radius, int(flip), 0, C.byref(out)) == 0
+        assert _bytes(out) == _bytes(ref)
+    for M, flip in (([[64, 0, 0, 278], [0, 0, -1, 548], [0, 32, 0, 280], [0, 0, 0, 1]], False),
+                    ([[32, 0, 0, 100], [0, 64, 0, 64], [0, 0, 1, 400], [0, 0, 0, 1]], True),
+                    ([[0.3, -1.2, 0.5, 1.0], [0.9, 0.1, -0.4, 2.0], [0.2, 0.7, 1.1, -3.0], [0, 0, 0, 1]], False)):
+        idx = sb.add_rectangle(M, 0, flip); ref = sb.shapes[idx]
+        out = abi.B2Shape()
+        flat = (C.c_float * 16)(*[float(x) for row in M for x in row])
+        assert L.b2_host_shape_rectangle(flat, int(flip), 0, C.byref(out)) == 0
+        assert (out.type, out.bsdf, out.emitter, out.flip_normals) == (ref.type, ref.bsdf, ref.emitter, ref.flip_normals)
+        assert np.array_equal(np.array(out.to_world[:]), np.array(ref.to_world[:]))
+        # (the inverse is computed in double and rounded once on both sides, by different formulas: last-ulp agreement)
+        assert np.allclose(np.array(out.to_object[:]), np.array(ref.to_object[:]), rtol=3e-7, atol=1e-9), (M, flip)
