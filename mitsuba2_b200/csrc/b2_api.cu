@@ -147,6 +147,14 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
             if (em.type == B2_EMITTER_ENVMAP && (!em.envmap || em.env_width < 2 || em.env_height < 2)) return fail(B2_ERR_INVALID, "Distribution2D(): input array resolution must be >= 2!");
         }
     }
+    for (uint32_t b = 0; b < desc->n_bsdfs; ++b) {
+        const int32_t t = desc->bsdfs[b].type;
+        if (t < B2_BSDF_DIFFUSE || t > B2_BSDF_PLASTIC) return fail(B2_ERR_INVALID, "bsdf %u: unsupported type %d", b, t);
+        if (t == B2_BSDF_ROUGHCONDUCTOR && desc->bsdfs[b].distribution != B2_MF_BECKMANN && desc->bsdfs[b].distribution != B2_MF_GGX)
+            return fail(B2_ERR_INVALID, "bsdf %u: Specified an invalid distribution (must be \"beckmann\" or \"ggx\")", b);   // microfacet.h
+        if (t == B2_BSDF_ROUGHCONDUCTOR && !desc->bsdfs[b].sample_visible)
+            return fail(B2_ERR_INVALID, "bsdf %u: roughconductor with sample_visible = false is not supported", b);
+    }
     for (uint32_t m = 0; m < desc->n_meshes; ++m) {
         const B2Mesh &me = desc->meshes[m];
         if (me.bsdf < 0 || (uint32_t) me.bsdf >= desc->n_bsdfs) return fail(B2_ERR_INVALID, "mesh %u: bad bsdf index", m);

@@ -169,6 +169,11 @@ def test_scene_description_is_validated_like_the_reference():
     assert "shape 0: bad bsdf index" in str(_create_error(sb))
     sb = scenes.cbox(H, 16, 16); sb.add_sphere((0, 0, 0), -1.0)
     assert "sphere radius must be positive" in str(_create_error(sb))
+    # BSDF records
+    sb = scenes.cbox(H, 16, 16); sb.bsdfs[0].type = 42
+    assert "bsdf 0: unsupported type 42" in str(_create_error(sb))
+    sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughconductor(sample_visible=False)})
+    assert "sample_visible = false is not supported" in str(_create_error(sb))
     # film limits
     sb = scenes.cbox(H, 16, 16); sb.film.crop_size[0] = 0
     assert "film crop size" in str(_create_error(sb))
