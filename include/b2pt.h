@@ -62,7 +62,9 @@ enum {
     B2_BSDF_ROUGHCONDUCTOR = 2, /* RoughConductor     roughconductor.cpp:196-382              */
     B2_BSDF_NULL = 3,           /* reflectance-0 diffuse given to emitters without a BSDF     */
     B2_BSDF_CONDUCTOR = 4,      /* SmoothConductor    conductor.cpp:197-258                   */
-    B2_BSDF_PLASTIC = 5         /* SmoothPlastic      plastic.cpp:181-314                     */
+    B2_BSDF_PLASTIC = 5,        /* SmoothPlastic      plastic.cpp:181-314                     */
+    B2_BSDF_ROUGHDIELECTRIC = 6 /* RoughDielectric    roughdielectric.cpp:203-452 — ORACLE ONLY in round 1: restated and
+                                   pinned in oracle/b2o.c; b2_scene_create rejects it until the CUDA path has it */
 };
 enum { B2_MF_BECKMANN = 0, B2_MF_GGX = 1 };   /* MicrofacetType, microfacet.h:27-33          */
 

@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 B2_OK, B2_ERR_INVALID, B2_ERR_CUDA, B2_ERR_CANCELLED, B2_ERR_NO_DEVICE = range(5)
-BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL, BSDF_CONDUCTOR, BSDF_PLASTIC = range(6)
+BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL, BSDF_CONDUCTOR, BSDF_PLASTIC, BSDF_ROUGHDIELECTRIC = range(7)
 MF_BECKMANN, MF_GGX = 0, 1
 EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT, EMITTER_POINT = range(4)
 FILTER_RESOLUTION = 31
@@ -216,6 +216,17 @@ class SceneBuffers:
         b.alpha_u = alpha; b.alpha_v = alpha if alpha_v is None else alpha_v
         b.cond_eta[:] = eta; b.cond_k[:] = k
         b.specular_reflectance[:] = specular_reflectance; b.specular_transmittance[:] = (1, 1, 1)
+        self.bsdfs.append(b); return len(self.bsdfs) - 1
+
+    def add_roughdielectric(self, alpha=0.1, distribution="beckmann", int_ior=1.5046, ext_ior=1.000277,
+                            specular_reflectance=(1, 1, 1), specular_transmittance=(1, 1, 1)):
+        """RoughDielectric (src/bsdfs/roughdielectric.cpp). Oracle only in round 1: b2_scene_create rejects it."""
+        b = B2Bsdf(); b.type = BSDF_ROUGHDIELECTRIC
+        b.distribution = MF_GGX if distribution == "ggx" else MF_BECKMANN
+        b.sample_visible = 1
+        b.alpha_u = b.alpha_v = alpha
+        b.eta = float(np.float32(int_ior) / np.float32(ext_ior))     # roughdielectric.cpp:171
+        b.specular_reflectance[:] = specular_reflectance; b.specular_transmittance[:] = specular_transmittance
         self.bsdfs.append(b); return len(self.bsdfs) - 1
 
     def add_conductor(self, eta=(0, 0, 0), k=(1, 1, 1), specular_reflectance=(1, 1, 1)):

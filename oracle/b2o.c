@@ -1001,6 +1001,25 @@ static v3 bsdf_eval(const B2Bsdf *b, const osi *si, v3 wo) {
                              result * b->specular_reflectance[2]);
             return v3_mul(F, res);
         }
+        case B2_BSDF_ROUGHDIELECTRIC: {                                    /* roughdielectric.cpp:312-384 */
+            if (cti == 0.f) return zero;
+            int reflect = cti * cto > 0.f;
+            float eta = cti > 0.f ? b->eta : b2o_rcp(b->eta), inv_eta = cti > 0.f ? b2o_rcp(b->eta) : b->eta;   /* m_inv_eta = 1 / m_eta (:172) */
+            v3 m = v3_normalize(v3_add(si->wi, v3_scale(wo, reflect ? 1.f : eta)));
+            if (m.z < 0.f || (m.z == 0.f && signbit(m.z))) m = v3_neg(m);                                        /* mulsign(m, cos_theta(m)) */
+            omf d = mf_make(b);
+            float D = mf_eval(&d, m);
+            float F = fresnel_r(v3_dot(si->wi, m), b->eta);
+            float G = mf_smith_g1(&d, si->wi, m) * mf_smith_g1(&d, wo, m);
+            if (reflect) {
+                float value = F * D * G / (4.f * fabsf(cti));
+                return v3_make(value * b->specular_reflectance[0], value * b->specular_reflectance[1], value * b->specular_reflectance[2]);
+            }
+            float scale = b2o_sqr(inv_eta);
+            float dwm = v3_dot(si->wi, m), dom = v3_dot(wo, m);
+            float value = fabsf((scale * (1.f - F) * D * G * eta * eta * dwm * dom) / (cti * b2o_sqr(dwm + eta * dom)));
+            return v3_make(value * b->specular_transmittance[0], value * b->specular_transmittance[1], value * b->specular_transmittance[2]);
+        }
         case B2_BSDF_PLASTIC: {                                            /* plastic.cpp:242-266 */
             if (!(cti > 0.f && cto > 0.f)) return zero;
             float f_i = fresnel_r(cti, b->eta), f_o = fresnel_r(cto, b->eta);
@@ -1021,6 +1040,22 @@ static float bsdf_pdf(const B2Bsdf *b, const osi *si, v3 wo) {
             if (!(cti > 0.f && cto > 0.f && v3_dot(si->wi, m) > 0.f && v3_dot(wo, m) > 0.f)) return 0.f;
             omf d = mf_make(b);
             return mf_eval(&d, m) * mf_smith_g1(&d, si->wi, m) / (4.f * cti);
+        }
+        case B2_BSDF_ROUGHDIELECTRIC: {                                    /* roughdielectric.cpp:386-452 */
+            if (cti == 0.f) return 0.f;
+            int reflect = cti * cto > 0.f;
+            float eta = cti > 0.f ? b->eta : b2o_rcp(b->eta);
+            v3 m = v3_normalize(v3_add(si->wi, v3_scale(wo, reflect ? 1.f : eta)));
+            if (m.z < 0.f || (m.z == 0.f && signbit(m.z))) m = v3_neg(m);
+            if (!(v3_dot(si->wi, m) * cti > 0.f && v3_dot(wo, m) * cto > 0.f)) return 0.f;
+            float dwh_dwo = reflect ? b2o_rcp(4.f * v3_dot(wo, m))
+                                    : (eta * eta * v3_dot(wo, m)) / b2o_sqr(v3_dot(si->wi, m) + eta * v3_dot(wo, m));
+            omf d = mf_make(b);
+            v3 wi_s = cti < 0.f ? v3_neg(si->wi) : si->wi;                                                        /* mulsign(wi, cos_theta(wi)) */
+            float prob = mf_eval(&d, m) * mf_smith_g1(&d, wi_s, m) * fabsf(v3_dot(wi_s, m)) / wi_s.z;            /* distr.pdf, microfacet.h:214-223 */
+            float F = fresnel_r(v3_dot(si->wi, m), b->eta);
+            prob *= reflect ? F : 1.f - F;
+            return prob * fabsf(dwh_dwo);
         }
         case B2_BSDF_PLASTIC: {                                            /* plastic.cpp:268-293 */
             if (!(cti > 0.f && cto > 0.f)) return 0.f;
@@ -1082,6 +1117,36 @@ static v3 bsdf_sample(const B2Bsdf *b, const osi *si, float sample1, float s2x, 
             v3 wv = v3_make(weight * b->specular_reflectance[0], weight * b->specular_reflectance[1],
                             weight * b->specular_reflectance[2]);
             return active ? v3_mul(F, wv) : zero;
+        }
+        case B2_BSDF_ROUGHDIELECTRIC: {                                    /* roughdielectric.cpp:203-310 */
+            int active = cti != 0.f;
+            omf d = mf_make(b);
+            v3 wi_s = cti < 0.f ? v3_neg(si->wi) : si->wi;
+            float pdf; v3 m = mf_sample(&d, wi_s, s2x, s2y, &pdf);
+            active = active && pdf != 0.f;
+            float F, cos_theta_t, eta_it, eta_ti;
+            fresnel(v3_dot(si->wi, m), b->eta, &F, &cos_theta_t, &eta_it, &eta_ti);
+            int selected_r = sample1 <= F && active;
+            v3 weight = v3_make(1.f, 1.f, 1.f);
+            pdf *= selected_r ? F : 1.f - F;
+            bs->eta = selected_r ? 1.f : eta_it; bs->delta = 0;
+            float dwh_dwo = 0.f;
+            float dwm = v3_dot(si->wi, m);
+            if (selected_r) {
+                float s = 2.f * dwm;                                       /* reflect(wi, m) = fmsub(m, 2 dot(wi, m), wi) */
+                bs->wo = v3_make(b2o_fma(m.x, s, -si->wi.x), b2o_fma(m.y, s, -si->wi.y), b2o_fma(m.z, s, -si->wi.z));
+                weight = v3_mul(weight, v3_make(b->specular_reflectance[0], b->specular_reflectance[1], b->specular_reflectance[2]));
+                dwh_dwo = b2o_rcp(4.f * v3_dot(bs->wo, m));
+            } else if (active) {
+                float s = b2o_fma(dwm, eta_ti, cos_theta_t);               /* refract(wi, m, cos_theta_t, eta_ti), fresnel.h:310-313 */
+                bs->wo = v3_make(b2o_fma(m.x, s, -(si->wi.x * eta_ti)), b2o_fma(m.y, s, -(si->wi.y * eta_ti)), b2o_fma(m.z, s, -(si->wi.z * eta_ti)));
+                float fct = b2o_sqr(eta_ti);
+                weight = v3_mul(weight, v3_make(fct * b->specular_transmittance[0], fct * b->specular_transmittance[1], fct * b->specular_transmittance[2]));
+                dwh_dwo = (b2o_sqr(bs->eta) * v3_dot(bs->wo, m)) / b2o_sqr(dwm + bs->eta * v3_dot(bs->wo, m));
+            }
+            weight = v3_scale(weight, mf_smith_g1(&d, bs->wo, m));
+            bs->pdf = pdf * fabsf(dwh_dwo);
+            return active ? weight : zero;
         }
         case B2_BSDF_CONDUCTOR: {                                          /* conductor.cpp:197-240 */
             if (!(cti > 0.f)) return zero;

@@ -448,6 +448,10 @@ PLASTIC = '<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.1, 0.27
 PLASTIC_SPEC = ('<bsdf type="plastic"><rgb name="diffuse_reflectance" value="0.7, 0.6, 0.5"/>'
                 '<rgb name="specular_reflectance" value="0.8, 0.9, 1.0"/><float name="int_ior" value="1.49"/>'
                 '<float name="ext_ior" value="1.000277"/></bsdf>')
+ROUGH_GLASS_GGX = ('<bsdf type="roughdielectric"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/>'
+                   '<float name="int_ior" value="1.5"/><float name="ext_ior" value="1.0"/></bsdf>')
+ROUGH_GLASS_BECK = ('<bsdf type="roughdielectric"><float name="alpha" value="0.25"/><float name="int_ior" value="1.33"/>'
+                    '<float name="ext_ior" value="1.0"/><rgb name="specular_transmittance" value="0.9, 0.95, 1.0"/></bsdf>')
 TWOSIDED_1 = '<bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.45, 0.3, 0.9"/></bsdf></bsdf>'
 TWOSIDED_2 = ('<bsdf type="twosided"><bsdf type="diffuse"><rgb name="reflectance" value="0.1, 0.6, 0.1"/></bsdf>'
               '<bsdf type="roughconductor"><float name="alpha" value="0.2"/></bsdf></bsdf>')
@@ -510,6 +514,9 @@ GOLDEN = {
     "cbox_64_spp16_constant_area": dict(width=64, height=64, spp=16, envmap="constant_area"),
     "cbox_64_spp16_point": dict(width=64, height=64, spp=16, no_patch=True, point_light="only"),
     "cbox_64_spp16_point_area": dict(width=64, height=64, spp=16, no_patch=True, point_light="with_area"),
+    # rough dielectric (ORACLE ONLY in round 1; the CUDA path rejects it): boxes lifted off the floor like the smooth dielectric case
+    "cbox_64_spp16_roughglass_ggx": dict(width=64, height=64, spp=16, no_patch=True, lift=10.0, materials={"box": ROUGH_GLASS_GGX}),
+    "cbox_64_spp16_roughglass_beckmann": dict(width=64, height=64, spp=16, no_patch=True, lift=10.0, materials={"box": ROUGH_GLASS_BECK}),
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }

@@ -36,6 +36,10 @@ def _material(xml):
         return lambda sb: sb.add_diffuse(_rgb(xml, "reflectance", (0.5, 0.5, 0.5)))
     if 'type="dielectric"' in xml:
         return lambda sb: sb.add_dielectric(_float(xml, "int_ior", 1.5046), _float(xml, "ext_ior", 1.000277))
+    if 'type="roughdielectric"' in xml:
+        return lambda sb: sb.add_roughdielectric(alpha=_float(xml, "alpha", 0.1), distribution="ggx" if 'value="ggx"' in xml else "beckmann",
+                                                 int_ior=_float(xml, "int_ior", 1.5046), ext_ior=_float(xml, "ext_ior", 1.000277),
+                                                 specular_transmittance=_rgb(xml, "specular_transmittance", (1, 1, 1)))
     if 'type="roughconductor"' in xml:
         return lambda sb: sb.add_roughconductor(alpha=_float(xml, "alpha", 0.1), distribution="ggx" if 'value="ggx"' in xml else "beckmann")
     if 'type="conductor"' in xml:

@@ -174,6 +174,9 @@ def test_scene_description_is_validated_like_the_reference():
     assert "bsdf 0: unsupported type 42" in str(_create_error(sb))
     sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughconductor(sample_visible=False)})
     assert "sample_visible = false is not supported" in str(_create_error(sb))
+    # rough dielectric: restated and pinned in the oracle only (round 1) -- the product must say so, not render black
+    sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughdielectric(0.1, "ggx", 1.5, 1.0)})
+    assert "unsupported type 6" in str(_create_error(sb))
     # film limits
     sb = scenes.cbox(H, 16, 16); sb.film.crop_size[0] = 0
     assert "film crop size" in str(_create_error(sb))
