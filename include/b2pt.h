@@ -110,7 +110,9 @@ typedef struct B2Texture {
 } B2Texture;
 
 /* ---- emitters (src/emitters/{area,envmap,constant,point}.cpp) --------------------------- */
-enum { B2_EMITTER_AREA = 0, B2_EMITTER_ENVMAP = 1, B2_EMITTER_CONSTANT = 2, B2_EMITTER_POINT = 3 /* src/emitters/point.cpp */ };
+enum { B2_EMITTER_AREA = 0, B2_EMITTER_ENVMAP = 1, B2_EMITTER_CONSTANT = 2, B2_EMITTER_POINT = 3 /* src/emitters/point.cpp */,
+       /* ORACLE ONLY in round 1 (restated and pinned in oracle/b2o.c, rejected by b2_scene_create): */
+       B2_EMITTER_SPOT = 4 /* src/emitters/spot.cpp, untextured */, B2_EMITTER_DIRECTIONAL = 5 /* src/emitters/directional.cpp */ };
 
 typedef struct B2Emitter {
     int32_t type;               /* B2_EMITTER_*                                                */
@@ -123,6 +125,7 @@ typedef struct B2Emitter {
     float env_to_object[16];    /* its inverse, as the reference's Transform stores it         */
     int32_t shape;              /* area: 0 = attached to `mesh`; k > 0 = attached to B2SceneDesc.shapes[k-1] */
     int32_t _pad;
+    float cutoff_angle, beam_width;   /* spot: radians, as SpotLight stores them (spot.cpp:88-92)       */
 } B2Emitter;
 
 /* ---- meshes (include/mitsuba/render/mesh.h:344-361) ------------------------------------- */

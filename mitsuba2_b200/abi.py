@@ -11,7 +11,7 @@ import numpy as np
 B2_OK, B2_ERR_INVALID, B2_ERR_CUDA, B2_ERR_CANCELLED, B2_ERR_NO_DEVICE = range(5)
 BSDF_DIFFUSE, BSDF_DIELECTRIC, BSDF_ROUGHCONDUCTOR, BSDF_NULL, BSDF_CONDUCTOR, BSDF_PLASTIC, BSDF_ROUGHDIELECTRIC = range(7)
 MF_BECKMANN, MF_GGX = 0, 1
-EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT, EMITTER_POINT = range(4)
+EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT, EMITTER_POINT, EMITTER_SPOT, EMITTER_DIRECTIONAL = range(6)
 FILTER_RESOLUTION = 31
 FLAG_STAGE_TIMING = 1
 FLAG_SINGLE_SET = 2
@@ -51,6 +51,7 @@ class B2Emitter(C.Structure):
         ("env_width", C.c_int32), ("env_height", C.c_int32),
         ("env_to_world", C.c_float * 16), ("env_to_object", C.c_float * 16),
         ("shape", C.c_int32), ("_pad", C.c_int32),
+        ("cutoff_angle", C.c_float), ("beam_width", C.c_float),
     ]
 
 
@@ -292,6 +293,28 @@ class SceneBuffers:
         e.env_to_object[:] = [float(x) for x in inv.reshape(-1)]
         self.emitters.append(e)
         return len(self.emitters) - 1
+
+    def add_spot_light(self, to_world, intensity=(1.0, 1.0, 1.0), cutoff_angle=20.0, beam_width=None):
+        """SpotLight (src/emitters/spot.cpp), untextured; angles in degrees like the plugin. Oracle only in round 1."""
+        e = B2Emitter(); e.type = EMITTER_SPOT; e.mesh = -1; e.scale = 1.0
+        e.radiance[:] = intensity
+        m = np.asarray(to_world, np.float32).reshape(4, 4)
+        e.env_to_world[:] = [float(x) for x in m.reshape(-1)]
+        e.env_to_object[:] = [float(x) for x in np.linalg.inv(m.astype(np.float64)).astype(np.float32).reshape(-1)]
+        f = np.float32
+        bw = f(cutoff_angle) * f(3.0) / f(4.0) if beam_width is None else f(beam_width)      # spot.cpp:88-92
+        d2r = f(np.pi / 180.0)
+        e.cutoff_angle = float(f(cutoff_angle) * d2r); e.beam_width = float(f(bw) * d2r)
+        self.emitters.append(e); return len(self.emitters) - 1
+
+    def add_directional_light(self, to_world, irradiance=(1.0, 1.0, 1.0)):
+        """DirectionalEmitter (src/emitters/directional.cpp): emits along to_world * (0, 0, 1). Oracle only in round 1."""
+        e = B2Emitter(); e.type = EMITTER_DIRECTIONAL; e.mesh = -1; e.scale = 1.0
+        e.radiance[:] = irradiance
+        m = np.asarray(to_world, np.float32).reshape(4, 4)
+        e.env_to_world[:] = [float(x) for x in m.reshape(-1)]
+        e.env_to_object[:] = [float(x) for x in np.linalg.inv(m.astype(np.float64)).astype(np.float32).reshape(-1)]
+        self.emitters.append(e); return len(self.emitters) - 1
 
     def add_envmap(self, rgb, scale=1.0, to_world=None):
         """EnvironmentMapEmitter (src/emitters/envmap.cpp): rgb = float32 [H, W, 3] lat-long image."""

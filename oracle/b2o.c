@@ -418,7 +418,9 @@ static oscene *oscene_create(const B2SceneDesc *d) {
        EnvironmentMapEmitter::set_scene (envmap.cpp:127-131) takes its bounding sphere */
     s->env = -1;
     for (uint32_t e = 0; e < d->n_emitters; ++e) if (d->emitters[e].type == B2_EMITTER_ENVMAP || d->emitters[e].type == B2_EMITTER_CONSTANT) s->env = (int) e;   /* is_environment() */
-    if (s->env >= 0) {
+    int need_bsphere = s->env >= 0;                 /* also DirectionalEmitter::set_scene, directional.cpp:64-69 */
+    for (uint32_t e = 0; e < d->n_emitters; ++e) if (d->emitters[e].type == B2_EMITTER_DIRECTIONAL) need_bsphere = 1;
+    if (need_bsphere) {
         float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
         for (uint32_t m = 0; m < n_top; ++m)
             for (uint32_t v = 0; v < d->meshes[m].n_vertices; ++v)
@@ -455,7 +457,7 @@ static oscene *oscene_create(const B2SceneDesc *d) {
         v3 dmax = v3_sub(c, v3_make(hi[0], hi[1], hi[2]));
         float radius = sqrtf(v3_dot(dmax, dmax));                      /* bbox.h:329-332 */
         s->env_radius = b2o_max(B2O_RAY_EPS, radius * (1.f + B2O_RAY_EPS));
-        if (d->emitters[s->env].type == B2_EMITTER_ENVMAP) env_build(s, &d->emitters[s->env]);
+        if (s->env >= 0 && d->emitters[s->env].type == B2_EMITTER_ENVMAP) env_build(s, &d->emitters[s->env]);
     }
     return s;
 }
@@ -1320,6 +1322,36 @@ static v3 env_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx,
 static float env_pdf_direction(const oscene *s, v3 d_world);
 static v3 emitter_sample_direction(const oscene *s, int emitter, v3 ref_p, float sx, float sy, ods *ds) {
     ds->delta = 0;
+    if (s->desc->emitters[emitter].type == B2_EMITTER_SPOT) {                  /* SpotLight::sample_direction + falloff_curve, spot.cpp:97-160 */
+        const B2Emitter *em = &s->desc->emitters[emitter];
+        ds->p = v3_make(em->env_to_world[3], em->env_to_world[7], em->env_to_world[11]);
+        ds->n = v3_make(0.f, 0.f, 0.f);
+        ds->pdf = 1.f; ds->delta = 1; ds->emitter = emitter;
+        ds->d = v3_sub(ds->p, ref_p);
+        ds->dist = sqrtf(v3_dot(ds->d, ds->d));
+        float inv_dist = b2o_rcp(ds->dist);
+        ds->d = v3_scale(ds->d, inv_dist);
+        v3 local_dir = v3_normalize(xf_vector(em->env_to_object, v3_neg(ds->d)));
+        float cos_theta = local_dir.z;
+        float cos_cutoff = cosf(em->cutoff_angle), cos_beam = cosf(em->beam_width);         /* host values, spot.cpp:93-94 */
+        float inv_transition = 1.0f / (em->cutoff_angle - em->beam_width);
+        float f = cos_theta >= cos_beam ? 1.f : (em->cutoff_angle - b2o_safe_acos(cos_theta)) * inv_transition;
+        if (cos_theta <= cos_cutoff) f = 0.f;
+        float w = inv_dist * inv_dist;
+        v3 res = v3_make(em->radiance[0], em->radiance[1], em->radiance[2]);
+        if (!(cos_theta >= cos_beam)) res = v3_scale(res, f);
+        if (cos_theta <= cos_cutoff) res = v3_make(0.f, 0.f, 0.f);
+        return v3_scale(res, w);
+    }
+    if (s->desc->emitters[emitter].type == B2_EMITTER_DIRECTIONAL) {           /* DirectionalEmitter::sample_direction, directional.cpp:107-134 */
+        const B2Emitter *em = &s->desc->emitters[emitter];
+        v3 d = xf_vector(em->env_to_world, v3_make(0.f, 0.f, 1.f));
+        float dist = 2.f * s->env_radius;
+        ds->p = v3_sub(ref_p, v3_scale(d, dist));
+        ds->n = d; ds->pdf = 1.f; ds->delta = 1; ds->emitter = emitter;
+        ds->d = v3_neg(d); ds->dist = dist;
+        return v3_make(em->radiance[0], em->radiance[1], em->radiance[2]);
+    }
     if (s->desc->emitters[emitter].type == B2_EMITTER_POINT) {                 /* PointLight::sample_direction, point.cpp:86-113 */
         const B2Emitter *em = &s->desc->emitters[emitter];
         ds->p = v3_make(em->env_to_world[3], em->env_to_world[7], em->env_to_world[11]);

@@ -206,6 +206,11 @@ ENV_DROPPED = {
     "constant_area": ("cbox_ceiling.obj", "cbox_greenwall.obj"),
 }
 CONSTANT_RADIANCE = (0.8, 1.1, 1.6)
+# spot light looking down from under the ceiling (exact-in-fp32 to_world: local z -> world -y); directional light along a
+# tilted axis (ORACLE ONLY in round 1)
+SPOT_LIGHT = dict(to_world=[[1, 0, 0, 278], [0, 0, -1, 540], [0, 1, 0, 279.5], [0, 0, 0, 1]], intensity=(900000.0, 700000.0, 500000.0),
+                  cutoff_angle=35.0, beam_width=20.0)
+DIRECTIONAL_LIGHT = dict(to_world=[[0.8, 0, 0.6, 0], [0, 1, 0, 0], [-0.6, 0, 0.8, 0], [0, 0, 0, 1]], irradiance=(3.0, 2.5, 2.0))
 POINT_LIGHT = dict(position=(278.0, 500.0, 279.5), intensity=(800000.0, 600000.0, 400000.0))
 
 
@@ -349,7 +354,7 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             bs.append(f'<bsdf type="diffuse" id="{k}"><rgb name="reflectance" value="{v[0]}, {v[1]}, {v[2]}"/></bsdf>')
     shapes = []
     for fn, bsdf, tr in CBOX_SHAPES:
-        if point_light == "only" and fn == "cbox_luminaire.obj":
+        if point_light in ("only", "spot") and fn == "cbox_luminaire.obj":
             continue                       # lit by the point light alone
         if analytic and fn in ("cbox_luminaire.obj", "cbox_smallbox.obj"):
             continue                       # replaced by analytic shapes (appended below)
@@ -382,7 +387,17 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
             write_uv_obj(path, dst)
             path = dst
         shapes.append(f'<shape type="obj"><string name="filename" value="{path}"/>{t}<ref id="{bsdf}"/>{em}</shape>')
-    if point_light:                    # PointLight (src/emitters/point.cpp), after the shapes
+    mat = lambda M: " ".join(repr(float(x)) for row in M for x in row)
+    if point_light == "spot":
+        sl = SPOT_LIGHT
+        shapes.append(f'<emitter type="spot"><transform name="to_world"><matrix value="{mat(sl["to_world"])}"/></transform>'
+                      f'<rgb name="intensity" value="{sl["intensity"][0]}, {sl["intensity"][1]}, {sl["intensity"][2]}"/>'
+                      f'<float name="cutoff_angle" value="{sl["cutoff_angle"]}"/><float name="beam_width" value="{sl["beam_width"]}"/></emitter>')
+    elif point_light == "directional":
+        dl = DIRECTIONAL_LIGHT
+        shapes.append(f'<emitter type="directional"><transform name="to_world"><matrix value="{mat(dl["to_world"])}"/></transform>'
+                      f'<rgb name="irradiance" value="{dl["irradiance"][0]}, {dl["irradiance"][1]}, {dl["irradiance"][2]}"/></emitter>')
+    elif point_light:                  # PointLight (src/emitters/point.cpp), after the shapes
         p, i = POINT_LIGHT["position"], POINT_LIGHT["intensity"]
         shapes.append(f'<emitter type="point"><point name="position" x="{p[0]}" y="{p[1]}" z="{p[2]}"/>'
                       f'<rgb name="intensity" value="{i[0]}, {i[1]}, {i[2]}"/></emitter>')
@@ -517,6 +532,8 @@ GOLDEN = {
     # rough dielectric (ORACLE ONLY in round 1; the CUDA path rejects it): boxes lifted off the floor like the smooth dielectric case
     "cbox_64_spp16_roughglass_ggx": dict(width=64, height=64, spp=16, no_patch=True, lift=10.0, materials={"box": ROUGH_GLASS_GGX}),
     "cbox_64_spp16_roughglass_beckmann": dict(width=64, height=64, spp=16, no_patch=True, lift=10.0, materials={"box": ROUGH_GLASS_BECK}),
+    "cbox_64_spp16_spot": dict(width=64, height=64, spp=16, no_patch=True, point_light="spot"),
+    "cbox_64_spp16_directional": dict(width=64, height=64, spp=16, envmap="constant_area", point_light="directional"),   # open box: + constant + area
     "cbox_64_spp16_textures": dict(width=64, height=64, spp=16, no_patch=True, textures=True),
     "cbox_64_spp16_plastic": dict(width=64, height=64, spp=16, no_patch=True, materials={"box": PLASTIC, "white": PLASTIC_SPEC, "red": PLASTIC_NONLINEAR}),
 }
@@ -597,7 +614,7 @@ def main():
             extra.update(env_rgb=env_image(), env_to_world=np.array(ENV_TO_WORLD, np.float32), env_scale=np.float32(1.5),
                          env_dropped=np.array([CBOX_SHAPES.index(next(s for s in CBOX_SHAPES if s[0] == fn)) for fn in ENV_DROPPED[kw["envmap"]]]))
         if kw.get("point_light"):
-            extra.update(point_light=np.array(repr(POINT_LIGHT)))
+            extra.update(point_light=np.array(repr(dict(spot=SPOT_LIGHT, directional=DIRECTIONAL_LIGHT).get(kw["point_light"], POINT_LIGHT))))
         if kw.get("analytic"):
             extra.update(shapes_spec=np.array(repr(SHAPES_SPEC)))
             if kw["analytic"] == "textured":

@@ -90,7 +90,7 @@ def load(name, host):
         sb = scenes.veach_mis(host, kw["width"], kw["height"])
         return sb, abi.render_params(max_depth=6, rr_depth=5, spp=kw["spp"], block_size=32), z["rgb"]
     env = None; drop = (0, 6) if kw.get("analytic") else ()      # analytic: luminaire + small box replaced by shapes
-    if kw.get("point_light") == "only":
+    if kw.get("point_light") in ("only", "spot"):
         drop = (0,)
     const_env = None
     if str(kw.get("envmap", "")).startswith("constant"):
@@ -103,8 +103,12 @@ def load(name, host):
                      texcoords={i: z[f"uv_m{i}"] for i in range(8)} if kw.get("textures") else None,
                      meshes_npz=nopatch_meshes() if kw.get("no_patch") else None, lift=kw.get("lift", 0.0),
                      instances=kw.get("instances"), crop=kw.get("crop"))
-    if kw.get("point_light"):
-        pl = ast.literal_eval(str(z["point_light"]))
+    pl = ast.literal_eval(str(z["point_light"])) if kw.get("point_light") else None
+    if kw.get("point_light") == "spot":
+        sb.add_spot_light(pl["to_world"], pl["intensity"], pl["cutoff_angle"], pl["beam_width"])
+    elif kw.get("point_light") == "directional":
+        sb.add_directional_light(pl["to_world"], pl["irradiance"])      # before the constant emitter, like the XML
+    elif kw.get("point_light"):
         sb.add_point_light(pl["position"], pl["intensity"])
     if const_env:                        # after the shapes, like the XML
         sb.add_constant_emitter(const_env)

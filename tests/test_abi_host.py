@@ -177,6 +177,11 @@ def test_scene_description_is_validated_like_the_reference():
     # rough dielectric: restated and pinned in the oracle only (round 1) -- the product must say so, not render black
     sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughdielectric(0.1, "ggx", 1.5, 1.0)})
     assert "unsupported type 6" in str(_create_error(sb))
+    # spot / directional emitters: oracle only in round 1
+    sb = scenes.cbox(H, 16, 16); sb.add_spot_light(np.eye(4), (1, 1, 1))
+    assert "only area, envmap, constant and point emitters are supported" in str(_create_error(sb))
+    sb = scenes.cbox(H, 16, 16); sb.add_directional_light(np.eye(4), (1, 1, 1))
+    assert "only area, envmap, constant and point emitters are supported" in str(_create_error(sb))
     # film limits
     sb = scenes.cbox(H, 16, 16); sb.film.crop_size[0] = 0
     assert "film crop size" in str(_create_error(sb))
