@@ -248,7 +248,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     }
     std::vector<DInstance> dinst(desc->n_instances);
     std::vector<uint32_t> inst_order;
-    uint32_t tlas_root = 0;
+    uint32_t tlas_root = 0, tlas_levels = 0;
     if (desc->n_instances) {
         std::vector<B2BvhBox> ib(desc->n_instances);
         for (uint32_t i = 0; i < desc->n_instances; ++i) {
@@ -274,9 +274,17 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         B2Bvh4 t; b2_build_bvh4_boxes(ib, 1, t);
         tlas_root = b2_bvh4_append(bvh.nodes, t, 0);
         inst_order = t.order;
-        bvh.depth += t.depth;
+        bvh.depth += t.depth; tlas_levels = t.depth;
     }
     bvh.n_nodes = (uint32_t) (bvh.nodes.size() / 32);
+    {   // the traversal stacks are fixed-size local arrays (Trav: 40 entries, TLAS walk: 32, k_trace_inst: 64): a BVH4 level
+        // pushes at most 3 entries, so refuse trees that could overflow them instead of corrupting local memory
+        const uint32_t tlas_depth = desc->n_instances ? tlas_levels : 0, blas_depth = bvh.depth - tlas_depth;
+        if (3 * blas_depth + 1 > 40 || (desc->n_instances && (3 * tlas_depth + 1 > 32 || 3 * (tlas_depth + blas_depth) + 3 > 64))) {
+            delete s;
+            return fail(B2_ERR_INVALID, "BVH too deep for the traversal stack (%u + %u levels)", blas_depth, tlas_depth);
+        }
+    }
 
     std::vector<float4> tri_pos(3 * (size_t) n_slots), tri_nrm(3 * (size_t) n_slots), tri_isect(3 * (size_t) n_slots);
     std::vector<uint32_t> prim_to_slot(n_slots);
