@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--workload", default="cbox", choices=["cbox", "veach", "grid", "matball"],
                     help="cbox = BASELINE configs[1] (the bench line); veach / grid = configs[3] / configs[4] (extra measurements)")
     ap.add_argument("--single-set", action="store_true", help="one lane set on one stream (A/B of the two-stream overlap)")
+    ap.add_argument("--bvh-counters", action="store_true", help="cbox: also run the BVH-counting step (always on for the other workloads)")
+    ap.add_argument("--parity", action="store_true", help="cbox: also render the configuration with the reference CLI and report rel-L2")
     return ap.parse_args()
 
 
@@ -109,14 +111,23 @@ def run_reference_cli(res, spp, spp_pass, max_depth, threads):
         return t, res * res * spp
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the committed `ncu --set full` captures
-# (cold caches: ncu flushes between replays). Launches of the default two-lane-set configuration.
-NCU_TRAFFIC = {
-    ("cbox", "k_shade"): {"bytes": 51105280 + 7729152, "note": "profiles/r01_ncu_full_v3.md: k_shade<0>, one single-set launch of 454656 lanes (the width the "
-                          "stage timers run), final round-1 build"},
-    ("cbox", "k_trace"): {"bytes": 32300800 + 256, "note": "profiles/r01_ncu_full_v3.md: k_trace<0,0>, one single-set launch of 454656 lanes + its shadow queue"},
-    ("grid", "k_trace"): {"bytes": 11925760 + 118272000, "note": "profiles/r01_ncu_grid.md: k_trace<1,0> (before k_trace_inst), 1024x1024 sample"},
-}
+def ncu_traffic(workload, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of `kernel`, from the committed
+    `ncu --set full` capture of the final build: profiles/r02_ncu_<workload>.csv with rows
+    kernel,duration_us,dram_read_bytes,dram_write_bytes,threads_per_warp_instr,issue_active_pct (written by
+    scripts/ncu_summary.py from the .ncu-rep). None when no capture is committed for this workload."""
+    path = os.path.join(ROOT, "profiles", f"r02_ncu_{workload}.csv")
+    try:
+        rows = [ln.strip().split(",") for ln in open(path) if ln.strip() and not ln.startswith("#")]
+        hdr = rows[0]
+        for r in rows[1:]:
+            d = dict(zip(hdr, r))
+            if d["kernel"].startswith(kernel):
+                return {"bytes": float(d["dram_read_bytes"]) + float(d["dram_write_bytes"]), "duration_us": float(d["duration_us"]),
+                        "source": os.path.relpath(path, ROOT)}
+    except Exception:
+        pass
+    return None
 
 
 def run_oracle_port(res, spp, spp_pass, max_depth, threads):
@@ -129,9 +140,32 @@ def run_oracle_port(res, spp, spp_pass, max_depth, threads):
     return time.perf_counter() - t0, res * res * spp
 
 
+def usable_cores():
+    """Host threads this process may actually use: the affinity mask, capped by the cgroup CPU quota (a leased box
+    reports every core of the node in os.cpu_count() even when the container may only burn a few of them)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0]); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if q > 0:
+                    n = min(n, max(1, int(q / per + 0.5)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
+
+
 def cpu_sample(a, spp):
     """One bounded CPU sample of the workload: same scene / resolution / depth, fewer spp."""
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     spp_pass = min(a.spp_per_pass or spp, spp)
     r = run_reference_cli(a.res, spp, spp_pass, a.max_depth, cores)
     kind = "reference"
@@ -148,7 +182,8 @@ def main_reference(a, rank):
     if rank != 0:
         return
     spp = 16                      # bounded sample per step (~4 s of host time on 128 threads)
-    for _ in range(min(a.warmup, 1)):
+    warm = min(a.warmup, 1)       # one warm-up sample pages the binary and the scene in; more would only burn minutes
+    for _ in range(warm):
         cpu_sample(a, spp)
     vals = []
     t0 = time.perf_counter()
@@ -159,7 +194,7 @@ def main_reference(a, rank):
     cb = dict(vals[-1]); cb["value"] = v
     emit(json.dumps({
         "impl": "reference", "metric": "Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+        "steps": a.steps, "warmup": warm, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"cbox {a.res}x{a.res}, {a.spp} spp (timed on a {spp}-spp sample per step), max_depth {a.max_depth}, "
                                "diffuse + area emitter, box filter, independent sampler seed 0, block_size 32"},
@@ -174,7 +209,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index = index; self.rows = []; self.p = None
+        self.index = index; self.rows = []; self.p = None; self.t0 = None; self.t1 = None
+
+    def mark(self, begin):
+        """bracket the timed region: samples inside it are the ones reported (all samples under load if it was too short)"""
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def start(self):
         try:
@@ -186,7 +228,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append([x.strip() for x in line.split(",")] + [time.time()])
 
     def stop(self):
         if not self.p:
@@ -196,16 +238,22 @@ class ClockSampler:
             self.p.wait(timeout=2)
         except Exception:
             self.p.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for r in self.rows if len(r) >= 10 and r[1].replace(".", "").isdigit()]
+        timed = [r for r in rows if self.t0 is not None and self.t1 is not None and self.t0 <= r[-1] <= self.t1 + 0.05]
+        window = "timed region"
+        if len(timed) < 3:     # a very short timed region: every sample since the warm-up started ran under the same load
+            timed = rows; window = "warm-up + timed region"
+        sm = [float(r[1]) for r in timed]
+        mx = [float(r[2]) for r in timed if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        self.window = window
+        for r in timed:
             if len(r) >= 9:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower() == "active":
                         reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 from mitsuba2_b200.dist import CudaArray  # noqa: E402,F401
@@ -229,17 +277,25 @@ def main_b2pt(a, rank, world, local_rank):
         sb = scenes.matball(api.Host(), a.res, a.res * 9 // 16, rfilter=a.rfilter or "gaussian")
     else:
         sb = scenes.cbox(api.Host(), a.res, a.res)
+    t0 = time.perf_counter()
     scene = api.Scene(sb)
+    t_scene = time.perf_counter() - t0
     integ = api.PathIntegrator(max_depth=a.max_depth, rr_depth=5, samples_per_pass=a.spp_per_pass, block_size=32)
     H, W = sb.film.crop_size[1], sb.film.crop_size[0]
     n_samples = H * W * a.spp
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device="cuda")     # > 126 MB L2
     host_film = torch.empty((H, W, 5), dtype=torch.float32).pin_memory().numpy()
+    base_flags = abi.FLAG_SINGLE_SET if a.single_set else 0
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def reduce_film(ptr, n, stream):
+        """the single collective of the job: XYZAW film of every rank -> rank 0 (NCCL, on the device)"""
+        film = torch.as_tensor(CudaArray(ptr, (n,)), device="cuda")
+        dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)
 
     def step_device(flags=0):
         """-> device ms of this rank's render (+ film reduce), stats"""
@@ -247,39 +303,38 @@ def main_b2pt(a, rank, world, local_rank):
         torch.cuda.synchronize()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        ptr = integ.render_device(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots,
-                                  flags=flags | (abi.FLAG_SINGLE_SET if a.single_set else 0))
+        ptr = integ.render_device(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots, flags=flags | base_flags)
         if world > 1:
-            film = torch.as_tensor(CudaArray(ptr, (H, W, 5)), device="cuda")
-            dist.reduce(film, dst=0, op=dist.ReduceOp.SUM)          # the single collective: film XYZAW -> rank 0
+            reduce_film(ptr, H * W * 5, None)
         e1.record(); e1.synchronize()
         return e0.elapsed_time(e1), dict(integ.stats)
 
     def step_e2e():
+        """the public call with a HOST film: b2_render (1 GPU) / b2_render_reduce (N GPUs: device-side NCCL reduce through
+        the callback, one device->host copy on rank 0)"""
         flush.zero_()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        integ.render(scene, a.spp, rank=rank, world_size=world, lane_slots=a.lane_slots, out=host_film)
-        if world > 1:      # host-side sum of the rank films happens on the caller side in e2e mode
-            t = torch.from_numpy(host_film).cuda()
-            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                host_film[...] = t.cpu().numpy()
+        if world > 1:
+            integ.render_reduce(scene, a.spp, reduce_film, rank=rank, world_size=world, lane_slots=a.lane_slots, out=host_film)
             torch.cuda.synchronize()
+        else:
+            integ.render(scene, a.spp, lane_slots=a.lane_slots, out=host_film)
         return time.perf_counter() - t0
 
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # (nvidia-smi needs ~1 s to deliver its first sample: started before the warm-up)
     for _ in range(max(a.warmup, 3)):
         step_device()
-    clocks = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        clocks.start()
-    barrier()
+    clocks.mark(True)
     ms_steps, stats = [], []
     for _ in range(a.steps):
         ms, st = step_device()
         ms_steps.append(ms); stats.append(st)
     barrier()
+    clocks.mark(False)
     total_ms = torch.tensor([sum(ms_steps)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
@@ -298,10 +353,15 @@ def main_b2pt(a, rank, world, local_rank):
         dist.all_reduce(e2e_total, op=dist.ReduceOp.MAX)
     e2e_total = float(e2e_total.item())
 
-    # per-stage device time: one extra step with every launch bracketed by CUDA events
-    roof = None; stages = None
+    # per-stage device time: extra steps with every launch bracketed by CUDA events (one lane set, so that a stage's
+    # time is its own), averaged over >= 3 steps so that `kernel` (the stage with the larger time) is a stable choice
+    roof = None; stages = None; bvh = None
     if not a.no_stage_timing:
-        ms_t, st = step_device(flags=abi.FLAG_STAGE_TIMING)
+        n_t = max(3, min(a.steps, 5))
+        acc = {"trace": 0.0, "shade": 0.0}; ms_t = 0.0; st = None
+        for _ in range(n_t):
+            m, st = step_device(flags=abi.FLAG_STAGE_TIMING)
+            ms_t += m / n_t; acc["trace"] += st["ms_intersect"] / n_t; acc["shade"] += st["ms_shade"] / n_t
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -309,40 +369,52 @@ def main_b2pt(a, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         n_it = st["n_iterations"]
-        # algorithmic bytes per stage: K2 52 B/ray; K4 224 + K5 8 B/segment, plus — fused into the
-        # same launch — K1 80 B/regenerated sample and K6 40 B/sample put; K3 68 B/shadow ray (+ K6 for the
-        # samples it completes)
-        put_sh = st.get("n_put_shadow", 0)
-        stage_bytes = {     # k_trace = K2 + K3 (+ K6 for the samples it completes); k_shade = K4 + K5 + K1 + K6
-            "trace": st["n_segments"] * B_HIT + st["n_shadow_rays"] * B_SHADOW + put_sh * B_FILM,
-            "shade": st["n_segments"] * (B_SHADE + B_COMPACT) + st["n_samples"] * B_RAYGEN + (st["n_samples"] - put_sh) * B_FILM,
+        # algorithmic bytes per stage. k_trace = K2 52 B/ray + K5 8 B/lane (the ballot compaction happens at the
+        # end of the traversal) + K3 68 B/shadow ray; k_shade = K4 224 B/segment + K6 40 B/sample put + K1 80 B/regenerated sample
+        stage_bytes = {
+            "trace": st["n_segments"] * (B_HIT + B_COMPACT) + st["n_shadow_rays"] * B_SHADOW,
+            "shade": st["n_segments"] * B_SHADE + st["n_samples"] * (B_RAYGEN + B_FILM),
         }
         stage_units = {"trace": st["n_segments"] + st["n_shadow_rays"], "shade": st["n_segments"]}
-        stage_ms = {"trace": st["ms_intersect"], "shade": st["ms_shade"]}
         stages = {}
         for k, nbytes in stage_bytes.items():
-            t = stage_ms[k]
-            stages[k] = {"ms": t, "units": stage_units[k], "bytes": nbytes, "gbs": (nbytes / (t * 1e-3) / 1e9) if t > 0 else None,
-                         "avg_launch_us": t / max(n_it, 1) * 1e3}
-        units = {k: (1, v) for k, v in stage_bytes.items()}
+            t = acc[k]
+            gbs = (nbytes / (t * 1e-3) / 1e9) if t > 0 else None
+            tr = ncu_traffic(a.workload, "k_" + k)
+            stages[k] = {"kernel": "k_" + k, "ms": t, "units": stage_units[k], "bytes": nbytes, "gbs": gbs, "frac": gbs / peak if gbs else None,
+                         "launches": n_it, "avg_launch_us": t / max(n_it, 1) * 1e3, "bytes_per_launch": nbytes / max(n_it, 1),
+                         "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None}
         dom = max(stages, key=lambda k: stages[k]["ms"])
-        ach = stages[dom]["gbs"]
-        tot_bytes = sum(n * b for n, b in units.values())
-        tot_t = sum(stages[k]["ms"] for k in stages)
-        roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak if ach else None, "traffic": NCU_TRAFFIC.get((a.workload, "k_" + dom), {}).get("bytes"),
-                "traffic_note": NCU_TRAFFIC.get((a.workload, "k_" + dom), {}).get("note"),
-                "achieved_bytes_per_launch": stage_bytes[dom] / max(n_it, 1),
+        tot_bytes = sum(stage_bytes.values()); tot_t = sum(acc.values())
+        roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["frac"], "traffic": stages[dom]["traffic"], "traffic_source": stages[dom]["traffic_source"],
+                "kernel_rule": f"stage with the larger device time, averaged over {n_t} stage-timed steps",
+                "achieved_bytes_per_launch": stages[dom]["bytes_per_launch"],
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
+                "stages": stages,
                 "all_stages_gbs": tot_bytes / (tot_t * 1e-3) / 1e9 if tot_t > 0 else None,
                 "all_stages_frac": tot_bytes / (tot_t * 1e-3) / 1e9 / peak if tot_t > 0 else None,
                 "step_ms_with_timing": ms_t}
+        # BVH term: nodes fetched and primitives tested by all rays of one step, from the counting
+        # instantiation of the traversal kernel (slower: its time is not used)
+        if a.workload != "cbox" or a.bvh_counters:
+            _, sc = step_device(flags=abi.FLAG_COUNT_BVH)
+            nb = sc["n_nodes_visited"] * 128 + sc["n_tris_tested"] * 48
+            rays = sc["n_segments"] + sc["n_shadow_rays"]
+            bvh = {"nodes_visited": sc["n_nodes_visited"], "tris_tested": sc["n_tris_tested"], "rays": rays,
+                   "nodes_per_ray": sc["n_nodes_visited"] / max(rays, 1), "tris_per_ray": sc["n_tris_tested"] / max(rays, 1),
+                   "node_bytes": 128, "tri_bytes": 48, "bytes": nb,
+                   "bytes_at_survey_node_size": sc["n_nodes_visited"] * 80 + sc["n_tris_tested"] * 48,
+                   "gbs_over_trace_time": nb / (acc["trace"] * 1e-3) / 1e9 if acc["trace"] > 0 else None,
+                   "frac_over_trace_time": nb / (acc["trace"] * 1e-3) / 1e9 / peak if acc["trace"] > 0 else None,
+                   "bvh_nodes": sc["bvh_nodes"], "bvh_prims": sc["bvh_tris"], "bvh_depth": sc["bvh_depth"],
+                   "note": "requested bytes (mostly served by L1/L2: the tree is smaller than the 126 MB L2)"}
 
     if rank == 0:
         st = stats[-1]
-        n_items = st["n_samples"] // max(1, (a.spp_per_pass or a.spp))
         value = n_samples * a.steps / (total_ms * 1e-3) / 1e6
         e2e_v = n_samples * a.steps / e2e_total / 1e6
+        q_bytes = (scene_lane_slots(a, st) * 172) / 1e6
         line = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
             "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -352,27 +424,60 @@ def main_b2pt(a, rank, world, local_rank):
                                     "matball": f"rough-conductor (GGX) ball on a checkerboard plane under an environment map, {sb.n_triangles} triangles, {W}x{H}, {a.spp} spp, gaussian filter (BASELINE configs[2] class)",
                                     "grid": f"instanced displaced grid, {sb.n_triangles} triangles x {len(sb.instances)} instances, {W}x{H}, {a.spp} spp (BASELINE configs[4])"}[a.workload], "samples_per_pass": a.spp_per_pass or a.spp, "block_size": 32, "seed": 0,
                        "parallelism": f"pixel blocks b % {world} == rank, one NCCL reduce of the film" if world > 1 else "1 GPU",
-                       "l2": "256 MB flush between steps; wavefront queues > L2", "lane_slots": a.lane_slots or "auto"},
+                       "l2": f"256 MB flush (> the 126 MB L2) between steps; within a step the wavefront queues (~{q_bytes:.0f} MB) are "
+                             "sized to stay L2-resident between the stages, so per-step DRAM traffic is below the algorithmic bytes",
+                       "lane_slots": a.lane_slots or "auto"},
             "mean_segments_per_sample": st["n_segments"] * world / n_samples if world == 1 else None,
+            "scene_create_s": t_scene,
             "e2e": {"value": e2e_v, "unit": "Msamples/s",
-                    "h2d_bytes_per_step": int(8 * (H * W // world) + 4 * min(1 << 22, max(1, n_items))),
-                    "d2h_bytes_per_step": int(H * W * 5 * 4 + 64 * st["n_iterations"] // 8)},
+                    # (the work-item tables are uploaded once per (film, block size, rank, world) and cached in the scene)
+                    "h2d_bytes_per_step": int(ctypes_sizeof_params()),
+                    "d2h_bytes_per_step": int(H * W * 5 * 4 + 128 * (st["n_iterations"] // 8) + 64),
+                    "api": "b2_render" if world == 1 else "b2_render_reduce (device-side NCCL reduce in the callback; rank 0 copies the film)"},
             "gpu_launches": int(sum(s["n_launches"] for s in stats)),
             "clocks": clk,
         }
         if roof:
-            # whole-step view: algorithmic bytes of all stages / the timed step (two lane sets overlapped)
-            spp_seg = stats[-1]["n_segments"] / max(1, stats[-1]["n_samples"]); spp_sh = stats[-1]["n_shadow_rays"] / max(1, stats[-1]["n_samples"])
+            # whole-step view: algorithmic bytes of all stages / the timed step (two lane sets overlapped), per GPU
+            spp_seg = st["n_segments"] * world / n_samples; spp_sh = st["n_shadow_rays"] * world / n_samples
             b_sample = B_RAYGEN + B_FILM + spp_seg * (B_HIT + B_SHADE + B_COMPACT) + spp_sh * B_SHADOW
             roof["bytes_per_sample"] = b_sample
-            roof["step_gbs"] = value * 1e6 * b_sample / 1e9
-            roof["step_frac"] = roof["step_gbs"] / roof["peak"]
+            roof["step_gbs_per_gpu"] = value * 1e6 * b_sample / 1e9 / world
+            roof["step_frac"] = roof["step_gbs_per_gpu"] / roof["peak"]
             line["roofline"] = roof; line["stages"] = stages
+            if bvh:
+                line["bvh"] = bvh
         if a.cpu_baseline and world == 1 and a.workload == "cbox":
             line["cpu_baseline"] = cpu_sample(a, 48)      # ~12 s on 128 host threads
+        if a.parity and world == 1 and a.workload == "cbox":
+            line["parity"] = parity_vs_reference(a, scene, integ)
         emit(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def scene_lane_slots(a, st):
+    return a.lane_slots or 148 * 3072
+
+
+def ctypes_sizeof_params():
+    import ctypes
+    from mitsuba2_b200 import abi
+    return ctypes.sizeof(abi.B2RenderParams)
+
+
+def parity_vs_reference(a, scene, integ):
+    """--parity: render the SAME configuration with the unmodified reference CLI on this box's host cores and compare the
+    developed images (rel-L2 of the fp32 RGB image, HDRFilm::bitmap semantics; flip-robust statistics as in DESIGN.md 5)."""
+    from tests import golden_cases as G
+    from tests.ref_cli import render_cbox
+    ref, secs = render_cbox(a.res, a.spp, a.spp_per_pass, a.max_depth, usable_cores())
+    if ref is None:
+        return {"unavailable": "oracle/_ref/dist/mitsuba cannot run here"}
+    film = integ.render(scene, a.spp)
+    s = G.parity_stats(scene.develop(film), ref)
+    s["reference_seconds"] = secs
+    return s
 
 
 _REAL_STDOUT = None

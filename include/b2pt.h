@@ -194,7 +194,15 @@ typedef struct B2SceneDesc {
     /* analytic shapes; in the closest-hit tie rule they follow all mesh triangles (primitive index = total
        triangle count + shape index, like a ShapeKDTree whose meshes come first) */
     uint32_t n_shapes; const B2Shape *shapes;
+    uint32_t build_flags;               /* B2_BUILD_*: which BVH builder b2_scene_create uses */
 } B2SceneDesc;
+
+/* BVH builders (both replace ShapeKDTree::build, kdtree.h:957-1900; the rendered film does not depend on the choice:
+   closest hits are defined independently of the tree) */
+#define B2_BUILD_HOST_SAH 0u      /* binned-SAH BVH2 on the host, collapsed to BVH4 (best traversal speed)                 */
+#define B2_BUILD_DEVICE_LBVH 1u   /* LBVH on the device (Morton sort + Karras hierarchy + fit + collapse): 10 M triangles in
+                                     tens of ms, for large or per-frame-changing geometry; triangle meshes and shapegroups
+                                     (the BVH over analytic shapes / instances stays on the host: it is tiny)            */
 
 /* ---- render parameters (integrator.cpp:23-40, sampler.cpp:20-30) ------------------------ */
 typedef struct B2RenderParams {
@@ -219,6 +227,8 @@ enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJI
 
 #define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */
 #define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */
+#define B2_FLAG_COUNT_BVH 4u    /* run the counting instantiation of the traversal kernel -> B2Stats.n_nodes_visited /
+                                   n_tris_tested (BVH bytes = nodes * 128 B + tris * 48 B); slower, for measurement */
 
 typedef struct B2Stats {
     uint64_t n_samples;         /* camera samples put on the film                              */
@@ -231,7 +241,12 @@ typedef struct B2Stats {
     float ms_regen, ms_intersect, ms_shade, ms_shadow;   /* per-stage device time: ms_regen = k_init,
                                                             ms_intersect = k_trace (closest + any hit), ms_shadow unused */
     uint64_t bvh_nodes, bvh_tris;
-    uint64_t n_put_shadow;      /* samples put on the film by k_shadow (rest: k_shade)          */
+    uint64_t n_nodes_visited;   /* B2_FLAG_COUNT_BVH: BVH4 nodes fetched by all rays (closest + any hit) */
+    uint64_t n_tris_tested;     /* B2_FLAG_COUNT_BVH: primitives tested                          */
+    uint32_t bvh_depth;         /* levels of the deepest BVH4 (+ the instance BVH's)             */
+    uint32_t _pad;
+    float ms_build;             /* b2_scene_create: BVH build (host or device)                  */
+    float ms_upload;            /* b2_scene_create: flattening + upload                          */
 } B2Stats;
 
 typedef struct B2Scene B2Scene;     /* opaque */
@@ -250,9 +265,22 @@ B2_API int b2_render(B2Scene *scene, const B2RenderParams *params, float *xyzaw,
    until the next render / destroy). For multi-GPU the caller reduces it (ncclReduce). */
 B2_API int b2_render_device(B2Scene *scene, const B2RenderParams *params, float **d_xyzaw,
                             B2Stats *stats);
-B2_API int b2_cancel(B2Scene *scene);                     /* async-safe: sets a flag */
+/* Multi-GPU through the API: every rank (B2RenderParams.rank / world_size) renders its spiral blocks; `reduce` is then
+   called ONCE with this rank's DEVICE film (n floats, enqueued work must go to `cuda_stream`) and must sum the rank
+   films into rank 0's — e.g. ncclReduce(film, film, n, ncclFloat, ncclSum, 0, comm, stream), or torch.distributed.reduce
+   on a tensor wrapping the pointer. Only after it the film is copied to `xyzaw` (may be NULL on ranks != 0), so the only
+   device->host copy of the job is rank 0's. Returns non-zero from `reduce` to signal failure. */
+typedef int (*b2_reduce_fn)(void *user, float *d_film, size_t n_floats, void *cuda_stream);
+B2_API int b2_render_reduce(B2Scene *scene, const B2RenderParams *params, b2_reduce_fn reduce, void *user,
+                            float *xyzaw, B2Stats *stats);
+/* b2_cancel(): async-safe, sets a flag; the running render returns B2_ERR_CANCELLED within one batch of iterations and the
+   film (host buffer of b2_render / device film of b2_render_device) holds the samples accumulated so far, with their count
+   in W — develop it like the reference develops a partial film on SIGHUP (src/mitsuba/mitsuba.cpp:112-121). */
+B2_API int b2_cancel(B2Scene *scene);
 /* HDRFilm::bitmap(): rgb[h*w*3] = M_xyz2rgb * xyz / W  (host in, host out, done on device) */
 B2_API int b2_develop(B2Scene *scene, const float *xyzaw, float *rgb);
+/* Same on the DEVICE film of the last b2_render_device / b2_render (no host round trip of the XYZAW film); rgb is a host buffer */
+B2_API int b2_develop_device(B2Scene *scene, float *rgb);
 /* run stream for b2_render_device (cudaStream_t as void*); default = legacy stream */
 B2_API int b2_set_stream(B2Scene *scene, void *cuda_stream);
 

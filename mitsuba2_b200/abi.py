@@ -15,6 +15,8 @@ EMITTER_AREA, EMITTER_ENVMAP, EMITTER_CONSTANT, EMITTER_POINT, EMITTER_SPOT, EMI
 FILTER_RESOLUTION = 31
 FLAG_STAGE_TIMING = 1
 FLAG_SINGLE_SET = 2
+FLAG_COUNT_BVH = 4
+BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1
 
 
 class B2Bsdf(C.Structure):
@@ -108,6 +110,7 @@ class B2SceneDesc(C.Structure):
         ("sensor", B2Sensor), ("film", B2Film),
         ("n_textures", C.c_uint32), ("textures", C.POINTER(B2Texture)),
         ("n_shapes", C.c_uint32), ("shapes", C.POINTER(B2Shape)),
+        ("build_flags", C.c_uint32),
     ]
 
 
@@ -129,7 +132,9 @@ class B2Stats(C.Structure):
         ("ms_total", C.c_float),
         ("ms_regen", C.c_float), ("ms_intersect", C.c_float), ("ms_shade", C.c_float), ("ms_shadow", C.c_float),
         ("bvh_nodes", C.c_uint64), ("bvh_tris", C.c_uint64),
-        ("n_put_shadow", C.c_uint64),
+        ("n_nodes_visited", C.c_uint64), ("n_tris_tested", C.c_uint64),
+        ("bvh_depth", C.c_uint32), ("_pad", C.c_uint32),
+        ("ms_build", C.c_float), ("ms_upload", C.c_float),
     ]
 
     def as_dict(self):
@@ -193,6 +198,7 @@ class SceneBuffers:
         self.textures = []    # B2Texture (src/textures/{checkerboard,bitmap}.cpp)
         self._tex_mean = []; self._tex_data = []
         self._keep = []
+        self.build_flags = BUILD_HOST_SAH      # B2SceneDesc.build_flags (BUILD_DEVICE_LBVH: build the BVHs on the GPU)
 
     # -- BSDF / emitter constructors with the reference plugins' defaults --------------------
     def add_diffuse(self, reflectance=(0.5, 0.5, 0.5), texture=0):
@@ -463,4 +469,5 @@ class SceneBuffers:
         ss = (B2Shape * max(1, len(shs)))(*shs)
         d.n_shapes = len(shs); d.shapes = ss if shs else None
         self._keep = [ms, bs, es, gf, ins, ts, ss]
+        d.build_flags = self.build_flags
         return d

@@ -24,8 +24,11 @@ EXPORTS = [
     "b2_scene_create", "b2_scene_destroy", "b2_last_error", "b2_device_count", "b2_render", "b2_render_device",
     "b2_cancel", "b2_develop", "b2_set_stream", "b2_stage_raygen", "b2_stage_intersect", "b2_stage_occluded",
     "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
-    "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4",
+    "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4", "b2_render_reduce", "b2_develop_device",
+    "b2_host_bsdf_plastic", "b2_host_shape_sphere", "b2_host_shape_rectangle",
 ]
+
+REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)     # b2_reduce_fn
 
 
 class B2Error(RuntimeError):
@@ -39,7 +42,7 @@ def build(force=False):
     src = os.path.join(_DIR, "csrc")
     if force:
         subprocess.run(["make", "-C", src, "clean"], check=True, capture_output=True)
-    r = subprocess.run(["make", "-C", src], capture_output=True, text=True)
+    r = subprocess.run(["make", "-j4", "-C", src], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("libb2pt build failed:\n" + r.stdout + r.stderr)
     return LIB_PATH
@@ -65,6 +68,10 @@ def lib():
         L.b2_render.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.c_void_p, C.POINTER(abi.B2Stats)]
         L.b2_render_device.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.POINTER(C.c_void_p),
                                        C.POINTER(abi.B2Stats)]
+        if hasattr(L, "b2_render_reduce"):      # (absent from older builds of the ABI loaded through B2PT_LIB for A/B runs)
+            L.b2_render_reduce.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), REDUCE_FN, C.c_void_p, C.c_void_p,
+                                           C.POINTER(abi.B2Stats)]
+            L.b2_develop_device.argtypes = [C.c_void_p, C.c_void_p]
         L.b2_cancel.argtypes = [C.c_void_p]
         L.b2_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -201,6 +208,28 @@ class PathIntegrator:
         _check(lib().b2_render(scene._h, C.byref(rp), out.ctypes.data, C.byref(st)))
         self.stats = st.as_dict()
         return out
+
+    def render_reduce(self, scene, spp, reduce, seed=0, rank=0, world_size=1, lane_slots=0, out=None):
+        """Multi-GPU render through the API: `reduce(ptr, n_floats, stream)` sums this rank's DEVICE film into rank 0's
+        (e.g. torch.distributed.reduce on a tensor wrapping `ptr`); the film is copied to the host only on rank 0
+        (-> [H, W, 5] array there, None elsewhere)."""
+        rp = self.params(spp, seed, rank, world_size, lane_slots)
+        if out is None and rank == 0:
+            out = np.empty((scene.height, scene.width, 5), np.float32)
+
+        def _cb(user, ptr, n, stream):
+            try:
+                reduce(ptr, n, stream)
+                return 0
+            except Exception:      # noqa: BLE001 — reported through the status code
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = REDUCE_FN(_cb)
+        st = abi.B2Stats()
+        _check(lib().b2_render_reduce(scene._h, C.byref(rp), cb, None, out.ctypes.data if rank == 0 else None, C.byref(st)))
+        self.stats = st.as_dict()
+        return out if rank == 0 else None
 
     def render_device(self, scene, spp, seed=0, rank=0, world_size=1, lane_slots=0, flags=0):
         """-> device pointer (int) of the XYZAW film; film stays in HBM."""

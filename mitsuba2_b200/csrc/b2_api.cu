@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -64,10 +65,26 @@ static ShadeFn shade_variant(uint32_t features) {
     if (!init) { fill_shade(table, std::make_integer_sequence<uint32_t, F_COUNT>{}); init = true; }
     return table[features & (F_COUNT - 1)];
 }
-static TraceFn trace_variant(bool inst, bool wide, bool shp) {
-    if (shp) return inst ? (wide ? k_trace_inst<true, true> : k_trace_inst<false, true>) : (wide ? k_trace<false, true, true> : k_trace<false, false, true>);
-    return inst ? (wide ? k_trace_inst<true, false> : k_trace_inst<false, false>) : (wide ? k_trace<false, true, false> : k_trace<false, false, false>);
+static TraceFn trace_variant(bool inst, bool shp, bool count) {
+    if (count) {
+        if (shp) return inst ? k_trace_inst<true, true> : k_trace<false, true, true>;
+        return inst ? k_trace_inst<false, true> : k_trace<false, false, true>;
+    }
+    if (shp) return inst ? k_trace_inst<true, false> : k_trace<false, true, false>;
+    return inst ? k_trace_inst<false, false> : k_trace<false, false, false>;
 }
+
+// CUDA events with scope lifetime (every early return of the driver releases them)
+struct EventPool {
+    std::vector<cudaEvent_t> ev;
+    ~EventPool() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    cudaEvent_t make(bool timing) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, timing ? cudaEventDefault : cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ev.push_back(e);
+        return e;
+    }
+};
 
 struct B2Scene {
     DScene d{};
@@ -83,26 +100,27 @@ struct B2Scene {
     uint32_t features = 0;          // F_* of this scene
     bool has_shapes = false;        // analytic shapes present (selects the SHP traversal variants)
     uint32_t n_tris = 0, n_nodes = 0, bvh_depth = 0;
+    float ms_build = 0.f, ms_upload = 0.f;
     int smem_bytes = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;     // second lane set
-    cudaStream_t stream_extra[2] = { nullptr, nullptr };
     std::atomic<int> cancel{0};
     // render state (allocated lazily, reused across renders)
-    DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c, sh_r;
+    DBuf<float4> ray_o, ray_d, hit, tp, res, sh_o, sh_d, sh_c;
     DBuf<uint4> st;
-    DBuf<float2> pos, sh_p;
-    DBuf<uint32_t> sh_f, cnt, item_pixel, item_seed;
+    DBuf<float2> pos;
+    DBuf<uint32_t> pixel, list, cnt, item_pixel, item_seed;
     DBuf<unsigned long long> stats;
     DBuf<float> film;
-    DBuf<float> film_wide;
-    DBuf<uint2> smp;                // per-lane sampler state of the non-independent samplers          // wide filters: padded accumulation film, 8 floats / pixel
-    uint32_t *h_cnt = nullptr;           // pinned readback
+    DBuf<float> film_wide;          // wide filters: padded accumulation film, 8 floats / pixel
+    DBuf<uint2> smp;                // per-lane sampler state of the non-independent samplers
+    uint32_t *h_cnt = nullptr;      // pinned readback
+    // the work-item tables of the last render (spiral order x Morton order) are kept: they depend only on this key
+    struct { int W = 0, H = 0; uint32_t bs = 0; int rank = -1, world = 0; uint32_t n_items = 0, n_blocks = 0; } items_key;
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
         if (stream2) cudaStreamDestroy(stream2);
-        for (cudaStream_t st : stream_extra) if (st) cudaStreamDestroy(st);
     }
 };
 
@@ -129,37 +147,40 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     for (uint32_t g = 0; g < desc->n_groups; ++g)
         if (desc->group_first[g] < n_top_meshes || desc->group_first[g] > desc->group_first[g + 1] || desc->group_first[g + 1] > desc->n_meshes)
             return fail(B2_ERR_INVALID, "shapegroup %u: bad mesh range", g);
+    // the groups must cover [n_top_meshes, n_meshes) exactly: every mesh is either a top-level shape or a member of one group
+    if (desc->n_groups && (desc->group_first[0] != n_top_meshes || desc->group_first[desc->n_groups] != desc->n_meshes))
+        return fail(B2_ERR_INVALID, "shapegroups must cover the meshes [n_top_meshes, n_meshes) exactly");
     for (uint32_t i = 0; i < desc->n_instances; ++i)
         if (desc->instances[i].group < 0 || (uint32_t) desc->instances[i].group >= desc->n_groups)
             return fail(B2_ERR_INVALID, "instance %u: bad shapegroup index", i);
     for (uint32_t m = n_top_meshes; m < desc->n_meshes; ++m)
         if (desc->meshes[m].emitter >= 0) return fail(B2_ERR_INVALID, "Instancing of emitters is not supported");   // shapegroup.cpp:24-25
     for (uint32_t e = 0; e < desc->n_emitters; ++e)
-        if (desc->emitters[e].type != B2_EMITTER_AREA && desc->emitters[e].type != B2_EMITTER_ENVMAP && desc->emitters[e].type != B2_EMITTER_CONSTANT &&
-            desc->emitters[e].type != B2_EMITTER_POINT)
-            return fail(B2_ERR_INVALID, "emitter %u: only area, envmap, constant and point emitters are supported", e);
+        if (desc->emitters[e].type < B2_EMITTER_AREA || desc->emitters[e].type > B2_EMITTER_DIRECTIONAL)
+            return fail(B2_ERR_INVALID, "emitter %u: only area, envmap, constant, point, spot and directional emitters are supported", e);
     {
         int n_env = 0;
         for (uint32_t e = 0; e < desc->n_emitters; ++e) {
             const B2Emitter &em = desc->emitters[e];
-            if (em.type == B2_EMITTER_AREA || em.type == B2_EMITTER_POINT) continue;
+            if (em.type != B2_EMITTER_ENVMAP && em.type != B2_EMITTER_CONSTANT) continue;
             if (++n_env > 1) return fail(B2_ERR_INVALID, "Only one environment emitter can be specified per scene.");   // scene.cpp:48-49
             if (em.type == B2_EMITTER_ENVMAP && (!em.envmap || em.env_width < 2 || em.env_height < 2)) return fail(B2_ERR_INVALID, "Distribution2D(): input array resolution must be >= 2!");
         }
     }
     for (uint32_t b = 0; b < desc->n_bsdfs; ++b) {
         const int32_t t = desc->bsdfs[b].type;
-        if (t < B2_BSDF_DIFFUSE || t > B2_BSDF_PLASTIC) return fail(B2_ERR_INVALID, "bsdf %u: unsupported type %d", b, t);
-        if (t == B2_BSDF_ROUGHCONDUCTOR && desc->bsdfs[b].distribution != B2_MF_BECKMANN && desc->bsdfs[b].distribution != B2_MF_GGX)
+        if (t < B2_BSDF_DIFFUSE || t > B2_BSDF_ROUGHDIELECTRIC) return fail(B2_ERR_INVALID, "bsdf %u: unsupported type %d", b, t);
+        const bool rough = t == B2_BSDF_ROUGHCONDUCTOR || t == B2_BSDF_ROUGHDIELECTRIC;
+        if (rough && desc->bsdfs[b].distribution != B2_MF_BECKMANN && desc->bsdfs[b].distribution != B2_MF_GGX)
             return fail(B2_ERR_INVALID, "bsdf %u: Specified an invalid distribution (must be \"beckmann\" or \"ggx\")", b);   // microfacet.h
-        if (t == B2_BSDF_ROUGHCONDUCTOR && !desc->bsdfs[b].sample_visible)
-            return fail(B2_ERR_INVALID, "bsdf %u: roughconductor with sample_visible = false is not supported", b);
+        if (rough && !desc->bsdfs[b].sample_visible)
+            return fail(B2_ERR_INVALID, "bsdf %u: rough BSDF with sample_visible = false is not supported", b);
     }
     for (uint32_t m = 0; m < desc->n_meshes; ++m) {
         const B2Mesh &me = desc->meshes[m];
         if (me.bsdf < 0 || (uint32_t) me.bsdf >= desc->n_bsdfs) return fail(B2_ERR_INVALID, "mesh %u: bad bsdf index", m);
         if (me.emitter >= (int32_t) desc->n_emitters) return fail(B2_ERR_INVALID, "mesh %u: bad emitter index", m);
-        for (uint32_t f = 0; f < 3 * me.n_faces; ++f)
+        for (size_t f = 0; f < 3 * (size_t) me.n_faces; ++f)
             if (me.faces[f] >= me.n_vertices) return fail(B2_ERR_INVALID, "mesh %u: face index out of range", m);
     }
     const uint32_t ns = desc->shapes ? desc->n_shapes : 0;
@@ -193,9 +214,19 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     uint32_t n_top_tris = mesh_first[n_top_meshes];
     struct { std::vector<float> nodes; std::vector<uint32_t> order; uint32_t n_nodes = 0, depth = 0; } bvh;
     uint32_t top_nodes = 0;
+    // builder: host binned SAH, or (B2_BUILD_DEVICE_LBVH) the device LBVH with the host builder as fallback
+    auto t_build0 = std::chrono::steady_clock::now();
+    float ms_device_build = 0.f; bool used_device = false;
+    auto build_tris = [&](const std::vector<B2BvhTri> &sub, B2Bvh4 &b) {
+        if ((desc->build_flags & B2_BUILD_DEVICE_LBVH) && sub.size() >= 2) {
+            float ms = 0.f; const char *why = nullptr;
+            if (b2_build_bvh4_device(&sub[0].p[0][0], (uint32_t) sub.size(), false, 2, b, &ms, &why)) { ms_device_build += ms; used_device = true; return; }
+        }
+        b2_build_bvh4(sub, b);
+    };
     if (ns == 0) {
         std::vector<B2BvhTri> sub(tris.begin(), tris.begin() + n_top_tris);
-        B2Bvh4 b; b2_build_bvh4(sub, b);
+        B2Bvh4 b; build_tris(sub, b);
         b2_bvh4_append(bvh.nodes, b, 0);
         bvh.order = b.order; bvh.depth = b.depth; top_nodes = b.n_nodes;
     } else {
@@ -236,7 +267,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     for (uint32_t g = 0; g < desc->n_groups; ++g) {
         uint32_t t0 = mesh_first[desc->group_first[g]], t1 = mesh_first[desc->group_first[g + 1]];
         std::vector<B2BvhTri> sub(tris.begin() + t0, tris.begin() + t1);
-        B2Bvh4 b; b2_build_bvh4(sub, b);
+        B2Bvh4 b; build_tris(sub, b);
         group_root[g] = b2_bvh4_append(bvh.nodes, b, (uint32_t) bvh.order.size());
         for (uint32_t o : b.order) bvh.order.push_back(t0 + o);
         bvh.depth = std::max(bvh.depth, b.depth);
@@ -277,10 +308,13 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         bvh.depth += t.depth; tlas_levels = t.depth;
     }
     bvh.n_nodes = (uint32_t) (bvh.nodes.size() / 32);
-    {   // the traversal stacks are fixed-size local arrays (Trav: 40 entries, TLAS walk: 32, k_trace_inst: 64): a BVH4 level
-        // pushes at most 3 entries, so refuse trees that could overflow them instead of corrupting local memory
+    s->ms_build = used_device ? ms_device_build : std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_build0).count();
+    auto t_upload0 = std::chrono::steady_clock::now();
+    {   // the traversal stacks are fixed-size local arrays (B2_STACK entries per BVH, B2_INST_STACK for k_trace_inst's
+        // single two-level stack); a BVH4 level pushes at most 3 entries. The builders bound the depth (b2_bvh.cpp:
+        // median splits once the level budget runs short), so this is a consistency check, not a limit on the input.
         const uint32_t tlas_depth = desc->n_instances ? tlas_levels : 0, blas_depth = bvh.depth - tlas_depth;
-        if (3 * blas_depth + 1 > 40 || (desc->n_instances && (3 * tlas_depth + 1 > 32 || 3 * (tlas_depth + blas_depth) + 3 > 64))) {
+        if (3 * blas_depth + 2 > B2_STACK || (desc->n_instances && (3 * tlas_depth + 2 > B2_STACK || 3 * (tlas_depth + blas_depth) + 4 > B2_INST_STACK))) {
             delete s;
             return fail(B2_ERR_INVALID, "BVH too deep for the traversal stack (%u + %u levels)", blas_depth, tlas_depth);
         }
@@ -348,7 +382,20 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         const B2Emitter &src = desc->emitters[e];
         if (src.type != B2_EMITTER_AREA) {
             std::memset(&ems[e], 0, sizeof(DEmitter)); ems[e].type = src.type; ems[e].mesh = -1; std::memcpy(ems[e].radiance, src.radiance, 12);
-            if (src.type == B2_EMITTER_POINT) { ems[e].position[0] = src.env_to_world[3]; ems[e].position[1] = src.env_to_world[7]; ems[e].position[2] = src.env_to_world[11]; s->features |= F_TEX; }
+            if (src.type == B2_EMITTER_POINT || src.type == B2_EMITTER_SPOT) {
+                ems[e].position[0] = src.env_to_world[3]; ems[e].position[1] = src.env_to_world[7]; ems[e].position[2] = src.env_to_world[11]; s->features |= F_TEX;
+            }
+            if (src.type == B2_EMITTER_SPOT) {                            // SpotLight::SpotLight, spot.cpp:88-95
+                std::memcpy(ems[e].to_object, src.env_to_object, 48);
+                ems[e].cutoff_angle = src.cutoff_angle; ems[e].beam_width = src.beam_width;
+                ems[e].cos_cutoff = std::cos(src.cutoff_angle); ems[e].cos_beam = std::cos(src.beam_width);
+                ems[e].inv_transition = 1.0f / (src.cutoff_angle - src.beam_width);
+            }
+            if (src.type == B2_EMITTER_DIRECTIONAL) {                     // d = to_world * (0,0,1), directional.cpp:113
+                const float *M = src.env_to_world;
+                for (int r = 0; r < 3; ++r) ems[e].position[r] = std::fma(M[4 * r + 2], 1.f, std::fma(M[4 * r + 1], 0.f, M[4 * r] * 0.f));
+                s->features |= F_TEX;
+            }
             continue;
         }
         if (src.shape > 0) {          // area emitter on an analytic shape
@@ -474,18 +521,55 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
                 delete s; return fail(B2_ERR_INVALID, "Only materials without a transmission component can be nested!"); }
             s->features |= F_TEX;
         }
-        if (b.type == B2_BSDF_ROUGHCONDUCTOR) s->features |= F_ROUGH;
+        if (b.type == B2_BSDF_ROUGHCONDUCTOR || b.type == B2_BSDF_ROUGHDIELECTRIC) s->features |= F_ROUGH;
         if (b.type == B2_BSDF_DIELECTRIC || b.type == B2_BSDF_CONDUCTOR || b.type == B2_BSDF_PLASTIC) s->features |= F_DIELECTRIC;
     }
     if (desc->film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f) s->features |= F_WIDE;
     d.instances = desc->n_instances ? s->instances.p : nullptr; d.inst_order = s->inst_order.p;
     d.n_instances = desc->n_instances; d.tlas_root = tlas_root; d.n_top_tris = n_top_prims;
+    auto scene_bsphere_radius = [&]() -> float {
+        // scene bbox = union of the top-level shapes' boxes (scene.cpp:35-39); instances: to_world * corner (instance.cpp:83-94)
+        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
+        for (uint32_t m = 0; m < n_top_meshes; ++m)
+            for (uint32_t vtx = 0; vtx < desc->meshes[m].n_vertices; ++vtx)
+                for (int k = 0; k < 3; ++k) { float c = desc->meshes[m].positions[3 * (size_t) vtx + k]; lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c); }
+        for (uint32_t i = 0; i < desc->n_instances; ++i) {
+            const B2Instance &in2 = desc->instances[i];
+            const B2BvhBox &gb = group_box[in2.group];
+            if (!(gb.lo[0] <= gb.hi[0])) continue;
+            for (int c = 0; c < 8; ++c) {
+                float p[3] = { c & 1 ? gb.hi[0] : gb.lo[0], c & 2 ? gb.hi[1] : gb.lo[1], c & 4 ? gb.hi[2] : gb.lo[2] };
+                for (int r = 0; r < 3; ++r) {
+                    const float *M = in2.to_world + 4 * r;
+                    float w = std::fma(M[2], p[2], std::fma(M[1], p[1], std::fma(M[0], p[0], M[3])));
+                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
+                }
+            }
+        }
+        for (uint32_t k = 0; k < ns; ++k) {                            // Rectangle::bbox rectangle.cpp:94-101, Sphere::bbox sphere.cpp:131-136
+            const B2Shape &sh = desc->shapes[k];
+            for (int cn = 0; cn < 4; ++cn)
+                for (int r = 0; r < 3; ++r) {
+                    float w;
+                    if (sh.type == B2_SHAPE_RECTANGLE) {
+                        const float *M = sh.to_world + 4 * r;
+                        w = std::fma(M[2], 0.f, std::fma(M[1], cn & 2 ? 1.f : -1.f, std::fma(M[0], cn & 1 ? 1.f : -1.f, M[3])));
+                    } else w = cn & 1 ? sh.center[r] - sh.radius : sh.center[r] + sh.radius;
+                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
+                }
+        }
+        float c[3] = { (lo[0] + hi[0]) * .5f, (lo[1] + hi[1]) * .5f, (lo[2] + hi[2]) * .5f };
+        float dd[3] = { c[0] - hi[0], c[1] - hi[1], c[2] - hi[2] };
+        float radius = std::sqrt((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]);     // bbox.h:329-332
+        const float ray_eps = 1500.0f * 5.9604644775390625e-08f;
+        return std::max(ray_eps, radius * (1.f + ray_eps));
+    };
     // environment map: Hierarchical2D levels (distr_2d.h:372-471) + scene bounding sphere (envmap.cpp:127-131)
     d.env.index = -1;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) if (desc->emitters[e].type == B2_EMITTER_ENVMAP || desc->emitters[e].type == B2_EMITTER_CONSTANT) s->features |= F_ENV;
     for (uint32_t e = 0; e < desc->n_emitters; ++e) {
         const B2Emitter &em = desc->emitters[e];
-        if (em.type == B2_EMITTER_AREA || em.type == B2_EMITTER_POINT) continue;
+        if (em.type != B2_EMITTER_ENVMAP && em.type != B2_EMITTER_CONSTANT) continue;
         DEnv &v = d.env;
         v.index = (int32_t) e; v.type = em.type; std::memcpy(v.radiance, em.radiance, 12);
         if (em.type == B2_EMITTER_ENVMAP) {
@@ -540,48 +624,18 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         v.scale = em.scale;
         std::memcpy(v.to_world, em.env_to_world, 48); std::memcpy(v.to_object, em.env_to_object, 48);
         }   // (constant background emitter, constant.cpp: only the bounding sphere below)
-        // scene bbox = union of the top-level shapes' boxes (scene.cpp:35-39); instances: to_world * corner (instance.cpp:83-94)
-        float lo[3] = { INFINITY, INFINITY, INFINITY }, hi[3] = { -INFINITY, -INFINITY, -INFINITY };
-        for (uint32_t m = 0; m < n_top_meshes; ++m)
-            for (uint32_t vtx = 0; vtx < desc->meshes[m].n_vertices; ++vtx)
-                for (int k = 0; k < 3; ++k) { float c = desc->meshes[m].positions[3 * (size_t) vtx + k]; lo[k] = std::min(lo[k], c); hi[k] = std::max(hi[k], c); }
-        for (uint32_t i = 0; i < desc->n_instances; ++i) {
-            const B2Instance &in2 = desc->instances[i];
-            const B2BvhBox &gb = group_box[in2.group];
-            if (!(gb.lo[0] <= gb.hi[0])) continue;
-            for (int c = 0; c < 8; ++c) {
-                float p[3] = { c & 1 ? gb.hi[0] : gb.lo[0], c & 2 ? gb.hi[1] : gb.lo[1], c & 4 ? gb.hi[2] : gb.lo[2] };
-                for (int r = 0; r < 3; ++r) {
-                    const float *M = in2.to_world + 4 * r;
-                    float w = std::fma(M[2], p[2], std::fma(M[1], p[1], std::fma(M[0], p[0], M[3])));
-                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
-                }
-            }
-        }
-        for (uint32_t k = 0; k < ns; ++k) {                            // Rectangle::bbox rectangle.cpp:94-101, Sphere::bbox sphere.cpp:131-136
-            const B2Shape &sh = desc->shapes[k];
-            for (int cn = 0; cn < 4; ++cn)
-                for (int r = 0; r < 3; ++r) {
-                    float w;
-                    if (sh.type == B2_SHAPE_RECTANGLE) {
-                        const float *M = sh.to_world + 4 * r;
-                        w = std::fma(M[2], 0.f, std::fma(M[1], cn & 2 ? 1.f : -1.f, std::fma(M[0], cn & 1 ? 1.f : -1.f, M[3])));
-                    } else w = cn & 1 ? sh.center[r] - sh.radius : sh.center[r] + sh.radius;
-                    lo[r] = std::min(lo[r], w); hi[r] = std::max(hi[r], w);
-                }
-        }
-        float c[3] = { (lo[0] + hi[0]) * .5f, (lo[1] + hi[1]) * .5f, (lo[2] + hi[2]) * .5f };
-        float dd[3] = { c[0] - hi[0], c[1] - hi[1], c[2] - hi[2] };
-        float radius = std::sqrt((dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]);     // bbox.h:329-332
-        const float ray_eps = 1500.0f * 5.9604644775390625e-08f;
-        v.radius = std::max(ray_eps, radius * (1.f + ray_eps));
+        v.radius = scene_bsphere_radius();
     }
+    // DirectionalEmitter::set_scene (directional.cpp:64-69) needs the bounding sphere too
+    if (d.env.index < 0)
+        for (uint32_t e = 0; e < desc->n_emitters; ++e)
+            if (desc->emitters[e].type == B2_EMITTER_DIRECTIONAL) { d.env.radius = scene_bsphere_radius(); break; }
     d.n_nodes = bvh.n_nodes; d.n_tris = n_slots; d.n_emitters = desc->n_emitters; d.n_bsdfs = desc->n_bsdfs;
     d.sensor = desc->sensor; d.film = desc->film;
     // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
     const uint32_t budget_all = 48 * 1024, budget_top = 32 * 1024;
     if (bvh.n_nodes * 128u + n_slots * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
-    else { d.smem_nodes = std::min<uint32_t>(top_nodes, budget_top / 128u); d.smem_tris = 0; }
+    else { d.smem_nodes = used_device ? 0u : std::min<uint32_t>(top_nodes, budget_top / 128u); d.smem_tris = 0; }   // (LBVH nodes are not in breadth-first order)
     // tiny flat scenes: list the BVH leaves (box + code) for the exhaustive leaf scan (traverse_flat)
     d.n_flat_leaves = 0; d.flat_leaves = nullptr;
     if (d.smem_tris && desc->n_instances == 0 && nt > 0 && ns == 0) {
@@ -601,13 +655,10 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? n_slots * 48u : 0u) + d.n_flat_leaves * 32u);
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(shade_variant(s->features), cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
     s->has_shapes = ns != 0;
-    cudaFuncSetAttribute(trace_variant(desc->n_instances != 0, (s->features & F_WIDE) != 0, s->has_shapes), cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_stage_intersect<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_stage_intersect<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_stage_occluded<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
-    cudaFuncSetAttribute(k_stage_occluded<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes);
+    s->ms_upload = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_upload0).count();
+    // (cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, process-wide attribute: it is set right before the
+    //  launches of b2_render_device / b2_stage_*, not here, so that several live scenes cannot clobber each other's limit)
     *out = s;
     return B2_OK;
 }
@@ -633,6 +684,41 @@ int b2_cancel(B2Scene *scene) {
 // --------------------------------------------------------------------------------------------
 // SamplingIntegrator::render (integrator.cpp:51-179) as a wavefront loop
 // --------------------------------------------------------------------------------------------
+// Work-item table of one pass: this rank's blocks in spiral order (spiral.cpp:27-72), Morton order inside a
+// block (integrator.cpp:196-209). Depends only on (crop size, block size, rank, world): kept across renders.
+static int prepare_work_items(B2Scene *s, int W, int H, uint32_t bs, int rank, int world) {
+    auto &k = s->items_key;
+    if (k.W == W && k.H == H && k.bs == bs && k.rank == rank && k.world == world) return B2_OK;
+    uint32_t n_blocks = 0;
+    b2_host_spiral(W, H, (int) bs, &n_blocks, nullptr);
+    std::vector<int32_t> order(2 * (size_t) n_blocks);
+    b2_host_spiral(W, H, (int) bs, &n_blocks, order.data());
+    // Morton decode table of one block: index -> (x, y)
+    std::vector<uint16_t> mxy(2 * (size_t) bs * bs);
+    for (uint32_t i = 0; i < bs * bs; ++i) {
+        uint32_t mx = 0, my = 0;
+        for (uint32_t bit = 0; bit < 16; ++bit) { mx |= ((i >> (2 * bit)) & 1u) << bit; my |= ((i >> (2 * bit + 1)) & 1u) << bit; }
+        mxy[2 * i] = (uint16_t) mx; mxy[2 * i + 1] = (uint16_t) my;
+    }
+    std::vector<uint32_t> item_pixel, item_seed;
+    item_pixel.reserve((size_t) W * H / (size_t) world + bs * bs); item_seed.reserve(item_pixel.capacity());
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        if ((int) (b % (uint32_t) world) != rank) continue;
+        int ox = order[2 * b] * (int) bs, oy = order[2 * b + 1] * (int) bs;
+        int bw = std::min((int) bs, W - ox), bh = std::min((int) bs, H - oy);
+        // Morton indices in increasing order, skipping pixels outside (integrator.cpp:200-202)
+        for (uint32_t i = 0; i < bs * bs; ++i) {
+            int mx = mxy[2 * i], my = mxy[2 * i + 1];
+            if (mx >= bw || my >= bh) continue;
+            item_pixel.push_back((uint32_t) (ox + mx) | ((uint32_t) (oy + my) << 16));
+            item_seed.push_back(b * bs * bs + i);
+        }
+    }
+    CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
+    k.W = W; k.H = H; k.bs = bs; k.rank = rank; k.world = world; k.n_items = (uint32_t) item_pixel.size(); k.n_blocks = n_blocks;
+    return B2_OK;
+}
+
 int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2Stats *stats) {
     if (!s || !rp) return fail(B2_ERR_INVALID, "b2_render: null argument");
     const B2Film &film = s->d.film;
@@ -649,30 +735,23 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     s->cancel.store(0);
     cudaStream_t stream = s->stream;
 
-    // work-item table of one pass: this rank's blocks in spiral order, Morton order inside a block
-    uint32_t n_blocks = 0;
-    b2_host_spiral(W, H, (int) bs, &n_blocks, nullptr);
-    std::vector<int32_t> order(2 * (size_t) n_blocks);
-    b2_host_spiral(W, H, (int) bs, &n_blocks, order.data());
-    std::vector<uint32_t> item_pixel, item_seed;
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-        if ((int) (b % (uint32_t) world) != rank) continue;
-        int ox = order[2 * b] * (int) bs, oy = order[2 * b + 1] * (int) bs;
-        int bw = std::min((int) bs, W - ox), bh = std::min((int) bs, H - oy);
-        // enumerate Morton indices in increasing order, skipping pixels outside (integrator.cpp:200-202)
-        for (uint32_t i = 0; i < bs * bs; ++i) {
-            uint32_t mx = 0, my = 0;
-            for (uint32_t bit = 0; bit < 16; ++bit) { mx |= ((i >> (2 * bit)) & 1u) << bit; my |= ((i >> (2 * bit + 1)) & 1u) << bit; }
-            if ((int) mx >= bw || (int) my >= bh) continue;
-            item_pixel.push_back((uint32_t) (ox + (int) mx) | ((uint32_t) (oy + (int) my) << 16));
-            item_seed.push_back(b * bs * bs + i);
-        }
+    { int rc = prepare_work_items(s, W, H, bs, rank, world); if (rc != B2_OK) return rc; }
+    const uint32_t n_items_pass = s->items_key.n_items, n_blocks = s->items_key.n_blocks;
+    uint64_t total64 = (uint64_t) n_items_pass * n_passes;
+    bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
+    CU(s->film.alloc((size_t) W * H * 5));
+    CU(s->stats.alloc(8));
+    if (total64 == 0) {
+        // a rank that owns no spiral block (world_size > number of blocks): empty film, nothing to launch
+        CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
+        CU(cudaStreamSynchronize(stream));
+        if (stats) { std::memset(stats, 0, sizeof *stats); stats->bvh_nodes = s->n_nodes; stats->bvh_tris = s->n_tris; stats->bvh_depth = s->bvh_depth; }
+        if (d_xyzaw) *d_xyzaw = s->film.p;
+        return B2_OK;
     }
-    uint64_t total64 = (uint64_t) item_pixel.size() * n_passes;
-    uint32_t n_items_pass = (uint32_t) item_pixel.size();
     // default wavefront width: a whole number of lanes per thread for every stage kernel
     // (sm_count * 3072 = 3 lanes/thread at 4 CTAs/SM, 4 lanes/thread at 3 CTAs/SM) — and small
-    // enough (71 MB of queues on 148 SMs) to stay resident in the 126 MB L2 between the stages
+    // enough (75 MB of queues on 148 SMs) to stay resident in the 126 MB L2 between the stages
     // (instanced scenes: ray cost varies by orders of magnitude, so the launches are made 16x longer to
     //  amortise their tails — measured 680 -> 890 Msamples/s on the BASELINE lattice)
     uint32_t slots = rp->lane_slots ? rp->lane_slots : (uint32_t) s->sm_count * 3072u * (s->d.n_instances ? 16u : 1u);
@@ -680,16 +759,13 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     slots = (slots + 31u) & ~31u;
     if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
 
-    bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
     const size_t cap = (size_t) slots + 128;      // two lane sets, each rounded up to a multiple of 32
     CU(s->ray_o.alloc(cap)); CU(s->ray_d.alloc(cap)); CU(s->hit.alloc(cap)); CU(s->tp.alloc(cap)); CU(s->res.alloc(cap));
-    CU(s->sh_o.alloc(cap)); CU(s->sh_d.alloc(cap)); CU(s->sh_c.alloc(cap)); CU(s->sh_r.alloc(cap)); CU(s->sh_f.alloc(cap));
-    CU(s->st.alloc(cap));
-    if (wide) { CU(s->pos.alloc(cap)); CU(s->sh_p.alloc(cap)); }
+    CU(s->sh_o.alloc(cap)); CU(s->sh_d.alloc(cap)); CU(s->sh_c.alloc(cap));
+    CU(s->st.alloc(cap)); CU(s->pixel.alloc(cap)); CU(s->list.alloc(2 * cap));
+    if (wide) CU(s->pos.alloc(cap));
     if (s->d.n_instances) CU(s->hit_inst.alloc(cap));
-    CU(s->cnt.alloc(32)); CU(s->stats.alloc(8));
-    CU(s->item_pixel.upload(item_pixel)); CU(s->item_seed.upload(item_seed));
-    CU(s->film.alloc((size_t) W * H * 5));
+    CU(s->cnt.alloc(32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
     // up and warns; here it is an error so that spp keeps its meaning)
@@ -709,30 +785,30 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             if ((1u << lg) != rp->spp || (lg & 1u) || rp->spp < 4) return fail(B2_ERR_INVALID, "Sample count should be square and power of two (got %u)", rp->spp);
             smp_res = lg;                                                // log2 of the sample count (permute(), random.h:194-207)
         } else return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
-        if (spp_pass > 65535u) return fail(B2_ERR_INVALID, "stratified sampler: samples_per_pass must be < 65536");
         CU(s->smp.alloc(cap));
     }
-    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 16 * sizeof(uint32_t)));
+    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 32 * sizeof(uint32_t)));
 
-    // The lane slots are split into independent lane SETS, each with its own counters and shadow
+    // The lane slots are split into two independent lane SETS, each with its own counters, lists and shadow
     // queue, driven on its own stream: while one set is in its (issue-bound) traversal launch the
     // other is in its (latency-bound) shading launch, so the two kinds of kernel share the SMs and the
-    // launch tails of one set are filled by the other. All sets pull work items from one counter.
-    // (per-stage timing runs the sets one at a time so that a stage's time is its own)
-    int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
-    if (n_sets > 1) { const char *e = getenv("B2_LANE_SETS"); if (e && atoi(e) >= 1 && atoi(e) <= 4) n_sets = atoi(e); }   // tuning knob
-    uint32_t set_slots = ((slots / n_sets) + 31u) & ~31u;
-    if (n_sets > 1) slots = set_slots * n_sets;     // (allocations below were sized with the rounded-up count)
-    Queues qs[4];
+    // launch tails of one set are filled by the other. Both sets pull work items from one counter.
+    // (per-stage timing runs one set so that a stage's time is its own)
+    const int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
+    const uint32_t set_slots = ((slots / n_sets) + 31u) & ~31u;
+    if (n_sets > 1) slots = set_slots * n_sets;     // (allocations above were sized with the rounded-up count)
+    const int WORK_WORD = 2 * B2_CNT_WORDS;
+    Queues qs[2];
     for (int k = 0; k < n_sets; ++k) {
         Queues &q = qs[k];
         q = Queues{};
         size_t o = (size_t) k * set_slots;
         q.ray_o = s->ray_o.p + o; q.ray_d = s->ray_d.p + o; q.hit = s->hit.p + o; q.tp = s->tp.p + o; q.res = s->res.p + o; q.st = s->st.p + o;
-        q.pos = wide ? s->pos.p + o : nullptr; q.sh_p = wide ? s->sh_p.p + o : nullptr;
+        q.pixel = s->pixel.p + o; q.list[0] = s->list.p + 2 * o; q.list[1] = s->list.p + 2 * o + set_slots;
+        q.pos = wide ? s->pos.p + o : nullptr;
         q.hit_inst = s->d.n_instances ? s->hit_inst.p + o : nullptr;
-        q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o; q.sh_r = s->sh_r.p + o; q.sh_f = s->sh_f.p + o;
-        q.cnt = s->cnt.p + 4 * k; q.work = s->cnt.p + 16; q.stats = s->stats.p;
+        q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o;
+        q.cnt = s->cnt.p + B2_CNT_WORDS * k; q.work = s->cnt.p + WORK_WORD; q.stats = s->stats.p;
         if (sampler_type != B2_SAMPLER_INDEPENDENT) {
             q.smp = s->smp.p + o; q.smp_count = rp->spp; q.smp_res = smp_res; q.smp_jitter = (rp->sampler & B2_SAMPLER_NO_JITTER) ? 0u : 1u;
             q.smp_inv_count = 1.f / (float) rp->spp; q.smp_inv_res = 1.f / (float) smp_res;
@@ -743,15 +819,11 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.total_items = (uint32_t) total64; q.n_slots = set_slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
     }
 
-    cudaEvent_t ev0, ev1, evb[2], evs;
-    CU(cudaEventCreate(&ev0)); CU(cudaEventCreate(&ev1));
-    CU(cudaEventCreateWithFlags(&evb[0], cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&evb[1], cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&evs, cudaEventDisableTiming));
-    cudaEvent_t evx[4] = { nullptr, nullptr, nullptr, nullptr };
-    for (int k = 1; k < 4; ++k) CU(cudaEventCreateWithFlags(&evx[k], cudaEventDisableTiming));
+    EventPool pool;
+    cudaEvent_t ev0 = pool.make(true), ev1 = pool.make(true), evb[2] = { pool.make(false), pool.make(false) }, evs = pool.make(false), evx = pool.make(false);
+    if (!ev0 || !ev1 || !evb[0] || !evb[1] || !evs || !evx) return fail(B2_ERR_CUDA, "cudaEventCreate failed");
     if (n_sets > 1 && !s->stream2) CU(cudaStreamCreateWithFlags(&s->stream2, cudaStreamNonBlocking));
-    for (int k = 2; k < n_sets; ++k) if (!s->stream_extra[k - 2]) CU(cudaStreamCreateWithFlags(&s->stream_extra[k - 2], cudaStreamNonBlocking));
-    cudaStream_t streams[4] = { stream, n_sets > 1 ? s->stream2 : stream, s->stream_extra[0], s->stream_extra[1] };
+    cudaStream_t streams[2] = { stream, n_sets > 1 ? s->stream2 : stream };
     CU(cudaEventRecord(ev0, stream));
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     if (wide) CU(cudaMemsetAsync(s->film_wide.p, 0, (size_t) W * H * 8 * sizeof(float), stream));
@@ -762,39 +834,42 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // non-independent samplers run in the extended (F_TEX) kernel variants
     const uint32_t run_features = s->features | (sampler_type != B2_SAMPLER_INDEPENDENT ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
-    if (run_features != s->features) cudaFuncSetAttribute(shade_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes);
-    const TraceFn trace_fn = trace_variant(inst, wide, s->has_shapes);
+    const TraceFn trace_fn = trace_variant(inst, s->has_shapes, (rp->flags & B2_FLAG_COUNT_BVH) != 0);
+    // (the limit is a per-function, process-wide attribute: set it for THIS scene right before its launches)
+    CU(cudaFuncSetAttribute(shade_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes));
+    CU(cudaFuncSetAttribute(trace_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
     uint32_t need_blocks = (set_slots + threads - 1) / threads;
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids
     int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = grid;
-    if (inst) grid_int = s->sm_count * B2_INST_MINBLOCKS;           // k_trace_inst: persistent warps, 3 CTAs/SM resident
+    if (inst) grid_int = s->sm_count * B2_INST_MINBLOCKS;           // k_trace_inst: persistent warps
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
-    std::vector<cudaEvent_t> tev;     // 3 events per iteration and set when stage timing is on
-    auto tick = [&](cudaStream_t st) { if (timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); tev.push_back(e); } };
+    std::vector<cudaEvent_t> tev;     // 3 events per iteration when stage timing is on
+    auto tick = [&](cudaStream_t st) { if (timing) { cudaEvent_t e = pool.make(true); if (e) { cudaEventRecord(e, st); tev.push_back(e); } } };
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;
-    if (timing) { cudaEventCreate(&evi0); cudaEventCreate(&evi1); cudaEventRecord(evi0, stream); }
+    if (timing) { evi0 = pool.make(true); evi1 = pool.make(true); if (evi0) cudaEventRecord(evi0, stream); }
     for (int k = 0; k < n_sets; ++k) {
         if (sampler_type != B2_SAMPLER_INDEPENDENT) k_init<true><<<grid, threads, 0, stream>>>(s->d, qs[k]);
         else k_init<false><<<grid, threads, 0, stream>>>(s->d, qs[k]);
         ++launches;
     }
-    if (timing) cudaEventRecord(evi1, stream);
-    if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); for (int k = 1; k < n_sets; ++k) CU(cudaStreamWaitEvent(streams[k], evs, 0)); }
+    if (timing && evi1) cudaEventRecord(evi1, stream);
+    if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); CU(cudaStreamWaitEvent(streams[1], evs, 0)); }
     int pending[2] = { 0, 0 };
     bool done = false;
     int status = B2_OK;
-    int parity = 0;         // k_shade of iteration k appends its emitter samples to cnt[CNT_SHADOW + (k & 1)]
+    int parity = 0;
     for (int b = 0; !done; ++b) {
         int slot = b & 1;
         for (int it = 0; it < batch; ++it) {
-            // iteration: trace (closest hit of every live lane + the previous iteration's emitter samples) -> shade
+            // iteration: trace (closest hit + the previous iteration's emitter samples + compaction) -> shade
             for (int k = 0; k < n_sets; ++k) {
                 cudaStream_t st = streams[k];
                 tick(st);
-                trace_fn<<<grid_int, threads, s->smem_bytes, st>>>(s->d, qs[k], parity ^ 1);
+                trace_fn<<<grid_int, threads, s->smem_bytes, st>>>(s->d, qs[k], parity);
+                if (inst) { k_classify<<<grid, threads, 0, st>>>(qs[k], parity); ++launches; }
                 tick(st);
                 shade_fn<<<grid_sha, threads, s->shade_smem_bytes, st>>>(s->d, qs[k], parity);
                 tick(st);
@@ -803,76 +878,113 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             parity ^= 1;
             ++iterations;
         }
-        for (int k = 1; k < n_sets; ++k) { CU(cudaEventRecord(evx[k], streams[k])); CU(cudaStreamWaitEvent(stream, evx[k], 0)); }
-        CU(cudaMemcpyAsync(s->h_cnt + 16 * slot, s->cnt.p, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        if (n_sets > 1) { CU(cudaEventRecord(evx, streams[1])); CU(cudaStreamWaitEvent(stream, evx, 0)); }
+        CU(cudaMemcpyAsync(s->h_cnt + 32 * slot, s->cnt.p, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
-        for (int k = 1; k < n_sets; ++k) CU(cudaStreamWaitEvent(streams[k], evb[slot], 0));     // keep the streams within one batch of each other
+        if (n_sets > 1) CU(cudaStreamWaitEvent(streams[1], evb[slot], 0));     // keep the streams within one batch of each other
         pending[slot] = 1;
         // wait for the PREVIOUS batch's readback so the GPU always has one batch queued
         int prev = slot ^ 1;
         if (pending[prev]) {
             CU(cudaEventSynchronize(evb[prev]));
             pending[prev] = 0;
-            const uint32_t *c = s->h_cnt + 16 * prev;
-            // finished when every lane retired and the last k_shade left no emitter sample unresolved
+            const uint32_t *c = s->h_cnt + 32 * prev;
+            // finished when every lane retired (parked lanes count as alive) and no emitter sample is unresolved
             bool all = true;
             for (int k = 0; k < n_sets; ++k)
-                all = all && c[4 * k + CNT_ALIVE] == 0 && c[4 * k + CNT_SHADOW] == 0 && c[4 * k + CNT_SHADOW + 1] == 0;
+                all = all && c[B2_CNT_WORDS * k + CNT_ALIVE] == 0 && c[B2_CNT_WORDS * k + CNT_SHADOW] == 0 && c[B2_CNT_WORDS * k + CNT_SHADOW + 1] == 0;
             if (all) done = true;
         }
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
         if (cudaPeekAtLastError() != cudaSuccess) break;
     }
-    for (int k = 1; k < n_sets; ++k) { CU(cudaEventRecord(evx[k], streams[k])); CU(cudaStreamWaitEvent(stream, evx[k], 0)); }
-    cudaEventDestroy(evs); for (int k = 1; k < 4; ++k) cudaEventDestroy(evx[k]);
+    if (n_sets > 1) { CU(cudaEventRecord(evx, streams[1])); CU(cudaStreamWaitEvent(stream, evx, 0)); }
     CU(cudaGetLastError());
     if (wide) { size_t np = (size_t) W * H; k_film_compact<<<(unsigned) ((np + 255) / 256), 256, 0, stream>>>(s->film_wide.p, s->film.p, np); ++launches; }
     CU(cudaEventRecord(ev1, stream));
     CU(cudaEventSynchronize(ev1));
     float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evb[0]); cudaEventDestroy(evb[1]);
     if (stats) {
         unsigned long long h[8];
-        CU(cudaMemcpy(h, s->stats.p, sizeof h, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpyAsync(h, s->stats.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+        CU(cudaStreamSynchronize(stream));
         std::memset(stats, 0, sizeof *stats);
         stats->n_samples = h[ST_SAMPLES]; stats->n_segments = h[ST_SEGMENTS]; stats->n_shadow_rays = h[ST_SHADOW];
         stats->n_invalid = h[ST_INVALID]; stats->n_iterations = iterations; stats->n_launches = launches;
-        stats->ms_total = ms; stats->bvh_nodes = s->n_nodes; stats->bvh_tris = s->n_tris;
+        stats->n_nodes_visited = h[ST_NODES]; stats->n_tris_tested = h[ST_TRIS];
+        stats->ms_total = ms; stats->bvh_nodes = s->n_nodes; stats->bvh_tris = s->n_tris; stats->bvh_depth = s->bvh_depth;
+        stats->ms_build = s->ms_build; stats->ms_upload = s->ms_upload;
         for (size_t i = 0; i + 2 < tev.size(); i += 3) {
-            float t[2];
+            float t[2] = { 0.f, 0.f };
             for (int k = 0; k < 2; ++k) cudaEventElapsedTime(&t[k], tev[i + k], tev[i + k + 1]);
-            stats->ms_intersect += t[0]; stats->ms_shade += t[1];     // ms_intersect = k_trace (closest + any hit)
+            stats->ms_intersect += t[0]; stats->ms_shade += t[1];     // ms_intersect = k_trace (closest + any hit + compaction)
         }
-        if (timing) cudaEventElapsedTime(&stats->ms_regen, evi0, evi1);      // k_init
-        stats->n_put_shadow = h[4];
+        if (timing && evi0 && evi1) cudaEventElapsedTime(&stats->ms_regen, evi0, evi1);      // k_init
     }
-    if (evi0) { cudaEventDestroy(evi0); cudaEventDestroy(evi1); }
-    for (cudaEvent_t e : tev) cudaEventDestroy(e);
     if (d_xyzaw) *d_xyzaw = s->film.p;
+    // (a cancelled render leaves the samples accumulated so far on the film: develop it like the reference does on
+    //  SIGHUP, mitsuba.cpp:112-121 / integrator.cpp:58-65 — W carries the per-pixel sample count)
     if (status == B2_ERR_CANCELLED) return fail(status, "render cancelled");
     return status;
 }
 
 int b2_render(B2Scene *s, const B2RenderParams *rp, float *xyzaw, B2Stats *stats) {
-    if (!xyzaw) return fail(B2_ERR_INVALID, "b2_render: null output");
+    return b2_render_reduce(s, rp, nullptr, nullptr, xyzaw, stats);
+}
+
+// Multi-GPU: every rank renders its blocks (b % world == rank); `reduce` is called once with this rank's DEVICE film
+// (n floats, on `stream`) and sums it into rank 0's — e.g. ncclReduce(film, film, n, ncclFloat, ncclSum, 0, comm, stream)
+// — and only then the film is copied to the host buffer (rank 0; other ranks may pass xyzaw = NULL).
+int b2_render_reduce(B2Scene *s, const B2RenderParams *rp, b2_reduce_fn reduce, void *user, float *xyzaw, B2Stats *stats) {
+    if (!s || !rp) return fail(B2_ERR_INVALID, "b2_render: null argument");
+    if (!xyzaw && !reduce) return fail(B2_ERR_INVALID, "b2_render: null output");
     float *d = nullptr;
     int rc = b2_render_device(s, rp, &d, stats);
-    if (rc != B2_OK) return rc;
+    if (rc != B2_OK && rc != B2_ERR_CANCELLED) return rc;
+    const std::string msg = g_error;
     size_t n = (size_t) s->d.film.crop_size[0] * s->d.film.crop_size[1] * 5;
-    CU(cudaMemcpyAsync(xyzaw, d, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
-    return B2_OK;
+    if (reduce && rc == B2_OK) {
+        int rr = reduce(user, d, n, (void *) s->stream);
+        if (rr != 0) return fail(B2_ERR_CUDA, "b2_render_reduce: the reduce callback failed (%d)", rr);
+    }
+    if (xyzaw) {
+        CU(cudaMemcpyAsync(xyzaw, d, n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    }
+    if (rc != B2_OK) g_error = msg;
+    return rc;
 }
+
+// host <-> device copies of the stage entry points are ordered on the scene's stream (b2_set_stream may install a
+// non-blocking stream, on which the legacy-stream cudaMemcpy would not be ordered with the kernel)
+#define H2D(dst, src, bytes) CU(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, s->stream))
+#define D2H(dst, src, bytes) CU(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, s->stream))
+#define SYNC() CU(cudaStreamSynchronize(s->stream))
 
 int b2_develop(B2Scene *s, const float *xyzaw, float *rgb) {
     if (!s || !xyzaw || !rgb) return fail(B2_ERR_INVALID, "b2_develop: null argument");
-    int n = s->d.film.crop_size[0] * s->d.film.crop_size[1];
+    const size_t n = (size_t) s->d.film.crop_size[0] * (size_t) s->d.film.crop_size[1];
     DBuf<float> in, out;
-    CU(in.alloc((size_t) n * 5)); CU(out.alloc((size_t) n * 3));
-    CU(cudaMemcpy(in.p, xyzaw, (size_t) n * 5 * sizeof(float), cudaMemcpyHostToDevice));
-    k_develop<<<(n + 255) / 256, 256, 0, s->stream>>>(in.p, out.p, n);
+    CU(in.alloc(n * 5)); CU(out.alloc(n * 3));
+    H2D(in.p, xyzaw, n * 5 * sizeof(float));
+    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s->stream>>>(in.p, out.p, (int) n);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(rgb, out.p, (size_t) n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    D2H(rgb, out.p, n * 3 * sizeof(float));
+    SYNC();
+    return B2_OK;
+}
+
+// HDRFilm::bitmap() on the device film of the last b2_render_device (no host round trip of the XYZAW film)
+int b2_develop_device(B2Scene *s, float *rgb) {
+    if (!s || !rgb) return fail(B2_ERR_INVALID, "b2_develop_device: null argument");
+    const size_t n = (size_t) s->d.film.crop_size[0] * (size_t) s->d.film.crop_size[1];
+    if (!s->film.p || s->film.n < n * 5) return fail(B2_ERR_INVALID, "b2_develop_device: no film (call b2_render_device first)");
+    DBuf<float> out;
+    CU(out.alloc(n * 3));
+    k_develop<<<(unsigned) ((n + 255) / 256), 256, 0, s->stream>>>(s->film.p, out.p, (int) n);
+    CU(cudaGetLastError());
+    D2H(rgb, out.p, n * 3 * sizeof(float));
+    SYNC();
     return B2_OK;
 }
 
@@ -883,14 +995,14 @@ int b2_stage_raygen(B2Scene *s, uint32_t n, const uint32_t *px, const uint32_t *
                     uint64_t base_seed, float *ray_o, float *ray_d, uint64_t *rng_state, float *pos) {
     if (!s || (n && (!px || !py || !seed_offset || !ray_o || !ray_d || !rng_state || !pos))) return fail(B2_ERR_INVALID, "b2_stage_raygen: null argument");
     if (n == 0) return B2_OK;
+    const size_t N = n;
     DBuf<uint32_t> dx, dy; DBuf<uint64_t> ds, dr; DBuf<float4> o, d; DBuf<float2> p;
-    CU(dx.alloc(n)); CU(dy.alloc(n)); CU(ds.alloc(n)); CU(dr.alloc(n)); CU(o.alloc(n)); CU(d.alloc(n)); CU(p.alloc(n));
-    CU(cudaMemcpy(dx.p, px, n * 4, cudaMemcpyHostToDevice)); CU(cudaMemcpy(dy.p, py, n * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(ds.p, seed_offset, n * 8, cudaMemcpyHostToDevice));
-    k_stage_raygen<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, dx.p, dy.p, ds.p, base_seed, o.p, d.p, dr.p, p.p);
+    CU(dx.alloc(N)); CU(dy.alloc(N)); CU(ds.alloc(N)); CU(dr.alloc(N)); CU(o.alloc(N)); CU(d.alloc(N)); CU(p.alloc(N));
+    H2D(dx.p, px, N * 4); H2D(dy.p, py, N * 4); H2D(ds.p, seed_offset, N * 8);
+    k_stage_raygen<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, dx.p, dy.p, ds.p, base_seed, o.p, d.p, dr.p, p.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(ray_o, o.p, n * 16, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(ray_d, d.p, n * 16, cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(rng_state, dr.p, n * 8, cudaMemcpyDeviceToHost)); CU(cudaMemcpy(pos, p.p, n * 8, cudaMemcpyDeviceToHost));
+    D2H(ray_o, o.p, N * 16); D2H(ray_d, d.p, N * 16); D2H(rng_state, dr.p, N * 8); D2H(pos, p.p, N * 8);
+    SYNC();
     return B2_OK;
 }
 
@@ -902,41 +1014,48 @@ static int stage_grid(const B2Scene *s, uint32_t n) {
 int b2_stage_intersect(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, float *hit, int32_t *inst) {
     if (!s || (n && (!ray_o || !ray_d || !hit))) return fail(B2_ERR_INVALID, "b2_stage_intersect: null argument");
     if (n == 0) return B2_OK;
+    const size_t N = n;
     DBuf<float4> o, d, h; DBuf<int32_t> di;
-    CU(o.alloc(n)); CU(d.alloc(n)); CU(h.alloc(n)); CU(di.alloc(n));
-    CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice));
-    if (s->d.n_instances) k_stage_intersect<true><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p, di.p);
-    else k_stage_intersect<false><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p, di.p);
+    CU(o.alloc(N)); CU(d.alloc(N)); CU(h.alloc(N)); CU(di.alloc(N));
+    H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16);
+    auto fn = s->d.n_instances ? k_stage_intersect<true> : k_stage_intersect<false>;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    fn<<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, h.p, di.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(hit, h.p, n * 16, cudaMemcpyDeviceToHost));
-    if (inst) CU(cudaMemcpy(inst, di.p, n * 4, cudaMemcpyDeviceToHost));
+    D2H(hit, h.p, N * 16);
+    if (inst) D2H(inst, di.p, N * 4);
+    SYNC();
     return B2_OK;
 }
 
 int b2_stage_occluded(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, uint8_t *occluded) {
     if (!s || (n && (!ray_o || !ray_d || !occluded))) return fail(B2_ERR_INVALID, "b2_stage_occluded: null argument");
     if (n == 0) return B2_OK;
+    const size_t N = n;
     DBuf<float4> o, d; DBuf<uint8_t> r;
-    CU(o.alloc(n)); CU(d.alloc(n)); CU(r.alloc(n));
-    CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice));
-    if (s->d.n_instances) k_stage_occluded<true><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
-    else k_stage_occluded<false><<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
+    CU(o.alloc(N)); CU(d.alloc(N)); CU(r.alloc(N));
+    H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16);
+    auto fn = s->d.n_instances ? k_stage_occluded<true> : k_stage_occluded<false>;
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    fn<<<stage_grid(s, n), 256, s->smem_bytes, s->stream>>>(s->d, n, o.p, d.p, r.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(occluded, r.p, n, cudaMemcpyDeviceToHost));
+    D2H(occluded, r.p, N);
+    SYNC();
     return B2_OK;
 }
 
 int b2_stage_si_fill(B2Scene *s, uint32_t n, const float *ray_o, const float *ray_d, const float *hit, const int32_t *inst, float *si) {
     if (!s || (n && (!ray_o || !ray_d || !hit || !si))) return fail(B2_ERR_INVALID, "b2_stage_si_fill: null argument");
     if (n == 0) return B2_OK;
+    const size_t N = n;
     DBuf<float4> o, d, h; DBuf<float> out; DBuf<int32_t> di;
-    CU(o.alloc(n)); CU(d.alloc(n)); CU(h.alloc(n)); CU(out.alloc((size_t) n * 16));
-    CU(cudaMemcpy(o.p, ray_o, n * 16, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(d.p, ray_d, n * 16, cudaMemcpyHostToDevice)); CU(cudaMemcpy(h.p, hit, n * 16, cudaMemcpyHostToDevice));
-    if (inst) { CU(di.alloc(n)); CU(cudaMemcpy(di.p, inst, n * 4, cudaMemcpyHostToDevice)); }
-    k_stage_si_fill<<<(n + 255) / 256, 256, 0, s->stream>>>(s->d, n, o.p, d.p, h.p, inst ? di.p : nullptr, out.p);
+    CU(o.alloc(N)); CU(d.alloc(N)); CU(h.alloc(N)); CU(out.alloc(N * 16));
+    H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16); H2D(h.p, hit, N * 16);
+    if (inst) { CU(di.alloc(N)); H2D(di.p, inst, N * 4); }
+    k_stage_si_fill<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, o.p, d.p, h.p, inst ? di.p : nullptr, out.p);
     CU(cudaGetLastError());
-    CU(cudaMemcpy(si, out.p, (size_t) n * 64, cudaMemcpyDeviceToHost));
+    D2H(si, out.p, N * 64);
+    SYNC();
     return B2_OK;
 }
 

@@ -1,8 +1,6 @@
 // b2_bvh.cpp — see b2_bvh.h
 #include <cstdlib>
 #include <thread>
-#include <chrono>
-#include <cstdio>
 #include "b2_bvh.h"
 
 #include <algorithm>
@@ -35,7 +33,15 @@ struct Builder {
     int kMaxLeaf = 2;
 
     // One node: bounds + binned-SAH split of idx[first, first+count). Returns false for a leaf.
-    bool make_node(uint32_t first, uint32_t count, Node2 &node, uint32_t &mid) {
+    // levels a balanced tree over `count` primitives needs below this node
+    int levels_needed(uint32_t count) const {
+        uint32_t leaves = (count + (uint32_t) kMaxLeaf - 1) / (uint32_t) kMaxLeaf;
+        int l = 0;
+        while ((1u << l) < leaves) ++l;
+        return l;
+    }
+
+    bool make_node(uint32_t first, uint32_t count, Node2 &node, uint32_t &mid, int depth) {
         Box box; box.reset();
         Box cbox; cbox.reset();
         for (uint32_t i = first; i < first + count; ++i) {
@@ -44,6 +50,16 @@ struct Builder {
         }
         node.box = box; node.first = first; node.count = count; node.left = node.right = -1;
         if (count <= (uint32_t) kMaxLeaf) return false;
+        if (depth + levels_needed(count) >= B2_BVH_MAX_DEPTH - 1) {
+            // level budget nearly spent: object-median split along the widest centroid axis (keeps the subtree balanced)
+            int ax = 0;
+            for (int k = 1; k < 3; ++k) if (cbox.hi[k] - cbox.lo[k] > cbox.hi[ax] - cbox.lo[ax]) ax = k;
+            mid = first + count / 2;
+            std::nth_element(idx.begin() + first, idx.begin() + mid, idx.begin() + first + count,
+                             [&](uint32_t a, uint32_t b) { float ca = cent[3 * a + ax], cb = cent[3 * b + ax]; return ca < cb || (ca == cb && a < b); });
+            node.count = 0;
+            return true;
+        }
         // binned SAH over the 3 axes
         float best_cost = std::numeric_limits<float>::infinity(); int best_axis = -1, best_bin = -1;
         for (int ax = 0; ax < 3; ++ax) {
@@ -83,28 +99,28 @@ struct Builder {
     }
 
     // serial build into `dst` (pre-order numbering, indices local to dst)
-    static int build_serial(Builder &b, std::vector<Node2> &dst, uint32_t first, uint32_t count) {
+    static int build_serial(Builder &b, std::vector<Node2> &dst, uint32_t first, uint32_t count, int depth) {
         int id = (int) dst.size();
         dst.emplace_back();
         Node2 n; uint32_t mid = 0;
-        bool inner = b.make_node(first, count, n, mid);
+        bool inner = b.make_node(first, count, n, mid, depth);
         dst[id] = n;
         if (!inner) return id;
-        int l = build_serial(b, dst, first, mid - first);
-        int r = build_serial(b, dst, mid, first + count - mid);
+        int l = build_serial(b, dst, first, mid - first, depth + 1);
+        int r = build_serial(b, dst, mid, first + count - mid, depth + 1);
         dst[id].left = l; dst[id].right = r;
         return id;
     }
 
     // Parallel build with the SAME result as the serial one: the two subtrees of the top `par_depth` levels are built
     // concurrently into their own arrays (they partition disjoint ranges of idx) and spliced in pre-order.
-    static void build_parallel(Builder &b, std::vector<Node2> &dst, uint32_t first, uint32_t count, int par_depth) {
-        if (par_depth <= 0 || count < 16384) { build_serial(b, dst, first, count); return; }
+    static void build_parallel(Builder &b, std::vector<Node2> &dst, uint32_t first, uint32_t count, int par_depth, int depth) {
+        if (par_depth <= 0 || count < 16384) { build_serial(b, dst, first, count, depth); return; }
         Node2 n; uint32_t mid = 0;
-        if (!b.make_node(first, count, n, mid)) { dst.push_back(n); return; }
+        if (!b.make_node(first, count, n, mid, depth)) { dst.push_back(n); return; }
         std::vector<Node2> L, R;
-        std::thread th([&] { build_parallel(b, L, first, mid - first, par_depth - 1); });
-        build_parallel(b, R, mid, first + count - mid, par_depth - 1);
+        std::thread th([&] { build_parallel(b, L, first, mid - first, par_depth - 1, depth + 1); });
+        build_parallel(b, R, mid, first + count - mid, par_depth - 1, depth + 1);
         th.join();
         const int base = (int) dst.size(), lo = base + 1, ro = base + 1 + (int) L.size();
         n.left = lo; n.right = ro;
@@ -120,7 +136,7 @@ struct Builder {
         int par_depth = 4;       // up to 16 concurrent subtrees
         if (const char *e = getenv("B2_BVH_THREADS")) { int t = atoi(e); par_depth = t <= 1 ? 0 : (t <= 2 ? 1 : (t <= 4 ? 2 : (t <= 8 ? 3 : 4))); }
         nodes.clear();
-        build_parallel(*this, nodes, first, count, par_depth);
+        build_parallel(*this, nodes, first, count, par_depth, 0);
         return 0;
     }
 };
@@ -175,9 +191,7 @@ void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh
         b.idx[i] = i;
     }
     b.nodes.reserve(2 * (size_t) n);
-    auto T0 = std::chrono::steady_clock::now();
     b.build(0, n);
-    auto T1 = std::chrono::steady_clock::now();
     out.order = b.idx;
 
     // conservative inflation of every child box: the fp32 triangle test can accept hits a few
@@ -224,8 +238,6 @@ void b2_build_bvh4_boxes(const std::vector<B2BvhBox> &boxes, int max_leaf, B2Bvh
         }
     }
     out.n_nodes = (uint32_t) (N.size() / 32);
-    if (getenv("B2_BVH_PROFILE")) { auto T2 = std::chrono::steady_clock::now();
-        fprintf(stderr, "bvh: build %.0f ms, collapse %.0f ms\n", std::chrono::duration<double, std::milli>(T1 - T0).count(), std::chrono::duration<double, std::milli>(T2 - T1).count()); }
 }
 
 #include "../../include/b2pt.h"

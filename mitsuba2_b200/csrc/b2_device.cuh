@@ -30,7 +30,10 @@ struct DEmitter {
     float cdf_sum, cdf_norm;
     uint32_t valid_first, valid_last;
     int32_t shape;              // 0: attached to a mesh; k > 0: analytic shape k - 1
-    float position[3];          // point light: trafo.translation() (point.cpp:92)
+    float position[3];          // point / spot: trafo.translation() (point.cpp:92, spot.cpp:108); directional: to_world * (0,0,1)
+    float to_object[12];        // spot: world -> local (3x4 row-major), spot.cpp:117
+    float cutoff_angle, beam_width, cos_cutoff, cos_beam, inv_transition;    // spot.cpp:88-95 (host-derived)
+    float _pad[3];
 };
 
 // analytic shapes (src/shapes/rectangle.cpp, sphere.cpp): 3x4 row-major transforms + the values update() derives
@@ -481,6 +484,25 @@ template <uint32_t F> B2_D float3 bsdf_eval(const B2Bsdf &b, const SI &si, float
             float3 res = v3(result * b.specular_reflectance[0], result * b.specular_reflectance[1], result * b.specular_reflectance[2]);
             return Fr * res;
         } else return zero;
+        case B2_BSDF_ROUGHDIELECTRIC: if constexpr ((F & F_ROUGH) != 0) {  // roughdielectric.cpp:312-384
+            if (cti == 0.f) return zero;
+            bool reflect = cti * cto > 0.f;
+            float eta = cti > 0.f ? b.eta : b2_rcp(b.eta), inv_eta = cti > 0.f ? b2_rcp(b.eta) : b.eta;
+            float3 m = normalize(si.wi + wo * (reflect ? 1.f : eta));
+            if (__float_as_uint(m.z) & 0x80000000u) m = -m;             // mulsign(m, cos_theta(m))
+            MF d = mf_make(b);
+            float D = mf_eval(d, m);
+            float Fr = fresnel_r(dot(si.wi, m), b.eta);
+            float G = mf_smith_g1(d, si.wi, m) * mf_smith_g1(d, wo, m);
+            if (reflect) {
+                float value = Fr * D * G / (4.f * fabsf(cti));
+                return v3(value * b.specular_reflectance[0], value * b.specular_reflectance[1], value * b.specular_reflectance[2]);
+            }
+            float scale = b2_sqr(inv_eta);
+            float dwm = dot(si.wi, m), dom = dot(wo, m);
+            float value = fabsf((scale * (1.f - Fr) * D * G * eta * eta * dwm * dom) / (cti * b2_sqr(dwm + eta * dom)));
+            return v3(value * b.specular_transmittance[0], value * b.specular_transmittance[1], value * b.specular_transmittance[2]);
+        } else return zero;
         case B2_BSDF_PLASTIC: if constexpr ((F & F_DIELECTRIC) != 0) {     // plastic.cpp:242-266
             if (!(cti > 0.f && cto > 0.f)) return zero;
             float f_i = fresnel_r(cti, b.eta), f_o = fresnel_r(cto, b.eta);
@@ -501,6 +523,21 @@ template <uint32_t F> B2_D float bsdf_pdf(const B2Bsdf &b, const SI &si, float3 
             if (!(cti > 0.f && cto > 0.f && dot(si.wi, m) > 0.f && dot(wo, m) > 0.f)) return 0.f;
             MF d = mf_make(b);
             return mf_eval(d, m) * mf_smith_g1(d, si.wi, m) / (4.f * cti);
+        } else return 0.f;
+        case B2_BSDF_ROUGHDIELECTRIC: if constexpr ((F & F_ROUGH) != 0) {  // roughdielectric.cpp:386-452
+            if (cti == 0.f) return 0.f;
+            bool reflect = cti * cto > 0.f;
+            float eta = cti > 0.f ? b.eta : b2_rcp(b.eta);
+            float3 m = normalize(si.wi + wo * (reflect ? 1.f : eta));
+            if (__float_as_uint(m.z) & 0x80000000u) m = -m;
+            if (!(dot(si.wi, m) * cti > 0.f && dot(wo, m) * cto > 0.f)) return 0.f;
+            float dwh_dwo = reflect ? b2_rcp(4.f * dot(wo, m)) : (eta * eta * dot(wo, m)) / b2_sqr(dot(si.wi, m) + eta * dot(wo, m));
+            MF d = mf_make(b);
+            float3 wi_s = cti < 0.f ? -si.wi : si.wi;                   // mulsign(wi, cos_theta(wi))
+            float prob = mf_eval(d, m) * mf_smith_g1(d, wi_s, m) * fabsf(dot(wi_s, m)) / wi_s.z;   // distr.pdf, microfacet.h:214-223
+            float Fr = fresnel_r(dot(si.wi, m), b.eta);
+            prob *= reflect ? Fr : 1.f - Fr;
+            return prob * fabsf(dwh_dwo);
         } else return 0.f;
         case B2_BSDF_PLASTIC: if constexpr ((F & F_DIELECTRIC) != 0) {     // plastic.cpp:268-293
             if (!(cti > 0.f && cto > 0.f)) return 0.f;
@@ -560,6 +597,36 @@ template <uint32_t F> B2_D float3 bsdf_sample(const B2Bsdf &b, const SI &si, flo
                            fresnel_conductor(c, b.cond_eta[2], b.cond_k[2]));
             float3 wv = v3(weight * b.specular_reflectance[0], weight * b.specular_reflectance[1], weight * b.specular_reflectance[2]);
             return active ? Fr * wv : zero;
+        } else return zero;
+        case B2_BSDF_ROUGHDIELECTRIC: if constexpr ((F & F_ROUGH) != 0) {  // roughdielectric.cpp:203-310
+            bool active = cti != 0.f;
+            MF d = mf_make(b);
+            float3 wi_s = cti < 0.f ? -si.wi : si.wi;
+            float pdf; float3 m = mf_sample(d, wi_s, s2x, s2y, pdf);
+            active = active && pdf != 0.f;
+            float Fr, cos_theta_t, eta_it, eta_ti;
+            fresnel(dot(si.wi, m), b.eta, Fr, cos_theta_t, eta_it, eta_ti);
+            bool selected_r = sample1 <= Fr && active;
+            float3 weight = v3(1.f, 1.f, 1.f);
+            pdf *= selected_r ? Fr : 1.f - Fr;
+            bs.eta = selected_r ? 1.f : eta_it;
+            float dwh_dwo = 0.f;
+            float dwm = dot(si.wi, m);
+            if (selected_r) {
+                float s = 2.f * dwm;                                 // reflect(wi, m) = fmsub(m, 2 dot(wi, m), wi)
+                bs.wo = v3(b2_fma(m.x, s, -si.wi.x), b2_fma(m.y, s, -si.wi.y), b2_fma(m.z, s, -si.wi.z));
+                weight = weight * rgb3(b.specular_reflectance);
+                dwh_dwo = b2_rcp(4.f * dot(bs.wo, m));
+            } else if (active) {
+                float s = b2_fma(dwm, eta_ti, cos_theta_t);          // refract(wi, m, cos_theta_t, eta_ti), fresnel.h:310-313
+                bs.wo = v3(b2_fma(m.x, s, -(si.wi.x * eta_ti)), b2_fma(m.y, s, -(si.wi.y * eta_ti)), b2_fma(m.z, s, -(si.wi.z * eta_ti)));
+                float fct = b2_sqr(eta_ti);
+                weight = weight * v3(fct * b.specular_transmittance[0], fct * b.specular_transmittance[1], fct * b.specular_transmittance[2]);
+                dwh_dwo = (b2_sqr(bs.eta) * dot(bs.wo, m)) / b2_sqr(dwm + bs.eta * dot(bs.wo, m));
+            }
+            weight = weight * mf_smith_g1(d, bs.wo, m);
+            bs.pdf = pdf * fabsf(dwh_dwo);
+            return active ? weight : zero;
         } else return zero;
         case B2_BSDF_CONDUCTOR: if constexpr ((F & F_DIELECTRIC) != 0) {   // conductor.cpp:197-240
             if (!(cti > 0.f)) return zero;
@@ -840,6 +907,30 @@ template <uint32_t F> B2_D float3 emitter_sample_direction(const Tables &sc, con
             ds.d = ds.d * inv_dist;
             float w = b2_sqr(inv_dist);
             return v3(em.radiance[0] * w, em.radiance[1] * w, em.radiance[2] * w);
+        }
+        if (em.type == B2_EMITTER_SPOT) {                             // SpotLight::sample_direction + falloff_curve, spot.cpp:97-160
+            ds.p = v3(em.position[0], em.position[1], em.position[2]);
+            ds.n = v3(0.f, 0.f, 0.f);
+            ds.pdf = 1.f; ds.delta = true;
+            ds.d = ds.p - ref_p;
+            ds.dist = sqrtf(dot(ds.d, ds.d));
+            float inv_dist = b2_rcp(ds.dist);
+            ds.d = ds.d * inv_dist;
+            float3 local_dir = normalize(xf_vector(em.to_object, -ds.d));
+            float cos_theta = local_dir.z;
+            float f = cos_theta >= em.cos_beam ? 1.f : (em.cutoff_angle - b2_safe_acos(cos_theta)) * em.inv_transition;
+            float3 res = v3(em.radiance[0], em.radiance[1], em.radiance[2]);
+            if (!(cos_theta >= em.cos_beam)) res = res * f;
+            if (cos_theta <= em.cos_cutoff) res = v3(0.f, 0.f, 0.f);
+            return res * (inv_dist * inv_dist);
+        }
+        if (em.type == B2_EMITTER_DIRECTIONAL) {                      // DirectionalEmitter::sample_direction, directional.cpp:107-134
+            float3 d = v3(em.position[0], em.position[1], em.position[2]);
+            float dist = 2.f * env.radius;
+            ds.p = ref_p - d * dist;
+            ds.n = d; ds.pdf = 1.f; ds.delta = true;
+            ds.d = -d; ds.dist = dist;
+            return v3(em.radiance[0], em.radiance[1], em.radiance[2]);
         }
         if (em.shape > 0) return shape_sample_direction(sc, em, ref_p, sx, sy, ds);
     }

@@ -1,42 +1,45 @@
 // b2_kernels.cuh — the wavefront stage kernels (sm_100a).
 //
-// One wavefront iteration = TWO launches per lane set over the SoA lane queues (a lane slot keeps
-// its index for its whole life, so every queue access is a direct, coalesced float4 access):
+// One wavefront iteration = TWO launches per lane set over the SoA lane queues. A lane slot keeps its
+// index for its whole life (its RNG stream, work item and film pixel travel with it); between the stages
+// the live lanes are COMPACTED by warp ballot into two dense index lists, so that every shading warp runs
+// one kind of work on 32 lanes:
 //
-//   K2+K3(+K6)  k_trace / k_trace_inst
-//                          closest hit of every live lane's ray (BVH4 traversal or the flat leaf scan +
-//                          Mesh::ray_intersect_triangle, mesh.h:194-226) AND any-hit visibility of the
-//                          emitter samples queued by the previous k_shade (scene.cpp:203-207):
-//                          `result += contribution`, and for a path that ended on that bounce the
-//                          film put of the completed sample. k_trace_inst is the persistent-warp,
-//                          dynamic-fetch variant for instanced scenes.
-//   K4+K1+K6+K5 k_shade    SI fill fused with one iteration of PathIntegrator::sample's loop body
-//                          (path.cpp:124-208); a path that ends is put on the film
-//                          (ImageBlock::put, imageblock.cpp:79-172) and the lane regenerates the
-//                          next camera sample of its work item in place (render_sample,
-//                          integrator.cpp:233-262; perspective.cpp:182-216) or fetches the next
-//                          work item; warp-ballot compaction of the emitter samples into the
-//                          dense shadow queue (one atomic per warp)
+//   K2+K3+K5    k_trace / k_trace_inst
+//                          closest hit of every lane that has a ray (BVH4 traversal or the flat leaf scan +
+//                          Mesh::ray_intersect_triangle, mesh.h:194-226), any-hit visibility of the emitter
+//                          samples queued by the previous k_shade (scene.cpp:203-207: unoccluded =>
+//                          `result += contribution`), and the compaction: a lane whose path goes on (hit and
+//                          depth < max_depth, path.cpp:131,147) is appended to the CONTINUE list, a lane whose
+//                          path ends here (miss / depth limit) to the TERMINATE list — one 64-bit atomic per warp.
+//                          k_trace_inst is the persistent-warp, dynamic-fetch variant for instanced scenes.
+//   K4+K1+K6    k_shade    warps [0, nC/32): SI fill + one iteration of PathIntegrator::sample's loop body
+//                          (path.cpp:124-208) for 32 CONTINUE lanes: emitter hit + MIS, Russian roulette,
+//                          emitter sampling -> dense shadow queue (warp-ballot append), BSDF sampling -> next ray.
+//                          warps [nC/32, ..): 32 TERMINATE lanes: last emitter / environment contribution,
+//                          ImageBlock::put (imageblock.cpp:79-172), and regeneration of the lane with the next
+//                          camera sample of its work item (render_sample, integrator.cpp:233-262;
+//                          perspective.cpp:182-216) or the next work item from the global counter.
+//                          A path that dies inside the loop body (roulette, zero throughput) is parked: its last
+//                          emitter sample is resolved by the next k_trace, and the lane joins the next TERMINATE list.
 //   (k_init = the regenerate step alone, run once to fill the lanes)
 #pragma once
 #include "b2_device.cuh"
 
 struct Queues {
-    float4 *ray_o, *ray_d;      // (o.xyz, mint), (d.xyz, maxt); maxt < 0 marks a retired lane   32 B
+    float4 *ray_o, *ray_d;      // (o.xyz, mint), (d.xyz, maxt); maxt < 0: no ray to trace (retired or parked lane)   32 B
     float4 *hit;                // (t, u, v, slot bits); t = +inf: miss                           16 B
     int32_t *hit_inst;          // instance index of the hit (-1: top-level shape); NULL for flat scenes
     float4 *tp;                 // (throughput.rgb, eta)                                          16 B
     float4 *res;                // (result.rgb, pdf of the last BSDF sample)                      16 B
     uint4 *st;                  // (rng.lo, rng.hi, work item, depth|flags|samples_left)          16 B
+    uint32_t *pixel;            // x | y << 16 of the lane's work item (crop-relative)             4 B
     float2 *pos;                // position_sample, only for wide (non-box) filters
-    // shadow queue (dense): ray + (contrib.rgb, lane bits | FINAL) [+ final entries only:
-    // (result.rgb, film word) and, for wide filters, position_sample]
-    float4 *sh_o, *sh_d, *sh_c, *sh_r;
-    uint32_t *sh_f;             // final entries: st.w flags (alpha, box-filter target)
-    float2 *sh_p;               // final entries, wide filters: position_sample
-    uint32_t *cnt;              // per lane set: [CNT_SHADOW + parity] shadow counts, [CNT_ALIVE] live lanes
+    float4 *sh_o, *sh_d, *sh_c; // dense shadow queue: ray + (contrib.rgb, lane bits)
+    uint32_t *list[2];          // per iteration parity: CONTINUE lanes from the front, TERMINATE lanes from the back   8 B
+    uint32_t *cnt;              // per lane set: see CNT_*
     uint32_t *work;             // global work-item counter (shared by the lane sets)
-    unsigned long long *stats;  // [0] samples, [1] segments, [2] shadow rays, [3] invalid
+    unsigned long long *stats;  // ST_*
     float *film;                // crop_h x crop_w x 5 (X,Y,Z,A,W)
     const uint32_t *item_pixel; // per work item of ONE pass: x | y << 16 (crop-relative)
     const uint32_t *item_seed;  // spiral_index * bs^2 + morton index
@@ -53,8 +56,11 @@ struct Queues {
     float smp_inv_count, smp_inv_res, smp_inv_res_y;
 };
 
-enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */ };
-enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_PUT_SHADOW = 4 };
+// q.cnt words of one lane set (B2_CNT_WORDS each)
+enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */,
+       CNT_LIST = 4 /* and 6: 64-bit (n_continue | n_terminate << 32) per iteration parity */ };
+#define B2_CNT_WORDS 8
+enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES = 4, ST_TRIS = 5 };
 
 // st.w layout
 #define STW_DEPTH(w)     ((w) & 0xffu)
@@ -63,8 +69,8 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_PUT_SH
 #define STW_FILM_DX      0x400u      // box filter: sample lands on pixel x-1
 #define STW_FILM_DY      0x800u      //             ... y-1
 #define STW_FILM_DROP    0x1000u     // sample falls outside its block (imageblock.cpp:166)
+#define STW_PARKED       0x2000u     // the path ended inside the loop body: the lane only waits for its film put
 #define STW_LEFT(w)      ((w) >> 16)
-#define SH_FINAL         0x80000000u // shadow entry of a path that ended: k_shadow puts the sample on the film
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
 
@@ -156,6 +162,10 @@ B2_D bool tri_isect(float3 p0, float3 e1, float3 e2, const Ray &ray, float tmax,
 // of the warp are still traversing and the caller can hand new rays to the idle lanes
 // (persistent-warp dynamic ray fetch, Aila & Laine 2009).
 #define B2_TRAV_DONE 0x7fffffff
+// Traversal stacks are fixed-size local arrays (only the touched entries ever occupy cache lines). A BVH4 level
+// pushes at most 3 entries; the host builder bounds the depth so that 3 * depth + 2 <= B2_STACK (b2_bvh.cpp).
+#define B2_STACK 128
+#define B2_MAX_BVH_DEPTH ((B2_STACK - 2) / 3)     /* 42 levels; the builders never exceed it (b2_bvh.h: B2_BVH_MAX_DEPTH) */
 #ifndef B2_REFILL_THRESHOLD
 #define B2_REFILL_THRESHOLD 22
 #endif
@@ -169,11 +179,12 @@ struct Trav {
     Hit best;
     int inst;                   // instance being traversed (-1: top level) — part of the tie key
     bool any_hit;
+    uint32_t n_nodes, n_tris;   // BVH4 nodes visited / primitives tested (only maintained by the COUNT instantiations)
 
     // (the traversal stack is a separate local array so that the scalar state stays in registers)
     B2_D void init(const DScene &sc, const Ray &r, int *stack) {
         best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu; best.inst = -1;
-        any_hit = false;
+        any_hit = false; n_nodes = 0; n_tris = 0;
         restart(sc, r, stack, sc.n_top_tris ? 0 : B2_TRAV_DONE, -1);
     }
     // (re)start on another BVH (a shapegroup's, with the ray in object space) keeping the best hit so far
@@ -200,10 +211,11 @@ struct Trav {
     // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the same
     // kind of work. Returns when the ray is finished, or (can_yield) when the warp has thinned out.
     // SHP: the scene has analytic shapes (compile-time, so that plain triangle scenes do not carry the sphere / rectangle code)
-    template <bool ANY, bool SHP>
+    template <bool ANY, bool SHP, bool COUNT = false>
     B2_D void run(const DScene &sc, const SmemScene &sm, int *stack, bool can_yield) {
         while (cur != B2_TRAV_DONE) {
             while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) {
+                if constexpr (COUNT) ++n_nodes;
                 float4 nx, ny, nz, fx, fy, fz, chf;
                 if ((uint32_t) cur < sc.smem_nodes) {
                     const float4 *np = sm.nodes + 8 * cur;
@@ -235,6 +247,7 @@ struct Trav {
             }
             while (cur < 0) {
                 uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
+                if constexpr (COUNT) n_tris += count;
                 for (uint32_t s = first; s < first + count; ++s) {
                     float4 a0, a1, a2;
                     if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
@@ -269,8 +282,8 @@ struct Trav {
 // tests at full lane utilisation.
 B2_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-template <bool ANY>
-B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
+template <bool ANY, bool COUNT = false>
+B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best, uint32_t *counters = nullptr) {
     best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu; best.inst = -1;
     float tmax = ray.maxt;
     float dx = copysignf(fmaxf(fabsf(ray.d.x), 1e-20f), ray.d.x), dy = copysignf(fmaxf(fabsf(ray.d.y), 1e-20f), ray.d.y),
@@ -278,6 +291,7 @@ B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, H
     const float idx = rcp_approx(dx), idy = rcp_approx(dy), idz = rcp_approx(dz);
     const float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
     const uint32_t n = sc.n_flat_leaves;
+    if constexpr (COUNT) counters[0] += (n + 3u) / 4u;            // n leaf boxes = n / 4 BVH4 nodes' worth of box tests
     uint32_t mask = 0; float near_t = B2_INF; uint32_t near_l = 0;
     {
         const float tlim = tmax * 1.0000004f;
@@ -310,6 +324,7 @@ B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, H
         mask &= ~(1u << l);
         uint32_t code = __float_as_uint(sm.flat[2 * l].w);
         uint32_t s0 = code & 0x07ffffffu, cnt = (code >> 27) & 0xfu;
+        if constexpr (COUNT) counters[1] += cnt;
         for (uint32_t s = s0; s < s0 + cnt; ++s) {
             float4 a0 = sm.tris[3 * s], a1 = sm.tris[3 * s + 1], a2 = sm.tris[3 * s + 2];
             float t, u, v;
@@ -331,12 +346,12 @@ B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, H
 // with the ray mapped to object space — origin as a point, direction as an UN-normalised vector,
 // mint/maxt unchanged so t stays in world units (instance.cpp:107-117).
 // INST is a compile-time switch so that flat scenes do not pay registers for the two-level code.
-template <bool ANY, bool INST, bool SHP>
-B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best) {
-    if (!INST && sc.n_flat_leaves) return traverse_flat<ANY>(sc, sm, ray, best);      // warp-uniform
-    int stack[40];
+template <bool ANY, bool INST, bool SHP, bool COUNT = false>
+B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best, uint32_t *counters = nullptr) {
+    if (!INST && sc.n_flat_leaves) return traverse_flat<ANY, COUNT>(sc, sm, ray, best, counters);      // warp-uniform
+    int stack[B2_STACK];
     Trav tr; tr.init(sc, ray, stack);
-    tr.run<ANY, SHP>(sc, sm, stack, false);
+    tr.run<ANY, SHP, COUNT>(sc, sm, stack, false);
     if (INST && sc.n_instances && !(ANY && tr.any_hit)) {
         float dx = fabsf(ray.d.x) > 1e-20f ? ray.d.x : (ray.d.x < 0.f ? -1e-20f : 1e-20f);
         float dy = fabsf(ray.d.y) > 1e-20f ? ray.d.y : (ray.d.y < 0.f ? -1e-20f : 1e-20f);
@@ -345,10 +360,11 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
         float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
         // front-to-back over the instance boxes: nearest child first, the others are pushed with their
         // entry distance and culled on pop against the best hit found so far
-        int tstack[32]; float tdist[32]; int tsp = 0;
+        int tstack[B2_STACK]; float tdist[B2_STACK]; int tsp = 0;
         int cur = (int) sc.tlas_root;
         for (;;) {
             if (cur >= 0) {
+                if constexpr (COUNT) ++tr.n_nodes;
                 const float4 *gp = sc.nodes + 8 * (size_t) cur;
                 float4 lox = __ldg(gp), loy = __ldg(gp + 1), loz = __ldg(gp + 2), hix = __ldg(gp + 3), hiy = __ldg(gp + 4),
                        hiz = __ldg(gp + 5), chf = __ldg(gp + 6);
@@ -374,8 +390,8 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
                     Ray ro; ro.o = xf_point(in.to_object, ray.o); ro.d = xf_vector(in.to_object, ray.d);
                     ro.mint = ray.mint; ro.maxt = ray.maxt;
                     tr.restart(sc, ro, stack, in.root, (int) ii);
-                    tr.run<ANY, false>(sc, sm, stack, false);       // (shapegroups hold meshes only)
-                    if (ANY && tr.any_hit) { best = tr.best; return true; }
+                    tr.run<ANY, false, COUNT>(sc, sm, stack, false);       // (shapegroups hold meshes only)
+                    if (ANY && tr.any_hit) { best = tr.best; if constexpr (COUNT) { counters[0] += tr.n_nodes; counters[1] += tr.n_tris; } return true; }
                 }
             }
             // pop the next entry that can still contain a closer hit
@@ -388,6 +404,7 @@ B2_D bool traverse(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &b
         }
     }
     best = tr.best;
+    if constexpr (COUNT) { counters[0] += tr.n_nodes; counters[1] += tr.n_tris; }
     return ANY ? tr.any_hit : best.t < B2_INF;
 }
 
@@ -450,66 +467,78 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
     return true;
 }
 
-// ---- K2 + K3 (+K6): one traversal launch per iteration ---------------------------------------------
-// Work items [0, n_slots) are the live lanes' rays (closest hit, BVH4 + Mesh::ray_intersect_triangle,
-// mesh.h:194-226); items [n_slots, n_slots + n_shadow) are the emitter samples queued by the previous
-// k_shade (any hit, scene.cpp:203-207): unoccluded => `result += contribution` (path.cpp:171), and for
-// a path that ended on that bounce the completed sample is put on the film. Both kinds are
-// independent (a lane's shadow entry only touches `res`, which the closest-hit part does not read),
-// so they share one launch: one tail and one shared-memory staging instead of two.
-// (A persistent-warp / dynamic-ray-fetch variant of the traversal was measured in round 1 and was
-// slower on the small-scene workload: 104 vs 93 ms per step.)
-template <bool INST, bool WIDE, bool SHP>
+// ---- K2 + K3 + K5: one traversal launch per iteration ----------------------------------------------
+// Warps stride over the lane slots: closest hit (BVH4 + Mesh::ray_intersect_triangle, mesh.h:194-226) of every
+// lane that has a ray, then the COMPACTION of the live lanes by warp ballot: a lane whose path goes on (it hit
+// something and depth < max_depth: path.cpp:131,147-149) is appended to the front of q.list[parity], a lane
+// whose path ends with this segment to its back (one 64-bit atomic per warp reserves both ranges).
+// Items [n_slots, n_slots + n_shadow) are the emitter samples queued by the previous k_shade (any hit,
+// scene.cpp:203-207): unoccluded => `result += contribution` (path.cpp:171). Both kinds of ray are independent
+// (a shadow entry only touches `res`, which the closest-hit part does not read), so they share one launch:
+// one tail and one shared-memory staging instead of two.
+B2_D void list_append(const Queues &q, int parity, uint32_t lane, bool cont, bool term, uint32_t mask) {
+    // `mask`: the lanes of the warp executing this call together
+    const uint32_t mc = __ballot_sync(mask, cont), mx = __ballot_sync(mask, term);
+    if ((mc | mx) == 0) return;
+    const int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((int) lane_id() == leader)
+        base = atomicAdd((unsigned long long *) (q.cnt + CNT_LIST + 2 * parity), (unsigned long long) __popc(mc) | ((unsigned long long) __popc(mx) << 32));
+    base = __shfl_sync(mask, base, leader);
+    const uint32_t below = (1u << lane_id()) - 1u;
+    if (cont) q.list[parity][(uint32_t) base + __popc(mc & below)] = lane;
+    if (term) q.list[parity][q.n_slots - 1u - ((uint32_t) (base >> 32) + __popc(mx & below))] = lane;
+}
+
+template <bool INST, bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    const uint32_t n_shadow = q.cnt[CNT_SHADOW + parity];               // filled by the previous k_shade
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];         // filled by the previous k_shade
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.cnt[CNT_SHADOW + (parity ^ 1)] = 0;                            // the next k_shade appends there
+        q.cnt[CNT_SHADOW + parity] = 0;                                  // the next k_shade appends there
+        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;   // consumed by the previous k_shade
         atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
-    const uint32_t total = q.n_slots + n_shadow;
-    uint32_t n_seg = 0, n_put = 0, n_bad = 0;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint32_t n_seg = 0;
+    uint32_t counters[2] = { 0u, 0u };
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
+        const uint32_t i = base + lane_id();
+        bool cont = false, term = false;
         if (i < q.n_slots) {
             float4 rd = q.ray_d[i];
-            if (rd.w < 0.f) continue;                                  // retired lane
-            float4 ro = q.ray_o[i];
-            Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-            Hit h; traverse<false, INST, SHP>(sc, sm, ray, h);
-            q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
-            if (INST) q.hit_inst[i] = h.inst;
-            ++n_seg;
-        } else {
-            uint32_t j = i - q.n_slots;
-            float4 ro = q.sh_o[j], rd = q.sh_d[j], c = q.sh_c[j];
-            Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-            Hit h;
-            bool occluded = traverse<true, INST, SHP>(sc, sm, ray, h);
-            uint32_t lw = __float_as_uint(c.w);
-            if (lw & SH_FINAL) {
-                float4 r = q.sh_r[j];
-                float2 p = WIDE ? q.sh_p[j] : make_float2(0.f, 0.f);
-                float3 L = v3(r);
-                if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
-                uint32_t pix = __float_as_uint(r.w);
-                uint32_t flags = q.sh_f[j];
-                bool ok = film_put<WIDE>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
-                ++n_put; n_bad += ok ? 0 : 1;
-            } else if (!occluded) {
-                float4 r = q.res[lw];
-                r.x += c.x; r.y += c.y; r.z += c.z;
-                q.res[lw] = r;
+            if (rd.w >= 0.f) {                                             // (retired / parked lanes carry maxt < 0)
+                float4 ro = q.ray_o[i];
+                const uint32_t stw = q.st[i].w;
+                Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+                Hit h; traverse<false, INST, SHP, COUNT>(sc, sm, ray, h, counters);
+                q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+                if (INST) q.hit_inst[i] = h.inst;
+                ++n_seg;
+                cont = h.t < B2_INF && STW_DEPTH(stw) < (uint32_t) q.max_depth;
+                term = !cont;
             }
+        }
+        list_append(q, parity, i, cont, term, 0xffffffffu);
+    }
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_shadow; j += gridDim.x * blockDim.x) {
+        float4 ro = q.sh_o[j], rd = q.sh_d[j];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Hit h;
+        if (!traverse<true, INST, SHP, COUNT>(sc, sm, ray, h, counters)) {
+            float4 c = q.sh_c[j];
+            const uint32_t lw = __float_as_uint(c.w);
+            float4 r = q.res[lw];
+            r.x += c.x; r.y += c.y; r.z += c.z;
+            q.res[lw] = r;
         }
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
-    if (lane_id() == 0) {
-        if (n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
-        if (n_put) atomicAdd(&q.stats[ST_PUT_SHADOW], (unsigned long long) n_put);
-        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
-        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
+    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+    if constexpr (COUNT) {
+        uint32_t a = __reduce_add_sync(0xffffffffu, counters[0]), b = __reduce_add_sync(0xffffffffu, counters[1]);
+        if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
     }
 }
 
@@ -526,24 +555,25 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
 // lexicographic (t, key) minimum, so the result is the same as traverse<ANY, true>() bit for bit.
 #define B2_TRAV_POP 0x7ffffffe
 #define B2_TRAV_NEEDPOP 0x7ffffffd
-#define B2_INST_STACK 64
+#define B2_INST_STACK (2 * B2_STACK)      /* TLAS + BLAS levels on ONE stack (+ POP markers) */
 #ifndef B2_INST_MINBLOCKS
 #define B2_INST_MINBLOCKS 4
 #endif
 
-template <bool WIDE, bool SHP>
+template <bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    const uint32_t n_shadow = q.cnt[CNT_SHADOW + parity];
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.cnt[CNT_SHADOW + (parity ^ 1)] = 0;
+        q.cnt[CNT_SHADOW + parity] = 0;
+        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;
         atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
     const uint32_t total = q.n_slots + n_shadow;
-    uint32_t n_seg = 0, n_put = 0, n_bad = 0;
+    uint32_t n_seg = 0;
     int stack[B2_INST_STACK]; float sdist[B2_INST_STACK];
-    Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f;
+    Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f; tr.n_nodes = 0; tr.n_tris = 0;
     uint32_t item = 0;
     bool busy = false, exhausted = false;
     for (;;) {
@@ -581,6 +611,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
             const bool any_ray = item >= q.n_slots;
             // ---- inner nodes (either level) ----
             while ((uint32_t) tr.cur < (uint32_t) B2_TRAV_NEEDPOP) {
+                if constexpr (COUNT) ++tr.n_nodes;
                 float4 nx, ny, nz, fx, fy, fz, chf;
                 if ((uint32_t) tr.cur < sc.smem_nodes) {
                     const float4 *np = sm.nodes + 8 * tr.cur;
@@ -628,6 +659,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     tr.cur = in.root;
                 } else {
                     const int key_inst = tr.inst < 0 ? -1 : tr.inst;
+                    if constexpr (COUNT) tr.n_tris += count;
                     for (uint32_t s = first; s < first + count; ++s) {
                         float4 a0 = __ldg(&sc.tri_isect[3 * (size_t) s]), a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]), a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]);
                         float t, u, v;
@@ -666,7 +698,8 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     if (sdist[tr.sp] <= tr.tmax * 1.0000004f) { tr.cur = c; break; }
                 }
             }
-            // ---- finished: write the result, the lane becomes idle ----
+            // ---- finished: write the result, the lane becomes idle (the compaction is k_classify's: rays finish here in
+            // arbitrary order, and lists in lane order keep the gathers of k_shade on consecutive addresses) ----
             if (tr.cur == B2_TRAV_DONE) {
                 busy = false;
                 if (!any_ray) {
@@ -674,36 +707,36 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     q.hit[item] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
                     q.hit_inst[item] = h.inst;
                     ++n_seg;
-                } else {
+                } else if (!tr.any_hit) {
                     const uint32_t j = item - q.n_slots;
-                    const bool occluded = tr.any_hit;
                     float4 c = q.sh_c[j];
-                    uint32_t lw = __float_as_uint(c.w);
-                    if (lw & SH_FINAL) {
-                        float4 r = q.sh_r[j];
-                        float2 p = WIDE ? q.sh_p[j] : make_float2(0.f, 0.f);
-                        float3 L = v3(r);
-                        if (!occluded) { L.x += c.x; L.y += c.y; L.z += c.z; }
-                        uint32_t pix = __float_as_uint(r.w);
-                        uint32_t flags = q.sh_f[j];
-                        bool ok = film_put<WIDE>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, flags, p, L, (flags & STW_ALPHA) != 0);
-                        ++n_put; n_bad += ok ? 0 : 1;
-                    } else if (!occluded) {
-                        float4 r = q.res[lw];
-                        r.x += c.x; r.y += c.y; r.z += c.z;
-                        q.res[lw] = r;
-                    }
+                    const uint32_t lw = __float_as_uint(c.w);
+                    float4 r = q.res[lw];
+                    r.x += c.x; r.y += c.y; r.z += c.z;
+                    q.res[lw] = r;
                 }
             }
         }
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-    n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
-    if (lane_id() == 0) {
-        if (n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
-        if (n_put) atomicAdd(&q.stats[ST_PUT_SHADOW], (unsigned long long) n_put);
-        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
-        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
+    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+    if constexpr (COUNT) {
+        uint32_t a = __reduce_add_sync(0xffffffffu, tr.n_nodes), b = __reduce_add_sync(0xffffffffu, tr.n_tris);
+        if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
+    }
+}
+
+// K5 for k_trace_inst: the CONTINUE / TERMINATE lists of k_trace, built in lane order from the hits it wrote
+__global__ void __launch_bounds__(256) k_classify(Queues q, int parity) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
+        const uint32_t i = base + lane_id();
+        bool cont = false, term = false;
+        if (i < q.n_slots && q.ray_d[i].w >= 0.f) {
+            cont = q.hit[i].x < B2_INF && STW_DEPTH(q.st[i].w) < (uint32_t) q.max_depth;
+            term = !cont;
+        }
+        list_append(q, parity, i, cont, term, 0xffffffffu);
     }
 }
 
@@ -809,7 +842,7 @@ template <bool EXT> B2_D float2 smp_next_2d(const Queues &q, uint64_t &rng, uint
 // `item`/`left`/`rng` are the lane's work-item state (left == 0: `w` is the freshly fetched work
 // item). Returns false if the work is exhausted (lane retires).
 template <bool EXT>
-B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_t w, uint32_t pix, uint32_t &item, uint32_t &left,
+B2_D bool regen_sample(const DScene &sc, const Queues &q, uint32_t lane, uint32_t w, uint32_t &pix, uint32_t &item, uint32_t &left,
                        uint64_t &rng, uint2 &sm, Ray &ray, uint32_t &stw) {
     const B2Film &film = sc.film;
     if (left == 0) {
@@ -860,14 +893,15 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
         uint32_t lane = base + lane_id();
         bool valid = lane < q.n_slots;
         uint32_t w = warp_append(q.work, valid);
-        uint32_t item = 0, left = 0, stw = 0; uint64_t rng = 0; Ray ray; uint2 sm = make_uint2(0u, 0u);
-        bool alive = valid && regen_sample<EXT>(sc, q, lane, w, 0u, item, left, rng, sm, ray, stw);
+        uint32_t item = 0, left = 0, stw = 0, pix = 0; uint64_t rng = 0; Ray ray; uint2 sm = make_uint2(0u, 0u);
+        bool alive = valid && regen_sample<EXT>(sc, q, lane, w, pix, item, left, rng, sm, ray, stw);
         if (alive) {
             q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
             q.ray_d[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
             q.tp[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
             q.res[lane] = make_float4(0.f, 0.f, 0.f, 1.f);
             q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), item, stw);
+            q.pixel[lane] = pix;
             if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
         } else if (valid)
             q.ray_d[lane] = make_float4(0.f, 0.f, 0.f, -1.f);
@@ -899,167 +933,231 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
     return tb;
 }
 
-// ---- K4 (+K1, K5, K6): shade -----------------------------------------------------------------
+// ---- K4 + K1 + K6: shade ---------------------------------------------------------------------------
 #ifndef B2_SHADE_MINBLOCKS
 #define B2_SHADE_MINBLOCKS 3
 #endif
+
+// 32 CONTINUE lanes: one iteration of PathIntegrator::sample's loop body (path.cpp:124-208). Called by whole warps.
+template <uint32_t F>
+B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane) {
+    constexpr bool EXT = (F & F_TEX) != 0;
+    // all queue loads are issued up front (one round trip)
+    const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
+    float4 rd = q.ray_d[ld], ro = q.ray_o[ld], h = q.hit[ld], tpe = q.tp[ld], rs = q.res[ld];
+    uint4 st = q.st[ld];
+    bool park = false, shadow = false, flip = false;
+    float4 sho, shd, shc;
+    float4 nro, nrd;                 // next ray
+    uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+    uint2 sm = make_uint2(0u, 0u);
+    if constexpr (EXT) if (q.smp) sm = q.smp[ld];
+    const int depth = (int) STW_DEPTH(st.w);
+    float3 throughput = v3(tpe), result = v3(rs);
+    float eta = tpe.w, bs_pdf = rs.w;
+    SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
+    // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling (the lane hit something and depth < max_depth) ----
+    if (valid) {
+        si_fill<EXT>(tb, __float_as_uint(h.w), h.x, h.y, h.z, v3(ro), v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
+        if (depth == 1) st.w |= STW_ALPHA;                                       // path.cpp:121
+        // ---- intersection with emitters (path.cpp:128-129) ----
+        if (si.emitter >= 0) {
+            float emission_weight = 1.f;
+            if (depth > 1) {                                                    // path.cpp:194-205, records.h:168-174
+                float emitter_pdf = 0.f;
+                if (!(st.w & STW_DELTA)) {
+                    float3 dd = si.p - v3(ro);
+                    float dist = sqrtf(dot(dd, dd));
+                    dd = dd * b2_rcp(dist);
+                    emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, v3(ro), dd, si.sh_n, dist);
+                }
+                emission_weight = mis_weight(bs_pdf, emitter_pdf);
+            }
+            const DEmitter &em = tb.emitters[si.emitter];
+            float3 ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
+            result = result + (throughput * emission_weight) * ev;
+        }
+        bool active = true;                                                     // path.cpp:131
+        if (depth > q.rr_depth) {                                               // path.cpp:137-141
+            float qq = b2_min(hmax(throughput) * b2_sqr(eta), .95f);
+            active = smp_next_1d<EXT>(q, rng, sm) < qq;
+            throughput = throughput * b2_rcp(qq);
+        }
+        if (!active) park = true;                                               // path.cpp:147-149
+        else {
+            bool smooth;
+            const B2Bsdf &bsdf = bsdf_side<F>(tb, si, flip, smooth);            // (twosided: side record, wi.z mirrored)
+            if (smooth) {                                                          // path.cpp:153-172
+                float2 se = smp_next_2d<EXT>(q, rng, sm); float sx = se.x, sy = se.y;
+                DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, sx, sy, ds);
+                if (ds.pdf != 0.f) {
+                    float3 wo = to_local(si, ds.d);
+                    if constexpr (EXT) if (flip) wo.z = -wo.z;
+                    float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo, bsdf_reflectance<F>(tb, bsdf, si));
+                    float bpdf = bsdf_pdf<F>(bsdf, si, wo);
+                    float mis = mis_weight(ds.pdf, bpdf);
+                    if constexpr (EXT) if (ds.delta) mis = 1.f;                // path.cpp:170
+                    float3 c = ((throughput * mis) * bsdf_val) * emitter_val;
+                    if (any_nonzero(c)) {                                       // visibility: scene.cpp:203-207
+                        shadow = true;
+                        sho = make_float4(si.p.x, si.p.y, si.p.z, B2_RAY_EPS * (1.f + hmax_abs(si.p)));
+                        shd = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.dist * (1.f - B2_SHADOW_EPS));
+                        shc = make_float4(c.x, c.y, c.z, __uint_as_float(lane));
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue. The atomic is issued
+    // here and its result is only consumed after phase 2 (latency hidden). ----
+    const uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
+    uint32_t sq_base = 0;
+    if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
+    // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
+    if (valid && !park) {
+        const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
+        float2 s2 = smp_next_2d<EXT>(q, rng, sm); float s2x = s2.x, s2y = s2.y;
+        float s1 = smp_next_1d<EXT>(q, rng, sm);
+        BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs, bsdf_reflectance<F>(tb, bsdf, si));
+        if constexpr (EXT) if (flip) bs.wo.z = -bs.wo.z;                       // twosided.cpp:122
+        throughput = throughput * bsdf_val;
+        if (!any_nonzero(throughput)) park = true;                             // path.cpp:182-184
+        else {
+            eta *= bs.eta;
+            float3 nd = to_world(si, bs.wo);                                    // interaction.h:58-61
+            nro = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
+            nrd = make_float4(nd.x, nd.y, nd.z, B2_INF);
+            bs_pdf = bs.pdf;
+            st.w = (st.w & ~(0xffu | STW_DELTA)) | (uint32_t) (depth + 1) | (bs.delta ? STW_DELTA : 0u);
+        }
+    }
+    __syncwarp();
+    // ---- a path that ended here is parked: no ray, the next k_trace resolves its last emitter sample, and the lane
+    // joins the TERMINATE list of the next iteration (appended behind the entries the next k_trace adds) ----
+    const uint32_t pk_mask = __ballot_sync(0xffffffffu, park);
+    if (pk_mask) {
+        unsigned long long pb = 0;
+        if (lane_id() == 0) pb = atomicAdd((unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)), (unsigned long long) __popc(pk_mask) << 32);
+        pb = __shfl_sync(0xffffffffu, pb, 0);
+        if (park) q.list[parity ^ 1][q.n_slots - 1u - ((uint32_t) (pb >> 32) + __popc(pk_mask & ((1u << lane_id()) - 1u)))] = lane;
+    }
+    if (sh_mask) {
+        const uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
+        if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
+    }
+    if (valid) {
+        if (park) { nrd = make_float4(0.f, 0.f, 0.f, -1.f); st.w |= STW_PARKED; }
+        else q.ray_o[lane] = nro;
+        q.ray_d[lane] = nrd;
+        q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
+        q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
+        q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+        if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
+    }
+}
+
+// 32 TERMINATE lanes: the path ends with this segment (miss, or a hit at the depth limit: path.cpp:128-149 up to the
+// break), or it was parked by shade_continue. Film put (ImageBlock::put) and regeneration. Called by whole warps.
+template <uint32_t F>
+B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, bool valid, uint32_t lane, uint32_t &n_put, uint32_t &n_bad) {
+    constexpr bool EXT = (F & F_TEX) != 0;
+    const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
+    uint4 st = q.st[ld];
+    float4 h = q.hit[ld], tpe = q.tp[ld], rs = q.res[ld];
+    uint32_t pix = q.pixel[ld];
+    uint32_t item = st.z, left = STW_LEFT(st.w);
+    // the work-item fetch is issued first: its latency hides behind the emitter evaluation and the film put
+    const bool need = valid && left == 0;
+    const uint32_t w = warp_append(q.work, need);
+    uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
+    uint2 sm = make_uint2(0u, 0u);
+    if constexpr (EXT) if (q.smp) sm = q.smp[ld];
+    float3 result = v3(rs);
+    if (valid && !(st.w & STW_PARKED)) {
+        const int depth = (int) STW_DEPTH(st.w);
+        const bool hit_valid = h.x < B2_INF;
+        const float3 throughput = v3(tpe);
+        const float bs_pdf = rs.w;
+        int emitter = -1;
+        if (hit_valid) emitter = (int) __float_as_uint(B2_LD(&tb.tri_nrm[3 * __float_as_uint(h.w) + 1]).w);
+        else if constexpr ((F & F_ENV) != 0) emitter = sc.env.index;              // scene->environment(), scene.h:243-253
+        if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                           // path.cpp:121
+        if (emitter >= 0) {                                                        // path.cpp:128-129
+            const float4 rd = q.ray_d[lane], ro = q.ray_o[lane];
+            SI si; si.emitter = emitter; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
+            if (hit_valid) si_fill<EXT>(tb, __float_as_uint(h.w), h.x, h.y, h.z, v3(ro), v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
+            float emission_weight = 1.f;
+            if (depth > 1) {                                                      // path.cpp:194-205, records.h:168-174
+                float emitter_pdf = 0.f;
+                if (!(st.w & STW_DELTA)) {
+                    float3 dd = si.p - v3(ro);
+                    float dist = sqrtf(dot(dd, dd));
+                    dd = dd * b2_rcp(dist);
+                    if (!hit_valid) dd = v3(rd);                                  // d[!it.is_valid()] = -it.wi
+                    emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, v3(ro), dd, si.sh_n, dist);
+                }
+                emission_weight = mis_weight(bs_pdf, emitter_pdf);
+            }
+            float3 ev;
+            bool miss = false;
+            if constexpr ((F & F_ENV) != 0) miss = !hit_valid;
+            if (miss) ev = env_eval(sc.env, v3(rd));                              // envmap.cpp:134-147
+            else {
+                const DEmitter &em = tb.emitters[si.emitter];
+                ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
+            }
+            result = result + (throughput * emission_weight) * ev;
+        }
+        // Russian roulette still draws its sample before the depth test ends the path (path.cpp:137-149): the sampler
+        // stream of the work item continues into the next camera sample
+        if (depth > q.rr_depth && hit_valid) (void) smp_next_1d<EXT>(q, rng, sm);
+    }
+    // ---- K6: ImageBlock::put ----
+    if (valid) {
+        float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
+        bool ok = film_put<(F & F_WIDE) != 0>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, result, (st.w & STW_ALPHA) != 0);
+        ++n_put; n_bad += ok ? 0 : 1;
+    }
+    // ---- K1: regenerate ----
+    bool retire = false;
+    if (valid) {
+        Ray ray; uint32_t stw;
+        if (regen_sample<EXT>(sc, q, lane, w, pix, item, left, rng, sm, ray, stw)) {
+            q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
+            q.ray_d[lane] = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
+            q.tp[lane] = make_float4(1.f, 1.f, 1.f, 1.f);
+            q.res[lane] = make_float4(0.f, 0.f, 0.f, 1.f);
+            q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), item, stw);
+            q.pixel[lane] = pix;
+            if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
+        } else { retire = true; q.ray_d[lane] = make_float4(0.f, 0.f, 0.f, -1.f); }
+    }
+    const uint32_t n_ret = __popc(__ballot_sync(0xffffffffu, retire));
+    if (lane_id() == 0 && n_ret) atomicSub(&q.cnt[CNT_ALIVE], n_ret);
+}
+
 template <uint32_t F>
 __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Tables tb = stage_shade_tables(sc, smem_raw);
-    uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    uint32_t n_put = 0, n_bad = 0;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_FETCH] = 0;       // ray counter of the next k_trace_inst
-    for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
-        uint32_t lane = base + lane_id();
-        // all queue loads are issued up front (one round trip), retired lanes included
-        uint32_t ld = lane < q.n_slots ? lane : q.n_slots - 1;
-        float4 rd = q.ray_d[ld], ro = q.ray_o[ld], h = q.hit[ld], tpe = q.tp[ld], rs = q.res[ld];
-        uint4 st = q.st[ld];
-        uint32_t pix = __ldg(&q.item_pixel[st.z % q.n_items_pass]);       // pixel of the lane's work item
-        bool valid = lane < q.n_slots && rd.w >= 0.f;
-        bool term = false, shadow = false, do_bsdf = false, flip = false;
-        float4 sho, shd, shc;
-        float4 nro, nrd;                 // next ray
-        uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
-        constexpr bool EXT = (F & F_TEX) != 0;
-        uint2 sm = make_uint2(0u, 0u);
-        if constexpr (EXT) if (q.smp) sm = q.smp[ld];
-        int depth = (int) STW_DEPTH(st.w);
-        float3 throughput = v3(tpe), result = v3(rs);
-        float eta = tpe.w, bs_pdf = rs.w;
-        SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
-        // ---- phase 1: SI fill, emitter hit, Russian roulette, emitter sampling ----
-        if (valid) {
-            bool hit_valid = h.x < B2_INF;
-            if (hit_valid) si_fill<(F & F_TEX) != 0>(tb, __float_as_uint(h.w), h.x, h.y, h.z, v3(ro), v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
-            else if constexpr ((F & F_ENV) != 0) si.emitter = sc.env.index;                // scene->environment(), scene.h:243-253
-            if (depth == 1 && hit_valid) st.w |= STW_ALPHA;                        // path.cpp:121
-            // ---- intersection with emitters (path.cpp:128-129) ----
-            if (si.emitter >= 0) {
-                float emission_weight = 1.f;
-                if (depth > 1) {                                                    // path.cpp:194-205, records.h:168-174
-                    float emitter_pdf = 0.f;
-                    if (!(st.w & STW_DELTA)) {
-                        float3 dd = si.p - v3(ro);
-                        float dist = sqrtf(dot(dd, dd));
-                        dd = dd * b2_rcp(dist);
-                        if (!hit_valid) dd = v3(rd);                                // d[!it.is_valid()] = -it.wi
-                        emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, v3(ro), dd, si.sh_n, dist);
-                    }
-                    emission_weight = mis_weight(bs_pdf, emitter_pdf);
-                }
-                float3 ev;
-                bool miss = false;
-                if constexpr ((F & F_ENV) != 0) miss = !hit_valid;
-                if (miss) ev = env_eval(sc.env, v3(rd));                            // envmap.cpp:134-147
-                else {
-                    const DEmitter &em = tb.emitters[si.emitter];
-                    ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
-                }
-                result = result + (throughput * emission_weight) * ev;
-            }
-            bool active = hit_valid;                                                // path.cpp:131
-            if (depth > q.rr_depth) {                                               // path.cpp:137-141
-                float qq = b2_min(hmax(throughput) * b2_sqr(eta), .95f);
-                if (active) active = smp_next_1d<EXT>(q, rng, sm) < qq;
-                throughput = throughput * b2_rcp(qq);
-            }
-            if ((uint32_t) depth >= (uint32_t) q.max_depth || !active) term = true;   // path.cpp:147-149
-            else {
-                do_bsdf = true;
-                bool smooth;
-                const B2Bsdf &bsdf = bsdf_side<F>(tb, si, flip, smooth);            // (twosided: side record, wi.z mirrored)
-                if (smooth) {                                                          // path.cpp:153-172
-                    float2 se = smp_next_2d<EXT>(q, rng, sm); float sx = se.x, sy = se.y;
-                    DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, sx, sy, ds);
-                    if (ds.pdf != 0.f) {
-                        float3 wo = to_local(si, ds.d);
-                        if constexpr ((F & F_TEX) != 0) if (flip) wo.z = -wo.z;
-                        float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo, bsdf_reflectance<F>(tb, bsdf, si));
-                        float bpdf = bsdf_pdf<F>(bsdf, si, wo);
-                        float mis = mis_weight(ds.pdf, bpdf);
-                        if constexpr ((F & F_TEX) != 0) if (ds.delta) mis = 1.f;                // path.cpp:170
-                        float3 c = ((throughput * mis) * bsdf_val) * emitter_val;
-                        if (any_nonzero(c)) {                                       // visibility: scene.cpp:203-207
-                            shadow = true;
-                            sho = make_float4(si.p.x, si.p.y, si.p.z, B2_RAY_EPS * (1.f + hmax_abs(si.p)));
-                            shd = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.dist * (1.f - B2_SHADOW_EPS));
-                            shc = make_float4(c.x, c.y, c.z, __uint_as_float(lane));
-                        }
-                    }
-                }
-            }
+    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
+    const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
+    const uint32_t n_cont = (uint32_t) n_list, n_term = (uint32_t) (n_list >> 32);
+    const uint32_t wc = (n_cont + 31u) >> 5, wt = (n_term + 31u) >> 5;
+    uint32_t n_put = 0, n_bad = 0;
+    for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
+        if (wi < wc) {
+            const uint32_t k = wi * 32u + lane_id();
+            const bool valid = k < n_cont;
+            shade_continue<F>(sc, tb, q, parity, valid, valid ? q.list[parity][k] : 0u);
+        } else {
+            const uint32_t k = (wi - wc) * 32u + lane_id();
+            const bool valid = k < n_term;
+            shade_terminate<F>(sc, tb, q, valid, valid ? q.list[parity][q.n_slots - 1u - k] : 0u, n_put, n_bad);
         }
-        __syncwarp();
-        // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue. The
-        // atomic is issued here and its result is only consumed after phase 2 (latency hidden). ----
-        uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
-        uint32_t sq_base = 0;
-#ifdef B2_EXPERIMENT_NO_SHADOW_ATOMIC      // timing experiment only (WRONG results): how much does the atomic cost?
-        if (lane_id() == 0 && sh_mask) { sq_base = base; if (base == 0) q.cnt[CNT_SHADOW + parity] = q.n_slots / 2; }
-#else
-        if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
-#endif
-        // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
-        if (do_bsdf) {
-            const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
-            float2 s2 = smp_next_2d<EXT>(q, rng, sm); float s2x = s2.x, s2y = s2.y;
-            float s1 = smp_next_1d<EXT>(q, rng, sm);
-            BS bs; float3 bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2x, s2y, bs, bsdf_reflectance<F>(tb, bsdf, si));
-            if constexpr ((F & F_TEX) != 0) if (flip) bs.wo.z = -bs.wo.z;          // twosided.cpp:122
-            throughput = throughput * bsdf_val;
-            if (!any_nonzero(throughput)) term = true;                             // path.cpp:182-184
-            else {
-                eta *= bs.eta;
-                float3 nd = to_world(si, bs.wo);                                    // interaction.h:58-61
-                nro = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
-                nrd = make_float4(nd.x, nd.y, nd.z, B2_INF);
-                bs_pdf = bs.pdf;
-                st.w = (st.w & ~(0xffu | STW_DELTA)) | (uint32_t) (depth + 1) | (bs.delta ? STW_DELTA : 0u);
-            }
-        }
-        __syncwarp();
-        uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
-        // ---- path ended: film put (now, or by k_shadow once the emitter sample is resolved) ----
-        uint32_t item = st.z, left = STW_LEFT(st.w);
-        if (term) {
-            if (shadow) {
-                shc.w = __uint_as_float(lane | SH_FINAL);
-                q.sh_r[sq] = make_float4(result.x, result.y, result.z, __uint_as_float(pix));
-                q.sh_f[sq] = st.w;
-                if (q.pos) q.sh_p[sq] = q.pos[lane];
-            } else {
-                float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
-                bool ok = film_put<(F & F_WIDE) != 0>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, result, (st.w & STW_ALPHA) != 0);
-                ++n_put; n_bad += ok ? 0 : 1;
-            }
-        }
-        if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
-        // ---- K1: regenerate the lanes whose path ended ----
-        bool need = term && left == 0;
-        uint32_t w = warp_append(q.work, need);
-        bool retire = false;
-        if (term) {
-            Ray ray; uint32_t stw;
-            if (regen_sample<EXT>(sc, q, lane, w, pix, item, left, rng, sm, ray, stw)) {
-                nro = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);
-                nrd = make_float4(ray.d.x, ray.d.y, ray.d.z, ray.maxt);
-                throughput = v3(1.f, 1.f, 1.f); eta = 1.f; result = v3(0.f, 0.f, 0.f); bs_pdf = 1.f;
-                st.z = item; st.w = stw;
-            } else { retire = true; nrd = make_float4(0.f, 0.f, 0.f, -1.f); nro = nrd; }
-        }
-        if (valid) {
-            q.ray_o[lane] = nro; q.ray_d[lane] = nrd;
-            if (!retire) {
-                q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
-                q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
-                q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
-                if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
-            }
-        }
-        uint32_t n_ret = __popc(__ballot_sync(0xffffffffu, retire));
-        if (lane_id() == 0 && n_ret) atomicSub(&q.cnt[CNT_ALIVE], n_ret);
     }
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {

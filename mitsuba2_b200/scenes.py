@@ -162,8 +162,10 @@ def veach_mis(host, width=1280, height=720, rfilter="box"):
 # instantiated on an n^3 lattice with a per-instance rotation drawn from a seeded generator;
 # one 2-triangle area emitter above; diffuse 0.5.
 # ---------------------------------------------------------------------------------------------
-def instanced_grid(host, width=2048, height=2048, grid=71, lattice=10, seed=1234, rfilter="box"):
-    """grid x grid vertices -> 2 (grid-1)^2 triangles per instance (71 -> 9800), lattice^3 instances."""
+def instanced_grid(host, width=2048, height=2048, grid=71, lattice=10, seed=1234, rfilter="box", flatten=False):
+    """grid x grid vertices -> 2 (grid-1)^2 triangles per instance (71 -> 9800), lattice^3 instances.
+    flatten: instead of instancing, ONE mesh holding every instance's transformed copy (lattice^3 * 9800 triangles:
+    10 M for the defaults) — the 'flattened C5' the BVH builders are timed on."""
     sb = abi.SceneBuffers()
     diffuse = sb.add_diffuse((0.5, 0.5, 0.5))
     light_b = sb.add_diffuse((0.0, 0.0, 0.0))
@@ -175,8 +177,10 @@ def instanced_grid(host, width=2048, height=2048, grid=71, lattice=10, seed=1234
     idx = np.arange(grid * grid).reshape(grid, grid)
     a, b, c, d = idx[:-1, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel(), idx[1:, :-1].ravel()
     faces = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
-    gm = sb.add_mesh(pos, faces, None, diffuse)
-    g = sb.add_shapegroup([gm])
+    if not flatten:
+        gm = sb.add_mesh(pos, faces, None, diffuse)
+        g = sb.add_shapegroup([gm])
+    flat_pos = []
     rng = np.random.default_rng(seed)
     span = float(lattice) * 1.5
     for i in range(lattice ** 3):
@@ -188,7 +192,15 @@ def instanced_grid(host, width=2048, height=2048, grid=71, lattice=10, seed=1234
                       [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
         M = np.eye(4); M[:3, :3] = R
         M[:3, 3] = [(ix + 0.5) * 1.5 - span / 2, (iy + 0.5) * 1.5 - span / 2, (iz + 0.5) * 1.5 - span / 2]
-        sb.add_instance(g, M.astype(np.float32))
+        if flatten:
+            M32 = M.astype(np.float32)
+            flat_pos.append((pos @ M32[:3, :3].T + M32[:3, 3]).astype(np.float32))
+        else:
+            sb.add_instance(g, M.astype(np.float32))
+    if flatten:
+        nv = len(pos); ni = len(flat_pos)
+        all_faces = (faces[None, :, :] + (np.arange(ni, dtype=np.uint32) * np.uint32(nv))[:, None, None]).reshape(-1, 3).astype(np.uint32)
+        sb.add_mesh(np.concatenate(flat_pos), all_faces, None, diffuse)
     # area emitter above the lattice, facing down
     s = span * 0.35; yl = span / 2 + 1.0
     lp = np.array([[-s, yl, -s], [s, yl, -s], [s, yl, s], [-s, yl, s]], np.float32)

@@ -174,14 +174,23 @@ def test_scene_description_is_validated_like_the_reference():
     assert "bsdf 0: unsupported type 42" in str(_create_error(sb))
     sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughconductor(sample_visible=False)})
     assert "sample_visible = false is not supported" in str(_create_error(sb))
-    # rough dielectric: restated and pinned in the oracle only (round 1) -- the product must say so, not render black
+    # rough dielectric, spot and directional emitters have a CUDA path (round 2): a valid description passes validation and
+    # only then fails for lack of a device (code 4) on a CPU box
     sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughdielectric(0.1, "ggx", 1.5, 1.0)})
-    assert "unsupported type 6" in str(_create_error(sb))
-    # spot / directional emitters: oracle only in round 1
+    assert _create_error(sb).code == 4
+    sb = scenes.cbox(H, 16, 16, materials={"box": lambda s: s.add_roughdielectric(0.1, "ggx", 1.5, 1.0)})
+    [b for b in sb.bsdfs if b.type == abi.BSDF_ROUGHDIELECTRIC][0].distribution = 7
+    assert "invalid distribution" in str(_create_error(sb))
     sb = scenes.cbox(H, 16, 16); sb.add_spot_light(np.eye(4), (1, 1, 1))
-    assert "only area, envmap, constant and point emitters are supported" in str(_create_error(sb))
+    assert _create_error(sb).code == 4
     sb = scenes.cbox(H, 16, 16); sb.add_directional_light(np.eye(4), (1, 1, 1))
-    assert "only area, envmap, constant and point emitters are supported" in str(_create_error(sb))
+    assert _create_error(sb).code == 4
+    sb = scenes.cbox(H, 16, 16); sb.add_point_light((0, 0, 0), (1, 1, 1)); sb.emitters[-1].type = 9
+    assert "emitters are supported" in str(_create_error(sb))
+    # shapegroups must cover the non-top-level meshes exactly
+    sb = scenes.cbox(H, 16, 16, instances=[np.eye(4, dtype=np.float32)])
+    d = sb.desc(); d.n_top_meshes -= 1; h = C.c_void_p()
+    assert api.lib().b2_scene_create(C.byref(d), C.byref(h)) == 1 and b"cover the meshes" in api.lib().b2_last_error()
     # film limits
     sb = scenes.cbox(H, 16, 16); sb.film.crop_size[0] = 0
     assert "film crop size" in str(_create_error(sb))

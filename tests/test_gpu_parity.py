@@ -123,7 +123,9 @@ def test_instances_intersect_vs_bruteforce(b2, oracle):
                                   "cbox_64_spp16_multijitter", "cbox_64_spp8_multijitter_nojitter",
                                   "cbox_64_spp16_shapes_textured", "cbox_64_spp16_ldsampler",
                                   "cbox_64_spp16_constant", "cbox_64_spp16_constant_area",
-                                  "cbox_64_spp16_point", "cbox_64_spp16_point_area"])
+                                  "cbox_64_spp16_point", "cbox_64_spp16_point_area",
+                                  "cbox_64_spp16_roughglass_beckmann", "cbox_64_spp16_roughglass_ggx",
+                                  "cbox_64_spp16_spot", "cbox_64_spp16_directional"])
 def test_render_bitexact_single_pass(b2, oracle, name):
     """Box filter + one pass: one lane owns a pixel and adds its samples in order, exactly like
     render_block -> the whole XYZAW film must match the oracle bit for bit."""

@@ -1,0 +1,100 @@
+"""Parity AT THE SIZES THE NUMBERS ARE QUOTED ON (BASELINE.json configs[1..3]): the unmodified reference CLI renders the
+configuration with its own `path` integrator on this box's host cores, then again with `<integrator type="b2path">`
+(plugins/b2path.so -> libb2pt.so -> GPU), and the two developed images are compared: rel-L2 (north_star: 1e-4) plus
+the flip statistics of DESIGN.md 5 (a 'flipped' pixel = one whose value differs by more than 1e-3 of the image mean,
+i.e. a path that took another branch because of a last-ulp difference; SURVEY App. C: the reference against ITSELF
+built with other compiler flags flips 17 of 65 536 pixels on C1).
+
+Each case writes its statistics to gpurun_out/parity_<name>.json (copied to profiles/ by the builder)."""
+import json
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tests.test_plugin_dropin import DIST, _read_pfm, _run, needs_matpreview, needs_ref   # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def _compare(tmp_path, name, xml_of, bounds):
+    from tests import golden_cases as G
+    import time
+    t0 = time.time(); r0, ref_out = _run(xml_of("path"), tmp_path, "ref_" + name); t_ref = time.time() - t0
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    t0 = time.time(); r1, b2_out = _run(xml_of("b2path"), tmp_path, "b2_" + name); t_b2 = time.time() - t0
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    s.update(case=name, reference_cli_seconds=t_ref, b2path_cli_seconds=t_b2)
+    m = re.search(r"b2path: .*", r1.stdout + r1.stderr)
+    if m:
+        s["b2path_log"] = m.group(0)[:300]
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        json.dump(s, open(os.path.join(out_dir, f"parity_{name}.json"), "w"), indent=1)
+    print("PARITY", json.dumps(s))
+    for k, v in bounds.items():
+        assert s[k] <= v, (k, s)
+    return s
+
+
+@needs_ref
+def test_parity_cbox_1024_spp256(tmp_path):
+    """BASELINE configs[1]: cbox 1024x1024, 256 spp, max_depth 6, box filter — the configuration bench.py quotes."""
+    import bench
+
+    def xml(integrator):
+        return bench._ref_cbox_xml(1024, 256, 16, 6).replace('<integrator type="path">', f'<integrator type="{integrator}">')
+    _compare(tmp_path, "cbox_1024_spp256", xml, dict(rel_l2=1e-4))
+
+
+@needs_ref
+def test_parity_cbox_xml_as_shipped(tmp_path):
+    """resources/data/scenes/cbox/cbox.xml exactly as shipped (256x256, 128 spp, gaussian filter, <spectrum> reflectances
+    pre-integrated to rgb by the reference's XML loader); only the integrator type and the output format are edited."""
+    d = os.path.join(ROOT, "oracle", "_ref", "scenes", "cbox")
+    src = open(os.path.join(d, "cbox.xml")).read()
+
+    def xml(integrator):
+        x = src.replace('<integrator type="path">', f'<integrator type="{integrator}">')
+        x = x.replace('value="meshes/', f'value="{d}/meshes/')
+        return x.replace('<rfilter type="gaussian"/>', '<rfilter type="gaussian"/><string name="pixel_format" value="rgb"/>'
+                         '<string name="component_format" value="float32"/><string name="file_format" value="pfm"/>')
+    # gaussian taps: a flipped path moves 16 pixels; fp32 atomics reorder the sums (rel 1e-7)
+    _compare(tmp_path, "cbox_xml_shipped", xml, dict(rel_l2_unflipped=1e-5, median_rel=2e-6))
+
+
+@needs_ref
+@needs_matpreview
+def test_parity_matpreview_ggx_1920x1080(tmp_path):
+    """BASELINE configs[2]: the shipped matpreview.xml (61.6 k triangles of matpreview.serialized, envmap.exr, checkerboard
+    plane) with the material swapped for a GGX rough conductor (alpha 0.1), 1920x1080, 64 spp, max_depth 6."""
+    d = os.path.join(ROOT, "oracle", "_ref", "scenes", "matpreview")
+    src = open(os.path.join(d, "matpreview.xml")).read()
+
+    def xml(integrator):
+        x = src.replace('<integrator type="path"/>', f'<integrator type="{integrator}"><integer name="max_depth" value="6"/></integrator>')
+        x = re.sub(r'<bsdf type="plastic" id="bsdf-matpreview">.*?</bsdf>',
+                   '<bsdf type="roughconductor" id="bsdf-matpreview"><string name="distribution" value="ggx"/><float name="alpha" value="0.1"/></bsdf>',
+                   x, flags=re.S)
+        x = x.replace('name="width" value="683"', 'name="width" value="1920"').replace('name="height" value="512"', 'name="height" value="1080"')
+        x = x.replace('value="envmap.exr"', f'value="{d}/envmap.exr"').replace('value="matpreview.serialized"', f'value="{d}/matpreview.serialized"')
+        return x.replace('<string name="pixel_format" value="rgb" />', '<string name="pixel_format" value="rgb" /><string name="component_format" value="float32"/>'
+                         '<string name="file_format" value="pfm"/>')
+    _compare(tmp_path, "matpreview_ggx_1920x1080_spp64", xml, dict(rel_l2_unflipped=1e-4, median_rel=5e-6))
+
+
+@needs_ref
+def test_parity_veach_1280x720(tmp_path):
+    """BASELINE configs[3] class: the synthesised veach-mis scene (four area emitters, dielectric + rough-conductor plates;
+    mitsuba2_b200.scenes.veach_mis_meshes written as OBJ files and loaded by the reference's own OBJ loader), 1280x720, 64 spp."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden as MG
+
+    def xml(integrator):
+        return MG.veach_xml(str(tmp_path), 1280, 720, 64).replace('<integrator type="path">', f'<integrator type="{integrator}">')
+    _compare(tmp_path, "veach_1280x720_spp64", xml, dict(rel_l2_unflipped=1e-4, median_rel=5e-6))
