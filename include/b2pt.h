@@ -227,6 +227,8 @@ enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJI
 
 #define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */
 #define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */
+#define B2_FLAG_PERSISTENT_TRACE 8u /* traverse with the persistent-warp / dynamic-ray-fetch kernel (k_trace_inst) also on scenes
+                                   without instances (always used with instances; ignored for tiny scenes on the flat leaf scan) */
 #define B2_FLAG_COUNT_BVH 4u    /* run the counting instantiation of the traversal kernel -> B2Stats.n_nodes_visited /
                                    n_tris_tested (BVH bytes = nodes * 128 B + tris * 48 B); slower, for measurement */
 
@@ -300,6 +302,33 @@ B2_API int b2_stage_occluded(B2Scene *scene, uint32_t n, const float *ray_o, con
 /* si[n*16] = p3, n3, sh_n3, sh_s3, wi3, (bsdf index as bits) */
 B2_API int b2_stage_si_fill(B2Scene *scene, uint32_t n, const float *ray_o, const float *ray_d,
                             const float *hit, const int32_t *inst, float *si);
+
+/* shade: ONE iteration of PathIntegrator::sample's loop body (path.cpp:124-208) — SI fill, emitter hit + MIS weight, Russian
+   roulette, emitter sampling, BSDF sampling, spawn_ray — i.e. one k_shade launch over n caller-provided lanes. Every lane
+   must have hit something (hit t < inf, as b2_stage_intersect returns it) with depth < max_depth: the lanes the traversal
+   stage puts on its CONTINUE list. Independent sampler only.
+     in/out  ray_o, ray_d [n*4]       the segment's ray -> the next ray (maxt < 0: the path ended inside the loop body)
+     in      hit [n*4], inst [n]      (t, u, v, prim bits); instance index or NULL for flat scenes
+     in/out  throughput_eta [n*4]     (throughput.rgb, eta)
+     in/out  result_pdf [n*4]         (result.rgb, pdf of the last BSDF sample — feeds the MIS weight of the next emitter hit)
+     in/out  rng_state [n]            PCG32 state (default stream), as b2_stage_raygen returns it
+     in/out  depth_flags [n]          depth (1 = camera segment) | B2_LANE_*
+     out     n_shadow, sh_o/sh_d/sh_c [n*4]   the dense emitter-sample queue: ray + (contribution.rgb, lane index bits),
+                                       in the (arbitrary) order the warps appended them
+   Uses params->max_depth / rr_depth only. */
+#define B2_LANE_ALPHA  0x100u    /* out: the camera ray hit something (valid_ray, path.cpp:121)          */
+#define B2_LANE_DELTA  0x200u    /* in/out: the last BSDF sample was a delta lobe                          */
+#define B2_LANE_PARKED 0x2000u   /* out: Russian roulette or a zero throughput ended the path in this call */
+B2_API int b2_stage_shade(B2Scene *scene, const B2RenderParams *params, uint32_t n, float *ray_o, float *ray_d,
+                          const float *hit, const int32_t *inst, float *throughput_eta, float *result_pdf,
+                          uint64_t *rng_state, uint32_t *depth_flags,
+                          uint32_t *n_shadow, float *sh_o, float *sh_d, float *sh_c);
+/* film_put: ImageBlock::put (imageblock.cpp:79-172) of n samples: sample i belongs to the image block of pixel (px, py)
+   (crop-relative) and lands at pos[2i..] = position_sample (film coordinates); rgb is converted to XYZ like render_sample
+   does (integrator.cpp:273). xyzaw[crop_h * crop_w * 5] receives the accumulated film (box: 5 reductions per sample,
+   wider filters: the LUT taps), n_invalid the samples rejected by the validity rule (imageblock.cpp:85-109). */
+B2_API int b2_stage_film_put(B2Scene *scene, uint32_t block_size, uint32_t n, const uint32_t *px, const uint32_t *py,
+                             const float *pos, const float *rgb, const uint8_t *alpha, float *xyzaw, uint32_t *n_invalid);
 
 /* ---- host-side helpers (C++ mirrors of reference host code; no GPU needed) --------------- */
 B2_API int b2_host_look_at(const float origin[3], const float target[3], const float up[3],

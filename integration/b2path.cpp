@@ -36,9 +36,29 @@
 
 #include <b2pt.h>
 
+#include <mitsuba/render/kdtree.h>
+
 NAMESPACE_BEGIN(mitsuba)
 
 namespace {
+// The unmodified reference has no accessor for a ShapeGroup's children or the Scene's shapegroup list (INTEGRATION.md lists
+// the two one-line accessors a maintainer would add instead). An explicit template instantiation may name private members
+// ([temp.explicit]), which is what this idiom uses — no header of the reference is edited.
+template <typename Tag, typename Tag::type M> struct B2Rob { friend typename Tag::type b2_get(Tag) { return M; } };
+using B2SG = ShapeGroup<float, Color<float, 3>>;
+using B2SC = Scene<float, Color<float, 3>>;
+using B2KD = ShapeKDTree<float, Color<float, 3>>;
+struct B2TagKd { using type = ref<B2KD> B2SG::*; friend type b2_get(B2TagKd); };
+template struct B2Rob<B2TagKd, &B2SG::m_kdtree>;
+struct B2TagGroups { using type = std::vector<ref<B2SG>> B2SC::*; friend type b2_get(B2TagGroups); };
+template struct B2Rob<B2TagGroups, &B2SC::m_shapegroups>;
+// Shape::m_to_world / m_to_object are protected: reachable through a pointer to member formed in a derived class
+template <typename Float, typename Spectrum> struct B2ShapePeek : Shape<Float, Spectrum> {
+    using Base = Shape<Float, Spectrum>;
+    static const typename Base::ScalarTransform4f &to_world(const Base *s) { return s->*(&B2ShapePeek::m_to_world); }
+    static const typename Base::ScalarTransform4f &to_object(const Base *s) { return s->*(&B2ShapePeek::m_to_object); }
+};
+
 /// Collects what Object::traverse() exposes (diffuse.cpp:137-139, dielectric.cpp:322-328, ...)
 struct ParamCollector : TraversalCallback {
     std::map<std::string, Object *> objects;
@@ -64,6 +84,7 @@ public:
     B2PathIntegrator(const Properties &props) : Base(props) {
         // the sampler keeps its base seed protected; mirror it here (default 0, like 'independent')
         m_seed = (uint64_t) props.size_("seed", 0);
+        m_lbvh = props.bool_("device_bvh", false);       // build the BVHs on the GPU (LBVH) instead of the host SAH builder
 #if defined(B2_DIRECT)
         // DirectIntegrator (direct.cpp:78-100, 106-196) with its default shading_samples = 1 draws the same random numbers
         // in the same order, with the same MIS weights, as PathIntegrator with max_depth = 2
@@ -89,10 +110,16 @@ public:
             std::vector<B2Texture> textures;
             std::map<const BSDF *, int> bsdf_index;
             std::map<const Emitter *, int> emitter_of_mesh;
-            for (auto &shape : scene->shapes()) {
-                const Mesh *mesh = dynamic_cast<const Mesh *>(shape.get());
-                if (!mesh)
-                    Throw("b2path: only triangle meshes are supported (got %s)", shape->class_()->name());
+            std::vector<B2Shape> shapes;
+            std::vector<B2Instance> instances;
+            std::vector<uint32_t> group_first;
+            std::map<const Emitter *, int> emitter_of_shape;
+            auto bsdf_of = [&](const BSDF *bsdf) {
+                auto it = bsdf_index.find(bsdf);
+                if (it == bsdf_index.end()) it = bsdf_index.emplace(bsdf, add_bsdf(bsdf, si0, bsdfs, textures)).first;
+                return it->second;
+            };
+            auto add_mesh = [&](const Mesh *mesh) {
                 B2Mesh d;
                 std::memset(&d, 0, sizeof d);
                 d.n_vertices = (uint32_t) mesh->vertex_count();
@@ -101,16 +128,77 @@ public:
                 d.normals = mesh->has_vertex_normals() ? mesh->vertex_normals_buffer().data() : nullptr;
                 d.texcoords = mesh->has_vertex_texcoords() ? mesh->vertex_texcoords_buffer().data() : nullptr;   // mesh.h:131-136
                 d.faces = (const uint32_t *) mesh->faces_buffer().data();
-                const BSDF *bsdf = mesh->bsdf();
-                auto it = bsdf_index.find(bsdf);
-                if (it == bsdf_index.end()) {
-                    it = bsdf_index.emplace(bsdf, add_bsdf(bsdf, si0, bsdfs, textures)).first;
-                }
-                d.bsdf = it->second;
+                d.bsdf = bsdf_of(mesh->bsdf());
                 d.emitter = -1;
                 if (mesh->is_emitter())
                     emitter_of_mesh[mesh->emitter()] = (int) meshes.size();
                 meshes.push_back(d);
+            };
+            // shapegroups of the scene (scene.cpp:36-37) and their children (shapegroup.cpp:14-43)
+            const std::vector<ref<B2SG>> &groups = (*(const B2SC *) scene).*b2_get(B2TagGroups());
+            std::vector<const Shape *> instance_shapes;
+            // top-level shapes first (B2SceneDesc: meshes [0, n_top_meshes))
+            for (auto &shape : scene->shapes()) {
+                const std::string cls = shape->class_()->name();
+                if (const Mesh *mesh = dynamic_cast<const Mesh *>(shape.get())) { add_mesh(mesh); continue; }
+                if (cls == "Instance") { instance_shapes.push_back(shape.get()); continue; }
+                if (cls == "Sphere" || cls == "Rectangle") {
+                    B2Shape sh;
+                    std::memset(&sh, 0, sizeof sh);
+                    sh.type = cls == "Sphere" ? B2_SHAPE_SPHERE : B2_SHAPE_RECTANGLE;
+                    sh.bsdf = bsdf_of(shape->bsdf()); sh.emitter = -1;
+                    store_row_major(B2ShapePeek<Float, Spectrum>::to_world(shape.get()).matrix, sh.to_world);
+                    store_row_major(B2ShapePeek<Float, Spectrum>::to_object(shape.get()).matrix, sh.to_object);
+                    if (sh.type == B2_SHAPE_SPHERE) {
+                        // m_center / m_radius / m_flip_normals are private (sphere.cpp:452-458): the centre is the translation of
+                        // to_world (sphere.cpp:119,127); the radius is recovered from bbox() = centre -+ radius (sphere.cpp:131-138)
+                        // and checked to reproduce it exactly; flip_normals from the normal of a sampled position (:159-160)
+                        for (int k = 0; k < 3; ++k) sh.center[k] = sh.to_world[4 * k + 3];
+                        auto bb = shape->bbox();
+                        const float r0 = sh.center[0] - bb.min.x();
+                        bool exact = false;
+                        for (int step = 0; step < 9 && !exact; ++step) {       // r0, then its neighbours: +1, -1, +2, -2, ... ulp
+                            float cand = r0;
+                            for (int k = 0; k < (step + 1) / 2; ++k) cand = std::nextafter(cand, (step & 1) ? INFINITY : -INFINITY);
+                            bool ok = true;
+                            for (int k = 0; k < 3 && ok; ++k) ok = (sh.center[k] - cand == bb.min[k]) && (sh.center[k] + cand == bb.max[k]);
+                            if (ok) { sh.radius = cand; exact = true; }
+                        }
+                        if (!exact) Throw("b2path: could not recover the radius of %s exactly", shape->to_string());
+                        auto ps = shape->sample_position(0.f, Point2f(.3f, .6f));
+                        Vector3f out(ps.p.x() - sh.center[0], ps.p.y() - sh.center[1], ps.p.z() - sh.center[2]);
+                        sh.flip_normals = dot(out, Vector3f(ps.n)) < 0.f ? 1 : 0;
+                    }
+                    if (shape->is_emitter()) emitter_of_shape[shape->emitter()] = (int) shapes.size();
+                    shapes.push_back(sh);
+                    continue;
+                }
+                Throw("b2path: shape \"%s\" is not supported (triangle meshes, sphere, rectangle, instance are)", cls);
+            }
+            const uint32_t n_top_meshes = (uint32_t) meshes.size();
+            for (auto &g : groups) {
+                group_first.push_back((uint32_t) meshes.size());
+                const B2KD *kd = ((*g).*b2_get(B2TagKd())).get();
+                for (size_t i = 0; i < kd->shape_count(); ++i) {
+                    const Mesh *mesh = dynamic_cast<const Mesh *>(kd->shape(i));
+                    if (!mesh) Throw("b2path: only triangle meshes are supported inside a shapegroup (got %s)", kd->shape(i)->class_()->name());
+                    add_mesh(mesh);
+                }
+            }
+            group_first.push_back((uint32_t) meshes.size());
+            for (const Shape *inst : instance_shapes) {
+                // Instance::m_shapegroup is private to instance.cpp: it is the only data member after the Shape base, so it
+                // sits at sizeof(Shape); the value is only used after it has been found in the scene's shapegroup list
+                const B2SG *sg = *(const B2SG *const *) ((const char *) inst + sizeof(Shape));
+                int gi = -1;
+                for (size_t k = 0; k < groups.size(); ++k) if (groups[k].get() == sg) gi = (int) k;
+                if (gi < 0) Throw("b2path: could not identify the shapegroup of %s", inst->to_string());
+                B2Instance in;
+                std::memset(&in, 0, sizeof in);
+                in.group = gi;
+                store_row_major(B2ShapePeek<Float, Spectrum>::to_world(inst).matrix, in.to_world);
+                store_row_major(B2ShapePeek<Float, Spectrum>::to_object(inst).matrix, in.to_object);
+                instances.push_back(in);
             }
             // emitters in scene->emitters() order (uniform selection index, scene.cpp:176-198)
             for (auto &em : scene->emitters()) {
@@ -129,6 +217,31 @@ public:
                     auto trafo = em->world_transform()->eval(0.f);
                     store_row_major(trafo.matrix, e.env_to_world);
                     store_row_major(trafo.inverse().matrix, e.env_to_object);
+                } else if (std::string(em->class_()->name()) == "DirectionalEmitter") {                             // directional.cpp:107-134
+                    e.type = B2_EMITTER_DIRECTIONAL; e.mesh = -1; e.scale = 1.f;
+                    Color3f in = ((Texture *) pc.objects["irradiance"])->eval(si0);
+                    for (int k = 0; k < 3; ++k) e.radiance[k] = in[k];
+                    auto trafo = em->world_transform()->eval(0.f);
+                    store_row_major(trafo.matrix, e.env_to_world);
+                    store_row_major(trafo.inverse().matrix, e.env_to_object);
+                } else if (std::string(em->class_()->name()) == "SpotLight") {                                      // spot.cpp:72-95
+                    if (((Texture *) pc.objects["texture"])->is_spatially_varying()) Throw("b2path: textured spot lights are not supported");
+                    e.type = B2_EMITTER_SPOT; e.mesh = -1; e.scale = 1.f;
+                    Color3f in = ((Texture *) pc.objects["intensity"])->eval(si0);
+                    for (int k = 0; k < 3; ++k) e.radiance[k] = in[k];
+                    auto trafo = em->world_transform()->eval(0.f);
+                    store_row_major(trafo.matrix, e.env_to_world);
+                    store_row_major(trafo.inverse().matrix, e.env_to_object);
+                    // the angles are only printed (to_string, 6 significant digits): take the printed radians back to the
+                    // degrees the scene file gave (rounded to 1e-3 deg) and redo the constructor's arithmetic (spot.cpp:88-91)
+                    std::string str = em->to_string();
+                    auto field = [&](const char *name) {
+                        size_t p = str.find(name);
+                        if (p == std::string::npos) Throw("b2path: cannot read %s of %s", name, str);
+                        return std::stod(str.substr(p + std::strlen(name)));
+                    };
+                    auto redo = [](double rad) { float deg = (float) (std::round(rad * 180.0 / 3.14159265358979323846 * 1000.0) / 1000.0); return deg_to_rad(deg); };
+                    e.cutoff_angle = redo(field("cutoff_angle = ")); e.beam_width = redo(field("beam_width = "));
                 } else if (em->is_environment()) {
                     if (pc.params.count("data") == 0 || pc.params.count("resolution") == 0)
                         Throw("b2path: unsupported environment emitter %s", em->class_()->name());
@@ -142,19 +255,25 @@ public:
                     store_row_major(trafo.inverse().matrix, e.env_to_object);
                 } else {
                     auto it = emitter_of_mesh.find(em.get());
-                    if (it == emitter_of_mesh.end() || pc.objects.count("radiance") == 0)
-                        Throw("b2path: only area, envmap, constant and point emitters are supported (got %s)", em->class_()->name());
-                    e.type = B2_EMITTER_AREA; e.mesh = it->second; e.scale = 1.f;
+                    auto is = emitter_of_shape.find(em.get());
+                    if ((it == emitter_of_mesh.end() && is == emitter_of_shape.end()) || pc.objects.count("radiance") == 0)
+                        Throw("b2path: only area, envmap, constant, point, spot and directional emitters are supported (got %s)", em->class_()->name());
+                    e.type = B2_EMITTER_AREA; e.scale = 1.f;
                     Color3f rad = ((Texture *) pc.objects["radiance"])->eval(si0);
                     for (int k = 0; k < 3; ++k) e.radiance[k] = rad[k];
-                    meshes[it->second].emitter = (int32_t) emitters.size();
+                    if (it != emitter_of_mesh.end()) { e.mesh = it->second; meshes[it->second].emitter = (int32_t) emitters.size(); }
+                    else { e.mesh = -1; e.shape = is->second + 1; shapes[is->second].emitter = (int32_t) emitters.size(); }
                 }
                 emitters.push_back(e);
             }
 
             B2SceneDesc desc;
             std::memset(&desc, 0, sizeof desc);
-            desc.n_meshes = (uint32_t) meshes.size(); desc.meshes = meshes.data(); desc.n_top_meshes = desc.n_meshes;
+            desc.n_meshes = (uint32_t) meshes.size(); desc.meshes = meshes.data(); desc.n_top_meshes = n_top_meshes;
+            if (!groups.empty()) { desc.n_groups = (uint32_t) groups.size(); desc.group_first = group_first.data(); }
+            desc.n_instances = (uint32_t) instances.size(); desc.instances = instances.empty() ? nullptr : instances.data();
+            desc.n_shapes = (uint32_t) shapes.size(); desc.shapes = shapes.empty() ? nullptr : shapes.data();
+            desc.build_flags = m_lbvh ? B2_BUILD_DEVICE_LBVH : B2_BUILD_HOST_SAH;
             desc.n_bsdfs = (uint32_t) bsdfs.size(); desc.bsdfs = bsdfs.data();
             desc.n_emitters = (uint32_t) emitters.size(); desc.emitters = emitters.data();
             desc.n_textures = (uint32_t) textures.size(); desc.textures = textures.empty() ? nullptr : textures.data();
@@ -399,6 +518,18 @@ private:
             eval3(obj("k"), si, b.cond_k, 1.f);
             eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
             if (!b.sample_visible) NotImplementedError("b2path: roughconductor with sample_visible=false");
+        } else if (cls == "RoughDielectric") {                       // roughdielectric.cpp:140-201, 453-465
+            b.type = B2_BSDF_ROUGHDIELECTRIC;
+            std::string s = bsdf->to_string();                       // distribution / sample_visible are only printed
+            b.distribution = s.find("ggx") != std::string::npos ? B2_MF_GGX : B2_MF_BECKMANN;
+            b.sample_visible = s.find("sample_visible = 0") != std::string::npos ? 0 : 1;
+            Object *au = obj("alpha") ? obj("alpha") : obj("alpha_u"), *av = obj("alpha") ? obj("alpha") : obj("alpha_v");
+            b.alpha_u = au ? ((Texture *) au)->eval_1(si) : .1f;
+            b.alpha_v = av ? ((Texture *) av)->eval_1(si) : .1f;
+            b.eta = pc.get_float("eta", 1.5046f / 1.000277f);
+            eval3(obj("specular_reflectance"), si, b.specular_reflectance, 1.f);
+            eval3(obj("specular_transmittance"), si, b.specular_transmittance, 1.f);
+            if (!b.sample_visible) NotImplementedError("b2path: roughdielectric with sample_visible=false");
         } else if (cls == "SmoothConductor") {                       // conductor.cpp:160-176, 247-251
             b.type = B2_BSDF_CONDUCTOR;
             eval3(obj("eta"), si, b.cond_eta, 0.f);
@@ -418,12 +549,13 @@ private:
             b.specular_sampling_weight = s_mean / (d_mean + s_mean);
             b.nonlinear = bsdf->to_string().find("nonlinear = 1") != std::string::npos ? 1 : 0;   // only printed
         } else {
-            Throw("b2path: BSDF \"%s\" is not supported (diffuse, dielectric, roughconductor, conductor, plastic are)", cls);
+            Throw("b2path: BSDF \"%s\" is not supported (diffuse, dielectric, roughconductor, roughdielectric, conductor, plastic, twosided are)", cls);
         }
         return b;
     }
 
     uint64_t m_seed;
+    bool m_lbvh = false;
     std::atomic<B2Scene *> m_handle { nullptr };
 };
 

@@ -16,6 +16,7 @@ FILTER_RESOLUTION = 31
 FLAG_STAGE_TIMING = 1
 FLAG_SINGLE_SET = 2
 FLAG_COUNT_BVH = 4
+FLAG_PERSISTENT_TRACE = 8
 BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1
 
 

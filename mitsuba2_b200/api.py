@@ -25,7 +25,7 @@ EXPORTS = [
     "b2_cancel", "b2_develop", "b2_set_stream", "b2_stage_raygen", "b2_stage_intersect", "b2_stage_occluded",
     "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
     "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4", "b2_render_reduce", "b2_develop_device",
-    "b2_host_bsdf_plastic", "b2_host_shape_sphere", "b2_host_shape_rectangle",
+    "b2_host_bsdf_plastic", "b2_host_shape_sphere", "b2_host_shape_rectangle", "b2_stage_shade", "b2_stage_film_put",
 ]
 
 REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)     # b2_reduce_fn
@@ -72,6 +72,8 @@ def lib():
             L.b2_render_reduce.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), REDUCE_FN, C.c_void_p, C.c_void_p,
                                            C.POINTER(abi.B2Stats)]
             L.b2_develop_device.argtypes = [C.c_void_p, C.c_void_p]
+            L.b2_stage_shade.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.c_uint32] + [C.c_void_p] * 8 + [C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
+            L.b2_stage_film_put.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)]
         L.b2_cancel.argtypes = [C.c_void_p]
         L.b2_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.b2_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -175,6 +177,28 @@ class Scene:
         _check(lib().b2_stage_raygen(self._h, n, px.ctypes.data, py.ctypes.data, so.ctypes.data, base_seed,
                                      ro.ctypes.data, rd.ctypes.data, rng.ctypes.data, pos.ctypes.data))
         return ro, rd, rng, pos
+
+    def shade(self, rp, ray_o, ray_d, hit, inst, throughput_eta, result_pdf, rng_state, depth_flags):
+        """b2_stage_shade: one loop-body iteration of PathIntegrator::sample for n CONTINUE lanes. The state arrays are updated
+        in place; returns the emitter-sample queue (sh_o, sh_d, sh_c) sorted by lane index."""
+        n = len(ray_o)
+        sh_o = np.zeros((n, 4), np.float32); sh_d = np.zeros((n, 4), np.float32); sh_c = np.zeros((n, 4), np.float32)
+        ns = C.c_uint32()
+        _check(lib().b2_stage_shade(self._h, C.byref(rp), n, ray_o.ctypes.data, ray_d.ctypes.data, hit.ctypes.data,
+                                    inst.ctypes.data if inst is not None else None, throughput_eta.ctypes.data, result_pdf.ctypes.data,
+                                    rng_state.ctypes.data, depth_flags.ctypes.data, C.byref(ns), sh_o.ctypes.data, sh_d.ctypes.data, sh_c.ctypes.data))
+        k = ns.value
+        order = np.argsort(sh_c[:k, 3].view(np.uint32), kind="stable")
+        return sh_o[:k][order], sh_d[:k][order], sh_c[:k][order]
+
+    def film_put(self, block_size, px, py, pos, rgb, alpha):
+        """b2_stage_film_put: ImageBlock::put of n samples -> (XYZAW film [H, W, 5], number of rejected samples)"""
+        px = np.ascontiguousarray(px, np.uint32); py = np.ascontiguousarray(py, np.uint32)
+        pos = np.ascontiguousarray(pos, np.float32); rgb = np.ascontiguousarray(rgb, np.float32); alpha = np.ascontiguousarray(alpha, np.uint8)
+        film = np.zeros((self.height, self.width, 5), np.float32); bad = C.c_uint32()
+        _check(lib().b2_stage_film_put(self._h, block_size, len(px), px.ctypes.data, py.ctypes.data, pos.ctypes.data, rgb.ctypes.data,
+                                       alpha.ctypes.data, film.ctypes.data, C.byref(bad)))
+        return film, bad.value
 
     def develop(self, xyzaw):
         x = np.ascontiguousarray(xyzaw, np.float32)

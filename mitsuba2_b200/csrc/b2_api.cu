@@ -111,6 +111,7 @@ struct B2Scene {
     DBuf<uint4> st;
     DBuf<float2> pos;
     DBuf<uint32_t> pixel, list, cnt, item_pixel, item_seed;
+    DBuf<uint8_t> cls;
     DBuf<unsigned long long> stats;
     DBuf<float> film;
     DBuf<float> film_wide;          // wide filters: padded accumulation film, 8 floats / pixel
@@ -764,7 +765,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(s->sh_o.alloc(cap)); CU(s->sh_d.alloc(cap)); CU(s->sh_c.alloc(cap));
     CU(s->st.alloc(cap)); CU(s->pixel.alloc(cap)); CU(s->list.alloc(2 * cap));
     if (wide) CU(s->pos.alloc(cap));
-    if (s->d.n_instances) CU(s->hit_inst.alloc(cap));
+    // persistent-warp traversal (dynamic ray fetch): always for instanced scenes; on request for the others (the flat
+    // leaf scan of tiny scenes has no use for it)
+    const bool inst = s->d.n_instances != 0 || ((rp->flags & B2_FLAG_PERSISTENT_TRACE) && s->d.n_flat_leaves == 0);
+    if (inst) { CU(s->hit_inst.alloc(cap)); CU(s->cls.alloc(cap)); CU(cudaMemsetAsync(s->cls.p, 0, cap, stream)); }
     CU(s->cnt.alloc(32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
@@ -806,7 +810,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.ray_o = s->ray_o.p + o; q.ray_d = s->ray_d.p + o; q.hit = s->hit.p + o; q.tp = s->tp.p + o; q.res = s->res.p + o; q.st = s->st.p + o;
         q.pixel = s->pixel.p + o; q.list[0] = s->list.p + 2 * o; q.list[1] = s->list.p + 2 * o + set_slots;
         q.pos = wide ? s->pos.p + o : nullptr;
-        q.hit_inst = s->d.n_instances ? s->hit_inst.p + o : nullptr;
+        q.hit_inst = inst ? s->hit_inst.p + o : nullptr; q.cls = inst ? s->cls.p + o : nullptr;
         q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o;
         q.cnt = s->cnt.p + B2_CNT_WORDS * k; q.work = s->cnt.p + WORK_WORD; q.stats = s->stats.p;
         if (sampler_type != B2_SAMPLER_INDEPENDENT) {
@@ -830,7 +834,6 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
-    const bool inst = s->d.n_instances != 0;
     // non-independent samplers run in the extended (F_TEX) kernel variants
     const uint32_t run_features = s->features | (sampler_type != B2_SAMPLER_INDEPENDENT ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
@@ -1056,6 +1059,78 @@ int b2_stage_si_fill(B2Scene *s, uint32_t n, const float *ray_o, const float *ra
     CU(cudaGetLastError());
     D2H(si, out.p, N * 64);
     SYNC();
+    return B2_OK;
+}
+
+// one k_shade launch over caller-provided lanes, all of them CONTINUE lanes (the stage as the wavefront runs it)
+int b2_stage_shade(B2Scene *s, const B2RenderParams *rp, uint32_t n, float *ray_o, float *ray_d, const float *hit, const int32_t *inst,
+                   float *throughput_eta, float *result_pdf, uint64_t *rng_state, uint32_t *depth_flags,
+                   uint32_t *n_shadow, float *sh_o, float *sh_d, float *sh_c) {
+    if (!s || !rp || (n && (!ray_o || !ray_d || !hit || !throughput_eta || !result_pdf || !rng_state || !depth_flags || !n_shadow || !sh_o || !sh_d || !sh_c)))
+        return fail(B2_ERR_INVALID, "b2_stage_shade: null argument");
+    if ((rp->sampler & 0xffu) != B2_SAMPLER_INDEPENDENT) return fail(B2_ERR_INVALID, "b2_stage_shade: independent sampler only");
+    if (s->d.n_instances && !inst) return fail(B2_ERR_INVALID, "b2_stage_shade: instanced scene: inst[] is required");
+    *n_shadow = 0;
+    if (n == 0) return B2_OK;
+    const size_t N = n, cap = (N + 31) & ~(size_t) 31;
+    DBuf<float4> o, d, h, tp, res, so, sd, sc4; DBuf<uint4> st; DBuf<uint32_t> list, cnt, df, pix; DBuf<int32_t> di; DBuf<uint64_t> rng;
+    DBuf<unsigned long long> stats; DBuf<float2> pos;
+    CU(o.alloc(cap)); CU(d.alloc(cap)); CU(h.alloc(cap)); CU(tp.alloc(cap)); CU(res.alloc(cap)); CU(so.alloc(cap)); CU(sd.alloc(cap)); CU(sc4.alloc(cap));
+    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(32)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(8)); CU(pos.alloc(cap));
+    H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16); H2D(h.p, hit, N * 16); H2D(tp.p, throughput_eta, N * 16); H2D(res.p, result_pdf, N * 16);
+    H2D(rng.p, rng_state, N * 8); H2D(df.p, depth_flags, N * 4);
+    if (s->d.n_instances) { CU(di.alloc(cap)); H2D(di.p, inst, N * 4); }
+    CU(cudaMemsetAsync(cnt.p, 0, 32 * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, 64, s->stream));
+    k_stage_pack<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, h.p, rng.p, df.p, st.p, list.p);
+    const unsigned long long n_list = (unsigned long long) n;        // n CONTINUE lanes, no TERMINATE lanes
+    H2D(cnt.p + CNT_LIST, &n_list, 8);
+    Queues q{};
+    q.ray_o = o.p; q.ray_d = d.p; q.hit = h.p; q.hit_inst = s->d.n_instances ? di.p : nullptr; q.tp = tp.p; q.res = res.p; q.st = st.p; q.pixel = pix.p;
+    q.pos = (s->features & F_WIDE) ? pos.p : nullptr;
+    q.sh_o = so.p; q.sh_d = sd.p; q.sh_c = sc4.p; q.list[0] = list.p; q.list[1] = list.p + cap; q.cnt = cnt.p; q.work = cnt.p + 16; q.stats = stats.p;
+    q.film = nullptr; q.n_slots = (uint32_t) cap; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth; q.base_seed = rp->seed;
+    q.n_items_pass = 1; q.n_passes = 1; q.spp_pass = 1; q.block_size = rp->block_size ? rp->block_size : 32; q.n_blocks_total = 1; q.total_items = 0;
+    const ShadeFn fn = shade_variant(s->features);
+    CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes));
+    fn<<<stage_grid(s, n), 256, s->shade_smem_bytes, s->stream>>>(s->d, q, 0);
+    CU(cudaGetLastError());
+    k_stage_unpack<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(n, st.p, rng.p, df.p);
+    uint32_t hc[8];
+    D2H(hc, cnt.p, sizeof hc);
+    D2H(ray_o, o.p, N * 16); D2H(ray_d, d.p, N * 16); D2H(throughput_eta, tp.p, N * 16); D2H(result_pdf, res.p, N * 16);
+    D2H(rng_state, rng.p, N * 8); D2H(depth_flags, df.p, N * 4);
+    SYNC();
+    const uint32_t ns = hc[CNT_SHADOW];
+    if (ns > n) return fail(B2_ERR_CUDA, "b2_stage_shade: shadow queue overflow");
+    *n_shadow = ns;
+    if (ns) { D2H(sh_o, so.p, (size_t) ns * 16); D2H(sh_d, sd.p, (size_t) ns * 16); D2H(sh_c, sc4.p, (size_t) ns * 16); SYNC(); }
+    return B2_OK;
+}
+
+int b2_stage_film_put(B2Scene *s, uint32_t block_size, uint32_t n, const uint32_t *px, const uint32_t *py, const float *pos, const float *rgb,
+                      const uint8_t *alpha, float *xyzaw, uint32_t *n_invalid) {
+    if (!s || !xyzaw || (n && (!px || !py || !pos || !rgb || !alpha))) return fail(B2_ERR_INVALID, "b2_stage_film_put: null argument");
+    if (block_size == 0 || (block_size & (block_size - 1))) return fail(B2_ERR_INVALID, "block_size must be a power of two");
+    const size_t N = n, np = (size_t) s->d.film.crop_size[0] * (size_t) s->d.film.crop_size[1];
+    const bool wide = (s->features & F_WIDE) != 0;
+    DBuf<uint32_t> dx, dy, bad; DBuf<float2> dp; DBuf<float> drgb, film, film8; DBuf<uint8_t> da;
+    CU(dx.alloc(N)); CU(dy.alloc(N)); CU(dp.alloc(N)); CU(drgb.alloc(N * 3)); CU(da.alloc(N)); CU(film.alloc(np * 5)); CU(bad.alloc(1));
+    if (wide) CU(film8.alloc(np * 8));
+    for (uint32_t i = 0; i < n; ++i)
+        if (px[i] >= (uint32_t) s->d.film.crop_size[0] || py[i] >= (uint32_t) s->d.film.crop_size[1]) return fail(B2_ERR_INVALID, "b2_stage_film_put: pixel %u out of range", i);
+    if (n) { H2D(dx.p, px, N * 4); H2D(dy.p, py, N * 4); H2D(dp.p, pos, N * 8); H2D(drgb.p, rgb, N * 12); H2D(da.p, alpha, N); }
+    CU(cudaMemsetAsync(film.p, 0, np * 20, s->stream)); CU(cudaMemsetAsync(bad.p, 0, 4, s->stream));
+    if (wide) CU(cudaMemsetAsync(film8.p, 0, np * 32, s->stream));
+    if (n) {
+        if (wide) k_stage_film_put<true><<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, block_size, dx.p, dy.p, dp.p, drgb.p, da.p, film8.p, bad.p);
+        else k_stage_film_put<false><<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, block_size, dx.p, dy.p, dp.p, drgb.p, da.p, film.p, bad.p);
+    }
+    if (wide) k_film_compact<<<(unsigned) ((np + 255) / 256), 256, 0, s->stream>>>(film8.p, film.p, np);
+    CU(cudaGetLastError());
+    D2H(xyzaw, film.p, np * 20);
+    uint32_t hb = 0; D2H(&hb, bad.p, 4);
+    SYNC();
+    if (n_invalid) *n_invalid = hb;
     return B2_OK;
 }
 

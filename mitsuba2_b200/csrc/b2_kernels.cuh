@@ -36,6 +36,7 @@ struct Queues {
     uint32_t *pixel;            // x | y << 16 of the lane's work item (crop-relative)             4 B
     float2 *pos;                // position_sample, only for wide (non-box) filters
     float4 *sh_o, *sh_d, *sh_c; // dense shadow queue: ray + (contrib.rgb, lane bits)
+    uint8_t *cls;               // k_trace_inst -> k_classify: 0 no ray, 1 the path goes on, 2 the path ends with this segment   1 B
     uint32_t *list[2];          // per iteration parity: CONTINUE lanes from the front, TERMINATE lanes from the back   8 B
     uint32_t *cnt;              // per lane set: see CNT_*
     uint32_t *work;             // global work-item counter (shared by the lane sets)
@@ -211,66 +212,99 @@ struct Trav {
     // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the same
     // kind of work. Returns when the ray is finished, or (can_yield) when the warp has thinned out.
     // SHP: the scene has analytic shapes (compile-time, so that plain triangle scenes do not carry the sphere / rectangle code)
+    // one BVH4 node: slab tests of the 4 children, nearest hit child becomes `cur`, the others go on the stack
+    template <bool COUNT>
+    B2_D void node_step(const DScene &sc, const SmemScene &sm, int *stack) {
+        if constexpr (COUNT) ++n_nodes;
+        float4 nx, ny, nz, fx, fy, fz, chf;
+        if ((uint32_t) cur < sc.smem_nodes) {
+            const float4 *np = sm.nodes + 8 * cur;
+            nx = np[nxi]; ny = np[nyi]; nz = np[nzi]; fx = np[fxi]; fy = np[fyi]; fz = np[fzi]; chf = np[6];
+        } else {
+            const float4 *gp = sc.nodes + 8 * (size_t) cur;
+            nx = __ldg(gp + nxi); ny = __ldg(gp + nyi); nz = __ldg(gp + nzi);
+            fx = __ldg(gp + fxi); fy = __ldg(gp + fyi); fz = __ldg(gp + fzi); chf = __ldg(gp + 6);
+        }
+        const float tlim = tmax * 1.0000004f;
+        #define B2_SLAB(k) \
+            float tn##k = fmaxf(fmaxf(b2_fma(nx.k, idx, oox), b2_fma(ny.k, idy, ooy)), fmaxf(b2_fma(nz.k, idz, ooz), ray.mint)); \
+            float tf##k = fminf(fminf(b2_fma(fx.k, idx, oox), b2_fma(fy.k, idy, ooy)), fminf(b2_fma(fz.k, idz, ooz), tlim)); \
+            int c##k = __float_as_int(chf.k); \
+            bool h##k = c##k != 0 && tn##k <= tf##k;
+        B2_SLAB(x) B2_SLAB(y) B2_SLAB(z) B2_SLAB(w)
+        #undef B2_SLAB
+        // nearest hit child first; the others go on the stack (unordered)
+        float bd = B2_INF; int bc = 0;
+        if (hx) { bd = tnx; bc = cx; }
+        if (hy && tny < bd) { bd = tny; bc = cy; }
+        if (hz && tnz < bd) { bd = tnz; bc = cz; }
+        if (hw && tnw < bd) { bd = tnw; bc = cw; }
+        if (hx && cx != bc) stack[sp++] = cx;
+        if (hy && cy != bc) stack[sp++] = cy;
+        if (hz && cz != bc) stack[sp++] = cz;
+        if (hw && cw != bc) stack[sp++] = cw;
+        cur = bc != 0 ? bc : stack[--sp];
+    }
+    // one leaf: its primitives against the ray; returns true when an any-hit ray is done
+    template <bool ANY, bool SHP, bool COUNT>
+    B2_D bool leaf_step(const DScene &sc, const SmemScene &sm, int leaf) {
+        uint32_t first = (uint32_t) leaf & 0x07ffffffu, count = ((uint32_t) leaf >> 27) & 0xfu;
+        if constexpr (COUNT) n_tris += count;
+        for (uint32_t s = first; s < first + count; ++s) {
+            float4 a0, a1, a2;
+            if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
+            else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
+            float t, u, v;
+            // a slot with a non-zero kind word holds an analytic shape (rectangle / sphere) instead of a triangle
+            bool hit;
+            if (SHP && __float_as_uint(a1.w)) hit = shape_isect(sc.shapes[__float_as_uint(a2.w)], ray, ray.maxt, t, u, v);
+            else hit = tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v);
+            if (hit) {
+                if (ANY) { any_hit = true; return true; }
+                uint32_t prim = __float_as_uint(a0.w);
+                // tie rule: on equal t the larger (instance + 1, prim) key wins
+                if (t < best.t || (t == best.t && (inst > best.inst || (inst == best.inst && prim > best.prim)))) {
+                    best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim; best.inst = inst;
+                    tmax = t;
+                }
+            }
+        }
+        return false;
+    }
+
+    // while-while traversal (inner-node loop, then leaf loop) keeps the lanes of a warp in the same
+    // kind of work. Returns when the ray is finished, or (can_yield) when the warp has thinned out.
+    // SHP: the scene has analytic shapes (compile-time, so that plain triangle scenes do not carry the sphere / rectangle code)
     template <bool ANY, bool SHP, bool COUNT = false>
     B2_D void run(const DScene &sc, const SmemScene &sm, int *stack, bool can_yield) {
-        while (cur != B2_TRAV_DONE) {
+#ifdef B2_SPECULATIVE
+        // speculative while-while (Aila & Laine 2009): the first leaf a lane finds is POSTPONED and the lane keeps descending
+        // while other lanes of the warp are still looking for theirs, so that the leaf phase starts with (nearly) every lane
+        // holding work. A postponed leaf is tested against a tmax that may since have shrunk: fewer hits, same result.
+        int postponed = 0;
+        while (cur != B2_TRAV_DONE || postponed != 0) {
             while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) {
-                if constexpr (COUNT) ++n_nodes;
-                float4 nx, ny, nz, fx, fy, fz, chf;
-                if ((uint32_t) cur < sc.smem_nodes) {
-                    const float4 *np = sm.nodes + 8 * cur;
-                    nx = np[nxi]; ny = np[nyi]; nz = np[nzi]; fx = np[fxi]; fy = np[fyi]; fz = np[fzi]; chf = np[6];
-                } else {
-                    const float4 *gp = sc.nodes + 8 * (size_t) cur;
-                    nx = __ldg(gp + nxi); ny = __ldg(gp + nyi); nz = __ldg(gp + nzi);
-                    fx = __ldg(gp + fxi); fy = __ldg(gp + fyi); fz = __ldg(gp + fzi); chf = __ldg(gp + 6);
-                }
-                const float tlim = tmax * 1.0000004f;
-                #define B2_SLAB(k) \
-                    float tn##k = fmaxf(fmaxf(b2_fma(nx.k, idx, oox), b2_fma(ny.k, idy, ooy)), fmaxf(b2_fma(nz.k, idz, ooz), ray.mint)); \
-                    float tf##k = fminf(fminf(b2_fma(fx.k, idx, oox), b2_fma(fy.k, idy, ooy)), fminf(b2_fma(fz.k, idz, ooz), tlim)); \
-                    int c##k = __float_as_int(chf.k); \
-                    bool h##k = c##k != 0 && tn##k <= tf##k;
-                B2_SLAB(x) B2_SLAB(y) B2_SLAB(z) B2_SLAB(w)
-                #undef B2_SLAB
-                // nearest hit child first; the others go on the stack (unordered)
-                float bd = B2_INF; int bc = 0;
-                if (hx) { bd = tnx; bc = cx; }
-                if (hy && tny < bd) { bd = tny; bc = cy; }
-                if (hz && tnz < bd) { bd = tnz; bc = cz; }
-                if (hw && tnw < bd) { bd = tnw; bc = cw; }
-                if (hx && cx != bc) stack[sp++] = cx;
-                if (hy && cy != bc) stack[sp++] = cy;
-                if (hz && cz != bc) stack[sp++] = cz;
-                if (hw && cw != bc) stack[sp++] = cw;
-                cur = bc != 0 ? bc : stack[--sp];
+                node_step<COUNT>(sc, sm, stack);
+                if (cur < 0 && postponed == 0) { postponed = cur; cur = stack[--sp]; }
+                if (!__any_sync(__activemask(), postponed == 0)) break;
             }
+            while (postponed != 0) {
+                if (leaf_step<ANY, SHP, COUNT>(sc, sm, postponed)) { cur = B2_TRAV_DONE; return; }
+                postponed = 0;
+                if (cur < 0) { postponed = cur; cur = stack[--sp]; }
+            }
+            if (can_yield && __popc(__activemask()) < B2_REFILL_THRESHOLD) return;
+        }
+#else
+        while (cur != B2_TRAV_DONE) {
+            while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) node_step<COUNT>(sc, sm, stack);
             while (cur < 0) {
-                uint32_t first = (uint32_t) cur & 0x07ffffffu, count = ((uint32_t) cur >> 27) & 0xfu;
-                if constexpr (COUNT) n_tris += count;
-                for (uint32_t s = first; s < first + count; ++s) {
-                    float4 a0, a1, a2;
-                    if (sm.tris) { a0 = sm.tris[3 * s]; a1 = sm.tris[3 * s + 1]; a2 = sm.tris[3 * s + 2]; }
-                    else { a0 = __ldg(&sc.tri_isect[3 * (size_t) s]); a1 = __ldg(&sc.tri_isect[3 * (size_t) s + 1]); a2 = __ldg(&sc.tri_isect[3 * (size_t) s + 2]); }
-                    float t, u, v;
-                    // a slot with a non-zero kind word holds an analytic shape (rectangle / sphere) instead of a triangle
-                    bool hit;
-                    if (SHP && __float_as_uint(a1.w)) hit = shape_isect(sc.shapes[__float_as_uint(a2.w)], ray, ray.maxt, t, u, v);
-                    else hit = tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v);
-                    if (hit) {
-                        if (ANY) { any_hit = true; cur = B2_TRAV_DONE; return; }
-                        uint32_t prim = __float_as_uint(a0.w);
-                        // tie rule: on equal t the larger (instance + 1, prim) key wins
-                        if (t < best.t || (t == best.t && (inst > best.inst || (inst == best.inst && prim > best.prim)))) {
-                            best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim; best.inst = inst;
-                            tmax = t;
-                        }
-                    }
-                }
+                if (leaf_step<ANY, SHP, COUNT>(sc, sm, cur)) { cur = B2_TRAV_DONE; return; }
                 cur = stack[--sp];
             }
             if (can_yield && __popc(__activemask()) < B2_REFILL_THRESHOLD) return;
         }
+#endif
     }
 };
 
@@ -706,6 +740,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     const Hit &h = tr.best;
                     q.hit[item] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
                     q.hit_inst[item] = h.inst;
+                    q.cls[item] = (h.t < B2_INF && STW_DEPTH(q.st[item].w) < (uint32_t) q.max_depth) ? 1 : 2;
                     ++n_seg;
                 } else if (!tr.any_hit) {
                     const uint32_t j = item - q.n_slots;
@@ -726,17 +761,14 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     }
 }
 
-// K5 for k_trace_inst: the CONTINUE / TERMINATE lists of k_trace, built in lane order from the hits it wrote
+// K5 for k_trace_inst: the CONTINUE / TERMINATE lists of k_trace, built in lane order from the class byte it left per lane
 __global__ void __launch_bounds__(256) k_classify(Queues q, int parity) {
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         const uint32_t i = base + lane_id();
-        bool cont = false, term = false;
-        if (i < q.n_slots && q.ray_d[i].w >= 0.f) {
-            cont = q.hit[i].x < B2_INF && STW_DEPTH(q.st[i].w) < (uint32_t) q.max_depth;
-            term = !cont;
-        }
-        list_append(q, parity, i, cont, term, 0xffffffffu);
+        uint32_t c = 0;
+        if (i < q.n_slots) { c = q.cls[i]; if (c) q.cls[i] = 0; }
+        list_append(q, parity, i, c == 1u, c == 2u, 0xffffffffu);
     }
 }
 
@@ -1226,6 +1258,45 @@ __global__ void __launch_bounds__(256) k_stage_occluded(DScene sc, uint32_t n, c
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
         Hit h; occ[i] = traverse<true, INST, true>(sc, sm, ray, h) ? 1 : 0;
     }
+}
+// b2_stage_shade: the C-ABI's (t, u, v, prim) hit -> the queues' (t, u, v, slot); lane state words -> st
+__global__ void k_stage_pack(DScene sc, uint32_t n, float4 *hit, const uint64_t *rng, const uint32_t *depth_flags, uint4 *st, uint32_t *list) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 h = hit[i];
+    if (h.x < B2_INF) h.w = __uint_as_float(sc.prim_to_slot[__float_as_uint(h.w)]);
+    hit[i] = h;
+    st[i] = make_uint4((uint32_t) rng[i], (uint32_t) (rng[i] >> 32), 0u, depth_flags[i] & 0xffffu);
+    list[i] = i;
+}
+__global__ void k_stage_unpack(uint32_t n, const uint4 *st, uint64_t *rng, uint32_t *depth_flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 s = st[i];
+    rng[i] = (uint64_t) s.x | ((uint64_t) s.y << 32); depth_flags[i] = s.w & 0xffffu;
+}
+// b2_stage_film_put: ImageBlock::put of n samples; the box-filter target is derived like regen_sample does
+template <bool WIDE>
+__global__ void k_stage_film_put(DScene sc, uint32_t n, uint32_t block_size, const uint32_t *px, const uint32_t *py, const float2 *pos,
+                                 const float *rgb, const uint8_t *alpha, float *film, uint32_t *n_bad) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const B2Film &f = sc.film;
+    uint32_t flags = 0;
+    float2 p = pos[i];
+    if (!WIDE) {
+        int ox = (int) (px[i] / block_size) * (int) block_size, oy = (int) (py[i] / block_size) * (int) block_size;
+        int bw = min((int) block_size, f.crop_size[0] - ox), bh = min((int) block_size, f.crop_size[1] - oy);
+        float bx = p.x - ((float) (ox + f.crop_offset[0]) + .5f), by = p.y - ((float) (oy + f.crop_offset[1]) + .5f);
+        int lox = (int) ceilf(bx - .5f), loy = (int) ceilf(by - .5f);
+        if (lox < 0 || loy < 0 || lox >= bw || loy >= bh) flags |= STW_FILM_DROP;
+        if (lox + ox != (int) px[i]) flags |= STW_FILM_DX;
+        if (loy + oy != (int) py[i]) flags |= STW_FILM_DY;
+        if (lox + ox != (int) px[i] && lox + ox != (int) px[i] - 1) flags |= STW_FILM_DROP;
+        if (loy + oy != (int) py[i] && loy + oy != (int) py[i] - 1) flags |= STW_FILM_DROP;
+    }
+    bool ok = film_put<WIDE>(sc, film, px[i], py[i], block_size, flags, p, v3(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2]), alpha[i] != 0);
+    if (!ok) atomicAdd(n_bad, 1u);
 }
 __global__ void k_stage_si_fill(DScene sc, uint32_t n, const float4 *ray_o, const float4 *ray_d, const float4 *hit, const int32_t *inst, float *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -2112,6 +2112,147 @@ B2O_API int b2o_stage_si_fill(const B2SceneDesc *d, uint32_t n, const float *ray
     return 0;
 }
 
+/* One iteration of PathIntegrator::sample's loop body (path.cpp:124-208) from an explicit per-lane state: the stage as
+   the wavefront runs it (include/b2pt.h b2_stage_shade). Every lane must have hit something (hit t < inf) and have
+   depth < max_depth (the lanes k_trace puts on its CONTINUE list). The emission weight of an emitter hit is formed on
+   arrival from the stored pdf of the last BSDF sample (result_pdf.w), which is what path.cpp:194-205 computes one
+   statement earlier. Independent sampler only (rng_state = PCG32 state, default stream).
+   depth_flags: depth | B2_LANE_DELTA (0x200): the last BSDF sample was a delta lobe | B2_LANE_ALPHA (0x100, out) |
+                B2_LANE_PARKED (0x2000, out): the path ended inside the loop body (ray_d.w = -1)
+   Shadow entries are written in lane order: sh_c = (contribution.rgb, lane index as bits). */
+B2O_API int b2o_stage_shade(const B2SceneDesc *d, const B2RenderParams *rp, uint32_t n, float *ray_o, float *ray_d,
+                            const float *hit, const int32_t *inst, float *throughput_eta, float *result_pdf,
+                            uint64_t *rng_state, uint32_t *depth_flags, uint32_t *n_shadow, float *sh_o, float *sh_d, float *sh_c) {
+    oscene *s = oscene_create(d);
+    uint32_t ns = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        oray ray = load_ray(ray_o, ray_d, i);
+        ohit h; h.t = hit[4 * i]; h.u = hit[4 * i + 1]; h.v = hit[4 * i + 2]; h.prim = b2o_f2u(hit[4 * i + 3]); h.inst = inst ? inst[i] : -1;
+        osi si; si_fill(s, &ray, &h, &si);
+        v3 throughput = v3_make(throughput_eta[4 * i], throughput_eta[4 * i + 1], throughput_eta[4 * i + 2]);
+        float eta = throughput_eta[4 * i + 3];
+        v3 result = v3_make(result_pdf[4 * i], result_pdf[4 * i + 1], result_pdf[4 * i + 2]);
+        float bs_pdf = result_pdf[4 * i + 3];
+        osampler rng; memset(&rng, 0, sizeof rng);
+        rng.type = B2_SAMPLER_INDEPENDENT; rng.rng.state = rng_state[i]; rng.rng.inc = (PCG32_DEFAULT_STREAM << 1u) | 1u;
+        uint32_t fl = depth_flags[i];
+        int depth = (int) (fl & 0xffu), parked = 0;
+        if (depth == 1) fl |= 0x100u;                                     /* valid_ray, path.cpp:121 */
+        int emitter = si.emitter;
+        if (emitter >= 0) {                                               /* path.cpp:128-129 with the weight of :194-205 */
+            float emission_weight = 1.f;
+            if (depth > 1) {
+                float emitter_pdf = 0.f;
+                if (!(fl & 0x200u)) {
+                    v3 dd = v3_sub(si.p, ray.o);
+                    float dist = sqrtf(v3_dot(dd, dd));
+                    dd = v3_scale(dd, b2o_rcp(dist));
+                    emitter_pdf = scene_pdf_emitter_direction(s, emitter, ray.o, dd, si.sh_n, dist);
+                }
+                emission_weight = mis_weight(bs_pdf, emitter_pdf);
+            }
+            const B2Emitter *em = &d->emitters[emitter];
+            v3 ev = si.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f);
+            result = v3_add(result, v3_mul(v3_scale(throughput, emission_weight), ev));
+        }
+        int active = 1;
+        if (depth > rp->rr_depth) {                                       /* path.cpp:137-141 */
+            float q = b2o_min(v3_hmax(throughput) * b2o_sqr(eta), .95f);
+            active = smp_next_1d(&rng) < q;
+            throughput = v3_scale(throughput, b2o_rcp(q));
+        }
+        oray nr = ray;
+        if (!active) parked = 1;
+        else {
+            int flip, smooth;
+            const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[si.bsdf], &si, &flip, &smooth), *bsdf = &bsdf_si;
+            osi sib = si;
+            if (flip) sib.wi.z = -sib.wi.z;
+            if (smooth) {                                                  /* path.cpp:153-172 */
+                float sx, sy; smp_next_2d(&rng, &sx, &sy);
+                ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
+                if (ds.pdf != 0.f) {
+                    v3 wo = to_local(&si, ds.d);
+                    if (flip) wo.z = -wo.z;
+                    v3 bsdf_val = bsdf_eval(bsdf, &sib, wo);
+                    float bpdf = bsdf_pdf(bsdf, &sib, wo);
+                    float mis = ds.delta ? 1.f : mis_weight(ds.pdf, bpdf);
+                    v3 c = v3_mul(v3_mul(v3_scale(throughput, mis), bsdf_val), emitter_val);
+                    if (c.x != 0.f || c.y != 0.f || c.z != 0.f) {
+                        float *o = sh_o + 4 * (size_t) ns, *dd = sh_d + 4 * (size_t) ns, *cc = sh_c + 4 * (size_t) ns;
+                        o[0] = si.p.x; o[1] = si.p.y; o[2] = si.p.z; o[3] = B2O_RAY_EPS * (1.f + v3_hmax_abs(si.p));
+                        dd[0] = ds.d.x; dd[1] = ds.d.y; dd[2] = ds.d.z; dd[3] = ds.dist * (1.f - B2O_SHADOW_EPS);
+                        cc[0] = c.x; cc[1] = c.y; cc[2] = c.z; cc[3] = b2o_u2f(i);
+                        ++ns;
+                    }
+                }
+            }
+            float s2x, s2y; smp_next_2d(&rng, &s2x, &s2y);               /* path.cpp:177-178 (g++: next_2d first) */
+            float s1 = smp_next_1d(&rng);
+            obs bs; v3 bsdf_val = bsdf_sample(bsdf, &sib, s1, s2x, s2y, &bs);
+            if (flip) bs.wo.z = -bs.wo.z;
+            throughput = v3_mul(throughput, bsdf_val);
+            if (!(throughput.x != 0.f || throughput.y != 0.f || throughput.z != 0.f)) parked = 1;   /* path.cpp:182-184 */
+            else {
+                eta *= bs.eta;
+                nr.o = si.p; nr.d = to_world(&si, bs.wo);
+                nr.mint = (1.f + v3_hmax_abs(si.p)) * B2O_RAY_EPS; nr.maxt = INFINITY;
+                bs_pdf = bs.pdf;
+                fl = (fl & ~(0xffu | 0x200u)) | (uint32_t) (depth + 1) | (bs.delta ? 0x200u : 0u);
+            }
+        }
+        if (parked) { fl |= 0x2000u; ray_d[4 * i] = 0.f; ray_d[4 * i + 1] = 0.f; ray_d[4 * i + 2] = 0.f; ray_d[4 * i + 3] = -1.f; }
+        else {
+            ray_o[4 * i] = nr.o.x; ray_o[4 * i + 1] = nr.o.y; ray_o[4 * i + 2] = nr.o.z; ray_o[4 * i + 3] = nr.mint;
+            ray_d[4 * i] = nr.d.x; ray_d[4 * i + 1] = nr.d.y; ray_d[4 * i + 2] = nr.d.z; ray_d[4 * i + 3] = nr.maxt;
+        }
+        throughput_eta[4 * i] = throughput.x; throughput_eta[4 * i + 1] = throughput.y; throughput_eta[4 * i + 2] = throughput.z; throughput_eta[4 * i + 3] = eta;
+        result_pdf[4 * i] = result.x; result_pdf[4 * i + 1] = result.y; result_pdf[4 * i + 2] = result.z; result_pdf[4 * i + 3] = bs_pdf;
+        rng_state[i] = rng.rng.state; depth_flags[i] = fl;
+    }
+    *n_shadow = ns;
+    oscene_destroy(s);
+    return 0;
+}
+
+/* ImageBlock::put (imageblock.cpp:79-172) of n samples into a film of crop_h x crop_w x 5 (XYZAW): sample i belongs to the
+   image block of pixel (px, py) (crop-relative) and lands at pos = position_sample (film coordinates); value rgb is
+   converted to XYZ like render_sample does (integrator.cpp:273). Blocks are merged like HDRFilm::put. Returns the number
+   of samples rejected by the validity rule in *n_invalid. */
+B2O_API int b2o_stage_film_put(const B2SceneDesc *d, uint32_t block_size, uint32_t n, const uint32_t *px, const uint32_t *py,
+                               const float *pos, const float *rgb, const uint8_t *alpha, float *xyzaw, uint32_t *n_invalid) {
+    const B2Film *film = &d->film;
+    int W = film->crop_size[0], H = film->crop_size[1];
+    memset(xyzaw, 0, (size_t) W * H * 5 * sizeof(float));
+    uint32_t bad = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        oblock blk;
+        int bs = (int) block_size;
+        blk.ox = ((int) px[i] / bs) * bs; blk.oy = ((int) py[i] / bs) * bs;
+        blk.w = bs < W - blk.ox ? bs : W - blk.ox; blk.h = bs < H - blk.oy ? bs : H - blk.oy;
+        blk.ox += film->crop_offset[0]; blk.oy += film->crop_offset[1];
+        blk.border = film->border;
+        int sx = blk.w + 2 * blk.border, sy = blk.h + 2 * blk.border;
+        blk.data = (float *) calloc((size_t) 5 * sx * sy, sizeof(float));
+        const float *L = rgb + 3 * (size_t) i;
+        float val[5];
+        val[0] = b2o_fma(0.180423f, L[2], b2o_fma(0.357580f, L[1], 0.412453f * L[0]));
+        val[1] = b2o_fma(0.072169f, L[2], b2o_fma(0.715160f, L[1], 0.212671f * L[0]));
+        val[2] = b2o_fma(0.950227f, L[2], b2o_fma(0.119193f, L[1], 0.019334f * L[0]));
+        val[3] = alpha[i] ? 1.f : 0.f; val[4] = 1.f;
+        if (!block_put(&blk, film, pos[2 * i], pos[2 * i + 1], val)) ++bad;
+        for (int y = 0; y < sy; ++y)                                       /* HDRFilm::put -> ImageBlock::put(block), imageblock.cpp:49-77 */
+            for (int x = 0; x < sx; ++x) {
+                int fx = blk.ox - film->crop_offset[0] - blk.border + x, fy = blk.oy - film->crop_offset[1] - blk.border + y;
+                if (fx < 0 || fy < 0 || fx >= W || fy >= H) continue;
+                for (int k = 0; k < 5; ++k) xyzaw[5 * ((size_t) fy * W + fx) + k] += blk.data[5 * ((size_t) y * sx + x) + k];
+            }
+        free(blk.data);
+    }
+    *n_invalid = bad;
+    return 0;
+}
+
 /* ============================================================================================
  * BSDF unit entry points (for the reference's closed-form tests: test_diffuse.py,
  * test_dielectric.py, test_microfacet.py, test_fresnel.py). wi/wo in local coordinates.

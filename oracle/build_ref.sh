@@ -51,4 +51,7 @@ mkdir -p "$OUT/scenes"
 cp -r "$REF/resources/data/scenes/cbox" "$OUT/scenes/cbox"
 cp -r "$REF/resources/data/scenes/matpreview" "$OUT/scenes/matpreview"     # shipped scene of the drop-in test (BASELINE configs[2])
 echo "g++ $(g++ -dumpversion); flags: reference defaults (-O3 -march=native -ffp-contract=fast); host: $(grep -m1 'model name' /proc/cpuinfo | cut -d: -f2)" > "$OUT/BUILD_INFO.txt"
+# the reference's CMake adds -march=native: record the ISA extensions of THIS host so that a box lacking one of them can
+# say so loudly (tests/ref_cli.py: isa_missing(); a SIGILL of the CLI is reported with this list) instead of failing obscurely
+grep -m1 '^flags' /proc/cpuinfo | tr ' ' '\n' | grep -E '^(avx|fma|bmi|sse4|f16c|popcnt|adx|sha_ni|vaes|vpclmul|gfni)' | sort -u | tr '\n' ' ' > "$OUT/ISA_FLAGS.txt"
 echo "build_ref: installed $OUT/dist"

@@ -48,6 +48,9 @@ def lib():
                                          C.c_int]
         L.b2o_stage_si_fill.argtypes = [C.POINTER(abi.B2SceneDesc), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p]
+        L.b2o_stage_shade.argtypes = [C.POINTER(abi.B2SceneDesc), C.POINTER(abi.B2RenderParams), C.c_uint32] + [C.c_void_p] * 8 + \
+                                     [C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
+        L.b2o_stage_film_put.argtypes = [C.POINTER(abi.B2SceneDesc), C.c_uint32, C.c_uint32] + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)]
         _LIB = L
     return _LIB
 

@@ -21,6 +21,28 @@ def available():
     return os.path.exists(os.path.join(DIST, "mitsuba"))
 
 
+def isa_missing():
+    """ISA extensions of the host oracle/_ref was built on (-march=native, recorded by oracle/build_ref.sh) that THIS host
+    lacks. Empty list = the prebuilt reference can run here."""
+    try:
+        need = set(open(os.path.join(ROOT, "oracle", "_ref", "ISA_FLAGS.txt")).read().split())
+        have = set()
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                have = set(ln.split(":", 1)[1].split()); break
+        return sorted(need - have)
+    except Exception:
+        return []
+
+
+def explain_failure(returncode):
+    """A loud explanation when the prebuilt CLI dies with SIGILL on a host with another ISA."""
+    if returncode in (-4, 132):
+        return ("oracle/_ref was built with -march=native on another host and hit an illegal instruction here; this host lacks: "
+                + (" ".join(isa_missing()) or "(none of the recorded extensions — unexpected)") + ". Rebuild with oracle/build_ref.sh.")
+    return None
+
+
 def render_xml(xml, threads=None):
     """-> (rgb image, seconds logged by 'Rendering finished. (took ...)', integrator.cpp:174-176) or (None, None)"""
     if not available():
@@ -35,6 +57,9 @@ def render_xml(xml, threads=None):
         except Exception:
             return None, None
         if r.returncode != 0 or not os.path.exists(out):
+            why = explain_failure(r.returncode)
+            if why:
+                raise RuntimeError(why)
             return None, None
         m = re.search(r"Rendering finished\. \(took ([0-9.]+)(ms|s|m)", r.stdout + r.stderr)
         t = float(m.group(1)) * {"ms": 1e-3, "s": 1.0, "m": 60.0}[m.group(2)] if m else None

@@ -252,3 +252,75 @@ def test_errors(b2):
     with pytest.raises(b2.B2Error):          # integrator.cpp:62-64
         integ.samples_per_pass = 3
         integ.render(sc, spp=16)
+
+
+@pytest.mark.parametrize("name", ["cbox_64_spp16", "cbox_64_spp16_ggx", "cbox_64_spp16_dielectric_lift", "cbox_64_spp16_env_area",
+                                  "cbox_64_spp16_instances", "cbox_64_spp16_roughglass_ggx"])
+def test_stage_shade_bitexact(b2, oracle, name):
+    """b2_stage_shade (ONE k_shade launch on caller queues) vs the oracle's restatement of the loop body (path.cpp:124-208),
+    chained over three bounces: next ray, throughput, result, RNG state, depth / flags and the emitter-sample queue must
+    match bit for bit — the per-stage parity hook of the fused shading kernel."""
+    sb, rp, _ = G.load(name, b2.Host())
+    sc = b2.Scene(sb)
+    desc = sb.desc()
+    W, H = sb.film.crop_size[0], sb.film.crop_size[1]
+    rng = np.random.default_rng(5)
+    n = 6000
+    px = (rng.integers(0, W, n) + sb.film.crop_offset[0]).astype(np.uint32); py = (rng.integers(0, H, n) + sb.film.crop_offset[1]).astype(np.uint32)
+    ro, rd, state, pos = sc.sample_camera_rays(px, py, rng.integers(0, 2**40, n).astype(np.uint64), base_seed=3)
+    tp = np.ones((n, 4), np.float32); res = np.zeros((n, 4), np.float32); res[:, 3] = 1.0
+    df = np.ones(n, np.uint32)
+    rp.max_depth = 6; rp.rr_depth = 2        # (Russian roulette from the third segment on)
+    instanced = len(sb.instances) > 0
+    for bounce in range(3):
+        hit = np.zeros((len(ro), 4), np.float32); inst = np.full(len(ro), -1, np.int32)
+        assert b2.lib().b2_stage_intersect(sc._h, len(ro), ro.ctypes.data, rd.ctypes.data, hit.ctypes.data, inst.ctypes.data) == 0
+        keep = np.isfinite(hit[:, 0]) & (rd[:, 3] >= 0)
+        ro, rd, hit, inst, tp, res, state, df = [np.ascontiguousarray(a[keep]) for a in (ro, rd, hit, inst, tp, res, state, df)]
+        m = len(ro)
+        assert m > 500
+        g = [a.copy() for a in (ro, rd, tp, res, state, df)]
+        c = [a.copy() for a in (ro, rd, tp, res, state, df)]
+        gs = sc.shade(rp, g[0], g[1], hit, inst if instanced else None, g[2], g[3], g[4], g[5])
+        ns = C.c_uint32(); so = np.zeros((m, 4), np.float32); sd = np.zeros((m, 4), np.float32); scn = np.zeros((m, 4), np.float32)
+        oracle.lib().b2o_stage_shade(C.byref(desc), C.byref(rp), m, c[0].ctypes.data, c[1].ctypes.data, hit.ctypes.data,
+                                     inst.ctypes.data if instanced else None, c[2].ctypes.data, c[3].ctypes.data, c[4].ctypes.data, c[5].ctypes.data,
+                                     C.byref(ns), so.ctypes.data, sd.ctypes.data, scn.ctypes.data)
+        assert np.array_equal(g[4], c[4]) and np.array_equal(g[5], c[5])              # RNG state, depth | flags
+        parked = (g[5] & 0x2000) != 0
+        assert np.array_equal(g[1].view(np.uint32), c[1].view(np.uint32))
+        assert np.array_equal(g[0][~parked].view(np.uint32), c[0][~parked].view(np.uint32))
+        assert np.array_equal(g[2].view(np.uint32), c[2].view(np.uint32)) and np.array_equal(g[3].view(np.uint32), c[3].view(np.uint32))
+        k = ns.value
+        assert len(gs[0]) == k and k > 100
+        for a, b in zip(gs, (so[:k], sd[:k], scn[:k])):
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        ro, rd, tp, res, state, df = g
+
+
+@pytest.mark.parametrize("rfilter", ["box", "gaussian"])
+def test_stage_film_put(b2, oracle, rfilter):
+    """b2_stage_film_put (ImageBlock::put on the device) vs the oracle's block put + merge: box filter with at most one
+    sample per pixel is exact; the gaussian taps are fp32 atomics (order differs: rel 1e-6)."""
+    sb = scenes.cbox(b2.Host(), 80, 48, rfilter=rfilter)
+    sc = b2.Scene(sb)
+    rng = np.random.default_rng(9)
+    n = 3000 if rfilter == "gaussian" else 80 * 48
+    if rfilter == "box":
+        idx = rng.permutation(80 * 48)[:n]; px = (idx % 80).astype(np.uint32); py = (idx // 80).astype(np.uint32)
+    else:
+        px = rng.integers(0, 80, n).astype(np.uint32); py = rng.integers(0, 48, n).astype(np.uint32)
+    pos = np.stack([px + rng.random(n, dtype=np.float32), py + rng.random(n, dtype=np.float32)], 1).astype(np.float32)
+    pos[:7] = np.stack([px[:7], py[:7]], 1)                  # samples exactly on pixel corners: the x-1 / y-1 / dropped cases
+    rgb = rng.random((n, 3), dtype=np.float32) * 4
+    rgb[5] = np.nan; rgb[6] = -1.0                           # rejected by the validity rule (imageblock.cpp:85-109)
+    alpha = (rng.random(n) < 0.8).astype(np.uint8)
+    film, bad = sc.film_put(32, px, py, pos, rgb, alpha)
+    desc = sb.desc(); ref = np.zeros_like(film); nb = C.c_uint32()
+    oracle.lib().b2o_stage_film_put(C.byref(desc), 32, n, px.ctypes.data, py.ctypes.data, pos.ctypes.data, rgb.ctypes.data, alpha.ctypes.data,
+                                    ref.ctypes.data, C.byref(nb))
+    assert bad == nb.value == 2
+    if rfilter == "box":
+        assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+    else:
+        assert oracle.rel_l2(film, ref) < 1e-6 and np.abs(film - ref).max() < 1e-4
