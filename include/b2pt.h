@@ -223,6 +223,7 @@ typedef struct B2RenderParams {
    spp must be a perfect square, :60-75; multijitter: spp = rx * ry with ry = floor(sqrt(spp)), multijitter.cpp:68-81) */
 enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJITTER = 2 /* src/samplers/multijitter.cpp */,
        B2_SAMPLER_LOW_DISCREPANCY = 3 /* src/samplers/ldsampler.cpp: (0,2)-sequence; spp = 4^k */,
+       B2_SAMPLER_ORTHOGONAL = 4 /* src/samplers/orthogonal.cpp, default strength 2 (Bose construction, :188-218): spp = p^2, p prime */,
        B2_SAMPLER_NO_JITTER = 0x100 };
 
 #define B2_FLAG_SINGLE_SET 2u   /* one lane set on one stream (default: two sets on two streams) */
@@ -275,6 +276,13 @@ B2_API int b2_render_device(B2Scene *scene, const B2RenderParams *params, float 
 typedef int (*b2_reduce_fn)(void *user, float *d_film, size_t n_floats, void *cuda_stream);
 B2_API int b2_render_reduce(B2Scene *scene, const B2RenderParams *params, b2_reduce_fn reduce, void *user,
                             float *xyzaw, B2Stats *stats);
+/* Progressive output (the reference develops the partially rendered film on SIGHUP, src/mitsuba/mitsuba.cpp:95-121, and shows
+   progress per block, integrator.cpp:100-135): while a render runs, at most every `min_interval_ms` the film accumulated so far
+   is copied to a pinned host buffer on a SIDE stream — the copy engine works while the wavefront kernels keep the SMs busy —
+   and handed to `fn` from the rendering thread. Every pixel carries its own sample count in W, so developing the snapshot
+   (XYZ / W) gives a valid partial image at any time. `fn` returns non-zero to cancel the render. fn = NULL switches it off. */
+typedef int (*b2_progress_fn)(void *user, const float *xyzaw_snapshot, uint64_t samples_done, uint64_t samples_total);
+B2_API int b2_set_progress_callback(B2Scene *scene, b2_progress_fn fn, void *user, uint32_t min_interval_ms);
 /* b2_cancel(): async-safe, sets a flag; the running render returns B2_ERR_CANCELLED within one batch of iterations and the
    film (host buffer of b2_render / device film of b2_render_device) holds the samples accumulated so far, with their count
    in W — develop it like the reference develops a partial film on SIGHUP (src/mitsuba/mitsuba.cpp:112-121). */

@@ -334,8 +334,10 @@ public:
                     rp.sampler = B2_SAMPLER_MULTIJITTER | (sensor->sampler()->to_string().find("jitter = 0") != std::string::npos ? B2_SAMPLER_NO_JITTER : 0);
                 else if (scls == "LowDiscrepancySampler")
                     rp.sampler = B2_SAMPLER_LOW_DISCREPANCY;
+                else if (scls == "OrthogonalSampler")        // (its 'strength' is not exposed: the default 2 = Bose construction is assumed)
+                    rp.sampler = B2_SAMPLER_ORTHOGONAL | (sensor->sampler()->to_string().find("jitter = 0") != std::string::npos ? B2_SAMPLER_NO_JITTER : 0);
                 else if (scls != "IndependentSampler")
-                    Throw("b2path: sampler \"%s\" is not supported (independent, stratified, multijitter, ldsampler are)", scls);
+                    Throw("b2path: sampler \"%s\" is not supported (independent, stratified, multijitter, ldsampler, orthogonal are)", scls);
             }
 
             film->prepare({ "X", "Y", "Z", "A", "W" });                  // integrator.cpp:71-73

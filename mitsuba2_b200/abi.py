@@ -152,12 +152,12 @@ def uptr(a):
 
 def render_params(max_depth=6, rr_depth=5, spp=16, samples_per_pass=0, block_size=32, seed=0,
                   rank=0, world_size=1, lane_slots=0, flags=0, sampler="independent", jitter=True):
-    smp = {"independent": SAMPLER_INDEPENDENT, "stratified": SAMPLER_STRATIFIED, "multijitter": SAMPLER_MULTIJITTER, "ldsampler": SAMPLER_LOW_DISCREPANCY}[sampler] | (0 if jitter else SAMPLER_NO_JITTER)
+    smp = {"independent": SAMPLER_INDEPENDENT, "stratified": SAMPLER_STRATIFIED, "multijitter": SAMPLER_MULTIJITTER, "ldsampler": SAMPLER_LOW_DISCREPANCY, "orthogonal": SAMPLER_ORTHOGONAL}[sampler] | (0 if jitter else SAMPLER_NO_JITTER)
     return B2RenderParams(max_depth, rr_depth, spp, samples_per_pass, block_size, lane_slots, seed, rank, world_size,
                           flags, smp)
 
 
-SAMPLER_INDEPENDENT, SAMPLER_STRATIFIED, SAMPLER_MULTIJITTER, SAMPLER_LOW_DISCREPANCY, SAMPLER_NO_JITTER = 0, 1, 2, 3, 0x100
+SAMPLER_INDEPENDENT, SAMPLER_STRATIFIED, SAMPLER_MULTIJITTER, SAMPLER_LOW_DISCREPANCY, SAMPLER_ORTHOGONAL, SAMPLER_NO_JITTER = 0, 1, 2, 3, 4, 0x100
 
 
 def fresnel_diffuse_reflectance(eta):

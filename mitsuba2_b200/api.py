@@ -26,8 +26,10 @@ EXPORTS = [
     "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
     "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4", "b2_render_reduce", "b2_develop_device",
     "b2_host_bsdf_plastic", "b2_host_shape_sphere", "b2_host_shape_rectangle", "b2_stage_shade", "b2_stage_film_put",
+    "b2_set_progress_callback",
 ]
 
+PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_uint64)     # b2_progress_fn
 REDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)     # b2_reduce_fn
 
 
@@ -72,6 +74,7 @@ def lib():
             L.b2_render_reduce.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), REDUCE_FN, C.c_void_p, C.c_void_p,
                                            C.POINTER(abi.B2Stats)]
             L.b2_develop_device.argtypes = [C.c_void_p, C.c_void_p]
+            L.b2_set_progress_callback.argtypes = [C.c_void_p, PROGRESS_FN, C.c_void_p, C.c_uint32]
             L.b2_stage_shade.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.c_uint32] + [C.c_void_p] * 8 + [C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
             L.b2_stage_film_put.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)]
         L.b2_cancel.argtypes = [C.c_void_p]
@@ -177,6 +180,20 @@ class Scene:
         _check(lib().b2_stage_raygen(self._h, n, px.ctypes.data, py.ctypes.data, so.ctypes.data, base_seed,
                                      ro.ctypes.data, rd.ctypes.data, rng.ctypes.data, pos.ctypes.data))
         return ro, rd, rng, pos
+
+    def set_progress_callback(self, fn, min_interval_ms=0):
+        """fn(xyzaw_snapshot [H, W, 5] (a view, valid during the call), samples_done, samples_total) -> truthy to cancel the
+        render; None switches the snapshots off. Called from the rendering thread while the GPU keeps rendering."""
+        if fn is None:
+            self._progress = None
+            _check(lib().b2_set_progress_callback(self._h, PROGRESS_FN(), None, 0))
+            return
+
+        def _cb(user, ptr, done, total):
+            snap = np.ctypeslib.as_array(ptr, shape=(self.height, self.width, 5))
+            return 1 if fn(snap, done, total) else 0
+        self._progress = PROGRESS_FN(_cb)          # (keeps the thunk alive)
+        _check(lib().b2_set_progress_callback(self._h, self._progress, None, int(min_interval_ms)))
 
     def shade(self, rp, ray_o, ray_d, hit, inst, throughput_eta, result_pdf, rng_state, depth_flags):
         """b2_stage_shade: one loop-body iteration of PathIntegrator::sample for n CONTINUE lanes. The state arrays are updated

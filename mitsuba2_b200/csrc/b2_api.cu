@@ -117,11 +117,18 @@ struct B2Scene {
     DBuf<float> film_wide;          // wide filters: padded accumulation film, 8 floats / pixel
     DBuf<uint2> smp;                // per-lane sampler state of the non-independent samplers
     uint32_t *h_cnt = nullptr;      // pinned readback
+    // progressive snapshots (b2_set_progress_callback)
+    b2_progress_fn progress_fn = nullptr; void *progress_user = nullptr; uint32_t progress_ms = 0;
+    cudaStream_t stream_snap = nullptr; float *h_snap = nullptr; size_t h_snap_floats = 0; unsigned long long *h_snap_samples = nullptr;
+    DBuf<float> snap_film;          // wide filters: packed copy of the padded film
     // the work-item tables of the last render (spiral order x Morton order) are kept: they depend only on this key
     struct { int W = 0, H = 0; uint32_t bs = 0; int rank = -1, world = 0; uint32_t n_items = 0, n_blocks = 0; } items_key;
     ~B2Scene() {
         if (h_cnt) cudaFreeHost(h_cnt);
+        if (h_snap) cudaFreeHost(h_snap);
+        if (h_snap_samples) cudaFreeHost(h_snap_samples);
         if (stream2) cudaStreamDestroy(stream2);
+        if (stream_snap) cudaStreamDestroy(stream_snap);
     }
 };
 
@@ -677,6 +684,12 @@ int b2_set_stream(B2Scene *scene, void *stream) {
     return B2_OK;
 }
 
+int b2_set_progress_callback(B2Scene *scene, b2_progress_fn fn, void *user, uint32_t min_interval_ms) {
+    if (!scene) return fail(B2_ERR_INVALID, "null scene");
+    scene->progress_fn = fn; scene->progress_user = user; scene->progress_ms = min_interval_ms;
+    return B2_OK;
+}
+
 int b2_cancel(B2Scene *scene) {
     if (scene) scene->cancel.store(1);
     return B2_OK;
@@ -788,6 +801,15 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             uint32_t lg = 0; while ((1u << lg) < rp->spp) ++lg;
             if ((1u << lg) != rp->spp || (lg & 1u) || rp->spp < 4) return fail(B2_ERR_INVALID, "Sample count should be square and power of two (got %u)", rp->spp);
             smp_res = lg;                                                // log2 of the sample count (permute(), random.h:194-207)
+        } else if (sampler_type == B2_SAMPLER_ORTHOGONAL) {            // orthogonal.cpp:76-90: spp = p^2 with p prime (strength 2)
+            uint32_t r = 2;
+            for (;; ++r) {
+                bool prime = true;
+                for (uint32_t i = 2; i <= r / 2; ++i) if (r % i == 0) { prime = false; break; }
+                if (prime && r * r >= rp->spp) break;
+            }
+            if (r * r != rp->spp) return fail(B2_ERR_INVALID, "Sample count should be the square of a prime number, rounding to %u (got %u)", r * r, rp->spp);
+            smp_res = smp_res_y = r;
         } else return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
         CU(s->smp.alloc(cap));
     }
@@ -860,6 +882,23 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     }
     if (timing && evi1) cudaEventRecord(evi1, stream);
     if (n_sets > 1) { CU(cudaEventRecord(evs, stream)); CU(cudaStreamWaitEvent(streams[1], evs, 0)); }
+    // progressive snapshots: film -> pinned host buffer on a side stream (copy engine), handed to the callback one batch later
+    const size_t film_floats = (size_t) W * H * 5;
+    cudaEvent_t ev_film = nullptr, ev_snap = nullptr;
+    bool snap_in_flight = false;
+    auto snap_last = std::chrono::steady_clock::now();
+    if (s->progress_fn) {
+        if (!s->stream_snap) CU(cudaStreamCreateWithFlags(&s->stream_snap, cudaStreamNonBlocking));
+        if (s->h_snap_floats < film_floats) {
+            if (s->h_snap) cudaFreeHost(s->h_snap);
+            s->h_snap = nullptr; s->h_snap_floats = 0;
+            CU(cudaMallocHost(&s->h_snap, film_floats * sizeof(float))); s->h_snap_floats = film_floats;
+        }
+        if (!s->h_snap_samples) CU(cudaMallocHost(&s->h_snap_samples, sizeof(unsigned long long)));
+        if (wide) CU(s->snap_film.alloc(film_floats));
+        ev_film = pool.make(false); ev_snap = pool.make(false);
+        if (!ev_film || !ev_snap) return fail(B2_ERR_CUDA, "cudaEventCreate failed");
+    }
     int pending[2] = { 0, 0 };
     bool done = false;
     int status = B2_OK;
@@ -898,10 +937,32 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
                 all = all && c[B2_CNT_WORDS * k + CNT_ALIVE] == 0 && c[B2_CNT_WORDS * k + CNT_SHADOW] == 0 && c[B2_CNT_WORDS * k + CNT_SHADOW + 1] == 0;
             if (all) done = true;
         }
+        if (s->progress_fn) {
+            if (snap_in_flight && cudaEventQuery(ev_snap) == cudaSuccess) {
+                snap_in_flight = false;
+                if (s->progress_fn(s->progress_user, s->h_snap, *s->h_snap_samples, (uint64_t) W * H * rp->spp / (uint64_t) world)) s->cancel.store(1);
+            }
+            auto now = std::chrono::steady_clock::now();
+            if (!snap_in_flight && !done && std::chrono::duration<double, std::milli>(now - snap_last).count() >= (double) s->progress_ms) {
+                snap_last = now;
+                CU(cudaEventRecord(ev_film, stream));                      // (both lane sets were joined into `stream` above)
+                CU(cudaStreamWaitEvent(s->stream_snap, ev_film, 0));
+                const float *src = s->film.p;
+                if (wide) {
+                    k_film_compact<<<(unsigned) (((size_t) W * H + 255) / 256), 256, 0, s->stream_snap>>>(s->film_wide.p, s->snap_film.p, (size_t) W * H);
+                    src = s->snap_film.p;
+                }
+                CU(cudaMemcpyAsync(s->h_snap, src, film_floats * sizeof(float), cudaMemcpyDeviceToHost, s->stream_snap));
+                CU(cudaMemcpyAsync(s->h_snap_samples, s->stats.p + ST_SAMPLES, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream_snap));
+                CU(cudaEventRecord(ev_snap, s->stream_snap));
+                snap_in_flight = true;
+            }
+        }
         if (s->cancel.load()) { status = B2_ERR_CANCELLED; done = true; }
         if (cudaPeekAtLastError() != cudaSuccess) break;
     }
     if (n_sets > 1) { CU(cudaEventRecord(evx, streams[1])); CU(cudaStreamWaitEvent(stream, evx, 0)); }
+    if (snap_in_flight) CU(cudaStreamSynchronize(s->stream_snap));       // (the snapshot buffers must not outlive this call in flight)
     CU(cudaGetLastError());
     if (wide) { size_t np = (size_t) W * H; k_film_compact<<<(unsigned) ((np + 255) / 256), 256, 0, stream>>>(s->film_wide.p, s->film.p, np); ++launches; }
     CU(cudaEventRecord(ev1, stream));

@@ -829,8 +829,27 @@ B2_D float sobol_2(uint32_t index, uint32_t scramble) {
         if (index & 1u) scramble ^= v;
     return (float) scramble / 4294967296.f;
 }
+// OrthogonalSampler::bose (orthogonal.cpp:188-218), strength 2: q.smp_res = the prime resolution, q.smp_count = its square
+B2_D float smp_bose(const Queues &q, uint64_t &rng, uint2 &sm) {
+    const uint32_t j = sm.x & 0xffffu, p = sm.y, res = q.smp_res; ++sm.x;
+    const uint32_t i = permute_kensler((sm.x >> 16) % q.smp_count, q.smp_count, p);
+    const uint32_t a_i0 = i / res, a_i1 = i - a_i0 * res;
+    uint32_t a_ij, a_ik;
+    if (j == 0) { a_ij = a_i0; a_ik = a_i1; }
+    else if (j == 1) { a_ij = a_i1; a_ik = a_i0; }
+    else {
+        const uint32_t k = (j & 1u) ? j - 1 : j + 1;
+        a_ij = (a_i0 + (j - 1) * a_i1) % res;
+        a_ik = (a_i0 + (k - 1) * a_i1) % res;
+    }
+    const uint32_t stratum = permute_kensler(a_ij, res, p * (j + 1) * 0x51633e2du);
+    const uint32_t sub_stratum = permute_kensler(a_ik, res, p * (j + 1) * 0x68bc21ebu);
+    const float jitter = q.smp_jitter ? pcg32_next_float(rng) : .5f;
+    return ((float) stratum + ((float) sub_stratum + jitter) / (float) res) / (float) res;
+}
 template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2 &sm) {
     if constexpr (EXT) if (q.smp) {
+        if (q.smp_type == B2_SAMPLER_ORTHOGONAL) return smp_bose(q, rng, sm);
         if (q.smp_type == B2_SAMPLER_LOW_DISCREPANCY) {
             uint32_t i = permute_tea(sm.x >> 16, q.smp_res, sm.y + (sm.x & 0xffffu)); ++sm.x;
             return radical_inverse_2(i, sample_tea_32(sm.y, 0x48bc48ebu));
@@ -845,6 +864,7 @@ template <bool EXT> B2_D float smp_next_1d(const Queues &q, uint64_t &rng, uint2
 }
 template <bool EXT> B2_D float2 smp_next_2d(const Queues &q, uint64_t &rng, uint2 &sm) {
     if constexpr (EXT) if (q.smp) {
+        if (q.smp_type == B2_SAMPLER_ORTHOGONAL) { float a = smp_bose(q, rng, sm), b = smp_bose(q, rng, sm); return make_float2(a, b); }   // orthogonal.cpp:128-132
         if (q.smp_type == B2_SAMPLER_LOW_DISCREPANCY) {
             uint32_t i = permute_tea(sm.x >> 16, q.smp_res, sm.y + (sm.x & 0xffffu)); ++sm.x;
             return make_float2(radical_inverse_2(i, sample_tea_32(sm.y, 0x98bc51abu)), sobol_2(i, sample_tea_32(sm.y, 0x04223e2du)));

@@ -1671,7 +1671,15 @@ static void smp_seed(osampler *s, const B2RenderParams *rp, uint64_t seed_offset
     sampler_seed(&s->rng, rp->seed, seed_offset);
     s->type = rp->sampler & 0xffu; s->jitter = !(rp->sampler & B2_SAMPLER_NO_JITTER);
     s->sample_index = 0; s->dim = 0;
-    if (s->type == B2_SAMPLER_MULTIJITTER) {                       /* multijitter.cpp:68-81 */
+    if (s->type == B2_SAMPLER_ORTHOGONAL) {                        /* orthogonal.cpp:76-90: the smallest prime p with p^2 >= spp */
+        uint32_t r = 2;
+        for (;; ++r) {
+            int prime = 1;
+            for (uint32_t i = 2; i <= r / 2; ++i) if (r % i == 0) { prime = 0; break; }
+            if (prime && r * r >= rp->spp) break;
+        }
+        s->res = s->res_y = r; s->count = r * r;
+    } else if (s->type == B2_SAMPLER_MULTIJITTER) {                /* multijitter.cpp:68-81 */
         s->res_y = (uint32_t) sqrtf((float) rp->spp);
         s->res = (rp->spp + s->res_y - 1) / s->res_y;
         s->count = s->res * s->res_y;
@@ -1685,8 +1693,26 @@ static void smp_seed(osampler *s, const B2RenderParams *rp, uint64_t seed_offset
     s->perm_seed = sample_tea_32((uint32_t) rp->seed, (uint32_t) seed_offset, 4);     /* compute_per_sequence_seed, sampler.cpp:55-60 */
 }
 static inline void smp_advance(osampler *s) { s->dim = 0; s->sample_index++; }
+/* OrthogonalSampler::bose (orthogonal.cpp:188-218), strength 2: s->res = the prime resolution, s->count = res^2 */
+static float smp_bose(osampler *s) {
+    uint32_t j = s->dim++, p = s->perm_seed, res = s->res;
+    uint32_t i = permute_kensler(s->sample_index % s->count, s->count, p);
+    uint32_t a_i0 = i / res, a_i1 = i - a_i0 * res, a_ij, a_ik;
+    if (j == 0) { a_ij = a_i0; a_ik = a_i1; }
+    else if (j == 1) { a_ij = a_i1; a_ik = a_i0; }
+    else {
+        uint32_t k = (j % 2) ? j - 1 : j + 1;
+        a_ij = (a_i0 + (j - 1) * a_i1) % res;
+        a_ik = (a_i0 + (k - 1) * a_i1) % res;
+    }
+    uint32_t stratum = permute_kensler(a_ij, res, p * (j + 1) * 0x51633e2du);
+    uint32_t sub_stratum = permute_kensler(a_ik, res, p * (j + 1) * 0x68bc21ebu);
+    float jitter = s->jitter ? pcg32_next_float(&s->rng) : .5f;
+    return ((float) stratum + ((float) sub_stratum + jitter) / (float) res) / (float) res;
+}
 static inline float smp_next_1d(osampler *s) {
     if (s->type == B2_SAMPLER_INDEPENDENT) return pcg32_next_float(&s->rng);
+    if (s->type == B2_SAMPLER_ORTHOGONAL) return smp_bose(s);
     if (s->type == B2_SAMPLER_LOW_DISCREPANCY) {
         uint32_t i = permute_tea(s->sample_index, s->count, s->perm_seed + s->dim++);
         return radical_inverse_2(i, sample_tea_32(s->perm_seed, 0x48bc48ebu, 4));
@@ -1699,6 +1725,7 @@ static inline float smp_next_1d(osampler *s) {
 }
 static inline void smp_next_2d(osampler *s, float *x, float *y) {
     if (s->type == B2_SAMPLER_INDEPENDENT) { *x = pcg32_next_float(&s->rng); *y = pcg32_next_float(&s->rng); return; }
+    if (s->type == B2_SAMPLER_ORTHOGONAL) { *x = smp_bose(s); *y = smp_bose(s); return; }     /* orthogonal.cpp:128-132 */
     if (s->type == B2_SAMPLER_LOW_DISCREPANCY) {
         uint32_t i = permute_tea(s->sample_index, s->count, s->perm_seed + s->dim++);
         *x = radical_inverse_2(i, sample_tea_32(s->perm_seed, 0x98bc51abu, 4));

@@ -525,6 +525,9 @@ GOLDEN = {
     "cbox_64_spp8_multijitter_nojitter": dict(width=64, height=64, spp=8, no_patch=True, sampler="multijitter", jitter=False),   # 4 x 2 strata
     "cbox_64_spp16_shapes_textured": dict(width=64, height=64, spp=16, no_patch=True, analytic="textured"),
     "cbox_64_spp16_ldsampler": dict(width=64, height=64, spp=16, no_patch=True, sampler="ldsampler"),
+    # orthogonal-array sampler (Bose construction, strength 2): spp = p^2 with p prime
+    "cbox_64_spp25_orthogonal": dict(width=64, height=64, spp=25, no_patch=True, sampler="orthogonal"),
+    "cbox_64_spp9_orthogonal_nojitter": dict(width=64, height=64, spp=9, no_patch=True, sampler="orthogonal", jitter=False),
     "cbox_64_spp16_constant": dict(width=64, height=64, spp=16, envmap="constant"),
     "cbox_64_spp16_constant_area": dict(width=64, height=64, spp=16, envmap="constant_area"),
     "cbox_64_spp16_point": dict(width=64, height=64, spp=16, no_patch=True, point_light="only"),

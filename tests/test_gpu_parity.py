@@ -125,7 +125,8 @@ def test_instances_intersect_vs_bruteforce(b2, oracle):
                                   "cbox_64_spp16_constant", "cbox_64_spp16_constant_area",
                                   "cbox_64_spp16_point", "cbox_64_spp16_point_area",
                                   "cbox_64_spp16_roughglass_beckmann", "cbox_64_spp16_roughglass_ggx",
-                                  "cbox_64_spp16_spot", "cbox_64_spp16_directional"])
+                                  "cbox_64_spp16_spot", "cbox_64_spp16_directional",
+                                  "cbox_64_spp25_orthogonal", "cbox_64_spp9_orthogonal_nojitter"])
 def test_render_bitexact_single_pass(b2, oracle, name):
     """Box filter + one pass: one lane owns a pixel and adds its samples in order, exactly like
     render_block -> the whole XYZAW film must match the oracle bit for bit."""
@@ -324,3 +325,47 @@ def test_stage_film_put(b2, oracle, rfilter):
         assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
     else:
         assert oracle.rel_l2(film, ref) < 1e-6 and np.abs(film - ref).max() < 1e-4
+
+
+def test_progressive_snapshots_and_cancel(b2):
+    """b2_set_progress_callback: partial films while the render runs (SIGHUP / progress semantics of the reference), the
+    final film is unaffected; a callback that asks to stop ends the render with B2_ERR_CANCELLED and leaves the samples
+    accumulated so far on the film."""
+    sb = scenes.cbox(b2.Host(), 512, 512)
+    sc = b2.Scene(sb)
+    integ = b2.PathIntegrator(max_depth=6, rr_depth=5, samples_per_pass=8, block_size=32)
+    ref = integ.render(sc, 64).copy()
+    seen = []
+
+    def on_progress(snap, done, total):
+        w = float(snap[..., 4].sum(dtype=np.float64))
+        seen.append((done, total, w, bool(np.isfinite(snap).all())))
+        return False
+    sc.set_progress_callback(on_progress, 0)
+    film = integ.render(sc, 64)
+    assert np.array_equal(film.view(np.uint32), ref.view(np.uint32))
+    assert len(seen) >= 2 and all(s[3] for s in seen) and all(s[1] == 512 * 512 * 64 for s in seen)
+    assert all(a[0] <= b[0] for a, b in zip(seen, seen[1:])) and 0 < seen[-1][0] <= 512 * 512 * 64
+    assert all(abs(s[2] - s[0]) <= 0.02 * 512 * 512 * 64 for s in seen)       # W of the snapshot ~ samples put so far (copy is not a cut)
+    # develop a partial snapshot: XYZ / W is a valid estimate of the final image
+    calls = []
+
+    def stop_early(snap, done, total):
+        calls.append(done)
+        return done > total // 4
+    sc.set_progress_callback(stop_early, 0)
+    with pytest.raises(b2.B2Error) as e:
+        integ.render(sc, 64)
+    assert e.value.code == 3
+    sc.set_progress_callback(None)
+    out = np.empty((512, 512, 5), np.float32); st = abi.B2Stats()
+    rp = integ.params(64)
+    sc.set_progress_callback(stop_early, 0)
+    rc = b2.lib().b2_render(sc._h, C.byref(rp), out.ctypes.data, C.byref(st))
+    assert rc == 3
+    wsum = float(out[..., 4].sum(dtype=np.float64))
+    assert 0.2 * 512 * 512 * 64 < wsum < 512 * 512 * 64            # a partial film came back
+    part = out[..., :3].sum(axis=(0, 1)) / wsum; full = ref[..., :3].sum(axis=(0, 1)) / ref[..., 4].sum()
+    assert np.allclose(part, full, rtol=0.2)
+    sc.set_progress_callback(None)
+    assert np.array_equal(integ.render(sc, 64).view(np.uint32), ref.view(np.uint32))

@@ -11,7 +11,8 @@ WELL_POSED = ["cbox_nopatch_256_spp16", "cbox_nopatch_64_spp64", "cbox_64_spp16_
               "cbox_64_spp16_depth2", "cbox_48_spp1", "cbox_64_spp16_shapes", "cbox_64_spp16_twosided", "cbox_64_spp16_direct",
               "cbox_64_spp16_stratified", "cbox_64_spp16_stratified_nojitter_pass4",
               "cbox_64_spp16_multijitter", "cbox_64_spp8_multijitter_nojitter", "cbox_64_spp16_shapes_textured", "cbox_64_spp16_constant", "cbox_64_spp16_constant_area",
-              "cbox_64_spp16_point", "cbox_64_spp16_point_area"]
+              "cbox_64_spp16_point", "cbox_64_spp16_point_area", "cbox_64_spp16_spot", "cbox_64_spp16_directional",
+              "cbox_64_spp25_orthogonal", "cbox_64_spp9_orthogonal_nojitter"]
 
 
 @pytest.mark.parametrize("name", G.names())
