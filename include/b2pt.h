@@ -217,6 +217,9 @@ typedef struct B2RenderParams {
     int32_t rank, world_size;   /* this process renders spiral blocks b with b % world == rank */
     uint32_t flags;             /* B2_FLAG_* */
     uint32_t sampler;           /* B2_SAMPLER_* (| B2_SAMPLER_NO_JITTER for stratified 'jitter' = false) */
+    /* DirectIntegrator (src/integrators/direct.cpp:78-196) instead of PathIntegrator: 'emitter_samples' / 'bsdf_samples'
+       (both 0 = path integrator; max_depth / rr_depth are ignored when either is set). */
+    uint32_t direct_emitter_samples, direct_bsdf_samples;
 } B2RenderParams;
 
 /* samplers: IndependentSampler (src/samplers/independent.cpp) and StratifiedSampler (src/samplers/stratified.cpp;

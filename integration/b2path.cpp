@@ -88,9 +88,13 @@ public:
 #if defined(B2_DIRECT)
         // DirectIntegrator (direct.cpp:78-100, 106-196) with its default shading_samples = 1 draws the same random numbers
         // in the same order, with the same MIS weights, as PathIntegrator with max_depth = 2
+        if (props.has_property("shading_samples") && (props.has_property("emitter_samples") || props.has_property("bsdf_samples")))
+            Throw("Cannot specify both 'shading_samples' and ('emitter_samples' and/or 'bsdf_samples').");     // direct.cpp:79-84
         size_t shading = props.size_("shading_samples", 1);
-        if (props.size_("emitter_samples", shading) != 1 || props.size_("bsdf_samples", shading) != 1)
-            NotImplementedError("b2direct: only emitter_samples = bsdf_samples = 1");
+        m_emitter_samples = (uint32_t) props.size_("emitter_samples", shading);
+        m_bsdf_samples = (uint32_t) props.size_("bsdf_samples", shading);
+        if (m_emitter_samples + m_bsdf_samples == 0)
+            Throw("Must have at least 1 BSDF or emitter sample!");                                                // direct.cpp:93-94
         m_max_depth = 2; m_rr_depth = 5;
 #endif
     }
@@ -326,6 +330,9 @@ public:
             }
             rp.block_size = block_size;
             rp.seed = m_seed; rp.rank = 0; rp.world_size = 1;
+            if (m_emitter_samples != 1 || m_bsdf_samples != 1) {       // (1, 1) is the path integrator with max_depth 2
+                rp.direct_emitter_samples = m_emitter_samples; rp.direct_bsdf_samples = m_bsdf_samples;
+            }
             {   // sampler plugin -> B2_SAMPLER_* ('jitter' is only printed, stratified.cpp:133-140)
                 std::string scls = sensor->sampler()->class_()->name();
                 if (scls == "StratifiedSampler")
@@ -557,6 +564,7 @@ private:
     }
 
     uint64_t m_seed;
+    uint32_t m_emitter_samples = 1, m_bsdf_samples = 1;       // b2direct only
     bool m_lbvh = false;
     std::atomic<B2Scene *> m_handle { nullptr };
 };

@@ -123,6 +123,7 @@ class B2RenderParams(C.Structure):
         ("seed", C.c_uint64),
         ("rank", C.c_int32), ("world_size", C.c_int32),
         ("flags", C.c_uint32), ("sampler", C.c_uint32),
+        ("direct_emitter_samples", C.c_uint32), ("direct_bsdf_samples", C.c_uint32),
     ]
 
 

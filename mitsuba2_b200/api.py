@@ -282,13 +282,22 @@ class PathIntegrator:
 
 
 class DirectIntegrator(PathIntegrator):
-    """DirectIntegrator (src/integrators/direct.cpp) for its default emitter_samples = bsdf_samples = 1: it consumes the
-    sampler exactly like PathIntegrator with max_depth = 2 and uses the same MIS weights (direct.cpp:106-196 vs
-    path.cpp:124-208; pinned by tests/golden/ref_cbox_64_spp16_direct.npz), so it runs on the same wavefront."""
+    """DirectIntegrator (src/integrators/direct.cpp:78-196): emitter_samples + bsdf_samples at the first hit, combined by
+    multiple importance sampling. With the default shading_samples = 1 it consumes the sampler exactly like PathIntegrator with
+    max_depth = 2 and uses the same MIS weights (pinned by tests/golden/ref_cbox_64_spp16_direct.npz), so that case runs as
+    such; any other combination runs the direct mode of the wavefront (B2RenderParams.direct_*)."""
 
-    def __init__(self, shading_samples=1, emitter_samples=None, bsdf_samples=None, samples_per_pass=0, block_size=32):
-        e = shading_samples if emitter_samples is None else emitter_samples
-        b = shading_samples if bsdf_samples is None else bsdf_samples
-        if e != 1 or b != 1:
-            raise NotImplementedError("DirectIntegrator: only emitter_samples = bsdf_samples = 1")
-        super().__init__(max_depth=2, rr_depth=5, samples_per_pass=samples_per_pass, block_size=block_size)
+    def __init__(self, shading_samples=1, emitter_samples=None, bsdf_samples=None, samples_per_pass=0, block_size=32, sampler="independent", jitter=True):
+        if shading_samples != 1 and (emitter_samples is not None or bsdf_samples is not None):
+            raise ValueError("Cannot specify both 'shading_samples' and ('emitter_samples' and/or 'bsdf_samples').")      # direct.cpp:79-84
+        self.emitter_samples = shading_samples if emitter_samples is None else emitter_samples
+        self.bsdf_samples = shading_samples if bsdf_samples is None else bsdf_samples
+        if self.emitter_samples + self.bsdf_samples == 0:
+            raise ValueError("Must have at least 1 BSDF or emitter sample!")                                               # direct.cpp:93-94
+        super().__init__(max_depth=2, rr_depth=5, samples_per_pass=samples_per_pass, block_size=block_size, sampler=sampler, jitter=jitter)
+
+    def params(self, *args, **kw):
+        rp = super().params(*args, **kw)
+        if (self.emitter_samples, self.bsdf_samples) != (1, 1):
+            rp.direct_emitter_samples, rp.direct_bsdf_samples = self.emitter_samples, self.bsdf_samples
+        return rp

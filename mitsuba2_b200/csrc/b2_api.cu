@@ -112,6 +112,7 @@ struct B2Scene {
     DBuf<float2> pos;
     DBuf<uint32_t> pixel, list, cnt, item_pixel, item_seed;
     DBuf<uint8_t> cls;
+    DBuf<float4> prim_o, prim_d, prim_hit; DBuf<int32_t> prim_inst;      // DirectIntegrator: the camera segment per lane
     DBuf<unsigned long long> stats;
     DBuf<float> film;
     DBuf<float> film_wide;          // wide filters: padded accumulation film, 8 floats / pixel
@@ -774,8 +775,14 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     if (total64 + slots >= 0xffffffffull) return fail(B2_ERR_INVALID, "too many work items (%llu)", (unsigned long long) total64);
 
     const size_t cap = (size_t) slots + 128;      // two lane sets, each rounded up to a multiple of 32
+    // DirectIntegrator (direct.cpp:78-100): E emitter samples + B BSDF samples at the camera hit
+    const uint32_t dE = rp->direct_emitter_samples, dB = rp->direct_bsdf_samples;
+    const bool direct = (dE | dB) != 0;
+    if (direct && (dE > 64 || dB > 64)) return fail(B2_ERR_INVALID, "direct integrator: at most 64 emitter / BSDF samples");
+    const size_t sh_cap = cap * (size_t) std::max<uint32_t>(dE, 1u);
     CU(s->ray_o.alloc(cap)); CU(s->ray_d.alloc(cap)); CU(s->hit.alloc(cap)); CU(s->tp.alloc(cap)); CU(s->res.alloc(cap));
-    CU(s->sh_o.alloc(cap)); CU(s->sh_d.alloc(cap)); CU(s->sh_c.alloc(cap));
+    CU(s->sh_o.alloc(sh_cap)); CU(s->sh_d.alloc(sh_cap)); CU(s->sh_c.alloc(sh_cap));
+    if (direct) { CU(s->prim_o.alloc(cap)); CU(s->prim_d.alloc(cap)); CU(s->prim_hit.alloc(cap)); CU(s->prim_inst.alloc(cap)); }
     CU(s->st.alloc(cap)); CU(s->pixel.alloc(cap)); CU(s->list.alloc(2 * cap));
     if (wide) CU(s->pos.alloc(cap));
     // persistent-warp traversal (dynamic ray fetch): always for instanced scenes; on request for the others (the flat
@@ -833,7 +840,14 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.pixel = s->pixel.p + o; q.list[0] = s->list.p + 2 * o; q.list[1] = s->list.p + 2 * o + set_slots;
         q.pos = wide ? s->pos.p + o : nullptr;
         q.hit_inst = inst ? s->hit_inst.p + o : nullptr; q.cls = inst ? s->cls.p + o : nullptr;
-        q.sh_o = s->sh_o.p + o; q.sh_d = s->sh_d.p + o; q.sh_c = s->sh_c.p + o;
+        const size_t so = o * (size_t) std::max<uint32_t>(dE, 1u);
+        q.sh_o = s->sh_o.p + so; q.sh_d = s->sh_d.p + so; q.sh_c = s->sh_c.p + so;
+        if (direct) {
+            q.direct_e = dE; q.direct_b = dB;
+            const float sum = (float) (dE + dB);                         // direct.cpp:96-100
+            q.d_weight_bsdf = 1.f / (float) dB; q.d_weight_lum = 1.f / (float) dE; q.d_frac_bsdf = (float) dB / sum; q.d_frac_lum = (float) dE / sum;
+            q.prim_o = s->prim_o.p + o; q.prim_d = s->prim_d.p + o; q.prim_hit = s->prim_hit.p + o; q.prim_inst = s->prim_inst.p + o;
+        }
         q.cnt = s->cnt.p + B2_CNT_WORDS * k; q.work = s->cnt.p + WORK_WORD; q.stats = s->stats.p;
         if (sampler_type != B2_SAMPLER_INDEPENDENT) {
             q.smp = s->smp.p + o; q.smp_count = rp->spp; q.smp_res = smp_res; q.smp_jitter = (rp->sampler & B2_SAMPLER_NO_JITTER) ? 0u : 1u;
@@ -843,6 +857,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.film = wide ? s->film_wide.p : s->film.p; q.item_pixel = s->item_pixel.p; q.item_seed = s->item_seed.p;
         q.n_items_pass = n_items_pass; q.n_passes = n_passes; q.spp_pass = spp_pass; q.block_size = bs; q.n_blocks_total = n_blocks;
         q.total_items = (uint32_t) total64; q.n_slots = set_slots; q.base_seed = rp->seed; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth;
+        if (direct) { q.max_depth = 2; q.rr_depth = 0x7fffffff; }          // (one bounce, no Russian roulette)
     }
 
     EventPool pool;
@@ -857,7 +872,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
     // non-independent samplers run in the extended (F_TEX) kernel variants
-    const uint32_t run_features = s->features | (sampler_type != B2_SAMPLER_INDEPENDENT ? (uint32_t) F_TEX : 0u);
+    const uint32_t run_features = s->features | ((sampler_type != B2_SAMPLER_INDEPENDENT || direct) ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
     const TraceFn trace_fn = trace_variant(inst, s->has_shapes, (rp->flags & B2_FLAG_COUNT_BVH) != 0);
     // (the limit is a per-function, process-wide attribute: set it for THIS scene right before its launches)
@@ -876,7 +891,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     cudaEvent_t evi0 = nullptr, evi1 = nullptr;
     if (timing) { evi0 = pool.make(true); evi1 = pool.make(true); if (evi0) cudaEventRecord(evi0, stream); }
     for (int k = 0; k < n_sets; ++k) {
-        if (sampler_type != B2_SAMPLER_INDEPENDENT) k_init<true><<<grid, threads, 0, stream>>>(s->d, qs[k]);
+        if (sampler_type != B2_SAMPLER_INDEPENDENT || direct) k_init<true><<<grid, threads, 0, stream>>>(s->d, qs[k]);
         else k_init<false><<<grid, threads, 0, stream>>>(s->d, qs[k]);
         ++launches;
     }

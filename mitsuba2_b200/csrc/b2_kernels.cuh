@@ -55,6 +55,12 @@ struct Queues {
     uint2 *smp;
     uint32_t smp_count, smp_res, smp_jitter, smp_type, smp_res_y;      // smp_res = m_resolution.x, smp_res_y = .y (multijitter)
     float smp_inv_count, smp_inv_res, smp_inv_res_y;
+    // DirectIntegrator (direct.cpp:78-196; extended kernel variants only): E emitter samples + B BSDF samples at the camera hit.
+    // The emitter samples of lane L are the shadow entries [L * E, (L + 1) * E) (maxt < 0: no entry; k_trace leaves the
+    // visibility in sh_c.w) and are summed in sample order; prim_* keep the camera segment, re-shaded for every BSDF sample.
+    uint32_t direct_e, direct_b;
+    float d_weight_bsdf, d_weight_lum, d_frac_bsdf, d_frac_lum;      // direct.cpp:96-100
+    float4 *prim_o, *prim_d, *prim_hit; int32_t *prim_inst;
 };
 
 // q.cnt words of one lane set (B2_CNT_WORDS each)
@@ -71,6 +77,7 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES 
 #define STW_FILM_DY      0x800u      //             ... y-1
 #define STW_FILM_DROP    0x1000u     // sample falls outside its block (imageblock.cpp:166)
 #define STW_PARKED       0x2000u     // the path ended inside the loop body: the lane only waits for its film put
+#define STW_DIRECT_EMIT  0x4000u     // DirectIntegrator: the lane's emitter samples have not been added to its result yet
 #define STW_LEFT(w)      ((w) >> 16)
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
@@ -532,7 +539,7 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         q.cnt[CNT_SHADOW + parity] = 0;                                  // the next k_shade appends there
         *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;   // consumed by the previous k_shade
-        atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
     uint32_t n_seg = 0;
     uint32_t counters[2] = { 0u, 0u };
@@ -556,11 +563,17 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
         }
         list_append(q, parity, i, cont, term, 0xffffffffu);
     }
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_shadow; j += gridDim.x * blockDim.x) {
-        float4 ro = q.sh_o[j], rd = q.sh_d[j];
+    uint32_t n_dsh = 0;
+    const uint32_t n_entries = q.direct_e ? q.n_slots * q.direct_e : n_shadow;      // (direct integrator: E entry slots per lane)
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_entries; j += gridDim.x * blockDim.x) {
+        float4 rd = q.sh_d[j];
+        if (q.direct_e && !(rd.w >= 0.f)) continue;
+        float4 ro = q.sh_o[j];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
         Hit h;
-        if (!traverse<true, INST, SHP, COUNT>(sc, sm, ray, h, counters)) {
+        const bool occluded = traverse<true, INST, SHP, COUNT>(sc, sm, ray, h, counters);
+        if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
+        else if (!occluded) {
             float4 c = q.sh_c[j];
             const uint32_t lw = __float_as_uint(c.w);
             float4 r = q.res[lw];
@@ -570,6 +583,7 @@ __global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
     if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_dsh); }
     if constexpr (COUNT) {
         uint32_t a = __reduce_add_sync(0xffffffffu, counters[0]), b = __reduce_add_sync(0xffffffffu, counters[1]);
         if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
@@ -602,10 +616,10 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         q.cnt[CNT_SHADOW + parity] = 0;
         *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;
-        atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
-    const uint32_t total = q.n_slots + n_shadow;
-    uint32_t n_seg = 0;
+    const uint32_t total = q.n_slots + (q.direct_e ? q.n_slots * q.direct_e : n_shadow);
+    uint32_t n_seg = 0, n_dsh = 0;
     int stack[B2_INST_STACK]; float sdist[B2_INST_STACK];
     Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f; tr.n_nodes = 0; tr.n_tris = 0;
     uint32_t item = 0;
@@ -742,6 +756,8 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     q.hit_inst[item] = h.inst;
                     q.cls[item] = (h.t < B2_INF && STW_DEPTH(q.st[item].w) < (uint32_t) q.max_depth) ? 1 : 2;
                     ++n_seg;
+                } else if (q.direct_e) {
+                    q.sh_c[item - q.n_slots].w = tr.any_hit ? 0.f : 1.f; ++n_dsh;
                 } else if (!tr.any_hit) {
                     const uint32_t j = item - q.n_slots;
                     float4 c = q.sh_c[j];
@@ -755,6 +771,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
     if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_dsh); }
     if constexpr (COUNT) {
         uint32_t a = __reduce_add_sync(0xffffffffu, tr.n_nodes), b = __reduce_add_sync(0xffffffffu, tr.n_tris);
         if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
@@ -957,6 +974,8 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
             if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
         } else if (valid)
             q.ray_d[lane] = make_float4(0.f, 0.f, 0.f, -1.f);
+        if constexpr (EXT) if (valid)
+            for (uint32_t i = 0; i < q.direct_e; ++i) q.sh_d[lane * q.direct_e + i] = make_float4(0.f, 0.f, 0.f, -1.f);
         uint32_t n_alive = __popc(__ballot_sync(0xffffffffu, alive));
         if (lane_id() == 0 && n_alive) atomicAdd(&q.cnt[CNT_ALIVE], n_alive);
     }
@@ -990,6 +1009,34 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
 #define B2_SHADE_MINBLOCKS 3
 #endif
 
+// DirectIntegrator (direct.cpp:167-176): BSDF samples b, b + 1, ... of the camera hit until one has a non-zero value (its ray is
+// traced next) or the B samples are spent. `si` / `bsdf` / `flip` as bsdf_side() left them.
+template <uint32_t F>
+B2_D bool direct_bsdf_samples(const Tables &tb, const Queues &q, const SI &si, const B2Bsdf &bsdf, bool flip, uint32_t &b,
+                              uint64_t &rng, uint2 &sm, float3 &bsdf_val, BS &bs) {
+    for (; b < q.direct_b; ++b) {
+        float2 s2 = smp_next_2d<true>(q, rng, sm);                             // (g++: next_2d before next_1d, direct.cpp:168-169)
+        float s1 = smp_next_1d<true>(q, rng, sm);
+        bsdf_val = bsdf_sample<F>(bsdf, si, s1, s2.x, s2.y, bs, bsdf_reflectance<F>(tb, bsdf, si));
+        if (flip) bs.wo.z = -bs.wo.z;
+        if (any_nonzero(bsdf_val)) return true;
+    }
+    return false;
+}
+// the lane's E emitter samples, in sample order, once k_trace has resolved their visibility (direct.cpp:161)
+B2_D float3 direct_add_emitter_samples(const Queues &q, uint32_t lane, float3 result) {
+    for (uint32_t i = 0; i < q.direct_e; ++i) {
+        const uint32_t j = lane * q.direct_e + i;
+        const float4 d4 = q.sh_d[j];
+        if (d4.w >= 0.f) {
+            const float4 c = q.sh_c[j];
+            if (c.w != 0.f) result = result + v3(c);
+            q.sh_d[j] = make_float4(0.f, 0.f, 0.f, -1.f);
+        }
+    }
+    return result;
+}
+
 // 32 CONTINUE lanes: one iteration of PathIntegrator::sample's loop body (path.cpp:124-208). Called by whole warps.
 template <uint32_t F>
 B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane) {
@@ -998,7 +1045,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
     float4 rd = q.ray_d[ld], ro = q.ray_o[ld], h = q.hit[ld], tpe = q.tp[ld], rs = q.res[ld];
     uint4 st = q.st[ld];
-    bool park = false, shadow = false, flip = false;
+    bool park = false, shadow = false, flip = false, direct_mode = false;
     float4 sho, shd, shc;
     float4 nro, nrd;                 // next ray
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
@@ -1035,7 +1082,50 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
             active = smp_next_1d<EXT>(q, rng, sm) < qq;
             throughput = throughput * b2_rcp(qq);
         }
-        if (!active) park = true;                                               // path.cpp:147-149
+        bool direct = false;
+        if constexpr (EXT) direct = (q.direct_e | q.direct_b) != 0;
+        direct_mode = direct;
+        if (direct) {
+            if constexpr (EXT) {        // DirectIntegrator::sample at the camera hit (direct.cpp:128-176)
+                bool smooth;
+                const B2Bsdf &bsdf = bsdf_side<F>(tb, si, flip, smooth);
+                for (uint32_t i = 0; i < q.direct_e; ++i) {                     // emitter sampling, direct.cpp:135-163
+                    const uint32_t j = lane * q.direct_e + i;
+                    float4 e_d = make_float4(0.f, 0.f, 0.f, -1.f);
+                    if (smooth) {
+                        float2 se = smp_next_2d<true>(q, rng, sm);
+                        DS ds; float3 emitter_val = scene_sample_emitter_direction<F>(tb, sc.env, si.p, se.x, se.y, ds);
+                        if (ds.pdf != 0.f) {
+                            float3 wo = to_local(si, ds.d);
+                            if (flip) wo.z = -wo.z;
+                            float3 bsdf_val = bsdf_eval<F>(bsdf, si, wo, bsdf_reflectance<F>(tb, bsdf, si));
+                            float bpdf = bsdf_pdf<F>(bsdf, si, wo);
+                            float mis = ds.delta ? 1.f : mis_weight(ds.pdf * q.d_frac_lum, bpdf * q.d_frac_bsdf) * q.d_weight_lum;
+                            float3 c = (bsdf_val * mis) * emitter_val;
+                            if (any_nonzero(c)) {
+                                q.sh_o[j] = make_float4(si.p.x, si.p.y, si.p.z, B2_RAY_EPS * (1.f + hmax_abs(si.p)));
+                                q.sh_c[j] = make_float4(c.x, c.y, c.z, 0.f);
+                                e_d = make_float4(ds.d.x, ds.d.y, ds.d.z, ds.dist * (1.f - B2_SHADOW_EPS));
+                            }
+                        }
+                    }
+                    q.sh_d[j] = e_d;
+                }
+                if (q.direct_e) st.w |= STW_DIRECT_EMIT;
+                q.prim_o[lane] = ro; q.prim_d[lane] = rd; q.prim_hit[lane] = h;
+                if (q.hit_inst) q.prim_inst[lane] = q.hit_inst[lane];
+                uint32_t b = 0; float3 bsdf_val; BS bs;                          // BSDF sampling, direct.cpp:167-176
+                if (!direct_bsdf_samples<F>(tb, q, si, tb.bsdfs[si.bsdf], flip, b, rng, sm, bsdf_val, bs)) park = true;
+                else {
+                    throughput = bsdf_val; eta = __uint_as_float(b);               // (tp.w carries the index of the sample in flight)
+                    float3 nd = to_world(si, bs.wo);
+                    nro = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
+                    nrd = make_float4(nd.x, nd.y, nd.z, B2_INF);
+                    bs_pdf = bs.pdf;
+                    st.w = (st.w & ~(0xffu | STW_DELTA)) | 2u | (bs.delta ? STW_DELTA : 0u);
+                }
+            }
+        } else if (!active) park = true;                                        // path.cpp:147-149
         else {
             bool smooth;
             const B2Bsdf &bsdf = bsdf_side<F>(tb, si, flip, smooth);            // (twosided: side record, wi.z mirrored)
@@ -1067,7 +1157,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     uint32_t sq_base = 0;
     if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
     // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
-    if (valid && !park) {
+    if (valid && !park && !direct_mode) {
         const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
         float2 s2 = smp_next_2d<EXT>(q, rng, sm); float s2x = s2.x, s2y = s2.y;
         float s1 = smp_next_1d<EXT>(q, rng, sm);
@@ -1111,6 +1201,8 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
 
 // 32 TERMINATE lanes: the path ends with this segment (miss, or a hit at the depth limit: path.cpp:128-149 up to the
 // break), or it was parked by shade_continue. Film put (ImageBlock::put) and regeneration. Called by whole warps.
+// DirectIntegrator (extended variants): a lane whose BSDF-sample ray came back adds that sample's contribution and, while
+// BSDF samples are left, re-shades the camera hit and leaves with the next sample's ray instead of finishing.
 template <uint32_t F>
 B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, bool valid, uint32_t lane, uint32_t &n_put, uint32_t &n_bad) {
     constexpr bool EXT = (F & F_TEX) != 0;
@@ -1119,13 +1211,21 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
     float4 h = q.hit[ld], tpe = q.tp[ld], rs = q.res[ld];
     uint32_t pix = q.pixel[ld];
     uint32_t item = st.z, left = STW_LEFT(st.w);
+    bool direct = false;
+    if constexpr (EXT) direct = (q.direct_e | q.direct_b) != 0;
     // the work-item fetch is issued first: its latency hides behind the emitter evaluation and the film put
-    const bool need = valid && left == 0;
-    const uint32_t w = warp_append(q.work, need);
+    // (direct integrator: only once it is known that the lane finishes its sample)
+    uint32_t w = 0;
+    if (!direct) w = warp_append(q.work, valid && left == 0);
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
     float3 result = v3(rs);
+    bool finishing = valid;
+    if constexpr (EXT) if (direct && valid && (st.w & STW_DIRECT_EMIT)) {
+        result = direct_add_emitter_samples(q, lane, result);
+        st.w &= ~STW_DIRECT_EMIT;
+    }
     if (valid && !(st.w & STW_PARKED)) {
         const int depth = (int) STW_DEPTH(st.w);
         const bool hit_valid = h.x < B2_INF;
@@ -1139,17 +1239,13 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
             const float4 rd = q.ray_d[lane], ro = q.ray_o[lane];
             SI si; si.emitter = emitter; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
             if (hit_valid) si_fill<EXT>(tb, __float_as_uint(h.w), h.x, h.y, h.z, v3(ro), v3(rd), q.hit_inst ? q.hit_inst[lane] : -1, si);
-            float emission_weight = 1.f;
-            if (depth > 1) {                                                      // path.cpp:194-205, records.h:168-174
-                float emitter_pdf = 0.f;
-                if (!(st.w & STW_DELTA)) {
-                    float3 dd = si.p - v3(ro);
-                    float dist = sqrtf(dot(dd, dd));
-                    dd = dd * b2_rcp(dist);
-                    if (!hit_valid) dd = v3(rd);                                  // d[!it.is_valid()] = -it.wi
-                    emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, v3(ro), dd, si.sh_n, dist);
-                }
-                emission_weight = mis_weight(bs_pdf, emitter_pdf);
+            float emitter_pdf = 0.f;
+            if (depth > 1 && !(st.w & STW_DELTA)) {                               // path.cpp:194-205, records.h:168-174
+                float3 dd = si.p - v3(ro);
+                float dist = sqrtf(dot(dd, dd));
+                dd = dd * b2_rcp(dist);
+                if (!hit_valid) dd = v3(rd);                                      // d[!it.is_valid()] = -it.wi
+                emitter_pdf = scene_pdf_emitter_direction<F>(tb, sc.env, si.emitter, v3(ro), dd, si.sh_n, dist);
             }
             float3 ev;
             bool miss = false;
@@ -1159,21 +1255,50 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
                 const DEmitter &em = tb.emitters[si.emitter];
                 ev = si.wi.z > 0.f ? v3(em.radiance[0], em.radiance[1], em.radiance[2]) : v3(0.f, 0.f, 0.f);   // area.cpp:63-71
             }
-            result = result + (throughput * emission_weight) * ev;
+            if (direct && depth > 1)                                              // direct.cpp:180-194
+                result = result + ((throughput * ev) * mis_weight(bs_pdf * q.d_frac_bsdf, emitter_pdf * q.d_frac_lum)) * q.d_weight_bsdf;
+            else {
+                const float emission_weight = depth > 1 ? mis_weight(bs_pdf, emitter_pdf) : 1.f;
+                result = result + (throughput * emission_weight) * ev;
+            }
         }
         // Russian roulette still draws its sample before the depth test ends the path (path.cpp:137-149): the sampler
         // stream of the work item continues into the next camera sample
         if (depth > q.rr_depth && hit_valid) (void) smp_next_1d<EXT>(q, rng, sm);
+        if constexpr (EXT) if (direct && depth > 1) {
+            // the next BSDF sample of the camera hit (direct.cpp:167-176), re-shaded from the stored camera segment
+            uint32_t b = __float_as_uint(tpe.w) + 1u;
+            if (b < q.direct_b) {
+                const float4 po = q.prim_o[lane], pd = q.prim_d[lane], ph = q.prim_hit[lane];
+                SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
+                si_fill<EXT>(tb, __float_as_uint(ph.w), ph.x, ph.y, ph.z, v3(po), v3(pd), q.hit_inst ? q.prim_inst[lane] : -1, si);
+                bool flip, smooth;
+                (void) bsdf_side<F>(tb, si, flip, smooth);
+                float3 bsdf_val; BS bs;
+                if (direct_bsdf_samples<F>(tb, q, si, tb.bsdfs[si.bsdf], flip, b, rng, sm, bsdf_val, bs)) {
+                    finishing = false;
+                    float3 nd = to_world(si, bs.wo);
+                    q.ray_o[lane] = make_float4(si.p.x, si.p.y, si.p.z, (1.f + hmax_abs(si.p)) * B2_RAY_EPS);
+                    q.ray_d[lane] = make_float4(nd.x, nd.y, nd.z, B2_INF);
+                    q.tp[lane] = make_float4(bsdf_val.x, bsdf_val.y, bsdf_val.z, __uint_as_float(b));
+                    q.res[lane] = make_float4(result.x, result.y, result.z, bs.pdf);
+                    st.w = (st.w & ~STW_DELTA) | (bs.delta ? STW_DELTA : 0u);
+                    q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+                    if (q.smp) q.smp[lane] = sm;
+                }
+            }
+        }
     }
+    if (direct) w = warp_append(q.work, finishing && left == 0);
     // ---- K6: ImageBlock::put ----
-    if (valid) {
+    if (finishing) {
         float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
         bool ok = film_put<(F & F_WIDE) != 0>(sc, q.film, pix & 0xffffu, pix >> 16, q.block_size, st.w, pos, result, (st.w & STW_ALPHA) != 0);
         ++n_put; n_bad += ok ? 0 : 1;
     }
     // ---- K1: regenerate ----
     bool retire = false;
-    if (valid) {
+    if (finishing) {
         Ray ray; uint32_t stw;
         if (regen_sample<EXT>(sc, q, lane, w, pix, item, left, rng, sm, ray, stw)) {
             q.ray_o[lane] = make_float4(ray.o.x, ray.o.y, ray.o.z, ray.mint);

@@ -1836,6 +1836,75 @@ static v3 path_sample(const oscene *s, const B2RenderParams *rp, osampler *rng, 
     return result;
 }
 
+/* DirectIntegrator::sample (direct.cpp:106-198) with emitter_samples = E, bsdf_samples = B */
+static v3 direct_sample(const oscene *s, const B2RenderParams *rp, osampler *rng, oray ray, int *valid_ray, int brute, ocount *cnt) {
+    const B2SceneDesc *d = s->desc;
+    const uint32_t E = rp->direct_emitter_samples, B = rp->direct_bsdf_samples;
+    const float sum = (float) (E + B);                                     /* direct.cpp:96-100 */
+    const float weight_bsdf = 1.f / (float) B, weight_lum = 1.f / (float) E, frac_bsdf = (float) B / sum, frac_lum = (float) E / sum;
+    v3 result = v3_make(0.f, 0.f, 0.f);
+    ohit h = scene_intersect(s, &ray, brute); cnt->segments++;
+    osi si; si_fill(s, &ray, &h, &si);
+    *valid_ray = h.t < INFINITY;
+    int emitter = (si.mesh != -1) ? si.emitter : s->env;                   /* visible emitters, direct.cpp:120-124 */
+    if (emitter >= 0) {
+        const B2Emitter *em = &d->emitters[emitter];
+        v3 ev;
+        if (si.mesh == -1) ev = env_eval(s, ray.d);
+        else ev = si.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f);
+        result = v3_add(result, ev);
+    }
+    if (!(si.t < INFINITY)) return result;
+    int flip, smooth;
+    const B2Bsdf bsdf_si = bsdf_at(d, &d->bsdfs[si.bsdf], &si, &flip, &smooth), *bsdf = &bsdf_si;
+    osi sib = si;
+    if (flip) sib.wi.z = -sib.wi.z;
+    if (smooth)                                                            /* emitter sampling, direct.cpp:135-163 */
+        for (uint32_t i = 0; i < E; ++i) {
+            float sx, sy; smp_next_2d(rng, &sx, &sy);
+            ods ds; v3 emitter_val = scene_sample_emitter_direction(s, si.p, sx, sy, &ds);
+            if (ds.pdf == 0.f) continue;
+            v3 wo = to_local(&si, ds.d);
+            if (flip) wo.z = -wo.z;
+            v3 bsdf_val = bsdf_eval(bsdf, &sib, wo);
+            float bpdf = bsdf_pdf(bsdf, &sib, wo);
+            float mis = ds.delta ? 1.f : mis_weight(ds.pdf * frac_lum, bpdf * frac_bsdf) * weight_lum;
+            v3 c = v3_mul(v3_scale(bsdf_val, mis), emitter_val);
+            if (c.x != 0.f || c.y != 0.f || c.z != 0.f) {                  /* scene.cpp:203-207 (see path_sample) */
+                oray sr; sr.o = si.p; sr.d = ds.d;
+                sr.mint = B2O_RAY_EPS * (1.f + v3_hmax_abs(si.p));
+                sr.maxt = ds.dist * (1.f - B2O_SHADOW_EPS);
+                cnt->shadow_rays++;
+                if (!scene_occluded(s, &sr, brute)) result = v3_add(result, c);
+            }
+        }
+    for (uint32_t i = 0; i < B; ++i) {                                      /* BSDF sampling, direct.cpp:167-195 */
+        float s2x, s2y; smp_next_2d(rng, &s2x, &s2y);                      /* g++: next_2d before next_1d */
+        float s1 = smp_next_1d(rng);
+        obs bs; v3 bsdf_val = bsdf_sample(bsdf, &sib, s1, s2x, s2y, &bs);
+        if (flip) bs.wo.z = -bs.wo.z;
+        if (!(bsdf_val.x != 0.f || bsdf_val.y != 0.f || bsdf_val.z != 0.f)) continue;
+        oray nr; nr.o = si.p; nr.d = to_world(&si, bs.wo);
+        nr.mint = (1.f + v3_hmax_abs(si.p)) * B2O_RAY_EPS; nr.maxt = INFINITY;
+        ohit h2 = scene_intersect(s, &nr, brute); cnt->segments++;
+        osi si2; si_fill(s, &nr, &h2, &si2);
+        int em2 = (si2.mesh != -1) ? si2.emitter : s->env;
+        if (em2 < 0) continue;
+        const B2Emitter *em = &d->emitters[em2];
+        v3 ev;
+        if (si2.mesh == -1) ev = env_eval(s, nr.d);
+        else ev = si2.wi.z > 0.f ? v3_make(em->radiance[0], em->radiance[1], em->radiance[2]) : v3_make(0.f, 0.f, 0.f);
+        v3 dd = v3_sub(si2.p, si.p);
+        float dist = sqrtf(v3_dot(dd, dd));
+        dd = v3_scale(dd, b2o_rcp(dist));
+        if (si2.mesh == -1) dd = nr.d;
+        float emitter_pdf = !bs.delta ? scene_pdf_emitter_direction(s, em2, si.p, dd, si2.sh_n, dist) : 0.f;
+        float w = mis_weight(bs.pdf * frac_bsdf, emitter_pdf * frac_lum);
+        result = v3_add(result, v3_scale(v3_scale(v3_mul(bsdf_val, ev), w), weight_bsdf));
+    }
+    return result;
+}
+
 /* ============================================================================================
  * Sensor + render driver — perspective.cpp:182-216, integrator.cpp:181-288, imageblock.cpp:79-172
  * ============================================================================================ */
@@ -1962,7 +2031,8 @@ static void render_item(ojob *j, uint32_t w, ocount *cnt, uint64_t *invalid, uin
                   ay = (psy - (float) film->crop_offset[1]) / (float) film->crop_size[1];   /* :254-256 */
             oray ray = sensor_sample_ray(&d->sensor, ax, ay);
             int valid;
-            v3 L = path_sample(j->s, rp, &rng, ray, &valid, j->brute, cnt);
+            v3 L = (rp->direct_emitter_samples | rp->direct_bsdf_samples) ? direct_sample(j->s, rp, &rng, ray, &valid, j->brute, cnt)
+                                                                           : path_sample(j->s, rp, &rng, ray, &valid, j->brute, cnt);
             /* ray_weight = 1 in rgb mode ; srgb_to_xyz spectrum.h:221-228 (M * rgb, matrix.h:170-177) */
             float val[5];
             val[0] = b2o_fma(0.180423f, L.z, b2o_fma(0.357580f, L.y, 0.412453f * L.x));

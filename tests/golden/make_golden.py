@@ -342,8 +342,8 @@ EXTRA_EMITTER_RADIANCE = (4.0, 16.0, 6.0)
 
 def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples_per_pass=None,
              rfilter="box", seed=0, materials=None, no_patch=False, mesh_dir=None, lift=0.0, extra_emitter=False, instances=None, envmap=None,
-             textures=False, crop=None, analytic=False, integrator="path", sampler="independent", jitter=True, point_light=None):
-    """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions."""
+             textures=False, crop=None, analytic=False, integrator="path", sampler="independent", jitter=True, point_light=None, direct=None):
+    """materials: optional {bsdf_id: xml-string} overriding the diffuse definitions. direct: (emitter_samples, bsdf_samples)"""
     bs = []
     for k, v in CBOX_BSDFS.items():
         if textures and k in TEX_SPEC:
@@ -431,7 +431,8 @@ def cbox_xml(width, height, spp, max_depth=6, rr_depth=5, block_size=32, samples
     if sampler != "independent":        # src/samplers/stratified.cpp
         xml = xml.replace('<sampler type="independent">', f'<sampler type="{sampler}">' + ("" if jitter else '<boolean name="jitter" value="false"/>'))
     if integrator == "direct":         # DirectIntegrator (src/integrators/direct.cpp): no depth parameters
-        xml = xml.replace('<integrator type="path">', '<integrator type="direct">')
+        xml = xml.replace('<integrator type="path">', '<integrator type="direct">' + (
+            f'<integer name="emitter_samples" value="{direct[0]}"/><integer name="bsdf_samples" value="{direct[1]}"/>' if direct else ""))
         xml = re.sub(r'\s*<integer name="(max_depth|rr_depth)" value="[^"]*"/>', "", xml)
     return xml
 
@@ -517,6 +518,10 @@ GOLDEN = {
     "cbox_64_spp16_twosided": dict(width=64, height=64, spp=16, no_patch=True, analytic=True, materials={"green": TWOSIDED_2, "box": TWOSIDED_1}),
     # the reference's `direct` integrator with its default shading_samples = 1 draws the same numbers in the same order as
     # `path` with max_depth = 2 (direct.cpp:106-196 vs path.cpp:124-208): rendered by `direct`, loaded as max_depth 2
+    # ... and with emitter_samples = 2, bsdf_samples = 3 (direct.cpp:106-196 proper)
+    "cbox_64_spp8_direct_e2_b3": dict(width=64, height=64, spp=8, no_patch=True, analytic=True, integrator="direct", direct=(2, 3)),
+    "cbox_64_spp8_direct_e3_b0": dict(width=64, height=64, spp=8, no_patch=True, integrator="direct", direct=(3, 0), materials=dict(box=ROUGH_GGX)),
+    "cbox_64_spp8_direct_e0_b2": dict(width=64, height=64, spp=8, no_patch=True, integrator="direct", direct=(0, 2), materials=dict(box=DIELECTRIC), lift=5.0),
     "cbox_64_spp16_direct": dict(width=64, height=64, spp=16, no_patch=True, analytic=True, integrator="direct", max_depth=2),
     # stratified sampler (with and without jitter; several passes re-seed and restart the strata like the reference)
     "cbox_64_spp16_stratified": dict(width=64, height=64, spp=16, no_patch=True, sampler="stratified"),

@@ -134,6 +134,8 @@ def load(name, host):
     rp = abi.render_params(max_depth=kw.get("max_depth", 6), rr_depth=kw.get("rr_depth", 5), spp=kw["spp"],
                            samples_per_pass=kw.get("samples_per_pass") or 0, block_size=kw.get("block_size", 32),
                            seed=kw.get("seed", 0), sampler=kw.get("sampler", "independent"), jitter=kw.get("jitter", True))
+    if kw.get("direct"):                 # DirectIntegrator with explicit sample counts (direct.cpp:78-100)
+        rp.direct_emitter_samples, rp.direct_bsdf_samples = kw["direct"]
     return sb, rp, z["rgb"]
 
 

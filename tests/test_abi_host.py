@@ -116,8 +116,14 @@ def test_scene_builders_reject_bad_input():
     d = sb.add_dielectric(1.5, 1.0)
     with pytest.raises(ValueError):
         sb.make_twosided(d)                                               # twosided.cpp:90-91
-    with pytest.raises(NotImplementedError):
-        api.DirectIntegrator(shading_samples=2)
+    with pytest.raises(ValueError):                                       # direct.cpp:79-84, 93-94
+        api.DirectIntegrator(shading_samples=2, emitter_samples=1)
+    with pytest.raises(ValueError):
+        api.DirectIntegrator(emitter_samples=0, bsdf_samples=0)
+    rp = api.DirectIntegrator(emitter_samples=2, bsdf_samples=3).params(8)
+    assert (rp.direct_emitter_samples, rp.direct_bsdf_samples, rp.max_depth) == (2, 3, 2)
+    rp = api.DirectIntegrator().params(8)                                 # shading_samples = 1 == path with max_depth 2
+    assert (rp.direct_emitter_samples, rp.direct_bsdf_samples, rp.max_depth) == (0, 0, 2)
 
 
 def test_parallel_bvh_build_is_deterministic():

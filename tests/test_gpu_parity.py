@@ -126,7 +126,8 @@ def test_instances_intersect_vs_bruteforce(b2, oracle):
                                   "cbox_64_spp16_point", "cbox_64_spp16_point_area",
                                   "cbox_64_spp16_roughglass_beckmann", "cbox_64_spp16_roughglass_ggx",
                                   "cbox_64_spp16_spot", "cbox_64_spp16_directional",
-                                  "cbox_64_spp25_orthogonal", "cbox_64_spp9_orthogonal_nojitter"])
+                                  "cbox_64_spp25_orthogonal", "cbox_64_spp9_orthogonal_nojitter",
+                                  "cbox_64_spp8_direct_e2_b3", "cbox_64_spp8_direct_e3_b0", "cbox_64_spp8_direct_e0_b2"])
 def test_render_bitexact_single_pass(b2, oracle, name):
     """Box filter + one pass: one lane owns a pixel and adds its samples in order, exactly like
     render_block -> the whole XYZAW film must match the oracle bit for bit."""

@@ -12,7 +12,8 @@ WELL_POSED = ["cbox_nopatch_256_spp16", "cbox_nopatch_64_spp64", "cbox_64_spp16_
               "cbox_64_spp16_stratified", "cbox_64_spp16_stratified_nojitter_pass4",
               "cbox_64_spp16_multijitter", "cbox_64_spp8_multijitter_nojitter", "cbox_64_spp16_shapes_textured", "cbox_64_spp16_constant", "cbox_64_spp16_constant_area",
               "cbox_64_spp16_point", "cbox_64_spp16_point_area", "cbox_64_spp16_spot", "cbox_64_spp16_directional",
-              "cbox_64_spp25_orthogonal", "cbox_64_spp9_orthogonal_nojitter"]
+              "cbox_64_spp25_orthogonal", "cbox_64_spp9_orthogonal_nojitter",
+              "cbox_64_spp8_direct_e2_b3", "cbox_64_spp8_direct_e3_b0", "cbox_64_spp8_direct_e0_b2"]
 
 
 @pytest.mark.parametrize("name", G.names())

@@ -216,6 +216,25 @@ def test_plugin_dropin_direct_integrator(tmp_path):
 
 @needs_ref
 @pytest.mark.gpu
+def test_plugin_dropin_direct_integrator_sample_counts(tmp_path):
+    """`<integrator type="direct">` with emitter_samples = 3, bsdf_samples = 2 vs `b2direct` (direct.cpp:106-196 proper)."""
+    import re
+    from tests import golden_cases as G
+
+    def xml(integrator):
+        s = _scene_xml("path").replace('<integrator type="path">', f'<integrator type="{integrator}"><integer name="emitter_samples" value="3"/>'
+                                       '<integer name="bsdf_samples" value="2"/>')
+        return re.sub(r'<integer name="max_depth" value="[^"]*"/>', "", s)
+    r0, ref_out = _run(xml("direct"), tmp_path, "ref_d2")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, b2_out = _run(xml("b2direct"), tmp_path, "b2_d2")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
+    assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 20, s
+
+
+@needs_ref
+@pytest.mark.gpu
 def test_plugin_dropin_stratified_sampler(tmp_path):
     """`<sampler type="stratified">` instantiated by the reference, recognised by the adapter and run on the GPU."""
     from tests import golden_cases as G
