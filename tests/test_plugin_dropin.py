@@ -295,3 +295,52 @@ def test_plugin_dropin_instances_and_analytic_shapes(tmp_path, device_bvh):
     assert r1.returncode == 0, r1.stdout + r1.stderr
     s = G.parity_stats(_read_pfm(b2_out), _read_pfm(ref_out))
     assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 40, s
+
+
+ACCEL = os.path.join(ROOT, "oracle", "_ref", "dist_b2accel")
+needs_accel = pytest.mark.skipif(not os.path.exists(os.path.join(ACCEL, "libmitsuba-render.so")),
+                                 reason="oracle/_ref/dist_b2accel not built (integration/build_accel_shim.sh)")
+
+
+def _run_accel(xml, tmp_path, name, threads=2):
+    """The reference CLI with the shim build of libmitsuba-render.so first on the library path (Scene::accel_* -> libb2pt)."""
+    env = dict(os.environ); env["LD_LIBRARY_PATH"] = ACCEL + ":" + DIST + ":" + env.get("LD_LIBRARY_PATH", "")
+    sp = str(tmp_path / f"{name}.xml"); out = str(tmp_path / f"{name}.pfm")
+    open(sp, "w").write(xml)
+    r = subprocess.run([os.path.join(DIST, "mitsuba"), "-m", "scalar_rgb", "-t", str(threads), "-o", out, sp], env=env, capture_output=True, text=True)
+    return r, out
+
+
+@needs_ref
+@needs_accel
+def test_accel_shim_fails_loudly_without_gpu(tmp_path):
+    from mitsuba2_b200 import api
+    if api.device_count() > 0:
+        pytest.skip("a GPU is present")
+    r, out = _run_accel(_scene_xml("path", res=16, spp=1), tmp_path, "acc")
+    assert r.returncode != 0 and "no CUDA device" in (r.stdout + r.stderr), r.stdout + r.stderr
+
+
+@needs_ref
+@needs_accel
+@pytest.mark.gpu
+def test_accel_shim_keeps_path_on_the_cpu(tmp_path):
+    """integration/scene_b2pt.inl: the reference's OWN `path` integrator runs on the CPU; only Scene::ray_intersect /
+    ray_test go to the GPU (one b2_stage_intersect / b2_stage_occluded call per ray — the boundary of
+    include/mitsuba/render/scene.h:184-205, not a fast path). Same image as the unmodified reference up to closest-hit
+    rounding (the well-posed cbox: ceiling patch removed)."""
+    from tests import golden_cases as G
+    import re
+    xml = _scene_xml("path", res=32, spp=4)
+    src = re.search(r'value="([^"]+cbox_ceiling\.obj)"', xml).group(1)
+    dst = str(tmp_path / "ceiling_nopatch.obj")
+    lines = open(src).read().splitlines()
+    faces = [ln for ln in lines if ln.startswith("f ")]
+    open(dst, "w").write("\n".join([ln for ln in lines if not ln.startswith("f ")] + faces[:1]) + "\n")
+    xml = xml.replace(src, dst)
+    r0, ref_out = _run(xml, tmp_path, "ref_acc")
+    assert r0.returncode == 0, r0.stdout + r0.stderr
+    r1, acc_out = _run_accel(xml, tmp_path, "b2_acc")
+    assert r1.returncode == 0, r1.stdout + r1.stderr
+    s = G.parity_stats(_read_pfm(acc_out), _read_pfm(ref_out))
+    assert s["median_rel"] < 2e-6 and s["rel_l2_unflipped"] < 1e-5 and s["flipped_pixels"] <= 10, s
