@@ -531,8 +531,11 @@ B2_D void list_append(const Queues &q, int parity, uint32_t lane, bool cont, boo
     if (term) q.list[parity][q.n_slots - 1u - ((uint32_t) (base >> 32) + __popc(mx & below))] = lane;
 }
 
+#ifndef B2_TRACE_MINBLOCKS
+#define B2_TRACE_MINBLOCKS 4
+#endif
 template <bool INST, bool SHP, bool COUNT>
-__global__ void __launch_bounds__(256, INST ? 3 : 4) k_trace(DScene sc, Queues q, int parity) {
+__global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
     const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];         // filled by the previous k_shade

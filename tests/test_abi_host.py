@@ -237,3 +237,40 @@ def test_c_record_builders_match_the_python_ones():
         assert np.array_equal(np.array(out.to_world[:]), np.array(ref.to_world[:]))
         # (the inverse is computed in double and rounded once on both sides, by different formulas: last-ulp agreement)
         assert np.allclose(np.array(out.to_object[:]), np.array(ref.to_object[:]), rtol=3e-7, atol=1e-9), (M, flip)
+
+
+def _bvh4_depth(nodes, n_nodes):
+    """levels of a BVH4 in the 128-byte node layout (child codes = words 24..27: > 0 inner node index)"""
+    codes = nodes[:n_nodes, 24:28].view(np.int32)
+    level = np.array([0]); depth = 0
+    while len(level):
+        depth += 1
+        c = codes[level].ravel()
+        level = c[c > 0]
+    return depth
+
+
+def test_host_bvh_depth_is_bounded():
+    """A 1 M-triangle multi-scale soup (triangle sizes over five decades, clustered): the binned-SAH builder alone goes 30+
+    levels deep on such input; the level budget (median splits once it runs short) keeps every tree within
+    B2_BVH_MAX_DEPTH = 42 levels, which is what the traversal kernels' 128-entry stacks are sized for — no mesh is refused
+    for its depth. Also: every triangle is referenced exactly once."""
+    L = api.lib()
+    L.b2_host_build_bvh4.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32), C.c_void_p]
+    rng = np.random.default_rng(7); n = 1_000_000
+    centres = rng.normal(size=(64, 3)) * 50
+    c = centres[rng.integers(0, 64, n)] + rng.normal(size=(n, 3)) * np.exp(rng.uniform(-6, 2, (n, 1)))
+    size = np.exp(rng.uniform(-9, 2, (n, 1, 1)))
+    tri = (c[:, None, :] + size * rng.normal(size=(n, 3, 3))).astype(np.float32)
+    tri[:1000] = tri[0]                                  # a thousand identical triangles (all centroids coincide)
+    nodes = np.zeros((n + 8, 32), np.float32); order = np.zeros(n, np.uint32); nn = C.c_uint32()
+    assert L.b2_host_build_bvh4(tri.ctypes.data, n, nodes.ctypes.data, len(nodes), C.byref(nn), order.ctypes.data) == 0
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))
+    d = _bvh4_depth(nodes, nn.value)
+    assert 8 <= d <= 42, d
+    # a long thin strip (SAH splits it one triangle at a time)
+    x = np.arange(200_000, dtype=np.float64)
+    strip = np.stack([np.stack([x * x * 1e-6, 0 * x, 0 * x], 1), np.stack([x * x * 1e-6 + 1e-3, 0 * x + 1, 0 * x], 1),
+                      np.stack([(x + 1) ** 2 * 1e-6, 0 * x, 0 * x + 1e-3], 1)], 1).astype(np.float32)
+    assert L.b2_host_build_bvh4(strip.ctypes.data, len(strip), nodes.ctypes.data, len(nodes), C.byref(nn), order.ctypes.data) == 0
+    assert _bvh4_depth(nodes, nn.value) <= 42
