@@ -10,7 +10,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 M = {"gpu__time_duration.sum": "duration", "dram__bytes_read.sum": "dram_read_bytes", "dram__bytes_write.sum": "dram_write_bytes",
-     "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_warp_instr", "sm__inst_executed.sum": "warp_instr",
+     "smsp__thread_inst_executed_per_inst_executed.ratio": "threads_per_warp_instr", "smsp__inst_executed.sum": "warp_instr",
      "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_active_pct",
      "launch__registers_per_thread": "registers", "lts__t_sector_hit_rate.pct": "l2_hit_pct", "l1tex__t_sector_hit_rate.pct": "l1_hit_pct",
      "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
@@ -36,12 +36,15 @@ def main():
     workload = sys.argv[1]
     rows = []
     for rep in sys.argv[2:]:
-        r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
-        rd = list(csv.reader(io.StringIO(r.stdout)))
+        if rep.endswith(".csv"):          # `ncu -i x.ncu-rep --page raw --csv` exported on the GPU box (the reports exceed gpurun's copy-back limit)
+            rd = list(csv.reader(open(rep)))
+        else:
+            r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
+            rd = list(csv.reader(io.StringIO(r.stdout)))
         hdr, units = rd[0], rd[1]
         for line in rd[2:]:
             d = dict(zip(hdr, line)); un = dict(zip(hdr, units))
-            row = {"kernel": d["Kernel Name"].split("(")[0], "report": os.path.basename(rep)}
+            row = {"kernel": d["Kernel Name"].split("(")[0].replace("void ", "").replace(", ", ";"), "report": os.path.basename(rep)}
             for k, name in M.items():
                 if k in d and d[k] != "":
                     row[name] = to_float(d[k], un[k])
