@@ -591,7 +591,11 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t defer_n;
     SmemScene sm = stage_scene(sc, smem_raw);
+#ifdef B2_NO_FLAT_DEFER       // A/B: every ray finishes its leaves in place (traverse_flat)
+    const bool flat = false;
+#else
     const bool flat = !INST && sc.n_flat_leaves != 0;                    // (warp-uniform)
+#endif
     DeferItem *defer = (DeferItem *) (smem_raw + ((16u + sc.smem_nodes * 128u + (sc.smem_tris ? sc.n_tris * 48u : 0u) + sc.n_flat_leaves * 32u + 15u) & ~15u));
     if (threadIdx.x == 0) defer_n = 0;
     ShadowQ shq; shq.load(q, parity ^ 1);                                // filled by the previous k_shade
@@ -669,7 +673,7 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
                 const uint32_t rest = mask & ~(1u << near_l);
                 if (!occluded && rest) {
                     const uint32_t k = atomicAdd(&defer_n, 1u);
-                    if (k < B2_DEFER_CAP) { DeferItem it; it.id = j | B2_DEFER_SHADOW; it.mask = rest; it.t = 0.f; it.u = 0.f; it.v = 0.f; it.slot = 0; it.prim = 0; it._pad = 0; defer[k] = it; deferred = true; }
+                    if (k < B2_DEFER_CAP) { DeferItem it; it.id = j | B2_DEFER_SHADOW; it.mask = rest; it.t = B2_INF; it.u = 0.f; it.v = 0.f; it.slot = 0; it.prim = 0; it._pad = 0; defer[k] = it; deferred = true; }
                     else occluded = flat_rest<true, COUNT>(sm, rest, ray, fr, tmax, h, counters);
                 }
             }
@@ -1128,15 +1132,20 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
 }
 
 // Small scenes: stage the shading tables (triangles, normals, CDFs, BSDF + emitter records) into
-// shared memory with one bulk copy and rebase the table pointers onto the copy.
-B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
+// shared memory with one bulk copy and rebase the table pointers onto the copy. Split into issue / wait so that the
+// caller can put its own first global load (the list counts) between the two: both round trips then overlap.
+B2_D void stage_shade_tables_issue(const DScene &sc, unsigned char *smem_raw) {
+    if (!sc.shade_smem) return;
+    uint64_t *mbar = (uint64_t *) smem_raw;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { mbar_expect_tx(mbar, sc.blob_bytes); stage_bulk(smem_raw + 16, sc.blob, sc.blob_bytes, mbar); }
+}
+B2_D Tables stage_shade_tables_wait(const DScene &sc, unsigned char *smem_raw) {
     Tables tb = make_tables(sc);
     if (!sc.shade_smem) return tb;
     uint64_t *mbar = (uint64_t *) smem_raw;
     unsigned char *dst = smem_raw + 16;
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) { mbar_expect_tx(mbar, sc.blob_bytes); stage_bulk(dst, sc.blob, sc.blob_bytes, mbar); }
     mbar_wait(mbar, 0);
     const unsigned char *g = sc.blob;
     tb.tri_pos = (const float4 *) (dst + ((const unsigned char *) sc.tri_pos - g));
@@ -1183,9 +1192,24 @@ B2_D float3 direct_add_emitter_samples(const Queues &q, uint32_t lane, float3 re
     return result;
 }
 
+// The emitter samples of a warp's previous CONTINUE chunk wait in the warp's shared-memory stash until the atomic that
+// reserved their shadow-queue range has returned: the reservation is issued at the end of phase 1 of chunk c and consumed
+// while chunk c + 1 waits for its queue loads (ncu, round 2: 19 % of k_shade's stall samples sat on that atomic's result).
+struct Pending { uint32_t mask, base; };
+B2_D void drain_pending(const Queues &q, const float4 *stash, Pending &p) {
+    if (p.mask == 0) return;                                   // (warp-uniform)
+    const uint32_t base = __shfl_sync(0xffffffffu, p.base, 0);
+    if (p.mask & (1u << lane_id())) {
+        const uint32_t sq = base + __popc(p.mask & ((1u << lane_id()) - 1u));
+        q.sh_o[sq] = stash[3 * lane_id()]; q.sh_d[sq] = stash[3 * lane_id() + 1]; q.sh_c[sq] = stash[3 * lane_id() + 2];
+    }
+    p.mask = 0;
+}
+
 // 32 CONTINUE lanes: one iteration of PathIntegrator::sample's loop body (path.cpp:124-208). Called by whole warps.
 template <uint32_t F>
-B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane, uint32_t subq) {
+B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane, uint32_t subq,
+                         float4 *stash, Pending &pend) {
     constexpr bool EXT = (F & F_TEX) != 0;
     // all queue loads are issued up front (one round trip)
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
@@ -1198,6 +1222,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
     const int depth = (int) STW_DEPTH(st.w);
+    drain_pending(q, stash, pend);       // (the queue loads above are in flight meanwhile)
     float3 throughput = v3(tpe), result = v3(rs);
     float eta = tpe.w, bs_pdf = rs.w;
     SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
@@ -1298,10 +1323,12 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     }
     __syncwarp();
     // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue. The atomic is issued
-    // here and its result is only consumed after phase 2 (latency hidden). ----
+    // here; the entries wait in the stash and are written by drain_pending() during the warp's next chunk ----
     const uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
     uint32_t sq_base = 0;
     if (lane_id() == 0 && sh_mask) sq_base = subq * q.sh_cap + atomicAdd(&q.cnt[CNT_SHADOW + parity * B2_SHQ + subq], __popc(sh_mask));
+    if (shadow) { stash[3 * lane_id()] = sho; stash[3 * lane_id() + 1] = shd; stash[3 * lane_id() + 2] = shc; }
+    pend.mask = sh_mask; pend.base = sq_base;
     // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
     if (valid && !park && !direct_mode) {
         const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
@@ -1330,10 +1357,6 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
         pb = __shfl_sync(0xffffffffu, pb, 0);
         if (park) q.list[parity ^ 1][q.n_slots - 1u - ((uint32_t) (pb >> 32) + __popc(pk_mask & ((1u << lane_id()) - 1u)))] = lane;
     }
-    if (sh_mask) {
-        const uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
-        if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
-    }
     if (valid) {
         if (park) { nrd = make_float4(0.f, 0.f, 0.f, -1.f); st.w |= STW_PARKED; }
         else q.ray_o[lane] = nro;
@@ -1350,7 +1373,8 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
 // DirectIntegrator (extended variants): a lane whose BSDF-sample ray came back adds that sample's contribution and, while
 // BSDF samples are left, re-shades the camera hit and leaves with the next sample's ray instead of finishing.
 template <uint32_t F>
-B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, bool valid, uint32_t lane, uint32_t &n_put, uint32_t &n_bad) {
+B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, bool valid, uint32_t lane, uint32_t &n_put, uint32_t &n_bad,
+                          const float4 *stash, Pending &pend) {
     constexpr bool EXT = (F & F_TEX) != 0;
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
     uint4 st = q.st[ld];
@@ -1363,6 +1387,7 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
     // (direct integrator: only once it is known that the lane finishes its sample)
     uint32_t w = 0;
     if (!direct) w = warp_append(q.work, valid && left == 0);
+    drain_pending(q, stash, pend);
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
@@ -1463,26 +1488,36 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
 template <uint32_t F>
 __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade); the load is issued before the table
-    // staging waits for its bulk copy, so that the two latencies overlap
-    const unsigned long long n_list = *(const volatile unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
-    const Tables tb = stage_shade_tables(sc, smem_raw);
+    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade): their counts are loaded between the
+    // issue of the table staging and the wait for its bulk copy, so that the two round trips overlap
+    stage_shade_tables_issue(sc, smem_raw);
+    unsigned long long n_list;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(n_list) : "l"(q.cnt + CNT_LIST + 2 * parity) : "memory");
+    const Tables tb = stage_shade_tables_wait(sc, smem_raw);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_FETCH] = 0;       // ray counter of the next k_trace_inst
     const uint32_t n_cont = (uint32_t) n_list, n_term = (uint32_t) (n_list >> 32);
     const uint32_t wc = (n_cont + 31u) >> 5, wt = (n_term + 31u) >> 5;
+    // the warp's stash (3 float4 per lane) behind the staged tables
+    float4 *stash = (float4 *) (smem_raw + ((16u + (sc.shade_smem ? sc.blob_bytes : 0u) + 15u) & ~15u)) + (threadIdx.x >> 5) * 96u;
+    Pending pend; pend.mask = 0; pend.base = 0;
     uint32_t n_put = 0, n_bad = 0;
+    // lane slot of this thread in chunk w: the w-th group of 32 entries of the CONTINUE list, then of the TERMINATE list
+    auto list_entry = [&](uint32_t w, bool &valid) -> uint32_t {
+        if (w < wc) { const uint32_t k = w * 32u + lane_id(); valid = k < n_cont; return valid ? q.list[parity][k] : 0u; }
+        const uint32_t k = (w - wc) * 32u + lane_id(); valid = k < n_term;
+        return valid ? q.list[parity][q.n_slots - 1u - k] : 0u;
+    };
+    bool valid = false, valid_next = false;
+    uint32_t slot = warp < wc + wt ? list_entry(warp, valid) : 0u, slot_next = 0u;
     for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
-        if (wi < wc) {
-            const uint32_t k = wi * 32u + lane_id();
-            const bool valid = k < n_cont;
-            shade_continue<F>(sc, tb, q, parity, valid, valid ? q.list[parity][k] : 0u, wi % B2_SHQ);
-        } else {
-            const uint32_t k = (wi - wc) * 32u + lane_id();
-            const bool valid = k < n_term;
-            shade_terminate<F>(sc, tb, q, valid, valid ? q.list[parity][q.n_slots - 1u - k] : 0u, n_put, n_bad);
-        }
+        // the list entry of the warp's NEXT chunk is fetched now and used one iteration later (one L2 round trip less per chunk)
+        if (wi + n_warps < wc + wt) slot_next = list_entry(wi + n_warps, valid_next);
+        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, wi % B2_SHQ, stash, pend);
+        else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad, stash, pend);
+        slot = slot_next; valid = valid_next;
     }
+    drain_pending(q, stash, pend);
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {
         if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
