@@ -522,8 +522,11 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.shapes = dshapes.empty() ? nullptr : (const DShape *) (s->blob.p + off_shp);
     if (any_uv || !texs.empty() || ns) s->features |= F_TEX;
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
-    // k_shade's dynamic shared memory: [mbarrier + the staged tables] + the per-warp stash of pending emitter samples (8 warps x 32 x 48 B)
-    s->shade_smem_bytes = (((d.shade_smem ? (int) blob_bytes : 0) + 16 + 15) & ~15) + 8 * 32 * 48;
+    // k_shade's dynamic shared memory: [mbarrier + the staged tables] (+ B2_OPT_STASH: the per-warp stash, 8 warps x 32 x 48 B)
+    s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
+#ifdef B2_OPT_STASH
+    s->shade_smem_bytes = ((s->shade_smem_bytes + 16 + 15) & ~15) + 8 * 32 * 48;
+#endif
     for (const B2Bsdf &b : bsdfs) {
         if (b.twosided_back != 0) {                                            // twosided.cpp:63-92
             if (b.twosided_back < 0 || (uint32_t) b.twosided_back > bsdfs.size()) { delete s; return fail(B2_ERR_INVALID, "twosided BSDF: bad back-side index"); }
@@ -663,7 +666,6 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         if (flat.size() / 2 <= 32 && s->flat_leaves.upload(flat) == cudaSuccess) { d.n_flat_leaves = (uint32_t) (flat.size() / 2); d.flat_leaves = s->flat_leaves.p; }
     }
     s->smem_bytes = 16 + (int) (d.smem_nodes * 128u + (d.smem_tris ? n_slots * 48u : 0u) + d.n_flat_leaves * 32u);
-    if (d.n_flat_leaves) s->smem_bytes = ((s->smem_bytes + 15) & ~15) + (int) (B2_DEFER_CAP * sizeof(DeferItem));     // k_trace's deferred-ray list
     int dev = 0; cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
     s->has_shapes = ns != 0;
@@ -781,8 +783,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     const uint32_t dE = rp->direct_emitter_samples, dB = rp->direct_bsdf_samples;
     const bool direct = (dE | dB) != 0;
     if (direct && (dE > 64 || dB > 64)) return fail(B2_ERR_INVALID, "direct integrator: at most 64 emitter / BSDF samples");
-    // (path mode: B2_SHQ sub-queues, each big enough for every B2_SHQ-th shading warp: <= cap + 64 * B2_SHQ entries in all)
-    const size_t sh_cap = direct ? cap * (size_t) std::max<uint32_t>(dE, 1u) : cap + 64 * B2_SHQ * 2;
+    const size_t sh_cap = cap * (size_t) std::max<uint32_t>(dE, 1u);
     CU(s->ray_o.alloc(cap)); CU(s->ray_d.alloc(cap)); CU(s->hit.alloc(cap)); CU(s->tp.alloc(cap)); CU(s->res.alloc(cap));
     CU(s->sh_o.alloc(sh_cap)); CU(s->sh_d.alloc(sh_cap)); CU(s->sh_c.alloc(sh_cap));
     if (direct) { CU(s->prim_o.alloc(cap)); CU(s->prim_d.alloc(cap)); CU(s->prim_hit.alloc(cap)); CU(s->prim_inst.alloc(cap)); }
@@ -792,7 +793,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // leaf scan of tiny scenes has no use for it)
     const bool inst = s->d.n_instances != 0 || ((rp->flags & B2_FLAG_PERSISTENT_TRACE) && s->d.n_flat_leaves == 0);
     if (inst) { CU(s->hit_inst.alloc(cap)); CU(s->cls.alloc(cap)); CU(cudaMemsetAsync(s->cls.p, 0, cap, stream)); }
-    CU(s->cnt.alloc(3 * B2_CNT_WORDS));
+    CU(s->cnt.alloc(32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
     // up and warns; here it is an error so that spp keeps its meaning)
@@ -823,7 +824,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         } else return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
         CU(s->smp.alloc(cap));
     }
-    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 3 * B2_CNT_WORDS * sizeof(uint32_t)));
+    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 32 * sizeof(uint32_t)));
 
     // The lane slots are split into two independent lane SETS, each with its own counters, lists and shadow
     // queue, driven on its own stream: while one set is in its (issue-bound) traversal launch the
@@ -833,7 +834,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     const int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
     const uint32_t set_slots = ((slots / n_sets) + 31u) & ~31u;
     if (n_sets > 1) slots = set_slots * n_sets;     // (allocations above were sized with the rounded-up count)
-    const int WORK_WORD = 2 * B2_CNT_WORDS;      // (cnt: two lane sets of B2_CNT_WORDS words, then the shared work-item counter)
+    const int WORK_WORD = 2 * B2_CNT_WORDS;
     Queues qs[2];
     for (int k = 0; k < n_sets; ++k) {
         Queues &q = qs[k];
@@ -843,9 +844,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.pixel = s->pixel.p + o; q.list[0] = s->list.p + 2 * o; q.list[1] = s->list.p + 2 * o + set_slots;
         q.pos = wide ? s->pos.p + o : nullptr;
         q.hit_inst = inst ? s->hit_inst.p + o : nullptr; q.cls = inst ? s->cls.p + o : nullptr;
-        // shadow queue of this set: direct mode E entries per lane; path mode B2_SHQ sub-queues of sh_cap entries
-        q.sh_cap = ((set_slots / 32u + B2_SHQ - 1u) / B2_SHQ + 1u) * 32u;
-        const size_t so = direct ? o * (size_t) std::max<uint32_t>(dE, 1u) : (size_t) k * ((size_t) q.sh_cap * B2_SHQ);
+        const size_t so = o * (size_t) std::max<uint32_t>(dE, 1u);
         q.sh_o = s->sh_o.p + so; q.sh_d = s->sh_d.p + so; q.sh_c = s->sh_c.p + so;
         if (direct) {
             q.direct_e = dE; q.direct_b = dB;
@@ -873,7 +872,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaEventRecord(ev0, stream));
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     if (wide) CU(cudaMemsetAsync(s->film_wide.p, 0, (size_t) W * H * 8 * sizeof(float), stream));
-    CU(cudaMemsetAsync(s->cnt.p, 0, 3 * B2_CNT_WORDS * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
     // non-independent samplers run in the extended (F_TEX) kernel variants
@@ -944,7 +943,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             ++iterations;
         }
         if (n_sets > 1) { CU(cudaEventRecord(evx, streams[1])); CU(cudaStreamWaitEvent(stream, evx, 0)); }
-        CU(cudaMemcpyAsync(s->h_cnt + 3 * B2_CNT_WORDS * slot, s->cnt.p, 3 * B2_CNT_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(s->h_cnt + 32 * slot, s->cnt.p, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
         if (n_sets > 1) CU(cudaStreamWaitEvent(streams[1], evb[slot], 0));     // keep the streams within one batch of each other
         pending[slot] = 1;
@@ -953,13 +952,11 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (pending[prev]) {
             CU(cudaEventSynchronize(evb[prev]));
             pending[prev] = 0;
-            const uint32_t *c = s->h_cnt + 3 * B2_CNT_WORDS * prev;
+            const uint32_t *c = s->h_cnt + 32 * prev;
             // finished when every lane retired (parked lanes count as alive) and no emitter sample is unresolved
             bool all = true;
-            for (int k = 0; k < n_sets; ++k) {
-                all = all && c[B2_CNT_WORDS * k + CNT_ALIVE] == 0;
-                for (int w = 0; w < 2 * B2_SHQ; ++w) all = all && c[B2_CNT_WORDS * k + CNT_SHADOW + w] == 0;
-            }
+            for (int k = 0; k < n_sets; ++k)
+                all = all && c[B2_CNT_WORDS * k + CNT_ALIVE] == 0 && c[B2_CNT_WORDS * k + CNT_SHADOW] == 0 && c[B2_CNT_WORDS * k + CNT_SHADOW + 1] == 0;
             if (all) done = true;
         }
         if (s->progress_fn) {
@@ -1161,21 +1158,19 @@ int b2_stage_shade(B2Scene *s, const B2RenderParams *rp, uint32_t n, float *ray_
     const size_t N = n, cap = (N + 31) & ~(size_t) 31;
     DBuf<float4> o, d, h, tp, res, so, sd, sc4; DBuf<uint4> st; DBuf<uint32_t> list, cnt, df, pix; DBuf<int32_t> di; DBuf<uint64_t> rng;
     DBuf<unsigned long long> stats; DBuf<float2> pos;
-    const uint32_t sub_cap = (uint32_t) (((cap / 32 + B2_SHQ - 1) / B2_SHQ + 1) * 32);
-    const size_t shq_cap = (size_t) sub_cap * B2_SHQ;
-    CU(o.alloc(cap)); CU(d.alloc(cap)); CU(h.alloc(cap)); CU(tp.alloc(cap)); CU(res.alloc(cap)); CU(so.alloc(shq_cap)); CU(sd.alloc(shq_cap)); CU(sc4.alloc(shq_cap));
-    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(B2_CNT_WORDS + 16)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(8)); CU(pos.alloc(cap));
+    CU(o.alloc(cap)); CU(d.alloc(cap)); CU(h.alloc(cap)); CU(tp.alloc(cap)); CU(res.alloc(cap)); CU(so.alloc(cap)); CU(sd.alloc(cap)); CU(sc4.alloc(cap));
+    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(32)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(8)); CU(pos.alloc(cap));
     H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16); H2D(h.p, hit, N * 16); H2D(tp.p, throughput_eta, N * 16); H2D(res.p, result_pdf, N * 16);
     H2D(rng.p, rng_state, N * 8); H2D(df.p, depth_flags, N * 4);
     if (s->d.n_instances) { CU(di.alloc(cap)); H2D(di.p, inst, N * 4); }
-    CU(cudaMemsetAsync(cnt.p, 0, (B2_CNT_WORDS + 16) * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, 64, s->stream));
+    CU(cudaMemsetAsync(cnt.p, 0, 32 * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, 64, s->stream));
     k_stage_pack<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, h.p, rng.p, df.p, st.p, list.p);
     const unsigned long long n_list = (unsigned long long) n;        // n CONTINUE lanes, no TERMINATE lanes
     H2D(cnt.p + CNT_LIST, &n_list, 8);
     Queues q{};
     q.ray_o = o.p; q.ray_d = d.p; q.hit = h.p; q.hit_inst = s->d.n_instances ? di.p : nullptr; q.tp = tp.p; q.res = res.p; q.st = st.p; q.pixel = pix.p;
     q.pos = (s->features & F_WIDE) ? pos.p : nullptr;
-    q.sh_o = so.p; q.sh_d = sd.p; q.sh_c = sc4.p; q.sh_cap = sub_cap; q.list[0] = list.p; q.list[1] = list.p + cap; q.cnt = cnt.p; q.work = cnt.p + B2_CNT_WORDS; q.stats = stats.p;
+    q.sh_o = so.p; q.sh_d = sd.p; q.sh_c = sc4.p; q.list[0] = list.p; q.list[1] = list.p + cap; q.cnt = cnt.p; q.work = cnt.p + 16; q.stats = stats.p;
     q.film = nullptr; q.n_slots = (uint32_t) cap; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth; q.base_seed = rp->seed;
     q.n_items_pass = 1; q.n_passes = 1; q.spp_pass = 1; q.block_size = rp->block_size ? rp->block_size : 32; q.n_blocks_total = 1; q.total_items = 0;
     const ShadeFn fn = shade_variant(s->features);
@@ -1183,23 +1178,15 @@ int b2_stage_shade(B2Scene *s, const B2RenderParams *rp, uint32_t n, float *ray_
     fn<<<stage_grid(s, n), 256, s->shade_smem_bytes, s->stream>>>(s->d, q, 0);
     CU(cudaGetLastError());
     k_stage_unpack<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(n, st.p, rng.p, df.p);
-    uint32_t hc[B2_CNT_WORDS];
+    uint32_t hc[8];
     D2H(hc, cnt.p, sizeof hc);
     D2H(ray_o, o.p, N * 16); D2H(ray_d, d.p, N * 16); D2H(throughput_eta, tp.p, N * 16); D2H(result_pdf, res.p, N * 16);
     D2H(rng_state, rng.p, N * 8); D2H(depth_flags, df.p, N * 4);
     SYNC();
-    uint32_t ns = 0;
-    for (int k = 0; k < B2_SHQ; ++k) {                 // the sub-queues, one after the other
-        const uint32_t c = hc[CNT_SHADOW + k];
-        if (c > sub_cap || ns + c > n) return fail(B2_ERR_CUDA, "b2_stage_shade: shadow queue overflow");
-        if (c) {
-            D2H(sh_o + 4 * (size_t) ns, so.p + (size_t) k * sub_cap, (size_t) c * 16); D2H(sh_d + 4 * (size_t) ns, sd.p + (size_t) k * sub_cap, (size_t) c * 16);
-            D2H(sh_c + 4 * (size_t) ns, sc4.p + (size_t) k * sub_cap, (size_t) c * 16);
-        }
-        ns += c;
-    }
-    SYNC();
+    const uint32_t ns = hc[CNT_SHADOW];
+    if (ns > n) return fail(B2_ERR_CUDA, "b2_stage_shade: shadow queue overflow");
     *n_shadow = ns;
+    if (ns) { D2H(sh_o, so.p, (size_t) ns * 16); D2H(sh_d, sd.p, (size_t) ns * 16); D2H(sh_c, sc4.p, (size_t) ns * 16); SYNC(); }
     return B2_OK;
 }
 

@@ -35,8 +35,7 @@ struct Queues {
     uint4 *st;                  // (rng.lo, rng.hi, work item, depth|flags|samples_left)          16 B
     uint32_t *pixel;            // x | y << 16 of the lane's work item (crop-relative)             4 B
     float2 *pos;                // position_sample, only for wide (non-box) filters
-    float4 *sh_o, *sh_d, *sh_c; // dense shadow queue (B2_SHQ sub-queues of sh_cap entries): ray + (contrib.rgb, lane bits)
-    uint32_t sh_cap;            // capacity of one sub-queue
+    float4 *sh_o, *sh_d, *sh_c; // dense shadow queue: ray + (contrib.rgb, lane bits)
     uint8_t *cls;               // k_trace_inst -> k_classify: 0 no ray, 1 the path goes on, 2 the path ends with this segment   1 B
     uint32_t *list[2];          // per iteration parity: CONTINUE lanes from the front, TERMINATE lanes from the back   8 B
     uint32_t *cnt;              // per lane set: see CNT_*
@@ -64,12 +63,10 @@ struct Queues {
     float4 *prim_o, *prim_d, *prim_hit; int32_t *prim_inst;
 };
 
-// q.cnt words of one lane set (B2_CNT_WORDS each). The shadow queue is split into B2_SHQ sub-queues (a shading warp appends to
-// sub-queue `chunk % B2_SHQ`): eight counters instead of one hot address for ten thousand warp-level atomics per launch.
-#define B2_SHQ 8
-enum { CNT_SHADOW = 0 /* [parity * B2_SHQ + sub-queue]: double buffered by iteration parity */, CNT_ALIVE = 16, CNT_FETCH = 17 /* k_trace_inst's ray counter */,
-       CNT_LIST = 18 /* and 20: 64-bit (n_continue | n_terminate << 32) per iteration parity */ };
-#define B2_CNT_WORDS 32
+// q.cnt words of one lane set (B2_CNT_WORDS each)
+enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */,
+       CNT_LIST = 4 /* and 6: 64-bit (n_continue | n_terminate << 32) per iteration parity */ };
+#define B2_CNT_WORDS 8
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES = 4, ST_TRIS = 5 };
 
 // st.w layout
@@ -326,86 +323,62 @@ struct Trav {
 // tests at full lane utilisation.
 B2_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-struct FlatRay {        // slab-test form of a ray for the flat leaf scan
-    float idx, idy, idz, oox, ooy, ooz;
-    B2_D void set(const Ray &ray) {
-        float dx = copysignf(fmaxf(fabsf(ray.d.x), 1e-20f), ray.d.x), dy = copysignf(fmaxf(fabsf(ray.d.y), 1e-20f), ray.d.y),
-              dz = copysignf(fmaxf(fabsf(ray.d.z), 1e-20f), ray.d.z);
-        idx = rcp_approx(dx); idy = rcp_approx(dy); idz = rcp_approx(dz);
-        oox = -(ray.o.x * idx); ooy = -(ray.o.y * idy); ooz = -(ray.o.z * idz);
-    }
-    B2_D float entry(const SmemScene &sm, uint32_t l, float mint) const {
-        float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
-        float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
-              z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
-        return fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), mint));
-    }
-};
-// the uniform scan over all leaf boxes: bit mask of the boxes the ray pierces, the nearest one and the entry distance of the
-// second nearest (if that is beyond the hit found in the nearest leaf, no other leaf needs to be looked at)
-B2_D uint32_t flat_scan(const DScene &sc, const SmemScene &sm, const Ray &ray, const FlatRay &fr, uint32_t &near_l, float &second_t) {
-    const uint32_t n = sc.n_flat_leaves;
-    uint32_t mask = 0; float near_t = B2_INF; near_l = 0; second_t = B2_INF;
-    const float tlim = ray.maxt * 1.0000004f;
-    #pragma unroll 4
-    for (uint32_t l = 0; l < n; ++l) {
-        float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
-        float x0 = b2_fma(lo.x, fr.idx, fr.oox), x1 = b2_fma(hi.x, fr.idx, fr.oox), y0 = b2_fma(lo.y, fr.idy, fr.ooy), y1 = b2_fma(hi.y, fr.idy, fr.ooy),
-              z0 = b2_fma(lo.z, fr.idz, fr.ooz), z1 = b2_fma(hi.z, fr.idz, fr.ooz);
-        float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
-        float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tlim));
-        bool h = tn <= tf;
-        if (h) mask |= 1u << l;
-        if (h) {
-            if (tn < near_t) { second_t = near_t; near_t = tn; near_l = l; }
-            else second_t = fminf(second_t, tn);
-        }
-    }
-    return mask;
-}
-// the primitives of leaf l; returns true when an any-hit ray is done
-template <bool ANY, bool COUNT>
-B2_D bool flat_leaf(const SmemScene &sm, uint32_t l, const Ray &ray, float &tmax, Hit &best, uint32_t *counters) {
-    uint32_t code = __float_as_uint(sm.flat[2 * l].w);
-    uint32_t s0 = code & 0x07ffffffu, cnt = (code >> 27) & 0xfu;
-    if constexpr (COUNT) counters[1] += cnt;
-    for (uint32_t s = s0; s < s0 + cnt; ++s) {
-        float4 a0 = sm.tris[3 * s], a1 = sm.tris[3 * s + 1], a2 = sm.tris[3 * s + 2];
-        float t, u, v;
-        if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
-            if (ANY) return true;
-            uint32_t prim = __float_as_uint(a0.w);
-            if (t < best.t || (t == best.t && prim > best.prim)) {
-                best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim;
-                tmax = t;
-            }
-        }
-    }
-    return false;
-}
-// the remaining pierced leaves (bit mask), each re-checked against the best hit so far
-template <bool ANY, bool COUNT>
-B2_D bool flat_rest(const SmemScene &sm, uint32_t mask, const Ray &ray, const FlatRay &fr, float &tmax, Hit &best, uint32_t *counters) {
-    while (mask) {
-        const uint32_t l = (uint32_t) __ffs((int) mask) - 1u;
-        mask &= ~(1u << l);
-        if (!ANY && best.t < B2_INF && fr.entry(sm, l, ray.mint) > tmax * 1.0000004f) continue;      // culled by the best hit
-        if (flat_leaf<ANY, COUNT>(sm, l, ray, tmax, best, counters)) return true;
-    }
-    return false;
-}
-
 template <bool ANY, bool COUNT = false>
 B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, Hit &best, uint32_t *counters = nullptr) {
     best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu; best.inst = -1;
     float tmax = ray.maxt;
-    FlatRay fr; fr.set(ray);
-    if constexpr (COUNT) counters[0] += (sc.n_flat_leaves + 3u) / 4u;       // n leaf boxes = n / 4 BVH4 nodes' worth of box tests
-    uint32_t near_l; float second_t;
-    uint32_t mask = flat_scan(sc, sm, ray, fr, near_l, second_t);
-    if (!mask) return false;
-    if (flat_leaf<ANY, COUNT>(sm, near_l, ray, tmax, best, counters)) return true;
-    if (flat_rest<ANY, COUNT>(sm, mask & ~(1u << near_l), ray, fr, tmax, best, counters)) return true;
+    float dx = copysignf(fmaxf(fabsf(ray.d.x), 1e-20f), ray.d.x), dy = copysignf(fmaxf(fabsf(ray.d.y), 1e-20f), ray.d.y),
+          dz = copysignf(fmaxf(fabsf(ray.d.z), 1e-20f), ray.d.z);
+    const float idx = rcp_approx(dx), idy = rcp_approx(dy), idz = rcp_approx(dz);
+    const float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
+    const uint32_t n = sc.n_flat_leaves;
+    if constexpr (COUNT) counters[0] += (n + 3u) / 4u;            // n leaf boxes = n / 4 BVH4 nodes' worth of box tests
+    uint32_t mask = 0; float near_t = B2_INF; uint32_t near_l = 0;
+    {
+        const float tlim = tmax * 1.0000004f;
+        #pragma unroll 4
+        for (uint32_t l = 0; l < n; ++l) {
+            float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+            float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                  z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+            float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+            float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tlim));
+            bool h = tn <= tf;
+            if (h) mask |= 1u << l;
+            if (h && tn < near_t) { near_t = tn; near_l = l; }
+        }
+    }
+    bool first = mask != 0;
+    while (mask) {
+        uint32_t l;
+        if (first) { l = near_l; first = false; }
+        else {
+            l = (uint32_t) __ffs((int) mask) - 1u;
+            if (!ANY && best.t < B2_INF) {      // still closer than the best hit?
+                float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+                float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                      z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+                float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+                if (tn > tmax * 1.0000004f) { mask &= ~(1u << l); continue; }
+            }
+        }
+        mask &= ~(1u << l);
+        uint32_t code = __float_as_uint(sm.flat[2 * l].w);
+        uint32_t s0 = code & 0x07ffffffu, cnt = (code >> 27) & 0xfu;
+        if constexpr (COUNT) counters[1] += cnt;
+        for (uint32_t s = s0; s < s0 + cnt; ++s) {
+            float4 a0 = sm.tris[3 * s], a1 = sm.tris[3 * s + 1], a2 = sm.tris[3 * s + 2];
+            float t, u, v;
+            if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
+                if (ANY) return true;
+                uint32_t prim = __float_as_uint(a0.w);
+                if (t < best.t || (t == best.t && prim > best.prim)) {
+                    best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim;
+                    tmax = t;
+                }
+            }
+        }
+    }
     return best.t < B2_INF;
 }
 
@@ -544,23 +517,6 @@ B2_D bool film_put(const DScene &sc, float *film, uint32_t px, uint32_t py, uint
 // scene.cpp:203-207): unoccluded => `result += contribution` (path.cpp:171). Both kinds of ray are independent
 // (a shadow entry only touches `res`, which the closest-hit part does not read), so they share one launch:
 // one tail and one shared-memory staging instead of two.
-// the shadow sub-queues written by the previous k_shade: prefix sums of their counts, and entry j -> its array index
-struct ShadowQ {
-    uint32_t pre[B2_SHQ + 1];
-    B2_D void load(const Queues &q, int parity) {
-        pre[0] = 0;
-        #pragma unroll
-        for (int k = 0; k < B2_SHQ; ++k) pre[k + 1] = pre[k] + q.cnt[CNT_SHADOW + parity * B2_SHQ + k];
-    }
-    B2_D uint32_t total() const { return pre[B2_SHQ]; }
-    B2_D uint32_t index(const Queues &q, uint32_t j) const {
-        uint32_t k = 0, first = 0;
-        #pragma unroll
-        for (int i = 1; i < B2_SHQ; ++i) if (j >= pre[i]) { k = (uint32_t) i; first = pre[i]; }
-        return k * q.sh_cap + (j - first);
-    }
-};
-
 B2_D void list_append(const Queues &q, int parity, uint32_t lane, bool cont, bool term, uint32_t mask) {
     // `mask`: the lanes of the warp executing this call together
     const uint32_t mc = __ballot_sync(mask, cont), mx = __ballot_sync(mask, term);
@@ -578,34 +534,16 @@ B2_D void list_append(const Queues &q, int parity, uint32_t lane, bool cont, boo
 #ifndef B2_TRACE_MINBLOCKS
 #define B2_TRACE_MINBLOCKS 4
 #endif
-// Flat scenes: the leaf scan is a uniform loop, but the number of leaves a ray then has to LOOK INTO varies (measured on the
-// cbox: 1.07 on average, up to 4 — the warp ran 8 triangle-test rounds with 3 of 32 lanes active in six of them). So the
-// traversal is split: phase 1 = scan + the nearest leaf, for every lane (dense); a ray that still has candidate leaves
-// in front of its hit is DEFERRED to a per-CTA shared-memory list and finished in phase 2, where the list is processed densely.
-struct DeferItem { uint32_t id, mask; float t, u, v; uint32_t slot, prim, _pad; };      // 32 B
-#define B2_DEFER_CAP 768
-#define B2_DEFER_SHADOW 0x80000000u
-
 template <bool INST, bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ uint32_t defer_n;
     SmemScene sm = stage_scene(sc, smem_raw);
-#ifdef B2_NO_FLAT_DEFER       // A/B: every ray finishes its leaves in place (traverse_flat)
-    const bool flat = false;
-#else
-    const bool flat = !INST && sc.n_flat_leaves != 0;                    // (warp-uniform)
-#endif
-    DeferItem *defer = (DeferItem *) (smem_raw + ((16u + sc.smem_nodes * 128u + (sc.smem_tris ? sc.n_tris * 48u : 0u) + sc.n_flat_leaves * 32u + 15u) & ~15u));
-    if (threadIdx.x == 0) defer_n = 0;
-    ShadowQ shq; shq.load(q, parity ^ 1);                                // filled by the previous k_shade
-    const uint32_t n_shadow = shq.total();
-    if (blockIdx.x == 0 && threadIdx.x < B2_SHQ) q.cnt[CNT_SHADOW + parity * B2_SHQ + threadIdx.x] = 0;   // the next k_shade appends there
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];         // filled by the previous k_shade
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[CNT_SHADOW + parity] = 0;                                  // the next k_shade appends there
         *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;   // consumed by the previous k_shade
         if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
-    if (flat) __syncthreads();
     uint32_t n_seg = 0;
     uint32_t counters[2] = { 0u, 0u };
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -618,67 +556,25 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
                 float4 ro = q.ray_o[i];
                 const uint32_t stw = q.st[i].w;
                 Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-                Hit h;
-                bool deferred = false;
-                if (flat) {
-                    // phase 1: scan + nearest leaf
-                    h.t = B2_INF; h.u = 0.f; h.v = 0.f; h.slot = 0xffffffffu; h.prim = 0xffffffffu; h.inst = -1;
-                    float tmax = ray.maxt;
-                    FlatRay fr; fr.set(ray);
-                    if constexpr (COUNT) counters[0] += (sc.n_flat_leaves + 3u) / 4u;
-                    uint32_t near_l; float second_t;
-                    uint32_t mask = flat_scan(sc, sm, ray, fr, near_l, second_t);
-                    if (mask) {
-                        flat_leaf<false, COUNT>(sm, near_l, ray, tmax, h, counters);
-                        const uint32_t rest = mask & ~(1u << near_l);
-                        if (rest && second_t <= tmax * 1.0000004f) {      // another pierced leaf starts in front of the hit
-                            const uint32_t k = atomicAdd(&defer_n, 1u);
-                            if (k < B2_DEFER_CAP) {
-                                DeferItem it; it.id = i; it.mask = rest; it.t = h.t; it.u = h.u; it.v = h.v; it.slot = h.slot; it.prim = h.prim; it._pad = 0;
-                                defer[k] = it; deferred = true;
-                            } else flat_rest<false, COUNT>(sm, rest, ray, fr, tmax, h, counters);      // (list full: finish here)
-                        }
-                    }
-                } else traverse<false, INST, SHP, COUNT>(sc, sm, ray, h, counters);
+                Hit h; traverse<false, INST, SHP, COUNT>(sc, sm, ray, h, counters);
+                q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+                if (INST) q.hit_inst[i] = h.inst;
                 ++n_seg;
-                if (!deferred) {
-                    q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
-                    if (INST) q.hit_inst[i] = h.inst;
-                    cont = h.t < B2_INF && STW_DEPTH(stw) < (uint32_t) q.max_depth;
-                    term = !cont;
-                }
+                cont = h.t < B2_INF && STW_DEPTH(stw) < (uint32_t) q.max_depth;
+                term = !cont;
             }
         }
         list_append(q, parity, i, cont, term, 0xffffffffu);
     }
     uint32_t n_dsh = 0;
     const uint32_t n_entries = q.direct_e ? q.n_slots * q.direct_e : n_shadow;      // (direct integrator: E entry slots per lane)
-    for (uint32_t jj = blockIdx.x * blockDim.x + threadIdx.x; jj < n_entries; jj += gridDim.x * blockDim.x) {
-        const uint32_t j = q.direct_e ? jj : shq.index(q, jj);
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_entries; j += gridDim.x * blockDim.x) {
         float4 rd = q.sh_d[j];
         if (q.direct_e && !(rd.w >= 0.f)) continue;
         float4 ro = q.sh_o[j];
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
         Hit h;
-        bool occluded = false, deferred = false;
-        if (flat) {
-            h.t = B2_INF; h.prim = 0xffffffffu;
-            float tmax = ray.maxt;
-            FlatRay fr; fr.set(ray);
-            if constexpr (COUNT) counters[0] += (sc.n_flat_leaves + 3u) / 4u;
-            uint32_t near_l; float second_t;
-            uint32_t mask = flat_scan(sc, sm, ray, fr, near_l, second_t);
-            if (mask) {
-                occluded = flat_leaf<true, COUNT>(sm, near_l, ray, tmax, h, counters);
-                const uint32_t rest = mask & ~(1u << near_l);
-                if (!occluded && rest) {
-                    const uint32_t k = atomicAdd(&defer_n, 1u);
-                    if (k < B2_DEFER_CAP) { DeferItem it; it.id = j | B2_DEFER_SHADOW; it.mask = rest; it.t = B2_INF; it.u = 0.f; it.v = 0.f; it.slot = 0; it.prim = 0; it._pad = 0; defer[k] = it; deferred = true; }
-                    else occluded = flat_rest<true, COUNT>(sm, rest, ray, fr, tmax, h, counters);
-                }
-            }
-        } else occluded = traverse<true, INST, SHP, COUNT>(sc, sm, ray, h, counters);
-        if (deferred) continue;
+        const bool occluded = traverse<true, INST, SHP, COUNT>(sc, sm, ray, h, counters);
         if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
         else if (!occluded) {
             float4 c = q.sh_c[j];
@@ -686,44 +582,6 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
             float4 r = q.res[lw];
             r.x += c.x; r.y += c.y; r.z += c.z;
             q.res[lw] = r;
-        }
-    }
-    if (flat) {
-        // phase 2: the deferred rays of this CTA, densely
-        __syncthreads();
-        const uint32_t n_def = min(defer_n, (uint32_t) B2_DEFER_CAP);
-        for (uint32_t base = (threadIdx.x >> 5) * 32u; base < n_def; base += blockDim.x) {
-            const uint32_t k = base + lane_id();
-            bool cont = false, term = false;
-            uint32_t lane_slot = 0;
-            if (k < n_def) {
-                const DeferItem it = defer[k];
-                const bool is_shadow = (it.id & B2_DEFER_SHADOW) != 0;
-                const uint32_t id = it.id & ~B2_DEFER_SHADOW;
-                const float4 ro = is_shadow ? q.sh_o[id] : q.ray_o[id], rd = is_shadow ? q.sh_d[id] : q.ray_d[id];
-                Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
-                FlatRay fr; fr.set(ray);
-                Hit h; h.t = it.t; h.u = it.u; h.v = it.v; h.slot = it.slot; h.prim = it.prim; h.inst = -1;
-                float tmax = fminf(ray.maxt, h.t);
-                if (is_shadow) {
-                    const bool occluded = flat_rest<true, COUNT>(sm, it.mask, ray, fr, tmax, h, counters);
-                    if (q.direct_e) { q.sh_c[id].w = occluded ? 0.f : 1.f; ++n_dsh; }
-                    else if (!occluded) {
-                        float4 c = q.sh_c[id];
-                        const uint32_t lw = __float_as_uint(c.w);
-                        float4 r = q.res[lw];
-                        r.x += c.x; r.y += c.y; r.z += c.z;
-                        q.res[lw] = r;
-                    }
-                } else {
-                    flat_rest<false, COUNT>(sm, it.mask, ray, fr, tmax, h, counters);
-                    q.hit[id] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
-                    cont = h.t < B2_INF && STW_DEPTH(q.st[id].w) < (uint32_t) q.max_depth;
-                    term = !cont;
-                    lane_slot = id;
-                }
-            }
-            list_append(q, parity, lane_slot, cont, term, 0xffffffffu);
         }
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
@@ -757,10 +615,9 @@ template <bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    ShadowQ shq; shq.load(q, parity ^ 1);
-    const uint32_t n_shadow = shq.total();
-    if (blockIdx.x == 0 && threadIdx.x < B2_SHQ) q.cnt[CNT_SHADOW + parity * B2_SHQ + threadIdx.x] = 0;
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[CNT_SHADOW + parity] = 0;
         *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;
         if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
@@ -781,14 +638,10 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                 uint32_t i = base + __popc(idle & ((1u << lane_id()) - 1u));
                 if (i < total) {
                     float4 ro, rd;
-                    uint32_t it = i;
                     if (i < q.n_slots) { rd = q.ray_d[i]; ro = q.ray_o[i]; }
-                    else {       // an emitter sample: `item` keeps n_slots + its array index
-                        const uint32_t j = q.direct_e ? i - q.n_slots : shq.index(q, i - q.n_slots);
-                        rd = q.sh_d[j]; ro = q.sh_o[j]; it = q.n_slots + j;
-                    }
+                    else { rd = q.sh_d[i - q.n_slots]; ro = q.sh_o[i - q.n_slots]; }
                     if (rd.w >= 0.f) {                                   // (retired lanes carry maxt < 0)
-                        item = it; busy = true;
+                        item = i; busy = true;
                         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
                         tr.best.t = B2_INF; tr.best.u = 0.f; tr.best.v = 0.f; tr.best.slot = 0xffffffffu; tr.best.prim = 0xffffffffu; tr.best.inst = -1;
                         tr.any_hit = false;
@@ -808,7 +661,11 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
         if (busy) {
             const bool any_ray = item >= q.n_slots;
             // ---- inner nodes (either level) ----
+#ifdef B2_INST_IFIF        // A/B: one node step per round (lanes at a leaf do not wait for the others' inner-node streaks)
+            if ((uint32_t) tr.cur < (uint32_t) B2_TRAV_NEEDPOP) {
+#else
             while ((uint32_t) tr.cur < (uint32_t) B2_TRAV_NEEDPOP) {
+#endif
                 if constexpr (COUNT) ++tr.n_nodes;
                 float4 nx, ny, nz, fx, fy, fz, chf;
                 if ((uint32_t) tr.cur < sc.smem_nodes) {
@@ -836,9 +693,14 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                 if (hy && cy != bc) { stack[tr.sp] = cy; sdist[tr.sp] = tny; ++tr.sp; }
                 if (hz && cz != bc) { stack[tr.sp] = cz; sdist[tr.sp] = tnz; ++tr.sp; }
                 if (hw && cw != bc) { stack[tr.sp] = cw; sdist[tr.sp] = tnw; ++tr.sp; }
+#ifdef B2_INST_IFIF
+                tr.cur = bc != 0 ? bc : B2_TRAV_NEEDPOP;
+            } else
+#else
                 if (bc != 0) { tr.cur = bc; continue; }
                 tr.cur = B2_TRAV_NEEDPOP;
             }
+#endif
             // ---- one leaf (looping over consecutive leaves here was measured slower) ----
             if (tr.cur < 0) {
                 const uint32_t first = (uint32_t) tr.cur & 0x07ffffffu, count = ((uint32_t) tr.cur >> 27) & 0xfu;
@@ -1132,20 +994,15 @@ __global__ void __launch_bounds__(256) k_init(DScene sc, Queues q) {
 }
 
 // Small scenes: stage the shading tables (triangles, normals, CDFs, BSDF + emitter records) into
-// shared memory with one bulk copy and rebase the table pointers onto the copy. Split into issue / wait so that the
-// caller can put its own first global load (the list counts) between the two: both round trips then overlap.
-B2_D void stage_shade_tables_issue(const DScene &sc, unsigned char *smem_raw) {
-    if (!sc.shade_smem) return;
-    uint64_t *mbar = (uint64_t *) smem_raw;
-    if (threadIdx.x == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    if (threadIdx.x == 0) { mbar_expect_tx(mbar, sc.blob_bytes); stage_bulk(smem_raw + 16, sc.blob, sc.blob_bytes, mbar); }
-}
-B2_D Tables stage_shade_tables_wait(const DScene &sc, unsigned char *smem_raw) {
+// shared memory with one bulk copy and rebase the table pointers onto the copy.
+B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
     Tables tb = make_tables(sc);
     if (!sc.shade_smem) return tb;
     uint64_t *mbar = (uint64_t *) smem_raw;
     unsigned char *dst = smem_raw + 16;
+    if (threadIdx.x == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) { mbar_expect_tx(mbar, sc.blob_bytes); stage_bulk(dst, sc.blob, sc.blob_bytes, mbar); }
     mbar_wait(mbar, 0);
     const unsigned char *g = sc.blob;
     tb.tri_pos = (const float4 *) (dst + ((const unsigned char *) sc.tri_pos - g));
@@ -1192,9 +1049,9 @@ B2_D float3 direct_add_emitter_samples(const Queues &q, uint32_t lane, float3 re
     return result;
 }
 
-// The emitter samples of a warp's previous CONTINUE chunk wait in the warp's shared-memory stash until the atomic that
-// reserved their shadow-queue range has returned: the reservation is issued at the end of phase 1 of chunk c and consumed
-// while chunk c + 1 waits for its queue loads (ncu, round 2: 19 % of k_shade's stall samples sat on that atomic's result).
+// Optional (B2_OPT_STASH): the emitter samples of a warp's previous CONTINUE chunk wait in the warp's shared-memory stash until the
+// atomic that reserved their shadow-queue range has returned (ncu, round 2: 19 % of k_shade's stall samples sit on that result):
+// the reservation is issued at the end of phase 1 of chunk c and its result is first touched while chunk c + 1 waits for its loads.
 struct Pending { uint32_t mask, base; };
 B2_D void drain_pending(const Queues &q, const float4 *stash, Pending &p) {
     if (p.mask == 0) return;                                   // (warp-uniform)
@@ -1208,8 +1065,7 @@ B2_D void drain_pending(const Queues &q, const float4 *stash, Pending &p) {
 
 // 32 CONTINUE lanes: one iteration of PathIntegrator::sample's loop body (path.cpp:124-208). Called by whole warps.
 template <uint32_t F>
-B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane, uint32_t subq,
-                         float4 *stash, Pending &pend) {
+B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane, float4 *stash, Pending &pend) {
     constexpr bool EXT = (F & F_TEX) != 0;
     // all queue loads are issued up front (one round trip)
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
@@ -1222,7 +1078,9 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
     const int depth = (int) STW_DEPTH(st.w);
+#ifdef B2_OPT_STASH
     drain_pending(q, stash, pend);       // (the queue loads above are in flight meanwhile)
+#endif
     float3 throughput = v3(tpe), result = v3(rs);
     float eta = tpe.w, bs_pdf = rs.w;
     SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
@@ -1323,12 +1181,14 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     }
     __syncwarp();
     // ---- K5: warp-ballot compaction of the emitter samples into the dense shadow queue. The atomic is issued
-    // here; the entries wait in the stash and are written by drain_pending() during the warp's next chunk ----
+    // here and its result is only consumed after phase 2 (latency hidden). ----
     const uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
     uint32_t sq_base = 0;
-    if (lane_id() == 0 && sh_mask) sq_base = subq * q.sh_cap + atomicAdd(&q.cnt[CNT_SHADOW + parity * B2_SHQ + subq], __popc(sh_mask));
+    if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
+#ifdef B2_OPT_STASH
     if (shadow) { stash[3 * lane_id()] = sho; stash[3 * lane_id() + 1] = shd; stash[3 * lane_id() + 2] = shc; }
-    pend.mask = sh_mask; pend.base = sq_base;
+    pend.mask = sh_mask; pend.base = sq_base;       // (sq_base is not touched again before drain_pending)
+#endif
     // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
     if (valid && !park && !direct_mode) {
         const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
@@ -1357,6 +1217,12 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
         pb = __shfl_sync(0xffffffffu, pb, 0);
         if (park) q.list[parity ^ 1][q.n_slots - 1u - ((uint32_t) (pb >> 32) + __popc(pk_mask & ((1u << lane_id()) - 1u)))] = lane;
     }
+#ifndef B2_OPT_STASH
+    if (sh_mask) {
+        const uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
+        if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
+    }
+#endif
     if (valid) {
         if (park) { nrd = make_float4(0.f, 0.f, 0.f, -1.f); st.w |= STW_PARKED; }
         else q.ray_o[lane] = nro;
@@ -1387,7 +1253,9 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
     // (direct integrator: only once it is known that the lane finishes its sample)
     uint32_t w = 0;
     if (!direct) w = warp_append(q.work, valid && left == 0);
+#ifdef B2_OPT_STASH
     drain_pending(q, stash, pend);
+#endif
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
@@ -1488,17 +1356,29 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
 template <uint32_t F>
 __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade): their counts are loaded between the
-    // issue of the table staging and the wait for its bulk copy, so that the two round trips overlap
-    stage_shade_tables_issue(sc, smem_raw);
-    unsigned long long n_list;
-    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(n_list) : "l"(q.cnt + CNT_LIST + 2 * parity) : "memory");
-    const Tables tb = stage_shade_tables_wait(sc, smem_raw);
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+#ifdef B2_OPT_SPECLIST
+    // the counts of the two lists AND this warp's first list entry (speculatively: the front of the CONTINUE list, which is
+    // what three of four warps need) are requested together, before the table staging waits for its bulk copy: one exposed
+    // round trip at kernel start instead of three
+    unsigned long long n_list; uint32_t spec_slot;
+    {
+        const uint32_t k0 = min(warp * 32u + lane_id(), q.n_slots - 1u);
+        // (the address is made to look thread-dependent so that the value stays in a vector register: a uniform register would
+        //  be filled — and waited for — right here instead of after the staging)
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(n_list) : "l"(q.cnt + CNT_LIST + 2 * parity + 2 * (threadIdx.x >> 30)) : "memory");
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(spec_slot) : "l"(q.list[parity] + k0) : "memory");
+    }
+    const Tables tb = stage_shade_tables(sc, smem_raw);
+#else
+    const Tables tb = stage_shade_tables(sc, smem_raw);
+    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
+    const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
+#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_FETCH] = 0;       // ray counter of the next k_trace_inst
     const uint32_t n_cont = (uint32_t) n_list, n_term = (uint32_t) (n_list >> 32);
     const uint32_t wc = (n_cont + 31u) >> 5, wt = (n_term + 31u) >> 5;
-    // the warp's stash (3 float4 per lane) behind the staged tables
+    // (B2_OPT_STASH) the warp's stash (3 float4 per lane) behind the staged tables
     float4 *stash = (float4 *) (smem_raw + ((16u + (sc.shade_smem ? sc.blob_bytes : 0u) + 15u) & ~15u)) + (threadIdx.x >> 5) * 96u;
     Pending pend; pend.mask = 0; pend.base = 0;
     uint32_t n_put = 0, n_bad = 0;
@@ -1508,16 +1388,29 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         const uint32_t k = (w - wc) * 32u + lane_id(); valid = k < n_term;
         return valid ? q.list[parity][q.n_slots - 1u - k] : 0u;
     };
+#ifdef B2_OPT_SPECLIST
     bool valid = false, valid_next = false;
-    uint32_t slot = warp < wc + wt ? list_entry(warp, valid) : 0u, slot_next = 0u;
+    uint32_t slot = 0, slot_next = 0;
+    if (warp < wc) { valid = warp * 32u + lane_id() < n_cont; slot = valid ? spec_slot : 0u; }
+    else if (warp < wc + wt) slot = list_entry(warp, valid);
     for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
-        // the list entry of the warp's NEXT chunk is fetched now and used one iteration later (one L2 round trip less per chunk)
+        // the list entry of the warp's NEXT chunk is fetched now and used one iteration later
         if (wi + n_warps < wc + wt) slot_next = list_entry(wi + n_warps, valid_next);
-        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, wi % B2_SHQ, stash, pend);
+        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, stash, pend);
         else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad, stash, pend);
         slot = slot_next; valid = valid_next;
     }
+#else
+    for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
+        bool valid;
+        const uint32_t slot = list_entry(wi, valid);
+        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, stash, pend);
+        else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad, stash, pend);
+    }
+#endif
+#ifdef B2_OPT_STASH
     drain_pending(q, stash, pend);
+#endif
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {
         if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
