@@ -522,11 +522,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     d.shapes = dshapes.empty() ? nullptr : (const DShape *) (s->blob.p + off_shp);
     if (any_uv || !texs.empty() || ns) s->features |= F_TEX;
     d.shade_smem = blob_bytes > 0 && blob_bytes <= 48 * 1024 ? 1 : 0;
-    // k_shade's dynamic shared memory: [mbarrier + the staged tables] (+ B2_OPT_STASH: the per-warp stash, 8 warps x 32 x 48 B)
     s->shade_smem_bytes = d.shade_smem ? (int) blob_bytes + 16 : 0;
-#ifdef B2_OPT_STASH
-    s->shade_smem_bytes = ((s->shade_smem_bytes + 16 + 15) & ~15) + 8 * 32 * 48;
-#endif
     for (const B2Bsdf &b : bsdfs) {
         if (b.twosided_back != 0) {                                            // twosided.cpp:63-92
             if (b.twosided_back < 0 || (uint32_t) b.twosided_back > bsdfs.size()) { delete s; return fail(B2_ERR_INVALID, "twosided BSDF: bad back-side index"); }
@@ -887,9 +883,6 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // measured: 8 CTAs/SM queued beats exactly-resident grids
     int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = grid;
     if (inst) grid_int = s->sm_count * B2_INST_MINBLOCKS;           // k_trace_inst: persistent warps
-#ifdef B2_SHADE_RESIDENT_GRID       // A/B: exactly the resident CTAs, every warp strides over several chunks
-    grid_sha = (int) std::min<uint32_t>((uint32_t) s->sm_count * B2_SHADE_MINBLOCKS, need_blocks);
-#endif
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;

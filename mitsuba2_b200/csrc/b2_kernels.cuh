@@ -155,12 +155,27 @@ struct Hit { float t, u, v; uint32_t slot, prim; int inst; };
 // (mesh.h:200-203), so the result is bit-identical to tri_intersect().
 B2_D bool tri_isect(float3 p0, float3 e1, float3 e2, const Ray &ray, float tmax, float &t, float &u, float &v) {
     float3 pvec = cross(ray.d, e2);
-    float inv_det = b2_rcp(dot(e1, pvec));
+    const float det = dot(e1, pvec);
     float3 tvec = ray.o - p0;
-    u = dot(tvec, pvec) * inv_det;
-    if (!(u >= 0.f && u <= 1.f)) return false;
+    const float un = dot(tvec, pvec);
+#ifndef B2_NO_TRI_PRETEST
+    // Most tests fail; a certain miss is recognised with one MUFU.RCP instead of the correctly rounded reciprocal (8
+    // instructions + a slow path): the approximation is within a few ulp, the margins are 1e-5, so whatever is rejected here
+    // is rejected by the exact comparisons below as well — the accepted set, and every accepted (t, u, v), is unchanged.
+    float ra; asm("rcp.approx.f32 %0, %1;" : "=f"(ra) : "f"(det));
+    const float ua = un * ra;
+    if (ua < -1e-5f || ua > 1.00001f) return false;
+#endif
     float3 qvec = cross(tvec, e1);
-    v = dot(ray.d, qvec) * inv_det;
+    const float vn = dot(ray.d, qvec);
+#ifndef B2_NO_TRI_PRETEST
+    const float va = vn * ra;
+    if (va < -1e-5f || ua + va > 1.00002f) return false;
+#endif
+    float inv_det = b2_rcp(det);
+    u = un * inv_det;
+    if (!(u >= 0.f && u <= 1.f)) return false;
+    v = vn * inv_det;
     if (!(v >= 0.f && u + v <= 1.f)) return false;
     t = dot(e2, qvec) * inv_det;
     return t >= ray.mint && t <= tmax;
@@ -623,7 +638,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     }
     const uint32_t total = q.n_slots + (q.direct_e ? q.n_slots * q.direct_e : n_shadow);
     uint32_t n_seg = 0, n_dsh = 0;
-    int stack[B2_INST_STACK]; float sdist[B2_INST_STACK];
+    int2 stk[B2_INST_STACK];          // (node / leaf code, entry distance bits): one 8-byte local-memory access per push / pop
     Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f; tr.n_nodes = 0; tr.n_tris = 0;
     uint32_t item = 0;
     bool busy = false, exhausted = false;
@@ -646,10 +661,10 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                         tr.best.t = B2_INF; tr.best.u = 0.f; tr.best.v = 0.f; tr.best.slot = 0xffffffffu; tr.best.prim = 0xffffffffu; tr.best.inst = -1;
                         tr.any_hit = false;
                         tr.set_ray(ray);
-                        stack[0] = B2_TRAV_DONE; sdist[0] = -B2_INF; tr.sp = 1;
+                        stk[0] = make_int2(B2_TRAV_DONE, __float_as_int(-B2_INF)); tr.sp = 1;
                         if (sc.n_top_tris) {                             // phase -2: the top-level triangles, then the TLAS
                             tr.inst = -2; tr.cur = 0;
-                            if (sc.n_instances) { stack[1] = B2_TRAV_POP; sdist[1] = -B2_INF; tr.sp = 2; }
+                            if (sc.n_instances) { stk[1] = make_int2(B2_TRAV_POP, __float_as_int(-B2_INF)); tr.sp = 2; }
                         } else { tr.inst = -1; tr.cur = (int) sc.tlas_root; }
                     }
                 }
@@ -661,11 +676,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
         if (busy) {
             const bool any_ray = item >= q.n_slots;
             // ---- inner nodes (either level) ----
-#ifdef B2_INST_IFIF        // A/B: one node step per round (lanes at a leaf do not wait for the others' inner-node streaks)
-            if ((uint32_t) tr.cur < (uint32_t) B2_TRAV_NEEDPOP) {
-#else
             while ((uint32_t) tr.cur < (uint32_t) B2_TRAV_NEEDPOP) {
-#endif
                 if constexpr (COUNT) ++tr.n_nodes;
                 float4 nx, ny, nz, fx, fy, fz, chf;
                 if ((uint32_t) tr.cur < sc.smem_nodes) {
@@ -689,25 +700,20 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                 if (hy && tny < bd) { bd = tny; bc = cy; }
                 if (hz && tnz < bd) { bd = tnz; bc = cz; }
                 if (hw && tnw < bd) { bd = tnw; bc = cw; }
-                if (hx && cx != bc) { stack[tr.sp] = cx; sdist[tr.sp] = tnx; ++tr.sp; }
-                if (hy && cy != bc) { stack[tr.sp] = cy; sdist[tr.sp] = tny; ++tr.sp; }
-                if (hz && cz != bc) { stack[tr.sp] = cz; sdist[tr.sp] = tnz; ++tr.sp; }
-                if (hw && cw != bc) { stack[tr.sp] = cw; sdist[tr.sp] = tnw; ++tr.sp; }
-#ifdef B2_INST_IFIF
-                tr.cur = bc != 0 ? bc : B2_TRAV_NEEDPOP;
-            } else
-#else
+                if (hx && cx != bc) { stk[tr.sp++] = make_int2(cx, __float_as_int(tnx)); }
+                if (hy && cy != bc) { stk[tr.sp++] = make_int2(cy, __float_as_int(tny)); }
+                if (hz && cz != bc) { stk[tr.sp++] = make_int2(cz, __float_as_int(tnz)); }
+                if (hw && cw != bc) { stk[tr.sp++] = make_int2(cw, __float_as_int(tnw)); }
                 if (bc != 0) { tr.cur = bc; continue; }
                 tr.cur = B2_TRAV_NEEDPOP;
             }
-#endif
             // ---- one leaf (looping over consecutive leaves here was measured slower) ----
             if (tr.cur < 0) {
                 const uint32_t first = (uint32_t) tr.cur & 0x07ffffffu, count = ((uint32_t) tr.cur >> 27) & 0xfu;
                 if (tr.inst == -1) {
                     // TLAS leaf: enter the (first) instance, keep the others for later
                     for (uint32_t s = first + 1; s < first + count; ++s) {
-                        stack[tr.sp] = (int) (0x80000000u | (1u << 27) | s); sdist[tr.sp] = -B2_INF; ++tr.sp;
+                        stk[tr.sp++] = make_int2((int) (0x80000000u | (1u << 27) | s), __float_as_int(-B2_INF));
                     }
                     const uint32_t ii = __ldg(&sc.inst_order[first]);
                     const DInstance &in = sc.instances[ii];
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     ro.mint = tr.ray.mint; ro.maxt = tr.ray.maxt;
                     tr.set_ray(ro);
                     tr.inst = (int) ii;
-                    stack[tr.sp] = B2_TRAV_POP; sdist[tr.sp] = -B2_INF; ++tr.sp;
+                    stk[tr.sp++] = make_int2(B2_TRAV_POP, __float_as_int(-B2_INF));
                     tr.cur = in.root;
                 } else {
                     const int key_inst = tr.inst < 0 ? -1 : tr.inst;
@@ -742,7 +748,8 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
             if (tr.cur == B2_TRAV_NEEDPOP) {
                 for (;;) {
                     --tr.sp;
-                    int c = stack[tr.sp];
+                    const int2 e = stk[tr.sp];
+                    const int c = e.x;
                     if (c == B2_TRAV_DONE) { tr.cur = c; break; }
                     if (c == B2_TRAV_POP) {
                         if (tr.inst == -2) { tr.inst = -1; tr.cur = (int) sc.tlas_root; break; }
@@ -755,7 +762,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                         tr.inst = -1;
                         continue;
                     }
-                    if (sdist[tr.sp] <= tr.tmax * 1.0000004f) { tr.cur = c; break; }
+                    if (__int_as_float(e.y) <= tr.tmax * 1.0000004f) { tr.cur = c; break; }
                 }
             }
             // ---- finished: write the result, the lane becomes idle (the compaction is k_classify's: rays finish here in
@@ -1049,23 +1056,9 @@ B2_D float3 direct_add_emitter_samples(const Queues &q, uint32_t lane, float3 re
     return result;
 }
 
-// Optional (B2_OPT_STASH): the emitter samples of a warp's previous CONTINUE chunk wait in the warp's shared-memory stash until the
-// atomic that reserved their shadow-queue range has returned (ncu, round 2: 19 % of k_shade's stall samples sit on that result):
-// the reservation is issued at the end of phase 1 of chunk c and its result is first touched while chunk c + 1 waits for its loads.
-struct Pending { uint32_t mask, base; };
-B2_D void drain_pending(const Queues &q, const float4 *stash, Pending &p) {
-    if (p.mask == 0) return;                                   // (warp-uniform)
-    const uint32_t base = __shfl_sync(0xffffffffu, p.base, 0);
-    if (p.mask & (1u << lane_id())) {
-        const uint32_t sq = base + __popc(p.mask & ((1u << lane_id()) - 1u));
-        q.sh_o[sq] = stash[3 * lane_id()]; q.sh_d[sq] = stash[3 * lane_id() + 1]; q.sh_c[sq] = stash[3 * lane_id() + 2];
-    }
-    p.mask = 0;
-}
-
 // 32 CONTINUE lanes: one iteration of PathIntegrator::sample's loop body (path.cpp:124-208). Called by whole warps.
 template <uint32_t F>
-B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane, float4 *stash, Pending &pend) {
+B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane) {
     constexpr bool EXT = (F & F_TEX) != 0;
     // all queue loads are issued up front (one round trip)
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
@@ -1078,9 +1071,6 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
     const int depth = (int) STW_DEPTH(st.w);
-#ifdef B2_OPT_STASH
-    drain_pending(q, stash, pend);       // (the queue loads above are in flight meanwhile)
-#endif
     float3 throughput = v3(tpe), result = v3(rs);
     float eta = tpe.w, bs_pdf = rs.w;
     SI si; si.emitter = -1; si.bsdf = 0; si.p = si.sh_n = v3(0.f, 0.f, 0.f);
@@ -1185,10 +1175,6 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     const uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
     uint32_t sq_base = 0;
     if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
-#ifdef B2_OPT_STASH
-    if (shadow) { stash[3 * lane_id()] = sho; stash[3 * lane_id() + 1] = shd; stash[3 * lane_id() + 2] = shc; }
-    pend.mask = sh_mask; pend.base = sq_base;       // (sq_base is not touched again before drain_pending)
-#endif
     // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
     if (valid && !park && !direct_mode) {
         const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
@@ -1217,12 +1203,10 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
         pb = __shfl_sync(0xffffffffu, pb, 0);
         if (park) q.list[parity ^ 1][q.n_slots - 1u - ((uint32_t) (pb >> 32) + __popc(pk_mask & ((1u << lane_id()) - 1u)))] = lane;
     }
-#ifndef B2_OPT_STASH
     if (sh_mask) {
         const uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
         if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
     }
-#endif
     if (valid) {
         if (park) { nrd = make_float4(0.f, 0.f, 0.f, -1.f); st.w |= STW_PARKED; }
         else q.ray_o[lane] = nro;
@@ -1239,8 +1223,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
 // DirectIntegrator (extended variants): a lane whose BSDF-sample ray came back adds that sample's contribution and, while
 // BSDF samples are left, re-shades the camera hit and leaves with the next sample's ray instead of finishing.
 template <uint32_t F>
-B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, bool valid, uint32_t lane, uint32_t &n_put, uint32_t &n_bad,
-                          const float4 *stash, Pending &pend) {
+B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, bool valid, uint32_t lane, uint32_t &n_put, uint32_t &n_bad) {
     constexpr bool EXT = (F & F_TEX) != 0;
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
     uint4 st = q.st[ld];
@@ -1253,9 +1236,6 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
     // (direct integrator: only once it is known that the lane finishes its sample)
     uint32_t w = 0;
     if (!direct) w = warp_append(q.work, valid && left == 0);
-#ifdef B2_OPT_STASH
-    drain_pending(q, stash, pend);
-#endif
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
@@ -1357,30 +1337,12 @@ template <uint32_t F>
 __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-#ifdef B2_OPT_SPECLIST
-    // the counts of the two lists AND this warp's first list entry (speculatively: the front of the CONTINUE list, which is
-    // what three of four warps need) are requested together, before the table staging waits for its bulk copy: one exposed
-    // round trip at kernel start instead of three
-    unsigned long long n_list; uint32_t spec_slot;
-    {
-        const uint32_t k0 = min(warp * 32u + lane_id(), q.n_slots - 1u);
-        // (the address is made to look thread-dependent so that the value stays in a vector register: a uniform register would
-        //  be filled — and waited for — right here instead of after the staging)
-        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(n_list) : "l"(q.cnt + CNT_LIST + 2 * parity + 2 * (threadIdx.x >> 30)) : "memory");
-        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(spec_slot) : "l"(q.list[parity] + k0) : "memory");
-    }
-    const Tables tb = stage_shade_tables(sc, smem_raw);
-#else
     const Tables tb = stage_shade_tables(sc, smem_raw);
     // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
     const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
-#endif
     if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_FETCH] = 0;       // ray counter of the next k_trace_inst
     const uint32_t n_cont = (uint32_t) n_list, n_term = (uint32_t) (n_list >> 32);
     const uint32_t wc = (n_cont + 31u) >> 5, wt = (n_term + 31u) >> 5;
-    // (B2_OPT_STASH) the warp's stash (3 float4 per lane) behind the staged tables
-    float4 *stash = (float4 *) (smem_raw + ((16u + (sc.shade_smem ? sc.blob_bytes : 0u) + 15u) & ~15u)) + (threadIdx.x >> 5) * 96u;
-    Pending pend; pend.mask = 0; pend.base = 0;
     uint32_t n_put = 0, n_bad = 0;
     // lane slot of this thread in chunk w: the w-th group of 32 entries of the CONTINUE list, then of the TERMINATE list
     auto list_entry = [&](uint32_t w, bool &valid) -> uint32_t {
@@ -1388,29 +1350,12 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
         const uint32_t k = (w - wc) * 32u + lane_id(); valid = k < n_term;
         return valid ? q.list[parity][q.n_slots - 1u - k] : 0u;
     };
-#ifdef B2_OPT_SPECLIST
-    bool valid = false, valid_next = false;
-    uint32_t slot = 0, slot_next = 0;
-    if (warp < wc) { valid = warp * 32u + lane_id() < n_cont; slot = valid ? spec_slot : 0u; }
-    else if (warp < wc + wt) slot = list_entry(warp, valid);
-    for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
-        // the list entry of the warp's NEXT chunk is fetched now and used one iteration later
-        if (wi + n_warps < wc + wt) slot_next = list_entry(wi + n_warps, valid_next);
-        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, stash, pend);
-        else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad, stash, pend);
-        slot = slot_next; valid = valid_next;
-    }
-#else
     for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
         bool valid;
         const uint32_t slot = list_entry(wi, valid);
-        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, stash, pend);
-        else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad, stash, pend);
+        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot);
+        else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad);
     }
-#endif
-#ifdef B2_OPT_STASH
-    drain_pending(q, stash, pend);
-#endif
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {
         if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);

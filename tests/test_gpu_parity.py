@@ -371,7 +371,10 @@ def test_progressive_snapshots_and_cancel(b2):
     assert rc == 3
     wsum = float(out[..., 4].sum(dtype=np.float64))
     assert 0.2 * 512 * 512 * 64 < wsum < 512 * 512 * 64            # a partial film came back
-    part = out[..., :3].sum(axis=(0, 1)) / wsum; full = ref[..., :3].sum(axis=(0, 1)) / ref[..., 4].sum()
-    assert np.allclose(part, full, rtol=0.2)
+    # developing it (XYZ / W per pixel) gives a valid estimate wherever samples have landed
+    done = out[..., 4] >= 16
+    assert done.sum() > 0.15 * 512 * 512
+    part = (out[..., :3] / np.maximum(out[..., 4:5], 1))[done].mean(axis=0); full = (ref[..., :3] / ref[..., 4:5])[done].mean(axis=0)
+    assert np.allclose(part, full, rtol=0.1), (part, full)
     sc.set_progress_callback(None)
     assert same(integ.render(sc, 64), ref)
