@@ -329,6 +329,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         }
     }
 
+    if (bvh.order.size() != n_slots) { delete s; return fail(B2_ERR_INVALID, "internal: BVH leaf order covers %zu of %u primitives", bvh.order.size(), n_slots); }
     std::vector<float4> tri_pos(3 * (size_t) n_slots), tri_nrm(3 * (size_t) n_slots), tri_isect(3 * (size_t) n_slots);
     std::vector<uint32_t> prim_to_slot(n_slots);
     bool any_uv = false;

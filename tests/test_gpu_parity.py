@@ -378,3 +378,42 @@ def test_progressive_snapshots_and_cancel(b2):
     assert np.allclose(part, full, rtol=0.1), (part, full)
     sc.set_progress_callback(None)
     assert same(integ.render(sc, 64), ref)
+
+
+def test_non_blocking_stream(b2, oracle):
+    """b2_set_stream with a NON-BLOCKING stream (what PyTorch hands out): the stage entry points order their host <-> device
+    copies on that stream, and a render on it gives the same film as on the legacy stream."""
+    import torch
+    sb, rp, _ = G.load("cbox_64_spp16", b2.Host())
+    sc = b2.Scene(sb)
+    ro, rd = _random_rays(sb, 50000, 7)
+    hit0 = sc.ray_intersect_preliminary(ro, rd)
+    occ0 = sc.ray_test(ro, rd)
+    film0 = np.empty((64, 64, 5), np.float32); st = abi.B2Stats()
+    assert b2.lib().b2_render(sc._h, C.byref(rp), film0.ctypes.data, C.byref(st)) == 0
+    stream = torch.cuda.Stream()
+    assert b2.lib().b2_set_stream(sc._h, C.c_void_p(stream.cuda_stream)) == 0
+    for _ in range(3):
+        hit1 = sc.ray_intersect_preliminary(ro, rd)
+        occ1 = sc.ray_test(ro, rd)
+        assert np.array_equal(hit0.view(np.uint32), hit1.view(np.uint32)) and np.array_equal(occ0, occ1)
+    film1 = np.empty_like(film0)
+    assert b2.lib().b2_render(sc._h, C.byref(rp), film1.ctypes.data, C.byref(st)) == 0
+    assert np.array_equal(film0.view(np.uint32), film1.view(np.uint32))
+    assert np.array_equal(sc.develop(film1).view(np.uint32), oracle.develop(film1).view(np.uint32))
+    assert b2.lib().b2_set_stream(sc._h, None) == 0
+
+
+def test_rank_without_blocks(b2):
+    """world_size larger than the number of spiral blocks: the ranks that own no block return an empty film without
+    launching, and the rank films still sum to the single-GPU film."""
+    sb, rp, _ = G.load("cbox_64_spp16", b2.Host())          # 64 x 64, block size 32: 4 blocks
+    full, _, sc = _gpu_render(b2, sb, rp)
+    acc = np.zeros_like(full)
+    for r in range(6):
+        rpr = abi.render_params(rp.max_depth, rp.rr_depth, rp.spp, rp.samples_per_pass, rp.block_size, rp.seed, r, 6)
+        part, st, _ = _gpu_render(b2, sb, rpr)
+        if r >= 4:
+            assert st["n_samples"] == 0 and st["n_launches"] == 0 and not part.any()
+        acc += part
+    assert np.array_equal(full.view(np.uint32), acc.view(np.uint32))
