@@ -334,6 +334,12 @@ B2_API int b2_stage_shade(B2Scene *scene, const B2RenderParams *params, uint32_t
                           const float *hit, const int32_t *inst, float *throughput_eta, float *result_pdf,
                           uint64_t *rng_state, uint32_t *depth_flags,
                           uint32_t *n_shadow, float *sh_o, float *sh_d, float *sh_c);
+/* compact: K5 alone — the warp-ballot compaction the traversal stage ends with. Lane i takes part if it has a ray
+   (ray_maxt[i] >= 0); it goes on the CONTINUE list if it hit something (hit_t[i] < inf) with depth < max_depth (path.cpp:131,147-149:
+   the path goes on), otherwise on the TERMINATE list. The lists come back in the order the warps appended them (each warp's
+   32 lanes ascending; terminate_lanes as stored from the back of the list array). */
+B2_API int b2_stage_compact(B2Scene *scene, int32_t max_depth, uint32_t n, const float *ray_maxt, const float *hit_t, const uint32_t *depth,
+                            uint32_t *n_continue, uint32_t *continue_lanes, uint32_t *n_terminate, uint32_t *terminate_lanes);
 /* film_put: ImageBlock::put (imageblock.cpp:79-172) of n samples: sample i belongs to the image block of pixel (px, py)
    (crop-relative) and lands at pos[2i..] = position_sample (film coordinates); rgb is converted to XYZ like render_sample
    does (integrator.cpp:273). xyzaw[crop_h * crop_w * 5] receives the accumulated film (box: 5 reductions per sample,

@@ -26,7 +26,7 @@ EXPORTS = [
     "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
     "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4", "b2_render_reduce", "b2_develop_device",
     "b2_host_bsdf_plastic", "b2_host_shape_sphere", "b2_host_shape_rectangle", "b2_stage_shade", "b2_stage_film_put",
-    "b2_set_progress_callback",
+    "b2_set_progress_callback", "b2_stage_compact",
 ]
 
 PROGRESS_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_float), C.c_uint64, C.c_uint64)     # b2_progress_fn
@@ -76,6 +76,8 @@ def lib():
             L.b2_develop_device.argtypes = [C.c_void_p, C.c_void_p]
             L.b2_set_progress_callback.argtypes = [C.c_void_p, PROGRESS_FN, C.c_void_p, C.c_uint32]
             L.b2_stage_shade.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.c_uint32] + [C.c_void_p] * 8 + [C.POINTER(C.c_uint32)] + [C.c_void_p] * 3
+            L.b2_stage_compact.argtypes = [C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p,
+                                           C.POINTER(C.c_uint32), C.c_void_p]
             L.b2_stage_film_put.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.c_void_p] * 6 + [C.POINTER(C.c_uint32)]
         L.b2_cancel.argtypes = [C.c_void_p]
         L.b2_develop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -207,6 +209,15 @@ class Scene:
         k = ns.value
         order = np.argsort(sh_c[:k, 3].view(np.uint32), kind="stable")
         return sh_o[:k][order], sh_d[:k][order], sh_c[:k][order]
+
+    def compact(self, max_depth, ray_maxt, hit_t, depth):
+        """b2_stage_compact: -> (continue lanes, terminate lanes), each sorted ascending"""
+        ray_maxt = np.ascontiguousarray(ray_maxt, np.float32); hit_t = np.ascontiguousarray(hit_t, np.float32); depth = np.ascontiguousarray(depth, np.uint32)
+        n = len(hit_t)
+        a = np.zeros(n, np.uint32); b = np.zeros(n, np.uint32); na = C.c_uint32(); nb = C.c_uint32()
+        _check(lib().b2_stage_compact(self._h, max_depth, n, ray_maxt.ctypes.data, hit_t.ctypes.data, depth.ctypes.data, C.byref(na), a.ctypes.data,
+                                      C.byref(nb), b.ctypes.data))
+        return np.sort(a[:na.value]), np.sort(b[:nb.value])
 
     def film_put(self, block_size, px, py, pos, rgb, alpha):
         """b2_stage_film_put: ImageBlock::put of n samples -> (XYZAW film [H, W, 5], number of rejected samples)"""

@@ -1184,6 +1184,34 @@ int b2_stage_shade(B2Scene *s, const B2RenderParams *rp, uint32_t n, float *ray_
     return B2_OK;
 }
 
+// K5 alone: the warp-ballot compaction of the live lanes into the CONTINUE / TERMINATE lists (what k_trace ends with)
+int b2_stage_compact(B2Scene *s, int32_t max_depth, uint32_t n, const float *ray_maxt, const float *hit_t, const uint32_t *depth,
+                     uint32_t *n_continue, uint32_t *continue_lanes, uint32_t *n_terminate, uint32_t *terminate_lanes) {
+    if (!s || !n_continue || !n_terminate || (n && (!ray_maxt || !hit_t || !depth || !continue_lanes || !terminate_lanes)))
+        return fail(B2_ERR_INVALID, "b2_stage_compact: null argument");
+    *n_continue = *n_terminate = 0;
+    if (n == 0) return B2_OK;
+    const size_t N = n;
+    DBuf<float> dm, dt; DBuf<uint32_t> dd, list, cnt;
+    CU(dm.alloc(N)); CU(dt.alloc(N)); CU(dd.alloc(N)); CU(list.alloc(N)); CU(cnt.alloc(B2_CNT_WORDS));
+    H2D(dm.p, ray_maxt, N * 4); H2D(dt.p, hit_t, N * 4); H2D(dd.p, depth, N * 4);
+    CU(cudaMemsetAsync(cnt.p, 0, B2_CNT_WORDS * 4, s->stream));
+    Queues q{};
+    q.list[0] = list.p; q.list[1] = list.p; q.cnt = cnt.p; q.n_slots = n; q.max_depth = max_depth;
+    k_stage_compact<<<stage_grid(s, n), 256, 0, s->stream>>>(q, n, dm.p, dt.p, dd.p);
+    CU(cudaGetLastError());
+    unsigned long long counts = 0;
+    D2H(&counts, cnt.p + CNT_LIST, 8);
+    SYNC();
+    const uint32_t nc = (uint32_t) counts, nx = (uint32_t) (counts >> 32);
+    if ((size_t) nc + nx > N) return fail(B2_ERR_CUDA, "b2_stage_compact: list overflow");
+    *n_continue = nc; *n_terminate = nx;
+    if (nc) D2H(continue_lanes, list.p, (size_t) nc * 4);
+    if (nx) D2H(terminate_lanes, list.p + (N - nx), (size_t) nx * 4);        // (appended from the back: descending positions)
+    SYNC();
+    return B2_OK;
+}
+
 int b2_stage_film_put(B2Scene *s, uint32_t block_size, uint32_t n, const uint32_t *px, const uint32_t *py, const float *pos, const float *rgb,
                       const uint8_t *alpha, float *xyzaw, uint32_t *n_invalid) {
     if (!s || !xyzaw || (n && (!px || !py || !pos || !rgb || !alpha))) return fail(B2_ERR_INVALID, "b2_stage_film_put: null argument");

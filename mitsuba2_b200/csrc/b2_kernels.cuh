@@ -1424,6 +1424,19 @@ __global__ void __launch_bounds__(256) k_stage_occluded(DScene sc, uint32_t n, c
         Hit h; occ[i] = traverse<true, INST, true>(sc, sm, ray, h) ? 1 : 0;
     }
 }
+// b2_stage_compact: K5 alone — the classification k_trace ends with, on caller data (ray present / hit distance / depth)
+__global__ void __launch_bounds__(256) k_stage_compact(Queues q, uint32_t n, const float *ray_maxt, const float *hit_t, const uint32_t *depth) {
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t base = warp * 32; base < n; base += n_warps * 32) {
+        const uint32_t i = base + lane_id();
+        bool cont = false, term = false;
+        if (i < n && ray_maxt[i] >= 0.f) {
+            cont = hit_t[i] < B2_INF && STW_DEPTH(depth[i]) < (uint32_t) q.max_depth;
+            term = !cont;
+        }
+        list_append(q, 0, i, cont, term, 0xffffffffu);
+    }
+}
 // b2_stage_shade: the C-ABI's (t, u, v, prim) hit -> the queues' (t, u, v, slot); lane state words -> st
 __global__ void k_stage_pack(DScene sc, uint32_t n, float4 *hit, const uint64_t *rng, const uint32_t *depth_flags, uint4 *st, uint32_t *list) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

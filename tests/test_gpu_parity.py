@@ -417,3 +417,19 @@ def test_rank_without_blocks(b2):
             assert st["n_samples"] == 0 and st["n_launches"] == 0 and not part.any()
         acc += part
     assert np.array_equal(full.view(np.uint32), acc.view(np.uint32))
+
+
+def test_stage_compact(b2):
+    """b2_stage_compact (K5: the warp-ballot compaction of the live lanes) vs numpy, ragged sizes included."""
+    sc = b2.Scene(scenes.cbox(b2.Host(), 32, 32))
+    rng = np.random.default_rng(3)
+    for n in (1, 31, 32, 33, 1000, 70001):
+        maxt = np.where(rng.random(n) < 0.9, np.inf, -1.0).astype(np.float32)
+        t = np.where(rng.random(n) < 0.7, rng.random(n) * 100, np.inf).astype(np.float32)
+        depth = (rng.integers(1, 8, n) | (rng.integers(0, 4, n) << 8)).astype(np.uint32)       # depth | flag bits
+        c, x = sc.compact(6, maxt, t, depth)
+        has = maxt >= 0
+        cont = has & np.isfinite(t) & ((depth & 0xff) < 6)
+        assert np.array_equal(c, np.nonzero(cont)[0]) and np.array_equal(x, np.nonzero(has & ~cont)[0])
+    c, x = sc.compact(-1, np.full(5, np.inf, np.float32), np.array([1, np.inf, 2, 3, np.inf], np.float32), np.full(5, 200, np.uint32))
+    assert list(c) == [0, 2, 3] and list(x) == [1, 4]          # max_depth = -1: only misses end a path
