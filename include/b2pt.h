@@ -260,6 +260,12 @@ typedef struct B2Scene B2Scene;     /* opaque */
 /* ---- lifecycle --------------------------------------------------------------------------- */
 B2_API int b2_scene_create(const B2SceneDesc *desc, B2Scene **out);
 B2_API int b2_scene_destroy(B2Scene *scene);
+/* Scene::parameters_changed -> accel_parameters_changed (scene.cpp:242-260, scene_optix.inl:236): replace the geometry /
+ * materials / emitters / sensor behind an existing handle by a new description (moved vertices, edited parameters). The BVHs
+ * are rebuilt as in b2_scene_create (B2_BUILD_DEVICE_LBVH: on the GPU, milliseconds); render state (queues, streams, pinned
+ * buffers, work-item tables, callbacks) is kept. On failure the handle keeps its old contents. Not concurrent with a render
+ * on the same handle. */
+B2_API int b2_scene_update(B2Scene *scene, const B2SceneDesc *desc);
 B2_API const char *b2_last_error(void);
 B2_API int b2_device_count(void);
 

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("B2PT_LIB", os.path.join(_DIR, "libb2pt.so"))     # B2
 _LIB = None
 
 EXPORTS = [
-    "b2_scene_create", "b2_scene_destroy", "b2_last_error", "b2_device_count", "b2_render", "b2_render_device",
+    "b2_scene_create", "b2_scene_destroy", "b2_scene_update", "b2_last_error", "b2_device_count", "b2_render", "b2_render_device",
     "b2_cancel", "b2_develop", "b2_set_stream", "b2_stage_raygen", "b2_stage_intersect", "b2_stage_occluded",
     "b2_stage_si_fill", "b2_host_look_at", "b2_host_perspective_sensor", "b2_host_parse_fov", "b2_host_film_box",
     "b2_host_film_gaussian", "b2_host_spiral", "b2_host_build_bvh4", "b2_render_reduce", "b2_develop_device",
@@ -67,6 +67,7 @@ def lib():
         L.b2_host_spiral.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_uint32), C.c_void_p]
         L.b2_scene_create.argtypes = [C.POINTER(abi.B2SceneDesc), C.POINTER(C.c_void_p)]
         L.b2_scene_destroy.argtypes = [C.c_void_p]
+        L.b2_scene_update.argtypes = [C.c_void_p, C.POINTER(abi.B2SceneDesc)]
         L.b2_render.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.c_void_p, C.POINTER(abi.B2Stats)]
         L.b2_render_device.argtypes = [C.c_void_p, C.POINTER(abi.B2RenderParams), C.POINTER(C.c_void_p),
                                        C.POINTER(abi.B2Stats)]
@@ -138,6 +139,13 @@ class Scene:
         self._desc = scene_buffers.desc()
         self._h = C.c_void_p()
         _check(lib().b2_scene_create(C.byref(self._desc), C.byref(self._h)))
+        self.height, self.width = scene_buffers.film.crop_size[1], scene_buffers.film.crop_size[0]
+
+    def update(self, scene_buffers):
+        """Scene::parameters_changed (scene.cpp:242-260): new geometry / parameters behind the same handle (b2_scene_update)."""
+        desc = scene_buffers.desc()
+        _check(lib().b2_scene_update(self._h, C.byref(desc)))
+        self.sb, self._desc = scene_buffers, desc
         self.height, self.width = scene_buffers.film.crop_size[1], scene_buffers.film.crop_size[0]
 
     def close(self):

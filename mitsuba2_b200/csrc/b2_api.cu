@@ -680,6 +680,29 @@ int b2_scene_destroy(B2Scene *scene) {
     return B2_OK;
 }
 
+// Scene::parameters_changed -> accel_parameters_changed (scene.cpp:242-260; the OptiX backend rebuilds its acceleration structure,
+// scene_optix.inl:236): the new description is flattened and built like in b2_scene_create (with B2_BUILD_DEVICE_LBVH the
+// rebuild is a few ms for millions of triangles) and swapped in under the same handle; the wavefront queues, the streams, the
+// pinned buffers, the work-item tables and the callbacks are kept. On failure the handle keeps its old contents.
+int b2_scene_update(B2Scene *scene, const B2SceneDesc *desc) {
+    if (!scene) return fail(B2_ERR_INVALID, "null scene");
+    B2Scene *fresh = nullptr;
+    int rc = b2_scene_create(desc, &fresh);
+    if (rc != B2_OK) return rc;
+    cudaStreamSynchronize(scene->stream);           // no render of the old geometry may still be in flight
+    if (scene->stream2) cudaStreamSynchronize(scene->stream2);
+    B2Scene &a = *scene, &b = *fresh;
+    std::swap(a.d, b.d);
+    auto sw = [](auto &x, auto &y) { std::swap(x.p, y.p); std::swap(x.n, y.n); };
+    sw(a.nodes, b.nodes); sw(a.tri_isect, b.tri_isect); sw(a.flat_leaves, b.flat_leaves); sw(a.instances, b.instances);
+    sw(a.env_data, b.env_data); sw(a.env_levels, b.env_levels); sw(a.inst_order, b.inst_order); sw(a.blob, b.blob); sw(a.tex_data, b.tex_data);
+    std::swap(a.shade_smem_bytes, b.shade_smem_bytes); std::swap(a.features, b.features); std::swap(a.has_shapes, b.has_shapes);
+    std::swap(a.n_tris, b.n_tris); std::swap(a.n_nodes, b.n_nodes); std::swap(a.bvh_depth, b.bvh_depth);
+    std::swap(a.ms_build, b.ms_build); std::swap(a.ms_upload, b.ms_upload); std::swap(a.smem_bytes, b.smem_bytes);
+    delete fresh;                                   // releases the old geometry
+    return B2_OK;
+}
+
 int b2_set_stream(B2Scene *scene, void *stream) {
     if (!scene) return fail(B2_ERR_INVALID, "null scene");
     scene->stream = (cudaStream_t) stream;

@@ -63,3 +63,34 @@ def test_lbvh_million_triangles(b2):
         sbs["ms_build"], sa["ms_build"], sbs["bvh_depth"], sa["bvh_depth"],
         sbs["n_nodes_visited"] / (sbs["n_segments"] + sbs["n_shadow_rays"]), sa["n_nodes_visited"] / (sa["n_segments"] + sa["n_shadow_rays"])))
     assert sbs["ms_build"] < 50.0
+
+
+def test_scene_update_equals_fresh_create(b2):
+    """b2_scene_update (Scene::parameters_changed -> accel_parameters_changed, scene.cpp:242-260): moved geometry, then a
+    completely different scene (instanced, other film size), behind ONE handle; each film is bit-identical to the film of a
+    freshly created scene, and the device rebuild is reported in the stats."""
+    H = b2.Host()
+    frames = [lambda: scenes.cbox(H, 64, 64, lift=0.0), lambda: scenes.cbox(H, 64, 64, lift=40.0),
+              lambda: scenes.instanced_grid(H, 96, 64, grid=21, lattice=4), lambda: scenes.cbox(H, 48, 80, lift=10.0)]
+    first = frames[0](); first.build_flags = abi.BUILD_DEVICE_LBVH
+    sc = b2.Scene(first)
+    rp = abi.render_params(max_depth=6, rr_depth=5, spp=8, block_size=32)
+    prev = None
+    for k, make in enumerate(frames):
+        sb = make(); sb.build_flags = abi.BUILD_DEVICE_LBVH
+        if k:
+            sc.update(sb)
+        out = np.empty((sc.height, sc.width, 5), np.float32); st = abi.B2Stats()
+        assert b2.lib().b2_render(sc._h, C.byref(rp), out.ctypes.data, C.byref(st)) == 0, b2.lib().b2_last_error()
+        ref, _, fresh = _render(b2, make(), spp=8)           # host-built tree, fresh handle: same film (tie rule is tree-independent)
+        fresh.close()
+        assert np.array_equal(out.view(np.uint32), ref.view(np.uint32)), k
+        if prev is not None and prev.shape == out.shape:
+            assert not np.array_equal(prev, out)             # the geometry did change
+        prev = out
+    # a failing update leaves the handle usable with its old contents
+    d = frames[3]().desc(); d.n_top_meshes = d.n_meshes + 1
+    assert b2.lib().b2_scene_update(sc._h, C.byref(d)) == 1
+    out2 = np.empty_like(prev)
+    assert b2.lib().b2_render(sc._h, C.byref(rp), out2.ctypes.data, None) == 0
+    assert np.array_equal(out2.view(np.uint32), prev.view(np.uint32))
