@@ -222,7 +222,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     // all in one node array (top-level first: it is the part staged into shared memory)
     uint32_t n_top_tris = mesh_first[n_top_meshes];
     struct { std::vector<float> nodes; std::vector<uint32_t> order; uint32_t n_nodes = 0, depth = 0; } bvh;
-    uint32_t top_nodes = 0;
+    uint32_t top_nodes = 0; bool top_bfs = true;
     // builder: host binned SAH, or (B2_BUILD_DEVICE_LBVH) the device LBVH with the host builder as fallback
     auto t_build0 = std::chrono::steady_clock::now();
     float ms_device_build = 0.f; bool used_device = false;
@@ -237,7 +237,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
         std::vector<B2BvhTri> sub(tris.begin(), tris.begin() + n_top_tris);
         B2Bvh4 b; build_tris(sub, b);
         b2_bvh4_append(bvh.nodes, b, 0);
-        bvh.order = b.order; bvh.depth = b.depth; top_nodes = b.n_nodes;
+        bvh.order = b.order; bvh.depth = b.depth; top_nodes = b.n_nodes; top_bfs = b.breadth_first;
     } else {
         // analytic shapes share the top-level BVH: primitive boxes = the top-level triangles' boxes, then one box per shape
         // (Rectangle::bbox rectangle.cpp:94-101, Sphere::bbox sphere.cpp:131-136); shape k is primitive nt + k
@@ -645,7 +645,7 @@ int b2_scene_create(const B2SceneDesc *desc, B2Scene **out) {
     // shared-memory staging plan: whole scene if it fits in 48 KB, else the top of the tree (32 KB)
     const uint32_t budget_all = 48 * 1024, budget_top = 32 * 1024;
     if (bvh.n_nodes * 128u + n_slots * 48u <= budget_all) { d.smem_nodes = bvh.n_nodes; d.smem_tris = 1; }
-    else { d.smem_nodes = used_device ? 0u : std::min<uint32_t>(top_nodes, budget_top / 128u); d.smem_tris = 0; }   // (LBVH nodes are not in breadth-first order)
+    else { d.smem_nodes = top_bfs ? std::min<uint32_t>(top_nodes, budget_top / 128u) : 0u; d.smem_tris = 0; }   // (a prefix of a breadth-first numbering)
     // tiny flat scenes: list the BVH leaves (box + code) for the exhaustive leaf scan (traverse_flat)
     d.n_flat_leaves = 0; d.flat_leaves = nullptr;
     if (d.smem_tris && desc->n_instances == 0 && nt > 0 && ns == 0) {

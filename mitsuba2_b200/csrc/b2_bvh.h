@@ -23,6 +23,7 @@ struct B2Bvh4 {
     std::vector<uint32_t> order;    // slot -> input triangle index
     uint32_t n_nodes = 0;
     uint32_t depth = 0;
+    bool breadth_first = true;      // node numbering: any prefix is a top of the tree (shared-memory staging)
 };
 
 void b2_build_bvh4(const std::vector<B2BvhTri> &tris, B2Bvh4 &out);

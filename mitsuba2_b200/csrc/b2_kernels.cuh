@@ -155,27 +155,12 @@ struct Hit { float t, u, v; uint32_t slot, prim; int inst; };
 // (mesh.h:200-203), so the result is bit-identical to tri_intersect().
 B2_D bool tri_isect(float3 p0, float3 e1, float3 e2, const Ray &ray, float tmax, float &t, float &u, float &v) {
     float3 pvec = cross(ray.d, e2);
-    const float det = dot(e1, pvec);
+    float inv_det = b2_rcp(dot(e1, pvec));
     float3 tvec = ray.o - p0;
-    const float un = dot(tvec, pvec);
-#ifndef B2_NO_TRI_PRETEST
-    // Most tests fail; a certain miss is recognised with one MUFU.RCP instead of the correctly rounded reciprocal (8
-    // instructions + a slow path): the approximation is within a few ulp, the margins are 1e-5, so whatever is rejected here
-    // is rejected by the exact comparisons below as well — the accepted set, and every accepted (t, u, v), is unchanged.
-    float ra; asm("rcp.approx.f32 %0, %1;" : "=f"(ra) : "f"(det));
-    const float ua = un * ra;
-    if (ua < -1e-5f || ua > 1.00001f) return false;
-#endif
-    float3 qvec = cross(tvec, e1);
-    const float vn = dot(ray.d, qvec);
-#ifndef B2_NO_TRI_PRETEST
-    const float va = vn * ra;
-    if (va < -1e-5f || ua + va > 1.00002f) return false;
-#endif
-    float inv_det = b2_rcp(det);
-    u = un * inv_det;
+    u = dot(tvec, pvec) * inv_det;
     if (!(u >= 0.f && u <= 1.f)) return false;
-    v = vn * inv_det;
+    float3 qvec = cross(tvec, e1);
+    v = dot(ray.d, qvec) * inv_det;
     if (!(v >= 0.f && u + v <= 1.f)) return false;
     t = dot(e2, qvec) * inv_det;
     return t >= ray.mint && t <= tmax;
@@ -639,6 +624,9 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     const uint32_t total = q.n_slots + (q.direct_e ? q.n_slots * q.direct_e : n_shadow);
     uint32_t n_seg = 0, n_dsh = 0;
     int2 stk[B2_INST_STACK];          // (node / leaf code, entry distance bits): one 8-byte local-memory access per push / pop
+#ifndef B2_INST_NOSAVE
+    float4 wsave[3];
+#endif
     Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f; tr.n_nodes = 0; tr.n_tris = 0;
     uint32_t item = 0;
     bool busy = false, exhausted = false;
@@ -719,6 +707,12 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     const DInstance &in = sc.instances[ii];
                     Ray ro; ro.o = xf_point(in.to_object, tr.ray.o); ro.d = xf_vector(in.to_object, tr.ray.d);
                     ro.mint = tr.ray.mint; ro.maxt = tr.ray.maxt;
+#ifndef B2_INST_NOSAVE
+                    // the world-space ray and its slab constants wait in local memory for the way back (3 x 16 B)
+                    wsave[0] = make_float4(tr.ray.o.x, tr.ray.o.y, tr.ray.o.z, tr.idx);
+                    wsave[1] = make_float4(tr.ray.d.x, tr.ray.d.y, tr.ray.d.z, tr.idy);
+                    wsave[2] = make_float4(tr.idz, tr.oox, tr.ooy, tr.ooz);
+#endif
                     tr.set_ray(ro);
                     tr.inst = (int) ii;
                     stk[tr.sp++] = make_int2(B2_TRAV_POP, __float_as_int(-B2_INF));
@@ -753,12 +747,22 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     if (c == B2_TRAV_DONE) { tr.cur = c; break; }
                     if (c == B2_TRAV_POP) {
                         if (tr.inst == -2) { tr.inst = -1; tr.cur = (int) sc.tlas_root; break; }
+#ifndef B2_INST_NOSAVE
+                        // back to world space: the saved ray and slab constants (what set_ray() derived from them on the way in)
+                        const float4 w0 = wsave[0], w1 = wsave[1], w2 = wsave[2];
+                        tr.ray.o = v3(w0); tr.ray.d = v3(w1); tr.idx = w0.w; tr.idy = w1.w; tr.idz = w2.x; tr.oox = w2.y; tr.ooy = w2.z; tr.ooz = w2.w;
+                        tr.tmax = fminf(tr.ray.maxt, tr.best.t);
+                        tr.nxi = w1.x < 0.f ? 3 : 0; tr.fxi = w1.x < 0.f ? 0 : 3;
+                        tr.nyi = w1.y < 0.f ? 4 : 1; tr.fyi = w1.y < 0.f ? 1 : 4;
+                        tr.nzi = w1.z < 0.f ? 5 : 2; tr.fzi = w1.z < 0.f ? 2 : 5;
+#else
                         // back to world space: the ray is re-read from the queue
                         float4 ro, rd;
                         if (!any_ray) { rd = q.ray_d[item]; ro = q.ray_o[item]; }
                         else { rd = q.sh_d[item - q.n_slots]; ro = q.sh_o[item - q.n_slots]; }
                         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
                         tr.set_ray(ray);
+#endif
                         tr.inst = -1;
                         continue;
                     }
