@@ -624,9 +624,6 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
     const uint32_t total = q.n_slots + (q.direct_e ? q.n_slots * q.direct_e : n_shadow);
     uint32_t n_seg = 0, n_dsh = 0;
     int2 stk[B2_INST_STACK];          // (node / leaf code, entry distance bits): one 8-byte local-memory access per push / pop
-#ifndef B2_INST_NOSAVE
-    float4 wsave[3];
-#endif
     Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f; tr.n_nodes = 0; tr.n_tris = 0;
     uint32_t item = 0;
     bool busy = false, exhausted = false;
@@ -707,12 +704,6 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     const DInstance &in = sc.instances[ii];
                     Ray ro; ro.o = xf_point(in.to_object, tr.ray.o); ro.d = xf_vector(in.to_object, tr.ray.d);
                     ro.mint = tr.ray.mint; ro.maxt = tr.ray.maxt;
-#ifndef B2_INST_NOSAVE
-                    // the world-space ray and its slab constants wait in local memory for the way back (3 x 16 B)
-                    wsave[0] = make_float4(tr.ray.o.x, tr.ray.o.y, tr.ray.o.z, tr.idx);
-                    wsave[1] = make_float4(tr.ray.d.x, tr.ray.d.y, tr.ray.d.z, tr.idy);
-                    wsave[2] = make_float4(tr.idz, tr.oox, tr.ooy, tr.ooz);
-#endif
                     tr.set_ray(ro);
                     tr.inst = (int) ii;
                     stk[tr.sp++] = make_int2(B2_TRAV_POP, __float_as_int(-B2_INF));
@@ -747,22 +738,12 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     if (c == B2_TRAV_DONE) { tr.cur = c; break; }
                     if (c == B2_TRAV_POP) {
                         if (tr.inst == -2) { tr.inst = -1; tr.cur = (int) sc.tlas_root; break; }
-#ifndef B2_INST_NOSAVE
-                        // back to world space: the saved ray and slab constants (what set_ray() derived from them on the way in)
-                        const float4 w0 = wsave[0], w1 = wsave[1], w2 = wsave[2];
-                        tr.ray.o = v3(w0); tr.ray.d = v3(w1); tr.idx = w0.w; tr.idy = w1.w; tr.idz = w2.x; tr.oox = w2.y; tr.ooy = w2.z; tr.ooz = w2.w;
-                        tr.tmax = fminf(tr.ray.maxt, tr.best.t);
-                        tr.nxi = w1.x < 0.f ? 3 : 0; tr.fxi = w1.x < 0.f ? 0 : 3;
-                        tr.nyi = w1.y < 0.f ? 4 : 1; tr.fyi = w1.y < 0.f ? 1 : 4;
-                        tr.nzi = w1.z < 0.f ? 5 : 2; tr.fzi = w1.z < 0.f ? 2 : 5;
-#else
                         // back to world space: the ray is re-read from the queue
                         float4 ro, rd;
                         if (!any_ray) { rd = q.ray_d[item]; ro = q.ray_o[item]; }
                         else { rd = q.sh_d[item - q.n_slots]; ro = q.sh_o[item - q.n_slots]; }
                         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
                         tr.set_ray(ray);
-#endif
                         tr.inst = -1;
                         continue;
                     }

@@ -9,13 +9,9 @@
 //   cub::DeviceRadixSort::SortPairs (key = code, value = primitive) — library sort; not on the render path
 //   k_hierarchy     Karras 2012: one thread per internal node finds its range and split (ties broken by index)
 //   k_fit           leaves walk up; the second arrival at a node unions its children (one atomic per node)
-//   k_expand/k_link  top-down collapse to BVH4, one launch pair per level: a node adopts the two children of its binary node
-//                   and keeps opening the child with the largest surface area until it has four (a subtree with <= max_leaf
-//                   primitives is a BVH4 leaf); cub::DeviceScan numbers the next level, so nodes come out in BREADTH-FIRST
-//                   order (root = 0, deterministic) and the top of the tree is a prefix that the trace kernels stage in
-//                   shared memory. 128-byte nodes, child boxes inflated like b2_bvh.cpp.
-//   k_select/k_emit the fallback when that tree would be deeper than the traversal stacks allow: binary nodes at EVEN depth
-//                   become BVH4 nodes (each adopts its grandchildren), which halves the binary depth exactly
+//   k_select        a subtree with <= max_leaf primitives becomes a BVH4 leaf; the other internal nodes at EVEN depth
+//                   become BVH4 nodes (each adopts its grandchildren), the odd ones dissolve
+//   cub::DeviceScan (node numbering: deterministic, root = 0), k_emit (128-byte nodes, child boxes inflated like b2_bvh.cpp)
 #include "b2_bvh.h"
 
 #include <cub/cub.cuh>
@@ -195,85 +191,6 @@ __global__ void k_emit(const Node2 *nodes, uint32_t n, uint32_t max_leaf, const 
     N[7] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
-
-// ---- level-by-level collapse (breadth-first numbering) ---------------------------------------------------------------
-__device__ __forceinline__ float box_area(float4 lo, float4 hi) {
-    float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
-    return dx * dy + dy * dz + dz * dx;
-}
-
-// frontier[i] = binary node that becomes BVH4 node base + i. Writes the node (boxes, leaf codes), the binary ids of its
-// internal children (pending[4 i + k], -1 = none) and their count.
-__global__ void k_expand(const Node2 *nodes, uint32_t max_leaf, const uint32_t *frontier, uint32_t fc, uint32_t base, const uint32_t *vals,
-                         const float4 *blo, const float4 *bhi, const float4 *nlo, const float4 *nhi, float pad_abs, float4 *out,
-                         int *pending, uint32_t *n_pending) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= fc) return;
-    const uint32_t b = frontier[i];
-    int c[4]; float area[4]; int ne = 0;
-    auto count_of = [&](int x) -> uint32_t { return x < 0 ? 1u : nodes[x].last - nodes[x].first + 1u; };
-    auto area_of = [&](int x) -> float { return (x < 0 || count_of(x) <= max_leaf) ? -1.f : box_area(nlo[x], nhi[x]); };   // -1: not expandable
-    const Node2 &nd = nodes[b];
-    if (nd.last - nd.first + 1u <= max_leaf) { c[0] = (int) b; area[0] = -1.f; ne = 1; }     // (only the root can be leaf-like here)
-    else {
-        c[0] = nd.left; c[1] = nd.right; area[0] = area_of(c[0]); area[1] = area_of(c[1]); ne = 2;
-        while (ne < 4) {
-            int best = -1; float ba = -1.f;
-            for (int k = 0; k < ne; ++k) if (area[k] > ba) { ba = area[k]; best = k; }      // ties: the first one
-            if (best < 0 || ba < 0.f) break;
-            const Node2 &o = nodes[c[best]];
-            for (int k = ne; k > best + 1; --k) { c[k] = c[k - 1]; area[k] = area[k - 1]; }     // keep the spatial order
-            c[best] = o.left; c[best + 1] = o.right; area[best] = area_of(o.left); area[best + 1] = area_of(o.right);
-            ++ne;
-        }
-    }
-    const float inf = __int_as_float(0x7f800000);
-    float v[6][4]; int code[4]; uint32_t np = 0;
-    for (int k = 0; k < 4; ++k) {
-        int pend = -1;
-        if (k < ne) {
-            float4 lo, hi;
-            if (c[k] < 0) { uint32_t p = (uint32_t) ~c[k], t = vals[p]; lo = blo[t]; hi = bhi[t]; code[k] = (int) (0x80000000u | (1u << 27) | p); }
-            else {
-                lo = nlo[c[k]]; hi = nhi[c[k]];
-                uint32_t cnt = count_of(c[k]);
-                if (cnt <= max_leaf) code[k] = (int) (0x80000000u | (cnt << 27) | nodes[c[k]].first);
-                else { code[k] = 0; pend = c[k]; ++np; }
-            }
-            const float l3[3] = { lo.x, lo.y, lo.z }, h3[3] = { hi.x, hi.y, hi.z };
-            for (int a = 0; a < 3; ++a) { v[a][k] = l3[a] - (1e-5f * fabsf(l3[a]) + pad_abs); v[3 + a][k] = h3[a] + (1e-5f * fabsf(h3[a]) + pad_abs); }
-        } else { for (int a = 0; a < 3; ++a) { v[a][k] = inf; v[3 + a][k] = -inf; } code[k] = 0; }
-        pending[4 * (size_t) i + k] = pend;
-    }
-    n_pending[i] = np;
-    float4 *N = out + 8 * (size_t) (base + i);
-    for (int a = 0; a < 6; ++a) N[a] = make_float4(v[a][0], v[a][1], v[a][2], v[a][3]);
-    N[6] = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), __int_as_float(code[2]), __int_as_float(code[3]));
-    N[7] = make_float4(0.f, 0.f, 0.f, 0.f);
-}
-
-// the internal children get the numbers next_base + offset[i] + rank and form the next frontier
-__global__ void k_link(const int *pending, const uint32_t *offset, uint32_t fc, uint32_t base, uint32_t next_base, float4 *out, uint32_t *next_frontier) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= fc) return;
-    uint32_t r = offset[i];
-    int *codes = reinterpret_cast<int *>(out + 8 * (size_t) (base + i) + 6);
-    for (int k = 0; k < 4; ++k) {
-        int p = pending[4 * (size_t) i + k];
-        if (p < 0) continue;
-        codes[k] = (int) (next_base + r);
-        next_frontier[r] = (uint32_t) p;
-        ++r;
-    }
-}
-
-__global__ void k_count_big(const Node2 *nodes, uint32_t n, uint32_t max_leaf, uint32_t *count) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool big = i < n - 1 && (nodes[i].last - nodes[i].first + 1u > max_leaf || i == 0);
-    uint32_t m = __ballot_sync(0xffffffffu, big);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (uint32_t) __popc(m));
-}
-
 template <typename T> struct Dev {
     T *p = nullptr;
     ~Dev() { if (p) cudaFree(p); }
@@ -293,14 +210,13 @@ bool b2_build_bvh4_device(const float *prims, uint32_t n, bool is_boxes, int max
     if (n < 2) { if (error) *error = "fewer than 2 primitives"; return false; }
     const size_t in_floats = (size_t) n * (is_boxes ? 6 : 9);
     Dev<float> d_in; Dev<float4> blo, bhi, nlo, nhi, d_nodes; Dev<Bounds> cb; Dev<unsigned long long> k0, k1; Dev<uint32_t> v0, v1, flags, sel, idx, maxd;
-    Dev<Node2> nodes; Dev<int> leaf_parent, pending; Dev<unsigned char> tmp;
+    Dev<Node2> nodes; Dev<int> leaf_parent; Dev<unsigned char> tmp;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     const unsigned T = 256, G = (n + T - 1) / T;
     size_t tmp_sort = 0, tmp_scan = 0;
     uint32_t n4 = 0, depth = 0;
     Bounds hb;
-    float diag = 0.f, pad_abs = 0.f;
-    bool bfs = false;
+    float diag = 0.f;
     {
         LB_CU(d_in.alloc(in_floats)); LB_CU(blo.alloc(n)); LB_CU(bhi.alloc(n)); LB_CU(nlo.alloc(n)); LB_CU(nhi.alloc(n)); LB_CU(cb.alloc(1));
         LB_CU(k0.alloc(n)); LB_CU(k1.alloc(n)); LB_CU(v0.alloc(n)); LB_CU(v1.alloc(n)); LB_CU(flags.alloc(n)); LB_CU(sel.alloc(n)); LB_CU(idx.alloc(n)); LB_CU(maxd.alloc(1));
@@ -319,8 +235,16 @@ bool b2_build_bvh4_device(const float *prims, uint32_t n, bool is_boxes, int max
         LB_CU(cub::DeviceRadixSort::SortPairs(tmp.p, tmp_sort, k0.p, k1.p, v0.p, v1.p, (int) n, 0, 63));
         k_hierarchy<<<G, T>>>(k1.p, n, nodes.p, leaf_parent.p);
         k_fit<<<G, T>>>(nodes.p, leaf_parent.p, v1.p, blo.p, bhi.p, n, nlo.p, nhi.p, flags.p);
-        LB_CU(cudaMemcpyAsync(&hb, cb.p, sizeof hb, cudaMemcpyDeviceToHost));
-        LB_CU(cudaStreamSynchronize(nullptr));
+        k_select<<<G, T>>>(nodes.p, n, (uint32_t) max_leaf, sel.p, maxd.p);
+        LB_CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_scan, sel.p, idx.p, (int) (n - 1)));
+        {   // number of BVH4 nodes = index[n-2] + selected[n-2]
+            uint32_t a = 0, b = 0;
+            LB_CU(cudaMemcpy(&a, idx.p + (n - 2), 4, cudaMemcpyDeviceToHost)); LB_CU(cudaMemcpy(&b, sel.p + (n - 2), 4, cudaMemcpyDeviceToHost));
+            n4 = a + b;
+        }
+        LB_CU(cudaMemcpy(&depth, maxd.p, 4, cudaMemcpyDeviceToHost));
+        if (depth > B2_BVH_MAX_DEPTH) { err = "LBVH deeper than B2_BVH_MAX_DEPTH"; goto fail; }
+        LB_CU(cudaMemcpy(&hb, cb.p, sizeof hb, cudaMemcpyDeviceToHost));
         // (the inflation constant uses the extent of the centroid bounds; the primitives' own extent is covered by the relative term)
         for (int k = 0; k < 3; ++k) {
             int lo = hb.lo[k], hi = hb.hi[k];
@@ -328,42 +252,8 @@ bool b2_build_bvh4_device(const float *prims, uint32_t n, bool is_boxes, int max
             std::memcpy(&a, &la, 4); std::memcpy(&b, &lb, 4);
             diag = std::max(diag, b - a);
         }
-        pad_abs = 1e-7f * diag + 1e-30f;
-        {   // breadth-first collapse, one level per iteration (sel = frontier, idx = next frontier, flags = offsets, v0 = counts)
-            uint32_t n_big = 0;
-            k_count_big<<<G, T>>>(nodes.p, n, (uint32_t) max_leaf, maxd.p);
-            LB_CU(cudaMemcpy(&n_big, maxd.p, 4, cudaMemcpyDeviceToHost));
-            LB_CU(d_nodes.alloc((size_t) n_big * 8)); LB_CU(pending.alloc((size_t) n_big * 4));
-            uint32_t *fr = sel.p, *fr_next = idx.p;
-            uint32_t fc = 1, base = 0, zero = 0;
-            LB_CU(cudaMemcpy(fr, &zero, 4, cudaMemcpyHostToDevice));
-            depth = 0; bool too_deep = false;
-            while (fc) {
-                if (++depth > B2_BVH_MAX_DEPTH) { too_deep = true; break; }
-                const unsigned g = (fc + T - 1) / T;
-                k_expand<<<g, T>>>(nodes.p, (uint32_t) max_leaf, fr, fc, base, v1.p, blo.p, bhi.p, nlo.p, nhi.p, pad_abs, d_nodes.p, pending.p, v0.p);
-                LB_CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_scan, v0.p, flags.p, (int) fc));
-                k_link<<<g, T>>>(pending.p, flags.p, fc, base, base + fc, d_nodes.p, fr_next);
-                uint32_t last[2] = { 0, 0 };
-                LB_CU(cudaMemcpy(&last[0], flags.p + (fc - 1), 4, cudaMemcpyDeviceToHost)); LB_CU(cudaMemcpy(&last[1], v0.p + (fc - 1), 4, cudaMemcpyDeviceToHost));
-                base += fc; fc = last[0] + last[1];
-                std::swap(fr, fr_next);
-            }
-            n4 = base; bfs = !too_deep;
-        }
-        if (!bfs) {     // the parity rule halves the binary depth
-            LB_CU(cudaMemsetAsync(maxd.p, 0, 4));
-            k_select<<<G, T>>>(nodes.p, n, (uint32_t) max_leaf, sel.p, maxd.p);
-            LB_CU(cub::DeviceScan::ExclusiveSum(tmp.p, tmp_scan, sel.p, idx.p, (int) (n - 1)));
-            {   // number of BVH4 nodes = index[n-2] + selected[n-2]
-                uint32_t a = 0, b = 0;
-                LB_CU(cudaMemcpy(&a, idx.p + (n - 2), 4, cudaMemcpyDeviceToHost)); LB_CU(cudaMemcpy(&b, sel.p + (n - 2), 4, cudaMemcpyDeviceToHost));
-                n4 = a + b;
-            }
-            LB_CU(cudaMemcpy(&depth, maxd.p, 4, cudaMemcpyDeviceToHost));
-            if (depth > B2_BVH_MAX_DEPTH) { err = "LBVH deeper than B2_BVH_MAX_DEPTH"; goto fail; }
-            k_emit<<<G, T>>>(nodes.p, n, (uint32_t) max_leaf, sel.p, idx.p, v1.p, blo.p, bhi.p, nlo.p, nhi.p, pad_abs, d_nodes.p);
-        }
+        LB_CU(d_nodes.alloc((size_t) n4 * 8));
+        k_emit<<<G, T>>>(nodes.p, n, (uint32_t) max_leaf, sel.p, idx.p, v1.p, blo.p, bhi.p, nlo.p, nhi.p, 1e-7f * diag + 1e-30f, d_nodes.p);
         LB_CU(cudaEventRecord(e1));
         LB_CU(cudaEventSynchronize(e1));
         LB_CU(cudaGetLastError());
@@ -371,7 +261,7 @@ bool b2_build_bvh4_device(const float *prims, uint32_t n, bool is_boxes, int max
         out.nodes.resize((size_t) n4 * 32); out.order.resize(n);
         LB_CU(cudaMemcpy(out.nodes.data(), d_nodes.p, (size_t) n4 * 128, cudaMemcpyDeviceToHost));
         LB_CU(cudaMemcpy(out.order.data(), v1.p, (size_t) n * 4, cudaMemcpyDeviceToHost));
-        out.n_nodes = n4; out.depth = depth; out.breadth_first = bfs;
+        out.n_nodes = n4; out.depth = depth; out.breadth_first = false;     // (numbered by a scan over the binary nodes)
         cudaEventDestroy(e0); cudaEventDestroy(e1);
         return true;
     }

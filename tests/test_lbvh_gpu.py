@@ -89,7 +89,7 @@ def test_scene_update_equals_fresh_create(b2):
             assert not np.array_equal(prev, out)             # the geometry did change
         prev = out
     # a failing update leaves the handle usable with its old contents
-    d = frames[3]().desc(); d.n_top_meshes = d.n_meshes + 1
+    bad = frames[3](); d = bad.desc(); d.meshes[0].bsdf = 99
     assert b2.lib().b2_scene_update(sc._h, C.byref(d)) == 1
     out2 = np.empty_like(prev)
     assert b2.lib().b2_render(sc._h, C.byref(rp), out2.ctypes.data, None) == 0
