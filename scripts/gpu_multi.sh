@@ -17,5 +17,5 @@ PY
 for n in 8 2; do timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) scripts/multi_parity.py > $out/${tag}_parity_n$n.json 2> $out/${tag}_parity_n$n.err; tail -c 900 $out/${tag}_parity_n$n.json; tail -3 $out/${tag}_parity_n$n.err | cut -c1-200; done
 for n in ${GPUS:-8 4 2}; do tr $n veach --workload veach --res 1280 --spp 1024 --steps 3 --warmup 3; done
 tr 8 grid --workload grid --res 2048 --spp 64 --steps 3 --warmup 3
-for n in 8 4 2; do tr $n cbox --workload cbox --steps 5 --warmup 3; done
-python bench.py --cpu-baseline 0 --workload veach --res 1280 --spp 1024 > $out/${tag}_veach_n1.json 2> $out/${tag}_veach_n1.err; tail -c 400 $out/${tag}_veach_n1.json | cut -c1-300
+if [ -n "$WITH_CBOX" ]; then for n in 8 4 2; do tr $n cbox --workload cbox --steps 5 --warmup 3; done; fi      # (the driver's own scaling run is exactly this)
+# (the 1-GPU line of the same configuration: scripts/gpu_session9.sh)
