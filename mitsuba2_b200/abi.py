@@ -17,6 +17,13 @@ FLAG_STAGE_TIMING = 1
 FLAG_SINGLE_SET = 2
 FLAG_COUNT_BVH = 4
 FLAG_PERSISTENT_TRACE = 8
+FLAG_STATIC_TRACE = 16
+
+
+def flag_yield_threshold(n):
+    """B2_FLAG_YIELD_THRESHOLD(n)"""
+    return (n & 0x1f) << 8
+
 BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1
 
 

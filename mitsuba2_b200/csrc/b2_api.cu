@@ -65,7 +65,11 @@ static ShadeFn shade_variant(uint32_t features) {
     if (!init) { fill_shade(table, std::make_integer_sequence<uint32_t, F_COUNT>{}); init = true; }
     return table[features & (F_COUNT - 1)];
 }
-static TraceFn trace_variant(bool inst, bool shp, bool count) {
+static TraceFn trace_variant(bool inst, bool shp, bool count, bool resume = false) {
+    if (resume && !inst) {
+        if (count) return shp ? k_trace_resume<true, true> : k_trace_resume<false, true>;
+        return shp ? k_trace_resume<true, false> : k_trace_resume<false, false>;
+    }
     if (count) {
         if (shp) return inst ? k_trace_inst<true, true> : k_trace<false, true, true>;
         return inst ? k_trace_inst<false, true> : k_trace<false, false, true>;
@@ -112,6 +116,7 @@ struct B2Scene {
     DBuf<float2> pos;
     DBuf<uint32_t> pixel, list, cnt, item_pixel, item_seed;
     DBuf<uint8_t> cls;
+    DBuf<uint32_t> resume; DBuf<int4> tsave;                              // k_trace_resume: suspended lanes + their traversal state
     DBuf<float4> prim_o, prim_d, prim_hit; DBuf<int32_t> prim_inst;      // DirectIntegrator: the camera segment per lane
     DBuf<unsigned long long> stats;
     DBuf<float> film;
@@ -813,6 +818,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // leaf scan of tiny scenes has no use for it)
     const bool inst = s->d.n_instances != 0 || ((rp->flags & B2_FLAG_PERSISTENT_TRACE) && s->d.n_flat_leaves == 0);
     if (inst) { CU(s->hit_inst.alloc(cap)); CU(s->cls.alloc(cap)); CU(cudaMemsetAsync(s->cls.p, 0, cap, stream)); }
+    // yield / resume traversal (k_trace_resume): BVH4 scenes without instances whose rays need a real tree walk (the flat
+    // leaf scan of tiny scenes has no tail to cut)
+    const bool resume = !inst && s->d.n_flat_leaves == 0 && !(rp->flags & B2_FLAG_STATIC_TRACE);
+    if (resume) { CU(s->resume.alloc(2 * cap)); CU(s->tsave.alloc(cap * B2_TSAVE_INT4)); }
     CU(s->cnt.alloc(32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
@@ -864,6 +873,11 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         q.pixel = s->pixel.p + o; q.list[0] = s->list.p + 2 * o; q.list[1] = s->list.p + 2 * o + set_slots;
         q.pos = wide ? s->pos.p + o : nullptr;
         q.hit_inst = inst ? s->hit_inst.p + o : nullptr; q.cls = inst ? s->cls.p + o : nullptr;
+        if (resume) {
+            q.resume[0] = s->resume.p + 2 * o; q.resume[1] = s->resume.p + 2 * o + set_slots; q.tsave = s->tsave.p + o * B2_TSAVE_INT4;
+            const uint32_t thr = (rp->flags >> 8) & 0x1fu;                // B2_FLAG_YIELD_THRESHOLD(n): tuning override
+            q.yield_threshold = thr ? thr : 12u;
+        }
         const size_t so = o * (size_t) std::max<uint32_t>(dE, 1u);
         q.sh_o = s->sh_o.p + so; q.sh_d = s->sh_d.p + so; q.sh_c = s->sh_c.p + so;
         if (direct) {
@@ -898,7 +912,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // non-independent samplers run in the extended (F_TEX) kernel variants
     const uint32_t run_features = s->features | ((sampler_type != B2_SAMPLER_INDEPENDENT || direct) ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
-    const TraceFn trace_fn = trace_variant(inst, s->has_shapes, (rp->flags & B2_FLAG_COUNT_BVH) != 0);
+    const TraceFn trace_fn = trace_variant(inst, s->has_shapes, (rp->flags & B2_FLAG_COUNT_BVH) != 0, resume);
     // (the limit is a per-function, process-wide attribute: set it for THIS scene right before its launches)
     CU(cudaFuncSetAttribute(shade_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes));
     CU(cudaFuncSetAttribute(trace_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));

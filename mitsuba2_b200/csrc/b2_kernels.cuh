@@ -61,12 +61,18 @@ struct Queues {
     uint32_t direct_e, direct_b;
     float d_weight_bsdf, d_weight_lum, d_frac_bsdf, d_frac_lum;      // direct.cpp:96-100
     float4 *prim_o, *prim_d, *prim_hit; int32_t *prim_inst;
+    // yield / resume traversal (k_trace_resume): per iteration parity the lanes whose closest-hit traversal was suspended,
+    // and their saved traversal state (B2_TSAVE_WORDS words per lane); NULL when the static kernel runs
+    uint32_t *resume[2];
+    int4 *tsave;
+    uint32_t yield_threshold;   // a warp suspends its unfinished rays when fewer lanes than this are still traversing
 };
 
 // q.cnt words of one lane set (B2_CNT_WORDS each)
 enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */,
-       CNT_LIST = 4 /* and 6: 64-bit (n_continue | n_terminate << 32) per iteration parity */ };
-#define B2_CNT_WORDS 8
+       CNT_LIST = 4 /* and 6: 64-bit (n_continue | n_terminate << 32) per iteration parity */,
+       CNT_RESUME = 8 /* and 9: suspended lanes per iteration parity (k_trace_resume) */ };
+#define B2_CNT_WORDS 12
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES = 4, ST_TRIS = 5 };
 
 // st.w layout
@@ -78,6 +84,7 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES 
 #define STW_FILM_DROP    0x1000u     // sample falls outside its block (imageblock.cpp:166)
 #define STW_PARKED       0x2000u     // the path ended inside the loop body: the lane only waits for its film put
 #define STW_DIRECT_EMIT  0x4000u     // DirectIntegrator: the lane's emitter samples have not been added to its result yet
+#define STW_INFLIGHT     0x8000u     // k_trace_resume: the lane's closest-hit traversal is suspended (state in q.tsave)
 #define STW_LEFT(w)      ((w) >> 16)
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
@@ -575,6 +582,132 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
         Hit h;
         const bool occluded = traverse<true, INST, SHP, COUNT>(sc, sm, ray, h, counters);
+        if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
+        else if (!occluded) {
+            float4 c = q.sh_c[j];
+            const uint32_t lw = __float_as_uint(c.w);
+            float4 r = q.res[lw];
+            r.x += c.x; r.y += c.y; r.z += c.z;
+            q.res[lw] = r;
+        }
+    }
+    n_seg = __reduce_add_sync(0xffffffffu, n_seg);
+    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
+    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_dsh); }
+    if constexpr (COUNT) {
+        uint32_t a = __reduce_add_sync(0xffffffffu, counters[0]), b = __reduce_add_sync(0xffffffffu, counters[1]);
+        if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
+    }
+}
+
+// ---- general BVH4 scenes: yield / resume traversal across launches ------------------------------------
+// The number of BVH steps of a ray is roughly exponentially distributed (ncu, matball: 7.9 node visits per ray on
+// average, but 33 node rounds per warp: the longest of 32 rays), so with a static ray -> lane mapping a warp spends most
+// of its rounds on a handful of lanes. Here a warp SUSPENDS its unfinished rays as soon as fewer than
+// q.yield_threshold of its lanes are still traversing: their state (current node, best hit, the live part of the stack)
+// goes to q.tsave, the lane is flagged STW_INFLIGHT and appended to a dense RESUME list, and the next launch of the same
+// lane set continues those rays in full warps of 32 list entries. A suspended lane simply takes part in a later
+// iteration of the wavefront (it is on neither list until its ray is finished), so nothing else changes: its RNG stream,
+// work item and film pixel stay with the lane, the hit is the same lexicographic (t, -prim) minimum, films stay bit-identical.
+// Unlike the persistent-warp kernel this keeps ordinary short launches, so the other lane set's k_shade still shares the SMs.
+// Any-hit rays (emitter samples) run to completion: their contribution must reach `res` before the lane's next k_shade.
+#define B2_SAVE_MAX 28                          /* stack entries a suspended ray may hold (deeper: the warp keeps going) */
+#define B2_TSAVE_INT4 (2 + B2_SAVE_MAX / 4)     /* int4 words of q.tsave per lane: (cur, sp, slot, prim) (t, u, v, -) + the stack */
+
+template <bool SHP, bool COUNT>
+__global__ void __launch_bounds__(256, B2_TRACE_MINBLOCKS) k_trace_resume(DScene sc, Queues q, int parity) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SmemScene sm = stage_scene(sc, smem_raw);
+    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];         // filled by the previous k_shade
+    const uint32_t n_res = q.cnt[CNT_RESUME + (parity ^ 1)];            // suspended by the previous launch (zeroed by the next k_shade)
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[CNT_SHADOW + parity] = 0;
+        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;
+        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+    }
+    uint32_t n_seg = 0;
+    uint32_t counters[2] = { 0u, 0u };
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t chunks_res = (n_res + 31u) >> 5, chunks_new = (q.n_slots + 31u) >> 5;
+    const uint32_t thr = q.yield_threshold;
+    int stack[B2_STACK];
+    // the suspended rays first (they are the long ones), then the lanes that got a new ray from k_shade
+    for (uint32_t c = warp; c < chunks_res + chunks_new; c += n_warps) {
+        const bool resumed = c < chunks_res;
+        uint32_t i = 0, stw = 0;
+        bool have = false;
+        if (resumed) { const uint32_t k = c * 32u + lane_id(); if (k < n_res) { i = q.resume[parity ^ 1][k]; have = true; } }
+        else { i = (c - chunks_res) * 32u + lane_id(); have = i < q.n_slots; }
+        Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.n_nodes = 0; tr.n_tris = 0;
+        if (have) {
+            const float4 rd = q.ray_d[i];
+            stw = q.st[i].w;
+            have = resumed || (rd.w >= 0.f && !(stw & STW_INFLIGHT));       // (retired / parked lanes carry maxt < 0)
+            if (have) {
+                const float4 ro = q.ray_o[i];
+                Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+                if (!resumed) tr.init(sc, ray, stack);
+                else {
+                    const int4 *sv = q.tsave + (size_t) i * B2_TSAVE_INT4;
+                    const int4 h0 = sv[0], h1 = sv[1];
+                    tr.best.t = __int_as_float(h1.x); tr.best.u = __int_as_float(h1.y); tr.best.v = __int_as_float(h1.z);
+                    tr.best.slot = (uint32_t) h0.z; tr.best.prim = (uint32_t) h0.w; tr.best.inst = -1;
+                    tr.any_hit = false; tr.inst = -1;
+                    tr.set_ray(ray);                                          // (tmax = min(maxt, best.t))
+                    tr.cur = h0.x; tr.sp = h0.y;
+                    for (int e = 0; e < tr.sp; e += 4) {
+                        const int4 v = sv[2 + (e >> 2)];
+                        stack[e] = v.x; stack[e + 1] = v.y; stack[e + 2] = v.z; stack[e + 3] = v.w;
+                    }
+                }
+            }
+        }
+        // a chunk may suspend rays only if it started well above the threshold (the drain at the end of a render and the
+        // last, partial chunk of a list run to completion)
+        const bool can_yield = (uint32_t) __popc(__ballot_sync(0xffffffffu, have && tr.cur != B2_TRAV_DONE)) >= thr + 4u;
+        for (;;) {
+            const bool active = have && tr.cur != B2_TRAV_DONE;
+            const uint32_t act = __ballot_sync(0xffffffffu, active);
+            if (act == 0) break;
+            if (can_yield && (uint32_t) __popc(act) < thr && !__any_sync(0xffffffffu, active && tr.sp > B2_SAVE_MAX)) break;
+            if (active) {       // one while-while round: inner nodes down to a leaf, then the leaves until the next inner node
+                while ((uint32_t) tr.cur < (uint32_t) B2_TRAV_DONE) tr.node_step<COUNT>(sc, sm, stack);
+                while (tr.cur < 0) { tr.leaf_step<false, SHP, COUNT>(sc, sm, tr.cur); tr.cur = stack[--tr.sp]; }
+            }
+        }
+        const bool suspended = have && tr.cur != B2_TRAV_DONE;
+        bool cont = false, term = false;
+        if (have && !suspended) {
+            const Hit &h = tr.best;
+            q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+            if (resumed) q.st[i].w = stw & ~STW_INFLIGHT;
+            ++n_seg;
+            cont = h.t < B2_INF && STW_DEPTH(stw) < (uint32_t) q.max_depth;
+            term = !cont;
+        }
+        if (suspended) {
+            int4 *sv = q.tsave + (size_t) i * B2_TSAVE_INT4;
+            sv[0] = make_int4(tr.cur, tr.sp, (int) tr.best.slot, (int) tr.best.prim);
+            sv[1] = make_int4(__float_as_int(tr.best.t), __float_as_int(tr.best.u), __float_as_int(tr.best.v), 0);
+            for (int e = 0; e < tr.sp; e += 4) sv[2 + (e >> 2)] = make_int4(stack[e], stack[e + 1], stack[e + 2], stack[e + 3]);
+            if (!resumed) q.st[i].w = stw | STW_INFLIGHT;
+        }
+        const uint32_t r = warp_append(&q.cnt[CNT_RESUME + parity], suspended);
+        if (suspended) q.resume[parity][r] = i;
+        list_append(q, parity, i, cont, term, 0xffffffffu);
+        if constexpr (COUNT) { counters[0] += tr.n_nodes; counters[1] += tr.n_tris; }
+    }
+    uint32_t n_dsh = 0;
+    const uint32_t n_entries = q.direct_e ? q.n_slots * q.direct_e : n_shadow;      // (direct integrator: E entry slots per lane)
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_entries; j += gridDim.x * blockDim.x) {
+        float4 rd = q.sh_d[j];
+        if (q.direct_e && !(rd.w >= 0.f)) continue;
+        float4 ro = q.sh_o[j];
+        Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+        Trav tr; tr.init(sc, ray, stack);
+        tr.run<true, SHP, COUNT>(sc, sm, stack, false);
+        const bool occluded = tr.any_hit;
+        if constexpr (COUNT) { counters[0] += tr.n_nodes; counters[1] += tr.n_tris; }
         if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
         else if (!occluded) {
             float4 c = q.sh_c[j];
@@ -1325,7 +1458,10 @@ __global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Qu
     const Tables tb = stage_shade_tables(sc, smem_raw);
     // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
     const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
-    if (blockIdx.x == 0 && threadIdx.x == 0) q.cnt[CNT_FETCH] = 0;       // ray counter of the next k_trace_inst
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        q.cnt[CNT_FETCH] = 0;                                             // ray counter of the next k_trace_inst
+        if (q.tsave) q.cnt[CNT_RESUME + (parity ^ 1)] = 0;                // consumed by the k_trace_resume before this launch
+    }
     const uint32_t n_cont = (uint32_t) n_list, n_term = (uint32_t) (n_list >> 32);
     const uint32_t wc = (n_cont + 31u) >> 5, wt = (n_term + 31u) >> 5;
     uint32_t n_put = 0, n_bad = 0;
