@@ -320,10 +320,10 @@ def main_b2pt(a, rank, world, local_rank):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         if world > 1:
-            integ.render_reduce(scene, a.spp, reduce_film, rank=rank, world_size=world, lane_slots=a.lane_slots, out=host_film)
+            integ.render_reduce(scene, a.spp, reduce_film, rank=rank, world_size=world, lane_slots=a.lane_slots, out=host_film, flags=base_flags)
             torch.cuda.synchronize()
         else:
-            integ.render(scene, a.spp, lane_slots=a.lane_slots, out=host_film)
+            integ.render(scene, a.spp, lane_slots=a.lane_slots, out=host_film, flags=base_flags)
         return time.perf_counter() - t0
 
     clocks = ClockSampler(local_rank)

@@ -259,9 +259,9 @@ class PathIntegrator:
         return abi.render_params(self.max_depth, self.rr_depth, spp, self.samples_per_pass, self.block_size, seed,
                                  rank, world_size, lane_slots, flags, self.sampler, self.jitter)
 
-    def render(self, scene, spp, seed=0, rank=0, world_size=1, lane_slots=0, out=None):
+    def render(self, scene, spp, seed=0, rank=0, world_size=1, lane_slots=0, out=None, flags=0):
         """-> XYZAW film as float32 [H, W, 5] in HOST memory (copies inside the call)."""
-        rp = self.params(spp, seed, rank, world_size, lane_slots)
+        rp = self.params(spp, seed, rank, world_size, lane_slots, flags)
         if out is None:
             out = np.empty((scene.height, scene.width, 5), np.float32)
         st = abi.B2Stats()
@@ -269,11 +269,11 @@ class PathIntegrator:
         self.stats = st.as_dict()
         return out
 
-    def render_reduce(self, scene, spp, reduce, seed=0, rank=0, world_size=1, lane_slots=0, out=None):
+    def render_reduce(self, scene, spp, reduce, seed=0, rank=0, world_size=1, lane_slots=0, out=None, flags=0):
         """Multi-GPU render through the API: `reduce(ptr, n_floats, stream)` sums this rank's DEVICE film into rank 0's
         (e.g. torch.distributed.reduce on a tensor wrapping `ptr`); the film is copied to the host only on rank 0
         (-> [H, W, 5] array there, None elsewhere)."""
-        rp = self.params(spp, seed, rank, world_size, lane_slots)
+        rp = self.params(spp, seed, rank, world_size, lane_slots, flags)
         if out is None and rank == 0:
             out = np.empty((scene.height, scene.width, 5), np.float32)
 

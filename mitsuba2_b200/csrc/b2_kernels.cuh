@@ -606,7 +606,8 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
 // of its rounds on a handful of lanes. Here a warp SUSPENDS its unfinished rays as soon as fewer than
 // q.yield_threshold of its lanes are still traversing: their state (current node, best hit, the live part of the stack)
 // goes to q.tsave, the lane is flagged STW_INFLIGHT and appended to a dense RESUME list, and the next launch of the same
-// lane set continues those rays in full warps of 32 list entries. A suspended lane simply takes part in a later
+// lane set continues those rays in full warps of 32 list entries. (The flag stays set until k_shade hands the lane its next
+// ray: the launch that finishes a suspended ray also scans the lane slots for new rays, and must not take that one again.) A suspended lane simply takes part in a later
 // iteration of the wavefront (it is on neither list until its ray is finished), so nothing else changes: its RNG stream,
 // work item and film pixel stay with the lane, the hit is the same lexicographic (t, -prim) minimum, films stay bit-identical.
 // Unlike the persistent-warp kernel this keeps ordinary short launches, so the other lane set's k_shade still shares the SMs.
@@ -680,7 +681,6 @@ __global__ void __launch_bounds__(256, B2_TRACE_MINBLOCKS) k_trace_resume(DScene
         if (have && !suspended) {
             const Hit &h = tr.best;
             q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
-            if (resumed) q.st[i].w = stw & ~STW_INFLIGHT;
             ++n_seg;
             cont = h.t < B2_INF && STW_DEPTH(stw) < (uint32_t) q.max_depth;
             term = !cont;
@@ -708,7 +708,9 @@ __global__ void __launch_bounds__(256, B2_TRACE_MINBLOCKS) k_trace_resume(DScene
         tr.run<true, SHP, COUNT>(sc, sm, stack, false);
         const bool occluded = tr.any_hit;
         if constexpr (COUNT) { counters[0] += tr.n_nodes; counters[1] += tr.n_tris; }
-        if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
+        // (direct integrator: the entry stays until its lane terminates, which may be launches away when the lane's BSDF-sample
+        //  ray is suspended: maxt = -2 marks it as resolved so that it is traced, and counted, once)
+        if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; q.sh_d[j].w = -2.f; ++n_dsh; }
         else if (!occluded) {
             float4 c = q.sh_c[j];
             const uint32_t lw = __float_as_uint(c.w);
@@ -1165,7 +1167,7 @@ B2_D float3 direct_add_emitter_samples(const Queues &q, uint32_t lane, float3 re
     for (uint32_t i = 0; i < q.direct_e; ++i) {
         const uint32_t j = lane * q.direct_e + i;
         const float4 d4 = q.sh_d[j];
-        if (d4.w >= 0.f) {
+        if (d4.w >= 0.f || d4.w == -2.f) {                                  // (-2: resolved by k_trace_resume)
             const float4 c = q.sh_c[j];
             if (c.w != 0.f) result = result + v3(c);
             q.sh_d[j] = make_float4(0.f, 0.f, 0.f, -1.f);
@@ -1331,7 +1333,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
         q.ray_d[lane] = nrd;
         q.tp[lane] = make_float4(throughput.x, throughput.y, throughput.z, eta);
         q.res[lane] = make_float4(result.x, result.y, result.z, bs_pdf);
-        q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+        q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w & ~STW_INFLIGHT);   // (see k_trace_resume)
         if constexpr (EXT) if (q.smp) q.smp[lane] = sm;
     }
 }
@@ -1420,7 +1422,7 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
                     q.tp[lane] = make_float4(bsdf_val.x, bsdf_val.y, bsdf_val.z, __uint_as_float(b));
                     q.res[lane] = make_float4(result.x, result.y, result.z, bs.pdf);
                     st.w = (st.w & ~STW_DELTA) | (bs.delta ? STW_DELTA : 0u);
-                    q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w);
+                    q.st[lane] = make_uint4((uint32_t) rng, (uint32_t) (rng >> 32), st.z, st.w & ~STW_INFLIGHT);
                     if (q.smp) q.smp[lane] = sm;
                 }
             }
