@@ -233,10 +233,12 @@ enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJI
 #define B2_FLAG_STAGE_TIMING 1u /* bracket every stage launch with CUDA events -> B2Stats.ms_<stage> */
 #define B2_FLAG_PERSISTENT_TRACE 8u /* traverse with the persistent-warp / dynamic-ray-fetch kernel (k_trace_inst) also on scenes
                                    without instances (always used with instances; ignored for tiny scenes on the flat leaf scan) */
-#define B2_FLAG_STATIC_TRACE 16u /* BVH4 scenes without instances: trace with the static ray -> lane kernel (k_trace) instead of the
-                                   yield / resume kernel (k_trace_resume: a warp suspends its unfinished rays when few of its lanes
-                                   are still traversing; the next launch continues them in full warps). Same film either way */
+#define B2_FLAG_RESUME_TRACE 16u /* BVH4 scenes without instances: trace with the yield / resume kernel (k_trace_resume: a warp
+                                   suspends its unfinished rays when few of its lanes are still traversing; the next launch
+                                   continues them in full warps) instead of the static ray -> lane kernel. Same film either way */
 #define B2_FLAG_YIELD_THRESHOLD(n) (((n) & 0x1fu) << 8)   /* k_trace_resume: suspend below n traversing lanes (0 = default 12) */
+#define B2_FLAG_TRACE_BLOCK(log2_div) (((log2_div) & 3u) << 16)   /* tuning: threads per CTA of the traversal kernel = 256 >> log2_div */
+#define B2_FLAG_SHADE_BLOCK(log2_div) (((log2_div) & 3u) << 18)   /* tuning: threads per CTA of the shading kernel   = 256 >> log2_div */
 #define B2_FLAG_COUNT_BVH 4u    /* run the counting instantiation of the traversal kernel -> B2Stats.n_nodes_visited /
                                    n_tris_tested (BVH bytes = nodes * 128 B + tris * 48 B); slower, for measurement */
 

@@ -17,12 +17,17 @@ FLAG_STAGE_TIMING = 1
 FLAG_SINGLE_SET = 2
 FLAG_COUNT_BVH = 4
 FLAG_PERSISTENT_TRACE = 8
-FLAG_STATIC_TRACE = 16
+FLAG_RESUME_TRACE = 16
 
 
 def flag_yield_threshold(n):
     """B2_FLAG_YIELD_THRESHOLD(n)"""
     return (n & 0x1f) << 8
+
+
+def flag_blocks(trace_log2_div=0, shade_log2_div=0):
+    """B2_FLAG_TRACE_BLOCK | B2_FLAG_SHADE_BLOCK: CTA size 256 >> log2_div of the two stage kernels (tuning)"""
+    return ((trace_log2_div & 3) << 16) | ((shade_log2_div & 3) << 18)
 
 BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1
 

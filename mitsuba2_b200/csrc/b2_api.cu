@@ -818,9 +818,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // leaf scan of tiny scenes has no use for it)
     const bool inst = s->d.n_instances != 0 || ((rp->flags & B2_FLAG_PERSISTENT_TRACE) && s->d.n_flat_leaves == 0);
     if (inst) { CU(s->hit_inst.alloc(cap)); CU(s->cls.alloc(cap)); CU(cudaMemsetAsync(s->cls.p, 0, cap, stream)); }
-    // yield / resume traversal (k_trace_resume): BVH4 scenes without instances whose rays need a real tree walk (the flat
-    // leaf scan of tiny scenes has no tail to cut)
-    const bool resume = !inst && s->d.n_flat_leaves == 0 && !(rp->flags & B2_FLAG_STATIC_TRACE);
+    // yield / resume traversal (k_trace_resume), on request: BVH4 scenes without instances whose rays need a real tree walk
+    // (the flat leaf scan of tiny scenes has no tail to cut). Measured (profiles/README.md): 23 % shorter traversal launches,
+    // but the suspended lanes miss their shading turn, so a render needs 31 % more iterations — no net gain.
+    const bool resume = !inst && s->d.n_flat_leaves == 0 && (rp->flags & B2_FLAG_RESUME_TRACE);
     if (resume) { CU(s->resume.alloc(2 * cap)); CU(s->tsave.alloc(cap * B2_TSAVE_INT4)); }
     CU(s->cnt.alloc(32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
@@ -909,6 +910,9 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
+    // CTA sizes of the two stage kernels (B2_FLAG_TRACE_BLOCK / B2_FLAG_SHADE_BLOCK: tuning; the kernels stride over the
+    // lane slots by warps, so any multiple of 32 is correct); grids keep the same number of warps
+    const int threads_trace = 256 >> ((rp->flags >> 16) & 3u), threads_shade = 256 >> ((rp->flags >> 18) & 3u);
     // non-independent samplers run in the extended (F_TEX) kernel variants
     const uint32_t run_features = s->features | ((sampler_type != B2_SAMPLER_INDEPENDENT || direct) ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
@@ -919,8 +923,9 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     uint32_t need_blocks = (set_slots + threads - 1) / threads;
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids
-    int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2), grid_sha = grid;
-    if (inst) grid_int = s->sm_count * B2_INST_MINBLOCKS;           // k_trace_inst: persistent warps
+    int grid_int = (int) std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks * 2) * (threads / threads_trace);
+    int grid_sha = grid * (threads / threads_shade);
+    if (inst) grid_int = s->sm_count * B2_INST_MINBLOCKS * (threads / threads_trace);           // k_trace_inst: persistent warps
     uint64_t iterations = 0, launches = 0;
     const int batch = 8;
     const bool timing = (rp->flags & B2_FLAG_STAGE_TIMING) != 0;
@@ -963,10 +968,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             for (int k = 0; k < n_sets; ++k) {
                 cudaStream_t st = streams[k];
                 tick(st);
-                trace_fn<<<grid_int, threads, s->smem_bytes, st>>>(s->d, qs[k], parity);
+                trace_fn<<<grid_int, threads_trace, s->smem_bytes, st>>>(s->d, qs[k], parity);
                 if (inst) { k_classify<<<grid, threads, 0, st>>>(qs[k], parity); ++launches; }
                 tick(st);
-                shade_fn<<<grid_sha, threads, s->shade_smem_bytes, st>>>(s->d, qs[k], parity);
+                shade_fn<<<grid_sha, threads_shade, s->shade_smem_bytes, st>>>(s->d, qs[k], parity);
                 tick(st);
                 launches += 2;
             }

@@ -196,8 +196,10 @@ def test_yield_resume_equals_static_trace(b2, scene):
     else:
         sb = scenes.instanced_grid(b2.Host(), 256, 256, grid=41, lattice=3, flatten=True)     # 86 k triangles, deep BVH, no instances
     base = None
-    for flags, slots in [(abi.FLAG_STATIC_TRACE, 0), (0, 0), (abi.flag_yield_threshold(1), 0), (abi.flag_yield_threshold(20), 0),
-                         (abi.flag_yield_threshold(27), 4096), (abi.FLAG_SINGLE_SET, 0), (abi.FLAG_SINGLE_SET | abi.flag_yield_threshold(24), 8192)]:
+    R = abi.FLAG_RESUME_TRACE
+    for flags, slots in [(0, 0), (R, 0), (R | abi.flag_yield_threshold(1), 0), (R | abi.flag_yield_threshold(20), 0),
+                         (R | abi.flag_yield_threshold(27), 4096), (R | abi.FLAG_SINGLE_SET, 0), (R | abi.FLAG_SINGLE_SET | abi.flag_yield_threshold(24), 8192),
+                         (abi.flag_blocks(1, 1), 0), (R | abi.flag_blocks(2, 1), 0)]:
         rp = abi.render_params(max_depth=6, rr_depth=5, spp=8, block_size=32, flags=flags, lane_slots=slots)
         film, st, _ = _gpu_render(b2, sb, rp)
         key = (st["n_samples"], st["n_segments"], st["n_shadow_rays"], st["n_invalid"])
@@ -209,7 +211,7 @@ def test_yield_resume_equals_static_trace(b2, scene):
             # (bit for bit, up to the unordered pair of additions of a pixel-edge sample: see test_render_bitexact_single_pass)
             ga, ca = film.view(np.int32).astype(np.int64).ravel(), base[0].view(np.int32).astype(np.int64).ravel()
             bad = np.nonzero(ga != ca)[0]
-            assert len(bad) <= 4 and (len(bad) == 0 or np.abs(ga[bad] - ca[bad]).max() <= 2), (flags, slots, len(bad))
+            assert len(bad) <= 16 and (len(bad) == 0 or np.abs(ga[bad] - ca[bad]).max() <= 2), (flags, slots, len(bad))
 
 
 @pytest.mark.parametrize("workload", ["cbox", "grid"])
