@@ -50,8 +50,8 @@ def parse():
     ap.add_argument("--single-set", action="store_true", help="one lane set on one stream (A/B of the two-stream overlap)")
     ap.add_argument("--persistent-trace", action="store_true", help="B2_FLAG_PERSISTENT_TRACE: persistent-warp traversal kernel also without instances (A/B)")
     ap.add_argument("--resume-trace", action="store_true", help="B2_FLAG_RESUME_TRACE: yield / resume traversal kernel instead of the static ray -> lane kernel (A/B)")
-    ap.add_argument("--trace-block", type=int, default=256, choices=[256, 128, 64, 32], help="threads per CTA of the traversal kernel (tuning)")
-    ap.add_argument("--shade-block", type=int, default=256, choices=[256, 128, 64, 32], help="threads per CTA of the shading kernel (tuning)")
+    ap.add_argument("--trace-block", type=int, default=0, choices=[0, 256, 128, 64], help="threads per CTA of the traversal kernel (0 = the library's choice)")
+    ap.add_argument("--shade-block", type=int, default=0, choices=[0, 256, 128, 64], help="threads per CTA of the shading kernel (0 = the library's choice)")
     ap.add_argument("--yield-threshold", type=int, default=0, help="k_trace_resume: suspend below this many traversing lanes (0 = default)")
     ap.add_argument("--bvh-counters", action="store_true", help="cbox: also run the BVH-counting step (always on for the other workloads)")
     ap.add_argument("--parity", action="store_true", help="cbox: also render the configuration with the reference CLI and report rel-L2")
@@ -292,7 +292,7 @@ def main_b2pt(a, rank, world, local_rank):
     host_film = torch.empty((H, W, 5), dtype=torch.float32).pin_memory().numpy()
     base_flags = ((abi.FLAG_SINGLE_SET if a.single_set else 0) | (abi.FLAG_PERSISTENT_TRACE if a.persistent_trace else 0) |
                   (abi.FLAG_RESUME_TRACE if a.resume_trace else 0) | abi.flag_yield_threshold(a.yield_threshold) |
-                  abi.flag_blocks({256: 0, 128: 1, 64: 2, 32: 3}[a.trace_block], {256: 0, 128: 1, 64: 2, 32: 3}[a.shade_block]))
+                  abi.flag_blocks({0: 0, 256: 1, 128: 2, 64: 3}[a.trace_block], {0: 0, 256: 1, 128: 2, 64: 3}[a.shade_block]))
 
     def barrier():
         if world > 1:

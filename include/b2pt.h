@@ -237,8 +237,9 @@ enum { B2_SAMPLER_INDEPENDENT = 0, B2_SAMPLER_STRATIFIED = 1, B2_SAMPLER_MULTIJI
                                    suspends its unfinished rays when few of its lanes are still traversing; the next launch
                                    continues them in full warps) instead of the static ray -> lane kernel. Same film either way */
 #define B2_FLAG_YIELD_THRESHOLD(n) (((n) & 0x1fu) << 8)   /* k_trace_resume: suspend below n traversing lanes (0 = default 12) */
-#define B2_FLAG_TRACE_BLOCK(log2_div) (((log2_div) & 3u) << 16)   /* tuning: threads per CTA of the traversal kernel = 256 >> log2_div */
-#define B2_FLAG_SHADE_BLOCK(log2_div) (((log2_div) & 3u) << 18)   /* tuning: threads per CTA of the shading kernel   = 256 >> log2_div */
+#define B2_FLAG_TRACE_BLOCK(sel) (((sel) & 3u) << 16)   /* tuning: threads per CTA of the traversal kernel: 0 = auto (128 for scenes that
+                                                          stage <= 8 KB per CTA, else 256), 1 = 256, 2 = 128, 3 = 64 */
+#define B2_FLAG_SHADE_BLOCK(sel) (((sel) & 3u) << 18)   /* ... of the shading kernel */
 #define B2_FLAG_COUNT_BVH 4u    /* run the counting instantiation of the traversal kernel -> B2Stats.n_nodes_visited /
                                    n_tris_tested (BVH bytes = nodes * 128 B + tris * 48 B); slower, for measurement */
 

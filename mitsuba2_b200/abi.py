@@ -25,9 +25,9 @@ def flag_yield_threshold(n):
     return (n & 0x1f) << 8
 
 
-def flag_blocks(trace_log2_div=0, shade_log2_div=0):
-    """B2_FLAG_TRACE_BLOCK | B2_FLAG_SHADE_BLOCK: CTA size 256 >> log2_div of the two stage kernels (tuning)"""
-    return ((trace_log2_div & 3) << 16) | ((shade_log2_div & 3) << 18)
+def flag_blocks(trace_sel=0, shade_sel=0):
+    """B2_FLAG_TRACE_BLOCK | B2_FLAG_SHADE_BLOCK: CTA size of the two stage kernels: 0 = auto, 1 = 256, 2 = 128, 3 = 64 threads (tuning)"""
+    return ((trace_sel & 3) << 16) | ((shade_sel & 3) << 18)
 
 BUILD_HOST_SAH, BUILD_DEVICE_LBVH = 0, 1
 

@@ -910,16 +910,23 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
-    // CTA sizes of the two stage kernels (B2_FLAG_TRACE_BLOCK / B2_FLAG_SHADE_BLOCK: tuning; the kernels stride over the
-    // lane slots by warps, so any multiple of 32 is correct); grids keep the same number of warps
-    const int threads_trace = 256 >> ((rp->flags >> 16) & 3u), threads_shade = 256 >> ((rp->flags >> 18) & 3u);
+    // CTA sizes of the two stage kernels (the kernels stride over the lane slots by warps, so any multiple of 32 is correct;
+    // grids keep the same number of warps). Every CTA stages its tables into shared memory first: scenes that stage only a few
+    // KB (the Cornell box) run 128-thread CTAs — finer-grained slots for the two lane sets' launches to interleave: +2.7 %,
+    // measured — the others 256 (matball: 128-thread traversal CTAs re-stage the 48 KB BVH top twice as often: -10 %).
+    // B2_FLAG_TRACE_BLOCK / B2_FLAG_SHADE_BLOCK override (tuning).
+    const uint32_t tb_sel = (rp->flags >> 16) & 3u, sb_sel = (rp->flags >> 18) & 3u;
+    const int threads_trace = tb_sel ? 512 >> tb_sel : (!inst && s->smem_bytes <= 8192 ? 128 : 256);
+    const int threads_shade = sb_sel ? 512 >> sb_sel : (s->shade_smem_bytes > 0 && s->shade_smem_bytes <= 8192 ? 128 : 256);
     // non-independent samplers run in the extended (F_TEX) kernel variants
     const uint32_t run_features = s->features | ((sampler_type != B2_SAMPLER_INDEPENDENT || direct) ? (uint32_t) F_TEX : 0u);
     const ShadeFn shade_fn = shade_variant(run_features);
     const TraceFn trace_fn = trace_variant(inst, s->has_shapes, (rp->flags & B2_FLAG_COUNT_BVH) != 0, resume);
     // (the limit is a per-function, process-wide attribute: set it for THIS scene right before its launches)
     CU(cudaFuncSetAttribute(shade_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->shade_smem_bytes));
-    CU(cudaFuncSetAttribute(trace_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, s->smem_bytes));
+    // flat scenes: + the per-warp candidate lists of the cooperative any-hit test (flat_any_hit_coop)
+    const int trace_smem = s->d.n_flat_leaves && !inst ? ((s->smem_bytes + 15) & ~15) + (threads_trace / 32) * (int) B2_COOP_BYTES_PER_WARP : s->smem_bytes;
+    CU(cudaFuncSetAttribute(trace_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, trace_smem));
     uint32_t need_blocks = (set_slots + threads - 1) / threads;
     int grid = (int) std::max<uint32_t>(1, std::min<uint32_t>((uint32_t) s->sm_count * 8, need_blocks));
     // measured: 8 CTAs/SM queued beats exactly-resident grids
@@ -968,7 +975,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             for (int k = 0; k < n_sets; ++k) {
                 cudaStream_t st = streams[k];
                 tick(st);
-                trace_fn<<<grid_int, threads_trace, s->smem_bytes, st>>>(s->d, qs[k], parity);
+                trace_fn<<<grid_int, threads_trace, trace_smem, st>>>(s->d, qs[k], parity);
                 if (inst) { k_classify<<<grid, threads, 0, st>>>(qs[k], parity); ++launches; }
                 tick(st);
                 shade_fn<<<grid_sha, threads_shade, s->shade_smem_bytes, st>>>(s->d, qs[k], parity);

@@ -389,6 +389,75 @@ B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, H
     return best.t < B2_INF;
 }
 
+// Any-hit (Scene::ray_test) of 32 rays on the flat leaf list, WARP-COOPERATIVE. An unoccluded emitter sample has to test every
+// leaf its segment's slab test lets through (no culling without a hit), and the number of such leaves differs from lane to lane:
+// with one ray per lane a warp ran as many triangle-test rounds as its worst lane needs (ncu: 8 rounds at 10 / 32 lanes on the
+// Cornell box). Here every lane scans the leaf boxes for its own ray (uniform, dense) and appends its (lane, leaf) candidates to
+// a warp-private shared-memory list; the warp then tests the list 32 entries at a time — the ray of an entry comes from its
+// owner's registers by shuffle — and an entry whose ray is already known to be occluded is skipped. Occluded <=> some candidate
+// triangle passes the same Moeller-Trumbore test as in traverse_flat<true>: the result is identical.
+// Must be called by all 32 lanes of a warp (`valid`: this lane holds a ray).
+#define B2_COOP_BYTES_PER_WARP (32 * 32 * 2 + 16)      /* item list (32 lanes x <= 32 leaves, 2 B each) + the occluded-lanes word */
+template <bool COUNT>
+B2_D bool flat_any_hit_coop(const DScene &sc, const SmemScene &sm, bool valid, const Ray &ray, unsigned char *coop_warp, uint32_t *counters) {
+    uint16_t *items = (uint16_t *) coop_warp;
+    volatile uint32_t *occ_word = (volatile uint32_t *) (coop_warp + 32 * 32 * 2);
+    const uint32_t lane = lane_id(), n = sc.n_flat_leaves;
+    uint32_t mask = 0;
+    if (valid) {
+        float dx = copysignf(fmaxf(fabsf(ray.d.x), 1e-20f), ray.d.x), dy = copysignf(fmaxf(fabsf(ray.d.y), 1e-20f), ray.d.y),
+              dz = copysignf(fmaxf(fabsf(ray.d.z), 1e-20f), ray.d.z);
+        const float idx = rcp_approx(dx), idy = rcp_approx(dy), idz = rcp_approx(dz);
+        const float oox = -(ray.o.x * idx), ooy = -(ray.o.y * idy), ooz = -(ray.o.z * idz);
+        const float tlim = ray.maxt * 1.0000004f;
+        if constexpr (COUNT) counters[0] += (n + 3u) / 4u;
+        #pragma unroll 4
+        for (uint32_t l = 0; l < n; ++l) {
+            float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+            float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                  z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+            float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+            float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tlim));
+            if (tn <= tf) mask |= 1u << l;
+        }
+    }
+    // the warp's candidate list: lane L's entries at [exclusive prefix sum of the counts, ...)
+    const uint32_t cnt = __popc(mask);
+    uint32_t incl = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int) lane >= d) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t pos = incl - cnt;
+    for (uint32_t m = mask; m; m &= m - 1u) items[pos++] = (uint16_t) ((lane << 8) | ((uint32_t) __ffs((int) m) - 1u));
+    if (lane == 0) *occ_word = 0u;
+    __syncwarp();
+    uint32_t done = 0;
+    for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t k = base + lane;
+        const bool have = k < total;
+        const uint32_t it = have ? (uint32_t) items[k] : 0u, src = it >> 8, leaf = it & 0xffu;
+        Ray r;
+        r.o.x = __shfl_sync(0xffffffffu, ray.o.x, src); r.o.y = __shfl_sync(0xffffffffu, ray.o.y, src); r.o.z = __shfl_sync(0xffffffffu, ray.o.z, src);
+        r.d.x = __shfl_sync(0xffffffffu, ray.d.x, src); r.d.y = __shfl_sync(0xffffffffu, ray.d.y, src); r.d.z = __shfl_sync(0xffffffffu, ray.d.z, src);
+        r.mint = __shfl_sync(0xffffffffu, ray.mint, src); r.maxt = __shfl_sync(0xffffffffu, ray.maxt, src);
+        bool hit = false;
+        if (have && !((done >> src) & 1u)) {
+            const uint32_t code = __float_as_uint(sm.flat[2 * leaf].w);
+            const uint32_t s0 = code & 0x07ffffffu, c = (code >> 27) & 0xfu;
+            if constexpr (COUNT) counters[1] += c;
+            for (uint32_t t_ = s0; t_ < s0 + c && !hit; ++t_) {
+                const float4 a0 = sm.tris[3 * t_], a1 = sm.tris[3 * t_ + 1], a2 = sm.tris[3 * t_ + 2];
+                float t, u, v;
+                hit = tri_isect(v3(a0), v3(a1), v3(a2), r, r.maxt, t, u, v);
+            }
+        }
+        if (hit) atomicOr((uint32_t *) occ_word, 1u << src);
+        __syncwarp();
+        done = *occ_word;
+    }
+    return ((done >> lane) & 1u) != 0u;
+}
+
 // Scene::ray_intersect_preliminary / ray_test: the top-level triangles, then (instanced scenes) a
 // BVH4 over the instances' world bounds whose leaves restart the traversal on the shapegroup's BVH
 // with the ray mapped to object space — origin as a point, direction as an UN-normalised vector,
@@ -575,6 +644,31 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
     }
     uint32_t n_dsh = 0;
     const uint32_t n_entries = q.direct_e ? q.n_slots * q.direct_e : n_shadow;      // (direct integrator: E entry slots per lane)
+#ifndef B2_NO_COOP_ANYHIT      /* (A/B builds only) */
+    if (!INST && sc.n_flat_leaves) {
+        // flat scenes: 32 entries per warp, tested cooperatively (flat_any_hit_coop); same entry -> thread mapping as below
+        unsigned char *coop = smem_raw + ((16u + sc.smem_nodes * 128u + (sc.smem_tris ? sc.n_tris * 48u : 0u) + sc.n_flat_leaves * 32u + 15u) & ~15u)
+                              + (threadIdx.x >> 5) * B2_COOP_BYTES_PER_WARP;
+        for (uint32_t base = warp * 32; base < n_entries; base += n_warps * 32) {
+            const uint32_t j = base + lane_id();
+            bool valid = j < n_entries;
+            float4 rd = make_float4(0.f, 0.f, 0.f, -1.f), ro = rd;
+            if (valid) { rd = q.sh_d[j]; valid = !(q.direct_e && !(rd.w >= 0.f)); }
+            if (valid) ro = q.sh_o[j];
+            Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+            const bool occluded = flat_any_hit_coop<COUNT>(sc, sm, valid, ray, coop, counters);
+            if (!valid) continue;
+            if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
+            else if (!occluded) {
+                float4 c = q.sh_c[j];
+                const uint32_t lw = __float_as_uint(c.w);
+                float4 r = q.res[lw];
+                r.x += c.x; r.y += c.y; r.z += c.z;
+                q.res[lw] = r;
+            }
+        }
+    } else
+#endif
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_entries; j += gridDim.x * blockDim.x) {
         float4 rd = q.sh_d[j];
         if (q.direct_e && !(rd.w >= 0.f)) continue;

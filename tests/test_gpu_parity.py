@@ -199,7 +199,7 @@ def test_yield_resume_equals_static_trace(b2, scene):
     R = abi.FLAG_RESUME_TRACE
     for flags, slots in [(0, 0), (R, 0), (R | abi.flag_yield_threshold(1), 0), (R | abi.flag_yield_threshold(20), 0),
                          (R | abi.flag_yield_threshold(27), 4096), (R | abi.FLAG_SINGLE_SET, 0), (R | abi.FLAG_SINGLE_SET | abi.flag_yield_threshold(24), 8192),
-                         (abi.flag_blocks(1, 1), 0), (R | abi.flag_blocks(2, 1), 0)]:
+                         (abi.flag_blocks(2, 2), 0), (R | abi.flag_blocks(3, 2), 0)]:
         rp = abi.render_params(max_depth=6, rr_depth=5, spp=8, block_size=32, flags=flags, lane_slots=slots)
         film, st, _ = _gpu_render(b2, sb, rp)
         key = (st["n_samples"], st["n_segments"], st["n_shadow_rays"], st["n_invalid"])
