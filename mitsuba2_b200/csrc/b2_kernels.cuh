@@ -397,11 +397,12 @@ B2_D bool traverse_flat(const DScene &sc, const SmemScene &sm, const Ray &ray, H
 // owner's registers by shuffle — and an entry whose ray is already known to be occluded is skipped. Occluded <=> some candidate
 // triangle passes the same Moeller-Trumbore test as in traverse_flat<true>: the result is identical.
 // Must be called by all 32 lanes of a warp (`valid`: this lane holds a ray).
-#define B2_COOP_BYTES_PER_WARP (32 * 32 * 2 + 16)      /* item list (32 lanes x <= 32 leaves, 2 B each) + the occluded-lanes word */
+#define B2_COOP_ITEM_BYTES (32 * 32 * 2)                /* candidate list: 32 lanes x <= 32 leaves, 2 B each */
+#define B2_COOP_BYTES_PER_WARP (B2_COOP_ITEM_BYTES + 16 + 32 * 8 + 3 * 32 * 4)   /* + occluded-lanes word, + per-lane (t, ~prim) keys, + (u, v, slot) of the winner */
 template <bool COUNT>
 B2_D bool flat_any_hit_coop(const DScene &sc, const SmemScene &sm, bool valid, const Ray &ray, unsigned char *coop_warp, uint32_t *counters) {
     uint16_t *items = (uint16_t *) coop_warp;
-    volatile uint32_t *occ_word = (volatile uint32_t *) (coop_warp + 32 * 32 * 2);
+    volatile uint32_t *occ_word = (volatile uint32_t *) (coop_warp + B2_COOP_ITEM_BYTES);
     const uint32_t lane = lane_id(), n = sc.n_flat_leaves;
     uint32_t mask = 0;
     if (valid) {
@@ -456,6 +457,120 @@ B2_D bool flat_any_hit_coop(const DScene &sc, const SmemScene &sm, bool valid, c
         done = *occ_word;
     }
     return ((done >> lane) & 1u) != 0u;
+}
+
+// Closest hit (Scene::ray_intersect_preliminary) of 32 rays on the flat leaf list, WARP-COOPERATIVE after the first leaf. Every
+// lane scans the leaf boxes and tests the leaf it enters first (dense: that leaf holds the hit for 93 % of the Cornell box's
+// rays). The leaves a lane still has to look into after that — entered before its hit distance — are few (2.2 per WARP on
+// average) but cost a whole triangle-test round each when every lane walks its own list (ncu: 3 more rounds at 4 / 32 lanes,
+// a quarter of the kernel's instructions). Here they go to the warp's shared-memory candidate list and are tested 32 at a time;
+// a hit competes for its ray through a 64-bit (t, ~prim) key with atomicMin in shared memory — the lexicographic (t, -prim)
+// minimum of DESIGN.md 4, which does not depend on the order of the tests — and the winner leaves (u, v, slot) for the owner.
+// Same triangle test, same tie rule: the result is identical to traverse_flat<false>. Called by all 32 lanes of a warp.
+template <bool COUNT>
+B2_D void flat_closest_hit_coop(const DScene &sc, const SmemScene &sm, bool valid, const Ray &ray, Hit &best, unsigned char *coop_warp, uint32_t *counters) {
+    uint16_t *items = (uint16_t *) coop_warp;
+    unsigned long long *keys = (unsigned long long *) (coop_warp + B2_COOP_ITEM_BYTES + 16);
+    float *pay_u = (float *) (coop_warp + B2_COOP_ITEM_BYTES + 16 + 32 * 8), *pay_v = pay_u + 32;
+    uint32_t *pay_s = (uint32_t *) (pay_v + 32);
+    const uint32_t lane = lane_id(), n = sc.n_flat_leaves;
+    best.t = B2_INF; best.u = 0.f; best.v = 0.f; best.slot = 0xffffffffu; best.prim = 0xffffffffu; best.inst = -1;
+    float tmax = ray.maxt;
+    uint32_t mask = 0, near_l = 0; float near_t = B2_INF;
+    float idx = 0.f, idy = 0.f, idz = 0.f, oox = 0.f, ooy = 0.f, ooz = 0.f;
+    if (valid) {
+        float dx = copysignf(fmaxf(fabsf(ray.d.x), 1e-20f), ray.d.x), dy = copysignf(fmaxf(fabsf(ray.d.y), 1e-20f), ray.d.y),
+              dz = copysignf(fmaxf(fabsf(ray.d.z), 1e-20f), ray.d.z);
+        idx = rcp_approx(dx); idy = rcp_approx(dy); idz = rcp_approx(dz);
+        oox = -(ray.o.x * idx); ooy = -(ray.o.y * idy); ooz = -(ray.o.z * idz);
+        if constexpr (COUNT) counters[0] += (n + 3u) / 4u;
+        const float tlim = tmax * 1.0000004f;
+        #pragma unroll 4
+        for (uint32_t l = 0; l < n; ++l) {
+            float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+            float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                  z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+            float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+            float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), tlim));
+            bool h = tn <= tf;
+            if (h) mask |= 1u << l;
+            if (h && tn < near_t) { near_t = tn; near_l = l; }
+        }
+    }
+    // the leaf entered first (dense)
+    if (mask) {
+        mask &= ~(1u << near_l);
+        const uint32_t code = __float_as_uint(sm.flat[2 * near_l].w);
+        const uint32_t s0 = code & 0x07ffffffu, c = (code >> 27) & 0xfu;
+        if constexpr (COUNT) counters[1] += c;
+        for (uint32_t s = s0; s < s0 + c; ++s) {
+            const float4 a0 = sm.tris[3 * s], a1 = sm.tris[3 * s + 1], a2 = sm.tris[3 * s + 2];
+            float t, u, v;
+            if (tri_isect(v3(a0), v3(a1), v3(a2), ray, tmax, t, u, v)) {
+                const uint32_t prim = __float_as_uint(a0.w);
+                if (t < best.t || (t == best.t && prim > best.prim)) { best.t = t; best.u = u; best.v = v; best.slot = s; best.prim = prim; tmax = t; }
+            }
+        }
+    }
+    // the other leaves: those entered beyond the hit are dropped here (cheap, per lane), the rest go to the warp's list
+    uint32_t keep = mask;
+    if (best.t < B2_INF) {
+        keep = 0;
+        for (uint32_t m = mask; m; m &= m - 1u) {
+            const uint32_t l = (uint32_t) __ffs((int) m) - 1u;
+            float4 lo = sm.flat[2 * l], hi = sm.flat[2 * l + 1];
+            float x0 = b2_fma(lo.x, idx, oox), x1 = b2_fma(hi.x, idx, oox), y0 = b2_fma(lo.y, idy, ooy), y1 = b2_fma(hi.y, idy, ooy),
+                  z0 = b2_fma(lo.z, idz, ooz), z1 = b2_fma(hi.z, idz, ooz);
+            float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), ray.mint));
+            if (!(tn > tmax * 1.0000004f)) keep |= 1u << l;
+        }
+    }
+    const uint32_t cnt = __popc(keep);
+    uint32_t incl = cnt;
+    #pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d); if ((int) lane >= d) incl += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+    if (total == 0u) return;                                   // (warp-uniform)
+    uint32_t pos = incl - cnt;
+    for (uint32_t m = keep; m; m &= m - 1u) items[pos++] = (uint16_t) ((lane << 8) | ((uint32_t) __ffs((int) m) - 1u));
+    const unsigned long long my_key = ((unsigned long long) __float_as_uint(best.t) << 32) | (unsigned long long) (~best.prim);
+    keys[lane] = my_key;                                       // (no hit yet: t = +inf)
+    __syncwarp();
+    for (uint32_t base = 0; base < total; base += 32u) {
+        const uint32_t k = base + lane;
+        const bool have = k < total;
+        const uint32_t it = have ? (uint32_t) items[k] : 0u, src = it >> 8, leaf = it & 0xffu;
+        Ray r;
+        r.o.x = __shfl_sync(0xffffffffu, ray.o.x, src); r.o.y = __shfl_sync(0xffffffffu, ray.o.y, src); r.o.z = __shfl_sync(0xffffffffu, ray.o.z, src);
+        r.d.x = __shfl_sync(0xffffffffu, ray.d.x, src); r.d.y = __shfl_sync(0xffffffffu, ray.d.y, src); r.d.z = __shfl_sync(0xffffffffu, ray.d.z, src);
+        r.mint = __shfl_sync(0xffffffffu, ray.mint, src);
+        const float tm = __shfl_sync(0xffffffffu, tmax, src);
+        bool found = false; float bt = B2_INF, bu = 0.f, bv = 0.f; uint32_t bs = 0, bp = 0;
+        if (have) {
+            const uint32_t code = __float_as_uint(sm.flat[2 * leaf].w);
+            const uint32_t s0 = code & 0x07ffffffu, c = (code >> 27) & 0xfu;
+            if constexpr (COUNT) counters[1] += c;
+            for (uint32_t s = s0; s < s0 + c; ++s) {
+                const float4 a0 = sm.tris[3 * s], a1 = sm.tris[3 * s + 1], a2 = sm.tris[3 * s + 2];
+                float t, u, v;
+                if (tri_isect(v3(a0), v3(a1), v3(a2), r, tm, t, u, v)) {
+                    const uint32_t prim = __float_as_uint(a0.w);
+                    if (!found || t < bt || (t == bt && prim > bp)) { found = true; bt = t; bu = u; bv = v; bs = s; bp = prim; }
+                }
+            }
+        }
+        const unsigned long long key = ((unsigned long long) __float_as_uint(bt) << 32) | (unsigned long long) (~bp);
+        if (found) atomicMin(&keys[src], key);
+        __syncwarp();
+        if (found && *(volatile unsigned long long *) &keys[src] == key) { pay_u[src] = bu; pay_v[src] = bv; pay_s[src] = bs; }
+    }
+    __syncwarp();
+    const unsigned long long kf = *(volatile unsigned long long *) &keys[lane];
+    if (kf != my_key) {
+        best.t = __uint_as_float((uint32_t) (kf >> 32)); best.prim = ~(uint32_t) kf;
+        best.u = *(volatile float *) &pay_u[lane]; best.v = *(volatile float *) &pay_v[lane]; best.slot = *(volatile uint32_t *) &pay_s[lane];
+    }
+    __syncwarp();                                              // (the list is reused by the warp's next chunk)
 }
 
 // Scene::ray_intersect_preliminary / ray_test: the top-level triangles, then (instanced scenes) a
@@ -623,6 +738,32 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
     uint32_t n_seg = 0;
     uint32_t counters[2] = { 0u, 0u };
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+#ifndef B2_NO_COOP_ANYHIT
+    // the warp's candidate list / keys of the cooperative tests on the flat leaf list (behind the staged scene)
+    unsigned char *coop = smem_raw + ((16u + sc.smem_nodes * 128u + (sc.smem_tris ? sc.n_tris * 48u : 0u) + sc.n_flat_leaves * 32u + 15u) & ~15u)
+                          + (threadIdx.x >> 5) * B2_COOP_BYTES_PER_WARP;
+#endif
+#ifndef B2_NO_COOP_CLOSEST      /* (A/B builds only) */
+    if (!INST && sc.n_flat_leaves) {
+        for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
+            const uint32_t i = base + lane_id();
+            bool has = false, cont = false, term = false;
+            float4 rd = make_float4(0.f, 0.f, 0.f, -1.f), ro = rd;
+            uint32_t stw = 0;
+            if (i < q.n_slots) { rd = q.ray_d[i]; has = rd.w >= 0.f; }      // (retired / parked lanes carry maxt < 0)
+            if (has) { ro = q.ray_o[i]; stw = q.st[i].w; }
+            Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
+            Hit h; flat_closest_hit_coop<COUNT>(sc, sm, has, ray, h, coop, counters);
+            if (has) {
+                q.hit[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.slot));
+                ++n_seg;
+                cont = h.t < B2_INF && STW_DEPTH(stw) < (uint32_t) q.max_depth;
+                term = !cont;
+            }
+            list_append(q, parity, i, cont, term, 0xffffffffu);
+        }
+    } else
+#endif
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         const uint32_t i = base + lane_id();
         bool cont = false, term = false;
@@ -647,8 +788,6 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
 #ifndef B2_NO_COOP_ANYHIT      /* (A/B builds only) */
     if (!INST && sc.n_flat_leaves) {
         // flat scenes: 32 entries per warp, tested cooperatively (flat_any_hit_coop); same entry -> thread mapping as below
-        unsigned char *coop = smem_raw + ((16u + sc.smem_nodes * 128u + (sc.smem_tris ? sc.n_tris * 48u : 0u) + sc.n_flat_leaves * 32u + 15u) & ~15u)
-                              + (threadIdx.x >> 5) * B2_COOP_BYTES_PER_WARP;
         for (uint32_t base = warp * 32; base < n_entries; base += n_warps * 32) {
             const uint32_t j = base + lane_id();
             bool valid = j < n_entries;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# session 12: warp-cooperative any-hit on the flat leaf list (flat_any_hit_coop) — parity, A/B against the build without it, ncu
+# session 12/13: warp-cooperative tests on the flat leaf list (flat_any_hit_coop, flat_closest_hit_coop) — parity, A/B against the build without the closest-hit part, ncu
 out=gpurun_out; mkdir -p $out; tag=${1:-s12}
 timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "bitexact or atomics or lane_slots or stage or errors or rank_without" > $out/${tag}_pytest.log 2>&1; echo "pytest exit $?" >> $out/${tag}_pytest.log
 grep -E "passed|failed|exit|^E  |Error|^FAILED" $out/${tag}_pytest.log | cut -c1-300 | tail -12
@@ -15,12 +15,13 @@ except Exception as e:
 PY
 }
 run() { local name=$1 lib=$2; shift 2; B2PT_LIB=$lib timeout 600 python bench.py --cpu-baseline 0 --steps 3 --warmup 3 "$@" > $out/${tag}_bench_$name.json 2> $out/${tag}_bench_$name.err; show $out/${tag}_bench_$name.json $name; }
-CUR=$PWD/mitsuba2_b200/libb2pt.so; OLD=$PWD/build_variants/libb2pt_nocoop.so
+CUR=$PWD/mitsuba2_b200/libb2pt.so; OLD=$PWD/build_variants/libb2pt_noclosest.so
 run cbox_coop $CUR
 run cbox_nocoop $OLD
 run cbox_coop2 $CUR
 run cbox_nocoop2 $OLD
 run cbox_coop_256 $CUR --trace-block 256 --shade-block 256
+run cbox_coop_t64 $CUR --trace-block 64
 NCU="ncu --set full --clock-control none --import-source on"
 prof() { local name=$1 k=$2 skip=$3; shift 3
   timeout 600 $NCU -k regex:$k -s $skip -c 1 -o /tmp/${name} -f "$@" > $out/${tag}_ncu_${name}.log 2>&1
