@@ -1380,6 +1380,9 @@ B2_D Tables stage_shade_tables(const DScene &sc, unsigned char *smem_raw) {
 #ifndef B2_SHADE_MINBLOCKS
 #define B2_SHADE_MINBLOCKS 3
 #endif
+#ifndef B2_SHADE_THREADS
+#define B2_SHADE_THREADS 256        /* largest CTA k_shade may be launched with (b2_api.cu picks 128 or 256 per scene) */
+#endif
 
 // DirectIntegrator (direct.cpp:167-176): BSDF samples b, b + 1, ... of the camera hit until one has a non-zero value (its ray is
 // traced next) or the B samples are spent. `si` / `bsdf` / `flip` as bsdf_side() left them.
@@ -1687,7 +1690,7 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
 }
 
 template <uint32_t F>
-__global__ void __launch_bounds__(256, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
+__global__ void __launch_bounds__(B2_SHADE_THREADS, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const Tables tb = stage_shade_tables(sc, smem_raw);
