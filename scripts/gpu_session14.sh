@@ -27,4 +27,10 @@ run matball_72_s128 $V $MB --shade-block 128
 run veach_80 $CUR $VE
 run veach_80_s128 $CUR $VE --shade-block 128
 run veach_72_s128 $V $VE --shade-block 128
+NCU="ncu --set full --clock-control none --import-source on"
+prof() { local name=$1 k=$2 skip=$3; shift 3
+  timeout 600 $NCU -k regex:$k -s $skip -c 1 -o /tmp/${name} -f "$@" > $out/${tag}_ncu_${name}.log 2>&1
+  ncu -i /tmp/${name}.ncu-rep --page raw --csv > $out/${tag}_ncu_${name}_raw.csv 2>/dev/null
+  ncu -i /tmp/${name}.ncu-rep --page source --csv > $out/${tag}_ncu_${name}_src.csv 2>/dev/null; rm -f /tmp/${name}.ncu-rep; }
+prof cbox_shade 'k_shade' 60 python scripts/render_once.py --workload cbox --spp 16
 du -sh $out
