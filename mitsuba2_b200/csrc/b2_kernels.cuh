@@ -66,6 +66,7 @@ struct Queues {
     uint32_t *resume[2];
     int4 *tsave;
     uint32_t yield_threshold;   // a warp suspends its unfinished rays when fewer lanes than this are still traversing
+    uint32_t zero;              // always 0 (atom_add_u32: keeps ptxas from proving an atomic's address warp-uniform)
 };
 
 // q.cnt words of one lane set (B2_CNT_WORDS each)
@@ -88,6 +89,22 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES 
 #define STW_LEFT(w)      ((w) >> 16)
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
+
+// atomicAdd whose RESULT may be consumed much later. For an atomic add on an address it can prove warp-uniform, ptxas emits its
+// own warp-aggregated form — leader ATOMG followed at once by a SHFL of the result — which stalls the warp on the atomic's L2
+// round trip right there (ncu: 22 % of k_shade's stall samples on that SHFL although the source uses the value a few hundred
+// instructions later; inline PTX does not help, the transformation is ptxas's). `zero` is a kernel parameter that is always 0:
+// (per-thread value) & zero makes the address formally per-thread, the instruction is issued as written, and the scoreboard only waits at
+// the first real use of the result. Call it from ONE lane (the callers aggregate by ballot themselves).
+B2_D uint32_t atom_add_u32(uint32_t *p, uint32_t v, uint32_t zero /* = salt & q.zero, salt any per-thread value */) {
+#ifdef B2_NO_ASYNC_ATOM        /* (A/B builds only) */
+    return atomicAdd(p, v);
+#else
+    uint32_t old;
+    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p + zero), "r"(v) : "memory");
+    return old;
+#endif
+}
 
 // warp-aggregated append: one atomic per warp, contiguous slots for the set lanes.
 // Must be called by all 32 lanes of the warp.
@@ -1530,7 +1547,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     // here and its result is only consumed after phase 2 (latency hidden). ----
     const uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
     uint32_t sq_base = 0;
-    if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask));
+    if (lane_id() == 0 && sh_mask) sq_base = atom_add_u32(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask), st.x & q.zero);
     // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
     if (valid && !park && !direct_mode) {
         const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
@@ -1591,7 +1608,9 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
     // the work-item fetch is issued first: its latency hides behind the emitter evaluation and the film put
     // (direct integrator: only once it is known that the lane finishes its sample)
     uint32_t w = 0;
-    if (!direct) w = warp_append(q.work, valid && left == 0);
+    const uint32_t fetch_mask = direct ? 0u : __ballot_sync(0xffffffffu, valid && left == 0);
+    uint32_t fetch_base = 0;
+    if (lane_id() == 0 && fetch_mask) fetch_base = atom_add_u32(q.work, __popc(fetch_mask), st.x & q.zero);
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
@@ -1665,6 +1684,7 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
         }
     }
     if (direct) w = warp_append(q.work, finishing && left == 0);
+    else w = __shfl_sync(0xffffffffu, fetch_base, 0) + __popc(fetch_mask & ((1u << lane_id()) - 1u));
     // ---- K6: ImageBlock::put ----
     if (finishing) {
         float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
@@ -1693,9 +1713,10 @@ template <uint32_t F>
 __global__ void __launch_bounds__(B2_SHADE_THREADS, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade): the counts are loaded first so
+    // that their L2 round trip overlaps the staging of the tables
+    const unsigned long long n_list = *(const volatile unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
     const Tables tb = stage_shade_tables(sc, smem_raw);
-    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
-    const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         q.cnt[CNT_FETCH] = 0;                                             // ray counter of the next k_trace_inst
         if (q.tsave) q.cnt[CNT_RESUME + (parity ^ 1)] = 0;                // consumed by the k_trace_resume before this launch
