@@ -116,6 +116,7 @@ struct B2Scene {
     DBuf<float2> pos;
     DBuf<uint32_t> pixel, list, cnt, item_pixel, item_seed;
     DBuf<uint8_t> cls;
+    DBuf<uint32_t> sh_cnt;                                                // counters of the shadow sub-queues (sh_counter())
     DBuf<uint32_t> resume; DBuf<int4> tsave;                              // k_trace_resume: suspended lanes + their traversal state
     DBuf<float4> prim_o, prim_d, prim_hit; DBuf<int32_t> prim_inst;      // DirectIntegrator: the camera segment per lane
     DBuf<unsigned long long> stats;
@@ -808,7 +809,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     const uint32_t dE = rp->direct_emitter_samples, dB = rp->direct_bsdf_samples;
     const bool direct = (dE | dB) != 0;
     if (direct && (dE > 64 || dB > 64)) return fail(B2_ERR_INVALID, "direct integrator: at most 64 emitter / BSDF samples");
-    const size_t sh_cap = cap * (size_t) std::max<uint32_t>(dE, 1u);
+    const size_t sh_cap = cap * (size_t) std::max<uint32_t>(dE, 1u) + 2u * B2_SH_MAXSUB * 32u;    // (+ the rounding of the sub-queues)
     CU(s->ray_o.alloc(cap)); CU(s->ray_d.alloc(cap)); CU(s->hit.alloc(cap)); CU(s->tp.alloc(cap)); CU(s->res.alloc(cap));
     CU(s->sh_o.alloc(sh_cap)); CU(s->sh_d.alloc(sh_cap)); CU(s->sh_c.alloc(sh_cap));
     if (direct) { CU(s->prim_o.alloc(cap)); CU(s->prim_d.alloc(cap)); CU(s->prim_hit.alloc(cap)); CU(s->prim_inst.alloc(cap)); }
@@ -824,6 +825,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     const bool resume = !inst && s->d.n_flat_leaves == 0 && (rp->flags & B2_FLAG_RESUME_TRACE);
     if (resume) { CU(s->resume.alloc(2 * cap)); CU(s->tsave.alloc(cap * B2_TSAVE_INT4)); }
     CU(s->cnt.alloc(32));
+    CU(s->sh_cnt.alloc(2 * 2 * B2_SH_MAXSUB * 32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
     // up and warns; here it is an error so that spp keeps its meaning)
@@ -879,8 +881,18 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             const uint32_t thr = (rp->flags >> 8) & 0x1fu;                // B2_FLAG_YIELD_THRESHOLD(n): tuning override
             q.yield_threshold = thr ? thr : 12u;
         }
-        const size_t so = o * (size_t) std::max<uint32_t>(dE, 1u);
+        // the shadow queue of a lane set: 8 sub-queues with their own counters (one 128-byte line each) once the wavefront is
+        // wide enough for the single counter to be a hot spot (b2_kernels.cuh: sh_counter()); the direct integrator's entries
+        // are addressed by lane
+#ifdef B2_NO_SH_SUB             /* (A/B builds only) */
+        const uint32_t sh_sub = 0u;
+#else
+        const uint32_t sh_sub = (!direct && set_slots >= 8192u) ? 8u : 0u;
+#endif
+        const size_t so = direct ? o * (size_t) dE : o + (size_t) k * B2_SH_MAXSUB * 32u;
         q.sh_o = s->sh_o.p + so; q.sh_d = s->sh_d.p + so; q.sh_c = s->sh_c.p + so;
+        q.sh_sub = sh_sub; q.sh_cnt = s->sh_cnt.p + (size_t) k * 2 * B2_SH_MAXSUB * 32;
+        q.sh_cap = sh_sub ? ((((set_slots + 31u) / 32u) + sh_sub - 1u) / sh_sub) * 32u : 0u;
         if (direct) {
             q.direct_e = dE; q.direct_b = dB;
             const float sum = (float) (dE + dB);                         // direct.cpp:96-100
@@ -908,6 +920,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     if (wide) CU(cudaMemsetAsync(s->film_wide.p, 0, (size_t) W * H * 8 * sizeof(float), stream));
     CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(s->sh_cnt.p, 0, 2 * 2 * B2_SH_MAXSUB * 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
     // CTA sizes of the two stage kernels (the kernels stride over the lane slots by warps, so any multiple of 32 is correct;

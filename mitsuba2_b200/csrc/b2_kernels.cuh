@@ -66,7 +66,11 @@ struct Queues {
     uint32_t *resume[2];
     int4 *tsave;
     uint32_t yield_threshold;   // a warp suspends its unfinished rays when fewer lanes than this are still traversing
-    uint32_t zero;              // always 0 (atom_add_u32: keeps ptxas from proving an atomic's address warp-uniform)
+    // shadow queue split into sh_sub sub-queues (power of two <= B2_SH_MAXSUB; 0: one queue counted by cnt[CNT_SHADOW + parity]):
+    // sub-queue k holds the entries [k * sh_cap, k * sh_cap + count_k), its counter of iteration parity p is
+    // sh_cnt[(p * B2_SH_MAXSUB + k) * 32] — one 128-byte line per counter (see sh_counter())
+    uint32_t *sh_cnt;
+    uint32_t sh_sub, sh_cap;
 };
 
 // q.cnt words of one lane set (B2_CNT_WORDS each)
@@ -90,22 +94,6 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES 
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
 
-// atomicAdd whose RESULT may be consumed much later. For an atomic add on an address it can prove warp-uniform, ptxas emits its
-// own warp-aggregated form — leader ATOMG followed at once by a SHFL of the result — which stalls the warp on the atomic's L2
-// round trip right there (ncu: 22 % of k_shade's stall samples on that SHFL although the source uses the value a few hundred
-// instructions later; inline PTX does not help, the transformation is ptxas's). `zero` is a kernel parameter that is always 0:
-// (per-thread value) & zero makes the address formally per-thread, the instruction is issued as written, and the scoreboard only waits at
-// the first real use of the result. Call it from ONE lane (the callers aggregate by ballot themselves).
-B2_D uint32_t atom_add_u32(uint32_t *p, uint32_t v, uint32_t zero /* = salt & q.zero, salt any per-thread value */) {
-#ifdef B2_NO_ASYNC_ATOM        /* (A/B builds only) */
-    return atomicAdd(p, v);
-#else
-    uint32_t old;
-    asm volatile("atom.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p + zero), "r"(v) : "memory");
-    return old;
-#endif
-}
-
 // warp-aggregated append: one atomic per warp, contiguous slots for the set lanes.
 // Must be called by all 32 lanes of the warp.
 B2_D uint32_t warp_append(uint32_t *counter, bool pred) {
@@ -114,6 +102,40 @@ B2_D uint32_t warp_append(uint32_t *counter, bool pred) {
     if (lane_id() == 0 && mask) base = atomicAdd(counter, __popc(mask));
     base = __shfl_sync(0xffffffffu, base, 0);
     return base + __popc(mask & ((1u << lane_id()) - 1u));
+}
+
+// ---- the shadow queue's counters --------------------------------------------------------------------
+// Every CONTINUE warp of k_shade reserves its emitter samples' slots with one atomic. On ONE counter those are ~11 000
+// same-address atomics per launch, issued in bursts (the warps of a wave reach that point together): ncu shows 22 % of
+// k_shade's stall samples on the first use of the atomic's result, ten times the wait k_trace sees on its (evenly spread) list
+// atomics. The queue is therefore split into sh_sub sub-queues, chunk c appends to sub-queue c % sh_sub, and every counter
+// sits in its own 128-byte line (adjacent words share an L2 sector and serialise just the same). Consumers see ONE dense
+// index space: sh_total() entries, dense index j -> storage slot sh_index(j).
+#define B2_SH_MAXSUB 16
+B2_D uint32_t *sh_counter(const Queues &q, int parity, uint32_t k) {
+    return q.sh_sub ? q.sh_cnt + ((uint32_t) parity * B2_SH_MAXSUB + k) * 32u : q.cnt + CNT_SHADOW + parity;
+}
+B2_D uint32_t sh_total(const Queues &q, int parity) {
+    if (!q.sh_sub) return q.cnt[CNT_SHADOW + parity];
+    uint32_t n = 0;
+    for (uint32_t k = 0; k < q.sh_sub; ++k) n += *sh_counter(q, parity, k);
+    return n;
+}
+B2_D uint32_t sh_index(const Queues &q, int parity, uint32_t j) {
+    if (!q.sh_sub) return j;
+    uint32_t k = 0;
+    for (; k + 1u < q.sh_sub; ++k) { const uint32_t c = *sh_counter(q, parity, k); if (j < c) break; j -= c; }
+    return k * q.sh_cap + j;
+}
+// k_trace*: block 0 resets the counters the next k_shade appends to and books the entries consumed by this launch
+B2_D void sh_begin_trace(const Queues &q, int parity, uint32_t n_shadow) {
+    if (blockIdx.x != 0) return;
+    if (q.sh_sub) { if (threadIdx.x < q.sh_sub) *sh_counter(q, parity, threadIdx.x) = 0; }
+    else if (threadIdx.x == 0) q.cnt[CNT_SHADOW + parity] = 0;
+    if (threadIdx.x == 0) {
+        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;   // consumed by the previous k_shade
+        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+    }
 }
 
 // ---- TMA (1-D bulk copy) staging of the BVH top + triangles into shared memory -----------------
@@ -746,12 +768,8 @@ template <bool INST, bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];         // filled by the previous k_shade
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.cnt[CNT_SHADOW + parity] = 0;                                  // the next k_shade appends there
-        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;   // consumed by the previous k_shade
-        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
-    }
+    const uint32_t n_shadow = sh_total(q, parity ^ 1);                    // filled by the previous k_shade
+    sh_begin_trace(q, parity, n_shadow);
     uint32_t n_seg = 0;
     uint32_t counters[2] = { 0u, 0u };
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -806,8 +824,9 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
     if (!INST && sc.n_flat_leaves) {
         // flat scenes: 32 entries per warp, tested cooperatively (flat_any_hit_coop); same entry -> thread mapping as below
         for (uint32_t base = warp * 32; base < n_entries; base += n_warps * 32) {
-            const uint32_t j = base + lane_id();
+            uint32_t j = base + lane_id();
             bool valid = j < n_entries;
+            if (valid && !q.direct_e) j = sh_index(q, parity ^ 1, j);
             float4 rd = make_float4(0.f, 0.f, 0.f, -1.f), ro = rd;
             if (valid) { rd = q.sh_d[j]; valid = !(q.direct_e && !(rd.w >= 0.f)); }
             if (valid) ro = q.sh_o[j];
@@ -825,7 +844,8 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
         }
     } else
 #endif
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_entries; j += gridDim.x * blockDim.x) {
+    for (uint32_t jd = blockIdx.x * blockDim.x + threadIdx.x; jd < n_entries; jd += gridDim.x * blockDim.x) {
+        const uint32_t j = q.direct_e ? jd : sh_index(q, parity ^ 1, jd);
         float4 rd = q.sh_d[j];
         if (q.direct_e && !(rd.w >= 0.f)) continue;
         float4 ro = q.sh_o[j];
@@ -869,13 +889,9 @@ template <bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, B2_TRACE_MINBLOCKS) k_trace_resume(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];         // filled by the previous k_shade
+    const uint32_t n_shadow = sh_total(q, parity ^ 1);                    // filled by the previous k_shade
     const uint32_t n_res = q.cnt[CNT_RESUME + (parity ^ 1)];            // suspended by the previous launch (zeroed by the next k_shade)
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.cnt[CNT_SHADOW + parity] = 0;
-        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;
-        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
-    }
+    sh_begin_trace(q, parity, n_shadow);
     uint32_t n_seg = 0;
     uint32_t counters[2] = { 0u, 0u };
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -949,7 +965,8 @@ __global__ void __launch_bounds__(256, B2_TRACE_MINBLOCKS) k_trace_resume(DScene
     }
     uint32_t n_dsh = 0;
     const uint32_t n_entries = q.direct_e ? q.n_slots * q.direct_e : n_shadow;      // (direct integrator: E entry slots per lane)
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_entries; j += gridDim.x * blockDim.x) {
+    for (uint32_t jd = blockIdx.x * blockDim.x + threadIdx.x; jd < n_entries; jd += gridDim.x * blockDim.x) {
+        const uint32_t j = q.direct_e ? jd : sh_index(q, parity ^ 1, jd);
         float4 rd = q.sh_d[j];
         if (q.direct_e && !(rd.w >= 0.f)) continue;
         float4 ro = q.sh_o[j];
@@ -1000,13 +1017,11 @@ template <bool SHP, bool COUNT>
 __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SmemScene sm = stage_scene(sc, smem_raw);
-    const uint32_t n_shadow = q.cnt[CNT_SHADOW + (parity ^ 1)];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        q.cnt[CNT_SHADOW + parity] = 0;
-        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;
-        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
-    }
+    const uint32_t n_shadow = sh_total(q, parity ^ 1);
+    sh_begin_trace(q, parity, n_shadow);
     const uint32_t total = q.n_slots + (q.direct_e ? q.n_slots * q.direct_e : n_shadow);
+    // storage slot of the shadow entry behind work item `it` (>= n_slots)
+    auto sh_slot = [&](uint32_t it) -> uint32_t { return q.direct_e ? it - q.n_slots : sh_index(q, parity ^ 1, it - q.n_slots); };
     uint32_t n_seg = 0, n_dsh = 0;
     int2 stk[B2_INST_STACK];          // (node / leaf code, entry distance bits): one 8-byte local-memory access per push / pop
     Trav tr; tr.cur = B2_TRAV_DONE; tr.sp = 0; tr.inst = -1; tr.any_hit = false; tr.tmax = 0.f; tr.n_nodes = 0; tr.n_tris = 0;
@@ -1024,7 +1039,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                 if (i < total) {
                     float4 ro, rd;
                     if (i < q.n_slots) { rd = q.ray_d[i]; ro = q.ray_o[i]; }
-                    else { rd = q.sh_d[i - q.n_slots]; ro = q.sh_o[i - q.n_slots]; }
+                    else { const uint32_t sj = sh_slot(i); rd = q.sh_d[sj]; ro = q.sh_o[sj]; }
                     if (rd.w >= 0.f) {                                   // (retired lanes carry maxt < 0)
                         item = i; busy = true;
                         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
@@ -1126,7 +1141,7 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                         // back to world space: the ray is re-read from the queue
                         float4 ro, rd;
                         if (!any_ray) { rd = q.ray_d[item]; ro = q.ray_o[item]; }
-                        else { rd = q.sh_d[item - q.n_slots]; ro = q.sh_o[item - q.n_slots]; }
+                        else { const uint32_t sj = sh_slot(item); rd = q.sh_d[sj]; ro = q.sh_o[sj]; }
                         Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
                         tr.set_ray(ray);
                         tr.inst = -1;
@@ -1146,9 +1161,9 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
                     q.cls[item] = (h.t < B2_INF && STW_DEPTH(q.st[item].w) < (uint32_t) q.max_depth) ? 1 : 2;
                     ++n_seg;
                 } else if (q.direct_e) {
-                    q.sh_c[item - q.n_slots].w = tr.any_hit ? 0.f : 1.f; ++n_dsh;
+                    q.sh_c[sh_slot(item)].w = tr.any_hit ? 0.f : 1.f; ++n_dsh;
                 } else if (!tr.any_hit) {
-                    const uint32_t j = item - q.n_slots;
+                    const uint32_t j = sh_slot(item);
                     float4 c = q.sh_c[j];
                     const uint32_t lw = __float_as_uint(c.w);
                     float4 r = q.res[lw];
@@ -1431,7 +1446,7 @@ B2_D float3 direct_add_emitter_samples(const Queues &q, uint32_t lane, float3 re
 
 // 32 CONTINUE lanes: one iteration of PathIntegrator::sample's loop body (path.cpp:124-208). Called by whole warps.
 template <uint32_t F>
-B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane) {
+B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, int parity, bool valid, uint32_t lane, uint32_t chunk) {
     constexpr bool EXT = (F & F_TEX) != 0;
     // all queue loads are issued up front (one round trip)
     const uint32_t ld = lane;        // (callers pass slot 0 for the padding lanes of the last warp)
@@ -1547,7 +1562,8 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     // here and its result is only consumed after phase 2 (latency hidden). ----
     const uint32_t sh_mask = __ballot_sync(0xffffffffu, shadow);
     uint32_t sq_base = 0;
-    if (lane_id() == 0 && sh_mask) sq_base = atom_add_u32(&q.cnt[CNT_SHADOW + parity], __popc(sh_mask), st.x & q.zero);
+    const uint32_t sh_k = q.sh_sub ? chunk & (q.sh_sub - 1u) : 0u;           // this chunk's sub-queue (see sh_counter())
+    if (lane_id() == 0 && sh_mask) sq_base = atomicAdd(sh_counter(q, parity, sh_k), __popc(sh_mask));
     // ---- phase 2: BSDF sampling (the reference (g++) draws next_2d BEFORE next_1d, path.cpp:177-178) ----
     if (valid && !park && !direct_mode) {
         const B2Bsdf &bsdf = tb.bsdfs[si.bsdf];
@@ -1577,7 +1593,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
         if (park) q.list[parity ^ 1][q.n_slots - 1u - ((uint32_t) (pb >> 32) + __popc(pk_mask & ((1u << lane_id()) - 1u)))] = lane;
     }
     if (sh_mask) {
-        const uint32_t sq = __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
+        const uint32_t sq = sh_k * q.sh_cap + __shfl_sync(0xffffffffu, sq_base, 0) + __popc(sh_mask & ((1u << lane_id()) - 1u));
         if (shadow) { q.sh_o[sq] = sho; q.sh_d[sq] = shd; q.sh_c[sq] = shc; }
     }
     if (valid) {
@@ -1608,9 +1624,7 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
     // the work-item fetch is issued first: its latency hides behind the emitter evaluation and the film put
     // (direct integrator: only once it is known that the lane finishes its sample)
     uint32_t w = 0;
-    const uint32_t fetch_mask = direct ? 0u : __ballot_sync(0xffffffffu, valid && left == 0);
-    uint32_t fetch_base = 0;
-    if (lane_id() == 0 && fetch_mask) fetch_base = atom_add_u32(q.work, __popc(fetch_mask), st.x & q.zero);
+    if (!direct) w = warp_append(q.work, valid && left == 0);
     uint64_t rng = (uint64_t) st.x | ((uint64_t) st.y << 32);
     uint2 sm = make_uint2(0u, 0u);
     if constexpr (EXT) if (q.smp) sm = q.smp[ld];
@@ -1684,7 +1698,6 @@ B2_D void shade_terminate(const DScene &sc, const Tables &tb, const Queues &q, b
         }
     }
     if (direct) w = warp_append(q.work, finishing && left == 0);
-    else w = __shfl_sync(0xffffffffu, fetch_base, 0) + __popc(fetch_mask & ((1u << lane_id()) - 1u));
     // ---- K6: ImageBlock::put ----
     if (finishing) {
         float2 pos = q.pos ? q.pos[lane] : make_float2(0.f, 0.f);
@@ -1713,10 +1726,9 @@ template <uint32_t F>
 __global__ void __launch_bounds__(B2_SHADE_THREADS, B2_SHADE_MINBLOCKS) k_shade(DScene sc, Queues q, int parity) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade): the counts are loaded first so
-    // that their L2 round trip overlaps the staging of the tables
-    const unsigned long long n_list = *(const volatile unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
     const Tables tb = stage_shade_tables(sc, smem_raw);
+    // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
+    const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         q.cnt[CNT_FETCH] = 0;                                             // ray counter of the next k_trace_inst
         if (q.tsave) q.cnt[CNT_RESUME + (parity ^ 1)] = 0;                // consumed by the k_trace_resume before this launch
@@ -1733,7 +1745,7 @@ __global__ void __launch_bounds__(B2_SHADE_THREADS, B2_SHADE_MINBLOCKS) k_shade(
     for (uint32_t wi = warp; wi < wc + wt; wi += n_warps) {
         bool valid;
         const uint32_t slot = list_entry(wi, valid);
-        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot);
+        if (wi < wc) shade_continue<F>(sc, tb, q, parity, valid, slot, wi);
         else shade_terminate<F>(sc, tb, q, valid, slot, n_put, n_bad);
     }
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
