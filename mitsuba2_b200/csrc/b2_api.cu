@@ -824,7 +824,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     // but the suspended lanes miss their shading turn, so a render needs 31 % more iterations — no net gain.
     const bool resume = !inst && s->d.n_flat_leaves == 0 && (rp->flags & B2_FLAG_RESUME_TRACE);
     if (resume) { CU(s->resume.alloc(2 * cap)); CU(s->tsave.alloc(cap * B2_TSAVE_INT4)); }
-    CU(s->cnt.alloc(32));
+    CU(s->cnt.alloc(B2_CNT_TOTAL));
     CU(s->sh_cnt.alloc(2 * 2 * B2_SH_MAXSUB * 32));
     if (wide) CU(s->film_wide.alloc((size_t) W * H * 8));
     // samplers (B2RenderParams.sampler): the stratified sampler needs a square sample count (stratified.cpp:63-72 rounds it
@@ -856,7 +856,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         } else return fail(B2_ERR_INVALID, "unsupported sampler %u", sampler_type);
         CU(s->smp.alloc(cap));
     }
-    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * 32 * sizeof(uint32_t)));
+    if (!s->h_cnt) CU(cudaMallocHost(&s->h_cnt, 2 * B2_CNT_TOTAL * sizeof(uint32_t)));
 
     // The lane slots are split into two independent lane SETS, each with its own counters, lists and shadow
     // queue, driven on its own stream: while one set is in its (issue-bound) traversal launch the
@@ -866,7 +866,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     const int n_sets = (slots >= 2 * 65536 && !(rp->flags & (B2_FLAG_SINGLE_SET | B2_FLAG_STAGE_TIMING))) ? 2 : 1;
     const uint32_t set_slots = ((slots / n_sets) + 31u) & ~31u;
     if (n_sets > 1) slots = set_slots * n_sets;     // (allocations above were sized with the rounded-up count)
-    const int WORK_WORD = 2 * B2_CNT_WORDS;
+    const int WORK_WORD = B2_CNT_WORK;
     Queues qs[2];
     for (int k = 0; k < n_sets; ++k) {
         Queues &q = qs[k];
@@ -919,7 +919,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaEventRecord(ev0, stream));
     CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
     if (wide) CU(cudaMemsetAsync(s->film_wide.p, 0, (size_t) W * H * 8 * sizeof(float), stream));
-    CU(cudaMemsetAsync(s->cnt.p, 0, 32 * sizeof(uint32_t), stream));
+    CU(cudaMemsetAsync(s->cnt.p, 0, B2_CNT_TOTAL * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->sh_cnt.p, 0, 2 * 2 * B2_SH_MAXSUB * 32 * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
     const int threads = 256;
@@ -999,7 +999,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             ++iterations;
         }
         if (n_sets > 1) { CU(cudaEventRecord(evx, streams[1])); CU(cudaStreamWaitEvent(stream, evx, 0)); }
-        CU(cudaMemcpyAsync(s->h_cnt + 32 * slot, s->cnt.p, 32 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CU(cudaMemcpyAsync(s->h_cnt + B2_CNT_TOTAL * slot, s->cnt.p, B2_CNT_TOTAL * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CU(cudaEventRecord(evb[slot], stream));
         if (n_sets > 1) CU(cudaStreamWaitEvent(streams[1], evb[slot], 0));     // keep the streams within one batch of each other
         pending[slot] = 1;
@@ -1008,7 +1008,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (pending[prev]) {
             CU(cudaEventSynchronize(evb[prev]));
             pending[prev] = 0;
-            const uint32_t *c = s->h_cnt + 32 * prev;
+            const uint32_t *c = s->h_cnt + B2_CNT_TOTAL * prev;
             // finished when every lane retired (parked lanes count as alive) and no emitter sample is unresolved
             bool all = true;
             for (int k = 0; k < n_sets; ++k)
@@ -1215,18 +1215,18 @@ int b2_stage_shade(B2Scene *s, const B2RenderParams *rp, uint32_t n, float *ray_
     DBuf<float4> o, d, h, tp, res, so, sd, sc4; DBuf<uint4> st; DBuf<uint32_t> list, cnt, df, pix; DBuf<int32_t> di; DBuf<uint64_t> rng;
     DBuf<unsigned long long> stats; DBuf<float2> pos;
     CU(o.alloc(cap)); CU(d.alloc(cap)); CU(h.alloc(cap)); CU(tp.alloc(cap)); CU(res.alloc(cap)); CU(so.alloc(cap)); CU(sd.alloc(cap)); CU(sc4.alloc(cap));
-    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(32)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(8)); CU(pos.alloc(cap));
+    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(B2_CNT_TOTAL)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(8)); CU(pos.alloc(cap));
     H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16); H2D(h.p, hit, N * 16); H2D(tp.p, throughput_eta, N * 16); H2D(res.p, result_pdf, N * 16);
     H2D(rng.p, rng_state, N * 8); H2D(df.p, depth_flags, N * 4);
     if (s->d.n_instances) { CU(di.alloc(cap)); H2D(di.p, inst, N * 4); }
-    CU(cudaMemsetAsync(cnt.p, 0, 32 * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, 64, s->stream));
+    CU(cudaMemsetAsync(cnt.p, 0, B2_CNT_TOTAL * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, 64, s->stream));
     k_stage_pack<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, h.p, rng.p, df.p, st.p, list.p);
     const unsigned long long n_list = (unsigned long long) n;        // n CONTINUE lanes, no TERMINATE lanes
     H2D(cnt.p + CNT_LIST, &n_list, 8);
     Queues q{};
     q.ray_o = o.p; q.ray_d = d.p; q.hit = h.p; q.hit_inst = s->d.n_instances ? di.p : nullptr; q.tp = tp.p; q.res = res.p; q.st = st.p; q.pixel = pix.p;
     q.pos = (s->features & F_WIDE) ? pos.p : nullptr;
-    q.sh_o = so.p; q.sh_d = sd.p; q.sh_c = sc4.p; q.list[0] = list.p; q.list[1] = list.p + cap; q.cnt = cnt.p; q.work = cnt.p + 16; q.stats = stats.p;
+    q.sh_o = so.p; q.sh_d = sd.p; q.sh_c = sc4.p; q.list[0] = list.p; q.list[1] = list.p + cap; q.cnt = cnt.p; q.work = cnt.p + B2_CNT_WORK; q.stats = stats.p;
     q.film = nullptr; q.n_slots = (uint32_t) cap; q.max_depth = rp->max_depth; q.rr_depth = rp->rr_depth; q.base_seed = rp->seed;
     q.n_items_pass = 1; q.n_passes = 1; q.spp_pass = 1; q.block_size = rp->block_size ? rp->block_size : 32; q.n_blocks_total = 1; q.total_items = 0;
     const ShadeFn fn = shade_variant(s->features);

@@ -73,11 +73,16 @@ struct Queues {
     uint32_t sh_sub, sh_cap;
 };
 
-// q.cnt words of one lane set (B2_CNT_WORDS each)
-enum { CNT_SHADOW = 0 /* and 1: double buffered by iteration parity */, CNT_ALIVE = 2, CNT_FETCH = 3 /* k_trace_inst's ray counter */,
-       CNT_LIST = 4 /* and 6: 64-bit (n_continue | n_terminate << 32) per iteration parity */,
-       CNT_RESUME = 8 /* and 9: suspended lanes per iteration parity (k_trace_resume) */ };
-#define B2_CNT_WORDS 12
+// q.cnt words of one lane set (B2_CNT_WORDS each). Every counter that takes atomics from a whole launch has a 128-byte line of
+// its own: the two lane sets' kernels run side by side, and atomics on neighbouring words serialise in one L2 sector.
+enum { CNT_SHADOW = 0 /* and 1: per iteration parity — only when the shadow queue is not split (Queues::sh_sub == 0) */,
+       CNT_ALIVE = 32, CNT_FETCH = 64 /* k_trace_inst's ray counter */,
+       CNT_LIST = 96 /* 64-bit (n_continue | n_terminate << 32) per iteration parity: words 96 and 128 (CNT_LIST_P) */,
+       CNT_RESUME = 160 /* and 161: suspended lanes per iteration parity (k_trace_resume) */ };
+#define CNT_LIST_P(parity) (CNT_LIST + 32 * (parity))
+#define B2_CNT_WORDS 192
+#define B2_CNT_WORK (2 * B2_CNT_WORDS)      /* the work-item counter shared by the lane sets */
+#define B2_CNT_TOTAL (B2_CNT_WORK + 32)
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES = 4, ST_TRIS = 5 };
 
 // st.w layout
@@ -133,7 +138,7 @@ B2_D void sh_begin_trace(const Queues &q, int parity, uint32_t n_shadow) {
     if (q.sh_sub) { if (threadIdx.x < q.sh_sub) *sh_counter(q, parity, threadIdx.x) = 0; }
     else if (threadIdx.x == 0) q.cnt[CNT_SHADOW + parity] = 0;
     if (threadIdx.x == 0) {
-        *(unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)) = 0ull;   // consumed by the previous k_shade
+        *(unsigned long long *) (q.cnt + CNT_LIST_P(parity ^ 1)) = 0ull;   // consumed by the previous k_shade
         if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
     }
 }
@@ -754,7 +759,7 @@ B2_D void list_append(const Queues &q, int parity, uint32_t lane, bool cont, boo
     const int leader = __ffs(mask) - 1;
     unsigned long long base = 0;
     if ((int) lane_id() == leader)
-        base = atomicAdd((unsigned long long *) (q.cnt + CNT_LIST + 2 * parity), (unsigned long long) __popc(mc) | ((unsigned long long) __popc(mx) << 32));
+        base = atomicAdd((unsigned long long *) (q.cnt + CNT_LIST_P(parity)), (unsigned long long) __popc(mc) | ((unsigned long long) __popc(mx) << 32));
     base = __shfl_sync(mask, base, leader);
     const uint32_t below = (1u << lane_id()) - 1u;
     if (cont) q.list[parity][(uint32_t) base + __popc(mc & below)] = lane;
@@ -1588,7 +1593,7 @@ B2_D void shade_continue(const DScene &sc, const Tables &tb, const Queues &q, in
     const uint32_t pk_mask = __ballot_sync(0xffffffffu, park);
     if (pk_mask) {
         unsigned long long pb = 0;
-        if (lane_id() == 0) pb = atomicAdd((unsigned long long *) (q.cnt + CNT_LIST + 2 * (parity ^ 1)), (unsigned long long) __popc(pk_mask) << 32);
+        if (lane_id() == 0) pb = atomicAdd((unsigned long long *) (q.cnt + CNT_LIST_P(parity ^ 1)), (unsigned long long) __popc(pk_mask) << 32);
         pb = __shfl_sync(0xffffffffu, pb, 0);
         if (park) q.list[parity ^ 1][q.n_slots - 1u - ((uint32_t) (pb >> 32) + __popc(pk_mask & ((1u << lane_id()) - 1u)))] = lane;
     }
@@ -1728,7 +1733,7 @@ __global__ void __launch_bounds__(B2_SHADE_THREADS, B2_SHADE_MINBLOCKS) k_shade(
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     const Tables tb = stage_shade_tables(sc, smem_raw);
     // the two dense lists written by k_trace (+ the lanes parked by the previous k_shade)
-    const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST + 2 * parity);
+    const unsigned long long n_list = *(const unsigned long long *) (q.cnt + CNT_LIST_P(parity));
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         q.cnt[CNT_FETCH] = 0;                                             // ray counter of the next k_trace_inst
         if (q.tsave) q.cnt[CNT_RESUME + (parity ^ 1)] = 0;                // consumed by the k_trace_resume before this launch
