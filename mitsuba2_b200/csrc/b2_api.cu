@@ -785,7 +785,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     uint64_t total64 = (uint64_t) n_items_pass * n_passes;
     bool wide = film.filter_radius > 0.5f + 1500.0f * 5.9604644775390625e-08f;
     CU(s->film.alloc((size_t) W * H * 5));
-    CU(s->stats.alloc(8));
+    CU(s->stats.alloc(B2_STAT_COPIES * B2_STAT_STRIDE));
     if (total64 == 0) {
         // a rank that owns no spiral block (world_size > number of blocks): empty film, nothing to launch
         CU(cudaMemsetAsync(s->film.p, 0, (size_t) W * H * 5 * sizeof(float), stream));
@@ -921,7 +921,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     if (wide) CU(cudaMemsetAsync(s->film_wide.p, 0, (size_t) W * H * 8 * sizeof(float), stream));
     CU(cudaMemsetAsync(s->cnt.p, 0, B2_CNT_TOTAL * sizeof(uint32_t), stream));
     CU(cudaMemsetAsync(s->sh_cnt.p, 0, 2 * 2 * B2_SH_MAXSUB * 32 * sizeof(uint32_t), stream));
-    CU(cudaMemsetAsync(s->stats.p, 0, 8 * sizeof(unsigned long long), stream));
+    CU(cudaMemsetAsync(s->stats.p, 0, B2_STAT_COPIES * B2_STAT_STRIDE * sizeof(unsigned long long), stream));
     const int threads = 256;
     // CTA sizes of the two stage kernels (the kernels stride over the lane slots by warps, so any multiple of 32 is correct;
     // grids keep the same number of warps). Every CTA stages its tables into shared memory first: scenes that stage only a few
@@ -972,7 +972,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
             s->h_snap = nullptr; s->h_snap_floats = 0;
             CU(cudaMallocHost(&s->h_snap, film_floats * sizeof(float))); s->h_snap_floats = film_floats;
         }
-        if (!s->h_snap_samples) CU(cudaMallocHost(&s->h_snap_samples, sizeof(unsigned long long)));
+        if (!s->h_snap_samples) CU(cudaMallocHost(&s->h_snap_samples, B2_STAT_COPIES * B2_STAT_STRIDE * sizeof(unsigned long long)));
         if (wide) CU(s->snap_film.alloc(film_floats));
         ev_film = pool.make(false); ev_snap = pool.make(false);
         if (!ev_film || !ev_snap) return fail(B2_ERR_CUDA, "cudaEventCreate failed");
@@ -1018,7 +1018,9 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         if (s->progress_fn) {
             if (snap_in_flight && cudaEventQuery(ev_snap) == cudaSuccess) {
                 snap_in_flight = false;
-                if (s->progress_fn(s->progress_user, s->h_snap, *s->h_snap_samples, (uint64_t) W * H * rp->spp / (uint64_t) world)) s->cancel.store(1);
+                unsigned long long n_snap = 0;                              // (the counters are kept in B2_STAT_COPIES copies)
+                for (int c = 0; c < B2_STAT_COPIES; ++c) n_snap += s->h_snap_samples[c * B2_STAT_STRIDE + ST_SAMPLES];
+                if (s->progress_fn(s->progress_user, s->h_snap, n_snap, (uint64_t) W * H * rp->spp / (uint64_t) world)) s->cancel.store(1);
             }
             auto now = std::chrono::steady_clock::now();
             if (!snap_in_flight && !done && std::chrono::duration<double, std::milli>(now - snap_last).count() >= (double) s->progress_ms) {
@@ -1031,7 +1033,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
                     src = s->snap_film.p;
                 }
                 CU(cudaMemcpyAsync(s->h_snap, src, film_floats * sizeof(float), cudaMemcpyDeviceToHost, s->stream_snap));
-                CU(cudaMemcpyAsync(s->h_snap_samples, s->stats.p + ST_SAMPLES, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream_snap));
+                CU(cudaMemcpyAsync(s->h_snap_samples, s->stats.p, B2_STAT_COPIES * B2_STAT_STRIDE * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s->stream_snap));
                 CU(cudaEventRecord(ev_snap, s->stream_snap));
                 snap_in_flight = true;
             }
@@ -1047,9 +1049,10 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
     CU(cudaEventSynchronize(ev1));
     float ms = 0.f; CU(cudaEventElapsedTime(&ms, ev0, ev1));
     if (stats) {
-        unsigned long long h[8];
-        CU(cudaMemcpyAsync(h, s->stats.p, sizeof h, cudaMemcpyDeviceToHost, stream));
+        unsigned long long hc[B2_STAT_COPIES * B2_STAT_STRIDE], h[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+        CU(cudaMemcpyAsync(hc, s->stats.p, sizeof hc, cudaMemcpyDeviceToHost, stream));
         CU(cudaStreamSynchronize(stream));
+        for (int c = 0; c < B2_STAT_COPIES; ++c) for (int k = 0; k < 8; ++k) h[k] += hc[c * B2_STAT_STRIDE + k];
         std::memset(stats, 0, sizeof *stats);
         stats->n_samples = h[ST_SAMPLES]; stats->n_segments = h[ST_SEGMENTS]; stats->n_shadow_rays = h[ST_SHADOW];
         stats->n_invalid = h[ST_INVALID]; stats->n_iterations = iterations; stats->n_launches = launches;
@@ -1215,11 +1218,11 @@ int b2_stage_shade(B2Scene *s, const B2RenderParams *rp, uint32_t n, float *ray_
     DBuf<float4> o, d, h, tp, res, so, sd, sc4; DBuf<uint4> st; DBuf<uint32_t> list, cnt, df, pix; DBuf<int32_t> di; DBuf<uint64_t> rng;
     DBuf<unsigned long long> stats; DBuf<float2> pos;
     CU(o.alloc(cap)); CU(d.alloc(cap)); CU(h.alloc(cap)); CU(tp.alloc(cap)); CU(res.alloc(cap)); CU(so.alloc(cap)); CU(sd.alloc(cap)); CU(sc4.alloc(cap));
-    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(B2_CNT_TOTAL)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(8)); CU(pos.alloc(cap));
+    CU(st.alloc(cap)); CU(list.alloc(2 * cap)); CU(cnt.alloc(B2_CNT_TOTAL)); CU(df.alloc(cap)); CU(pix.alloc(cap)); CU(rng.alloc(cap)); CU(stats.alloc(B2_STAT_COPIES * B2_STAT_STRIDE)); CU(pos.alloc(cap));
     H2D(o.p, ray_o, N * 16); H2D(d.p, ray_d, N * 16); H2D(h.p, hit, N * 16); H2D(tp.p, throughput_eta, N * 16); H2D(res.p, result_pdf, N * 16);
     H2D(rng.p, rng_state, N * 8); H2D(df.p, depth_flags, N * 4);
     if (s->d.n_instances) { CU(di.alloc(cap)); H2D(di.p, inst, N * 4); }
-    CU(cudaMemsetAsync(cnt.p, 0, B2_CNT_TOTAL * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, 64, s->stream));
+    CU(cudaMemsetAsync(cnt.p, 0, B2_CNT_TOTAL * 4, s->stream)); CU(cudaMemsetAsync(stats.p, 0, B2_STAT_COPIES * B2_STAT_STRIDE * 8, s->stream));
     k_stage_pack<<<(unsigned) ((N + 255) / 256), 256, 0, s->stream>>>(s->d, n, h.p, rng.p, df.p, st.p, list.p);
     const unsigned long long n_list = (unsigned long long) n;        // n CONTINUE lanes, no TERMINATE lanes
     H2D(cnt.p + CNT_LIST, &n_list, 8);

@@ -84,6 +84,10 @@ enum { CNT_SHADOW = 0 /* and 1: per iteration parity — only when the shadow qu
 #define B2_CNT_WORK (2 * B2_CNT_WORDS)      /* the work-item counter shared by the lane sets */
 #define B2_CNT_TOTAL (B2_CNT_WORK + 32)
 enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES = 4, ST_TRIS = 5 };
+// q.stats = B2_STAT_COPIES copies of the ST_* block, one 128-byte line each; a CTA adds to copy blockIdx.x % B2_STAT_COPIES and the
+// host sums the copies (every warp of every launch books its counts: on one line those reductions queue up in one L2 sector)
+#define B2_STAT_COPIES 8
+#define B2_STAT_STRIDE 16       /* unsigned long long words per copy */
 
 // st.w layout
 #define STW_DEPTH(w)     ((w) & 0xffu)
@@ -98,6 +102,9 @@ enum { ST_SAMPLES = 0, ST_SEGMENTS = 1, ST_SHADOW = 2, ST_INVALID = 3, ST_NODES 
 #define STW_LEFT(w)      ((w) >> 16)
 
 B2_D uint32_t lane_id() { return threadIdx.x & 31; }
+B2_D void stat_add(const Queues &q, int which, unsigned long long v) {
+    atomicAdd(q.stats + (blockIdx.x % B2_STAT_COPIES) * B2_STAT_STRIDE + which, v);
+}
 
 // warp-aggregated append: one atomic per warp, contiguous slots for the set lanes.
 // Must be called by all 32 lanes of the warp.
@@ -139,7 +146,7 @@ B2_D void sh_begin_trace(const Queues &q, int parity, uint32_t n_shadow) {
     else if (threadIdx.x == 0) q.cnt[CNT_SHADOW + parity] = 0;
     if (threadIdx.x == 0) {
         *(unsigned long long *) (q.cnt + CNT_LIST_P(parity ^ 1)) = 0ull;   // consumed by the previous k_shade
-        if (!q.direct_e) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_shadow);
+        if (!q.direct_e) stat_add(q, ST_SHADOW, (unsigned long long) n_shadow);
     }
 }
 
@@ -867,11 +874,11 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
         }
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
-    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_dsh); }
+    if (lane_id() == 0 && n_seg) stat_add(q, ST_SEGMENTS, (unsigned long long) n_seg);
+    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) stat_add(q, ST_SHADOW, (unsigned long long) n_dsh); }
     if constexpr (COUNT) {
         uint32_t a = __reduce_add_sync(0xffffffffu, counters[0]), b = __reduce_add_sync(0xffffffffu, counters[1]);
-        if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
+        if (lane_id() == 0) { stat_add(q, ST_NODES, (unsigned long long) a); stat_add(q, ST_TRIS, (unsigned long long) b); }
     }
 }
 
@@ -992,11 +999,11 @@ __global__ void __launch_bounds__(256, B2_TRACE_MINBLOCKS) k_trace_resume(DScene
         }
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
-    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_dsh); }
+    if (lane_id() == 0 && n_seg) stat_add(q, ST_SEGMENTS, (unsigned long long) n_seg);
+    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) stat_add(q, ST_SHADOW, (unsigned long long) n_dsh); }
     if constexpr (COUNT) {
         uint32_t a = __reduce_add_sync(0xffffffffu, counters[0]), b = __reduce_add_sync(0xffffffffu, counters[1]);
-        if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
+        if (lane_id() == 0) { stat_add(q, ST_NODES, (unsigned long long) a); stat_add(q, ST_TRIS, (unsigned long long) b); }
     }
 }
 
@@ -1179,11 +1186,11 @@ __global__ void __launch_bounds__(256, B2_INST_MINBLOCKS) k_trace_inst(DScene sc
         }
     }
     n_seg = __reduce_add_sync(0xffffffffu, n_seg);
-    if (lane_id() == 0 && n_seg) atomicAdd(&q.stats[ST_SEGMENTS], (unsigned long long) n_seg);
-    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) atomicAdd(&q.stats[ST_SHADOW], (unsigned long long) n_dsh); }
+    if (lane_id() == 0 && n_seg) stat_add(q, ST_SEGMENTS, (unsigned long long) n_seg);
+    if (q.direct_e) { n_dsh = __reduce_add_sync(0xffffffffu, n_dsh); if (lane_id() == 0 && n_dsh) stat_add(q, ST_SHADOW, (unsigned long long) n_dsh); }
     if constexpr (COUNT) {
         uint32_t a = __reduce_add_sync(0xffffffffu, tr.n_nodes), b = __reduce_add_sync(0xffffffffu, tr.n_tris);
-        if (lane_id() == 0) { atomicAdd(&q.stats[ST_NODES], (unsigned long long) a); atomicAdd(&q.stats[ST_TRIS], (unsigned long long) b); }
+        if (lane_id() == 0) { stat_add(q, ST_NODES, (unsigned long long) a); stat_add(q, ST_TRIS, (unsigned long long) b); }
     }
 }
 
@@ -1755,8 +1762,8 @@ __global__ void __launch_bounds__(B2_SHADE_THREADS, B2_SHADE_MINBLOCKS) k_shade(
     }
     n_put = __reduce_add_sync(0xffffffffu, n_put); n_bad = __reduce_add_sync(0xffffffffu, n_bad);
     if (lane_id() == 0) {
-        if (n_put) atomicAdd(&q.stats[ST_SAMPLES], (unsigned long long) n_put);
-        if (n_bad) atomicAdd(&q.stats[ST_INVALID], (unsigned long long) n_bad);
+        if (n_put) stat_add(q, ST_SAMPLES, (unsigned long long) n_put);
+        if (n_bad) stat_add(q, ST_INVALID, (unsigned long long) n_bad);
     }
 }
 
