@@ -797,8 +797,8 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
             bool has = false, cont = false, term = false;
             float4 rd = make_float4(0.f, 0.f, 0.f, -1.f), ro = rd;
             uint32_t stw = 0;
-            if (i < q.n_slots) { rd = q.ray_d[i]; has = rd.w >= 0.f; }      // (retired / parked lanes carry maxt < 0)
-            if (has) { ro = q.ray_o[i]; stw = q.st[i].w; }
+            // (all three loads are issued together: one L2 round trip per chunk instead of two)
+            if (i < q.n_slots) { rd = q.ray_d[i]; ro = q.ray_o[i]; stw = q.st[i].w; has = rd.w >= 0.f; }      // (retired / parked lanes carry maxt < 0)
             Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
             Hit h; flat_closest_hit_coop<COUNT>(sc, sm, has, ray, h, coop, counters);
             if (has) {
@@ -839,17 +839,17 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
             uint32_t j = base + lane_id();
             bool valid = j < n_entries;
             if (valid && !q.direct_e) j = sh_index(q, parity ^ 1, j);
-            float4 rd = make_float4(0.f, 0.f, 0.f, -1.f), ro = rd;
-            if (valid) { rd = q.sh_d[j]; valid = !(q.direct_e && !(rd.w >= 0.f)); }
-            if (valid) ro = q.sh_o[j];
+            // the entry (ray + contribution) and the result word it may add to are fetched up front: their two dependent L2
+            // round trips overlap the leaf scan instead of ending the chunk
+            float4 rd = make_float4(0.f, 0.f, 0.f, -1.f), ro = rd, c = rd, r = rd;
+            if (valid) { rd = q.sh_d[j]; ro = q.sh_o[j]; if (!q.direct_e) c = q.sh_c[j]; valid = !(q.direct_e && !(rd.w >= 0.f)); }
+            const uint32_t lw = __float_as_uint(c.w);
+            if (valid && !q.direct_e) r = q.res[lw];
             Ray ray; ray.o = v3(ro); ray.d = v3(rd); ray.mint = ro.w; ray.maxt = rd.w;
             const bool occluded = flat_any_hit_coop<COUNT>(sc, sm, valid, ray, coop, counters);
             if (!valid) continue;
             if (q.direct_e) { q.sh_c[j].w = occluded ? 0.f : 1.f; ++n_dsh; }
             else if (!occluded) {
-                float4 c = q.sh_c[j];
-                const uint32_t lw = __float_as_uint(c.w);
-                float4 r = q.res[lw];
                 r.x += c.x; r.y += c.y; r.z += c.z;
                 q.res[lw] = r;
             }
