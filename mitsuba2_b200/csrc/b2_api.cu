@@ -884,11 +884,7 @@ int b2_render_device(B2Scene *s, const B2RenderParams *rp, float **d_xyzaw, B2St
         // the shadow queue of a lane set: 8 sub-queues with their own counters (one 128-byte line each) once the wavefront is
         // wide enough for the single counter to be a hot spot (b2_kernels.cuh: sh_counter()); the direct integrator's entries
         // are addressed by lane
-#ifdef B2_NO_SH_SUB             /* (A/B builds only) */
-        const uint32_t sh_sub = 0u;
-#else
         const uint32_t sh_sub = (!direct && set_slots >= 8192u) ? 8u : 0u;
-#endif
         const size_t so = direct ? o * (size_t) dE : o + (size_t) k * B2_SH_MAXSUB * 32u;
         q.sh_o = s->sh_o.p + so; q.sh_d = s->sh_d.p + so; q.sh_c = s->sh_c.p + so;
         q.sh_sub = sh_sub; q.sh_cnt = s->sh_cnt.p + (size_t) k * 2 * B2_SH_MAXSUB * 32;

@@ -342,25 +342,6 @@ struct Trav {
     // SHP: the scene has analytic shapes (compile-time, so that plain triangle scenes do not carry the sphere / rectangle code)
     template <bool ANY, bool SHP, bool COUNT = false>
     B2_D void run(const DScene &sc, const SmemScene &sm, int *stack, bool can_yield) {
-#ifdef B2_SPECULATIVE
-        // speculative while-while (Aila & Laine 2009): the first leaf a lane finds is POSTPONED and the lane keeps descending
-        // while other lanes of the warp are still looking for theirs, so that the leaf phase starts with (nearly) every lane
-        // holding work. A postponed leaf is tested against a tmax that may since have shrunk: fewer hits, same result.
-        int postponed = 0;
-        while (cur != B2_TRAV_DONE || postponed != 0) {
-            while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) {
-                node_step<COUNT>(sc, sm, stack);
-                if (cur < 0 && postponed == 0) { postponed = cur; cur = stack[--sp]; }
-                if (!__any_sync(__activemask(), postponed == 0)) break;
-            }
-            while (postponed != 0) {
-                if (leaf_step<ANY, SHP, COUNT>(sc, sm, postponed)) { cur = B2_TRAV_DONE; return; }
-                postponed = 0;
-                if (cur < 0) { postponed = cur; cur = stack[--sp]; }
-            }
-            if (can_yield && __popc(__activemask()) < B2_REFILL_THRESHOLD) return;
-        }
-#else
         while (cur != B2_TRAV_DONE) {
             while ((uint32_t) cur < (uint32_t) B2_TRAV_DONE) node_step<COUNT>(sc, sm, stack);
             while (cur < 0) {
@@ -369,7 +350,6 @@ struct Trav {
             }
             if (can_yield && __popc(__activemask()) < B2_REFILL_THRESHOLD) return;
         }
-#endif
     }
 };
 
@@ -785,12 +765,9 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
     uint32_t n_seg = 0;
     uint32_t counters[2] = { 0u, 0u };
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-#ifndef B2_NO_COOP_ANYHIT
     // the warp's candidate list / keys of the cooperative tests on the flat leaf list (behind the staged scene)
     unsigned char *coop = smem_raw + ((16u + sc.smem_nodes * 128u + (sc.smem_tris ? sc.n_tris * 48u : 0u) + sc.n_flat_leaves * 32u + 15u) & ~15u)
                           + (threadIdx.x >> 5) * B2_COOP_BYTES_PER_WARP;
-#endif
-#ifndef B2_NO_COOP_CLOSEST      /* (A/B builds only) */
     if (!INST && sc.n_flat_leaves) {
         for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
             const uint32_t i = base + lane_id();
@@ -810,7 +787,6 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
             list_append(q, parity, i, cont, term, 0xffffffffu);
         }
     } else
-#endif
     for (uint32_t base = warp * 32; base < q.n_slots; base += n_warps * 32) {
         const uint32_t i = base + lane_id();
         bool cont = false, term = false;
@@ -832,7 +808,6 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
     }
     uint32_t n_dsh = 0;
     const uint32_t n_entries = q.direct_e ? q.n_slots * q.direct_e : n_shadow;      // (direct integrator: E entry slots per lane)
-#ifndef B2_NO_COOP_ANYHIT      /* (A/B builds only) */
     if (!INST && sc.n_flat_leaves) {
         // flat scenes: 32 entries per warp, tested cooperatively (flat_any_hit_coop); same entry -> thread mapping as below
         for (uint32_t base = warp * 32; base < n_entries; base += n_warps * 32) {
@@ -855,7 +830,6 @@ __global__ void __launch_bounds__(256, INST ? 3 : B2_TRACE_MINBLOCKS) k_trace(DS
             }
         }
     } else
-#endif
     for (uint32_t jd = blockIdx.x * blockDim.x + threadIdx.x; jd < n_entries; jd += gridDim.x * blockDim.x) {
         const uint32_t j = q.direct_e ? jd : sh_index(q, parity ^ 1, jd);
         float4 rd = q.sh_d[j];
