@@ -41,6 +41,23 @@ def test_struct_layouts_match_the_header(tmp_path):
         assert int(out[s]) == C.sizeof(getattr(abi, s)), (s, out[s], C.sizeof(getattr(abi, s)))
 
 
+def test_flag_constants_match_the_header(tmp_path):
+    """abi.FLAG_* / flag_yield_threshold / flag_blocks mirror the B2_FLAG_* macros of include/b2pt.h (evaluated by the C compiler)."""
+    names = ["B2_FLAG_STAGE_TIMING", "B2_FLAG_SINGLE_SET", "B2_FLAG_COUNT_BVH", "B2_FLAG_PERSISTENT_TRACE", "B2_FLAG_RESUME_TRACE",
+             "B2_FLAG_YIELD_THRESHOLD(20)", "B2_FLAG_TRACE_BLOCK(2)", "B2_FLAG_SHADE_BLOCK(3)"]
+    src = tmp_path / "fl.c"
+    src.write_text('#include "b2pt.h"\n#include <stdio.h>\nint main(void) {\n' +
+                   "".join(f'  printf("%u\\n", (unsigned) ({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "fl"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    want = [abi.FLAG_STAGE_TIMING, abi.FLAG_SINGLE_SET, abi.FLAG_COUNT_BVH, abi.FLAG_PERSISTENT_TRACE, abi.FLAG_RESUME_TRACE,
+            abi.flag_yield_threshold(20), abi.flag_blocks(trace_sel=2), abi.flag_blocks(shade_sel=3)]
+    assert got == want, (got, want)
+    # the fields do not overlap
+    assert abi.flag_yield_threshold(31) & (abi.flag_blocks(3, 3) | 0xff) == 0 and abi.flag_blocks(3, 0) & abi.flag_blocks(0, 3) == 0
+
+
 def test_host_helpers_match_oracle(oracle):
     H, O = api.Host(), oracle.OracleHost()
     assert _bytes(H.look_at((278, 273, -800), (278, 273, -799), (0, 1, 0))) == _bytes(O.look_at((278, 273, -800), (278, 273, -799), (0, 1, 0)))
