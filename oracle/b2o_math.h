@@ -35,8 +35,32 @@ typedef struct { float x, y, z; } v3;
 #define B2O_ONE_MINUS_EPS 0.999999940395355225f                   /* math::OneMinusEpsilon<float>, math.h:31-33 */
 
 static inline float b2o_fma(float a, float b, float c) { return __builtin_fmaf(a, b, c); }
+#if defined(B2O_REF_RCP) && defined(__AVX512F__) && defined(__FMA__)
+/* ANALYSIS build only (oracle/Makefile: libb2oracle_refrcp.so; scripts/refrcp_analysis.py; never what the CUDA path is compared
+ * with): rcp / rsqrt by the very instruction sequences the reference executes on an AVX-512 host — vrcp14ss / vrsqrt14ss, one
+ * Newton-Raphson step, vfixupimmss (ext/enoki/include/enoki/array_fallbacks.h:32-58, 112-140) — to MEASURE how much of the
+ * oracle-vs-reference noise floor (which closest-hit wins between coplanar triangles) comes from the last-ulp
+ * difference between these and the correctly rounded 1/x, 1/sqrt(x) that the oracle and the CUDA kernels use. */
+#include <immintrin.h>
+static inline float b2o_rcp(float x) {
+    __m128 v = _mm_set_ss(x), r = _mm_rcp14_ss(v, v);
+    __m128 t0 = _mm_add_ss(r, r), t1 = _mm_mul_ss(r, v);
+    r = _mm_fnmadd_ss(r, t1, t0);
+    r = _mm_fixupimm_ss(r, v, _mm_set1_epi32(0x0087A622), 0);
+    return _mm_cvtss_f32(r);
+}
+static inline float b2o_rsqrt(float x) {
+    __m128 v = _mm_set_ss(x), r = _mm_rsqrt14_ss(v, v);
+    const __m128 c0 = _mm_set_ss(0.5f), c1 = _mm_set_ss(3.0f);
+    __m128 t0 = _mm_mul_ss(r, c0), t1 = _mm_mul_ss(r, v);
+    r = _mm_mul_ss(_mm_fnmadd_ss(t1, r, c1), t0);
+    r = _mm_fixupimm_ss(r, v, _mm_set1_epi32(0x0383A622), 0);
+    return _mm_cvtss_f32(r);
+}
+#else
 static inline float b2o_rcp(float x) { return 1.0f / x; }
 static inline float b2o_rsqrt(float x) { return 1.0f / sqrtf(x); }
+#endif
 static inline float b2o_sqr(float x) { return x * x; }
 static inline float b2o_safe_sqrt(float x) { return sqrtf(x > 0.0f ? x : 0.0f); } /* sqrt(max(x,0)) */
 static inline float b2o_min(float a, float b) { return a < b ? a : b; }   /* minss semantics */

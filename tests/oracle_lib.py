@@ -23,6 +23,7 @@ def lib():
         src = os.path.join(ROOT, "oracle", "b2o.c")
         if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
             build()
+        path = os.environ.get("B2O_LIB", path)      # (scripts/refrcp_analysis.py: the analysis build of the oracle)
         L = C.CDLL(path)
         L.b2o_parse_fov.restype = C.c_float
         L.b2o_parse_fov.argtypes = [C.c_float, C.c_char_p, C.c_int, C.c_int]
