@@ -128,7 +128,13 @@ def ncu_traffic(workload, kernel):
         for r in rows[1:]:
             d = dict(zip(hdr, r))
             if d["kernel"].startswith(kernel):
+                def f(k):
+                    try:
+                        return float(d[k])
+                    except Exception:
+                        return None
                 return {"bytes": float(d["dram_read_bytes"]) + float(d["dram_write_bytes"]), "duration_us": float(d["duration_us"]),
+                        "issue_active_pct": f("issue_active_pct"), "lanes_per_warp_instr": f("threads_per_warp_instr"),
                         "source": os.path.relpath(path, ROOT)}
     except Exception:
         pass
@@ -390,7 +396,11 @@ def main_b2pt(a, rank, world, local_rank):
             tr = ncu_traffic(a.workload, "k_" + k)
             stages[k] = {"kernel": "k_" + k, "ms": t, "units": stage_units[k], "bytes": nbytes, "gbs": gbs, "frac": gbs / peak if gbs else None,
                          "launches": n_it, "avg_launch_us": t / max(n_it, 1) * 1e3, "bytes_per_launch": nbytes / max(n_it, 1),
-                         "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None}
+                         "traffic": tr["bytes"] if tr else None, "traffic_source": tr["source"] if tr else None,
+                         # from the same committed ncu capture: what bounds a kernel whose HBM fraction is low — the share of issue
+                         # slots it keeps busy and the lanes active per warp instruction (not measured in this run)
+                         "ncu_issue_active_pct": tr["issue_active_pct"] if tr else None,
+                         "ncu_lanes_per_warp_instr": tr["lanes_per_warp_instr"] if tr else None}
         dom = max(stages, key=lambda k: stages[k]["ms"])
         tot_bytes = sum(stage_bytes.values()); tot_t = sum(acc.values())
         roof = {"bound": "hbm", "kernel": "k_" + dom, "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
