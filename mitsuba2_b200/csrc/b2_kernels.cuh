@@ -492,9 +492,11 @@ B2_D bool flat_any_hit_coop(const DScene &sc, const SmemScene &sm, bool valid, c
 
 // Closest hit (Scene::ray_intersect_preliminary) of 32 rays on the flat leaf list, WARP-COOPERATIVE after the first leaf. Every
 // lane scans the leaf boxes and tests the leaf it enters first (dense: that leaf holds the hit for 93 % of the Cornell box's
-// rays). The leaves a lane still has to look into after that — entered before its hit distance — are few (2.2 per WARP on
-// average) but cost a whole triangle-test round each when every lane walks its own list (ncu: 3 more rounds at 4 / 32 lanes,
-// a quarter of the kernel's instructions). Here they go to the warp's shared-memory candidate list and are tested 32 at a time;
+// rays). The leaves a lane still has to look into after that — entered before its hit distance — are few (the per-lane loop
+// tested 2.2 of them per WARP on average) but cost a whole triangle-test round each when every lane walks its own list (ncu: 3
+// more rounds at 4 / 32 lanes, a quarter of the kernel's instructions). Here they go to the warp's shared-memory candidate list
+// (≈ 13 entries per warp: the list is built against the hit distance after the first leaf, without the per-lane loop's
+// progressive culling) and are tested 32 at a time, normally in ONE round;
 // a hit competes for its ray through a 64-bit (t, ~prim) key with atomicMin in shared memory — the lexicographic (t, -prim)
 // minimum of DESIGN.md 4, which does not depend on the order of the tests — and the winner leaves (u, v, slot) for the owner.
 // Same triangle test, same tie rule: the result is identical to traverse_flat<false>. Called by all 32 lanes of a warp.
