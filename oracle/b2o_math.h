@@ -97,7 +97,7 @@ static inline v3 v3_fnmadd(v3 a, float s, v3 c) {
  * Stands in for glibc sinf/cosf (which the reference reaches through enoki::sincos ->
  * std::sin/std::cos for scalars, ext/enoki/include/enoki/array_math.h). Accurate to <= 2 ulp
  * for |x| < 1e4; uses only fmaf, + and x, so the CUDA twin (csrc/b2_math.cuh) is bit-identical. */
-static inline void b2o_sincos(float x, float *s_out, float *c_out) {
+static inline void b2o_sincos_poly(float x, float *s_out, float *c_out) {
     float q = rintf(x * 0.63661977236758134308f);          /* x * 2/pi, round-half-even */
     int n = (int) q;
     float r = b2o_fma(q, -1.5707962512969970703125f, x);    /* pi/2 split in 3 parts */
@@ -120,7 +120,7 @@ static inline void b2o_sincos(float x, float *s_out, float *c_out) {
 }
 
 /* ---- expf / logf / erf / erfinv twins (polynomial; used by Beckmann + gaussian filter) ---- */
-static inline float b2o_exp(float x) {
+static inline float b2o_exp_poly(float x) {
     /* exp(x) = 2^k * exp(r), r in [-ln2/2, ln2/2] */
     if (x < -87.0f) return 0.0f;
     if (x > 88.0f) return INFINITY;
@@ -143,7 +143,7 @@ static inline float b2o_exp(float x) {
     return e;
 }
 
-static inline float b2o_log(float x) {
+static inline float b2o_log_poly(float x) {
     if (x < 0.0f) return NAN;
     if (x == 0.0f) return -INFINITY;
     if (!(x < INFINITY)) return x;
@@ -172,6 +172,18 @@ static inline float b2o_log(float x) {
     r = b2o_fma(fe, 0.693359375f, r);
     return r;
 }
+
+/* ANALYSIS build only (libb2oracle_reflibm.so, scripts/refrcp_analysis.py): glibc's sinf / cosf / expf / logf / atan2f — what the
+ * reference reaches for scalars — instead of the polynomial twins the oracle shares with the CUDA kernels. */
+#ifdef B2O_REF_LIBM
+static inline void b2o_sincos(float x, float *s_out, float *c_out) { *s_out = sinf(x); *c_out = cosf(x); }
+static inline float b2o_exp(float x) { return expf(x); }
+static inline float b2o_log(float x) { return logf(x); }
+#else
+static inline void b2o_sincos(float x, float *s_out, float *c_out) { b2o_sincos_poly(x, s_out, c_out); }
+static inline float b2o_exp(float x) { return b2o_exp_poly(x); }
+static inline float b2o_log(float x) { return b2o_log_poly(x); }
+#endif
 
 /* erf: Abramowitz-Stegun-free, uses the same structure as Enoki's erf
  * (ext/enoki/include/enoki/array_math.h erf(): polynomial for |x|<1, exp-based tail) */
@@ -256,7 +268,7 @@ static inline float b2o_asin(float x) {            /* |x| <= 1 */
     float r = 1.57079632679489661923f - 2.f * b2o_asin_poly(sqrtf(0.5f * (1.f - ax)));
     return b2o_mulsign(r, x);
 }
-static inline float b2o_atan2(float y, float x) {
+static inline float b2o_atan2_poly(float y, float x) {
     float ax = fabsf(x), ay = fabsf(y);
     float mx = b2o_max(ax, ay), mn = b2o_min(ax, ay);
     float a = mx == 0.f ? 0.f : mn / mx;           /* in [0, 1] */
@@ -272,5 +284,11 @@ static inline float b2o_atan2(float y, float x) {
     if (x < 0.f) r = 3.14159265358979323846f - r;
     return b2o_mulsign(r, y);
 }
+
+#ifdef B2O_REF_LIBM
+static inline float b2o_atan2(float y, float x) { return atan2f(y, x); }
+#else
+static inline float b2o_atan2(float y, float x) { return b2o_atan2_poly(y, x); }
+#endif
 
 #endif /* B2O_MATH_H */
