@@ -1758,10 +1758,12 @@ __global__ void k_develop(const float *xyzaw, float *rgb, int n) {
     if (i >= n) return;
     const float *p = xyzaw + 5 * (size_t) i;
     float iw = 1.f / p[4];
-    float r = 0.f, g = 0.f, b = 0.f;
-    r += 3.240479f * p[0]; r += -1.537150f * p[1]; r += -0.498535f * p[2];
-    g += -0.969256f * p[0]; g += 1.875991f * p[1]; g += 0.041556f * p[2];
-    b += 0.055648f * p[0]; b += -0.204043f * p[1]; b += 1.057311f * p[2];
+    // the blend of StructConverter's compiled loop: first product rounded, the others fused (struct.cpp:1380-1386: muls, then
+    // fmadd231 per further channel), then the multiplication by 1 / weight (struct.cpp:1398-1403)
+    float r = 3.240479f * p[0], g = -0.969256f * p[0], b = 0.055648f * p[0];
+    r = b2_fma(-1.537150f, p[1], r); r = b2_fma(-0.498535f, p[2], r);
+    g = b2_fma(1.875991f, p[1], g); g = b2_fma(0.041556f, p[2], g);
+    b = b2_fma(-0.204043f, p[1], b); b = b2_fma(1.057311f, p[2], b);
     rgb[3 * i] = r * iw; rgb[3 * i + 1] = g * iw; rgb[3 * i + 2] = b * iw;
 }
 

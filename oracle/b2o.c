@@ -2128,15 +2128,16 @@ B2O_API int b2o_render(const B2SceneDesc *d, const B2RenderParams *rp, float *xy
 }
 
 /* HDRFilm::bitmap(): XYZAW -> RGB — hdrfilm.cpp:251-322, bitmap.cpp:420-427, struct.cpp:1750-1812
-   (value = sum coef*channel in fp32, then * (1/W)) */
+   (value = blend of the channels in fp32 — first product rounded, the others fused —, then * (1/W)) */
 B2O_API int b2o_develop(const float *xyzaw, int n_pixels, float *rgb) {
     for (int i = 0; i < n_pixels; ++i) {
         const float *p = xyzaw + 5 * (size_t) i;
         float iw = 1.f / p[4];
-        float r = 0.f, g = 0.f, b = 0.f;
-        r += 3.240479f * p[0]; r += -1.537150f * p[1]; r += -0.498535f * p[2];
-        g += -0.969256f * p[0]; g += 1.875991f * p[1]; g += 0.041556f * p[2];
-        b += 0.055648f * p[0]; b += -0.204043f * p[1]; b += 1.057311f * p[2];
+        /* the compiled conversion loop: first product rounded, the others fused — struct.cpp:1380-1386 (muls, then fmadd231) */
+        float r = 3.240479f * p[0], g = -0.969256f * p[0], b = 0.055648f * p[0];
+        r = b2o_fma(-1.537150f, p[1], r); r = b2o_fma(-0.498535f, p[2], r);
+        g = b2o_fma(1.875991f, p[1], g); g = b2o_fma(0.041556f, p[2], g);
+        b = b2o_fma(-0.204043f, p[1], b); b = b2o_fma(1.057311f, p[2], b);
         rgb[3 * i] = r * iw; rgb[3 * i + 1] = g * iw; rgb[3 * i + 2] = b * iw;
     }
     return 0;
