@@ -411,7 +411,10 @@ def main_b2pt(a, rank, world, local_rank):
                 "stages": stages,
                 "all_stages_gbs": tot_bytes / (tot_t * 1e-3) / 1e9 if tot_t > 0 else None,
                 "all_stages_frac": tot_bytes / (tot_t * 1e-3) / 1e9 / peak if tot_t > 0 else None,
-                "step_ms_with_timing": ms_t}
+                "step_ms_with_timing": ms_t,
+                "note": ("the wavefront is sized to stay in L2 and the stage kernels are instruction- / latency-bound, not HBM-bound: the "
+                         "HBM fraction is what the contract asks for; stages[*].ncu_issue_active_pct / ncu_lanes_per_warp_instr (committed "
+                         "ncu capture) say how busy the issue slots are")}
         # BVH term: nodes fetched and primitives tested by all rays of one step, from the counting
         # instantiation of the traversal kernel (slower: its time is not used)
         if a.workload != "cbox" or a.bvh_counters:
